@@ -1,0 +1,188 @@
+/* hcs.h — C ABI of the B200-native hydroelastic contact-surface engine (libhcs_b200.so).
+ *
+ * Drop-in boundary for the hot path of ubi-agni/mujoco_contact_surfaces.  Every entry point
+ * cites the reference interface it replaces; paths are relative to the reference root,
+ *   CS   = mujoco_contact_surfaces,  SENS = mujoco_contact_surface_sensors,
+ *   plugin.cpp = CS/src/mujoco_contact_surfaces_plugin.cpp.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no C++/torch types; nothing throws across this boundary.
+ *   - every function returns HCS_OK (0) or a negative hcs_status; hcs_last_error() explains.
+ *   - a context is single-caller (the reference calls the path from the one MuJoCo physics thread,
+ *     plugin.cpp:88-95); it owns all device memory and one CUDA stream on one GPU.
+ *   - geoms are addressed by their CONFIGURATION INDEX: the order of hcs_add_* calls, which plays the
+ *     role of drake_id = GeometryId::get_new_id() (CS/include/mujoco_contact_surfaces/
+ *     mujoco_contact_surfaces_plugin.h:175): the geom with the smaller index is M, normals point
+ *     out of N into M (plugin.cpp:308-311, 346-348).
+ *   - per-step arrays are batched over n_envs independent environments (one env = one mjData of the
+ *     reference, plugin.cpp:88); env-major, geom index second:
+ *         xpos[env][geom][3]   = mjData.geom_xpos              (plugin.cpp:116-126)
+ *         xmat[env][geom][9]   = mjData.geom_xmat, row-major   (plugin.cpp:118-121)
+ *         vel [env][geom][6]   = mj_objectVelocity(m,d,mjOBJ_GEOM,id,res,0) = (omega, v)
+ *                                                              (plugin.cpp:107-114)
+ *   - units SI, world frame, fp64 geometry ("fp64 geometry mode" of the north star).
+ */
+#ifndef HCS_H_
+#define HCS_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct hcs_ctx hcs_ctx;
+
+typedef enum hcs_status {
+	HCS_OK             = 0,
+	HCS_E_INVALID      = -1, /* bad argument / call order */
+	HCS_E_UNSUPPORTED  = -2, /* geom type the reference does not support either (plugin.cpp:634-647) */
+	HCS_E_CUDA         = -3, /* CUDA runtime error (no CPU fallback exists) */
+	HCS_E_CAPACITY     = -4, /* candidate / triangle / bin capacity exceeded: results incomplete */
+	HCS_E_NOT_FINALIZED = -5
+} hcs_status;
+
+/* MuJoCo mjtGeom values used by plugin.cpp:633-808 */
+enum { HCS_GEOM_PLANE = 0, HCS_GEOM_HFIELD = 1, HCS_GEOM_SPHERE = 2, HCS_GEOM_CAPSULE = 3, HCS_GEOM_ELLIPSOID = 4,
+	   HCS_GEOM_CYLINDER = 5, HCS_GEOM_BOX = 6, HCS_GEOM_MESH = 7 };
+
+/* drake::geometry::HydroelasticContactRepresentation, parsed from the MuJoCo custom text
+ * "cs::HydroelasticContactRepresentation" (plugin.cpp:574-591) */
+enum { HCS_REP_POLYGON = 0, HCS_REP_TRIANGLE = 1 };
+
+/* FlatTactileSensor windowing (SENS/src/flat_tactile_sensor.cpp:140-168, DynamicFlatTactile.cfg) */
+enum { HCS_WINDOW_NONE = 0, HCS_WINDOW_GAUSS = 1, HCS_WINDOW_TUKEY = 2, HCS_WINDOW_SQUARE = 3 };
+
+typedef struct hcs_config {
+	int device;                   /* CUDA device ordinal */
+	int n_envs;                   /* independent environments resident on this GPU */
+	int representation;           /* HCS_REP_* */
+	int apply_contact_forces;     /* cs::ApplyContactSurfaceForces (plugin.cpp:603-611) */
+	int max_candidates_per_slice; /* 0 = automatic; broadphase slab capacity */
+	int max_faces;                /* >0: keep a per-face dump (PointCollision views) of that capacity */
+	int max_tactile_triangles;    /* 0 = automatic; triangle pool for the tactile stage */
+	int max_triangles_per_taxel;  /* 0 = automatic (64) */
+	void *stream;                 /* cudaStream_t to run on, NULL = context-owned stream */
+} hcs_config;
+
+/* result of one geom pair in one env: what passiveCallback applies (plugin.cpp:411-483), reduced.
+ * F acts on geom gM at the world origin-referenced torque tau (sum of p x f); -F, -tau act on gN. */
+typedef struct hcs_pair_result {
+	double F[3];
+	double tau[3];
+	double centroid[3]; /* area-weighted centroid of the contact surface (ContactSurface::centroid) */
+	double area;        /* ContactSurface::total_area */
+	int32_t gM, gN;     /* configuration indices, gM < gN */
+	int32_t n_polygons; /* contact polygons emitted (= |emitted candidate set|) */
+	int32_t n_faces;    /* faces of the surface (kPolygon: = n_polygons; kTriangle: fan triangles) */
+	int32_t n_points;   /* PointCollisions that pass plugin.cpp:345 and :362 */
+	int32_t n_candidates; /* narrowphase pair-evals spent on this pair */
+} hcs_pair_result;
+
+/* one PointCollision (CS/include/mujoco_contact_surfaces/common_types.h:48-56) plus provenance */
+typedef struct hcs_face {
+	double p[3], n[3];
+	double fn0, stiffness, damping;
+	double f[3];              /* force applied to gM at p (plugin.cpp:473-475) */
+	int32_t env, pair;
+	int32_t elemM, elemN;     /* mesh elements that produced the polygon */
+	int32_t nverts, face;     /* polygon vertex count; face index inside the polygon's fan */
+} hcs_face;
+
+/* --- lifetime ------------------------------------------------------------------------------- */
+/* replaces MujocoContactSurfacesPlugin::load() up to parseMujocoCustomFields (plugin.cpp:208-222) */
+int hcs_create(const hcs_config *cfg, hcs_ctx **out);
+/* replaces ~MujocoContactSurfacesPlugin (plugin.cpp:191-206) */
+void hcs_destroy(hcs_ctx *ctx);
+const char *hcs_last_error(const hcs_ctx *ctx); /* ctx may be NULL: error of the last failed create */
+
+/* --- configuration: one call per `cs::<geom>` numeric, in XML order ------------------------------ */
+/* replaces the geom switch of parseMujocoCustomFields (plugin.cpp:613-812).
+ *   size  = mjModel.geom_size[3*id..]  (sphere r | ellipsoid semi-axes | cylinder r,half-length | box half sizes)
+ *   props = {hydroelasticModulus, dissipation, resolutionHint, staticFriction, dynamicFriction};
+ *           modulus > 0 => SOFT (tet mesh + linear pressure field), else RIGID (triangle surface / plane)
+ *   mesh_vert/mesh_face: mjModel.mesh_vert (float32) / mesh_face (int32) of a MESH geom (plugin.cpp:745-763)
+ * returns the configuration index >= 0, HCS_E_UNSUPPORTED for plane-soft / hfield / capsule. */
+int hcs_add_geom(hcs_ctx *ctx, int mj_geom_type, const double size[3], const float *mesh_vert, int n_vert,
+                 const int32_t *mesh_face, int n_face, const double props[5]);
+/* user-supplied meshes (same role as the drake::geometry::VolumeMesh / TriangleSurfaceMesh a
+ * ContactProperties holds, mujoco_contact_surfaces_plugin.h:147-150) */
+int hcs_add_soft_mesh(hcs_ctx *ctx, const double *verts, int n_vert, const int32_t *tets, int n_tet,
+                      const double *vertex_pressure, const double props[5]);
+int hcs_add_rigid_mesh(hcs_ctx *ctx, const double *verts, int n_vert, const int32_t *tris, int n_tri,
+                       const double props[5]);
+/* replaces MujocoContactSurfacesPlugin::onGeomChanged (plugin.cpp:828-975): rebuild one geom after a
+ * size change (the reference's Q2 bugs are not reproduced: the new pressure field IS installed). */
+int hcs_update_geom(hcs_ctx *ctx, int geom, const double size[3]);
+
+/* geom pairs MuJoCo's collision pass hands to collision_cb (plugin.cpp:255-318), same for every env.
+ * (g1,g2) in the order MuJoCo would pass them; rigid-rigid pairs are accepted and ignored. */
+int hcs_set_pairs(hcs_ctx *ctx, const int32_t *g1, const int32_t *g2, int n_pairs);
+
+/* replaces FlatTactileSensor::load (SENS/src/flat_tactile_sensor.cpp:127-214): taxel grid
+ * cx = floor(2*size[0]/resolution + 0.1), cy likewise, sampling_resolution^2 rays per taxel.
+ * geom must be a box geom already added; returns the sensor index. */
+int hcs_add_flat_sensor(hcs_ctx *ctx, int geom, double resolution, int sampling_resolution, int window, float sigma);
+int hcs_sensor_dims(const hcs_ctx *ctx, int sensor, int *cx, int *cy);
+
+/* builds fields, tet half spaces and LBVHs on the GPU, allocates per-env buffers */
+int hcs_finalize(hcs_ctx *ctx);
+
+/* --- per step ----------------------------------------------------------------------------------- */
+/* replaces, for all envs at once: every collision_cb (plugin.cpp:255-318) + evaluateContactSurface
+ * (:320-409) + the force loop of passiveCallback (:411-483) + FlatTactileSensor::bvh_update
+ * (SENS/src/flat_tactile_sensor.cpp:262-402) when sensors exist and with_sensors != 0.
+ * HOST pointers; copies in/out are part of the call (this is the end-to-end entry point). */
+int hcs_step(hcs_ctx *ctx, const double *xpos, const double *xmat, const double *vel, int with_sensors);
+/* same with DEVICE pointers; asynchronous on the context stream, results stay on the GPU */
+int hcs_step_device(hcs_ctx *ctx, const double *d_xpos, const double *d_xmat, const double *d_vel,
+                    int with_sensors);
+/* wait for the stream, check the capacity flags (HCS_E_CAPACITY) */
+int hcs_sync(hcs_ctx *ctx);
+/* copy the device results of the last hcs_step_device into the context's pinned host mirrors */
+int hcs_fetch_results(hcs_ctx *ctx, int with_sensors);
+
+/* --- results (valid until the next step) ------------------------------------------------------------ */
+int hcs_n_geoms(const hcs_ctx *ctx);
+int hcs_n_pairs(const hcs_ctx *ctx);
+/* out[n_envs * n_pairs], env-major */
+int hcs_get_pair_results(hcs_ctx *ctx, hcs_pair_result *out);
+/* out[n_envs * n_geoms * 6]: (F, tau about the world origin) the contact surfaces apply to each geom;
+ * the adapter feeds this to ONE mj_applyFT per body instead of two per face (plugin.cpp:477-482) */
+int hcs_get_geom_wrenches(hcs_ctx *ctx, double *out);
+/* out[n_envs * cx * cy], index x + cy*y inside an image (SENS/src/flat_tactile_sensor.cpp:396-397) */
+int hcs_get_sensor_image(hcs_ctx *ctx, int sensor, float *out);
+/* device-resident views of the same results (no copy) */
+const hcs_pair_result *hcs_device_pair_results(hcs_ctx *ctx);
+const double *hcs_device_geom_wrenches(hcs_ctx *ctx);
+const float *hcs_device_sensor_image(hcs_ctx *ctx, int sensor);
+
+/* per-face dump = the GeomCollision/PointCollision views handed to SurfacePlugin::update
+ * (CS/include/mujoco_contact_surfaces/plugin_utils.h:94); needs cfg.max_faces > 0.
+ * returns the number of faces written (<= cap) or a negative status. Order is unspecified. */
+int hcs_get_faces(hcs_ctx *ctx, hcs_face *out, int cap);
+/* emitted candidate set of one pair in one env: triples (elemM, elemN, nverts); returns count */
+int hcs_get_emitted(hcs_ctx *ctx, int env, int pair, int32_t *out, int cap);
+/* kTriangle contact-surface triangle soup of one env (world frame), 12 doubles per triangle:
+ * 9 vertex coordinates + 3 vertex pressures; only pairs touching a sensor geom are kept. */
+int hcs_get_tactile_triangles(hcs_ctx *ctx, int env, double *out, int cap);
+
+/* --- introspection (tests, DESIGN.md evidence) ---------------------------------------------------------- */
+/* info = {kind (0 rigid mesh, 1 soft, 2 plane), n_vertices, n_elements} */
+int hcs_geom_info(const hcs_ctx *ctx, int geom, int info[3]);
+/* copies the device-resident mesh back: verts[nv*3], elems[ne*(4|3)], and for soft geoms
+ * pressure[nv], grad[ne*3], e0[ne]; for rigid geoms grad receives the unit face normals */
+int hcs_get_mesh(hcs_ctx *ctx, int geom, double *verts, int32_t *elems, double *pressure, double *grad, double *e0);
+/* counters of the last step: {candidate pair-evals, polygons, faces, tactile triangles, kernels launched} */
+int hcs_get_counters(hcs_ctx *ctx, int64_t out[5]);
+/* per-stage GPU time of the last step in ms (CUDA events on the context stream); needs hcs_set_profiling(1):
+ * {setup, broadphase, narrowphase, reduce, tactile_bin, tactile_raster, total} */
+int hcs_set_profiling(hcs_ctx *ctx, int enable);
+int hcs_get_stage_ms(hcs_ctx *ctx, float out[7]);
+const char *hcs_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HCS_H_ */

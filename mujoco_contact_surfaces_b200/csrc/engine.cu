@@ -1,0 +1,1160 @@
+// libhcs_b200 — context, resident-geometry management and the C ABI (include/hcs.h).
+//
+// Host-side mirror of MujocoContactSurfacesPlugin's configuration/dispatch logic
+// (mujoco_contact_surfaces_plugin.cpp:208-318, 571-813) for a BATCH of independent environments on one
+// GPU.  There is no CPU compute path: every entry point that needs a result launches CUDA kernels and
+// fails with HCS_E_CUDA when no device is usable.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "hcs_internal.h"
+#include "mesh_host.h"
+
+namespace hcs {
+
+static thread_local std::string g_create_error;
+
+#define CK(call)                                                                                        \
+	do {                                                                                                \
+		cudaError_t e_ = (call);                                                                        \
+		if (e_ != cudaSuccess) {                                                                        \
+			char buf_[512];                                                                             \
+			snprintf(buf_, sizeof buf_, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, \
+			         __LINE__);                                                                         \
+			throw std::runtime_error(buf_);                                                             \
+		}                                                                                               \
+	} while (0)
+
+struct GeomHost {
+	int mj_type = 0;
+	double size[3] = { 0, 0, 0 };
+	double props[5] = { 0, 0, 0, 0, 0 };
+	HostMesh mesh;
+	GeomDev dev{};
+	bool custom = false; // added through hcs_add_soft_mesh / hcs_add_rigid_mesh
+	std::vector<void *> allocs;
+	double E() const { return mesh.soft ? props[0] : std::numeric_limits<double>::infinity(); }
+	double dissipation() const { return mesh.soft ? props[1] : 1.0; } // ContactProperties ctor, plugin.h:197-198
+};
+
+struct SensorHost {
+	int geom;
+	double resolution;
+	int S, window;
+	float sigma;
+	int cx, cy;
+	SensorDev dev{};
+	std::vector<float> weights;
+	float *h_image = nullptr; // pinned [n_env][cx*cy]
+};
+
+} // namespace hcs
+
+using namespace hcs;
+
+struct hcs_ctx {
+	hcs_config cfg{};
+	std::string err;
+	cudaStream_t stream = nullptr;
+	bool own_stream     = false;
+	bool finalized      = false;
+	std::vector<GeomHost> geoms;
+	std::vector<std::pair<int, int>> pairs;
+	std::vector<PairDesc> pair_desc;
+	std::vector<SensorHost> sensors;
+	std::vector<void *> step_allocs;
+	PairDesc *d_pairs = nullptr;
+	StepIO io{};
+	double *d_xpos = nullptr, *d_xmat = nullptr, *d_vel = nullptr; // staging for the host entry point
+	hcs_pair_result *h_pair = nullptr;                             // pinned mirrors
+	double *h_wrench        = nullptr;
+	int32_t *h_flags        = nullptr;
+	int64_t kernels_last_step = 0;
+	bool profiling = false;
+	cudaEvent_t ev[8]{};
+	float stage_ms[7]{};
+	bool results_on_host = false, sensors_on_host = false, last_with_sensors = false;
+};
+
+namespace hcs {
+
+template <class T>
+static T *dalloc(std::vector<void *> &bag, size_t n)
+{
+	void *p = nullptr;
+	CK(cudaMalloc(&p, std::max<size_t>(n, 1) * sizeof(T)));
+	bag.push_back(p);
+	return (T *)p;
+}
+
+static void free_bag(std::vector<void *> &bag)
+{
+	for (void *p : bag)
+		cudaFree(p);
+	bag.clear();
+}
+
+// ---- LBVH over the tets of a soft geom: Morton codes of element centroids, Karras radix tree,
+// children boxes stored in the parent (float, rounded outward).  Built once per geom in its own frame;
+// meshes are rigid so the tree is never rebuilt in the step.
+static inline uint32_t expand_bits(uint32_t v)
+{
+	v = (v * 0x00010001u) & 0xFF0000FFu;
+	v = (v * 0x00000101u) & 0x0F00F00Fu;
+	v = (v * 0x00000011u) & 0xC30C30C3u;
+	v = (v * 0x00000005u) & 0x49249249u;
+	return v;
+}
+static inline float down(double x)
+{
+	float f = (float)x;
+	return (double)f > x ? std::nextafterf(f, -INFINITY) : f;
+}
+static inline float up(double x)
+{
+	float f = (float)x;
+	return (double)f < x ? std::nextafterf(f, INFINITY) : f;
+}
+
+struct BoxD {
+	double lo[3], hi[3];
+};
+
+static std::vector<BvhNode> build_lbvh(const HostMesh &m)
+{
+	const int n = m.n_elems();
+	std::vector<BoxD> leaf(n);
+	std::vector<double> cen(3 * (size_t)n);
+	double glo[3] = { 1e300, 1e300, 1e300 }, ghi[3] = { -1e300, -1e300, -1e300 };
+	for (int t = 0; t < n; ++t) {
+		BoxD b{ { 1e300, 1e300, 1e300 }, { -1e300, -1e300, -1e300 } };
+		double c[3] = { 0, 0, 0 };
+		for (int k = 0; k < 4; ++k) {
+			const double *p = &m.verts[3 * (size_t)m.elems[4 * (size_t)t + k]];
+			for (int a = 0; a < 3; ++a) {
+				b.lo[a] = std::min(b.lo[a], p[a]);
+				b.hi[a] = std::max(b.hi[a], p[a]);
+				c[a] += 0.25 * p[a];
+			}
+		}
+		leaf[t] = b;
+		for (int a = 0; a < 3; ++a) {
+			cen[3 * (size_t)t + a] = c[a];
+			glo[a] = std::min(glo[a], c[a]);
+			ghi[a] = std::max(ghi[a], c[a]);
+		}
+	}
+	std::vector<std::pair<uint64_t, int>> keys(n);
+	for (int t = 0; t < n; ++t) {
+		uint32_t q[3];
+		for (int a = 0; a < 3; ++a) {
+			double ext = ghi[a] - glo[a];
+			double u   = ext > 0 ? (cen[3 * (size_t)t + a] - glo[a]) / ext : 0.0;
+			q[a]       = (uint32_t)std::min(1023.0, std::max(0.0, u * 1024.0));
+		}
+		uint32_t code = expand_bits(q[0]) * 4 + expand_bits(q[1]) * 2 + expand_bits(q[2]);
+		keys[t]       = { ((uint64_t)code << 32) | (uint32_t)t, t };
+	}
+	std::sort(keys.begin(), keys.end());
+	std::vector<BvhNode> nodes(std::max(1, n - 1));
+	auto set_box = [&](BvhNode &nd, bool left, const BoxD &b) {
+		float *lo = left ? nd.llo : nd.rlo, *hi = left ? nd.lhi : nd.rhi;
+		for (int a = 0; a < 3; ++a) {
+			lo[a] = down(b.lo[a]);
+			hi[a] = up(b.hi[a]);
+		}
+	};
+	if (n == 1) {
+		BvhNode &nd = nodes[0];
+		set_box(nd, true, leaf[keys[0].second]);
+		nd.left = ~keys[0].second;
+		for (int a = 0; a < 3; ++a)
+			nd.rlo[a] = 3e38f, nd.rhi[a] = -3e38f;
+		nd.right  = ~keys[0].second;
+		nd.pad[0] = nd.pad[1] = 0;
+		return nodes;
+	}
+	// Karras 2012: common-prefix length of the (unique) 64-bit keys
+	auto delta = [&](int i, int j) -> int {
+		if (j < 0 || j >= n)
+			return -1;
+		return __builtin_clzll(keys[i].first ^ keys[j].first);
+	};
+	std::vector<int> left(n - 1), right(n - 1); // >=0 internal, <0 ~leaf slot
+	for (int i = 0; i < n - 1; ++i) {
+		int d     = delta(i, i + 1) - delta(i, i - 1) >= 0 ? 1 : -1;
+		int dmin  = delta(i, i - d);
+		int lmax  = 2;
+		while (delta(i, i + lmax * d) > dmin)
+			lmax *= 2;
+		int l = 0;
+		for (int t = lmax / 2; t >= 1; t /= 2)
+			if (delta(i, i + (l + t) * d) > dmin)
+				l += t;
+		int j     = i + l * d;
+		int dnode = delta(i, j);
+		int s     = 0;
+		for (int t = (l + 1) / 2;; t = (t + 1) / 2) {
+			if (delta(i, i + (s + t) * d) > dnode)
+				s += t;
+			if (t == 1)
+				break;
+		}
+		int gamma = i + s * d + std::min(d, 0);
+		left[i]   = std::min(i, j) == gamma ? ~gamma : gamma;
+		right[i]  = std::max(i, j) == gamma + 1 ? ~(gamma + 1) : gamma + 1;
+	}
+	// bottom-up boxes with an explicit stack (post-order from the root = node 0)
+	std::vector<BoxD> nbox(n - 1);
+	std::vector<char> done(n - 1, 0);
+	std::vector<int> stack = { 0 };
+	auto child_box = [&](int c) -> const BoxD & { return c < 0 ? leaf[keys[~c].second] : nbox[c]; };
+	while (!stack.empty()) {
+		int i = stack.back();
+		bool ready = true;
+		for (int c : { left[i], right[i] })
+			if (c >= 0 && !done[c]) {
+				stack.push_back(c);
+				ready = false;
+			}
+		if (!ready)
+			continue;
+		stack.pop_back();
+		const BoxD &a = child_box(left[i]), &b = child_box(right[i]);
+		for (int k = 0; k < 3; ++k) {
+			nbox[i].lo[k] = std::min(a.lo[k], b.lo[k]);
+			nbox[i].hi[k] = std::max(a.hi[k], b.hi[k]);
+		}
+		done[i]     = 1;
+		BvhNode &nd = nodes[i];
+		set_box(nd, true, a);
+		set_box(nd, false, b);
+		nd.left   = left[i] < 0 ? ~keys[~left[i]].second : left[i];
+		nd.right  = right[i] < 0 ? ~keys[~right[i]].second : right[i];
+		nd.pad[0] = nd.pad[1] = 0;
+	}
+	return nodes;
+}
+
+static void upload_geom(hcs_ctx *c, GeomHost &g)
+{
+	free_bag(g.allocs);
+	GeomDev d{};
+	const HostMesh &m = g.mesh;
+	d.kind            = m.plane ? 2 : (m.soft ? 1 : 0);
+	d.n_verts         = m.n_verts();
+	d.n_elems         = m.n_elems();
+	if (!m.plane) {
+		d.verts = dalloc<double>(g.allocs, m.verts.size());
+		d.elems = dalloc<int32_t>(g.allocs, m.elems.size());
+		CK(cudaMemcpyAsync(d.verts, m.verts.data(), m.verts.size() * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+		CK(cudaMemcpyAsync(d.elems, m.elems.data(), m.elems.size() * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+		// bounding sphere about the box centre of the vertices
+		double lo[3] = { 1e300, 1e300, 1e300 }, hi[3] = { -1e300, -1e300, -1e300 };
+		for (int i = 0; i < d.n_verts; ++i)
+			for (int a = 0; a < 3; ++a) {
+				lo[a] = std::min(lo[a], m.verts[3 * (size_t)i + a]);
+				hi[a] = std::max(hi[a], m.verts[3 * (size_t)i + a]);
+			}
+		double r2 = 0;
+		for (int a = 0; a < 3; ++a)
+			d.bound_c[a] = 0.5 * (lo[a] + hi[a]);
+		for (int i = 0; i < d.n_verts; ++i) {
+			double s = 0;
+			for (int a = 0; a < 3; ++a) {
+				double t = m.verts[3 * (size_t)i + a] - d.bound_c[a];
+				s += t * t;
+			}
+			r2 = std::max(r2, s);
+		}
+		d.bound_r = std::sqrt(r2) * (1 + 1e-12) + 1e-12;
+		if (m.soft) {
+			d.pressure = dalloc<double>(g.allocs, m.pressure.size());
+			CK(cudaMemcpyAsync(d.pressure, m.pressure.data(), m.pressure.size() * sizeof(double), cudaMemcpyHostToDevice,
+			                   c->stream));
+			d.tet_geom  = dalloc<TetGeom>(g.allocs, d.n_elems);
+			d.tet_field = dalloc<TetField>(g.allocs, d.n_elems);
+			std::vector<BvhNode> nodes = build_lbvh(m);
+			d.nodes                     = dalloc<BvhNode>(g.allocs, nodes.size());
+			CK(cudaMemcpyAsync(d.nodes, nodes.data(), nodes.size() * sizeof(BvhNode), cudaMemcpyHostToDevice, c->stream));
+			CK(cudaStreamSynchronize(c->stream)); // `nodes` is a local
+			launch_build_tets(d, c->stream);
+		} else {
+			d.tris = dalloc<TriRec>(g.allocs, d.n_elems);
+			launch_build_tris(d, c->stream);
+		}
+		CK(cudaGetLastError());
+	} else {
+		d.bound_r = 1e300;
+	}
+	g.dev = d;
+}
+
+// plugin.cpp:128-159
+static double combined_dissipation(const GeomHost &a, const GeomHost &b)
+{
+	const double inf = std::numeric_limits<double>::infinity();
+	double EA = a.E(), EB = b.E(), dA = a.dissipation(), dB = b.dissipation();
+	double Es = EA == inf ? EB : (EB == inf ? EA : EA * EB / (EA + EB));
+	if (Es == inf)
+		return 0.5 * (dA + dB);
+	double d = 0;
+	if (EA != inf)
+		d += Es / EA * dA;
+	if (EB != inf)
+		d += Es / EB * dB;
+	return d;
+}
+// drake CalcContactFrictionFromSurfaceProperties, dynamic coefficient (plugin.cpp:427-433)
+static double combined_mu(const GeomHost &a, const GeomHost &b)
+{
+	double den = a.props[4] + b.props[4];
+	return den == 0 ? 0.0 : 2 * a.props[4] * b.props[4] / den;
+}
+
+static bool is_sensor_geom(const hcs_ctx *c, int g)
+{
+	for (const SensorHost &s : c->sensors)
+		if (s.geom == g)
+			return true;
+	return false;
+}
+
+static void build_pairs(hcs_ctx *c)
+{
+	const int n_env = c->cfg.n_envs;
+	c->pair_desc.clear();
+	const long target_units = 16384;
+	for (size_t pi = 0; pi < c->pairs.size(); ++pi) {
+		int g1 = c->pairs[pi].first, g2 = c->pairs[pi].second;
+		const GeomHost *c1 = &c->geoms[g1], *c2 = &c->geoms[g2];
+		PairDesc P{};
+		P.index = (int)pi;
+		P.gM    = std::min(g1, g2);
+		P.gN    = std::max(g1, g2);
+		P.kind  = PAIR_NONE;
+		bool s1 = c1->mesh.soft, s2 = c2->mesh.soft;
+		if (s1 || s2) { // collision_cb dispatch, plugin.cpp:280-305
+			if (s1 && s2) {
+				P.kind = PAIR_SOFT_SOFT;
+				P.gA = g1, P.gB = g2;
+			} else {
+				if (!s1) {
+					std::swap(c1, c2);
+					std::swap(g1, g2);
+				}
+				P.gA = g1, P.gB = g2;
+				P.kind = c2->mesh.plane ? PAIR_SOFT_PLANE : PAIR_SOFT_RIGID;
+			}
+			const GeomHost &A = c->geoms[P.gA], &B = c->geoms[P.gB];
+			P.A = A.dev, P.B = B.dev;
+			P.sign        = P.gA == P.gM ? 1.0 : -1.0;
+			P.dissipation = combined_dissipation(c->geoms[P.gM], c->geoms[P.gN]);
+			P.mu          = combined_mu(c->geoms[P.gM], c->geoms[P.gN]);
+			P.n_tree      = A.dev.n_elems;
+			P.nq          = P.kind == PAIR_SOFT_PLANE ? A.dev.n_elems : B.dev.n_elems;
+			P.emit_tactile = c->cfg.representation == HCS_REP_TRIANGLE && (is_sensor_geom(c, P.gA) || is_sensor_geom(c, P.gB));
+			int chunks   = (P.nq + 31) / 32;
+			long want    = std::max<long>(1, (target_units + n_env - 1) / n_env);
+			int S        = (int)std::min<long>(chunks, want);
+			S            = std::max(S, 1);
+			P.slice_q    = 32 * ((chunks + S - 1) / S);
+			P.n_slices   = (P.nq + P.slice_q - 1) / P.slice_q;
+			size_t units = (size_t)n_env * P.n_slices;
+			P.partial    = dalloc<SlicePartial>(c->step_allocs, units);
+			if (P.kind == PAIR_SOFT_PLANE) {
+				P.cap         = 0;
+				P.slab_nverts = dalloc<uint8_t>(c->step_allocs, (size_t)n_env * P.nq);
+				CK(cudaMemsetAsync(P.slab_nverts, 0, (size_t)n_env * P.nq, c->stream));
+			} else {
+				long cap = c->cfg.max_candidates_per_slice > 0 ?
+				               c->cfg.max_candidates_per_slice :
+				               std::min<long>((long)P.slice_q * P.n_tree, std::max<long>(1024, 64L * P.slice_q));
+				P.cap         = (int)cap;
+				P.slab        = dalloc<uint2>(c->step_allocs, units * cap);
+				P.slab_count  = dalloc<int32_t>(c->step_allocs, units);
+				P.slab_nverts = dalloc<uint8_t>(c->step_allocs, units * cap);
+				CK(cudaMemsetAsync(P.slab_count, 0, units * sizeof(int32_t), c->stream));
+			}
+		}
+		c->pair_desc.push_back(P);
+	}
+	c->d_pairs = dalloc<PairDesc>(c->step_allocs, c->pair_desc.size());
+	CK(cudaMemcpyAsync(c->d_pairs, c->pair_desc.data(), c->pair_desc.size() * sizeof(PairDesc), cudaMemcpyHostToDevice,
+	                   c->stream));
+}
+
+// window weights of FlatTactileSensor (flat_tactile_sensor.cpp:179-185, 305-314, 353-388), which depend
+// only on the sub-sample (i, j): tabulated once on the host with the same float/double mix.
+static void build_sensor(hcs_ctx *c, SensorHost &s)
+{
+	const GeomHost &g = c->geoms[s.geom];
+	const int S       = s.S;
+	double resolution = s.resolution;
+	float di_factor     = resolution / S;
+	float sub_halfwidth = di_factor / 2.0f - resolution / 2.0f;
+	float rmean         = 1. / (S * S);
+	float rS            = resolution / S;
+	const float SQRT_2  = 1.41421356237;
+	float max_dist      = SQRT_2 * resolution / 2.0f;
+	float sigma         = s.sigma;
+	float rsigma_squared = 0, rtukey = 0;
+	if (s.window == HCS_WINDOW_GAUSS)
+		rsigma_squared = 0.5f / (sigma * sigma);
+	else if (s.window == HCS_WINDOW_TUKEY)
+		rtukey = 1.f / sigma * S * S;
+	s.weights.assign((size_t)S * S, 1.0f);
+	for (int i = 0; i < S; ++i)
+		for (int j = 0; j < S; ++j) {
+			float weight = 1.0f;
+			if (s.window == HCS_WINDOW_GAUSS) {
+				float dist = std::hypot(di_factor * i + sub_halfwidth, di_factor * j + sub_halfwidth) / max_dist;
+				weight     = std::exp((double)(-(dist * dist) * rsigma_squared));
+			} else if (s.window == HCS_WINDOW_TUKEY) {
+				if (S / 2 - std::abs(S / 2 - i) <= sigma * S / 2)
+					weight *= 0.5f * (1.f - cosf(2.f * M_PI * (S / 2 - std::abs(S / 2 - i)) * rtukey));
+				if (S / 2 - std::abs(S / 2 - j) <= sigma * S / 2)
+					weight *= 0.5f * (1.f - cosf(2.f * M_PI * (S / 2 - std::abs(S / 2 - j)) * rtukey));
+			} else if (s.window == HCS_WINDOW_SQUARE) {
+				float inv_dist = 1 - std::hypot(di_factor * i + sub_halfwidth, di_factor * j + sub_halfwidth) / max_dist;
+				weight         = inv_dist * inv_dist;
+			}
+			s.weights[(size_t)i * S + j] = weight;
+		}
+	SensorDev d{};
+	d.geom = s.geom, d.cx = s.cx, d.cy = s.cy, d.S = S, d.window = s.window, d.sigma = sigma;
+	d.resolution = resolution;
+	for (int a = 0; a < 3; ++a)
+		d.size[a] = g.size[a];
+	d.rmean = rmean, d.rS = rS;
+	float *w = dalloc<float>(c->step_allocs, s.weights.size());
+	CK(cudaMemcpyAsync(w, s.weights.data(), s.weights.size() * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+	d.weights    = w;
+	size_t ncell = (size_t)c->cfg.n_envs * s.cx * s.cy;
+	d.image      = dalloc<float>(c->step_allocs, ncell);
+	CK(cudaMemsetAsync(d.image, 0, ncell * sizeof(float), c->stream));
+	d.bin_cap   = c->cfg.max_triangles_per_taxel > 0 ? c->cfg.max_triangles_per_taxel : 64;
+	d.bin_count = dalloc<int32_t>(c->step_allocs, ncell);
+	d.bin_items = dalloc<int32_t>(c->step_allocs, ncell * d.bin_cap);
+	s.dev       = d;
+	CK(cudaMallocHost((void **)&s.h_image, std::max<size_t>(ncell, 1) * sizeof(float)));
+}
+
+static void release_step_buffers(hcs_ctx *c)
+{
+	free_bag(c->step_allocs);
+	for (SensorHost &s : c->sensors)
+		if (s.h_image) {
+			cudaFreeHost(s.h_image);
+			s.h_image = nullptr;
+		}
+	if (c->h_pair)
+		cudaFreeHost(c->h_pair), c->h_pair = nullptr;
+	if (c->h_wrench)
+		cudaFreeHost(c->h_wrench), c->h_wrench = nullptr;
+	if (c->h_flags)
+		cudaFreeHost(c->h_flags), c->h_flags = nullptr;
+	c->d_pairs = nullptr;
+}
+
+static void finalize(hcs_ctx *c)
+{
+	release_step_buffers(c);
+	const int n_env = c->cfg.n_envs, ng = (int)c->geoms.size(), np = (int)c->pairs.size();
+	for (GeomHost &g : c->geoms)
+		upload_geom(c, g);
+	for (SensorHost &s : c->sensors)
+		build_sensor(c, s);
+	build_pairs(c);
+	StepIO io{};
+	io.n_env = n_env, io.n_geoms = ng, io.n_pairs = np;
+	io.representation = c->cfg.representation;
+	io.apply_forces   = c->cfg.apply_contact_forces;
+	io.flags          = dalloc<int32_t>(c->step_allocs, 4);
+	io.max_faces      = std::max(0, c->cfg.max_faces);
+	io.faces          = dalloc<hcs_face>(c->step_allocs, io.max_faces);
+	io.face_count     = dalloc<int32_t>(c->step_allocs, 1);
+	bool tactile      = false;
+	for (const PairDesc &P : c->pair_desc)
+		tactile |= P.emit_tactile != 0;
+	io.max_tris = 0;
+	if (tactile) {
+		long automatic = 0;
+		for (const PairDesc &P : c->pair_desc)
+			if (P.emit_tactile) // every tet could emit one polygon of <= 8 fan triangles per env; cap the default
+				automatic += std::min<long>(8L * P.nq, 4096);
+		io.max_tris = c->cfg.max_tactile_triangles > 0 ? c->cfg.max_tactile_triangles :
+		                                                   (int)std::min<long>(automatic * n_env, 1L << 28);
+	}
+	io.tri_pool    = dalloc<TactileTri>(c->step_allocs, io.max_tris);
+	io.tri_count   = dalloc<int32_t>(c->step_allocs, 1);
+	io.pair_out    = dalloc<hcs_pair_result>(c->step_allocs, (size_t)n_env * np);
+	io.geom_wrench = dalloc<double>(c->step_allocs, (size_t)n_env * ng * 6);
+	CK(cudaMemsetAsync(io.flags, 0, 4 * sizeof(int32_t), c->stream));
+	CK(cudaMemsetAsync(io.face_count, 0, sizeof(int32_t), c->stream));
+	CK(cudaMemsetAsync(io.tri_count, 0, sizeof(int32_t), c->stream));
+	CK(cudaMemsetAsync(io.pair_out, 0, (size_t)n_env * np * sizeof(hcs_pair_result), c->stream));
+	CK(cudaMemsetAsync(io.geom_wrench, 0, (size_t)n_env * ng * 6 * sizeof(double), c->stream));
+	c->d_xpos = dalloc<double>(c->step_allocs, (size_t)n_env * ng * 3);
+	c->d_xmat = dalloc<double>(c->step_allocs, (size_t)n_env * ng * 9);
+	c->d_vel  = dalloc<double>(c->step_allocs, (size_t)n_env * ng * 6);
+	CK(cudaMallocHost((void **)&c->h_pair, std::max<size_t>((size_t)n_env * np, 1) * sizeof(hcs_pair_result)));
+	CK(cudaMallocHost((void **)&c->h_wrench, std::max<size_t>((size_t)n_env * ng * 6, 1) * sizeof(double)));
+	CK(cudaMallocHost((void **)&c->h_flags, 4 * sizeof(int32_t)));
+	memset(c->h_flags, 0, 4 * sizeof(int32_t));
+	c->io = io;
+	CK(cudaStreamSynchronize(c->stream));
+	c->finalized = true;
+}
+
+static void step_device(hcs_ctx *c, const double *xpos, const double *xmat, const double *vel, int with_sensors)
+{
+	StepIO io = c->io;
+	io.xpos = xpos, io.xmat = xmat, io.vel = vel;
+	cudaStream_t s = c->stream;
+	int64_t k      = 0;
+	bool prof      = c->profiling;
+	if (prof)
+		CK(cudaEventRecord(c->ev[0], s));
+	CK(cudaMemsetAsync(io.flags, 0, 4 * sizeof(int32_t), s));
+	if (io.max_faces > 0)
+		CK(cudaMemsetAsync(io.face_count, 0, sizeof(int32_t), s));
+	if (io.max_tris > 0)
+		CK(cudaMemsetAsync(io.tri_count, 0, sizeof(int32_t), s));
+	if (prof)
+		CK(cudaEventRecord(c->ev[1], s));
+	for (const PairDesc &P : c->pair_desc)
+		if (P.kind == PAIR_SOFT_RIGID || P.kind == PAIR_SOFT_SOFT) {
+			launch_broadphase(P, io, s);
+			++k;
+		}
+	if (prof)
+		CK(cudaEventRecord(c->ev[2], s));
+	for (const PairDesc &P : c->pair_desc)
+		if (P.kind != PAIR_NONE) {
+			launch_narrowphase(P, io, s);
+			++k;
+		}
+	if (prof)
+		CK(cudaEventRecord(c->ev[3], s));
+	launch_finalize(c->d_pairs, io, s);
+	k += 2;
+	if (prof)
+		CK(cudaEventRecord(c->ev[4], s));
+	if (with_sensors)
+		for (SensorHost &sh : c->sensors) {
+			launch_tactile(sh.dev, io, c->d_pairs, s);
+			k += 3;
+		}
+	if (prof)
+		CK(cudaEventRecord(c->ev[5], s));
+	CK(cudaGetLastError());
+	c->kernels_last_step = k;
+	c->results_on_host = c->sensors_on_host = false;
+	c->last_with_sensors                   = with_sensors != 0;
+}
+
+static void fetch(hcs_ctx *c, int with_sensors)
+{
+	const int n_env = c->cfg.n_envs, ng = (int)c->geoms.size(), np = (int)c->pairs.size();
+	cudaStream_t s = c->stream;
+	CK(cudaMemcpyAsync(c->h_pair, c->io.pair_out, (size_t)n_env * np * sizeof(hcs_pair_result), cudaMemcpyDeviceToHost, s));
+	CK(cudaMemcpyAsync(c->h_wrench, c->io.geom_wrench, (size_t)n_env * ng * 6 * sizeof(double), cudaMemcpyDeviceToHost, s));
+	CK(cudaMemcpyAsync(c->h_flags, c->io.flags, 4 * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+	if (with_sensors)
+		for (SensorHost &sh : c->sensors)
+			CK(cudaMemcpyAsync(sh.h_image, sh.dev.image, (size_t)n_env * sh.cx * sh.cy * sizeof(float), cudaMemcpyDeviceToHost, s));
+	CK(cudaStreamSynchronize(s));
+	c->results_on_host = true;
+	c->sensors_on_host = with_sensors != 0;
+}
+
+static int check_flags(hcs_ctx *c)
+{
+	if (c->h_flags[1]) {
+		c->err = "LBVH traversal stack overflow (tree deeper than 64)";
+		return HCS_E_CAPACITY;
+	}
+	if (c->h_flags[0] & 1) {
+		c->err = "broadphase candidate slab overflow: raise hcs_config.max_candidates_per_slice";
+		return HCS_E_CAPACITY;
+	}
+	if (c->h_flags[0] & 2) {
+		c->err = "tactile triangle pool overflow: raise hcs_config.max_tactile_triangles";
+		return HCS_E_CAPACITY;
+	}
+	if (c->h_flags[0] & 4) {
+		c->err = "tactile taxel bin overflow: raise hcs_config.max_triangles_per_taxel";
+		return HCS_E_CAPACITY;
+	}
+	return HCS_OK;
+}
+
+} // namespace hcs
+
+// =====================================================================================================
+// C ABI
+// =====================================================================================================
+#define API_BEGIN(ctx_)            \
+	if (!(ctx_))                   \
+		return HCS_E_INVALID;      \
+	try {
+#define API_END(ctx_)                        \
+	}                                        \
+	catch (const std::exception &e)          \
+	{                                        \
+		(ctx_)->err = e.what();              \
+		return HCS_E_CUDA;                   \
+	}
+
+extern "C" {
+
+const char *hcs_version(void) { return "hcs_b200 0.1 (sm_100a, fp64 geometry mode)"; }
+
+const char *hcs_last_error(const hcs_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int hcs_create(const hcs_config *cfg, hcs_ctx **out)
+{
+	if (!cfg || !out || cfg->n_envs < 1) {
+		g_create_error = "hcs_create: bad arguments";
+		return HCS_E_INVALID;
+	}
+	int ndev = 0;
+	cudaError_t e = cudaGetDeviceCount(&ndev);
+	if (e != cudaSuccess || ndev == 0) {
+		// no CPU fallback: the engine exists only on the GPU
+		g_create_error = std::string("hcs_create: no usable CUDA device (") + cudaGetErrorString(e) + ")";
+		return HCS_E_CUDA;
+	}
+	if (cfg->device < 0 || cfg->device >= ndev) {
+		g_create_error = "hcs_create: device ordinal out of range";
+		return HCS_E_INVALID;
+	}
+	hcs_ctx *c = new hcs_ctx();
+	c->cfg     = *cfg;
+	try {
+		CK(cudaSetDevice(cfg->device));
+		if (cfg->stream) {
+			c->stream = (cudaStream_t)cfg->stream;
+		} else {
+			CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+			c->own_stream = true;
+		}
+		for (auto &ev : c->ev)
+			CK(cudaEventCreate(&ev));
+	} catch (const std::exception &ex) {
+		g_create_error = ex.what();
+		delete c;
+		return HCS_E_CUDA;
+	}
+	*out = c;
+	return HCS_OK;
+}
+
+void hcs_destroy(hcs_ctx *c)
+{
+	if (!c)
+		return;
+	cudaSetDevice(c->cfg.device);
+	cudaStreamSynchronize(c->stream);
+	release_step_buffers(c);
+	for (GeomHost &g : c->geoms)
+		free_bag(g.allocs);
+	for (auto &ev : c->ev)
+		if (ev)
+			cudaEventDestroy(ev);
+	if (c->own_stream)
+		cudaStreamDestroy(c->stream);
+	delete c;
+}
+
+int hcs_add_geom(hcs_ctx *c, int mj_geom_type, const double size[3], const float *mesh_vert, int n_vert,
+                 const int32_t *mesh_face, int n_face, const double props[5])
+{
+	API_BEGIN(c)
+	if (!size || !props) {
+		c->err = "hcs_add_geom: size/props required";
+		return HCS_E_INVALID;
+	}
+	GeomHost g;
+	g.mj_type = mj_geom_type;
+	for (int i = 0; i < 3; ++i)
+		g.size[i] = size[i];
+	for (int i = 0; i < 5; ++i)
+		g.props[i] = props[i];
+	std::string err;
+	if (!build_geom_mesh(mj_geom_type, size, mesh_vert, n_vert, mesh_face, n_face, props, g.mesh, err)) {
+		c->err = err;
+		return HCS_E_UNSUPPORTED;
+	}
+	c->geoms.push_back(std::move(g));
+	c->finalized = false;
+	return (int)c->geoms.size() - 1;
+	API_END(c)
+}
+
+int hcs_add_soft_mesh(hcs_ctx *c, const double *verts, int n_vert, const int32_t *tets, int n_tet,
+                      const double *vertex_pressure, const double props[5])
+{
+	API_BEGIN(c)
+	if (!verts || !tets || !vertex_pressure || !props || n_vert < 4 || n_tet < 1 || !(props[0] > 0)) {
+		c->err = "hcs_add_soft_mesh: bad arguments (modulus must be > 0)";
+		return HCS_E_INVALID;
+	}
+	GeomHost g;
+	g.mj_type = HCS_GEOM_MESH;
+	g.custom  = true;
+	for (int i = 0; i < 5; ++i)
+		g.props[i] = props[i];
+	g.mesh.soft = true;
+	g.mesh.verts.assign(verts, verts + 3 * (size_t)n_vert);
+	g.mesh.elems.assign(tets, tets + 4 * (size_t)n_tet);
+	g.mesh.pressure.assign(vertex_pressure, vertex_pressure + n_vert);
+	c->geoms.push_back(std::move(g));
+	c->finalized = false;
+	return (int)c->geoms.size() - 1;
+	API_END(c)
+}
+
+int hcs_add_rigid_mesh(hcs_ctx *c, const double *verts, int n_vert, const int32_t *tris, int n_tri, const double props[5])
+{
+	API_BEGIN(c)
+	if (!verts || !tris || !props || n_vert < 3 || n_tri < 1) {
+		c->err = "hcs_add_rigid_mesh: bad arguments";
+		return HCS_E_INVALID;
+	}
+	GeomHost g;
+	g.mj_type = HCS_GEOM_MESH;
+	g.custom  = true;
+	for (int i = 0; i < 5; ++i)
+		g.props[i] = props[i];
+	g.props[0]  = 0;
+	g.mesh.soft = false;
+	g.mesh.verts.assign(verts, verts + 3 * (size_t)n_vert);
+	g.mesh.elems.assign(tris, tris + 3 * (size_t)n_tri);
+	c->geoms.push_back(std::move(g));
+	c->finalized = false;
+	return (int)c->geoms.size() - 1;
+	API_END(c)
+}
+
+int hcs_update_geom(hcs_ctx *c, int geom, const double size[3])
+{
+	API_BEGIN(c)
+	if (geom < 0 || geom >= (int)c->geoms.size() || !size || c->geoms[geom].custom) {
+		c->err = "hcs_update_geom: bad geom";
+		return HCS_E_INVALID;
+	}
+	GeomHost &g = c->geoms[geom];
+	if (g.mj_type == HCS_GEOM_MESH || g.mj_type == HCS_GEOM_PLANE)
+		return HCS_OK; // nothing depends on geom_size
+	HostMesh m;
+	std::string err;
+	if (!build_geom_mesh(g.mj_type, size, nullptr, 0, nullptr, 0, g.props, m, err)) {
+		c->err = err;
+		return HCS_E_UNSUPPORTED;
+	}
+	for (int i = 0; i < 3; ++i)
+		g.size[i] = size[i];
+	g.mesh = std::move(m);
+	if (c->finalized) { // element counts may change: rebuild the per-pair buffers as well
+		CK(cudaStreamSynchronize(c->stream));
+		finalize(c);
+	}
+	return HCS_OK;
+	API_END(c)
+}
+
+int hcs_set_pairs(hcs_ctx *c, const int32_t *g1, const int32_t *g2, int n_pairs)
+{
+	API_BEGIN(c)
+	if (n_pairs < 0 || (n_pairs > 0 && (!g1 || !g2))) {
+		c->err = "hcs_set_pairs: bad arguments";
+		return HCS_E_INVALID;
+	}
+	std::vector<std::pair<int, int>> p;
+	for (int i = 0; i < n_pairs; ++i) {
+		if (g1[i] < 0 || g2[i] < 0 || g1[i] >= (int)c->geoms.size() || g2[i] >= (int)c->geoms.size() || g1[i] == g2[i]) {
+			c->err = "hcs_set_pairs: geom index out of range";
+			return HCS_E_INVALID;
+		}
+		p.emplace_back(g1[i], g2[i]);
+	}
+	c->pairs     = p;
+	c->finalized = false;
+	return HCS_OK;
+	API_END(c)
+}
+
+int hcs_add_flat_sensor(hcs_ctx *c, int geom, double resolution, int sampling_resolution, int window, float sigma)
+{
+	API_BEGIN(c)
+	if (geom < 0 || geom >= (int)c->geoms.size() || c->geoms[geom].mj_type != HCS_GEOM_BOX || !(resolution > 0) ||
+	    sampling_resolution < 1 || sampling_resolution > 32 || window < 0 || window > 3) {
+		c->err = "hcs_add_flat_sensor: needs a box geom, resolution > 0, 1 <= sampling_resolution <= 32, window in 0..3";
+		return HCS_E_INVALID;
+	}
+	SensorHost s{};
+	s.geom = geom, s.resolution = resolution, s.S = sampling_resolution, s.window = window, s.sigma = sigma;
+	// defaults of flat_tactile_sensor.cpp:148-160
+	if (window == HCS_WINDOW_GAUSS && sigma == -1.0f)
+		s.sigma = 0.1;
+	if (window == HCS_WINDOW_TUKEY && sigma == -1.0f)
+		s.sigma = 0.3;
+	const double *gs = c->geoms[geom].size;
+	s.cx = (int)::floorl(2 * gs[0] / resolution + 0.1); // flat_tactile_sensor.cpp:196-197
+	s.cy = (int)::floorl(2 * gs[1] / resolution + 0.1);
+	if (s.cx < 1 || s.cy < 1) {
+		c->err = "hcs_add_flat_sensor: resolution larger than the sensor geom";
+		return HCS_E_INVALID;
+	}
+	c->sensors.push_back(s);
+	c->finalized = false;
+	return (int)c->sensors.size() - 1;
+	API_END(c)
+}
+
+int hcs_sensor_dims(const hcs_ctx *c, int sensor, int *cx, int *cy)
+{
+	if (!c || sensor < 0 || sensor >= (int)c->sensors.size() || !cx || !cy)
+		return HCS_E_INVALID;
+	*cx = c->sensors[sensor].cx;
+	*cy = c->sensors[sensor].cy;
+	return HCS_OK;
+}
+
+int hcs_finalize(hcs_ctx *c)
+{
+	API_BEGIN(c)
+	CK(cudaSetDevice(c->cfg.device));
+	finalize(c);
+	return HCS_OK;
+	API_END(c)
+}
+
+int hcs_step_device(hcs_ctx *c, const double *d_xpos, const double *d_xmat, const double *d_vel, int with_sensors)
+{
+	API_BEGIN(c)
+	if (!c->finalized) {
+		c->err = "hcs_step: call hcs_finalize first";
+		return HCS_E_NOT_FINALIZED;
+	}
+	if (!d_xpos || !d_xmat || !d_vel) {
+		c->err = "hcs_step_device: null pose/velocity pointer";
+		return HCS_E_INVALID;
+	}
+	step_device(c, d_xpos, d_xmat, d_vel, with_sensors);
+	return HCS_OK;
+	API_END(c)
+}
+
+int hcs_step(hcs_ctx *c, const double *xpos, const double *xmat, const double *vel, int with_sensors)
+{
+	API_BEGIN(c)
+	if (!c->finalized) {
+		c->err = "hcs_step: call hcs_finalize first";
+		return HCS_E_NOT_FINALIZED;
+	}
+	if (!xpos || !xmat || !vel) {
+		c->err = "hcs_step: null pose/velocity pointer";
+		return HCS_E_INVALID;
+	}
+	size_t n = (size_t)c->cfg.n_envs * c->geoms.size();
+	CK(cudaMemcpyAsync(c->d_xpos, xpos, n * 3 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+	CK(cudaMemcpyAsync(c->d_xmat, xmat, n * 9 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+	CK(cudaMemcpyAsync(c->d_vel, vel, n * 6 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+	step_device(c, c->d_xpos, c->d_xmat, c->d_vel, with_sensors);
+	fetch(c, with_sensors);
+	return check_flags(c);
+	API_END(c)
+}
+
+int hcs_sync(hcs_ctx *c)
+{
+	API_BEGIN(c)
+	CK(cudaMemcpyAsync(c->h_flags, c->io.flags, 4 * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+	CK(cudaStreamSynchronize(c->stream));
+	if (c->profiling) {
+		for (int i = 0; i < 5; ++i)
+			cudaEventElapsedTime(&c->stage_ms[i], c->ev[i], c->ev[i + 1]);
+		c->stage_ms[5] = 0;
+		cudaEventElapsedTime(&c->stage_ms[6], c->ev[0], c->ev[5]);
+	}
+	return check_flags(c);
+	API_END(c)
+}
+
+int hcs_fetch_results(hcs_ctx *c, int with_sensors)
+{
+	API_BEGIN(c)
+	if (!c->finalized)
+		return HCS_E_NOT_FINALIZED;
+	fetch(c, with_sensors && c->last_with_sensors);
+	return check_flags(c);
+	API_END(c)
+}
+
+int hcs_n_geoms(const hcs_ctx *c) { return c ? (int)c->geoms.size() : HCS_E_INVALID; }
+int hcs_n_pairs(const hcs_ctx *c) { return c ? (int)c->pairs.size() : HCS_E_INVALID; }
+
+int hcs_get_pair_results(hcs_ctx *c, hcs_pair_result *out)
+{
+	API_BEGIN(c)
+	if (!c->finalized || !out)
+		return HCS_E_INVALID;
+	if (!c->results_on_host)
+		fetch(c, 0);
+	memcpy(out, c->h_pair, (size_t)c->cfg.n_envs * c->pairs.size() * sizeof(hcs_pair_result));
+	return HCS_OK;
+	API_END(c)
+}
+
+int hcs_get_geom_wrenches(hcs_ctx *c, double *out)
+{
+	API_BEGIN(c)
+	if (!c->finalized || !out)
+		return HCS_E_INVALID;
+	if (!c->results_on_host)
+		fetch(c, 0);
+	memcpy(out, c->h_wrench, (size_t)c->cfg.n_envs * c->geoms.size() * 6 * sizeof(double));
+	return HCS_OK;
+	API_END(c)
+}
+
+int hcs_get_sensor_image(hcs_ctx *c, int sensor, float *out)
+{
+	API_BEGIN(c)
+	if (!c->finalized || !out || sensor < 0 || sensor >= (int)c->sensors.size())
+		return HCS_E_INVALID;
+	if (!c->last_with_sensors) {
+		c->err = "hcs_get_sensor_image: the last step ran with with_sensors == 0";
+		return HCS_E_INVALID;
+	}
+	if (!c->sensors_on_host)
+		fetch(c, 1);
+	SensorHost &s = c->sensors[sensor];
+	memcpy(out, s.h_image, (size_t)c->cfg.n_envs * s.cx * s.cy * sizeof(float));
+	return HCS_OK;
+	API_END(c)
+}
+
+const hcs_pair_result *hcs_device_pair_results(hcs_ctx *c) { return c && c->finalized ? c->io.pair_out : nullptr; }
+const double *hcs_device_geom_wrenches(hcs_ctx *c) { return c && c->finalized ? c->io.geom_wrench : nullptr; }
+const float *hcs_device_sensor_image(hcs_ctx *c, int sensor)
+{
+	if (!c || !c->finalized || sensor < 0 || sensor >= (int)c->sensors.size())
+		return nullptr;
+	return c->sensors[sensor].dev.image;
+}
+
+int hcs_get_faces(hcs_ctx *c, hcs_face *out, int cap)
+{
+	API_BEGIN(c)
+	if (!c->finalized || c->io.max_faces <= 0) {
+		c->err = "hcs_get_faces: needs hcs_config.max_faces > 0";
+		return HCS_E_INVALID;
+	}
+	int32_t n = 0;
+	CK(cudaMemcpyAsync(&n, c->io.face_count, sizeof n, cudaMemcpyDeviceToHost, c->stream));
+	CK(cudaStreamSynchronize(c->stream));
+	if (n > c->io.max_faces) {
+		c->err = "per-face dump overflow: raise hcs_config.max_faces";
+		return HCS_E_CAPACITY;
+	}
+	int m = std::min<int>(n, cap);
+	if (m > 0 && out) {
+		CK(cudaMemcpyAsync(out, c->io.faces, (size_t)m * sizeof(hcs_face), cudaMemcpyDeviceToHost, c->stream));
+		CK(cudaStreamSynchronize(c->stream));
+	}
+	return n;
+	API_END(c)
+}
+
+int hcs_get_emitted(hcs_ctx *c, int env, int pair, int32_t *out, int cap)
+{
+	API_BEGIN(c)
+	if (!c->finalized || env < 0 || env >= c->cfg.n_envs || pair < 0 || pair >= (int)c->pairs.size())
+		return HCS_E_INVALID;
+	const PairDesc &P = c->pair_desc[pair];
+	if (P.kind == PAIR_NONE)
+		return 0;
+	int n = 0;
+	auto put = [&](int eA, int eB, int nv) {
+		if (n < cap && out) {
+			out[3 * n]     = P.sign > 0 ? eA : eB;
+			out[3 * n + 1] = P.sign > 0 ? eB : eA;
+			out[3 * n + 2] = nv;
+		}
+		++n;
+	};
+	if (P.kind == PAIR_SOFT_PLANE) {
+		std::vector<uint8_t> nv(P.nq);
+		CK(cudaMemcpyAsync(nv.data(), P.slab_nverts + (size_t)env * P.nq, P.nq, cudaMemcpyDeviceToHost, c->stream));
+		CK(cudaStreamSynchronize(c->stream));
+		for (int t = 0; t < P.nq; ++t)
+			if (nv[t] >= 3)
+				put(t, 0, nv[t]);
+		return n;
+	}
+	std::vector<int32_t> counts(P.n_slices);
+	CK(cudaMemcpyAsync(counts.data(), P.slab_count + (size_t)env * P.n_slices, P.n_slices * sizeof(int32_t),
+	                   cudaMemcpyDeviceToHost, c->stream));
+	CK(cudaStreamSynchronize(c->stream));
+	std::vector<uint2> cand;
+	std::vector<uint8_t> nv;
+	for (int s = 0; s < P.n_slices; ++s) {
+		int cnt = counts[s];
+		if (cnt <= 0)
+			continue;
+		size_t off = ((size_t)env * P.n_slices + s) * P.cap;
+		cand.resize(cnt);
+		nv.resize(cnt);
+		CK(cudaMemcpyAsync(cand.data(), P.slab + off, cnt * sizeof(uint2), cudaMemcpyDeviceToHost, c->stream));
+		CK(cudaMemcpyAsync(nv.data(), P.slab_nverts + off, cnt, cudaMemcpyDeviceToHost, c->stream));
+		CK(cudaStreamSynchronize(c->stream));
+		for (int i = 0; i < cnt; ++i)
+			if (nv[i] >= 3)
+				put((int)cand[i].y, (int)cand[i].x, nv[i]); // (tree element of A, query element of B)
+	}
+	return n;
+	API_END(c)
+}
+
+int hcs_get_tactile_triangles(hcs_ctx *c, int env, double *out, int cap)
+{
+	API_BEGIN(c)
+	if (!c->finalized || env < 0 || env >= c->cfg.n_envs)
+		return HCS_E_INVALID;
+	if (c->io.max_tris <= 0)
+		return 0;
+	int32_t n = 0;
+	CK(cudaMemcpyAsync(&n, c->io.tri_count, sizeof n, cudaMemcpyDeviceToHost, c->stream));
+	CK(cudaStreamSynchronize(c->stream));
+	n = std::min(n, c->io.max_tris);
+	std::vector<TactileTri> pool(n);
+	if (n > 0) {
+		CK(cudaMemcpyAsync(pool.data(), c->io.tri_pool, (size_t)n * sizeof(TactileTri), cudaMemcpyDeviceToHost, c->stream));
+		CK(cudaStreamSynchronize(c->stream));
+	}
+	std::vector<const TactileTri *> mine;
+	for (const TactileTri &t : pool)
+		if (t.env == env)
+			mine.push_back(&t);
+	std::sort(mine.begin(), mine.end(), [](const TactileTri *a, const TactileTri *b) {
+		return a->pair != b->pair ? a->pair < b->pair : a->order < b->order;
+	});
+	int m = 0;
+	for (const TactileTri *t : mine) {
+		if (m < cap && out) {
+			for (int k = 0; k < 9; ++k)
+				out[12 * m + k] = t->v[k];
+			for (int k = 0; k < 3; ++k)
+				out[12 * m + 9 + k] = t->e[k];
+		}
+		++m;
+	}
+	return m;
+	API_END(c)
+}
+
+int hcs_geom_info(const hcs_ctx *c, int geom, int info[3])
+{
+	if (!c || geom < 0 || geom >= (int)c->geoms.size() || !info)
+		return HCS_E_INVALID;
+	const HostMesh &m = c->geoms[geom].mesh;
+	info[0]           = m.plane ? 2 : (m.soft ? 1 : 0);
+	info[1]           = m.n_verts();
+	info[2]           = m.n_elems();
+	return HCS_OK;
+}
+
+int hcs_get_mesh(hcs_ctx *c, int geom, double *verts, int32_t *elems, double *pressure, double *grad, double *e0)
+{
+	API_BEGIN(c)
+	if (!c->finalized || geom < 0 || geom >= (int)c->geoms.size()) {
+		c->err = "hcs_get_mesh: finalize first";
+		return HCS_E_INVALID;
+	}
+	const GeomDev &d = c->geoms[geom].dev;
+	if (d.kind == 2)
+		return HCS_OK;
+	cudaStream_t s = c->stream;
+	if (verts)
+		CK(cudaMemcpyAsync(verts, d.verts, (size_t)d.n_verts * 3 * sizeof(double), cudaMemcpyDeviceToHost, s));
+	if (elems)
+		CK(cudaMemcpyAsync(elems, d.elems, (size_t)d.n_elems * (d.kind == 1 ? 4 : 3) * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+	if (d.kind == 1) {
+		if (pressure)
+			CK(cudaMemcpyAsync(pressure, d.pressure, (size_t)d.n_verts * sizeof(double), cudaMemcpyDeviceToHost, s));
+		std::vector<TetField> tf(d.n_elems);
+		CK(cudaMemcpyAsync(tf.data(), d.tet_field, (size_t)d.n_elems * sizeof(TetField), cudaMemcpyDeviceToHost, s));
+		CK(cudaStreamSynchronize(s));
+		for (int t = 0; t < d.n_elems; ++t) {
+			if (grad)
+				for (int k = 0; k < 3; ++k)
+					grad[3 * (size_t)t + k] = tf[t].grad[k];
+			if (e0)
+				e0[t] = tf[t].e0;
+		}
+	} else {
+		std::vector<TriRec> tr(d.n_elems);
+		CK(cudaMemcpyAsync(tr.data(), d.tris, (size_t)d.n_elems * sizeof(TriRec), cudaMemcpyDeviceToHost, s));
+		CK(cudaStreamSynchronize(s));
+		if (grad)
+			for (int t = 0; t < d.n_elems; ++t)
+				for (int k = 0; k < 3; ++k)
+					grad[3 * (size_t)t + k] = tr[t].n[k];
+	}
+	CK(cudaStreamSynchronize(s));
+	return HCS_OK;
+	API_END(c)
+}
+
+int hcs_get_counters(hcs_ctx *c, int64_t out[5])
+{
+	API_BEGIN(c)
+	if (!c->finalized || !out)
+		return HCS_E_INVALID;
+	if (!c->results_on_host)
+		fetch(c, 0);
+	int64_t cand = 0, poly = 0, faces = 0;
+	size_t n = (size_t)c->cfg.n_envs * c->pairs.size();
+	for (size_t i = 0; i < n; ++i) {
+		cand += c->h_pair[i].n_candidates;
+		poly += c->h_pair[i].n_polygons;
+		faces += c->h_pair[i].n_faces;
+	}
+	int32_t ntri = 0;
+	if (c->io.max_tris > 0) {
+		CK(cudaMemcpyAsync(&ntri, c->io.tri_count, sizeof ntri, cudaMemcpyDeviceToHost, c->stream));
+		CK(cudaStreamSynchronize(c->stream));
+	}
+	out[0] = cand, out[1] = poly, out[2] = faces, out[3] = ntri, out[4] = c->kernels_last_step;
+	return HCS_OK;
+	API_END(c)
+}
+
+int hcs_set_profiling(hcs_ctx *c, int enable)
+{
+	if (!c)
+		return HCS_E_INVALID;
+	c->profiling = enable != 0;
+	return HCS_OK;
+}
+
+int hcs_get_stage_ms(hcs_ctx *c, float out[7])
+{
+	if (!c || !out)
+		return HCS_E_INVALID;
+	for (int i = 0; i < 7; ++i)
+		out[i] = c->stage_ms[i];
+	return HCS_OK;
+}
+
+} // extern "C"

@@ -1,0 +1,124 @@
+// Internal device data layout + kernel launchers of libhcs_b200 (sm_100a).
+// All device arithmetic is compiled with -fmad=false: the classification decisions of the
+// clipping kernels (signed distance <= 0, duplicate threshold 1e-14) must reproduce the fp64
+// operation order of the restated Drake path bit for bit (DESIGN.md "Floating-point contract").
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/hcs.h"
+
+namespace hcs {
+
+// ---- resident geometry records (HBM) ---------------------------------------------------------
+// Gather records are padded to whole 32-B sectors and 16-B aligned so that one thread fetches its
+// element with double2 loads; consecutive lanes of the streaming kernels read consecutive records.
+
+struct __align__(16) TetGeom { // 128 B = one cache line: tet vertices + vertex pressures
+	double v[4][3];
+	double e[4];
+};
+struct __align__(16) TetField { // 192 B: what the tet contributes to a (tet, triangle) clip
+	double plane[4][4]; // outward unit normal + offset of faces {1,2,3},{0,3,2},{0,1,3},{0,2,1}
+	double grad[3];     // pressure gradient
+	double e0;          // pressure at the geom-frame origin
+	double ghat[3];     // normalized gradient (cull direction)
+	double pad;
+};
+struct __align__(16) TriRec { // 96 B: rigid triangle vertices + unit normal
+	double v[3][3];
+	double n[3];
+};
+struct __align__(16) BvhNode { // 64 B: both children's boxes live in the parent
+	float llo[3], lhi[3], rlo[3], rhi[3];
+	int32_t left, right; // >= 0 internal node, < 0 leaf holding element ~child
+	float pad[2];
+};
+
+struct GeomDev {
+	int kind; // 0 rigid mesh, 1 soft, 2 plane
+	int n_verts, n_elems;
+	double *verts;      // [nv][3]
+	int32_t *elems;     // [ne][4|3]
+	double *pressure;   // [nv]
+	TetGeom *tet_geom;  // soft
+	TetField *tet_field;
+	TriRec *tris;       // rigid
+	BvhNode *nodes;     // soft: LBVH over tets (root = node 0)
+	double bound_c[3];  // bounding sphere in the geom frame
+	double bound_r;
+};
+
+enum PairKind { PAIR_NONE = 0, PAIR_SOFT_RIGID = 1, PAIR_SOFT_PLANE = 2, PAIR_SOFT_SOFT = 3 };
+
+struct SlicePartial { // one warp's deterministic partial sums
+	double F[3], tau[3], area, ac[3];
+	int32_t n_polygons, n_faces, n_points, n_candidates;
+};
+
+struct TactileTri { // kTriangle contact-surface triangle handed to the tactile stage (72 B)
+	float v[9];
+	int32_t env;
+	double e[3];
+	int32_t pair, order; // order = deterministic key inside (env, pair)
+};
+
+// Everything a step kernel needs to know about one configured geom pair (passed by value).
+struct PairDesc {
+	int kind;
+	int index;           // pair index inside the scene
+	int gA, gB;          // gA: soft geom whose frame hosts the computation; gB: the other one
+	int gM, gN;          // min / max configuration index
+	double sign;         // +1 when gA == gM, -1 otherwise (ContactSurface M/N swap)
+	double dissipation;  // calcCombinedDissipation (plugin.cpp:138-159)
+	double mu;           // combined dynamic friction
+	int nq, n_tree;      // query elements (of gB) / tree elements (tets of gA); plane: nq = tets of gA
+	int n_slices, slice_q, cap;
+	int emit_tactile;    // pair touches a sensor geom and representation is kTriangle
+	GeomDev A, B;
+	uint2 *slab;           // [n_env * n_slices][cap] candidates (query, tree element)
+	int32_t *slab_count;   // [n_env * n_slices]
+	uint8_t *slab_nverts;  // [n_env * n_slices][cap] polygon vertex count per candidate (plane: per tet)
+	SlicePartial *partial; // [n_env * n_slices]
+};
+
+struct StepIO {
+	int n_env, n_geoms, n_pairs;
+	const double *xpos, *xmat, *vel;
+	int representation, apply_forces;
+	int32_t *flags;          // [0] capacity overflow bits, [1] traversal stack overflow
+	hcs_face *faces;         // optional per-face dump
+	int32_t *face_count;
+	int max_faces;
+	TactileTri *tri_pool;
+	int32_t *tri_count;
+	int max_tris;
+	hcs_pair_result *pair_out; // [n_env][n_pairs]
+	double *geom_wrench;       // [n_env][n_geoms][6]
+};
+
+struct SensorDev {
+	int geom, cx, cy, S, window;
+	float sigma;
+	double resolution;
+	double size[3];
+	float rmean, rS;
+	const float *weights; // [S*S] window weights
+	float *image;         // [n_env][cx*cy]
+	int32_t *bin_count;   // [n_env][cx*cy]
+	int32_t *bin_items;   // [n_env][cx*cy][bin_cap]
+	int bin_cap;
+};
+
+// ---- launchers (definitions in the .cu files) ---------------------------------------------------
+void launch_build_tets(const GeomDev &g, cudaStream_t s);
+void launch_build_tris(const GeomDev &g, cudaStream_t s);
+
+void launch_broadphase(const PairDesc &P, const StepIO &io, cudaStream_t s);
+void launch_narrowphase(const PairDesc &P, const StepIO &io, cudaStream_t s);
+void launch_finalize(const PairDesc *d_pairs, const StepIO &io, cudaStream_t s);
+
+// clear bins, bin the triangle pool, rasterise: 3 kernels
+void launch_tactile(const SensorDev &sd, const StepIO &io, const PairDesc *d_pairs, cudaStream_t s);
+
+} // namespace hcs

@@ -1,0 +1,92 @@
+// K1 build_fields — per-element derived data, built once at hcs_finalize (and hcs_update_geom).
+// Replaces the Drake VolumeMeshFieldLinear constructor (CalcGradBarycentric, value at mesh origin)
+// and TriangleSurfaceMesh face normals the reference gets at plugin.cpp:654-662, and hoists the
+// per-candidate half-space construction of mesh_intersection.cc ClipTriangleByTetrahedron
+// (normal = (B-A)x(C-A), normalized; d = nhat.A) out of the step: those values depend on the tet
+// only, so precomputing them is bit-identical to recomputing them per candidate.
+// Streaming kernel: one thread per element, 128..192-B records written with full-sector stores.
+#include "dmath.cuh"
+#include "hcs_internal.h"
+
+namespace hcs {
+
+__global__ void __launch_bounds__(128) build_tets_kernel(GeomDev g)
+{
+	int t = blockIdx.x * blockDim.x + threadIdx.x;
+	if (t >= g.n_elems)
+		return;
+	int4 idx = reinterpret_cast<const int4 *>(g.elems)[t];
+	int vi[4] = { idx.x, idx.y, idx.z, idx.w };
+	D3 v[4];
+	double e[4];
+#pragma unroll
+	for (int i = 0; i < 4; ++i) {
+		v[i] = ld3(g.verts + 3 * (size_t)vi[i]);
+		e[i] = g.pressure[vi[i]];
+	}
+	TetGeom tg;
+#pragma unroll
+	for (int i = 0; i < 4; ++i) {
+		tg.v[i][0] = v[i].x, tg.v[i][1] = v[i].y, tg.v[i][2] = v[i].z;
+		tg.e[i] = e[i];
+	}
+	g.tet_geom[t] = tg;
+
+	TetField tf;
+	// gradient: sum_i e_i * grad(b_i), grad(b_i) = (AB x AC) / ((AB x AC) . AV), A,B,C = vertices i+1,i+2,i+3
+	D3 grad = mk(0, 0, 0);
+#pragma unroll
+	for (int i = 0; i < 4; ++i) {
+		D3 V = v[i], A = v[(i + 1) & 3], B = v[(i + 2) & 3], C = v[(i + 3) & 3];
+		D3 area_vec = cross(B - A, C - A);
+		double sv   = dot(area_vec, V - A);
+		D3 gb       = area_vec / sv;
+		grad        = i == 0 ? e[0] * gb : grad + e[i] * gb;
+	}
+	tf.grad[0] = grad.x, tf.grad[1] = grad.y, tf.grad[2] = grad.z;
+	tf.e0 = e[0] - dot(grad, v[0]);
+	D3 gh = normalized(grad);
+	tf.ghat[0] = gh.x, tf.ghat[1] = gh.y, tf.ghat[2] = gh.z;
+	tf.pad = 0;
+	const int F[4][3] = { { 1, 2, 3 }, { 0, 3, 2 }, { 0, 1, 3 }, { 0, 2, 1 } };
+#pragma unroll
+	for (int k = 0; k < 4; ++k) {
+		D3 A = v[F[k][0]], B = v[F[k][1]], C = v[F[k][2]];
+		D3 n = normalized(cross(B - A, C - A));
+		tf.plane[k][0] = n.x, tf.plane[k][1] = n.y, tf.plane[k][2] = n.z;
+		tf.plane[k][3] = dot(n, A);
+	}
+	g.tet_field[t] = tf;
+}
+
+__global__ void __launch_bounds__(128) build_tris_kernel(GeomDev g)
+{
+	int t = blockIdx.x * blockDim.x + threadIdx.x;
+	if (t >= g.n_elems)
+		return;
+	TriRec r;
+	D3 v[3];
+#pragma unroll
+	for (int i = 0; i < 3; ++i) {
+		v[i]      = ld3(g.verts + 3 * (size_t)g.elems[3 * (size_t)t + i]);
+		r.v[i][0] = v[i].x, r.v[i][1] = v[i].y, r.v[i][2] = v[i].z;
+	}
+	D3 cr     = cross(v[1] - v[0], v[2] - v[0]);
+	double nn = sqrt(dot(cr, cr));
+	D3 n      = nn != 0.0 ? cr / nn : cr;
+	r.n[0] = n.x, r.n[1] = n.y, r.n[2] = n.z;
+	g.tris[t] = r;
+}
+
+void launch_build_tets(const GeomDev &g, cudaStream_t s)
+{
+	if (g.n_elems > 0)
+		build_tets_kernel<<<(g.n_elems + 127) / 128, 128, 0, s>>>(g);
+}
+void launch_build_tris(const GeomDev &g, cudaStream_t s)
+{
+	if (g.n_elems > 0)
+		build_tris_kernel<<<(g.n_elems + 127) / 128, 128, 0, s>>>(g);
+}
+
+} // namespace hcs

@@ -1,0 +1,227 @@
+"""Synthetic scenes of the shapes BASELINE.json names, engine-agnostic.
+
+A scene is plain data: geoms in CONFIGURATION ORDER (the order of the `cs::<geom>` numerics in the
+MuJoCo XML = drake_id order), the geom pairs MuJoCo's collision pass would hand to collision_cb, flat
+sensors, and a seeded pose generator.  `configure()` feeds the same call sequence to any object with the
+add_geom / set_pairs / add_flat_sensor surface (the CUDA engine, or the CPU oracle inside tests/bench).
+MuJoCo itself is absent in this environment, so poses come from these generators instead of mj_step.
+"""
+import os
+
+import numpy as np
+
+GEOM_PLANE, GEOM_HFIELD, GEOM_SPHERE, GEOM_CAPSULE, GEOM_ELLIPSOID, GEOM_CYLINDER, GEOM_BOX, GEOM_MESH = range(8)
+
+_FIXTURES = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tests", "golden")
+
+
+class Geom:
+    def __init__(self, name, mj_type, size, props, mesh_vert=None, mesh_face=None):
+        self.name, self.mj_type = name, mj_type
+        self.size = np.resize(np.asarray(size, dtype=np.float64), 3)
+        self.props = np.asarray(props, dtype=np.float64)  # [E, dissipation, hint, mu_s, mu_d]
+        self.mesh_vert, self.mesh_face = mesh_vert, mesh_face
+
+
+class Scene:
+    def __init__(self, name, geoms, pairs, triangle=False, sensors=(), apply_forces=True):
+        self.name, self.geoms, self.pairs = name, geoms, [tuple(p) for p in pairs]
+        self.triangle, self.sensors, self.apply_forces = triangle, list(sensors), apply_forces
+        self.pose_fn = None
+
+    @property
+    def n_geoms(self):
+        return len(self.geoms)
+
+    def poses(self, n_envs, seed, env_offset=0):
+        """xpos[n,ng,3], xmat[n,ng,9], vel[n,ng,6] for envs env_offset .. env_offset+n-1 (per-env RNG streams,
+        so a shard of envs sees exactly the poses the full batch would)."""
+        ng = self.n_geoms
+        xpos, xmat, vel = np.zeros((n_envs, ng, 3)), np.zeros((n_envs, ng, 9)), np.zeros((n_envs, ng, 6))
+        for e in range(n_envs):
+            rng = np.random.Generator(np.random.PCG64([seed, env_offset + e]))
+            self.pose_fn(rng, env_offset + e, xpos[e], xmat[e], vel[e])
+        return xpos, xmat, vel
+
+
+def configure(target, scene):
+    """Replay the scene's configuration calls on an engine-like object; returns its geom indices."""
+    ids = []
+    for g in scene.geoms:
+        ids.append(target.add_geom(g.mj_type, g.size, g.props, g.mesh_vert, g.mesh_face))
+    target.set_pairs([(ids[a], ids[b]) for a, b in scene.pairs])
+    for s in scene.sensors:
+        kw = dict(resolution=s["resolution"], sampling_resolution=s["sampling_resolution"],
+                  window=s.get("window", 0), sigma=s.get("sigma", -1.0))
+        if hasattr(target, "orc_needs_geom_size") or target.__class__.__name__ == "OracleScene":
+            target.add_flat_sensor(ids[s["geom"]], scene.geoms[s["geom"]].size, **kw)
+        else:
+            target.add_flat_sensor(ids[s["geom"]], **kw)
+    return ids
+
+
+# ---- helpers ------------------------------------------------------------------------------------------
+def random_rotation(rng):
+    q = rng.normal(size=4)
+    q /= np.linalg.norm(q)
+    w, x, y, z = q
+    return np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)],
+                     [2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)],
+                     [2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)]])
+
+
+def rot_zyx(yaw, pitch, roll):
+    cz, sz, cy, sy, cx, sx = np.cos(yaw), np.sin(yaw), np.cos(pitch), np.sin(pitch), np.cos(roll), np.sin(roll)
+    Rz = np.array([[cz, -sz, 0], [sz, cz, 0], [0, 0, 1]])
+    Ry = np.array([[cy, 0, sy], [0, 1, 0], [-sy, 0, cy]])
+    Rx = np.array([[1, 0, 0], [0, cx, -sx], [0, sx, cx]])
+    return Rz @ Ry @ Rx
+
+
+def random_velocity(rng, vmax, wmax):
+    def ball(r):
+        d = rng.normal(size=3)
+        return d / np.linalg.norm(d) * r * rng.uniform() ** (1 / 3)
+    return np.concatenate([ball(wmax), ball(vmax)])  # (omega, v) like mj_objectVelocity
+
+
+def load_mesh_fixture(name):
+    """Meshes of the reference's example worlds, stored as de-duplicated float32 vertex / int32 face
+    arrays (tests/golden/make_mesh_fixtures.py generated them from the reference assets)."""
+    d = np.load(os.path.join(_FIXTURES, "meshes.npz"))
+    return d[name + "_vert"].astype(np.float32), d[name + "_face"].astype(np.int32)
+
+
+def box_surface_vertices(half, hint):
+    n = [max(1, int(np.ceil(2 * h / hint))) for h in half]
+    axes = [np.linspace(-h, h, k + 1) for h, k in zip(half, n)]
+    g = np.stack(np.meshgrid(*axes, indexing="ij"), -1).reshape(-1, 3)
+    return g
+
+
+# ---- C1: soft sphere on rigid box (CS/assets/sphere_on_box_world.xml:22-41) ----------------------------
+def sphere_on_box(identity_orientation=False):
+    geoms = [Geom("box0", GEOM_BOX, [0.1, 0.1, 0.1], [0, 1.0, 0.1, 0.3, 0.3]),
+             Geom("sphere0", GEOM_SPHERE, [0.08], [5e4, 5.0, 0.05, 0.3, 0.3])]
+    # mj_collideGeoms orders a pair by geom type (sphere=2 < box=6): collision_cb(g1=sphere0, g2=box0)
+    sc = Scene("c1_sphere_on_box", geoms, [(1, 0)], triangle=False)
+    depths = [0.001, 0.005, 0.012, 0.03]
+
+    def pose(rng, env, xpos, xmat, vel):
+        d = depths[env % 4]
+        dx, dy = rng.uniform(-0.05, 0.05, size=2)
+        xpos[0] = [0, 0, 0.1]
+        xmat[0] = np.eye(3).reshape(-1)
+        xpos[1] = [dx, dy, 0.2 + 0.08 - d]
+        R = np.eye(3) if identity_orientation else random_rotation(rng)
+        xmat[1] = R.reshape(-1)
+        vel[1] = random_velocity(rng, 0.1, 1.0)
+
+    sc.pose_fn = pose
+    return sc
+
+
+# ---- C2: Myrmex foam pressed by a rigid object, 16x16 taxel image (SENS/assets/myrmex_*_world.xml) ------
+def myrmex(presser="box", sampling_resolution=20, window=0, sigma=-1.0, resolution=0.025):
+    if presser == "box":
+        pg = Geom("box1", GEOM_BOX, [0.1, 0.1, 0.1], [0, 1.0, 0.05, 0.3, 0.3])
+        pverts = box_surface_vertices([0.1, 0.1, 0.1], 0.05)
+    elif presser == "plate":
+        v, f = load_mesh_fixture("plate")
+        pg, pverts = Geom("plate", GEOM_MESH, [0, 0, 0], [0, 1.0, 0, 0.3, 0.3], v, f), v.astype(np.float64)
+    elif presser == "spot":
+        v, f = load_mesh_fixture("spot")
+        v = (v * np.float32(0.05)).astype(np.float32)
+        pg, pverts = Geom("spot", GEOM_MESH, [0, 0, 0], [0, 1.0, 0, 0.3, 0.3], v, f), v.astype(np.float64)
+    else:
+        raise ValueError(presser)
+    foam = Geom("myrmex_foam", GEOM_BOX, [0.2, 0.2, 0.02], [5e4, 5.0, 0, 0.3, 0.3])
+    sensors = [dict(geom=1, resolution=resolution, sampling_resolution=sampling_resolution, window=window, sigma=sigma)]
+    sc = Scene("c2_myrmex_" + presser, [pg, foam], [(0, 1)], triangle=True, sensors=sensors)
+    foam_top = 0.033 + 0.02
+
+    def pose(rng, env, xpos, xmat, vel):
+        depth = rng.uniform(0.0005, 0.005)
+        tilt = np.deg2rad(rng.uniform(-2, 2, size=2))
+        yaw = rng.uniform(0, 2 * np.pi)
+        R = rot_zyx(yaw, tilt[0], tilt[1])
+        lowest = (pverts @ R.T)[:, 2].min()
+        xy = rng.uniform(-0.05, 0.05, size=2)
+        xpos[0] = [xy[0], xy[1], foam_top - depth - lowest]
+        xmat[0] = R.reshape(-1)
+        vel[0] = random_velocity(rng, 0.05, 0.5)
+        xpos[1] = [0, 0, 0.033]
+        xmat[1] = np.eye(3).reshape(-1)
+
+    sc.pose_fn = pose
+    return sc
+
+
+# ---- C3: two soft ellipsoids, equal-pressure-plane intersection -----------------------------------------
+def soft_soft(hint=0.01, triangle=False):
+    a, b = np.array([0.05, 0.04, 0.03]), np.array([0.04, 0.04, 0.06])
+    geoms = [Geom("ell0", GEOM_ELLIPSOID, a, [5e4, 5.0, hint, 0.3, 0.3]),
+             Geom("ell1", GEOM_ELLIPSOID, b, [1e5, 2.0, hint, 0.4, 0.2])]
+    sc = Scene("c3_soft_soft", geoms, [(0, 1)], triangle=triangle)
+
+    def support(axes, R, d):  # centre-to-surface distance of the rotated ellipsoid along direction d
+        return 1.0 / np.linalg.norm((R.T @ d) / axes)
+
+    def pose(rng, env, xpos, xmat, vel):
+        R0, R1 = random_rotation(rng), random_rotation(rng)
+        d = rng.normal(size=3)
+        d /= np.linalg.norm(d)
+        overlap = rng.uniform(0.001, 0.005)
+        dist = support(a, R0, d) + support(b, R1, d) - overlap
+        c0 = rng.uniform(-0.1, 0.1, size=3) + [0, 0, 0.3]
+        xpos[0], xmat[0] = c0, R0.reshape(-1)
+        xpos[1], xmat[1] = c0 + dist * d, R1.reshape(-1)
+        vel[0], vel[1] = random_velocity(rng, 0.2, 2.0), random_velocity(rng, 0.2, 2.0)
+
+    sc.pose_fn = pose
+    return sc
+
+
+# ---- C4: mixed soft objects dropped on a rigid plane ------------------------------------------------------
+def objects_on_plane(triangle=False):
+    tip_v, tip_f = load_mesh_fixture("ubi_tip")
+    tip_v = (tip_v * np.float32(0.001)).astype(np.float32)  # the STL is in millimetres
+    geoms = [Geom("ground", GEOM_PLANE, [0, 0, 1], [0, 1.0, 0, 0.5, 0.5]),
+             Geom("sphere", GEOM_SPHERE, [0.05], [5e4, 5.0, 0.025, 0.3, 0.3]),
+             Geom("ellipsoid", GEOM_ELLIPSOID, [0.06, 0.04, 0.03], [8e4, 3.0, 0.015, 0.3, 0.3]),
+             Geom("box", GEOM_BOX, [0.05, 0.04, 0.03], [6e4, 4.0, 0, 0.3, 0.3]),
+             Geom("tip", GEOM_MESH, [0, 0, 0], [1e5, 2.0, 0, 0.6, 0.6], tip_v, tip_f)]
+    # plane (type 0) comes first in MuJoCo's pair order
+    sc = Scene("c4_objects_on_plane", geoms, [(0, 1), (0, 2), (0, 3), (0, 4)], triangle=triangle)
+    extents = [None, np.full(3, 0.05), np.array([0.06, 0.04, 0.03]), None, None]
+    box_corners = np.array([[sx * 0.05, sy * 0.04, sz * 0.03] for sx in (-1, 1) for sy in (-1, 1) for sz in (-1, 1)])
+    tip = tip_v.astype(np.float64)
+
+    def pose(rng, env, xpos, xmat, vel):
+        xmat[0] = np.eye(3).reshape(-1)
+        for g in range(1, 5):
+            R = random_rotation(rng)
+            if g in (1, 2):
+                low, size = -np.linalg.norm(extents[g] * R[2]), 2 * extents[g].min()
+            elif g == 3:
+                low, size = (box_corners @ R.T)[:, 2].min(), 0.06
+            else:
+                z = (tip @ R.T)[:, 2]
+                low, size = z.min(), z.max() - z.min()
+            depth = rng.uniform(0, 0.2 * size)
+            xpos[g] = [rng.uniform(-1, 1), rng.uniform(-1, 1), -low - depth]
+            xmat[g] = R.reshape(-1)
+            vel[g] = random_velocity(rng, 0.5, 5.0)
+
+    sc.pose_fn = pose
+    return sc
+
+
+SCENES = {
+    "c1_sphere_on_box": sphere_on_box,
+    "c2_myrmex_box": lambda: myrmex("box"),
+    "c2_myrmex_plate": lambda: myrmex("plate"),
+    "c2_myrmex_spot": lambda: myrmex("spot"),
+    "c3_soft_soft": soft_soft,
+    "c4_objects_on_plane": objects_on_plane,
+}

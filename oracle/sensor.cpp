@@ -1,0 +1,455 @@
+// CPU ORACLE (test infrastructure, parity unpinned) — Myrmex flat tactile sensor.
+//
+// Restates mujoco_contact_surface_sensors/src/flat_tactile_sensor.cpp:127-214 (load constants),
+// :262-402 (bvh_update) and the float32 ray caster of src/bvh.cpp:49-476 +
+// include/mujoco_contact_surface_sensors/bvh.h:157-176 (scalar, non-SSE code path).
+// The mixed float/double arithmetic of the reference is reproduced operation by operation
+// (SURVEY.md App. B.3/B.4).  Deviation noted in DESIGN.md (Q16): mju_rotVecMat(pos,pos,rot) is
+// evaluated alias-safe (the mathematically intended rotation).
+#include "oracle.hpp"
+
+#include <algorithm>
+#include <cstring>
+
+namespace orc {
+
+namespace {
+
+struct F3 {
+	float x, y, z;
+	float operator[](int i) const { return i == 0 ? x : (i == 1 ? y : z); }
+};
+inline F3 operator-(F3 a, F3 b) { return { a.x - b.x, a.y - b.y, a.z - b.z }; }
+inline F3 operator+(F3 a, F3 b) { return { a.x + b.x, a.y + b.y, a.z + b.z }; }
+inline F3 operator*(F3 a, float b) { return { a.x * b, a.y * b, a.z * b }; }
+inline F3 operator-(F3 a) { return { -a.x, -a.y, -a.z }; }
+inline F3 crossf(F3 a, F3 b) { return { a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x }; }
+inline float dotf(F3 a, F3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; } // float3.h: left to right
+inline float fmin_(float a, float b) { return a < b ? a : b; }
+inline float fmax_(float a, float b) { return a > b ? a : b; }
+inline F3 fmin3(F3 a, F3 b) { return { fmin_(a.x, b.x), fmin_(a.y, b.y), std::fmin(a.z, b.z) }; }
+inline F3 fmax3(F3 a, F3 b) { return { fmax_(a.x, b.x), fmax_(a.y, b.y), std::fmax(a.z, b.z) }; }
+
+struct Tri {
+	F3 v0, v1, v2, centroid;
+};
+struct Ray {
+	F3 O, D, rD;
+	float t, u, v;
+	unsigned hit; // (blas << 20) + triangle
+};
+
+// bvh.cpp:49-74
+inline void intersect_triangle(Ray &ray, const Tri &tri, unsigned id)
+{
+	F3 edge1 = tri.v1 - tri.v0, edge2 = tri.v2 - tri.v0;
+	F3 h    = crossf(ray.D, edge2);
+	float a = dotf(edge1, h);
+	if (std::fabs(a) < 1e-10f)
+		return;
+	float f = 1.0f / a;
+	F3 s    = ray.O - tri.v0;
+	float u = f * dotf(s, h);
+	if (u < 0.0f || u > 1.0f)
+		return;
+	F3 q    = crossf(s, edge1);
+	float v = f * dotf(ray.D, q);
+	if (v < 0.0f || u + v > 1.0f)
+		return;
+	float t = f * dotf(edge2, q);
+	if (t < ray.t && t > 0.0f) {
+		ray.t   = t;
+		ray.u   = u;
+		ray.v   = v;
+		ray.hit = id;
+	}
+}
+
+// bvh.h:157-176
+inline float intersect_aabb(const Ray &ray, F3 bmin, F3 bmax)
+{
+	float tx1 = (bmin.x - ray.O.x) * ray.rD.x, tx2 = (bmax.x - ray.O.x) * ray.rD.x;
+	float tmin = std::min(tx1, tx2), tmax = std::max(tx1, tx2);
+	float ty1 = (bmin.y - ray.O.y) * ray.rD.y, ty2 = (bmax.y - ray.O.y) * ray.rD.y;
+	tmin      = std::max(tmin, std::min(ty1, ty2));
+	tmax      = std::min(tmax, std::max(ty1, ty2));
+	float tz1 = (bmin.z - ray.O.z) * ray.rD.z, tz2 = (bmax.z - ray.O.z) * ray.rD.z;
+	tmin      = std::max(tmin, std::min(tz1, tz2));
+	tmax      = std::min(tmax, std::max(tz1, tz2));
+	if (tmax >= tmin && tmin < ray.t && tmax > 0)
+		return tmin;
+	return 1e30f;
+}
+
+struct Node {
+	F3 mn;
+	unsigned left_first;
+	F3 mx;
+	unsigned count;
+};
+inline float area_of(F3 mn, F3 mx)
+{
+	F3 s = mx - mn;
+	return s.x * s.y + s.x * s.z + s.y * s.z;
+}
+
+const int BINS = 8;
+
+// bvh.cpp:90-357: binned-SAH BLAS over the float32 copy of one contact surface
+struct Blas {
+	std::vector<Tri> tri;
+	std::vector<unsigned> idx;
+	std::vector<Node> node;
+	unsigned used = 2;
+	F3 bmin, bmax;
+	const Surface *surface = nullptr;
+
+	void update_bounds(unsigned ni, F3 &cmin, F3 &cmax)
+	{
+		Node &n = node[ni];
+		n.mn    = { 1e30f, 1e30f, 1e30f };
+		n.mx    = { -1e30f, -1e30f, -1e30f };
+		cmin    = n.mn;
+		cmax    = n.mx;
+		for (unsigned i = 0; i < n.count; ++i) {
+			const Tri &t = tri[idx[n.left_first + i]];
+			n.mn         = fmin3(fmin3(fmin3(n.mn, t.v0), t.v1), t.v2);
+			n.mx         = fmax3(fmax3(fmax3(n.mx, t.v0), t.v1), t.v2);
+			cmin         = fmin3(cmin, t.centroid);
+			cmax         = fmax3(cmax, t.centroid);
+		}
+	}
+	float best_split(const Node &n, int &axis, int &split, F3 cmin, F3 cmax)
+	{
+		float best = 1e30f;
+		for (int a = 0; a < 3; ++a) {
+			float bmn = cmin[a], bmx = cmax[a];
+			float scale = BINS / (bmx - bmn);
+			struct Bin {
+				F3 mn{ 1e30f, 1e30f, 1e30f }, mx{ -1e30f, -1e30f, -1e30f };
+				int count = 0;
+			} bin[BINS];
+			for (unsigned i = 0; i < n.count; ++i) {
+				const Tri &t = tri[idx[n.left_first + i]];
+				int b        = std::max(std::min(BINS - 1, (int)((t.centroid[a] - bmn) * scale)), 0);
+				bin[b].count++;
+				bin[b].mn = fmin3(fmin3(fmin3(bin[b].mn, t.v0), t.v1), t.v2);
+				bin[b].mx = fmax3(fmax3(fmax3(bin[b].mx, t.v0), t.v1), t.v2);
+			}
+			float la[BINS - 1], ra[BINS - 1];
+			F3 lmn{ 1e30f, 1e30f, 1e30f }, lmx{ -1e30f, -1e30f, -1e30f }, rmn = lmn, rmx = lmx;
+			int ls = 0, rs = 0;
+			for (int i = 0; i < BINS - 1; ++i) {
+				ls += bin[i].count;
+				if (bin[i].mn.x != 1e30f) {
+					lmn = fmin3(fmin3(lmn, bin[i].mn), bin[i].mx);
+					lmx = fmax3(fmax3(lmx, bin[i].mn), bin[i].mx);
+				}
+				la[i] = area_of(lmn, lmx) * ls;
+				rs += bin[BINS - 1 - i].count;
+				if (bin[BINS - 1 - i].mn.x != 1e30f) {
+					rmn = fmin3(fmin3(rmn, bin[BINS - 1 - i].mn), bin[BINS - 1 - i].mx);
+					rmx = fmax3(fmax3(rmx, bin[BINS - 1 - i].mn), bin[BINS - 1 - i].mx);
+				}
+				ra[BINS - 2 - i] = area_of(rmn, rmx) * rs;
+			}
+			for (int i = 0; i < BINS - 1; ++i) {
+				float cost = la[i] + ra[i];
+				if (cost < best) {
+					best  = cost;
+					axis  = a;
+					split = i + 1;
+				}
+			}
+		}
+		return best;
+	}
+	void subdivide(unsigned ni, F3 cmin, F3 cmax)
+	{
+		int axis = 0, split = 0;
+		float cost   = best_split(node[ni], axis, split, cmin, cmax);
+		float nosplit = area_of(node[ni].mn, node[ni].mx) * node[ni].count;
+		if (cost >= nosplit)
+			return;
+		int i = node[ni].left_first, j = i + node[ni].count - 1;
+		float scale = BINS / (cmax[axis] - cmin[axis]);
+		while (i <= j) {
+			int b = std::min(BINS - 1, (int)((tri[idx[i]].centroid[axis] - cmin[axis]) * scale));
+			if (b < split)
+				i++;
+			else
+				std::swap(idx[i], idx[j--]);
+		}
+		unsigned left_count = i - node[ni].left_first;
+		if (left_count == 0 || left_count == node[ni].count)
+			return;
+		unsigned l = used++, r = used++;
+		node[l].left_first  = node[ni].left_first;
+		node[l].count       = left_count;
+		node[r].left_first  = i;
+		node[r].count       = node[ni].count - left_count;
+		node[ni].left_first = l;
+		node[ni].count      = 0;
+		F3 cmn, cmx;
+		update_bounds(l, cmn, cmx);
+		subdivide(l, cmn, cmx);
+		update_bounds(r, cmn, cmx);
+		subdivide(r, cmn, cmx);
+	}
+	void build(const Surface &s)
+	{
+		surface = &s;
+		int n   = s.num_faces();
+		tri.resize(n);
+		idx.resize(n);
+		for (int i = 0; i < n; ++i) {
+			const int *f = &s.face_idx[s.face_first[i]];
+			auto cvt     = [&](int v) { return F3{ (float)s.v[v].x, (float)s.v[v].y, (float)s.v[v].z }; };
+			tri[i].v0 = cvt(f[0]);
+			tri[i].v1 = cvt(f[1]);
+			tri[i].v2 = cvt(f[2]);
+			tri[i].centroid = ((tri[i].v0 + tri[i].v1) + tri[i].v2) * 0.3333f;
+			idx[i]          = i;
+		}
+		node.assign(2 * std::max(n, 1), Node{ { 0, 0, 0 }, 0, { 0, 0, 0 }, 0 });
+		used               = 2;
+		node[0].left_first = 0;
+		node[0].count      = n;
+		F3 cmn, cmx;
+		update_bounds(0, cmn, cmx);
+		subdivide(0, cmn, cmx);
+		bmin = node[0].mn;
+		bmax = node[0].mx;
+	}
+	void intersect(Ray &ray, unsigned blas_idx) const
+	{
+		const Node *n = &node[0], *stack[64];
+		unsigned sp   = 0;
+		while (true) {
+			if (n->count > 0) {
+				for (unsigned i = 0; i < n->count; ++i)
+					intersect_triangle(ray, tri[idx[n->left_first + i]], (blas_idx << 20) + idx[n->left_first + i]);
+				if (sp == 0)
+					break;
+				n = stack[--sp];
+				continue;
+			}
+			const Node *c1 = &node[n->left_first], *c2 = &node[n->left_first + 1];
+			float d1 = intersect_aabb(ray, c1->mn, c1->mx), d2 = intersect_aabb(ray, c2->mn, c2->mx);
+			if (d1 > d2) {
+				std::swap(c1, c2);
+				std::swap(d1, d2);
+			}
+			if (d1 == 1e30f) {
+				if (sp == 0)
+					break;
+				n = stack[--sp];
+			} else {
+				n = c1;
+				if (d2 != 1e30f)
+					stack[sp++] = c2;
+			}
+		}
+	}
+};
+
+// bvh.cpp:359-476: agglomerative TLAS over the BLAS bounds
+struct Tlas {
+	struct TNode {
+		F3 mn;
+		unsigned left_right;
+		F3 mx;
+		unsigned blas;
+	};
+	std::vector<TNode> node;
+	const std::vector<Blas> *blas = nullptr;
+
+	void build(const std::vector<Blas> &b)
+	{
+		blas  = &b;
+		int n = (int)b.size();
+		node.assign(2 * n + 2, TNode{ { 0, 0, 0 }, 0, { 0, 0, 0 }, 0 });
+		std::vector<unsigned> ni(n);
+		unsigned used = 1;
+		for (int i = 0; i < n; ++i) {
+			ni[i]                 = used;
+			node[used].mn         = b[i].bmin;
+			node[used].mx         = b[i].bmax;
+			node[used].blas       = i;
+			node[used].left_right = 0;
+			used++;
+		}
+		auto best_match = [&](int N, int A) {
+			float smallest = 1e30f;
+			int best       = -1;
+			for (int B = 0; B < N; ++B)
+				if (B != A) {
+					F3 mx = fmax3(node[ni[A]].mx, node[ni[B]].mx), mn = fmin3(node[ni[A]].mn, node[ni[B]].mn);
+					float sa = area_of(mn, mx);
+					if (sa < smallest)
+						smallest = sa, best = B;
+				}
+			return best;
+		};
+		int cnt = n, A = 0, B = n > 1 ? best_match(cnt, A) : -1;
+		while (cnt > 1) {
+			int C = best_match(cnt, B);
+			if (A == C) {
+				unsigned ia = ni[A], ib = ni[B];
+				node[used].left_right = ia + (ib << 16);
+				node[used].mn         = fmin3(node[ia].mn, node[ib].mn);
+				node[used].mx         = fmax3(node[ia].mx, node[ib].mx);
+				ni[A]                 = used++;
+				ni[B]                 = ni[cnt - 1];
+				B                     = best_match(--cnt, A);
+			} else {
+				A = B;
+				B = C;
+			}
+		}
+		node[0] = node[ni[A]];
+	}
+	void intersect(Ray &ray) const
+	{
+		ray.rD = { 1.0f / ray.D.x, 1.0f / ray.D.y, 1.0f / ray.D.z };
+		const TNode *n = &node[0], *stack[64];
+		unsigned sp    = 0;
+		while (true) {
+			if (n->left_right == 0) {
+				(*blas)[n->blas].intersect(ray, n->blas);
+				if (sp == 0)
+					break;
+				n = stack[--sp];
+				continue;
+			}
+			const TNode *c1 = &node[n->left_right & 0xffff], *c2 = &node[n->left_right >> 16];
+			float d1 = intersect_aabb(ray, c1->mn, c1->mx), d2 = intersect_aabb(ray, c2->mn, c2->mx);
+			if (d1 > d2) {
+				std::swap(c1, c2);
+				std::swap(d1, d2);
+			}
+			if (d1 == 1e30f) {
+				if (sp == 0)
+					break;
+				n = stack[--sp];
+			} else {
+				n = c1;
+				if (d2 != 1e30f)
+					stack[sp++] = c2;
+			}
+		}
+	}
+};
+
+const float SQRT_2f = 1.41421356237; // flat_tactile_sensor.h:47 (float)
+
+} // namespace
+
+// flat_tactile_sensor.cpp:262-402 bvh_update.  use_bvh=false replaces the TLAS/BLAS traversal by a
+// linear scan over all triangles in surface order (same Möller–Trumbore arithmetic, same strict
+// `t < hit.t` rule) and is used to bound tie-breaking effects.
+void flat_sensor_image(const Scene &sc, const StepState &st, int sensor, float *out, bool use_bvh, bool parallel)
+{
+	const FlatSensor &fs = sc.sensors[sensor];
+	int id = fs.geom, cx = fs.cx, cy = fs.cy, S = fs.S;
+	float xs = (float)fs.size[0], ys = (float)fs.size[1], zs = (float)fs.size[2];
+	double resolution = fs.resolution;
+	// load(): :179-185
+	float di_factor     = resolution / S;
+	float sub_halfwidth = di_factor / 2.0f - resolution / 2.0f;
+	float rmean         = 1. / (S * S);
+	float rS            = resolution / S;
+	float max_dist      = SQRT_2f * resolution / 2.0f;
+	float sigma         = fs.sigma;
+	bool use_gaussian = fs.window == 1, use_tukey = fs.window == 2, use_square = fs.window == 3;
+
+	double rot[9];
+	std::memcpy(rot, &st.xmat[9 * id], sizeof(rot));
+	F3 sensor_normal{ (float)rot[2], (float)rot[5], (float)rot[8] };
+	double sensor_xpos[3]    = { st.xpos[3 * id], st.xpos[3 * id + 1], st.xpos[3 * id + 2] };
+	double sensor_topleft[3] = { -xs, -ys, zs };
+
+	std::fill(out, out + cx * cy, 0.0f);
+	std::vector<Blas> blas;
+	for (const PairOut &po : st.out)
+		if (po.has_surface && (po.gM == id || po.gN == id) && po.s->tri)
+			blas.emplace_back();
+	{
+		int b = 0;
+		for (const PairOut &po : st.out)
+			if (po.has_surface && (po.gM == id || po.gN == id) && po.s->tri)
+				blas[b++].build(*po.s);
+	}
+	if (blas.empty())
+		return;
+	Tlas tlas;
+	tlas.build(blas);
+
+	float rsigma_squared = 0, rtukey = 0;
+	if (use_gaussian)
+		rsigma_squared = 0.5f / (sigma * sigma);
+	else if (use_tukey)
+		rtukey = 1.f / sigma * S * S;
+
+#pragma omp parallel for collapse(2) schedule(dynamic) if (parallel)
+	for (int x = 0; x < cx; x++) {
+		for (int y = 0; y < cy; y++) {
+			float avg_pressure = 0;
+			for (int i = 0; i < S; i++) {
+				for (int j = 0; j < S; j++) {
+					double pos[3] = { sensor_topleft[0] + x * resolution + i * rS + 0.5 * rS,
+						              sensor_topleft[1] + y * resolution + j * rS + 0.5 * rS, 1.5 * zs };
+					double w[3]   = { rot[0] * pos[0] + rot[1] * pos[1] + rot[2] * pos[2],
+						              rot[3] * pos[0] + rot[4] * pos[1] + rot[5] * pos[2],
+						              rot[6] * pos[0] + rot[7] * pos[1] + rot[8] * pos[2] };
+					w[0] += sensor_xpos[0];
+					w[1] += sensor_xpos[1];
+					w[2] += sensor_xpos[2];
+					F3 sensor_point{ (float)w[0], (float)w[1], (float)w[2] };
+					Ray ray;
+					ray.O   = sensor_point + sensor_normal * (float)1e-8;
+					ray.D   = -sensor_normal;
+					ray.t   = 1e30f;
+					ray.u = ray.v = 0;
+					ray.hit = 0;
+					if (use_bvh) {
+						tlas.intersect(ray);
+					} else {
+						ray.rD = { 1.0f / ray.D.x, 1.0f / ray.D.y, 1.0f / ray.D.z };
+						for (unsigned b = 0; b < blas.size(); ++b)
+							for (unsigned t = 0; t < blas[b].tri.size(); ++t)
+								intersect_triangle(ray, blas[b].tri[t], (b << 20) + t);
+					}
+					if (ray.t < 1.5 * zs && ray.t > 0.0f) {
+						double bary[3]   = { (double)(1 - ray.u - ray.v), (double)ray.u, (double)ray.v };
+						unsigned tri_idx = ray.hit & 0xFFFFF, blas_idx = ray.hit >> 20;
+						const Surface &s = *blas[blas_idx].surface;
+						const int *f     = &s.face_idx[s.face_first[tri_idx]];
+						double ev        = bary[0] * s.e[f[0]];
+						ev += bary[1] * s.e[f[1]];
+						ev += bary[2] * s.e[f[2]];
+						float raw    = ev * rmean;
+						float weight = 1.0f;
+						if (use_gaussian) {
+							float dist = std::hypot(di_factor * i + sub_halfwidth, di_factor * j + sub_halfwidth) / max_dist;
+							weight     = std::exp((double)(-(dist * dist) * rsigma_squared));
+						} else if (use_tukey) {
+							if (S / 2 - std::abs(S / 2 - i) <= sigma * S / 2)
+								weight *= 0.5f * (1.f - cosf(2.f * M_PI * (S / 2 - std::abs(S / 2 - i)) * rtukey));
+							if (S / 2 - std::abs(S / 2 - j) <= sigma * S / 2)
+								weight *= 0.5f * (1.f - cosf(2.f * M_PI * (S / 2 - std::abs(S / 2 - j)) * rtukey));
+						} else if (use_square) {
+							float inv_dist =
+							    1 - std::hypot(di_factor * i + sub_halfwidth, di_factor * j + sub_halfwidth) / max_dist;
+							weight = inv_dist * inv_dist;
+						}
+						avg_pressure += weight * raw;
+					}
+				}
+			}
+			out[x + cy * y] = avg_pressure;
+		}
+	}
+}
+
+} // namespace orc
