@@ -33,8 +33,8 @@ BYTES_PER_POLYGON = 80
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=400)
+    ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c1_sphere_on_box")
     ap.add_argument("--envs", type=int, default=4096, help="environments per GPU")
@@ -117,15 +117,21 @@ def cpu_baseline(scene, seed, sample_envs, with_sensors, threads_all=True):
     t8, _, _ = orc.bench(xp, xm, ve, use_bvh=True, with_sensors=with_sensors, threads=1)
     per_env = max(t8 / 8, 1e-7)
     if sample_envs <= 0:
-        sample_envs = int(min(8192, max(32, 10.0 / per_env / max(1, n_threads) * (n_threads if threads_all else 1))))
+        sample_envs = int(min(4096, max(32, 2.0 / per_env)))
     xp, xm, ve = scene.poses(sample_envs, seed)
-    n1 = max(8, min(sample_envs, int(5.0 / per_env)))
-    t1, c1, _ = orc.bench(xp[:n1], xm[:n1], ve[:n1], use_bvh=True, with_sensors=with_sensors, threads=1)
-    out = {"single_thread": {"env_steps_per_s": n1 / t1, "pair_evals_per_s": c1 / t1, "envs": n1, "seconds": t1}}
+
+    def timed(threads, budget_s):
+        """repeat passes over the sample until about budget_s of wall time has been spent"""
+        orc.bench(xp, xm, ve, use_bvh=True, with_sensors=with_sensors, threads=threads)  # warm caches
+        t, c, n = 0.0, 0, 0
+        while t < budget_s:
+            dt, dc, _ = orc.bench(xp, xm, ve, use_bvh=True, with_sensors=with_sensors, threads=threads)
+            t, c, n = t + dt, c + dc, n + sample_envs
+        return {"env_steps_per_s": n / t, "pair_evals_per_s": c / t, "envs": n, "seconds": t, "threads": threads}
+
+    out = {"single_thread": timed(1, 6.0)}
     if threads_all:
-        tn, cn, _ = orc.bench(xp, xm, ve, use_bvh=True, with_sensors=with_sensors, threads=n_threads)
-        out["all_threads"] = {"env_steps_per_s": sample_envs / tn, "pair_evals_per_s": cn / tn, "envs": sample_envs,
-                              "seconds": tn, "threads": n_threads}
+        out["all_threads"] = timed(n_threads, 6.0)
     return out, n_threads
 
 
@@ -222,13 +228,19 @@ def main():
         eng.step_raw(h[0].data_ptr(), h[1].data_ptr(), h[2].data_ptr(), with_sensors)
 
     # ---------------- device-resident throughput (`value`) ----------------
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
     for i in range(args.warmup):
         dev_step(i)
     eng.sync()
     eng.set_profiling(True)
-    sampler = ClockSampler(local_rank)
     if rank == 0:
-        sampler.start()
+        t_wait = time.perf_counter()  # nvidia-smi needs a moment to start streaming: keep the GPU under load meanwhile
+        while not sampler.rows and time.perf_counter() - t_wait < 3.0:
+            dev_step(0)
+            eng.sync()
+        sampler.rows.clear()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     stage = {"broadphase": 0.0, "narrowphase": 0.0, "reduce": 0.0, "tactile": 0.0, "setup": 0.0}
     cand = poly = faces = 0
@@ -322,9 +334,9 @@ def main():
             cb, threads = cpu_baseline(scene, 1234, args.cpu_sample_envs, with_sensors)
             a = cb["all_threads"]
             line["cpu_baseline"] = {"value": a["env_steps_per_s"], "unit": "env-steps/s", "cores": threads, "kind": "port",
-                                    "sample": "%d envs of the same workload, OpenMP over envs (%.1f s); single thread: "
-                                              "%.1f env-steps/s on %d envs" % (a["envs"], a["seconds"], cb["single_thread"]["env_steps_per_s"],
-                                                                                cb["single_thread"]["envs"]),
+                                    "sample": "%d env-steps of the same workload (seeded poses), OpenMP over envs, %.1f s; single "
+                                              "thread: %.1f env-steps/s over %d env-steps" % (a["envs"], a["seconds"], cb["single_thread"]["env_steps_per_s"],
+                                                                                               cb["single_thread"]["envs"]),
                                     "single_thread_value": cb["single_thread"]["env_steps_per_s"],
                                     "pair_evals_per_sec": a["pair_evals_per_s"]}
         print(json.dumps(line))

@@ -439,10 +439,11 @@ static void build_sensor(hcs_ctx *c, SensorHost &s)
 	size_t ncell = (size_t)c->cfg.n_envs * s.cx * s.cy;
 	d.image      = dalloc<float>(c->step_allocs, ncell);
 	CK(cudaMemsetAsync(d.image, 0, ncell * sizeof(float), c->stream));
-	d.bin_cap   = c->cfg.max_triangles_per_taxel > 0 ? c->cfg.max_triangles_per_taxel : 64;
-	d.bin_count = dalloc<int32_t>(c->step_allocs, ncell);
-	d.bin_items = dalloc<int32_t>(c->step_allocs, ncell * d.bin_cap);
-	s.dev       = d;
+	d.bin_count  = dalloc<int32_t>(c->step_allocs, ncell);
+	d.bin_offset = dalloc<int32_t>(c->step_allocs, ncell + 1);
+	d.bin_cursor = dalloc<int32_t>(c->step_allocs, ncell);
+	d.scan_tmp   = dalloc<int32_t>(c->step_allocs, ncell / 1024 + 2);
+	s.dev        = d; // items are sized in finalize() once the triangle pool capacity is known
 	CK(cudaMallocHost((void **)&s.h_image, std::max<size_t>(ncell, 1) * sizeof(float)));
 }
 
@@ -491,6 +492,13 @@ static void finalize(hcs_ctx *c)
 				automatic += std::min<long>(8L * P.nq, 4096);
 		io.max_tris = c->cfg.max_tactile_triangles > 0 ? c->cfg.max_tactile_triangles :
 		                                                   (int)std::min<long>(automatic * n_env, 1L << 28);
+	}
+	for (SensorHost &sh : c->sensors) { // bins hold (triangle, taxel) overlaps back to back
+		size_t ncell = (size_t)n_env * sh.cx * sh.cy;
+		size_t per   = c->cfg.max_triangles_per_taxel > 0 ? c->cfg.max_triangles_per_taxel : 32;
+		size_t cap   = std::min<size_t>(std::max<size_t>(16 * (size_t)io.max_tris, per * ncell), (size_t)1 << 30);
+		sh.dev.items_cap = (int)cap;
+		sh.dev.bin_items = dalloc<int32_t>(c->step_allocs, cap);
 	}
 	io.tri_pool    = dalloc<TactileTri>(c->step_allocs, io.max_tris);
 	io.tri_count   = dalloc<int32_t>(c->step_allocs, 1);
@@ -549,8 +557,7 @@ static void step_device(hcs_ctx *c, const double *xpos, const double *xmat, cons
 		CK(cudaEventRecord(c->ev[4], s));
 	if (with_sensors)
 		for (SensorHost &sh : c->sensors) {
-			launch_tactile(sh.dev, io, c->d_pairs, s);
-			k += 3;
+			k += launch_tactile(sh.dev, io, c->d_pairs, s);
 		}
 	if (prof)
 		CK(cudaEventRecord(c->ev[5], s));
@@ -590,7 +597,7 @@ static int check_flags(hcs_ctx *c)
 		return HCS_E_CAPACITY;
 	}
 	if (c->h_flags[0] & 4) {
-		c->err = "tactile taxel bin overflow: raise hcs_config.max_triangles_per_taxel";
+		c->err = "tactile bin overflow: raise hcs_config.max_triangles_per_taxel (average bin depth)";
 		return HCS_E_CAPACITY;
 	}
 	return HCS_OK;

@@ -105,9 +105,12 @@ struct SensorDev {
 	float rmean, rS;
 	const float *weights; // [S*S] window weights
 	float *image;         // [n_env][cx*cy]
-	int32_t *bin_count;   // [n_env][cx*cy]
-	int32_t *bin_items;   // [n_env][cx*cy][bin_cap]
-	int bin_cap;
+	int32_t *bin_count;   // [n_env * cx*cy] (triangle, taxel) overlaps per taxel
+	int32_t *bin_offset;  // [n_env * cx*cy + 1] exclusive scan of bin_count
+	int32_t *bin_cursor;  // [n_env * cx*cy] fill cursors
+	int32_t *bin_items;   // [items_cap] triangle ids, bins back to back
+	int32_t *scan_tmp;    // tile sums of the scan
+	int items_cap;
 };
 
 // ---- launchers (definitions in the .cu files) ---------------------------------------------------
@@ -118,7 +121,7 @@ void launch_broadphase(const PairDesc &P, const StepIO &io, cudaStream_t s);
 void launch_narrowphase(const PairDesc &P, const StepIO &io, cudaStream_t s);
 void launch_finalize(const PairDesc *d_pairs, const StepIO &io, cudaStream_t s);
 
-// clear bins, bin the triangle pool, rasterise: 3 kernels
-void launch_tactile(const SensorDev &sd, const StepIO &io, const PairDesc *d_pairs, cudaStream_t s);
+// clear, count, scan, fill, rasterise; returns the number of kernels launched
+int launch_tactile(const SensorDev &sd, const StepIO &io, const PairDesc *d_pairs, cudaStream_t s);
 
 } // namespace hcs

@@ -168,13 +168,17 @@ __device__ __forceinline__ void integrate_polygon(const D3 *P, int n, D3 nhat, D
 		cen = ((P[0] + P[1]) + P[2]) / 3.0;
 	else
 		cen = A2 != 0.0 ? csum / (3.0 * A2) : p0;
-	bool g_ok = !(gM < 1.0e-14 || gN < 1.0e-14);
-	double g  = 1.0 / (1.0 / gM + 1.0 / gN);
-	(void)kInf;
+	// A face whose winding opposes nhat (only possible for a negatively oriented tet of a user mesh) gets
+	// the flipped normal, like the mesh constructors that derive face normals from the winding.
 	if (!TRI) {
 		acc.n_faces += 1;
-		double area = 0.5 * A2;
-		D3 cW       = IDENT ? cen : apply(c.X_WA, cen);
+		double sg   = A2 < 0 ? -1.0 : 1.0;
+		double area = 0.5 * (sg * A2);
+		double gMf = sg * gM, gNf = gN == kInf ? gN : sg * gN;
+		bool g_ok  = !(gMf < 1.0e-14 || gNf < 1.0e-14);
+		double g   = 1.0 / (1.0 / gMf + 1.0 / gNf);
+		nW         = sg * nW;
+		D3 cW      = IDENT ? cen : apply(c.X_WA, cen);
 		if (area > 0) {
 			acc.area += area;
 			acc.ac = acc.ac + area * cW;
@@ -190,11 +194,10 @@ __device__ __forceinline__ void integrate_polygon(const D3 *P, int n, D3 nhat, D
 				int slot = atomicAdd(io.face_count, 1);
 				if (slot < io.max_faces) {
 					hcs_face &o = io.faces[slot];
-					double sg   = Pd.sign;
-					o.p[0] = cW.x, o.p[1] = cW.y, o.p[2] = cW.z;
-					o.n[0] = sg * nW.x, o.n[1] = sg * nW.y, o.n[2] = sg * nW.z;
+										o.p[0] = cW.x, o.p[1] = cW.y, o.p[2] = cW.z;
+					o.n[0] = Pd.sign * nW.x, o.n[1] = Pd.sign * nW.y, o.n[2] = Pd.sign * nW.z;
 					o.fn0 = fn0, o.stiffness = k, o.damping = c.dissipation;
-					o.f[0] = sg * f.x, o.f[1] = sg * f.y, o.f[2] = sg * f.z;
+					o.f[0] = Pd.sign * f.x, o.f[1] = Pd.sign * f.y, o.f[2] = Pd.sign * f.z;
 					o.env = info.env, o.pair = info.pair;
 					o.elemM = Pd.sign > 0 ? info.elemA : info.elemB;
 					o.elemN = Pd.sign > 0 ? info.elemB : info.elemA;
@@ -217,8 +220,13 @@ __device__ __forceinline__ void integrate_polygon(const D3 *P, int n, D3 nhat, D
 	for (int i = 0; i < n; ++i) {
 		D3 a = P[cur], b = P[i];
 		double a2   = dot(cross(b - a, cen - a), nhat);
-		double area = 0.5 * a2;
-		D3 fc       = ((W_out[cur] + W_out[i]) + cW) / 3.0;
+		double sg   = a2 < 0 ? -1.0 : 1.0;
+		double area = 0.5 * (sg * a2);
+		double gMf = sg * gM, gNf = gN == kInf ? gN : sg * gN;
+		bool g_ok  = !(gMf < 1.0e-14 || gNf < 1.0e-14);
+		double g   = 1.0 / (1.0 / gMf + 1.0 / gNf);
+		D3 nWf     = sg * nW;
+		D3 fc      = ((W_out[cur] + W_out[i]) + cW) / 3.0;
 		if (area > 0) {
 			acc.area += area;
 			acc.ac = acc.ac + area * fc;
@@ -229,7 +237,7 @@ __device__ __forceinline__ void integrate_polygon(const D3 *P, int n, D3 nhat, D
 			pc += b3 * e[i];
 			pc += b3 * ec;
 			double fn0 = area * pc, k = area * g;
-			D3 f       = face_force(fc, nW, fn0, k, c);
+			D3 f       = face_force(fc, nWf, fn0, k, c);
 			acc.F      = acc.F + f;
 			acc.tau    = acc.tau + cross(fc, f);
 			acc.n_points += 1;
@@ -237,11 +245,10 @@ __device__ __forceinline__ void integrate_polygon(const D3 *P, int n, D3 nhat, D
 				int slot = atomicAdd(io.face_count, 1);
 				if (slot < io.max_faces) {
 					hcs_face &o = io.faces[slot];
-					double sg   = Pd.sign;
-					o.p[0] = fc.x, o.p[1] = fc.y, o.p[2] = fc.z;
-					o.n[0] = sg * nW.x, o.n[1] = sg * nW.y, o.n[2] = sg * nW.z;
+										o.p[0] = fc.x, o.p[1] = fc.y, o.p[2] = fc.z;
+					o.n[0] = Pd.sign * nWf.x, o.n[1] = Pd.sign * nWf.y, o.n[2] = Pd.sign * nWf.z;
 					o.fn0 = fn0, o.stiffness = k, o.damping = c.dissipation;
-					o.f[0] = sg * f.x, o.f[1] = sg * f.y, o.f[2] = sg * f.z;
+					o.f[0] = Pd.sign * f.x, o.f[1] = Pd.sign * f.y, o.f[2] = Pd.sign * f.z;
 					o.env = info.env, o.pair = info.pair;
 					o.elemM = Pd.sign > 0 ? info.elemA : info.elemB;
 					o.elemN = Pd.sign > 0 ? info.elemB : info.elemA;

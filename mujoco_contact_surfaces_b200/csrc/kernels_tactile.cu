@@ -5,7 +5,8 @@
 // casts sampling_resolution^2 parallel rays per taxel and keeps the nearest Moeller-Trumbore hit; the
 // hit test depends only on (ray, triangle), so instead of rebuilding a BVH every update we
 //   (a) tactile_bin:    splat every contact-surface triangle into the taxels its footprint (in the
-//                       sensor frame) can touch — per-taxel atomics on the bin counters;
+//                       sensor frame) can touch — per-taxel atomics on the bin counters; count pass,
+//                       exclusive scan, fill pass, so bins are sized exactly;
 //   (b) tactile_raster: one warp per taxel walks its bin with the SAME float32 Moeller-Trumbore
 //                       arithmetic (bvh.cpp:49-74) for each of its S*S sample rays, stores the weighted
 //                       sample pressures in a shared-memory tile and sums them in the reference's
@@ -25,6 +26,9 @@ __device__ __forceinline__ F3 operator*(F3 a, float s) { return f3(a.x * s, a.y 
 __device__ __forceinline__ F3 crossf(F3 a, F3 b) { return f3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x); }
 __device__ __forceinline__ float dotf(F3 a, F3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; } // float3.h order
 
+// FILL == false: count the (triangle, taxel) overlaps per taxel; FILL == true: write the triangle ids into
+// the exactly-sized bins delimited by the exclusive scan of the counts.
+template <bool FILL>
 __global__ void __launch_bounds__(256) tactile_bin_kernel(SensorDev sd, StepIO io, const PairDesc *pairs)
 {
 	int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -59,12 +63,97 @@ __global__ void __launch_bounds__(256) tactile_bin_kernel(SensorDev sd, StepIO i
 	for (int x = ix0; x <= ix1; ++x)
 		for (int y = iy0; y <= iy1; ++y) {
 			int cell = env * ntax + x + sd.cx * y; // bins are indexed x + cx*y (unique)
-			int slot = atomicAdd(sd.bin_count + cell, 1);
-			if (slot < sd.bin_cap)
-				sd.bin_items[(size_t)cell * sd.bin_cap + slot] = i;
-			else
-				atomicOr(io.flags, 4);
+			if (!FILL) {
+				atomicAdd(sd.bin_count + cell, 1);
+			} else {
+				int slot = sd.bin_offset[cell] + atomicAdd(sd.bin_cursor + cell, 1);
+				if (slot < sd.items_cap)
+					sd.bin_items[slot] = i;
+				else
+					atomicOr(io.flags, 4);
+			}
 		}
+}
+
+// ---- exclusive scan of the per-taxel counts (3 phases, 1024-element tiles) ----------------------------------
+constexpr int SCAN_TILE = 1024;
+__global__ void __launch_bounds__(256) scan_tiles_kernel(const int32_t *in, int32_t *out, int32_t *tile_sums, int n)
+{
+	__shared__ int warp_sums[8];
+	int base = blockIdx.x * SCAN_TILE + threadIdx.x * 4;
+	int v[4], sum = 0;
+#pragma unroll
+	for (int k = 0; k < 4; ++k) {
+		v[k] = base + k < n ? in[base + k] : 0;
+		sum += v[k];
+	}
+	int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+	int incl = sum;
+#pragma unroll
+	for (int o = 1; o < 32; o <<= 1) {
+		int t = __shfl_up_sync(0xffffffffu, incl, o);
+		if (lane >= o)
+			incl += t;
+	}
+	if (lane == 31)
+		warp_sums[w] = incl;
+	__syncthreads();
+	int woff = 0;
+	for (int k = 0; k < w; ++k)
+		woff += warp_sums[k];
+	int excl = woff + incl - sum;
+#pragma unroll
+	for (int k = 0; k < 4; ++k) {
+		if (base + k < n)
+			out[base + k] = excl;
+		excl += v[k];
+	}
+	if (threadIdx.x == 255)
+		tile_sums[blockIdx.x] = woff + incl;
+}
+__global__ void __launch_bounds__(1024) scan_sums_kernel(int32_t *tile_sums, int n_tiles, int32_t *total_out)
+{
+	__shared__ int warp_sums[32];
+	__shared__ int carry;
+	if (threadIdx.x == 0)
+		carry = 0;
+	__syncthreads();
+	int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+	for (int base = 0; base < n_tiles; base += 1024) {
+		int i    = base + threadIdx.x;
+		int v    = i < n_tiles ? tile_sums[i] : 0;
+		int incl = v;
+#pragma unroll
+		for (int o = 1; o < 32; o <<= 1) {
+			int t = __shfl_up_sync(0xffffffffu, incl, o);
+			if (lane >= o)
+				incl += t;
+		}
+		if (lane == 31)
+			warp_sums[w] = incl;
+		__syncthreads();
+		int woff = 0;
+		for (int k = 0; k < w; ++k)
+			woff += warp_sums[k];
+		int c = carry;
+		if (i < n_tiles)
+			tile_sums[i] = c + woff + incl - v;
+		__syncthreads();
+		if (threadIdx.x == 1023)
+			carry = c + woff + incl;
+		__syncthreads();
+	}
+	if (threadIdx.x == 0)
+		*total_out = carry;
+}
+__global__ void __launch_bounds__(256) scan_add_kernel(int32_t *out, const int32_t *tile_sums, int n)
+{
+	int base = blockIdx.x * SCAN_TILE + threadIdx.x * 4;
+	int off  = tile_sums[blockIdx.x];
+#pragma unroll
+	for (int k = 0; k < 4; ++k)
+		if (base + k < n)
+			out[base + k] += off;
 }
 
 constexpr int RASTER_WARPS = 4;
@@ -85,14 +174,15 @@ __global__ void __launch_bounds__(32 * RASTER_WARPS) tactile_raster_kernel(Senso
 	int oidx = x + sd.cy * y;
 	if (oidx >= ntax)
 		return;
-	int n = min(sd.bin_count[unit], sd.bin_cap);
+	int first = sd.bin_offset[unit];
+	int n     = min(sd.bin_count[unit], max(sd.items_cap - first, 0));
 	float *out = sd.image + (size_t)env * ntax + oidx;
 	if (n == 0) {
 		if (lane == 0)
 			*out = 0.0f;
 		return;
 	}
-	const int32_t *items = sd.bin_items + (size_t)unit * sd.bin_cap;
+	const int32_t *items = sd.bin_items + first;
 	const double *R  = io.xmat + ((size_t)env * io.n_geoms + sd.geom) * 9;
 	const double *xp = io.xpos + ((size_t)env * io.n_geoms + sd.geom) * 3;
 	double rot[9];
@@ -172,17 +262,28 @@ __global__ void __launch_bounds__(32 * RASTER_WARPS) tactile_raster_kernel(Senso
 __global__ void tactile_clear_kernel(SensorDev sd, int n)
 {
 	int i = blockIdx.x * blockDim.x + threadIdx.x;
-	if (i < n)
-		sd.bin_count[i] = 0;
+	if (i < n) {
+		sd.bin_count[i]  = 0;
+		sd.bin_cursor[i] = 0;
+	}
 }
 
-void launch_tactile(const SensorDev &sd, const StepIO &io, const PairDesc *d_pairs, cudaStream_t s)
+// 7 launches: clear, count, 3-phase scan, fill, raster
+int launch_tactile(const SensorDev &sd, const StepIO &io, const PairDesc *d_pairs, cudaStream_t s)
 {
-	int ncell = io.n_env * sd.cx * sd.cy;
+	int ncell   = io.n_env * sd.cx * sd.cy;
+	int n_tiles = (ncell + SCAN_TILE - 1) / SCAN_TILE;
+	int tgrid   = (io.max_tris + 255) / 256;
 	tactile_clear_kernel<<<(ncell + 255) / 256, 256, 0, s>>>(sd, ncell);
 	if (io.max_tris > 0)
-		tactile_bin_kernel<<<(io.max_tris + 255) / 256, 256, 0, s>>>(sd, io, d_pairs);
+		tactile_bin_kernel<false><<<tgrid, 256, 0, s>>>(sd, io, d_pairs);
+	scan_tiles_kernel<<<n_tiles, 256, 0, s>>>(sd.bin_count, sd.bin_offset, sd.scan_tmp, ncell);
+	scan_sums_kernel<<<1, 1024, 0, s>>>(sd.scan_tmp, n_tiles, sd.bin_offset + ncell);
+	scan_add_kernel<<<n_tiles, 256, 0, s>>>(sd.bin_offset, sd.scan_tmp, ncell);
+	if (io.max_tris > 0)
+		tactile_bin_kernel<true><<<tgrid, 256, 0, s>>>(sd, io, d_pairs);
 	tactile_raster_kernel<<<(ncell + RASTER_WARPS - 1) / RASTER_WARPS, 32 * RASTER_WARPS, 0, s>>>(sd, io);
+	return 5 + (io.max_tris > 0 ? 2 : 0);
 }
 
 } // namespace hcs
