@@ -283,6 +283,10 @@ static void upload_geom(hcs_ctx *c, GeomHost &g)
 			std::vector<BvhNode> nodes = build_lbvh(m);
 			d.nodes                     = dalloc<BvhNode>(g.allocs, nodes.size());
 			CK(cudaMemcpyAsync(d.nodes, nodes.data(), nodes.size() * sizeof(BvhNode), cudaMemcpyHostToDevice, c->stream));
+			for (int a = 0; a < 3; ++a) {
+				d.root_lo[a] = std::min(nodes[0].llo[a], nodes[0].rlo[a]);
+				d.root_hi[a] = std::max(nodes[0].lhi[a], nodes[0].rhi[a]);
+			}
 			CK(cudaStreamSynchronize(c->stream)); // `nodes` is a local
 			launch_build_tets(d, c->stream);
 		} else {
@@ -379,6 +383,8 @@ static void build_pairs(hcs_ctx *c)
 				P.cap         = (int)cap;
 				P.slab        = dalloc<uint2>(c->step_allocs, units * cap);
 				P.slab_count  = dalloc<int32_t>(c->step_allocs, units);
+				P.slab_evals  = dalloc<int32_t>(c->step_allocs, units);
+				CK(cudaMemsetAsync(P.slab_evals, 0, units * sizeof(int32_t), c->stream));
 				P.slab_nverts = dalloc<uint8_t>(c->step_allocs, units * cap);
 				CK(cudaMemsetAsync(P.slab_count, 0, units * sizeof(int32_t), c->stream));
 			}

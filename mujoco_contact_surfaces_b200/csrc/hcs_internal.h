@@ -47,6 +47,7 @@ struct GeomDev {
 	BvhNode *nodes;     // soft: LBVH over tets (root = node 0)
 	double bound_c[3];  // bounding sphere in the geom frame
 	double bound_r;
+	float root_lo[3], root_hi[3]; // soft: box of the whole LBVH
 };
 
 enum PairKind { PAIR_NONE = 0, PAIR_SOFT_RIGID = 1, PAIR_SOFT_PLANE = 2, PAIR_SOFT_SOFT = 3 };
@@ -77,7 +78,8 @@ struct PairDesc {
 	int emit_tactile;    // pair touches a sensor geom and representation is kTriangle
 	GeomDev A, B;
 	uint2 *slab;           // [n_env * n_slices][cap] candidates (query, tree element)
-	int32_t *slab_count;   // [n_env * n_slices]
+	int32_t *slab_count;   // [n_env * n_slices] candidates that survived the early-outs (need clipping)
+	int32_t *slab_evals;   // [n_env * n_slices] LBVH leaf hits = pair-evals started in the broadphase
 	uint8_t *slab_nverts;  // [n_env * n_slices][cap] polygon vertex count per candidate (plane: per tet)
 	SlicePartial *partial; // [n_env * n_slices]
 };

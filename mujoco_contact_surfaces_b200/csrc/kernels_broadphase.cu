@@ -1,0 +1,234 @@
+// K3 broadphase — warp-cooperative LBVH traversal with shared-memory work queues (sm_100a).
+//
+// Replaces Bvh<Obb,.>::Collide inside the Drake queries the reference calls at
+// mujoco_contact_surfaces_plugin.cpp:284-303 (candidate generation), and hoists the two exact early-outs
+// of mesh_intersection.cc into the traversal so the clipping kernel only sees pairs that need clipping:
+//   * IsFaceNormalAlongPressureGradient:  ghat . (R_SR n) > cos(5 pi / 8)
+//   * trivial reject: all three triangle vertices strictly outside one tet half space (then the
+//     Sutherland-Hodgman clip is empty; a 1e-12 margin keeps the decision identical to the clip's).
+//
+// One warp owns one (env, pair, query slice).  Lane-per-query traversal left 3 of 32 lanes busy on the
+// sphere-on-box scene (most query triangles die at the root), so the warp instead shares two LIFO queues
+// in shared memory:  node items (query, internal node) and leaf items (query, tet).  Every iteration all
+// lanes pop one item each; children / survivors are appended with warp-ballot + popc prefix sums, which
+// also makes the emitted candidate order deterministic (no atomics anywhere).
+#include "dmath.cuh"
+#include "hcs_internal.h"
+
+namespace hcs {
+
+#define FULL_MASK 0xffffffffu
+constexpr int BP_WARPS = 4;
+constexpr int BP_BLOCK = 32 * BP_WARPS;
+constexpr int NODE_Q   = 768; // LIFO of (query slot, node); grows by <= 32 per iteration
+constexpr int LEAF_Q   = 128; // (query slot, tet); drained in batches of 32
+
+struct __align__(16) WarpQueues {
+	uint2 nodeq[NODE_Q];
+	uint2 leafq[LEAF_Q];
+	double qv[12][32];  // transformed query vertices (tri: 9 + rotated normal 3; tet: 12), lane-interleaved
+	float qbox[6][32];
+	int qid[32];
+};
+
+__device__ __forceinline__ bool box_overlap(const float *q, float4 a, float4 b, float4 c, bool left)
+{
+	// node layout: llo[3] lhi[3] rlo[3] rhi[3]
+	float lo0 = left ? a.x : b.z, lo1 = left ? a.y : b.w, lo2 = left ? a.z : c.x;
+	float hi0 = left ? a.w : c.y, hi1 = left ? b.x : c.z, hi2 = left ? b.y : c.w;
+	return q[0] <= hi0 && q[3] >= lo0 && q[1] <= hi1 && q[4] >= lo1 && q[2] <= hi2 && q[5] >= lo2;
+}
+
+// QTET: query elements are tets of B (soft-soft), otherwise triangles of B (soft-rigid)
+template <bool QTET>
+__global__ void __launch_bounds__(BP_BLOCK) broadphase_kernel(PairDesc P, StepIO io)
+{
+	__shared__ WarpQueues sm[BP_WARPS];
+	int warp = (blockIdx.x * BP_BLOCK + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+	int n_units = io.n_env * P.n_slices;
+	if (warp >= n_units)
+		return;
+	WarpQueues &W = sm[threadIdx.x >> 5];
+	int env = warp / P.n_slices, slice = warp - env * P.n_slices;
+	Xform X_WA = load_pose(io.xpos, io.xmat, io.n_geoms, env, P.gA);
+	Xform X_WB = load_pose(io.xpos, io.xmat, io.n_geoms, env, P.gB);
+	{ // pair-level reject on bounding spheres
+		D3 ca = apply(X_WA, mk(P.A.bound_c[0], P.A.bound_c[1], P.A.bound_c[2]));
+		D3 cb = apply(X_WB, mk(P.B.bound_c[0], P.B.bound_c[1], P.B.bound_c[2]));
+		D3 d  = ca - cb;
+		double rr = P.A.bound_r + P.B.bound_r + 1e-9;
+		if (dot(d, d) > rr * rr) {
+			if (lane == 0) {
+				P.slab_count[warp] = 0;
+				P.slab_evals[warp] = 0;
+			}
+			return;
+		}
+	}
+	Xform X_AB  = invert_and_compose(X_WA, X_WB);
+	uint2 *slab = P.slab + (size_t)warp * P.cap;
+	int count = 0, evals = 0; // warp-uniform
+	int q_begin = slice * P.slice_q, q_end = min(P.nq, q_begin + P.slice_q);
+	unsigned lt_mask = (1u << lane) - 1u;
+	const float4 *nodes4 = reinterpret_cast<const float4 *>(P.A.nodes);
+
+	for (int q0 = q_begin; q0 < q_end; q0 += 32) {
+		// ---- load + transform this chunk's queries, test against the root box, compact survivors ----
+		int q = q0 + lane;
+		bool alive = q < q_end;
+		double v[12];
+		float box[6];
+		if (alive) {
+			double lo[3] = { 1e300, 1e300, 1e300 }, hi[3] = { -1e300, -1e300, -1e300 };
+			const double *vp = QTET ? &P.B.tet_geom[q].v[0][0] : &P.B.tris[q].v[0][0];
+			const int nv     = QTET ? 4 : 3;
+#pragma unroll
+			for (int i = 0; i < nv; ++i) {
+				D3 p = apply(X_AB, ld3(vp + 3 * i));
+				v[3 * i] = p.x, v[3 * i + 1] = p.y, v[3 * i + 2] = p.z;
+				lo[0] = fmin(lo[0], p.x), lo[1] = fmin(lo[1], p.y), lo[2] = fmin(lo[2], p.z);
+				hi[0] = fmax(hi[0], p.x), hi[1] = fmax(hi[1], p.y), hi[2] = fmax(hi[2], p.z);
+			}
+			if (!QTET) {
+				D3 nS = rot(X_AB.R, ld3(P.B.tris[q].n));
+				v[9] = nS.x, v[10] = nS.y, v[11] = nS.z;
+			}
+#pragma unroll
+			for (int a = 0; a < 3; ++a) {
+				box[a]     = __double2float_rd(lo[a] - 1e-9);
+				box[3 + a] = __double2float_ru(hi[a] + 1e-9);
+			}
+			alive = box[0] <= P.A.root_hi[0] && box[3] >= P.A.root_lo[0] && box[1] <= P.A.root_hi[1] &&
+			        box[4] >= P.A.root_lo[1] && box[2] <= P.A.root_hi[2] && box[5] >= P.A.root_lo[2];
+		}
+		unsigned m_alive = __ballot_sync(FULL_MASK, alive);
+		int n_alive      = __popc(m_alive);
+		if (n_alive == 0)
+			continue;
+		__syncwarp();
+		if (alive) {
+			int slot = __popc(m_alive & lt_mask);
+#pragma unroll
+			for (int k = 0; k < 12; ++k)
+				W.qv[k][slot] = v[k];
+#pragma unroll
+			for (int k = 0; k < 6; ++k)
+				W.qbox[k][slot] = box[k];
+			W.qid[slot]   = q;
+			W.nodeq[slot] = make_uint2((unsigned)slot, 0u);
+		}
+		__syncwarp();
+		int n_node = n_alive, n_leaf = 0;
+
+		// ---- shared-queue traversal ----
+		while (n_node > 0 || n_leaf > 0) {
+			if (n_leaf >= 32 || n_node == 0) {
+				// drain up to 32 leaf items: exact early-outs, survivors go to the candidate slab
+				int k     = min(32, n_leaf);
+				bool keep = false;
+				uint2 it  = make_uint2(0, 0);
+				if (lane < k) {
+					it   = W.leafq[n_leaf - k + lane];
+					keep = true;
+					if (!QTET) {
+						const TetField &tf = P.A.tet_field[it.y];
+						int s  = (int)it.x;
+						D3 nS  = mk(W.qv[9][s], W.qv[10][s], W.qv[11][s]);
+						keep   = dot(ld3(tf.ghat), nS) > HCS_COS_ALPHA;
+						if (keep) {
+							D3 a = mk(W.qv[0][s], W.qv[1][s], W.qv[2][s]), b = mk(W.qv[3][s], W.qv[4][s], W.qv[5][s]),
+							   c = mk(W.qv[6][s], W.qv[7][s], W.qv[8][s]);
+#pragma unroll
+							for (int f = 0; f < 4; ++f) {
+								D3 nh = ld3(tf.plane[f]);
+								double d = tf.plane[f][3];
+								double sa = dot(nh, a) - d, sb = dot(nh, b) - d, sc = dot(nh, c) - d;
+								if (sa > 1e-12 && sb > 1e-12 && sc > 1e-12)
+									keep = false;
+							}
+						}
+					}
+				}
+				n_leaf -= k;
+				evals += k;
+				unsigned mk_ = __ballot_sync(FULL_MASK, keep);
+				if (keep) {
+					int pos = count + __popc(mk_ & lt_mask);
+					if (pos < P.cap)
+						slab[pos] = make_uint2((unsigned)W.qid[it.x], it.y);
+				}
+				count += __popc(mk_);
+				__syncwarp();
+			} else {
+				int k = min(32, n_node);
+				bool pushL = false, pushR = false, leafL = false, leafR = false;
+				int cl = 0, cr = 0;
+				unsigned s = 0;
+				if (lane < k) {
+					uint2 it = W.nodeq[n_node - k + lane];
+					s        = it.x;
+					float qb[6];
+#pragma unroll
+					for (int a = 0; a < 6; ++a)
+						qb[a] = W.qbox[a][s];
+					const float4 *nd = nodes4 + 4 * (size_t)it.y;
+					float4 a = nd[0], b = nd[1], c = nd[2], d = nd[3];
+					cl = __float_as_int(d.x), cr = __float_as_int(d.y);
+					if (box_overlap(qb, a, b, c, true)) {
+						leafL = cl < 0;
+						pushL = !leafL;
+					}
+					if (box_overlap(qb, a, b, c, false)) {
+						leafR = cr < 0;
+						pushR = !leafR;
+					}
+				}
+				n_node -= k;
+				__syncwarp();
+				unsigned mL = __ballot_sync(FULL_MASK, pushL), mR = __ballot_sync(FULL_MASK, pushR);
+				unsigned lL = __ballot_sync(FULL_MASK, leafL), lR = __ballot_sync(FULL_MASK, leafR);
+				int nL = __popc(mL), nR = __popc(mR), nlL = __popc(lL), nlR = __popc(lR);
+				if (n_node + nL + nR > NODE_Q) { // cannot happen for trees shallower than NODE_Q/32 levels
+					if (lane == 0)
+						atomicOr(io.flags + 1, 1);
+					n_node = 0;
+					n_leaf = 0;
+					break;
+				}
+				if (pushL)
+					W.nodeq[n_node + __popc(mL & lt_mask)] = make_uint2(s, (unsigned)cl);
+				if (pushR)
+					W.nodeq[n_node + nL + __popc(mR & lt_mask)] = make_uint2(s, (unsigned)cr);
+				if (leafL)
+					W.leafq[n_leaf + __popc(lL & lt_mask)] = make_uint2(s, (unsigned)~cl);
+				if (leafR)
+					W.leafq[n_leaf + nlL + __popc(lR & lt_mask)] = make_uint2(s, (unsigned)~cr);
+				n_node += nL + nR;
+				n_leaf += nlL + nlR;
+				__syncwarp();
+			}
+		}
+	}
+	if (lane == 0) {
+		if (count > P.cap) {
+			atomicOr(io.flags, 1);
+			count = P.cap;
+		}
+		P.slab_count[warp] = count;
+		P.slab_evals[warp] = evals;
+	}
+}
+
+void launch_broadphase(const PairDesc &P, const StepIO &io, cudaStream_t s)
+{
+	long units = (long)io.n_env * P.n_slices;
+	if (units == 0)
+		return;
+	int grid = (int)((units + BP_WARPS - 1) / BP_WARPS);
+	if (P.kind == PAIR_SOFT_RIGID)
+		broadphase_kernel<false><<<grid, BP_BLOCK, 0, s>>>(P, io);
+	else if (P.kind == PAIR_SOFT_SOFT)
+		broadphase_kernel<true><<<grid, BP_BLOCK, 0, s>>>(P, io);
+}
+
+} // namespace hcs

@@ -1,19 +1,18 @@
-// Per-step kernels of the hydroelastic contact engine (sm_100a, fp64 geometry mode, -fmad=false).
+// Narrowphase + reduction kernels of the hydroelastic contact engine (sm_100a, fp64, -fmad=false).
 //
-//   K3 broadphase_kernel      one warp per (env, pair, query slice): each lane walks the soft geom's LBVH
-//                             with one query element of the other geom; leaf hits are compacted with a
-//                             warp ballot + popc prefix into the warp's candidate slab (deterministic order).
-//                             Replaces Bvh<Obb,.>::Collide inside the Drake queries called at
-//                             mujoco_contact_surfaces_plugin.cpp:284-303.
-//   K4 narrow_tet_tri_kernel  one thread per (tet, triangle) candidate: normal/gradient cull, Sutherland-
-//                             Hodgman clip against the tet's four precomputed half spaces, duplicate removal,
-//                             polygon quadrature (plugin.cpp:320-409) and the force law (plugin.cpp:411-483).
-//                             Restates mesh_intersection.cc.
+//   K4 narrow_tet_tri_kernel   one thread per (tet, triangle) candidate that survived the broadphase
+//                              early-outs: Sutherland-Hodgman clip against the tet's four precomputed half
+//                              spaces, duplicate removal, polygon quadrature (mujoco_contact_surfaces_plugin.
+//                              cpp:320-409) and the force law (plugin.cpp:411-483).  Restates Drake
+//                              mesh_intersection.cc.
 //   K5 narrow_tet_plane_kernel one thread per (tet, half space): marching-tets slice (App. A.5).
-//   K6 narrow_tet_tet_kernel  one thread per (tet, tet) candidate: equal-pressure plane, slice + clip (A.6).
-//   K7 finalize kernels       fixed-order reduction of the per-warp partial sums to per-pair wrenches and
-//                             per-geom wrenches (replaces two mj_applyFT per face, plugin.cpp:477-482).
+//   K6 narrow_tet_tet_kernel   one thread per (tet, tet) candidate: equal-pressure plane, slice + clip (A.6).
+//   K7 finalize kernels        fixed-order reduction of the per-warp partial sums to per-pair wrenches and
+//                              per-geom wrenches (replaces two mj_applyFT per face, plugin.cpp:477-482).
 //
+// Polygon vertices live in a lane-interleaved shared-memory tile ([vertex][coord][lane], conflict free),
+// loops over vertices / planes are deliberately NOT unrolled: the first version inlined everything into
+// ~20k SASS instructions and stalled on instruction fetch (profiles/r01_notes.md).
 // The polygon vertex arithmetic follows the oracle's (= restated Drake) operation order exactly; the
 // quadrature uses the known unit normal instead of per-fan-triangle norms (differences ~1e-16 relative).
 #include "dmath.cuh"
@@ -22,17 +21,34 @@
 namespace hcs {
 
 #define FULL_MASK 0xffffffffu
-constexpr int MAXV       = 8;
-constexpr int STACK_SIZE = 64;
-constexpr int WARPS_PER_BLOCK = 4;
-constexpr int BLOCK           = 32 * WARPS_PER_BLOCK;
+constexpr int MAXV     = 8;
+constexpr int NP_WARPS = 4;
+constexpr int NP_BLOCK = 32 * NP_WARPS;
+
+// per-warp shared-memory tile: two polygon buffers + vertex pressures, lane-interleaved
+struct WarpTile {
+	double xyz[2][MAXV][3][32];
+	double e[MAXV][32];
+};
+constexpr size_t NP_SMEM = sizeof(WarpTile) * NP_WARPS;
+
+struct Poly { // view of one lane's polygon buffer
+	double *b;
+	__device__ __forceinline__ D3 get(int i) const { return mk(b[(3 * i) * 32], b[(3 * i + 1) * 32], b[(3 * i + 2) * 32]); }
+	__device__ __forceinline__ void set(int i, D3 v) const
+	{
+		b[(3 * i) * 32]     = v.x;
+		b[(3 * i + 1) * 32] = v.y;
+		b[(3 * i + 2) * 32] = v.z;
+	}
+};
 
 struct WarpCtx { // warp-uniform per (env, pair) data
 	Xform X_WA;    // soft geom A (computation frame) -> world
 	D3 xA, wA, vA; // origin, angular, linear velocity of geom A (world)
 	D3 xB, wB, vB;
-	double dissipation, mu;
-	int apply;
+	double dissipation, mu, sign;
+	int apply, env, pair;
 };
 
 struct Acc {
@@ -59,7 +75,10 @@ __device__ __forceinline__ WarpCtx make_ctx(const PairDesc &P, const StepIO &io,
 	load_vel(io.vel, io.n_geoms, env, P.gB, c.wB, c.vB);
 	c.dissipation = P.dissipation;
 	c.mu          = P.mu;
+	c.sign        = P.sign;
 	c.apply       = io.apply_forces;
+	c.env         = env;
+	c.pair        = P.index;
 	return c;
 }
 
@@ -87,87 +106,124 @@ __device__ __forceinline__ D3 face_force(D3 p, D3 n, double fn0, double k, const
 }
 
 // ---- Sutherland-Hodgman step: ClipPolygonByHalfSpace + CalcIntersection (mesh_intersection.cc) ----
-__device__ __forceinline__ int clip_halfspace(const D3 *in, int n, D3 nh, double d, D3 *out)
+__device__ __forceinline__ int clip_halfspace(Poly in, int n, D3 nh, double d, Poly out)
 {
-	double sd[MAXV];
-	for (int i = 0; i < n; ++i)
-		sd[i] = dot(nh, in[i]) - d;
-	int m = 0;
+	if (n == 0)
+		return 0;
+	D3 pprev     = in.get(n - 1);
+	double sprev = dot(nh, pprev) - d;
+	int m        = 0;
+#pragma unroll 1
 	for (int i = 0; i < n; ++i) {
-		int ip   = i == 0 ? n - 1 : i - 1;
-		bool cin = sd[i] <= 0, pin = sd[ip] <= 0;
-		if (cin != pin) { // CalcIntersection(current, previous)
-			double a = sd[i], b = sd[ip];
-			double wa = b / (b - a);
+		D3 pc     = in.get(i);
+		double sc = dot(nh, pc) - d;
+		bool cin = sc <= 0, pin = sprev <= 0;
+		if (cin != pin) { // CalcIntersection(current, previous): a = sd(current), b = sd(previous)
+			double wa = sprev / (sprev - sc);
 			double wb = 1.0 - wa;
-			out[m++]  = wa * in[i] + wb * in[ip];
+			out.set(m++, wa * pc + wb * pprev);
 		}
 		if (cin)
-			out[m++] = in[i];
+			out.set(m++, pc);
+		pprev = pc;
+		sprev = sc;
 	}
 	return m;
 }
 
 // RemoveDuplicateVertices: std::unique over consecutive near vertices, then last vs first
-__device__ __forceinline__ int remove_duplicates(D3 *p, int n)
+__device__ __forceinline__ int remove_duplicates(Poly p, int n)
 {
 	const double eps2 = 1e-14 * 1e-14;
 	if (n == 0)
 		return 0;
-	int m = 1;
+	int m   = 1;
+	D3 last = p.get(0);
+#pragma unroll 1
 	for (int i = 1; i < n; ++i) {
-		D3 d = p[m - 1] - p[i];
-		if (!(dot(d, d) < eps2))
-			p[m++] = p[i];
+		D3 q = p.get(i);
+		D3 d = last - q;
+		if (!(dot(d, d) < eps2)) {
+			p.set(m++, q);
+			last = q;
+		}
 	}
 	if (m >= 3) {
-		D3 d = p[0] - p[m - 1];
+		D3 d = p.get(0) - last;
 		if (dot(d, d) < eps2)
 			--m;
 	}
 	return m;
 }
 
-__constant__ int c_tet_edges[6][2]     = { { 0, 1 }, { 1, 2 }, { 2, 0 }, { 0, 3 }, { 1, 3 }, { 2, 3 } };
+__constant__ int c_tet_edges[6][2]      = { { 0, 1 }, { 1, 2 }, { 2, 0 }, { 0, 3 }, { 1, 3 }, { 2, 3 } };
 __constant__ int c_marching_tets[16][4] = { { -1, -1, -1, -1 }, { 0, 3, 2, -1 }, { 0, 1, 4, -1 }, { 4, 3, 2, 1 },
 	                                        { 1, 2, 5, -1 },    { 0, 3, 5, 1 },  { 0, 2, 5, 4 },  { 3, 5, 4, -1 },
 	                                        { 3, 4, 5, -1 },    { 4, 5, 2, 0 },  { 1, 5, 3, 0 },  { 1, 5, 2, -1 },
 	                                        { 1, 2, 3, 4 },     { 0, 4, 1, -1 }, { 0, 2, 3, -1 }, { -1, -1, -1, -1 } };
 
-struct EmitInfo { // provenance for the optional dumps
-	int env, pair, elemA, elemB, slot;
-};
+__device__ __forceinline__ double pick4(const double *d, int i)
+{
+	return i == 0 ? d[0] : (i == 1 ? d[1] : (i == 2 ? d[2] : d[3]));
+}
+
+// optional per-face dump (PointCollision views for CPU sub-plugins); cold path, kept out of line
+__device__ __noinline__ void dump_face(const StepIO &io, const WarpCtx &c, D3 p, D3 n, double fn0, double k, D3 f,
+                                       int elemA, int elemB, int nverts, int face)
+{
+	int slot = atomicAdd(io.face_count, 1);
+	if (slot >= io.max_faces)
+		return;
+	hcs_face &o = io.faces[slot];
+	double sg   = c.sign;
+	o.p[0] = p.x, o.p[1] = p.y, o.p[2] = p.z;
+	o.n[0] = sg * n.x, o.n[1] = sg * n.y, o.n[2] = sg * n.z;
+	o.fn0 = fn0, o.stiffness = k, o.damping = c.dissipation;
+	o.f[0] = sg * f.x, o.f[1] = sg * f.y, o.f[2] = sg * f.z;
+	o.env = c.env, o.pair = c.pair;
+	o.elemM  = sg > 0 ? elemA : elemB;
+	o.elemN  = sg > 0 ? elemB : elemA;
+	o.nverts = nverts, o.face = face;
+}
 
 // Quadrature + force accumulation of one contact polygon.
-//   P[0..n): vertices in the builder frame (A's frame, or world when IDENT), winding such that the
-//   right-handed normal is nhat (unit, points into A); e[i]: pressures; grad: sampled-field gradient
-//   (builder frame); gN: -grad_N . nhat or +inf.  TRI selects kTriangle (centroid fan) vs kPolygon.
+//   P[0..n): vertices in the builder frame (A's frame, or world when IDENT), right-handed normal nhat
+//   (unit, into A); e[i*32] (shared tile): vertex pressures; grad: sampled-field gradient (builder frame);
+//   gN: -grad_N . nhat or +inf.  TRI selects kTriangle (centroid fan) vs kPolygon.
+//   Returns the polygon centroid (builder frame) and its pressure for the tactile emission.
 template <bool TRI, bool IDENT>
-__device__ __forceinline__ void integrate_polygon(const D3 *P, int n, D3 nhat, D3 grad, const double *e, double gN,
-                                                  const WarpCtx &c, const PairDesc &Pd, const StepIO &io,
-                                                  const EmitInfo &info, Acc &acc, int &tri_faces, D3 *W_out, D3 &cW_out,
-                                                  double &ec_out)
+__device__ __forceinline__ void integrate_polygon(Poly P, int n, D3 nhat, D3 grad, const double *e, double gN,
+                                                  const WarpCtx &c, const StepIO &io, int elemA, int elemB, Acc &acc,
+                                                  D3 &cen_out, double &ec_out)
 {
 	const double kInf = __longlong_as_double(0x7ff0000000000000LL);
 	double gM         = dot(grad, nhat);
 	D3 nW             = IDENT ? nhat : rot(c.X_WA.R, nhat);
 	acc.n_polygons += 1;
-	tri_faces = 0;
 	// polygon centroid (contact_surface_utility.cc CalcPolygonCentroid): fan about vertex 0, signed
 	// areas measured along nhat
-	D3 p0     = P[0];
+	D3 p0     = P.get(0);
+	D3 p1     = P.get(1);
 	double A2 = 0;
 	D3 csum   = mk(0, 0, 0);
+	D3 pi     = p1;
+#pragma unroll 1
 	for (int i = 1; i < n - 1; ++i) {
-		double a2 = dot(cross(P[i] - p0, P[i + 1] - p0), nhat);
+		D3 pn     = P.get(i + 1);
+		double a2 = dot(cross(pi - p0, pn - p0), nhat);
 		A2 += a2;
-		csum = csum + a2 * ((p0 + P[i]) + P[i + 1]);
+		csum = csum + a2 * ((p0 + pi) + pn);
+		pi   = pn;
 	}
 	D3 cen;
 	if (n == 3)
-		cen = ((P[0] + P[1]) + P[2]) / 3.0;
+		cen = ((p0 + p1) + pi) / 3.0;
 	else
 		cen = A2 != 0.0 ? csum / (3.0 * A2) : p0;
+	double ec = e[0] + dot(grad, cen - p0);
+	cen_out   = cen;
+	ec_out    = ec;
+	D3 cW     = IDENT ? cen : apply(c.X_WA, cen);
 	// A face whose winding opposes nhat (only possible for a negatively oriented tet of a user mesh) gets
 	// the flipped normal, like the mesh constructors that derive face normals from the winding.
 	if (!TRI) {
@@ -175,95 +231,67 @@ __device__ __forceinline__ void integrate_polygon(const D3 *P, int n, D3 nhat, D
 		double sg   = A2 < 0 ? -1.0 : 1.0;
 		double area = 0.5 * (sg * A2);
 		double gMf = sg * gM, gNf = gN == kInf ? gN : sg * gN;
-		bool g_ok  = !(gMf < 1.0e-14 || gNf < 1.0e-14);
-		double g   = 1.0 / (1.0 / gMf + 1.0 / gNf);
-		nW         = sg * nW;
-		D3 cW      = IDENT ? cen : apply(c.X_WA, cen);
 		if (area > 0) {
 			acc.area += area;
 			acc.ac = acc.ac + area * cW;
 		}
-		if (area > 1.0e-14 && g_ok) {
-			double pc  = e[0] + dot(grad, cen - p0);
-			double fn0 = area * pc, k = area * g;
-			D3 f       = face_force(cW, nW, fn0, k, c);
+		if (area > 1.0e-14 && !(gMf < 1.0e-14 || gNf < 1.0e-14)) {
+			double g   = 1.0 / (1.0 / gMf + 1.0 / gNf);
+			double fn0 = area * ec, k = area * g;
+			D3 nf      = sg * nW;
+			D3 f       = face_force(cW, nf, fn0, k, c);
 			acc.F      = acc.F + f;
 			acc.tau    = acc.tau + cross(cW, f);
 			acc.n_points += 1;
-			if (io.max_faces > 0) {
-				int slot = atomicAdd(io.face_count, 1);
-				if (slot < io.max_faces) {
-					hcs_face &o = io.faces[slot];
-										o.p[0] = cW.x, o.p[1] = cW.y, o.p[2] = cW.z;
-					o.n[0] = Pd.sign * nW.x, o.n[1] = Pd.sign * nW.y, o.n[2] = Pd.sign * nW.z;
-					o.fn0 = fn0, o.stiffness = k, o.damping = c.dissipation;
-					o.f[0] = Pd.sign * f.x, o.f[1] = Pd.sign * f.y, o.f[2] = Pd.sign * f.z;
-					o.env = info.env, o.pair = info.pair;
-					o.elemM = Pd.sign > 0 ? info.elemA : info.elemB;
-					o.elemN = Pd.sign > 0 ? info.elemB : info.elemA;
-					o.nverts = n, o.face = 0;
-				}
-			}
+			if (io.max_faces > 0)
+				dump_face(io, c, cW, nf, fn0, k, f, elemA, elemB, n, 0);
 		}
 		return;
 	}
 	// kTriangle: TriMeshBuilder::AddPolygon — centroid vertex, pressure by the gradient, fan (prev,next,c)
-	double ec = e[0] + dot(grad, cen - p0);
-	D3 cW     = IDENT ? cen : apply(c.X_WA, cen);
-	for (int i = 0; i < n; ++i)
-		W_out[i] = IDENT ? P[i] : apply(c.X_WA, P[i]);
-	cW_out    = cW;
-	ec_out    = ec;
-	tri_faces = n;
 	acc.n_faces += n;
-	int cur = n - 1;
+	int cur   = n - 1;
+	D3 a      = P.get(cur);
+	D3 aW     = IDENT ? a : apply(c.X_WA, a);
+	double ea = e[cur * 32];
+#pragma unroll 1
 	for (int i = 0; i < n; ++i) {
-		D3 a = P[cur], b = P[i];
+		D3 b        = P.get(i);
+		D3 bW       = IDENT ? b : apply(c.X_WA, b);
+		double eb   = e[i * 32];
 		double a2   = dot(cross(b - a, cen - a), nhat);
 		double sg   = a2 < 0 ? -1.0 : 1.0;
 		double area = 0.5 * (sg * a2);
 		double gMf = sg * gM, gNf = gN == kInf ? gN : sg * gN;
-		bool g_ok  = !(gMf < 1.0e-14 || gNf < 1.0e-14);
-		double g   = 1.0 / (1.0 / gMf + 1.0 / gNf);
-		D3 nWf     = sg * nW;
-		D3 fc      = ((W_out[cur] + W_out[i]) + cW) / 3.0;
+		D3 fc = ((aW + bW) + cW) / 3.0;
 		if (area > 0) {
 			acc.area += area;
 			acc.ac = acc.ac + area * fc;
 		}
-		if (area > 1.0e-14 && g_ok) {
+		if (area > 1.0e-14 && !(gMf < 1.0e-14 || gNf < 1.0e-14)) {
+			double g  = 1.0 / (1.0 / gMf + 1.0 / gNf);
 			double b3 = 1 / 3.;
-			double pc = b3 * e[cur];
-			pc += b3 * e[i];
+			double pc = b3 * ea;
+			pc += b3 * eb;
 			pc += b3 * ec;
 			double fn0 = area * pc, k = area * g;
-			D3 f       = face_force(fc, nWf, fn0, k, c);
+			D3 nf      = sg * nW;
+			D3 f       = face_force(fc, nf, fn0, k, c);
 			acc.F      = acc.F + f;
 			acc.tau    = acc.tau + cross(fc, f);
 			acc.n_points += 1;
-			if (io.max_faces > 0) {
-				int slot = atomicAdd(io.face_count, 1);
-				if (slot < io.max_faces) {
-					hcs_face &o = io.faces[slot];
-										o.p[0] = fc.x, o.p[1] = fc.y, o.p[2] = fc.z;
-					o.n[0] = Pd.sign * nWf.x, o.n[1] = Pd.sign * nWf.y, o.n[2] = Pd.sign * nWf.z;
-					o.fn0 = fn0, o.stiffness = k, o.damping = c.dissipation;
-					o.f[0] = Pd.sign * f.x, o.f[1] = Pd.sign * f.y, o.f[2] = Pd.sign * f.z;
-					o.env = info.env, o.pair = info.pair;
-					o.elemM = Pd.sign > 0 ? info.elemA : info.elemB;
-					o.elemN = Pd.sign > 0 ? info.elemB : info.elemA;
-					o.nverts = n, o.face = i;
-				}
-			}
+			if (io.max_faces > 0)
+				dump_face(io, c, fc, nf, fn0, k, f, elemA, elemB, n, i);
 		}
-		cur = i;
+		a = b, aW = bW, ea = eb;
 	}
 }
 
-// Warp-cooperative append of this lane's fan triangles to the tactile pool (ballot-free exclusive scan
-// over lane counts, one atomicAdd per warp).
-__device__ __forceinline__ void emit_tactile(int n_faces, const D3 *W, D3 cW, const double *e, double ec,
-                                             const PairDesc &Pd, const StepIO &io, const EmitInfo &info, int lane)
+// Warp-cooperative append of this lane's fan triangles to the tactile pool: exclusive scan over the lane
+// counts, ONE atomicAdd per warp.  World vertices are recomputed from the shared tile.
+template <bool IDENT>
+__device__ __forceinline__ void emit_tactile(int n_faces, Poly P, const double *e, D3 cen, double ec, const WarpCtx &c,
+                                             const StepIO &io, int slot, int lane)
 {
 	int incl = n_faces;
 #pragma unroll
@@ -281,23 +309,30 @@ __device__ __forceinline__ void emit_tactile(int n_faces, const D3 *W, D3 cW, co
 	base    = __shfl_sync(FULL_MASK, base, 0);
 	int pos = base + incl - n_faces;
 	if (n_faces > 0) {
-		int cur = n_faces - 1;
+		D3 cW     = IDENT ? cen : apply(c.X_WA, cen);
+		int cur   = n_faces - 1;
+		D3 aW     = IDENT ? P.get(cur) : apply(c.X_WA, P.get(cur));
+		double ea = e[cur * 32];
+#pragma unroll 1
 		for (int i = 0; i < n_faces; ++i, ++pos) {
+			D3 bW     = IDENT ? P.get(i) : apply(c.X_WA, P.get(i));
+			double eb = e[i * 32];
 			if (pos < io.max_tris) {
 				// (prev, next, centroid); the M/N swap of ContactSurface reverses winding by swapping the
 				// first two vertices
-				int ia = Pd.sign > 0 ? cur : i, ib = Pd.sign > 0 ? i : cur;
+				bool fwd = c.sign > 0;
+				D3 v0 = fwd ? aW : bW, v1 = fwd ? bW : aW;
 				TactileTri t;
-				t.v[0] = (float)W[ia].x, t.v[1] = (float)W[ia].y, t.v[2] = (float)W[ia].z;
-				t.v[3] = (float)W[ib].x, t.v[4] = (float)W[ib].y, t.v[5] = (float)W[ib].z;
+				t.v[0] = (float)v0.x, t.v[1] = (float)v0.y, t.v[2] = (float)v0.z;
+				t.v[3] = (float)v1.x, t.v[4] = (float)v1.y, t.v[5] = (float)v1.z;
 				t.v[6] = (float)cW.x, t.v[7] = (float)cW.y, t.v[8] = (float)cW.z;
-				t.e[0] = e[ia], t.e[1] = e[ib], t.e[2] = ec;
-				t.env = info.env, t.pair = info.pair, t.order = info.slot * 8 + i;
+				t.e[0] = fwd ? ea : eb, t.e[1] = fwd ? eb : ea, t.e[2] = ec;
+				t.env = c.env, t.pair = c.pair, t.order = slot * 8 + i;
 				io.tri_pool[pos] = t;
 			} else {
 				atomicOr(io.flags, 2);
 			}
-			cur = i;
+			aW = bW, ea = eb;
 		}
 	}
 }
@@ -326,6 +361,17 @@ __device__ __forceinline__ void reduce_and_store(Acc acc, SlicePartial *out, int
 	}
 }
 
+__device__ __forceinline__ void store_zero(SlicePartial *out, int n_candidates)
+{
+	SlicePartial sp;
+	for (int k = 0; k < 3; ++k)
+		sp.F[k] = sp.tau[k] = sp.ac[k] = 0;
+	sp.area = 0;
+	sp.n_polygons = sp.n_faces = sp.n_points = 0;
+	sp.n_candidates = n_candidates;
+	*out = sp;
+}
+
 __device__ __forceinline__ Acc zero_acc()
 {
 	Acc a;
@@ -336,182 +382,76 @@ __device__ __forceinline__ Acc zero_acc()
 }
 
 // =================================================================================================
-// K3 broadphase
-// =================================================================================================
-struct BoxF {
-	float lo[3], hi[3];
-};
-__device__ __forceinline__ bool overlap(const BoxF &q, const float *lo, const float *hi)
-{
-	return q.lo[0] <= hi[0] && q.hi[0] >= lo[0] && q.lo[1] <= hi[1] && q.hi[1] >= lo[1] && q.lo[2] <= hi[2] &&
-	       q.hi[2] >= lo[2];
-}
-
-// QTET: query elements are tets of B (soft-soft) instead of triangles of B (soft-rigid)
-template <bool QTET>
-__global__ void __launch_bounds__(BLOCK) broadphase_kernel(PairDesc P, StepIO io)
-{
-	int warp = (blockIdx.x * BLOCK + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-	int n_units = io.n_env * P.n_slices;
-	if (warp >= n_units)
-		return;
-	int env = warp / P.n_slices, slice = warp - env * P.n_slices;
-	Xform X_WA = load_pose(io.xpos, io.xmat, io.n_geoms, env, P.gA);
-	Xform X_WB = load_pose(io.xpos, io.xmat, io.n_geoms, env, P.gB);
-	// pair-level reject on bounding spheres
-	{
-		D3 ca = apply(X_WA, mk(P.A.bound_c[0], P.A.bound_c[1], P.A.bound_c[2]));
-		D3 cb = apply(X_WB, mk(P.B.bound_c[0], P.B.bound_c[1], P.B.bound_c[2]));
-		D3 d  = ca - cb;
-		double rr = P.A.bound_r + P.B.bound_r + 1e-9;
-		if (dot(d, d) > rr * rr) {
-			if (lane == 0)
-				P.slab_count[warp] = 0;
-			return;
-		}
-	}
-	Xform X_AB = invert_and_compose(X_WA, X_WB);
-	uint2 *slab = P.slab + (size_t)warp * P.cap;
-	int count   = 0;
-	int q_begin = slice * P.slice_q, q_end = min(P.nq, q_begin + P.slice_q);
-	unsigned lt_mask = (1u << lane) - 1u;
-	for (int q0 = q_begin; q0 < q_end; q0 += 32) {
-		int q      = q0 + lane;
-		bool valid = q < q_end;
-		BoxF box;
-		if (valid) {
-			double lo[3] = { 1e300, 1e300, 1e300 }, hi[3] = { -1e300, -1e300, -1e300 };
-			const double *vp = QTET ? &P.B.tet_geom[q].v[0][0] : &P.B.tris[q].v[0][0];
-			const int nv     = QTET ? 4 : 3;
-#pragma unroll
-			for (int i = 0; i < nv; ++i) {
-				D3 p = apply(X_AB, ld3(vp + 3 * i));
-				lo[0] = fmin(lo[0], p.x), lo[1] = fmin(lo[1], p.y), lo[2] = fmin(lo[2], p.z);
-				hi[0] = fmax(hi[0], p.x), hi[1] = fmax(hi[1], p.y), hi[2] = fmax(hi[2], p.z);
-			}
-#pragma unroll
-			for (int a = 0; a < 3; ++a) {
-				box.lo[a] = __double2float_rd(lo[a] - 1e-9);
-				box.hi[a] = __double2float_ru(hi[a] + 1e-9);
-			}
-		}
-		int stack[STACK_SIZE];
-		int sp = 0;
-		if (valid)
-			stack[sp++] = 0;
-		while (__any_sync(FULL_MASK, sp > 0)) {
-			bool hitL = false, hitR = false;
-			int eL = 0, eR = 0;
-			if (sp > 0) {
-				const BvhNode &nd = P.A.nodes[stack[--sp]];
-				float4 a = reinterpret_cast<const float4 *>(&nd)[0], b = reinterpret_cast<const float4 *>(&nd)[1],
-				       c = reinterpret_cast<const float4 *>(&nd)[2], d = reinterpret_cast<const float4 *>(&nd)[3];
-				float llo[3] = { a.x, a.y, a.z }, lhi[3] = { a.w, b.x, b.y }, rlo[3] = { b.z, b.w, c.x },
-				      rhi[3] = { c.y, c.z, c.w };
-				int left = __float_as_int(d.x), right = __float_as_int(d.y);
-				if (overlap(box, llo, lhi)) {
-					if (left < 0)
-						hitL = true, eL = ~left;
-					else if (sp < STACK_SIZE)
-						stack[sp++] = left;
-					else
-						atomicOr(io.flags + 1, 1);
-				}
-				if (overlap(box, rlo, rhi)) {
-					if (right < 0)
-						hitR = true, eR = ~right;
-					else if (sp < STACK_SIZE)
-						stack[sp++] = right;
-					else
-						atomicOr(io.flags + 1, 1);
-				}
-			}
-			unsigned mL = __ballot_sync(FULL_MASK, hitL), mR = __ballot_sync(FULL_MASK, hitR);
-			int nL = __popc(mL), nR = __popc(mR);
-			if (hitL) {
-				int pos = count + __popc(mL & lt_mask);
-				if (pos < P.cap)
-					slab[pos] = make_uint2((unsigned)q, (unsigned)eL);
-			}
-			if (hitR) {
-				int pos = count + nL + __popc(mR & lt_mask);
-				if (pos < P.cap)
-					slab[pos] = make_uint2((unsigned)q, (unsigned)eR);
-			}
-			count += nL + nR;
-		}
-	}
-	if (lane == 0) {
-		if (count > P.cap) {
-			atomicOr(io.flags, 1);
-			count = P.cap;
-		}
-		P.slab_count[warp] = count;
-	}
-}
-
-// =================================================================================================
 // K4 soft-rigid narrowphase: one thread per (tet, triangle) candidate
 // =================================================================================================
 template <bool TRI>
-__global__ void __launch_bounds__(BLOCK) narrow_tet_tri_kernel(PairDesc P, StepIO io)
+__global__ void __launch_bounds__(NP_BLOCK, 3) narrow_tet_tri_kernel(PairDesc P, StepIO io)
 {
-	int warp = (blockIdx.x * BLOCK + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+	extern __shared__ __align__(16) unsigned char smem_raw[];
+	int warp = (blockIdx.x * NP_BLOCK + threadIdx.x) >> 5, lane = threadIdx.x & 31;
 	int n_units = io.n_env * P.n_slices;
 	if (warp >= n_units)
 		return;
 	int env = warp / P.n_slices;
 	int cnt = P.slab_count[warp];
-	Acc acc = zero_acc();
-	if (cnt > 0) {
-		Xform X_WS = load_pose(io.xpos, io.xmat, io.n_geoms, env, P.gA);
-		Xform X_WR = load_pose(io.xpos, io.xmat, io.n_geoms, env, P.gB);
-		Xform X_SR = invert_and_compose(X_WS, X_WR);
-		WarpCtx ctx = make_ctx(P, io, env, X_WS, X_WR);
-		const uint2 *slab = P.slab + (size_t)warp * P.cap;
-		uint8_t *nvout    = P.slab_nverts + (size_t)warp * P.cap;
-		const double kInf = __longlong_as_double(0x7ff0000000000000LL);
-		for (int i0 = 0; i0 < cnt; i0 += 32) {
-			int i       = i0 + lane;
-			int nv      = 0;
-			int tfaces  = 0;
-			D3 W[MAXV], cW = mk(0, 0, 0);
-			double e[MAXV], ec = 0;
-			EmitInfo info{ env, P.index, 0, 0, i };
-			if (i < cnt) {
-				uint2 cand = slab[i];
-				int tri = (int)cand.x, tet = (int)cand.y;
-				info.elemA = tet, info.elemB = tri;
-				acc.n_candidates += 1;
-				const TetField &tf = P.A.tet_field[tet];
-				const TriRec &tr   = P.B.tris[tri];
-				D3 nS   = rot(X_SR.R, ld3(tr.n));
-				D3 ghat = ld3(tf.ghat);
-				if (dot(ghat, nS) > HCS_COS_ALPHA) {
-					D3 bufA[MAXV], bufB[MAXV];
-#pragma unroll
-					for (int k = 0; k < 3; ++k)
-						bufA[k] = apply(X_SR, ld3(tr.v[k]));
-					int n = 3;
-					n = clip_halfspace(bufA, n, ld3(tf.plane[0]), tf.plane[0][3], bufB);
-					n = clip_halfspace(bufB, n, ld3(tf.plane[1]), tf.plane[1][3], bufA);
-					n = clip_halfspace(bufA, n, ld3(tf.plane[2]), tf.plane[2][3], bufB);
-					n = clip_halfspace(bufB, n, ld3(tf.plane[3]), tf.plane[3][3], bufA);
-					n = remove_duplicates(bufA, n);
-					if (n >= 3) {
-						nv      = n;
-						D3 grad = ld3(tf.grad);
-						for (int k = 0; k < n; ++k)
-							e[k] = dot(grad, bufA[k]) + tf.e0;
-						integrate_polygon<TRI, false>(bufA, n, nS, grad, e, kInf, ctx, P, io, info, acc, tfaces, W, cW, ec);
-					}
-				}
-				nvout[i] = (uint8_t)nv;
-			}
-			if (TRI && P.emit_tactile)
-				emit_tactile(tfaces, W, cW, e, ec, P, io, info, lane);
-		}
+	if (cnt == 0) { // nothing to clip: most slices
+		if (lane == 0)
+			store_zero(P.partial + warp, P.slab_evals[warp]);
+		return;
 	}
+	WarpTile &T = reinterpret_cast<WarpTile *>(smem_raw)[threadIdx.x >> 5];
+	Poly buf[2] = { Poly{ &T.xyz[0][0][0][lane] }, Poly{ &T.xyz[1][0][0][lane] } };
+	double *e   = &T.e[0][lane];
+	Acc acc     = zero_acc();
+	Xform X_WS = load_pose(io.xpos, io.xmat, io.n_geoms, env, P.gA);
+	Xform X_WR = load_pose(io.xpos, io.xmat, io.n_geoms, env, P.gB);
+	Xform X_SR = invert_and_compose(X_WS, X_WR);
+	WarpCtx ctx = make_ctx(P, io, env, X_WS, X_WR);
+	const uint2 *slab = P.slab + (size_t)warp * P.cap;
+	uint8_t *nvout    = P.slab_nverts + (size_t)warp * P.cap;
+	const double kInf = __longlong_as_double(0x7ff0000000000000LL);
+#pragma unroll 1
+	for (int i0 = 0; i0 < cnt; i0 += 32) {
+		int i      = i0 + lane;
+		int tfaces = 0;
+		int cur    = 0;
+		D3 cen     = mk(0, 0, 0);
+		double ec  = 0;
+		if (i < cnt) {
+			uint2 cand = slab[i];
+			int tri = (int)cand.x, tet = (int)cand.y;
+			const TetField &tf = P.A.tet_field[tet];
+			const TriRec &tr   = P.B.tris[tri];
+			// the normal/gradient cull and the trivial reject already ran in the broadphase
+			D3 nS = rot(X_SR.R, ld3(tr.n));
+#pragma unroll
+			for (int k = 0; k < 3; ++k)
+				buf[0].set(k, apply(X_SR, ld3(tr.v[k])));
+			int n = 3;
+#pragma unroll 1
+			for (int k = 0; k < 4; ++k) {
+				n = clip_halfspace(buf[cur], n, ld3(tf.plane[k]), tf.plane[k][3], buf[cur ^ 1]);
+				cur ^= 1;
+			}
+			n      = remove_duplicates(buf[cur], n);
+			int nv = 0;
+			if (n >= 3) {
+				nv        = n;
+				D3 grad   = ld3(tf.grad);
+				double e0 = tf.e0;
+#pragma unroll 1
+				for (int k = 0; k < n; ++k)
+					e[k * 32] = dot(grad, buf[cur].get(k)) + e0;
+				integrate_polygon<TRI, false>(buf[cur], n, nS, grad, e, kInf, ctx, io, tet, tri, acc, cen, ec);
+				tfaces = n;
+			}
+			nvout[i] = (uint8_t)nv;
+		}
+		if (TRI && P.emit_tactile)
+			emit_tactile<false>(tfaces, buf[cur], e, cen, ec, ctx, io, i, lane);
+	}
+	if (lane == 0)
+		acc.n_candidates = P.slab_evals[warp];
 	reduce_and_store(acc, P.partial + warp, lane);
 }
 
@@ -519,116 +459,131 @@ __global__ void __launch_bounds__(BLOCK) narrow_tet_tri_kernel(PairDesc P, StepI
 // K6 soft-soft narrowphase: one thread per (tet of A, tet of B) candidate
 // =================================================================================================
 template <bool TRI>
-__global__ void __launch_bounds__(BLOCK) narrow_tet_tet_kernel(PairDesc P, StepIO io)
+__global__ void __launch_bounds__(NP_BLOCK, 3) narrow_tet_tet_kernel(PairDesc P, StepIO io)
 {
-	int warp = (blockIdx.x * BLOCK + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+	extern __shared__ __align__(16) unsigned char smem_raw[];
+	int warp = (blockIdx.x * NP_BLOCK + threadIdx.x) >> 5, lane = threadIdx.x & 31;
 	int n_units = io.n_env * P.n_slices;
 	if (warp >= n_units)
 		return;
 	int env = warp / P.n_slices;
 	int cnt = P.slab_count[warp];
-	Acc acc = zero_acc();
-	if (cnt > 0) {
-		Xform X_WM = load_pose(io.xpos, io.xmat, io.n_geoms, env, P.gA);
-		Xform X_WN = load_pose(io.xpos, io.xmat, io.n_geoms, env, P.gB);
-		Xform X_MN = invert_and_compose(X_WM, X_WN);
-		D3 p_NMo   = -rotT(X_MN.R, X_MN.p);
-		WarpCtx ctx = make_ctx(P, io, env, X_WM, X_WN);
-		const uint2 *slab = P.slab + (size_t)warp * P.cap;
-		uint8_t *nvout    = P.slab_nverts + (size_t)warp * P.cap;
-		for (int i0 = 0; i0 < cnt; i0 += 32) {
-			int i      = i0 + lane;
-			int nv     = 0;
-			int tfaces = 0;
-			D3 W[MAXV], cW = mk(0, 0, 0);
-			double e[MAXV], ec = 0;
-			EmitInfo info{ env, P.index, 0, 0, i };
-			if (i < cnt) {
-				uint2 cand = slab[i];
-				int t1 = (int)cand.x, t0 = (int)cand.y;
-				info.elemA = t0, info.elemB = t1;
-				acc.n_candidates += 1;
-				const TetField &f0 = P.A.tet_field[t0];
-				const TetField &f1 = P.B.tet_field[t1];
-				// CalcEquilibriumPlane
-				D3 grad0 = ld3(f0.grad), grad1_N = ld3(f1.grad);
-				double f0_Mo = f0.e0;
-				D3 grad1_M   = rot(X_MN.R, grad1_N);
-				double f1_Mo = dot(grad1_N, p_NMo) + f1.e0;
-				D3 n_M       = grad0 - grad1_M;
-				double mag   = sqrt(dot(n_M, n_M));
-				bool ok      = mag > 0.0;
-				D3 nhat      = mk(0, 0, 1);
-				double pd    = 0;
-				if (ok) {
-					nhat    = n_M / mag;
-					D3 p_MQ = -((f0_Mo - f1_Mo) / mag) * nhat;
-					pd      = dot(nhat, p_MQ);
-					ok      = dot(nhat, ld3(f0.ghat)) > HCS_COS_ALPHA;
-				}
-				if (ok) {
-					D3 rev_N = rotT(X_MN.R, -nhat);
-					ok       = dot(rev_N, ld3(f1.ghat)) > HCS_COS_ALPHA;
-				}
-				D3 bufA[MAXV], bufB[MAXV];
-				int n = 0;
-				if (ok) { // SliceTetrahedronWithPlane(tet0)
-					const TetGeom &g0 = P.A.tet_geom[t0];
-					double dist[4];
-					int code = 0;
-#pragma unroll
-					for (int k = 0; k < 4; ++k) {
-						dist[k] = dot(nhat, ld3(g0.v[k])) - pd;
-						if (dist[k] > 0)
-							code |= 1 << k;
-					}
-					for (int ed = 0; ed < 4; ++ed) {
-						int edge = c_marching_tets[code][ed];
-						if (edge < 0)
-							break;
-						int l0 = c_tet_edges[edge][0], l1 = c_tet_edges[edge][1];
-						D3 a = ld3(g0.v[l0]), b = ld3(g0.v[l1]);
-						double t  = dist[l0] / (dist[l0] - dist[l1]);
-						bufA[n++] = a + t * (b - a);
-					}
-					n  = remove_duplicates(bufA, n);
-					ok = n >= 3;
-				}
-				if (ok) { // clip by the four half spaces of tet1 expressed in M
-					const TetGeom &g1 = P.B.tet_geom[t1];
-					D3 pv[4];
-#pragma unroll
-					for (int k = 0; k < 4; ++k)
-						pv[k] = apply(X_MN, ld3(g1.v[k]));
-					const int F[4][3] = { { 1, 2, 3 }, { 0, 3, 2 }, { 0, 1, 3 }, { 0, 2, 1 } };
-					D3 *in = bufA, *out = bufB;
-#pragma unroll
-					for (int k = 0; k < 4; ++k) {
-						if (ok) {
-							D3 A = pv[F[k][0]], B = pv[F[k][1]], C = pv[F[k][2]];
-							D3 nh = normalized(cross(B - A, C - A));
-							n     = clip_halfspace(in, n, nh, dot(nh, A), out);
-							n     = remove_duplicates(out, n);
-							ok    = n >= 3;
-							D3 *tmp = in;
-							in      = out;
-							out     = tmp;
-						}
-					}
-					if (ok) {
-						nv = n;
-						for (int k = 0; k < n; ++k)
-							e[k] = dot(grad0, in[k]) + f0_Mo;
-						double gN = -dot(grad1_M, nhat);
-						integrate_polygon<TRI, false>(in, n, nhat, grad0, e, gN, ctx, P, io, info, acc, tfaces, W, cW, ec);
-					}
-				}
-				nvout[i] = (uint8_t)nv;
-			}
-			if (TRI && P.emit_tactile)
-				emit_tactile(tfaces, W, cW, e, ec, P, io, info, lane);
-		}
+	if (cnt == 0) {
+		if (lane == 0)
+			store_zero(P.partial + warp, P.slab_evals[warp]);
+		return;
 	}
+	WarpTile &T = reinterpret_cast<WarpTile *>(smem_raw)[threadIdx.x >> 5];
+	Poly buf[2] = { Poly{ &T.xyz[0][0][0][lane] }, Poly{ &T.xyz[1][0][0][lane] } };
+	double *e   = &T.e[0][lane];
+	Acc acc     = zero_acc();
+	Xform X_WM = load_pose(io.xpos, io.xmat, io.n_geoms, env, P.gA);
+	Xform X_WN = load_pose(io.xpos, io.xmat, io.n_geoms, env, P.gB);
+	Xform X_MN = invert_and_compose(X_WM, X_WN);
+	D3 p_NMo   = -rotT(X_MN.R, X_MN.p);
+	WarpCtx ctx = make_ctx(P, io, env, X_WM, X_WN);
+	const uint2 *slab = P.slab + (size_t)warp * P.cap;
+	uint8_t *nvout    = P.slab_nverts + (size_t)warp * P.cap;
+#pragma unroll 1
+	for (int i0 = 0; i0 < cnt; i0 += 32) {
+		int i      = i0 + lane;
+		int tfaces = 0;
+		int cur    = 0;
+		D3 cen     = mk(0, 0, 0);
+		double ec  = 0;
+		if (i < cnt) {
+			uint2 cand = slab[i];
+			int t1 = (int)cand.x, t0 = (int)cand.y;
+			const TetField &f0 = P.A.tet_field[t0];
+			const TetField &f1 = P.B.tet_field[t1];
+			// CalcEquilibriumPlane
+			D3 grad0 = ld3(f0.grad), grad1_N = ld3(f1.grad);
+			double f0_Mo = f0.e0;
+			D3 grad1_M   = rot(X_MN.R, grad1_N);
+			double f1_Mo = dot(grad1_N, p_NMo) + f1.e0;
+			D3 n_M       = grad0 - grad1_M;
+			double mag   = sqrt(dot(n_M, n_M));
+			bool ok      = mag > 0.0;
+			D3 nhat      = mk(0, 0, 1);
+			double pd    = 0;
+			if (ok) {
+				nhat    = n_M / mag;
+				D3 p_MQ = -((f0_Mo - f1_Mo) / mag) * nhat;
+				pd      = dot(nhat, p_MQ);
+				ok      = dot(nhat, ld3(f0.ghat)) > HCS_COS_ALPHA;
+			}
+			if (ok) {
+				D3 rev_N = rotT(X_MN.R, -nhat);
+				ok       = dot(rev_N, ld3(f1.ghat)) > HCS_COS_ALPHA;
+			}
+			int n = 0;
+			if (ok) { // SliceTetrahedronWithPlane(tet0)
+				const TetGeom &g0 = P.A.tet_geom[t0];
+				double dist[4];
+				int code = 0;
+#pragma unroll
+				for (int k = 0; k < 4; ++k) {
+					dist[k] = dot(nhat, ld3(g0.v[k])) - pd;
+					if (dist[k] > 0)
+						code |= 1 << k;
+				}
+#pragma unroll 1
+				for (int ed = 0; ed < 4; ++ed) {
+					int edge = c_marching_tets[code][ed];
+					if (edge < 0)
+						break;
+					int l0 = c_tet_edges[edge][0], l1 = c_tet_edges[edge][1];
+					D3 a = ld3(g0.v[l0]), b = ld3(g0.v[l1]);
+					double d0 = pick4(dist, l0), d1 = pick4(dist, l1);
+					double t  = d0 / (d0 - d1);
+					buf[0].set(n++, a + t * (b - a));
+				}
+				n  = remove_duplicates(buf[0], n);
+				ok = n >= 3;
+			}
+			if (ok) { // clip by the four half spaces of tet1 expressed in M
+				const TetGeom &g1 = P.B.tet_geom[t1];
+				D3 pv[4];
+#pragma unroll
+				for (int k = 0; k < 4; ++k)
+					pv[k] = apply(X_MN, ld3(g1.v[k]));
+#pragma unroll
+				for (int k = 0; k < 4; ++k) {
+					if (ok) {
+						D3 A, B, C; // outward faces {1,2,3},{0,3,2},{0,1,3},{0,2,1}
+						if (k == 0)
+							A = pv[1], B = pv[2], C = pv[3];
+						else if (k == 1)
+							A = pv[0], B = pv[3], C = pv[2];
+						else if (k == 2)
+							A = pv[0], B = pv[1], C = pv[3];
+						else
+							A = pv[0], B = pv[2], C = pv[1];
+						D3 nh = normalized(cross(B - A, C - A));
+						n     = clip_halfspace(buf[cur], n, nh, dot(nh, A), buf[cur ^ 1]);
+						cur ^= 1;
+						n  = remove_duplicates(buf[cur], n);
+						ok = n >= 3;
+					}
+				}
+			}
+			int nv = 0;
+			if (ok) {
+				nv = n;
+#pragma unroll 1
+				for (int k = 0; k < n; ++k)
+					e[k * 32] = dot(grad0, buf[cur].get(k)) + f0_Mo;
+				double gN = -dot(grad1_M, nhat);
+				integrate_polygon<TRI, false>(buf[cur], n, nhat, grad0, e, gN, ctx, io, t0, t1, acc, cen, ec);
+				tfaces = n;
+			}
+			nvout[i] = (uint8_t)nv;
+		}
+		if (TRI && P.emit_tactile)
+			emit_tactile<false>(tfaces, buf[cur], e, cen, ec, ctx, io, i, lane);
+	}
+	if (lane == 0)
+		acc.n_candidates = P.slab_evals[warp];
 	reduce_and_store(acc, P.partial + warp, lane);
 }
 
@@ -636,14 +591,18 @@ __global__ void __launch_bounds__(BLOCK) narrow_tet_tet_kernel(PairDesc P, StepI
 // K5 soft-half-space narrowphase: one thread per tet of the soft geom (no candidate list needed)
 // =================================================================================================
 template <bool TRI>
-__global__ void __launch_bounds__(BLOCK) narrow_tet_plane_kernel(PairDesc P, StepIO io)
+__global__ void __launch_bounds__(NP_BLOCK, 3) narrow_tet_plane_kernel(PairDesc P, StepIO io)
 {
-	int warp = (blockIdx.x * BLOCK + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+	extern __shared__ __align__(16) unsigned char smem_raw[];
+	int warp = (blockIdx.x * NP_BLOCK + threadIdx.x) >> 5, lane = threadIdx.x & 31;
 	int n_units = io.n_env * P.n_slices;
 	if (warp >= n_units)
 		return;
 	int env = warp / P.n_slices, slice = warp - env * P.n_slices;
-	Acc acc = zero_acc();
+	WarpTile &T = reinterpret_cast<WarpTile *>(smem_raw)[threadIdx.x >> 5];
+	Poly poly   = Poly{ &T.xyz[0][0][0][lane] };
+	double *e   = &T.e[0][lane];
+	Acc acc     = zero_acc();
 	Xform X_WS = load_pose(io.xpos, io.xmat, io.n_geoms, env, P.gA);
 	Xform X_WR = load_pose(io.xpos, io.xmat, io.n_geoms, env, P.gB);
 	Xform X_SR = invert_and_compose(X_WS, X_WR);
@@ -654,12 +613,12 @@ __global__ void __launch_bounds__(BLOCK) narrow_tet_plane_kernel(PairDesc P, Ste
 	const double kInf = __longlong_as_double(0x7ff0000000000000LL);
 	int q_begin = slice * P.slice_q, q_end = min(P.nq, q_begin + P.slice_q);
 	uint8_t *nvout = P.slab_nverts + (size_t)env * P.nq;
+#pragma unroll 1
 	for (int q0 = q_begin; q0 < q_end; q0 += 32) {
 		int t      = q0 + lane;
 		int tfaces = 0;
-		D3 W[MAXV], cW = mk(0, 0, 0);
-		double e[MAXV], ec = 0;
-		EmitInfo info{ env, P.index, t, 0, t };
+		D3 cen     = mk(0, 0, 0);
+		double ec  = 0;
 		if (t < q_end) {
 			acc.n_candidates += 1;
 			const TetGeom &g = P.A.tet_geom[t];
@@ -673,33 +632,36 @@ __global__ void __launch_bounds__(BLOCK) narrow_tet_plane_kernel(PairDesc P, Ste
 			}
 			int nv = 0;
 			if (code != 0 && code != 15) {
-				int4 gid4   = reinterpret_cast<const int4 *>(P.A.elems)[t];
-				int gid[4]  = { gid4.x, gid4.y, gid4.z, gid4.w };
-				D3 poly[4];
+				int4 gid4 = reinterpret_cast<const int4 *>(P.A.elems)[t];
+#pragma unroll 1
 				for (int ed = 0; ed < 4; ++ed) {
 					int edge = c_marching_tets[code][ed];
 					if (edge < 0)
 						break;
 					int l0 = c_tet_edges[edge][0], l1 = c_tet_edges[edge][1];
-					if (gid[l0] > gid[l1]) { // canonical direction: lower global vertex id first
+					int g0 = l0 == 0 ? gid4.x : (l0 == 1 ? gid4.y : (l0 == 2 ? gid4.z : gid4.w));
+					int g1 = l1 == 0 ? gid4.x : (l1 == 1 ? gid4.y : (l1 == 2 ? gid4.z : gid4.w));
+					if (g0 > g1) { // canonical direction: lower global vertex id first
 						int tmp = l0;
 						l0      = l1;
 						l1      = tmp;
 					}
+					double d0 = pick4(dist, l0), d1 = pick4(dist, l1);
 					D3 a = ld3(g.v[l0]), b = ld3(g.v[l1]);
-					double tt = dist[l0] / (dist[l0] - dist[l1]);
-					D3 pc     = a + tt * (b - a);
-					e[nv]     = g.e[l0] + tt * (g.e[l1] - g.e[l0]);
-					poly[nv]  = apply(X_WS, pc);
+					double tt  = d0 / (d0 - d1);
+					D3 pc      = a + tt * (b - a);
+					e[nv * 32] = g.e[l0] + tt * (g.e[l1] - g.e[l0]);
+					poly.set(nv, apply(X_WS, pc));
 					++nv;
 				}
 				D3 grad_W = rot(X_WS.R, ld3(P.A.tet_field[t].grad));
-				integrate_polygon<TRI, true>(poly, nv, nhat_W, grad_W, e, kInf, ctx, P, io, info, acc, tfaces, W, cW, ec);
+				integrate_polygon<TRI, true>(poly, nv, nhat_W, grad_W, e, kInf, ctx, io, t, 0, acc, cen, ec);
+				tfaces = nv;
 			}
 			nvout[t] = (uint8_t)nv;
 		}
 		if (TRI && P.emit_tactile)
-			emit_tactile(tfaces, W, cW, e, ec, P, io, info, lane);
+			emit_tactile<true>(tfaces, poly, e, cen, ec, ctx, io, t, lane);
 	}
 	reduce_and_store(acc, P.partial + warp, lane);
 }
@@ -769,17 +731,12 @@ __global__ void finalize_geoms_kernel(const PairDesc *pairs, StepIO io)
 // =================================================================================================
 // launchers
 // =================================================================================================
-static inline int blocks_for_warps(long n_warps) { return (int)((n_warps + WARPS_PER_BLOCK - 1) / WARPS_PER_BLOCK); }
-
-void launch_broadphase(const PairDesc &P, const StepIO &io, cudaStream_t s)
+template <class K>
+static void launch_np(K kernel, int grid, const PairDesc &P, const StepIO &io, cudaStream_t s)
 {
-	long units = (long)io.n_env * P.n_slices;
-	if (units == 0)
-		return;
-	if (P.kind == PAIR_SOFT_RIGID)
-		broadphase_kernel<false><<<blocks_for_warps(units), BLOCK, 0, s>>>(P, io);
-	else if (P.kind == PAIR_SOFT_SOFT)
-		broadphase_kernel<true><<<blocks_for_warps(units), BLOCK, 0, s>>>(P, io);
+	// opt in to > 48 KB dynamic shared memory (idempotent and cheap; contexts may live on several devices)
+	cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)NP_SMEM);
+	kernel<<<grid, NP_BLOCK, NP_SMEM, s>>>(P, io);
 }
 
 void launch_narrowphase(const PairDesc &P, const StepIO &io, cudaStream_t s)
@@ -787,26 +744,26 @@ void launch_narrowphase(const PairDesc &P, const StepIO &io, cudaStream_t s)
 	long units = (long)io.n_env * P.n_slices;
 	if (units == 0)
 		return;
-	int grid = blocks_for_warps(units);
+	int grid = (int)((units + NP_WARPS - 1) / NP_WARPS);
 	bool tri = io.representation == HCS_REP_TRIANGLE;
 	switch (P.kind) {
 		case PAIR_SOFT_RIGID:
 			if (tri)
-				narrow_tet_tri_kernel<true><<<grid, BLOCK, 0, s>>>(P, io);
+				launch_np(narrow_tet_tri_kernel<true>, grid, P, io, s);
 			else
-				narrow_tet_tri_kernel<false><<<grid, BLOCK, 0, s>>>(P, io);
+				launch_np(narrow_tet_tri_kernel<false>, grid, P, io, s);
 			break;
 		case PAIR_SOFT_SOFT:
 			if (tri)
-				narrow_tet_tet_kernel<true><<<grid, BLOCK, 0, s>>>(P, io);
+				launch_np(narrow_tet_tet_kernel<true>, grid, P, io, s);
 			else
-				narrow_tet_tet_kernel<false><<<grid, BLOCK, 0, s>>>(P, io);
+				launch_np(narrow_tet_tet_kernel<false>, grid, P, io, s);
 			break;
 		case PAIR_SOFT_PLANE:
 			if (tri)
-				narrow_tet_plane_kernel<true><<<grid, BLOCK, 0, s>>>(P, io);
+				launch_np(narrow_tet_plane_kernel<true>, grid, P, io, s);
 			else
-				narrow_tet_plane_kernel<false><<<grid, BLOCK, 0, s>>>(P, io);
+				launch_np(narrow_tet_plane_kernel<false>, grid, P, io, s);
 			break;
 		default:
 			break;
