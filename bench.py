@@ -274,7 +274,7 @@ def main():
     barrier()
     e2e_s = time.perf_counter() - t0
     h2d = n_envs * ng * 18 * 8
-    d2h = n_envs * (npairs * 104 + ng * 48) + 16
+    d2h = n_envs * (npairs * 112 + ng * 48) + 16
     if with_sensors:
         d2h += sum(n_envs * cx * cy * 4 for cx, cy in eng.sensors)
 
@@ -319,6 +319,7 @@ def main():
             "pair_evals_per_sec": cand_all / (dev_ms_max * 1e-3),
             "pair_evals_per_env_step": cand_all / (total_envs * args.steps),
             "polygons_per_env_step": poly_all / (total_envs * args.steps),
+            "clipped_pairs_per_env_step_rank0": float(res["n_clipped"].sum()) / n_envs,
             "stage_ms_per_step": {k: v / args.steps for k, v in stage.items()},
             "wall_ms_per_step_incl_flush_and_readback": 1e3 * (wall1 - wall0) / args.steps,
             "e2e": {"value": e2e_val, "unit": "env-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,

@@ -77,7 +77,9 @@ typedef struct hcs_pair_result {
 	int32_t n_polygons; /* contact polygons emitted (= |emitted candidate set|) */
 	int32_t n_faces;    /* faces of the surface (kPolygon: = n_polygons; kTriangle: fan triangles) */
 	int32_t n_points;   /* PointCollisions that pass plugin.cpp:345 and :362 */
-	int32_t n_candidates; /* narrowphase pair-evals spent on this pair */
+	int32_t n_candidates; /* pair-evals spent on this pair: LBVH leaf hits / tets sliced (cull + clip) */
+	int32_t n_clipped;    /* pair-evals that survived the early-outs and ran the clipper */
+	int32_t reserved;
 } hcs_pair_result;
 
 /* one PointCollision (CS/include/mujoco_contact_surfaces/common_types.h:48-56) plus provenance */

@@ -54,7 +54,7 @@ enum PairKind { PAIR_NONE = 0, PAIR_SOFT_RIGID = 1, PAIR_SOFT_PLANE = 2, PAIR_SO
 
 struct SlicePartial { // one warp's deterministic partial sums
 	double F[3], tau[3], area, ac[3];
-	int32_t n_polygons, n_faces, n_points, n_candidates;
+	int32_t n_polygons, n_faces, n_points, n_candidates, n_clipped, pad;
 };
 
 struct TactileTri { // kTriangle contact-surface triangle handed to the tactile stage (72 B)

@@ -146,6 +146,14 @@ __global__ void __launch_bounds__(BP_BLOCK) broadphase_kernel(PairDesc P, StepIO
 								if (sa > 1e-12 && sb > 1e-12 && sc > 1e-12)
 									keep = false;
 							}
+							// the triangle's plane must cut the tet: all four tet vertices strictly on one side => empty
+							const TetGeom &tg = P.A.tet_geom[it.y];
+							double dt = dot(nS, a);
+							double h0 = dot(nS, ld3(tg.v[0])) - dt, h1 = dot(nS, ld3(tg.v[1])) - dt,
+							       h2 = dot(nS, ld3(tg.v[2])) - dt, h3 = dot(nS, ld3(tg.v[3])) - dt;
+							if ((h0 > 1e-12 && h1 > 1e-12 && h2 > 1e-12 && h3 > 1e-12) ||
+							    (h0 < -1e-12 && h1 < -1e-12 && h2 < -1e-12 && h3 < -1e-12))
+								keep = false;
 						}
 					}
 				}

@@ -54,7 +54,7 @@ struct WarpCtx { // warp-uniform per (env, pair) data
 struct Acc {
 	D3 F, tau, ac;
 	double area;
-	int n_polygons, n_faces, n_points, n_candidates;
+	int n_polygons, n_faces, n_points, n_candidates, n_clipped;
 };
 
 __device__ __forceinline__ void load_vel(const double *vel, int n_geoms, int env, int g, D3 &w, D3 &v)
@@ -340,14 +340,14 @@ __device__ __forceinline__ void emit_tactile(int n_faces, Poly P, const double *
 __device__ __forceinline__ void reduce_and_store(Acc acc, SlicePartial *out, int lane)
 {
 	double d[10] = { acc.F.x, acc.F.y, acc.F.z, acc.tau.x, acc.tau.y, acc.tau.z, acc.area, acc.ac.x, acc.ac.y, acc.ac.z };
-	int n[4]     = { acc.n_polygons, acc.n_faces, acc.n_points, acc.n_candidates };
+	int n[5]     = { acc.n_polygons, acc.n_faces, acc.n_points, acc.n_candidates, acc.n_clipped };
 #pragma unroll
 	for (int o = 16; o > 0; o >>= 1) {
 #pragma unroll
 		for (int k = 0; k < 10; ++k)
 			d[k] += __shfl_xor_sync(FULL_MASK, d[k], o);
 #pragma unroll
-		for (int k = 0; k < 4; ++k)
+		for (int k = 0; k < 5; ++k)
 			n[k] += __shfl_xor_sync(FULL_MASK, n[k], o);
 	}
 	if (lane == 0) {
@@ -356,7 +356,8 @@ __device__ __forceinline__ void reduce_and_store(Acc acc, SlicePartial *out, int
 		sp.tau[0] = d[3], sp.tau[1] = d[4], sp.tau[2] = d[5];
 		sp.area = d[6];
 		sp.ac[0] = d[7], sp.ac[1] = d[8], sp.ac[2] = d[9];
-		sp.n_polygons = n[0], sp.n_faces = n[1], sp.n_points = n[2], sp.n_candidates = n[3];
+		sp.n_polygons = n[0], sp.n_faces = n[1], sp.n_points = n[2], sp.n_candidates = n[3], sp.n_clipped = n[4];
+		sp.pad = 0;
 		*out = sp;
 	}
 }
@@ -369,6 +370,7 @@ __device__ __forceinline__ void store_zero(SlicePartial *out, int n_candidates)
 	sp.area = 0;
 	sp.n_polygons = sp.n_faces = sp.n_points = 0;
 	sp.n_candidates = n_candidates;
+	sp.n_clipped = sp.pad = 0;
 	*out = sp;
 }
 
@@ -377,7 +379,7 @@ __device__ __forceinline__ Acc zero_acc()
 	Acc a;
 	a.F = a.tau = a.ac = mk(0, 0, 0);
 	a.area                                                  = 0;
-	a.n_polygons = a.n_faces = a.n_points = a.n_candidates = 0;
+	a.n_polygons = a.n_faces = a.n_points = a.n_candidates = a.n_clipped = 0;
 	return a;
 }
 
@@ -420,6 +422,7 @@ __global__ void __launch_bounds__(NP_BLOCK, 3) narrow_tet_tri_kernel(PairDesc P,
 		if (i < cnt) {
 			uint2 cand = slab[i];
 			int tri = (int)cand.x, tet = (int)cand.y;
+			acc.n_clipped += 1;
 			const TetField &tf = P.A.tet_field[tet];
 			const TriRec &tr   = P.B.tris[tri];
 			// the normal/gradient cull and the trivial reject already ran in the broadphase
@@ -494,6 +497,7 @@ __global__ void __launch_bounds__(NP_BLOCK, 3) narrow_tet_tet_kernel(PairDesc P,
 		if (i < cnt) {
 			uint2 cand = slab[i];
 			int t1 = (int)cand.x, t0 = (int)cand.y;
+			acc.n_clipped += 1;
 			const TetField &f0 = P.A.tet_field[t0];
 			const TetField &f1 = P.B.tet_field[t1];
 			// CalcEquilibriumPlane
@@ -632,6 +636,7 @@ __global__ void __launch_bounds__(NP_BLOCK, 3) narrow_tet_plane_kernel(PairDesc 
 			}
 			int nv = 0;
 			if (code != 0 && code != 15) {
+				acc.n_clipped += 1;
 				int4 gid4 = reinterpret_cast<const int4 *>(P.A.elems)[t];
 #pragma unroll 1
 				for (int ed = 0; ed < 4; ++ed) {
@@ -681,7 +686,7 @@ __global__ void finalize_pairs_kernel(const PairDesc *pairs, StepIO io)
 		r.F[k] = r.tau[k] = r.centroid[k] = 0;
 	r.area = 0;
 	r.gM = P.gM, r.gN = P.gN;
-	r.n_polygons = r.n_faces = r.n_points = r.n_candidates = 0;
+	r.n_polygons = r.n_faces = r.n_points = r.n_candidates = r.n_clipped = r.reserved = 0;
 	if (P.kind != PAIR_NONE) {
 		double ac[3] = { 0, 0, 0 };
 		const SlicePartial *sp = P.partial + (size_t)env * P.n_slices;
@@ -696,6 +701,7 @@ __global__ void finalize_pairs_kernel(const PairDesc *pairs, StepIO io)
 			r.n_faces += sp[s].n_faces;
 			r.n_points += sp[s].n_points;
 			r.n_candidates += sp[s].n_candidates;
+			r.n_clipped += sp[s].n_clipped;
 		}
 		for (int k = 0; k < 3; ++k) {
 			r.F[k] *= P.sign;

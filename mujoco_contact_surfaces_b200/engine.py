@@ -26,11 +26,12 @@ class HcsConfig(C.Structure):
 
 PAIR_RESULT_DTYPE = np.dtype([("F", "<f8", 3), ("tau", "<f8", 3), ("centroid", "<f8", 3), ("area", "<f8"),
                               ("gM", "<i4"), ("gN", "<i4"), ("n_polygons", "<i4"), ("n_faces", "<i4"),
-                              ("n_points", "<i4"), ("n_candidates", "<i4")], align=True)
+                              ("n_points", "<i4"), ("n_candidates", "<i4"), ("n_clipped", "<i4"),
+                              ("reserved", "<i4")], align=True)
 FACE_DTYPE = np.dtype([("p", "<f8", 3), ("n", "<f8", 3), ("fn0", "<f8"), ("stiffness", "<f8"), ("damping", "<f8"),
                        ("f", "<f8", 3), ("env", "<i4"), ("pair", "<i4"), ("elemM", "<i4"), ("elemN", "<i4"),
                        ("nverts", "<i4"), ("face", "<i4")], align=True)
-assert PAIR_RESULT_DTYPE.itemsize == 104 and FACE_DTYPE.itemsize == 120
+assert PAIR_RESULT_DTYPE.itemsize == 112 and FACE_DTYPE.itemsize == 120
 
 # every symbol include/hcs.h declares (tests check the library exports all of them)
 ABI_SYMBOLS = [
