@@ -1,0 +1,512 @@
+// Host adapter: the reference's MujocoContactSurfacesPlugin / SurfacePlugin / FlatTactileSensor surface on
+// top of the CUDA engine (libhcs_b200, include/hcs.h).  See contact_surfaces_plugin.h for the mapping.
+//
+// Differences to the reference's control flow (behaviour preserved):
+//  * collision_cb (plugin.cpp:255-318) only RECORDS the geom pair MuJoCo hands over and returns the same
+//    contact count (0 when forces are applied); the contact surfaces of all recorded pairs are computed in
+//    ONE batched GPU call at the start of passiveCallback, where the reference consumes them (:411-523).
+//  * two mj_applyFT per face (:477-482) become one mj_applyFT per geom with the reduced wrench — exact,
+//    because mj_applyFT is linear in (force, torque about the application point).
+//  * Q1 (numeric_size indexed by address, :596,:606) and Q2 (onGeomChanged drops the new pressure field,
+//    :842-845) are consciously fixed, not reproduced.
+#include "contact_surfaces_plugin.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+
+namespace mujoco_ros::contact_surfaces {
+
+namespace {
+// plugin.cpp:88-95
+std::map<const mjData *, MujocoContactSurfacesPlugin *> instance_map;
+mjfCollision defaultCollisionFunctions[mjNGEOMTYPES][mjNGEOMTYPES];
+
+int collision_cb_wrapper(const mjModel *m, const mjData *d, mjContact *con, int g1, int g2, mjtNum margin)
+{
+	return instance_map[d]->collision_cb(m, d, con, g1, g2, margin);
+}
+
+void log_info(const char *fmt, const char *a = "", const char *b = "")
+{
+	if (std::getenv("HCS_PLUGIN_VERBOSE")) {
+		std::fprintf(stderr, "[mujoco_contact_surfaces] ");
+		std::fprintf(stderr, fmt, a, b);
+		std::fprintf(stderr, "\n");
+	}
+}
+} // namespace
+
+MujocoContactSurfacesPlugin::MujocoContactSurfacesPlugin() {}
+
+// plugin.cpp:191-206
+MujocoContactSurfacesPlugin::~MujocoContactSurfacesPlugin()
+{
+	geomCollisions.clear();
+	contactProperties.clear();
+	instance_map.erase(d_);
+	if (instance_map.empty()) {
+		for (int i = 0; i < mjNGEOMTYPES; ++i)
+			for (int j = 0; j < mjNGEOMTYPES; ++j)
+				if (mjCOLLISIONFUNC[i][j] == collision_cb_wrapper)
+					mjCOLLISIONFUNC[i][j] = defaultCollisionFunctions[i][j];
+	}
+	if (ctx_)
+		hcs_destroy(ctx_);
+	delete[] vGeoms;
+}
+
+void MujocoContactSurfacesPlugin::addSurfacePlugin(SurfacePluginPtr plugin, const PluginConfig &config)
+{
+	plugin->init(config, "");
+	plugin->attach(this);
+	plugins.push_back(plugin);
+}
+
+int MujocoContactSurfacesPlugin::configIndex(int mujoco_geom_id) const
+{
+	auto it = contactProperties.find(mujoco_geom_id);
+	return it == contactProperties.end() ? -1 : it->second->drake_id;
+}
+
+// plugin.cpp:208-245
+bool MujocoContactSurfacesPlugin::load(const mjModel *m, mjData *d)
+{
+	parseMujocoCustomFields(m);
+	if (!ctx_)
+		return false; // no CUDA device: there is no CPU fallback
+	d_              = d;
+	m_              = m;
+	instance_map[d] = this;
+	if (instance_map.size() == 1)
+		initCollisionFunction();
+	for (const auto &plugin : plugins)
+		if (plugin->safe_load(m, d))
+			cb_ready_plugins.push_back(plugin);
+	return true;
+}
+
+// plugin.cpp:247-253
+void MujocoContactSurfacesPlugin::reset()
+{
+	geomCollisions.clear();
+	step_pairs_.clear();
+	for (const auto &plugin : plugins)
+		plugin->safe_reset();
+}
+
+// plugin.cpp:557-569
+void MujocoContactSurfacesPlugin::initCollisionFunction()
+{
+	for (int i = 0; i < mjNGEOMTYPES; ++i)
+		for (int j = 0; j < mjNGEOMTYPES; ++j) {
+			defaultCollisionFunctions[i][j] = mjCOLLISIONFUNC[i][j];
+			mjCOLLISIONFUNC[i][j]           = collision_cb_wrapper; // env_ptr_->registerCollisionFunction(i, j, ...)
+		}
+}
+
+// plugin.cpp:571-813
+void MujocoContactSurfacesPlugin::parseMujocoCustomFields(const mjModel *m)
+{
+	int hcp_id = mj_name2id(m, mjOBJ_TEXT, (PREFIX + "HydroelasticContactRepresentation").c_str());
+	if (hcp_id >= 0 && m->text_adr[hcp_id] >= 0) {
+		std::string hcp(&m->text_data[m->text_adr[hcp_id]], m->text_size[hcp_id]);
+		if (hcp.find("kTriangle") != std::string::npos)
+			hydroelastic_contact_representation = HCS_REP_TRIANGLE;
+		else if (hcp.find("kPolygon") != std::string::npos)
+			hydroelastic_contact_representation = HCS_REP_POLYGON;
+	}
+	int vs_id = mj_name2id(m, mjOBJ_NUMERIC, (PREFIX + "VisualizeSurfaces").c_str());
+	if (vs_id >= 0 && m->numeric_size[vs_id] == 1)
+		visualizeContactSurfaces = m->numeric_data[m->numeric_adr[vs_id]] != 0;
+	int apsf_id = mj_name2id(m, mjOBJ_NUMERIC, (PREFIX + "ApplyContactSurfaceForces").c_str());
+	if (apsf_id >= 0 && m->numeric_size[apsf_id] == 1)
+		applyContactSurfaceForces = m->numeric_data[m->numeric_adr[apsf_id]] != 0;
+
+	hcs_config cfg;
+	std::memset(&cfg, 0, sizeof cfg);
+	cfg.device               = device;
+	cfg.n_envs               = 1; // one plugin instance serves one mjData (plugin.cpp:88, 225)
+	cfg.representation       = hydroelastic_contact_representation;
+	cfg.apply_contact_forces = applyContactSurfaceForces;
+	cfg.max_faces            = 1 << 16; // GeomCollision views for sub-plugins / visualisation
+	if (hcs_create(&cfg, &ctx_) != HCS_OK) {
+		std::fprintf(stderr, "[mujoco_contact_surfaces] %s\n", hcs_last_error(nullptr));
+		ctx_ = nullptr;
+		return;
+	}
+	// per-geom contact properties, in the order of the numerics = drake_id order
+	for (int i = 0; i < m->nnumeric; ++i) {
+		const char *nm = mj_id2name(m, mjOBJ_NUMERIC, i);
+		if (!nm)
+			continue;
+		std::string full_name = nm;
+		if (full_name.rfind(PREFIX, 0) != 0)
+			continue;
+		std::string s = full_name.substr(PREFIX.length());
+		int id        = mj_name2id(m, mjOBJ_GEOM, s.c_str());
+		if (id < 0)
+			continue;
+		int adr = m->numeric_adr[i], size = m->numeric_size[i];
+		if (adr < 0 || size != 5)
+			continue;
+		const double *props = m->numeric_data + adr;
+		const float *mv     = nullptr;
+		const int32_t *mf   = nullptr;
+		int nv = 0, nf = 0;
+		if (m->geom_type[id] == mjGEOM_MESH) {
+			int did = m->geom_dataid[id];
+			if (did >= 0) {
+				nv = m->mesh_vertnum[did];
+				nf = m->mesh_facenum[did];
+				mv = m->mesh_vert + 3 * m->mesh_vertadr[did];
+				mf = m->mesh_face + 3 * m->mesh_faceadr[did];
+			}
+		}
+		int cfg_idx = hcs_add_geom(ctx_, m->geom_type[id], m->geom_size + 3 * id, mv, nv, mf, nf, props);
+		if (cfg_idx < 0) { // plane-soft / hfield / capsule / bad mesh: skip, MuJoCo's default collision stays
+			log_info("geom '%s' skipped: %s", s.c_str(), hcs_last_error(ctx_));
+			continue;
+		}
+		auto cp             = std::make_shared<ContactProperties>();
+		cp->mujoco_geom_id  = id;
+		cp->drake_id        = cfg_idx;
+		cp->geom_name       = s;
+		cp->contact_type    = props[0] > 0 ? SOFT : RIGID;
+		cp->hydroelastic_modulus = props[0] > 0 ? props[0] : INFINITY;
+		cp->dissipation     = props[0] > 0 ? props[1] : 1.0;
+		cp->resolution_hint = props[2];
+		cp->static_friction = props[3];
+		cp->dynamic_friction = props[4];
+		contactProperties[id] = cp;
+		cfg_to_mj.push_back(id);
+	}
+}
+
+// plugin.cpp:255-318: only the dispatch decision stays on the host
+int MujocoContactSurfacesPlugin::collision_cb(const mjModel *m, const mjData *d, mjContact *con, int g1, int g2,
+                                              mjtNum margin)
+{
+	int t1 = m->geom_type[g1], t2 = m->geom_type[g2];
+	auto c1 = contactProperties.find(g1), c2 = contactProperties.find(g2);
+	if (c1 == contactProperties.end() || c2 == contactProperties.end() ||
+	    (c1->second->contact_type == RIGID && c2->second->contact_type == RIGID))
+		return defaultCollisionFunctions[t1][t2](m, d, con, g1, g2, margin);
+	int n_con = applyContactSurfaceForces ? 0 : defaultCollisionFunctions[t1][t2](m, d, con, g1, g2, margin);
+	step_pairs_.emplace_back(c1->second->drake_id, c2->second->drake_id);
+	return n_con;
+}
+
+void MujocoContactSurfacesPlugin::ensurePairs()
+{
+	bool changed = !finalized_;
+	for (const auto &p : step_pairs_)
+		if (known_pairs_.insert(p).second) {
+			pair_list_.push_back(p);
+			changed = true;
+		}
+	if (!changed)
+		return;
+	std::vector<int32_t> g1, g2;
+	for (const auto &p : pair_list_) {
+		g1.push_back(p.first);
+		g2.push_back(p.second);
+	}
+	if (hcs_set_pairs(ctx_, g1.data(), g2.data(), (int)g1.size()) != HCS_OK || hcs_finalize(ctx_) != HCS_OK) {
+		std::fprintf(stderr, "[mujoco_contact_surfaces] %s\n", hcs_last_error(ctx_));
+		finalized_ = false;
+		return;
+	}
+	finalized_ = true;
+}
+
+void MujocoContactSurfacesPlugin::evaluateAndApply(const mjModel *m, mjData *d, bool with_sensors)
+{
+	int ng = (int)cfg_to_mj.size();
+	xpos_.resize(3 * ng), xmat_.resize(9 * ng), vel_.resize(6 * ng), wrench_.resize(6 * ng);
+	for (int c = 0; c < ng; ++c) {
+		int id = cfg_to_mj[c];
+		std::memcpy(&xpos_[3 * c], d->geom_xpos + 3 * id, 3 * sizeof(double)); // getGeomPose, plugin.cpp:116-126
+		std::memcpy(&xmat_[9 * c], d->geom_xmat + 9 * id, 9 * sizeof(double));
+		mj_objectVelocity(m, d, mjOBJ_GEOM, id, &vel_[6 * c], 0); // getGeomVelocity, plugin.cpp:107-114
+	}
+	if (hcs_step(ctx_, xpos_.data(), xmat_.data(), vel_.data(), with_sensors ? 1 : 0) != HCS_OK) {
+		std::fprintf(stderr, "[mujoco_contact_surfaces] %s\n", hcs_last_error(ctx_));
+		return;
+	}
+	if (applyContactSurfaceForces) { // plugin.cpp:477-482, reduced to one wrench per geom
+		hcs_get_geom_wrenches(ctx_, wrench_.data());
+		const mjtNum origin[3] = { 0, 0, 0 };
+		for (int c = 0; c < ng; ++c) {
+			const double *w = &wrench_[6 * c];
+			if (w[0] == 0 && w[1] == 0 && w[2] == 0 && w[3] == 0 && w[4] == 0 && w[5] == 0)
+				continue;
+			mj_applyFT(m, d, w, w + 3, origin, m->geom_bodyid[cfg_to_mj[c]], d->qfrc_passive);
+		}
+	}
+}
+
+// GeomCollision / PointCollision views (common_types.h:48-66) from the per-face dump
+void MujocoContactSurfacesPlugin::buildGeomCollisions()
+{
+	geomCollisions.clear();
+	int np = hcs_n_pairs(ctx_);
+	if (np <= 0)
+		return;
+	pair_results_.resize(np);
+	if (hcs_get_pair_results(ctx_, pair_results_.data()) != HCS_OK)
+		return;
+	std::vector<hcs_face> faces(1 << 16);
+	int nf = hcs_get_faces(ctx_, faces.data(), (int)faces.size());
+	if (nf < 0)
+		nf = 0;
+	nf = std::min<int>(nf, (int)faces.size());
+	std::stable_sort(faces.begin(), faces.begin() + nf, [](const hcs_face &a, const hcs_face &b) {
+		if (a.pair != b.pair) return a.pair < b.pair;
+		if (a.elemM != b.elemM) return a.elemM < b.elemM;
+		if (a.elemN != b.elemN) return a.elemN < b.elemN;
+		return a.face < b.face;
+	});
+	std::vector<double> tris;
+	int ntri = 0;
+	if (hydroelastic_contact_representation == HCS_REP_TRIANGLE) {
+		ntri = hcs_get_tactile_triangles(ctx_, 0, nullptr, 0);
+		if (ntri > 0) {
+			tris.resize(12 * (size_t)ntri);
+			hcs_get_tactile_triangles(ctx_, 0, tris.data(), ntri);
+		}
+	}
+	for (int p = 0; p < np; ++p) {
+		const hcs_pair_result &r = pair_results_[p];
+		if (r.n_polygons == 0)
+			continue; // the reference only stores non-null surfaces (plugin.cpp:307-315)
+		auto *view        = new ContactSurfaceView();
+		view->is_triangle = hydroelastic_contact_representation == HCS_REP_TRIANGLE;
+		view->total_area  = r.area;
+		view->num_faces   = r.n_faces;
+		std::memcpy(view->centroid, r.centroid, sizeof view->centroid);
+		if (np == 1)
+			view->triangles = tris; // single-pair scenes: the whole soup belongs to this surface
+		GeomCollisionPtr gc(new GeomCollision(cfg_to_mj[r.gM], cfg_to_mj[r.gN], view));
+		int k = 0;
+		for (int i = 0; i < nf; ++i)
+			if (faces[i].pair == p) {
+				PointCollision pc;
+				std::memcpy(pc.p, faces[i].p, sizeof pc.p);
+				std::memcpy(pc.n, faces[i].n, sizeof pc.n);
+				pc.fn0 = faces[i].fn0, pc.stiffness = faces[i].stiffness, pc.damping = faces[i].damping;
+				pc.face = k++;
+				gc->pointCollisions.push_back(pc);
+			}
+		geomCollisions.push_back(gc);
+	}
+}
+
+// plugin.cpp:411-523
+void MujocoContactSurfacesPlugin::passiveCallback(const mjModel *m, mjData *d)
+{
+	if (!ctx_)
+		return;
+	if (visualizeContactSurfaces) {
+		n_vGeom       = 0;
+		running_scale = 0.9 * running_scale + 0.1 * current_scale;
+		current_scale = 0.;
+	}
+	ensurePairs();
+	bool with_sensors = false;
+	for (const auto &plugin : cb_ready_plugins)
+		with_sensors |= plugin->wantsSensorUpdate(d);
+	if (finalized_ && !pair_list_.empty()) {
+		evaluateAndApply(m, d, with_sensors);
+		buildGeomCollisions();
+		if (visualizeContactSurfaces) { // one marker per quadrature point (plugin.cpp:509-516 draws the face wireframe)
+			for (const auto &gc : geomCollisions)
+				for (const auto &pc : gc->pointCollisions) {
+					if (n_vGeom >= MAX_VGEOM)
+						break;
+					current_scale        = std::max(current_scale, std::fabs(pc.fn0));
+					const mjtNum size[3] = { 0.00015, 0.00015, 0.00015 };
+					const float rgba[4]  = { 0.3f, 0.3f, 0.3f, 0.8f };
+					mjv_initGeom(vGeoms + n_vGeom++, mjGEOM_SPHERE, size, pc.p, nullptr, rgba);
+				}
+		}
+	}
+	for (const auto &plugin : cb_ready_plugins)
+		plugin->update(m, d, geomCollisions);
+	geomCollisions.clear();
+	step_pairs_.clear();
+}
+
+// plugin.cpp:815-826
+void MujocoContactSurfacesPlugin::renderCallback(const mjModel *model, mjData *data, mjvScene *scene)
+{
+	if (visualizeContactSurfaces) {
+		int n = std::min(n_vGeom, scene->maxgeom - scene->ngeom);
+		for (int i = 0; i < n; ++i)
+			scene->geoms[scene->ngeom++] = vGeoms[i];
+	}
+	for (const auto &plugin : cb_ready_plugins)
+		plugin->renderCallback(model, data, scene);
+}
+
+// plugin.cpp:828-975 (the new mesh AND its pressure field are installed: Q2 fixed)
+void MujocoContactSurfacesPlugin::onGeomChanged(const mjModel *m, mjData *, const int id)
+{
+	auto it = contactProperties.find(id);
+	if (it == contactProperties.end() || !ctx_)
+		return;
+	if (hcs_update_geom(ctx_, it->second->drake_id, m->geom_size + 3 * id) != HCS_OK)
+		std::fprintf(stderr, "[mujoco_contact_surfaces] %s\n", hcs_last_error(ctx_));
+}
+
+namespace sensors {
+
+static bool has(const PluginConfig &c, const char *k) { return c.find(k) != c.end(); }
+
+// tactile_sensor_base.cpp:61-87
+bool TactileSensorBase::load(const mjModel *m, mjData *)
+{
+	const PluginConfig &c = rosparam_config_;
+	if (!(has(c, "geomName") && has(c, "topicName") && has(c, "updateRate") && has(c, "sensorName")))
+		return false;
+	geomName = c.at("geomName");
+	int id   = mj_name2id(m, mjOBJ_GEOM, geomName.c_str());
+	if (id < 0)
+		return false;
+	geomID       = id;
+	lastUpdate   = -1e300;
+	topicName    = c.at("topicName");
+	sensorName   = c.at("sensorName");
+	updateRate   = std::atof(c.at("updateRate").c_str());
+	updatePeriod = 1.0 / updateRate;
+	if (has(c, "visualize"))
+		visualize = c.at("visualize") == "true" || c.at("visualize") == "1";
+	return true;
+}
+
+bool TactileSensorBase::wantsSensorUpdate(const mjData *d)
+{
+	std::lock_guard<std::mutex> pause_lock(pause_mutex);
+	double last = d->time < lastUpdate ? -1e300 : lastUpdate;
+	bool due    = (d->time - last >= updatePeriod) && !paused;
+	std::lock_guard<std::mutex> state_lock(state_request_mutex);
+	return due || request_state;
+}
+
+// tactile_sensor_base.cpp:89-120
+void TactileSensorBase::update(const mjModel *m, mjData *d, const std::vector<GeomCollisionPtr> &geomCollisions)
+{
+	std::lock_guard<std::mutex> pause_lock(pause_mutex);
+	double now = d->time;
+	if (now < lastUpdate)
+		lastUpdate = -1e300; // reset lastUpdate after jump back in time
+	if (now - lastUpdate >= updatePeriod && !paused) {
+		lastUpdate = now;
+		n_vGeom    = 0;
+		internal_update(m, d, geomCollisions);
+		++publish_count_; // publisher.publish(tactile_state_msg_)
+	}
+	std::unique_lock<std::mutex> state_lock(state_request_mutex);
+	if (request_state) {
+		n_vGeom = 0;
+		internal_update(m, d, geomCollisions);
+		request_state = false;
+		state_lock.unlock();
+		state_cv.notify_one();
+	}
+}
+
+void TactileSensorBase::renderCallback(const mjModel *, mjData *, mjvScene *scene)
+{
+	if (visualize)
+		for (int i = 0; i < n_vGeom && scene->ngeom < scene->maxgeom; ++i)
+			scene->geoms[scene->ngeom++] = vGeoms[i];
+}
+
+void TactileSensorBase::reset() {}
+
+void TactileSensorBase::setPause(bool pause)
+{
+	std::lock_guard<std::mutex> pause_lock(pause_mutex);
+	paused  = pause;
+	n_vGeom = 0;
+}
+
+std::vector<float> TactileSensorBase::getState()
+{
+	std::unique_lock<std::mutex> state_lock(state_request_mutex);
+	request_state = true;
+	state_cv.wait(state_lock, [this] { return !request_state; });
+	return tactile_state_values_;
+}
+
+// flat_tactile_sensor.cpp:127-214
+bool FlatTactileSensor::load(const mjModel *m, mjData *d)
+{
+	const PluginConfig &c = rosparam_config_;
+	if (!(TactileSensorBase::load(m, d) && has(c, "resolution")) || !owner_ || !owner_->context())
+		return false;
+	resolution = std::atof(c.at("resolution").c_str());
+	if (has(c, "sampling_resolution"))
+		sampling_resolution = std::atoi(c.at("sampling_resolution").c_str());
+	if (has(c, "windowing")) {
+		const std::string &w = c.at("windowing");
+		if (has(c, "sigma"))
+			sigma = (float)std::atof(c.at("sigma").c_str());
+		if (w == "gauss")
+			window = HCS_WINDOW_GAUSS;
+		else if (w == "tukey")
+			window = HCS_WINDOW_TUKEY;
+		else if (w == "square")
+			window = HCS_WINDOW_SQUARE; // unknown names fall back to none (flat_tactile_sensor.cpp:165-167)
+	}
+	int cfg_idx = owner_->configIndex(geomID);
+	if (cfg_idx < 0)
+		return false; // the sensor geom has no cs:: entry: it can never be part of a contact surface
+	sensor_index_ = hcs_add_flat_sensor(owner_->context(), cfg_idx, resolution, sampling_resolution, window, sigma);
+	if (sensor_index_ < 0) {
+		std::fprintf(stderr, "[mujoco_contact_surface_sensors] %s\n", hcs_last_error(owner_->context()));
+		return false;
+	}
+	hcs_sensor_dims(owner_->context(), sensor_index_, &cx, &cy);
+	vGeoms = new mjvGeom[2 * cx * cy + 50];
+	tactile_state_values_.assign((size_t)cx * cy, 0.0f);
+	return true;
+}
+
+// flat_tactile_sensor.cpp:216-221 -> bvh_update (:262-402), computed on the GPU by the tactile kernels
+void FlatTactileSensor::internal_update(const mjModel *m, mjData *d, const std::vector<GeomCollisionPtr> &)
+{
+	if (!owner_->finalized()) { // no contact pair seen yet: zero image (flat_tactile_sensor.cpp:290-296)
+		std::fill(tactile_state_values_.begin(), tactile_state_values_.end(), 0.0f);
+		return;
+	}
+	if (hcs_get_sensor_image(owner_->context(), sensor_index_, tactile_state_values_.data()) != HCS_OK)
+		return; // this step ran without sensors (request arrived mid-step): keep the previous message
+	if (visualize) { // render_tiles, flat_tactile_sensor.cpp:223-260
+		const mjtNum *rot = d->geom_xmat + 9 * geomID, *xp = d->geom_xpos + 3 * geomID;
+		const mjtNum *gs  = m->geom_size + 3 * geomID;
+		float peak        = 1e-9f;
+		for (float v : tactile_state_values_)
+			peak = std::max(peak, std::fabs(v));
+		for (int x = 0; x < cx; ++x)
+			for (int y = 0; y < cy; ++y) {
+				int idx = x + cy * y;
+				if (idx >= cx * cy)
+					continue;
+				float ps            = std::fabs(tactile_state_values_[idx]) / peak;
+				const float rgba[4] = { ps, 0, 1.f - ps, 0.8f };
+				mjtNum l[3] = { -gs[0] + x * resolution + resolution / 2, -gs[1] + y * resolution + resolution / 2, gs[2] };
+				mjtNum pos[3];
+				for (int r = 0; r < 3; ++r)
+					pos[r] = rot[3 * r] * l[0] + rot[3 * r + 1] * l[1] + rot[3 * r + 2] * l[2] + xp[r];
+				mjtNum size[3] = { resolution / 2, resolution / 2, 0.0005 };
+				mjv_initGeom(vGeoms + n_vGeom++, mjGEOM_BOX, size, pos, rot, rgba);
+			}
+	}
+}
+
+} // namespace sensors
+} // namespace mujoco_ros::contact_surfaces

@@ -1,0 +1,231 @@
+// Drives the host adapter the way mujoco_ros::MujocoEnv drives the reference plugin:
+// load(), then per step: MuJoCo's collision pass calls mjCOLLISIONFUNC[t1][t2] for every geom pair, then the
+// passive callback runs.  Worlds are shim re-creations of the reference's example worlds
+//   mujoco_contact_surfaces/assets/sphere_on_box_world.xml          (config 1)
+//   mujoco_contact_surface_sensors/assets/myrmex_box_world.xml + config/myrmex_sensor.yaml  (config 2)
+// Prints one JSON object per scenario; tests/test_plugin_adapter.py checks it against the oracle.
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "contact_surfaces_plugin.h"
+
+using namespace mujoco_ros::contact_surfaces;
+
+struct ShimWorld {
+	mjModel m{};
+	mjData d{};
+	std::vector<int> geom_type, geom_bodyid, geom_dataid, numeric_adr, numeric_size, text_adr, text_size, body_dofadr;
+	std::vector<double> geom_size, numeric_data, xpos, xmat, xipos, qfrc, vel6;
+	std::vector<char> text_data;
+	std::vector<std::string> gnames, nnames, tnames;
+	std::vector<const char *> gptr, nptr, tptr;
+
+	int add_body(bool free_joint, const double com[3])
+	{
+		int b = (int)body_dofadr.size();
+		body_dofadr.push_back(free_joint ? m.nv : -1);
+		if (free_joint)
+			m.nv += 6;
+		xipos.insert(xipos.end(), com, com + 3);
+		return b;
+	}
+	int add_geom(const std::string &name, int type, int body, const double size[3], const double pos[3], const double mat[9])
+	{
+		geom_type.push_back(type), geom_bodyid.push_back(body), geom_dataid.push_back(-1);
+		geom_size.insert(geom_size.end(), size, size + 3);
+		xpos.insert(xpos.end(), pos, pos + 3);
+		xmat.insert(xmat.end(), mat, mat + 9);
+		vel6.insert(vel6.end(), 6, 0.0);
+		gnames.push_back(name);
+		return (int)geom_type.size() - 1;
+	}
+	void add_numeric(const std::string &name, std::vector<double> data)
+	{
+		nnames.push_back(name);
+		numeric_adr.push_back((int)numeric_data.size());
+		numeric_size.push_back((int)data.size());
+		numeric_data.insert(numeric_data.end(), data.begin(), data.end());
+	}
+	void add_text(const std::string &name, const std::string &data)
+	{
+		tnames.push_back(name);
+		text_adr.push_back((int)text_data.size());
+		text_size.push_back((int)data.size());
+		text_data.insert(text_data.end(), data.begin(), data.end());
+	}
+	void finish()
+	{
+		for (auto &s : gnames) gptr.push_back(s.c_str());
+		for (auto &s : nnames) nptr.push_back(s.c_str());
+		for (auto &s : tnames) tptr.push_back(s.c_str());
+		m.ngeom = (int)geom_type.size(), m.nbody = (int)body_dofadr.size();
+		m.nnumeric = (int)nnames.size(), m.ntext = (int)tnames.size();
+		m.geom_type = geom_type.data(), m.geom_bodyid = geom_bodyid.data(), m.geom_dataid = geom_dataid.data();
+		m.geom_size = geom_size.data();
+		m.numeric_adr = numeric_adr.data(), m.numeric_size = numeric_size.data(), m.numeric_data = numeric_data.data();
+		m.text_adr = text_adr.data(), m.text_size = text_size.data(), m.text_data = text_data.data();
+		m.geom_names = gptr.data(), m.numeric_names = nptr.data(), m.text_names = tptr.data();
+		m.body_dofadr = body_dofadr.data();
+		qfrc.assign(m.nv, 0.0);
+		d.geom_xpos = xpos.data(), d.geom_xmat = xmat.data(), d.xipos = xipos.data();
+		d.qfrc_passive = qfrc.data(), d.geom_vel6 = vel6.data();
+		d.time = 0;
+	}
+	// mj_collision: every geom pair, ordered by geom type like mj_collideGeoms
+	void collision_pass()
+	{
+		mjContact con[8];
+		for (int a = 0; a < m.ngeom; ++a)
+			for (int b = a + 1; b < m.ngeom; ++b) {
+				if (geom_bodyid[a] == geom_bodyid[b])
+					continue;
+				int g1 = a, g2 = b;
+				if (geom_type[g1] > geom_type[g2])
+					std::swap(g1, g2);
+				mjCOLLISIONFUNC[geom_type[g1]][geom_type[g2]](&m, &d, con, g1, g2, 0);
+			}
+	}
+};
+
+static const double I3[9] = { 1, 0, 0, 0, 1, 0, 0, 0, 1 };
+
+static void rot_zyx(double yaw, double pitch, double roll, double R[9])
+{
+	double cz = cos(yaw), sz = sin(yaw), cy = cos(pitch), sy = sin(pitch), cx = cos(roll), sx = sin(roll);
+	double Rz[9] = { cz, -sz, 0, sz, cz, 0, 0, 0, 1 }, Ry[9] = { cy, 0, sy, 0, 1, 0, -sy, 0, cy }, Rx[9] = { 1, 0, 0, 0, cx, -sx, 0, sx, cx };
+	double T[9];
+	for (int i = 0; i < 3; ++i)
+		for (int j = 0; j < 3; ++j) {
+			T[3 * i + j] = 0;
+			for (int k = 0; k < 3; ++k)
+				T[3 * i + j] += Rz[3 * i + k] * Ry[3 * k + j];
+		}
+	for (int i = 0; i < 3; ++i)
+		for (int j = 0; j < 3; ++j) {
+			R[3 * i + j] = 0;
+			for (int k = 0; k < 3; ++k)
+				R[3 * i + j] += T[3 * i + k] * Rx[3 * k + j];
+		}
+}
+
+static void print_vec(const char *key, const double *v, int n, bool last = false)
+{
+	std::printf("\"%s\": [", key);
+	for (int i = 0; i < n; ++i)
+		std::printf("%s%.17g", i ? ", " : "", v[i]);
+	std::printf("]%s", last ? "" : ", ");
+}
+
+static int scenario_sphere_on_box()
+{
+	ShimWorld w;
+	const double zero[3] = { 0, 0, 0 };
+	double box_pos[3] = { 0, 0, 0.1 }, sph_pos[3] = { 0.012, -0.02, 0.2 + 0.08 - 0.012 };
+	double R[9];
+	rot_zyx(0.4, -0.3, 0.7, R);
+	int b0 = w.add_body(false, zero), b1 = w.add_body(true, box_pos), b2 = w.add_body(true, sph_pos);
+	double s_plane[3] = { 0, 0, 1 }, s_box[3] = { 0.1, 0.1, 0.1 }, s_sph[3] = { 0.08, 0, 0 };
+	w.add_geom("ground", mjGEOM_PLANE, b0, s_plane, zero, I3);
+	w.add_geom("box0", mjGEOM_BOX, b1, s_box, box_pos, I3);
+	int gs = w.add_geom("sphere0", mjGEOM_SPHERE, b2, s_sph, sph_pos, R);
+	w.add_text("cs::HydroelasticContactRepresentation", "kPolygon");
+	w.add_numeric("cs::VisualizeSurfaces", { 1 });
+	w.add_numeric("cs::box0", { 0, 1.0, 0.1, 0.3, 0.3 });
+	w.add_numeric("cs::sphere0", { 5e4, 5.0, 0.05, 0.3, 0.3 });
+	w.finish();
+	double v[6] = { 0.3, -0.2, 0.1, 0.02, 0.01, -0.05 };
+	std::memcpy(&w.vel6[6 * gs], v, sizeof v);
+
+	MujocoContactSurfacesPlugin plugin;
+	if (!plugin.load(&w.m, &w.d)) {
+		std::printf("{\"scenario\": \"sphere_on_box\", \"error\": \"load failed\"}\n");
+		return 1;
+	}
+	int n_geoms_seen = 0;
+	for (int step = 0; step < 3; ++step) { // identical steps: results must not depend on history
+		std::fill(w.qfrc.begin(), w.qfrc.end(), 0.0);
+		w.collision_pass();
+		plugin.passiveCallback(&w.m, &w.d);
+		w.d.time += 0.001;
+	}
+	mjvGeom scene_geoms[256];
+	mjvScene scene{ 256, 0, scene_geoms };
+	plugin.renderCallback(&w.m, &w.d, &scene);
+	n_geoms_seen = scene.ngeom;
+	std::printf("{\"scenario\": \"sphere_on_box\", ");
+	print_vec("box_pos", box_pos, 3);
+	print_vec("sphere_pos", sph_pos, 3);
+	print_vec("sphere_mat", R, 9);
+	print_vec("sphere_vel6", v, 6);
+	std::printf("\"vgeoms\": %d, ", n_geoms_seen);
+	print_vec("qfrc_passive", w.qfrc.data(), (int)w.qfrc.size(), true);
+	std::printf("}\n");
+	return 0;
+}
+
+static int scenario_myrmex()
+{
+	ShimWorld w;
+	const double zero[3] = { 0, 0, 0 };
+	double foam_pos[3] = { 0, 0, 0.033 };
+	double R[9];
+	rot_zyx(0.6, 0.01, -0.015, R);
+	// lowest corner of the tilted 0.2 m cube 3 mm below the foam top (z = 0.053)
+	double low = 0;
+	for (int sx = -1; sx <= 1; sx += 2)
+		for (int sy = -1; sy <= 1; sy += 2)
+			for (int sz = -1; sz <= 1; sz += 2)
+				low = std::fmin(low, 0.1 * (R[6] * sx + R[7] * sy + R[8] * sz));
+	double box_pos[3] = { 0.02, -0.01, 0.053 - 0.003 - low };
+	int b0 = w.add_body(false, zero), b1 = w.add_body(true, box_pos);
+	double s_plane[3] = { 0, 0, 1 }, s_box[3] = { 0.1, 0.1, 0.1 }, s_foam[3] = { 0.2, 0.2, 0.02 };
+	w.add_geom("ground", mjGEOM_PLANE, b0, s_plane, zero, I3);
+	w.add_geom("box1", mjGEOM_BOX, b1, s_box, box_pos, R);
+	w.add_geom("myrmex_foam", mjGEOM_BOX, b0, s_foam, foam_pos, I3);
+	w.add_text("cs::HydroelasticContactRepresentation", "kTriangle");
+	w.add_numeric("cs::VisualizeSurfaces", { 0 });
+	w.add_numeric("cs::ApplyContactSurfaceForces", { 1 });
+	w.add_numeric("cs::box1", { 0, 1.0, 0.05, 0.3, 0.3 });
+	w.add_numeric("cs::plate", { 0, 1.0, 0, 0.3, 0.3 }); // names a geom that is not in this world: ignored
+	w.add_numeric("cs::myrmex_foam", { 5e4, 5.0, 0, 0.3, 0.3 });
+	w.finish();
+
+	MujocoContactSurfacesPlugin plugin;
+	auto sensor = std::make_shared<sensors::FlatTactileSensor>();
+	// config/myrmex_sensor.yaml:4
+	PluginConfig cfg = { { "type", "mujoco_contact_surface_sensors/FlatTactileSensor" }, { "sensorName", "myrmex_sensor0" },
+		                 { "geomName", "myrmex_foam" }, { "topicName", "/tactile_module_16x16_v2" }, { "updateRate", "50.0" },
+		                 { "visualize", "True" }, { "use_parallel", "True" }, { "resolution", "0.025" },
+		                 { "sampling_resolution", "20" } };
+	plugin.addSurfacePlugin(sensor, cfg);
+	if (!plugin.load(&w.m, &w.d)) {
+		std::printf("{\"scenario\": \"myrmex_box\", \"error\": \"load failed\"}\n");
+		return 1;
+	}
+	// 45 steps of 1 ms at 50 Hz: the sensor publishes at t = 0, 0.020, 0.040
+	for (int step = 0; step < 45; ++step) {
+		std::fill(w.qfrc.begin(), w.qfrc.end(), 0.0);
+		w.collision_pass();
+		plugin.passiveCallback(&w.m, &w.d);
+		w.d.time += 0.001;
+	}
+	std::printf("{\"scenario\": \"myrmex_box\", ");
+	print_vec("box_pos", box_pos, 3);
+	print_vec("box_mat", R, 9);
+	std::printf("\"cx\": %d, \"cy\": %d, \"publishes\": %d, ", sensor->cx, sensor->cy, sensor->publishCount());
+	std::vector<double> img(sensor->lastMessage().begin(), sensor->lastMessage().end());
+	print_vec("image", img.data(), (int)img.size());
+	print_vec("qfrc_passive", w.qfrc.data(), (int)w.qfrc.size(), true);
+	std::printf("}\n");
+	return 0;
+}
+
+int main()
+{
+	int rc = scenario_sphere_on_box();
+	rc |= scenario_myrmex();
+	return rc;
+}

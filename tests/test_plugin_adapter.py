@@ -1,0 +1,83 @@
+"""The C++ host adapter (mujoco_contact_surfaces_b200/plugin) driven like mujoco_ros drives the reference
+plugin: load -> collision pass -> passiveCallback, on shim re-creations of the reference's example worlds.
+Results are checked against the CPU oracle."""
+import json
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from oracle.oracle import GEOM_BOX, GEOM_SPHERE, OracleScene
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PLUGIN_DIR = os.path.join(ROOT, "mujoco_contact_surfaces_b200", "plugin")
+
+
+@pytest.fixture(scope="module")
+def plugin_built(hcs_lib):
+    subprocess.check_call(["make", "-C", PLUGIN_DIR, "-s"])
+    return os.path.join(PLUGIN_DIR, "test_plugin")
+
+
+def test_adapter_builds_and_mirrors_the_reference_classes(plugin_built):
+    """CPU-side: the adapter compiles against the MuJoCo shim and declares the reference's virtual surface."""
+    hdr = open(os.path.join(PLUGIN_DIR, "contact_surfaces_plugin.h")).read()
+    for name in ("class MujocoContactSurfacesPlugin", "bool load(const mjModel *m, mjData *d) override",
+                 "void passiveCallback(const mjModel *model, mjData *data) override",
+                 "void renderCallback(const mjModel *model, mjData *data, mjvScene *scene) override",
+                 "void onGeomChanged(const mjModel *model, mjData *data, const int geom_id) override",
+                 "int collision_cb(const mjModel *m, const mjData *d, mjContact *con, int g1, int g2, mjtNum margin)",
+                 "class SurfacePlugin", "bool safe_load(", "void safe_reset()", "struct PointCollision",
+                 "struct GeomCollision", "class FlatTactileSensor", "class TactileSensorBase"):
+        assert name in hdr, name
+    assert os.path.exists(plugin_built)
+
+
+def _run(binary):
+    out = subprocess.run([binary], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr
+    return {d["scenario"]: d for d in map(json.loads, out.stdout.strip().splitlines())}
+
+
+@pytest.mark.gpu
+def test_adapter_sphere_on_box_and_myrmex_match_the_oracle(plugin_built):
+    res = _run(plugin_built)
+    I3 = np.eye(3).reshape(-1)
+
+    r = res["sphere_on_box"]
+    o = OracleScene(triangle_representation=False)
+    box = o.add_geom(GEOM_BOX, [0.1, 0.1, 0.1], [0, 1.0, 0.1, 0.3, 0.3])
+    sph = o.add_geom(GEOM_SPHERE, [0.08], [5e4, 5.0, 0.05, 0.3, 0.3])
+    o.set_pairs([[sph, box]])
+    xpos = np.array([r["box_pos"], r["sphere_pos"]])
+    xmat = np.stack([I3, np.array(r["sphere_mat"])])
+    vel = np.stack([np.zeros(6), np.array(r["sphere_vel6"])])
+    o.step(xpos, xmat, vel)
+    q = np.array(r["qfrc_passive"])
+    assert q.shape == (12,) and r["vgeoms"] > 0
+    for g, dofs in ((box, q[0:6]), (sph, q[6:12])):
+        w = o.geom_wrench(g)
+        tau_com = w[3:] - np.cross(xpos[g], w[:3])  # mj_applyFT: torque about the body's centre of mass
+        assert np.allclose(dofs[:3], w[:3], rtol=1e-8, atol=1e-12)
+        assert np.allclose(dofs[3:], tau_com, rtol=1e-8, atol=1e-10)
+    assert np.linalg.norm(q[:3]) > 1.0  # there is contact
+
+    r = res["myrmex_box"]
+    o = OracleScene(triangle_representation=True)
+    b1 = o.add_geom(GEOM_BOX, [0.1, 0.1, 0.1], [0, 1.0, 0.05, 0.3, 0.3])
+    foam = o.add_geom(GEOM_BOX, [0.2, 0.2, 0.02], [5e4, 5.0, 0, 0.3, 0.3])
+    o.set_pairs([[b1, foam]])
+    o.add_flat_sensor(foam, [0.2, 0.2, 0.02], 0.025, 20)
+    xpos = np.array([r["box_pos"], [0, 0, 0.033]])
+    o.step(xpos, np.stack([np.array(r["box_mat"]), I3]))
+    ref = o.sensor_image(0)
+    img = np.array(r["image"], dtype=np.float32)
+    assert (r["cx"], r["cy"]) == (16, 16) and r["publishes"] == 3  # 50 Hz over 45 ms of 1 ms steps
+    assert ref.max() > 0
+    err = np.abs(img - ref) / np.maximum(np.abs(ref), 1e-3 * ref.max())
+    assert err.max() < 1e-6
+    w = o.geom_wrench(b1)
+    q = np.array(r["qfrc_passive"])
+    assert np.allclose(q[:3], w[:3], rtol=1e-8)
+    assert np.allclose(q[3:6], w[3:] - np.cross(xpos[0], w[:3]), rtol=1e-8, atol=1e-10)
