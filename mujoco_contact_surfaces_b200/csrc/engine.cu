@@ -559,7 +559,7 @@ static void step_device(hcs_ctx *c, const double *xpos, const double *xmat, cons
 	if (prof)
 		CK(cudaEventRecord(c->ev[3], s));
 	launch_finalize(c->d_pairs, io, s);
-	k += 2;
+	k += 1;
 	if (prof)
 		CK(cudaEventRecord(c->ev[4], s));
 	if (with_sensors)

@@ -21,27 +21,50 @@
 namespace hcs {
 
 #define FULL_MASK 0xffffffffu
-constexpr int MAXV     = 8;
+constexpr int MAXV     = 8; // tet-tet; tet-triangle polygons have <= 7 vertices, plane slices <= 4
 constexpr int NP_WARPS = 4;
 constexpr int NP_BLOCK = 32 * NP_WARPS;
 
 // per-warp shared-memory tile: two polygon buffers + vertex pressures, lane-interleaved
+template <int MV>
 struct WarpTile {
-	double xyz[2][MAXV][3][32];
-	double e[MAXV][32];
+	double xyz[2][MV][3][32];
+	double e[MV][32];
 };
-constexpr size_t NP_SMEM = sizeof(WarpTile) * NP_WARPS;
 
-struct Poly { // view of one lane's polygon buffer
-	double *b;
-	__device__ __forceinline__ D3 get(int i) const { return mk(b[(3 * i) * 32], b[(3 * i + 1) * 32], b[(3 * i + 2) * 32]); }
+// Explicit shared-window accesses: through a generic pointer stored in a struct the compiler emitted
+// generic LD/ST with 64-bit address arithmetic in the clip loop (profiles/r01_notes.md).
+// All accesses index the one dynamic shared array directly, so the compiler emits LDS/STS and keeps its
+// freedom to schedule them (inline-asm volatile accessors serialised the loop and were slower).
+extern __shared__ __align__(16) double smem_d[];
+__device__ __forceinline__ double lds_f64(unsigned a) { return smem_d[a >> 3]; }
+__device__ __forceinline__ void sts_f64(unsigned a, double v) { smem_d[a >> 3] = v; }
+
+struct Poly { // view of one lane's polygon buffer: 32-bit shared address of vertex 0, x; stride 256 B per scalar
+	unsigned a;
+	__device__ __forceinline__ D3 get(int i) const
+	{
+		unsigned p = a + 768u * i;
+		return mk(lds_f64(p), lds_f64(p + 256u), lds_f64(p + 512u));
+	}
 	__device__ __forceinline__ void set(int i, D3 v) const
 	{
-		b[(3 * i) * 32]     = v.x;
-		b[(3 * i + 1) * 32] = v.y;
-		b[(3 * i + 2) * 32] = v.z;
+		unsigned p = a + 768u * i;
+		sts_f64(p, v.x);
+		sts_f64(p + 256u, v.y);
+		sts_f64(p + 512u, v.z);
 	}
 };
+struct PressTile { // vertex pressures of one lane
+	unsigned a;
+	__device__ __forceinline__ double get(int i) const { return lds_f64(a + 256u * i); }
+	__device__ __forceinline__ void set(int i, double v) const { sts_f64(a + 256u * i, v); }
+};
+// byte offset of p inside the dynamic shared array
+__device__ __forceinline__ unsigned smem_addr(const void *p)
+{
+	return (unsigned)(reinterpret_cast<const char *>(p) - reinterpret_cast<const char *>(smem_d));
+}
 
 struct WarpCtx { // warp-uniform per (env, pair) data
 	Xform X_WA;    // soft geom A (computation frame) -> world
@@ -188,11 +211,11 @@ __device__ __noinline__ void dump_face(const StepIO &io, const WarpCtx &c, D3 p,
 
 // Quadrature + force accumulation of one contact polygon.
 //   P[0..n): vertices in the builder frame (A's frame, or world when IDENT), right-handed normal nhat
-//   (unit, into A); e[i*32] (shared tile): vertex pressures; grad: sampled-field gradient (builder frame);
+//   (unit, into A); e (shared tile): vertex pressures; grad: sampled-field gradient (builder frame);
 //   gN: -grad_N . nhat or +inf.  TRI selects kTriangle (centroid fan) vs kPolygon.
 //   Returns the polygon centroid (builder frame) and its pressure for the tactile emission.
 template <bool TRI, bool IDENT>
-__device__ __forceinline__ void integrate_polygon(Poly P, int n, D3 nhat, D3 grad, const double *e, double gN,
+__device__ __forceinline__ void integrate_polygon(Poly P, int n, D3 nhat, D3 grad, PressTile e, double gN,
                                                   const WarpCtx &c, const StepIO &io, int elemA, int elemB, Acc &acc,
                                                   D3 &cen_out, double &ec_out)
 {
@@ -220,7 +243,7 @@ __device__ __forceinline__ void integrate_polygon(Poly P, int n, D3 nhat, D3 gra
 		cen = ((p0 + p1) + pi) / 3.0;
 	else
 		cen = A2 != 0.0 ? csum / (3.0 * A2) : p0;
-	double ec = e[0] + dot(grad, cen - p0);
+	double ec = e.get(0) + dot(grad, cen - p0);
 	cen_out   = cen;
 	ec_out    = ec;
 	D3 cW     = IDENT ? cen : apply(c.X_WA, cen);
@@ -253,12 +276,12 @@ __device__ __forceinline__ void integrate_polygon(Poly P, int n, D3 nhat, D3 gra
 	int cur   = n - 1;
 	D3 a      = P.get(cur);
 	D3 aW     = IDENT ? a : apply(c.X_WA, a);
-	double ea = e[cur * 32];
+	double ea = e.get(cur);
 #pragma unroll 1
 	for (int i = 0; i < n; ++i) {
 		D3 b        = P.get(i);
 		D3 bW       = IDENT ? b : apply(c.X_WA, b);
-		double eb   = e[i * 32];
+		double eb   = e.get(i);
 		double a2   = dot(cross(b - a, cen - a), nhat);
 		double sg   = a2 < 0 ? -1.0 : 1.0;
 		double area = 0.5 * (sg * a2);
@@ -290,7 +313,7 @@ __device__ __forceinline__ void integrate_polygon(Poly P, int n, D3 nhat, D3 gra
 // Warp-cooperative append of this lane's fan triangles to the tactile pool: exclusive scan over the lane
 // counts, ONE atomicAdd per warp.  World vertices are recomputed from the shared tile.
 template <bool IDENT>
-__device__ __forceinline__ void emit_tactile(int n_faces, Poly P, const double *e, D3 cen, double ec, const WarpCtx &c,
+__device__ __forceinline__ void emit_tactile(int n_faces, Poly P, PressTile e, D3 cen, double ec, const WarpCtx &c,
                                              const StepIO &io, int slot, int lane)
 {
 	int incl = n_faces;
@@ -312,11 +335,11 @@ __device__ __forceinline__ void emit_tactile(int n_faces, Poly P, const double *
 		D3 cW     = IDENT ? cen : apply(c.X_WA, cen);
 		int cur   = n_faces - 1;
 		D3 aW     = IDENT ? P.get(cur) : apply(c.X_WA, P.get(cur));
-		double ea = e[cur * 32];
+		double ea = e.get(cur);
 #pragma unroll 1
 		for (int i = 0; i < n_faces; ++i, ++pos) {
 			D3 bW     = IDENT ? P.get(i) : apply(c.X_WA, P.get(i));
-			double eb = e[i * 32];
+			double eb = e.get(i);
 			if (pos < io.max_tris) {
 				// (prev, next, centroid); the M/N swap of ContactSurface reverses winding by swapping the
 				// first two vertices
@@ -389,7 +412,6 @@ __device__ __forceinline__ Acc zero_acc()
 template <bool TRI>
 __global__ void __launch_bounds__(NP_BLOCK, 3) narrow_tet_tri_kernel(PairDesc P, StepIO io)
 {
-	extern __shared__ __align__(16) unsigned char smem_raw[];
 	int warp = (blockIdx.x * NP_BLOCK + threadIdx.x) >> 5, lane = threadIdx.x & 31;
 	int n_units = io.n_env * P.n_slices;
 	if (warp >= n_units)
@@ -401,9 +423,9 @@ __global__ void __launch_bounds__(NP_BLOCK, 3) narrow_tet_tri_kernel(PairDesc P,
 			store_zero(P.partial + warp, P.slab_evals[warp]);
 		return;
 	}
-	WarpTile &T = reinterpret_cast<WarpTile *>(smem_raw)[threadIdx.x >> 5];
-	Poly buf[2] = { Poly{ &T.xyz[0][0][0][lane] }, Poly{ &T.xyz[1][0][0][lane] } };
-	double *e   = &T.e[0][lane];
+	WarpTile<7> &T = reinterpret_cast<WarpTile<7> *>(smem_d)[threadIdx.x >> 5];
+	const unsigned buf0 = smem_addr(&T.xyz[0][0][0][lane]), buf_stride = (unsigned)sizeof(T.xyz[0]);
+	PressTile e{ smem_addr(&T.e[0][lane]) };
 	Acc acc     = zero_acc();
 	Xform X_WS = load_pose(io.xpos, io.xmat, io.n_geoms, env, P.gA);
 	Xform X_WR = load_pose(io.xpos, io.xmat, io.n_geoms, env, P.gB);
@@ -429,14 +451,14 @@ __global__ void __launch_bounds__(NP_BLOCK, 3) narrow_tet_tri_kernel(PairDesc P,
 			D3 nS = rot(X_SR.R, ld3(tr.n));
 #pragma unroll
 			for (int k = 0; k < 3; ++k)
-				buf[0].set(k, apply(X_SR, ld3(tr.v[k])));
+				Poly{ buf0 }.set(k, apply(X_SR, ld3(tr.v[k])));
 			int n = 3;
 #pragma unroll 1
 			for (int k = 0; k < 4; ++k) {
-				n = clip_halfspace(buf[cur], n, ld3(tf.plane[k]), tf.plane[k][3], buf[cur ^ 1]);
+				n = clip_halfspace(Poly{ buf0 + cur * buf_stride }, n, ld3(tf.plane[k]), tf.plane[k][3], Poly{ buf0 + (cur ^ 1) * buf_stride });
 				cur ^= 1;
 			}
-			n      = remove_duplicates(buf[cur], n);
+			n      = remove_duplicates(Poly{ buf0 + cur * buf_stride }, n);
 			int nv = 0;
 			if (n >= 3) {
 				nv        = n;
@@ -444,14 +466,14 @@ __global__ void __launch_bounds__(NP_BLOCK, 3) narrow_tet_tri_kernel(PairDesc P,
 				double e0 = tf.e0;
 #pragma unroll 1
 				for (int k = 0; k < n; ++k)
-					e[k * 32] = dot(grad, buf[cur].get(k)) + e0;
-				integrate_polygon<TRI, false>(buf[cur], n, nS, grad, e, kInf, ctx, io, tet, tri, acc, cen, ec);
+					e.set(k, dot(grad, Poly{ buf0 + cur * buf_stride }.get(k)) + e0);
+				integrate_polygon<TRI, false>(Poly{ buf0 + cur * buf_stride }, n, nS, grad, e, kInf, ctx, io, tet, tri, acc, cen, ec);
 				tfaces = n;
 			}
 			nvout[i] = (uint8_t)nv;
 		}
 		if (TRI && P.emit_tactile)
-			emit_tactile<false>(tfaces, buf[cur], e, cen, ec, ctx, io, i, lane);
+			emit_tactile<false>(tfaces, Poly{ buf0 + cur * buf_stride }, e, cen, ec, ctx, io, i, lane);
 	}
 	if (lane == 0)
 		acc.n_candidates = P.slab_evals[warp];
@@ -464,7 +486,6 @@ __global__ void __launch_bounds__(NP_BLOCK, 3) narrow_tet_tri_kernel(PairDesc P,
 template <bool TRI>
 __global__ void __launch_bounds__(NP_BLOCK, 3) narrow_tet_tet_kernel(PairDesc P, StepIO io)
 {
-	extern __shared__ __align__(16) unsigned char smem_raw[];
 	int warp = (blockIdx.x * NP_BLOCK + threadIdx.x) >> 5, lane = threadIdx.x & 31;
 	int n_units = io.n_env * P.n_slices;
 	if (warp >= n_units)
@@ -476,9 +497,9 @@ __global__ void __launch_bounds__(NP_BLOCK, 3) narrow_tet_tet_kernel(PairDesc P,
 			store_zero(P.partial + warp, P.slab_evals[warp]);
 		return;
 	}
-	WarpTile &T = reinterpret_cast<WarpTile *>(smem_raw)[threadIdx.x >> 5];
-	Poly buf[2] = { Poly{ &T.xyz[0][0][0][lane] }, Poly{ &T.xyz[1][0][0][lane] } };
-	double *e   = &T.e[0][lane];
+	WarpTile<8> &T = reinterpret_cast<WarpTile<8> *>(smem_d)[threadIdx.x >> 5];
+	const unsigned buf0 = smem_addr(&T.xyz[0][0][0][lane]), buf_stride = (unsigned)sizeof(T.xyz[0]);
+	PressTile e{ smem_addr(&T.e[0][lane]) };
 	Acc acc     = zero_acc();
 	Xform X_WM = load_pose(io.xpos, io.xmat, io.n_geoms, env, P.gA);
 	Xform X_WN = load_pose(io.xpos, io.xmat, io.n_geoms, env, P.gB);
@@ -540,9 +561,9 @@ __global__ void __launch_bounds__(NP_BLOCK, 3) narrow_tet_tet_kernel(PairDesc P,
 					D3 a = ld3(g0.v[l0]), b = ld3(g0.v[l1]);
 					double d0 = pick4(dist, l0), d1 = pick4(dist, l1);
 					double t  = d0 / (d0 - d1);
-					buf[0].set(n++, a + t * (b - a));
+					Poly{ buf0 }.set(n++, a + t * (b - a));
 				}
-				n  = remove_duplicates(buf[0], n);
+				n  = remove_duplicates(Poly{ buf0 }, n);
 				ok = n >= 3;
 			}
 			if (ok) { // clip by the four half spaces of tet1 expressed in M
@@ -564,9 +585,9 @@ __global__ void __launch_bounds__(NP_BLOCK, 3) narrow_tet_tet_kernel(PairDesc P,
 						else
 							A = pv[0], B = pv[2], C = pv[1];
 						D3 nh = normalized(cross(B - A, C - A));
-						n     = clip_halfspace(buf[cur], n, nh, dot(nh, A), buf[cur ^ 1]);
+						n     = clip_halfspace(Poly{ buf0 + cur * buf_stride }, n, nh, dot(nh, A), Poly{ buf0 + (cur ^ 1) * buf_stride });
 						cur ^= 1;
-						n  = remove_duplicates(buf[cur], n);
+						n  = remove_duplicates(Poly{ buf0 + cur * buf_stride }, n);
 						ok = n >= 3;
 					}
 				}
@@ -576,15 +597,15 @@ __global__ void __launch_bounds__(NP_BLOCK, 3) narrow_tet_tet_kernel(PairDesc P,
 				nv = n;
 #pragma unroll 1
 				for (int k = 0; k < n; ++k)
-					e[k * 32] = dot(grad0, buf[cur].get(k)) + f0_Mo;
+					e.set(k, dot(grad0, Poly{ buf0 + cur * buf_stride }.get(k)) + f0_Mo);
 				double gN = -dot(grad1_M, nhat);
-				integrate_polygon<TRI, false>(buf[cur], n, nhat, grad0, e, gN, ctx, io, t0, t1, acc, cen, ec);
+				integrate_polygon<TRI, false>(Poly{ buf0 + cur * buf_stride }, n, nhat, grad0, e, gN, ctx, io, t0, t1, acc, cen, ec);
 				tfaces = n;
 			}
 			nvout[i] = (uint8_t)nv;
 		}
 		if (TRI && P.emit_tactile)
-			emit_tactile<false>(tfaces, buf[cur], e, cen, ec, ctx, io, i, lane);
+			emit_tactile<false>(tfaces, Poly{ buf0 + cur * buf_stride }, e, cen, ec, ctx, io, i, lane);
 	}
 	if (lane == 0)
 		acc.n_candidates = P.slab_evals[warp];
@@ -597,15 +618,14 @@ __global__ void __launch_bounds__(NP_BLOCK, 3) narrow_tet_tet_kernel(PairDesc P,
 template <bool TRI>
 __global__ void __launch_bounds__(NP_BLOCK, 3) narrow_tet_plane_kernel(PairDesc P, StepIO io)
 {
-	extern __shared__ __align__(16) unsigned char smem_raw[];
 	int warp = (blockIdx.x * NP_BLOCK + threadIdx.x) >> 5, lane = threadIdx.x & 31;
 	int n_units = io.n_env * P.n_slices;
 	if (warp >= n_units)
 		return;
 	int env = warp / P.n_slices, slice = warp - env * P.n_slices;
-	WarpTile &T = reinterpret_cast<WarpTile *>(smem_raw)[threadIdx.x >> 5];
-	Poly poly   = Poly{ &T.xyz[0][0][0][lane] };
-	double *e   = &T.e[0][lane];
+	WarpTile<4> &T = reinterpret_cast<WarpTile<4> *>(smem_d)[threadIdx.x >> 5];
+	Poly poly{ smem_addr(&T.xyz[0][0][0][lane]) };
+	PressTile e{ smem_addr(&T.e[0][lane]) };
 	Acc acc     = zero_acc();
 	Xform X_WS = load_pose(io.xpos, io.xmat, io.n_geoms, env, P.gA);
 	Xform X_WR = load_pose(io.xpos, io.xmat, io.n_geoms, env, P.gB);
@@ -655,7 +675,7 @@ __global__ void __launch_bounds__(NP_BLOCK, 3) narrow_tet_plane_kernel(PairDesc 
 					D3 a = ld3(g.v[l0]), b = ld3(g.v[l1]);
 					double tt  = d0 / (d0 - d1);
 					D3 pc      = a + tt * (b - a);
-					e[nv * 32] = g.e[l0] + tt * (g.e[l1] - g.e[l0]);
+					e.set(nv, g.e[l0] + tt * (g.e[l1] - g.e[l0]));
 					poly.set(nv, apply(X_WS, pc));
 					++nv;
 				}
@@ -674,12 +694,9 @@ __global__ void __launch_bounds__(NP_BLOCK, 3) narrow_tet_plane_kernel(PairDesc 
 // =================================================================================================
 // K7 finalize: fixed-order reductions
 // =================================================================================================
-__global__ void finalize_pairs_kernel(const PairDesc *pairs, StepIO io)
+__device__ __forceinline__ void finalize_pair(const PairDesc *pairs, const StepIO &io, int env, int p)
 {
-	int idx = blockIdx.x * blockDim.x + threadIdx.x;
-	if (idx >= io.n_env * io.n_pairs)
-		return;
-	int env = idx / io.n_pairs, p = idx - env * io.n_pairs;
+	int idx = env * io.n_pairs + p;
 	const PairDesc &P = pairs[p];
 	hcs_pair_result r;
 	for (int k = 0; k < 3; ++k)
@@ -712,37 +729,38 @@ __global__ void finalize_pairs_kernel(const PairDesc *pairs, StepIO io)
 	io.pair_out[idx] = r;
 }
 
-__global__ void finalize_geoms_kernel(const PairDesc *pairs, StepIO io)
+// K7: one thread per env reduces its pairs (slices in index order) and then its geoms
+__global__ void finalize_kernel(const PairDesc *pairs, StepIO io)
 {
-	int idx = blockIdx.x * blockDim.x + threadIdx.x;
-	if (idx >= io.n_env * io.n_geoms)
+	int env = blockIdx.x * blockDim.x + threadIdx.x;
+	if (env >= io.n_env)
 		return;
-	int env = idx / io.n_geoms, g = idx - env * io.n_geoms;
-	double w[6] = { 0, 0, 0, 0, 0, 0 };
+	for (int p = 0; p < io.n_pairs; ++p)
+		finalize_pair(pairs, io, env, p);
+	double *w = io.geom_wrench + (size_t)env * io.n_geoms * 6;
+	for (int k = 0; k < io.n_geoms * 6; ++k)
+		w[k] = 0;
 	for (int p = 0; p < io.n_pairs; ++p) {
-		const hcs_pair_result &r = io.pair_out[(size_t)env * io.n_pairs + p];
 		if (pairs[p].kind == PAIR_NONE)
 			continue;
-		if (r.gM == g)
-			for (int k = 0; k < 3; ++k)
-				w[k] += r.F[k], w[3 + k] += r.tau[k];
-		if (r.gN == g)
-			for (int k = 0; k < 3; ++k)
-				w[k] -= r.F[k], w[3 + k] -= r.tau[k];
+		const hcs_pair_result &r = io.pair_out[(size_t)env * io.n_pairs + p];
+		for (int k = 0; k < 3; ++k) {
+			w[6 * r.gM + k] += r.F[k], w[6 * r.gM + 3 + k] += r.tau[k];
+			w[6 * r.gN + k] -= r.F[k], w[6 * r.gN + 3 + k] -= r.tau[k];
+		}
 	}
-	for (int k = 0; k < 6; ++k)
-		io.geom_wrench[(size_t)idx * 6 + k] = w[k];
 }
 
 // =================================================================================================
 // launchers
 // =================================================================================================
-template <class K>
+template <int MV, class K>
 static void launch_np(K kernel, int grid, const PairDesc &P, const StepIO &io, cudaStream_t s)
 {
 	// opt in to > 48 KB dynamic shared memory (idempotent and cheap; contexts may live on several devices)
-	cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)NP_SMEM);
-	kernel<<<grid, NP_BLOCK, NP_SMEM, s>>>(P, io);
+	const int smem = (int)sizeof(WarpTile<MV>) * NP_WARPS;
+	cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+	kernel<<<grid, NP_BLOCK, smem, s>>>(P, io);
 }
 
 void launch_narrowphase(const PairDesc &P, const StepIO &io, cudaStream_t s)
@@ -755,21 +773,21 @@ void launch_narrowphase(const PairDesc &P, const StepIO &io, cudaStream_t s)
 	switch (P.kind) {
 		case PAIR_SOFT_RIGID:
 			if (tri)
-				launch_np(narrow_tet_tri_kernel<true>, grid, P, io, s);
+				launch_np<7>(narrow_tet_tri_kernel<true>, grid, P, io, s);
 			else
-				launch_np(narrow_tet_tri_kernel<false>, grid, P, io, s);
+				launch_np<7>(narrow_tet_tri_kernel<false>, grid, P, io, s);
 			break;
 		case PAIR_SOFT_SOFT:
 			if (tri)
-				launch_np(narrow_tet_tet_kernel<true>, grid, P, io, s);
+				launch_np<8>(narrow_tet_tet_kernel<true>, grid, P, io, s);
 			else
-				launch_np(narrow_tet_tet_kernel<false>, grid, P, io, s);
+				launch_np<8>(narrow_tet_tet_kernel<false>, grid, P, io, s);
 			break;
 		case PAIR_SOFT_PLANE:
 			if (tri)
-				launch_np(narrow_tet_plane_kernel<true>, grid, P, io, s);
+				launch_np<4>(narrow_tet_plane_kernel<true>, grid, P, io, s);
 			else
-				launch_np(narrow_tet_plane_kernel<false>, grid, P, io, s);
+				launch_np<4>(narrow_tet_plane_kernel<false>, grid, P, io, s);
 			break;
 		default:
 			break;
@@ -778,11 +796,8 @@ void launch_narrowphase(const PairDesc &P, const StepIO &io, cudaStream_t s)
 
 void launch_finalize(const PairDesc *d_pairs, const StepIO &io, cudaStream_t s)
 {
-	int n1 = io.n_env * io.n_pairs, n2 = io.n_env * io.n_geoms;
-	if (n1 > 0)
-		finalize_pairs_kernel<<<(n1 + 127) / 128, 128, 0, s>>>(d_pairs, io);
-	if (n2 > 0)
-		finalize_geoms_kernel<<<(n2 + 127) / 128, 128, 0, s>>>(d_pairs, io);
+	if (io.n_env > 0)
+		finalize_kernel<<<(io.n_env + 63) / 64, 64, 0, s>>>(d_pairs, io);
 }
 
 } // namespace hcs
