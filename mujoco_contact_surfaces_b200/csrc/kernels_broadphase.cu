@@ -66,6 +66,7 @@ __global__ void __launch_bounds__(BP_BLOCK) broadphase_kernel(PairDesc P, StepIO
 		}
 	}
 	Xform X_AB  = invert_and_compose(X_WA, X_WB);
+	D3 p_BAo    = -rotT(X_AB.R, X_AB.p); // origin of A expressed in B (p_NMo of field_intersection.cc)
 	uint2 *slab = P.slab + (size_t)warp * P.cap;
 	int count = 0, evals = 0; // warp-uniform
 	int q_begin = slice * P.slice_q, q_end = min(P.nq, q_begin + P.slice_q);
@@ -154,6 +155,42 @@ __global__ void __launch_bounds__(BP_BLOCK) broadphase_kernel(PairDesc P, StepIO
 							if ((h0 > 1e-12 && h1 > 1e-12 && h2 > 1e-12 && h3 > 1e-12) ||
 							    (h0 < -1e-12 && h1 < -1e-12 && h2 < -1e-12 && h3 < -1e-12))
 								keep = false;
+						}
+					} else {
+						// soft-soft: CalcEquilibriumPlane + the two IsPlaneNormalAlongPressureGradient culls of
+						// field_intersection.cc (same arithmetic as the clip kernel), then: the equal-pressure plane
+						// must cut BOTH tets, otherwise slice-and-clip is empty.
+						const TetField &f0 = P.A.tet_field[it.y];
+						const TetField &f1 = P.B.tet_field[W.qid[it.x]];
+						int s      = (int)it.x;
+						D3 grad0 = ld3(f0.grad), grad1_N = ld3(f1.grad);
+						D3 grad1_M   = rot(X_AB.R, grad1_N);
+						double f1_Mo = dot(grad1_N, p_BAo) + f1.e0;
+						D3 n_M       = grad0 - grad1_M;
+						double mag   = sqrt(dot(n_M, n_M));
+						keep         = mag > 0.0;
+						if (keep) {
+							D3 nhat   = n_M / mag;
+							D3 p_MQ   = -((f0.e0 - f1_Mo) / mag) * nhat;
+							double pd = dot(nhat, p_MQ);
+							keep      = dot(nhat, ld3(f0.ghat)) > HCS_COS_ALPHA;
+							if (keep)
+								keep = dot(rotT(X_AB.R, -nhat), ld3(f1.ghat)) > HCS_COS_ALPHA;
+							if (keep) {
+								const TetGeom &tg = P.A.tet_geom[it.y];
+								double h0 = dot(nhat, ld3(tg.v[0])) - pd, h1 = dot(nhat, ld3(tg.v[1])) - pd,
+								       h2 = dot(nhat, ld3(tg.v[2])) - pd, h3 = dot(nhat, ld3(tg.v[3])) - pd;
+								if ((h0 > 1e-12 && h1 > 1e-12 && h2 > 1e-12 && h3 > 1e-12) ||
+								    (h0 < -1e-12 && h1 < -1e-12 && h2 < -1e-12 && h3 < -1e-12))
+									keep = false;
+								double g0 = dot(nhat, mk(W.qv[0][s], W.qv[1][s], W.qv[2][s])) - pd,
+								       g1 = dot(nhat, mk(W.qv[3][s], W.qv[4][s], W.qv[5][s])) - pd,
+								       g2 = dot(nhat, mk(W.qv[6][s], W.qv[7][s], W.qv[8][s])) - pd,
+								       g3 = dot(nhat, mk(W.qv[9][s], W.qv[10][s], W.qv[11][s])) - pd;
+								if ((g0 > 1e-12 && g1 > 1e-12 && g2 > 1e-12 && g3 > 1e-12) ||
+								    (g0 < -1e-12 && g1 < -1e-12 && g2 < -1e-12 && g3 < -1e-12))
+									keep = false;
+							}
 						}
 					}
 				}

@@ -473,7 +473,7 @@ __global__ void __launch_bounds__(NP_BLOCK, 3) narrow_tet_tri_kernel(PairDesc P,
 			nvout[i] = (uint8_t)nv;
 		}
 		if (TRI && P.emit_tactile)
-			emit_tactile<false>(tfaces, Poly{ buf0 + cur * buf_stride }, e, cen, ec, ctx, io, i, lane);
+			emit_tactile<false>(tfaces, Poly{ buf0 + cur * buf_stride }, e, cen, ec, ctx, io, (warp - env * P.n_slices) * P.cap + i, lane);
 	}
 	if (lane == 0)
 		acc.n_candidates = P.slab_evals[warp];
@@ -605,7 +605,7 @@ __global__ void __launch_bounds__(NP_BLOCK, 3) narrow_tet_tet_kernel(PairDesc P,
 			nvout[i] = (uint8_t)nv;
 		}
 		if (TRI && P.emit_tactile)
-			emit_tactile<false>(tfaces, Poly{ buf0 + cur * buf_stride }, e, cen, ec, ctx, io, i, lane);
+			emit_tactile<false>(tfaces, Poly{ buf0 + cur * buf_stride }, e, cen, ec, ctx, io, (warp - env * P.n_slices) * P.cap + i, lane);
 	}
 	if (lane == 0)
 		acc.n_candidates = P.slab_evals[warp];

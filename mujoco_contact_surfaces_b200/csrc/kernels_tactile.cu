@@ -157,11 +157,46 @@ __global__ void __launch_bounds__(256) scan_add_kernel(int32_t *out, const int32
 }
 
 constexpr int RASTER_WARPS = 4;
-constexpr int MAX_SAMPLES  = 32 * 32;
+constexpr int RANK_MAX     = 128; // chunk size; bins up to this size get an order-independent tie-break
+constexpr int RASTER_EXTRA = RANK_MAX * 16 + (RANK_MAX + 4) * 4 + RANK_MAX * 4 + RANK_MAX * 24; // fp_box + fp_cnt + rank_k + fp_xy
+__host__ __device__ inline size_t raster_warp_bytes(int S)
+{
+	return (((size_t)S * S * 20 + 15) & ~(size_t)15) + RASTER_EXTRA; // keys + origins, rounded to 16 B, + extras
+}
 
+// Moeller-Trumbore, bvh.cpp:49-74, float32 and in the reference's operation order
+__device__ __forceinline__ bool moller_trumbore(F3 O, F3 D, const TactileTri &t, float &tt, float &u, float &v)
+{
+	F3 v0 = f3(t.v[0], t.v[1], t.v[2]), v1 = f3(t.v[3], t.v[4], t.v[5]), v2 = f3(t.v[6], t.v[7], t.v[8]);
+	F3 edge1 = v1 - v0, edge2 = v2 - v0;
+	F3 h    = crossf(D, edge2);
+	float a = dotf(edge1, h);
+	if (fabsf(a) < 1e-10f)
+		return false;
+	float f = 1.0f / a;
+	F3 sv   = O - v0;
+	u       = f * dotf(sv, h);
+	if (u < 0.0f || u > 1.0f)
+		return false;
+	F3 q = crossf(sv, edge1);
+	v    = f * dotf(D, q);
+	if (v < 0.0f || u + v > 1.0f)
+		return false;
+	tt = f * dotf(edge2, q);
+	return tt > 0.0f;
+}
+
+// One warp per taxel.  Dynamic shared memory per warp: S*S 64-bit depth keys, S*S float3 ray origins,
+// per-chunk triangle footprints/offsets and bin ranks.
+//   phase 0  lanes over samples: ray origins exactly as flat_tactile_sensor.cpp:324-337, keys = +inf
+//   phase 1  lanes over the taxel's binned triangles: each triangle is splatted onto the samples inside its
+//            footprint (sensor frame), every hit does atomicMin(key[sample], t << 32 | tie-break) in shared
+//            memory -> nearest hit per sample, ties resolved by a (pair, order) rank, never by arrival order
+//   phase 2  lanes over samples: winner's barycentric pressure * window weight (float/double mix of :346-391)
+//   phase 3  lane 0 sums the samples in the reference's (i, j) order -> bit-identical float accumulation
 __global__ void __launch_bounds__(32 * RASTER_WARPS) tactile_raster_kernel(SensorDev sd, StepIO io)
 {
-	__shared__ float tile[RASTER_WARPS][MAX_SAMPLES];
+	extern __shared__ __align__(16) unsigned char raster_smem[];
 	int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
 	int ntax = sd.cx * sd.cy;
 	long unit = (long)blockIdx.x * RASTER_WARPS + wib;
@@ -182,6 +217,15 @@ __global__ void __launch_bounds__(32 * RASTER_WARPS) tactile_raster_kernel(Senso
 			*out = 0.0f;
 		return;
 	}
+	const int S = sd.S, S2 = S * S;
+	size_t per_warp = raster_warp_bytes(S);
+	unsigned long long *key = reinterpret_cast<unsigned long long *>(raster_smem + wib * per_warp);
+	float *org              = reinterpret_cast<float *>(key + S2); // [3][S2]
+	// per triangle of the chunk: i0, j0, cols, tie (16-byte aligned: starts at the rounded-up array size)
+	int4 *fp_box            = reinterpret_cast<int4 *>(raster_smem + wib * per_warp + (per_warp - RASTER_EXTRA));
+	int *fp_cnt             = reinterpret_cast<int *>(fp_box + RANK_MAX); // footprint sizes -> exclusive offsets
+	int *rank_k             = fp_cnt + RANK_MAX + 4;                      // rank -> bin slot
+	float *fp_xy            = reinterpret_cast<float *>(rank_k + RANK_MAX); // 2-D triangle vertices, taxel frame
 	const int32_t *items = sd.bin_items + first;
 	const double *R  = io.xmat + ((size_t)env * io.n_geoms + sd.geom) * 9;
 	const double *xp = io.xpos + ((size_t)env * io.n_geoms + sd.geom) * 3;
@@ -190,71 +234,182 @@ __global__ void __launch_bounds__(32 * RASTER_WARPS) tactile_raster_kernel(Senso
 	for (int k = 0; k < 9; ++k)
 		rot[k] = R[k];
 	float xs = (float)sd.size[0], ys = (float)sd.size[1], zs = (float)sd.size[2];
-	F3 normal      = f3((float)rot[2], (float)rot[5], (float)rot[8]);
+	F3 normal         = f3((float)rot[2], (float)rot[5], (float)rot[8]);
 	double topleft[3] = { (double)(-xs), (double)(-ys), (double)zs };
 	double resolution = sd.resolution;
 	float rS = sd.rS, rmean = sd.rmean;
-	int S  = sd.S;
 	F3 D   = f3(-normal.x, -normal.y, -normal.z);
 	F3 off = normal * (float)1e-8;
 	double tmax = 1.5 * zs;
-	for (int s = lane; s < S * S; s += 32) {
-		int i = s / S, j = s - i * S;
-		double pos[3] = { topleft[0] + x * resolution + (double)((float)i * rS) + 0.5 * (double)rS,
-			              topleft[1] + y * resolution + (double)((float)j * rS) + 0.5 * (double)rS, 1.5 * (double)zs };
-		double w[3]   = { rot[0] * pos[0] + rot[1] * pos[1] + rot[2] * pos[2], rot[3] * pos[0] + rot[4] * pos[1] + rot[5] * pos[2],
-			              rot[6] * pos[0] + rot[7] * pos[1] + rot[8] * pos[2] };
-		w[0] += xp[0], w[1] += xp[1], w[2] += xp[2];
-		F3 O = f3((float)w[0], (float)w[1], (float)w[2]) + off;
-		float best_t = 1e30f, best_u = 0, best_v = 0;
-		int best = -1, best_pair = 0, best_order = 0;
-		for (int k = 0; k < n; ++k) {
-			int ti = items[k];
-			const TactileTri &t = io.tri_pool[ti];
-			F3 v0 = f3(t.v[0], t.v[1], t.v[2]), v1 = f3(t.v[3], t.v[4], t.v[5]), v2 = f3(t.v[6], t.v[7], t.v[8]);
-			// Moeller-Trumbore, bvh.cpp:49-74
-			F3 edge1 = v1 - v0, edge2 = v2 - v0;
-			F3 h    = crossf(D, edge2);
-			float a = dotf(edge1, h);
-			if (fabsf(a) < 1e-10f)
-				continue;
-			float f = 1.0f / a;
-			F3 sv   = O - v0;
-			float u = f * dotf(sv, h);
-			if (u < 0.0f || u > 1.0f)
-				continue;
-			F3 q    = crossf(sv, edge1);
-			float v = f * dotf(D, q);
-			if (v < 0.0f || u + v > 1.0f)
-				continue;
-			float tt = f * dotf(edge2, q);
-			if (!(tt > 0.0f))
-				continue;
-			bool better = tt < best_t;
-			if (tt == best_t && best >= 0) // deterministic tie-break independent of pool order
-				better = t.pair < best_pair || (t.pair == best_pair && t.order < best_order);
-			if (better) {
-				best_t = tt, best_u = u, best_v = v, best = ti;
-				best_pair = t.pair, best_order = t.order;
-			}
+	// ---- phase 0
+	// pos[0] depends on i only, pos[1] on j only: tabulate the products rot[r][0]*pos0(i) and rot[r][1]*pos1(j)
+	// (the sums below are evaluated in the reference's order, so every rounding is unchanged)
+	double *prod = reinterpret_cast<double *>(fp_box); // [2][3][S] doubles in the (still unused) phase-1 scratch
+	if (lane < S) {
+		double p0 = topleft[0] + x * resolution + (double)((float)lane * rS) + 0.5 * (double)rS;
+		double p1 = topleft[1] + y * resolution + (double)((float)lane * rS) + 0.5 * (double)rS;
+#pragma unroll
+		for (int r = 0; r < 3; ++r) {
+			prod[r * S + lane]       = rot[3 * r] * p0;
+			prod[(3 + r) * S + lane] = rot[3 * r + 1] * p1;
 		}
-		float val = 0.0f;
-		if (best >= 0 && (double)best_t < tmax && best_t > 0.0f) {
-			const TactileTri &t = io.tri_pool[best];
-			double b0 = (double)(1 - best_u - best_v), b1 = (double)best_u, b2 = (double)best_v;
-			double ev = b0 * t.e[0];
-			ev += b1 * t.e[1];
-			ev += b2 * t.e[2];
-			float raw = (float)(ev * (double)rmean);
-			val       = sd.weights[s] * raw;
-		}
-		tile[wib][s] = val;
 	}
 	__syncwarp();
+	double pz   = 1.5 * (double)zs;
+	double c[3] = { rot[2] * pz, rot[5] * pz, rot[8] * pz };
+	for (int s = lane; s < S2; s += 32) {
+		int i = s / S, j = s - i * S;
+		double w[3] = { prod[i] + prod[3 * S + j] + c[0], prod[S + i] + prod[4 * S + j] + c[1], prod[2 * S + i] + prod[5 * S + j] + c[2] };
+		w[0] += xp[0], w[1] += xp[1], w[2] += xp[2];
+		F3 O = f3((float)w[0], (float)w[1], (float)w[2]) + off;
+		org[s] = O.x, org[S2 + s] = O.y, org[2 * S2 + s] = O.z;
+		key[s] = ~0ull;
+	}
+	__syncwarp();
+	// ---- phase 1: splat.  Triangles are taken in chunks of CHUNK; lanes first compute each triangle's sample
+	// footprint and tie-break rank, a warp scan turns the footprint sizes into item offsets, then the lanes
+	// share the flattened (triangle, sample-row) items evenly; each item tests only the samples of its row that
+	// the triangle can cover (fan triangles are slivers: their boxes are mostly empty).
+	bool ranked = n <= RANK_MAX;
+	double base_x = topleft[0] + x * resolution, base_y = topleft[1] + y * resolution;
+	const double margin = 1e-5; // >> float32 rounding of the hit test at these magnitudes, << sample spacing
+	for (int c0 = 0; c0 < n; c0 += RANK_MAX) {
+		int m = min(RANK_MAX, n - c0);
+		for (int k = lane; k < m; k += 32) {
+			const TactileTri &t = io.tri_pool[items[c0 + k]];
+			double lo[2] = { 1e300, 1e300 }, hi[2] = { -1e300, -1e300 }, lxy[3][2];
+#pragma unroll
+			for (int c = 0; c < 3; ++c) {
+				double d[3] = { (double)t.v[3 * c] - xp[0], (double)t.v[3 * c + 1] - xp[1], (double)t.v[3 * c + 2] - xp[2] };
+				double lx = rot[0] * d[0] + rot[3] * d[1] + rot[6] * d[2], ly = rot[1] * d[0] + rot[4] * d[1] + rot[7] * d[2];
+				lxy[c][0] = lx, lxy[c][1] = ly;
+				lo[0] = fmin(lo[0], lx), hi[0] = fmax(hi[0], lx), lo[1] = fmin(lo[1], ly), hi[1] = fmax(hi[1], ly);
+			}
+			// sample i sits at base + (i + 0.5) * rS
+			int i0 = max(0, (int)ceil((lo[0] - margin - base_x) / (double)rS - 0.5)),
+			    i1 = min(S - 1, (int)floor((hi[0] + margin - base_x) / (double)rS - 0.5));
+			int j0 = max(0, (int)ceil((lo[1] - margin - base_y) / (double)rS - 0.5)),
+			    j1 = min(S - 1, (int)floor((hi[1] + margin - base_y) / (double)rS - 0.5));
+			int rows = max(0, i1 - i0 + 1), cols = max(0, j1 - j0 + 1);
+			int r = c0 + k;
+			if (ranked) { // order-independent tie-break: rank under the (pair, order) key
+				r = 0;
+				for (int k2 = 0; k2 < n; ++k2) {
+					const TactileTri &o = io.tri_pool[items[k2]];
+					r += (o.pair < t.pair) || (o.pair == t.pair && (o.order < t.order || (o.order == t.order && items[k2] < items[k])));
+				}
+				rank_k[r] = k;
+			}
+			fp_cnt[k] = cols > 0 ? rows : 0; // one item per sample row of the footprint
+			fp_box[k] = make_int4(i0, j0, j1, r);
+#pragma unroll
+			for (int c = 0; c < 3; ++c) { // 2-D vertices in the sensor frame, relative to the taxel corner
+				fp_xy[6 * k + 2 * c]     = (float)(lxy[c][0] - base_x);
+				fp_xy[6 * k + 2 * c + 1] = (float)(lxy[c][1] - base_y);
+			}
+		}
+		__syncwarp();
+		// exclusive scan of up to RANK_MAX footprint sizes: 4 consecutive entries per lane
+		int v4[4], sum = 0;
+#pragma unroll
+		for (int q = 0; q < 4; ++q) {
+			int idx = 4 * lane + q;
+			v4[q]   = idx < m ? fp_cnt[idx] : 0;
+			sum += v4[q];
+		}
+		int incl = sum;
+#pragma unroll
+		for (int o = 1; o < 32; o <<= 1) {
+			int t = __shfl_up_sync(0xffffffffu, incl, o);
+			if (lane >= o)
+				incl += t;
+		}
+		int total = __shfl_sync(0xffffffffu, incl, 31);
+		int excl  = incl - sum;
+		__syncwarp();
+#pragma unroll
+		for (int q = 0; q < 4; ++q) {
+			int idx = 4 * lane + q;
+			if (idx <= m)
+				fp_cnt[idx] = excl;
+			excl += v4[q];
+		}
+		if (lane == 31 && m == RANK_MAX)
+			fp_cnt[RANK_MAX] = total;
+		__syncwarp();
+		for (int w = lane; w < total; w += 32) {
+			int lo_k = 0, hi_k = m; // largest k with offset[k] <= w
+			while (hi_k - lo_k > 1) {
+				int mid = (lo_k + hi_k) >> 1;
+				if (fp_cnt[mid] <= w)
+					lo_k = mid;
+				else
+					hi_k = mid;
+			}
+			int4 b = fp_box[lo_k];
+			int i  = b.x + (w - fp_cnt[lo_k]);
+			// conservative column span of row i: y-extent of (triangle  ∩  strip |x - x_i| <= m), widened by m.
+			// Any sample within the float32 hit tolerance (~1e-6 m) of the triangle lies inside this span.
+			const float m2 = 2e-5f;
+			float xi = ((float)i + 0.5f) * rS, xa = xi - m2, xb = xi + m2;
+			float ymin = 1e30f, ymax = -1e30f;
+			const float *q = fp_xy + 6 * lo_k;
+#pragma unroll
+			for (int c = 0; c < 3; ++c) {
+				float px = q[2 * c], py = q[2 * c + 1], qx = q[2 * ((c + 1) % 3)], qy = q[2 * ((c + 1) % 3) + 1];
+				if (px >= xa && px <= xb)
+					ymin = fminf(ymin, py), ymax = fmaxf(ymax, py);
+				float dx = qx - px;
+				if ((px - xa) * (qx - xa) < 0.f) {
+					float yy = py + (xa - px) / dx * (qy - py);
+					ymin = fminf(ymin, yy), ymax = fmaxf(ymax, yy);
+				}
+				if ((px - xb) * (qx - xb) < 0.f) {
+					float yy = py + (xb - px) / dx * (qy - py);
+					ymin = fminf(ymin, yy), ymax = fmaxf(ymax, yy);
+				}
+			}
+			int ja = max(b.y, (int)ceilf((ymin - m2) / rS - 0.5f)), jb = min(b.z, (int)floorf((ymax + m2) / rS - 0.5f));
+			const TactileTri &t = io.tri_pool[items[c0 + lo_k]];
+			for (int j = ja; j <= jb; ++j) {
+				int s = i * S + j;
+				F3 O  = f3(org[s], org[S2 + s], org[2 * S2 + s]);
+				float tt, u, v;
+				if (moller_trumbore(O, D, t, tt, u, v))
+					atomicMin(&key[s], ((unsigned long long)__float_as_uint(tt) << 32) | (unsigned)b.w);
+			}
+		}
+		__syncwarp();
+	}
+	// ---- phase 2: winners -> weighted sample pressures (written over the key slots)
+	float *val = reinterpret_cast<float *>(key);
+	for (int s = lane; s < S2; s += 32) {
+		unsigned long long kk = key[s];
+		float value = 0.0f;
+		if (kk != ~0ull) {
+			unsigned tie = (unsigned)(kk & 0xffffffffu);
+			int k        = ranked ? rank_k[tie] : (int)tie;
+			const TactileTri &t = io.tri_pool[items[k]];
+			F3 O = f3(org[s], org[S2 + s], org[2 * S2 + s]);
+			float tt, u, v;
+			if (moller_trumbore(O, D, t, tt, u, v) && (double)tt < tmax) {
+				double b0 = (double)(1 - u - v), b1 = (double)u, b2 = (double)v;
+				double ev = b0 * t.e[0];
+				ev += b1 * t.e[1];
+				ev += b2 * t.e[2];
+				float raw = (float)(ev * (double)rmean);
+				value     = sd.weights[s] * raw;
+			}
+		}
+		val[2 * s] = value; // low word of this sample's own key slot (read above by the same lane)
+	}
+	__syncwarp();
+	// ---- phase 3
 	if (lane == 0) {
 		float avg = 0;
-		for (int s = 0; s < S * S; ++s)
-			avg += tile[wib][s];
+#pragma unroll 8
+		for (int s = 0; s < S2; ++s) // loads are independent (batched by the unroll); the adds stay in order
+			avg += val[2 * s];
 		*out = avg;
 	}
 }
@@ -282,7 +437,9 @@ int launch_tactile(const SensorDev &sd, const StepIO &io, const PairDesc *d_pair
 	scan_add_kernel<<<n_tiles, 256, 0, s>>>(sd.bin_offset, sd.scan_tmp, ncell);
 	if (io.max_tris > 0)
 		tactile_bin_kernel<true><<<tgrid, 256, 0, s>>>(sd, io, d_pairs);
-	tactile_raster_kernel<<<(ncell + RASTER_WARPS - 1) / RASTER_WARPS, 32 * RASTER_WARPS, 0, s>>>(sd, io);
+	int raster_smem = RASTER_WARPS * (int)raster_warp_bytes(sd.S);
+	cudaFuncSetAttribute(tactile_raster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, raster_smem);
+	tactile_raster_kernel<<<(ncell + RASTER_WARPS - 1) / RASTER_WARPS, 32 * RASTER_WARPS, raster_smem, s>>>(sd, io);
 	return 5 + (io.max_tris > 0 ? 2 : 0);
 }
 
