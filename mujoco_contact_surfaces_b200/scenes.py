@@ -225,3 +225,44 @@ SCENES = {
     "c3_soft_soft": soft_soft,
     "c4_objects_on_plane": objects_on_plane,
 }
+
+
+# ---- every mesh family of plugin.cpp:633-808 in one scene (parity coverage, not a benchmark) ---------------
+def mixed_shapes(triangle=False):
+    geoms = [Geom("rigid_box", GEOM_BOX, [0.3, 0.3, 0.05], [0, 1.0, 0.1, 0.4, 0.4]),            # 0 rigid grid box
+             Geom("soft_cyl_long", GEOM_CYLINDER, [0.03, 0.06, 0], [7e4, 3.0, 0.02, 0.3, 0.3]),   # 1 MA cylinder, segment
+             Geom("soft_cyl_flat", GEOM_CYLINDER, [0.06, 0.02, 0], [7e4, 3.0, 0.03, 0.3, 0.3]),   # 2 MA cylinder, disc
+             Geom("soft_box_grid", GEOM_BOX, [0.04, 0.05, 0.03], [4e4, 2.0, 0.03, 0.2, 0.2]),      # 3 soft grid box
+             Geom("rigid_sphere", GEOM_SPHERE, [0.05], [0, 1.0, 0.02, 0.5, 0.5]),                  # 4 rigid sphere
+             Geom("rigid_ellipsoid", GEOM_ELLIPSOID, [0.05, 0.03, 0.04], [0, 1.0, 0.02, 0.5, 0.5]),  # 5
+             Geom("rigid_cyl", GEOM_CYLINDER, [0.04, 0.05, 0], [0, 1.0, 0.02, 0.5, 0.5]),          # 6 rigid cylinder
+             Geom("soft_box_ma", GEOM_BOX, [0.05, 0.05, 0.05], [6e4, 4.0, 0, 0.3, 0.3])]           # 7 soft MA cube
+    # soft things resting on the rigid box, rigid things pressed into soft things, one soft-soft pair
+    pairs = [(1, 0), (2, 0), (0, 3), (4, 3), (5, 7), (6, 7), (1, 2)]
+    sc = Scene("mixed_shapes", geoms, pairs, triangle=triangle)
+    top = 0.05
+
+    def pose(rng, env, xpos, xmat, vel):
+        xmat[:] = np.eye(3).reshape(-1)
+        xpos[0] = [0, 0, 0]
+        # cylinders lying / standing on the box with small random tilt
+        xpos[1] = [-0.15, -0.15, top + 0.06 - rng.uniform(0.002, 0.01)]
+        xmat[1] = rot_zyx(rng.uniform(0, 6.28), *np.deg2rad(rng.uniform(-5, 5, size=2))).reshape(-1)
+        xpos[2] = [-0.13, -0.13 + rng.uniform(-0.01, 0.01), top + 0.06 + 0.06 + 0.02 - rng.uniform(0.012, 0.02)]
+        xmat[2] = rot_zyx(rng.uniform(0, 6.28), *np.deg2rad(rng.uniform(-3, 3, size=2))).reshape(-1)
+        xpos[3] = [0.15, 0.15, top + 0.03 - rng.uniform(0.002, 0.008)]
+        xmat[3] = rot_zyx(rng.uniform(0, 6.28), *np.deg2rad(rng.uniform(-4, 4, size=2))).reshape(-1)
+        xpos[4] = [0.15 + rng.uniform(-0.01, 0.01), 0.15, xpos[3][2] + 0.03 + 0.05 - rng.uniform(0.003, 0.01)]
+        xmat[4] = random_rotation(rng).reshape(-1)
+        xpos[7] = [0.6, 0, 0.3]
+        xmat[7] = random_rotation(rng).reshape(-1)
+        d = random_rotation(rng)[:, 0]
+        xpos[5] = xpos[7] + d * 0.075
+        xmat[5] = random_rotation(rng).reshape(-1)
+        xpos[6] = xpos[7] - d * 0.08
+        xmat[6] = random_rotation(rng).reshape(-1)
+        for g in (1, 2, 3, 4, 5, 6):
+            vel[g] = random_velocity(rng, 0.2, 2.0)
+
+    sc.pose_fn = pose
+    return sc

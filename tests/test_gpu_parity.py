@@ -91,6 +91,33 @@ def test_c2_myrmex_windows(hcs_lib, window, sigma):
                with_sensors=True)
 
 
+@pytest.mark.parametrize("triangle", [False, True])
+def test_mixed_shapes_every_mesh_family(hcs_lib, triangle):
+    """Soft MA cylinders (segment and disc regimes), soft grid box, soft MA cube, rigid box / sphere / ellipsoid /
+    cylinder surfaces, a soft-soft cylinder pair and one pair without contact."""
+    _run_scene(scenes.mixed_shapes(triangle=triangle), 24, seed=21, hcs_lib=hcs_lib)
+
+
+def test_geom_update_rebuilds_mesh_and_field(hcs_lib):
+    """onGeomChanged (plugin.cpp:828-975): after a size change the engine matches an oracle built at the new size."""
+    scene = scenes.sphere_on_box()
+    eng = make_engine(scene, 4)
+    xpos, xmat, vel = scene.poses(4, seed=77)
+    eng.step(xpos, xmat, vel)
+    before = eng.pair_results()["F"].copy()
+    eng.update_geom(1, [0.085, 0, 0])  # sphere0 grows by 5 mm
+    eng.step(xpos, xmat, vel)
+    res = eng.pair_results()
+    bigger = scenes.sphere_on_box()
+    bigger.geoms[1].size[0] = 0.085
+    orc = make_oracle(bigger)
+    for e in range(4):
+        ref_pairs, _ = oracle_env(orc, bigger, xpos[e], xmat[e], vel[e], sensors=False)
+        compare_env(res[e], [eng.emitted(e, 0)], ref_pairs)
+    assert not np.allclose(before, res["F"])
+    eng.close()
+
+
 def test_batch_is_env_independent(hcs_lib):
     """A shard of envs gives bit-identical results to the same envs inside a larger batch (multi-GPU
     sharding is by env index with no exchange)."""
