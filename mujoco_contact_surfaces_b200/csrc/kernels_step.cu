@@ -119,7 +119,7 @@ __device__ __forceinline__ D3 face_force(D3 p, D3 n, double fn0, double k, const
 	double eps   = 1.0e-4 * 1.0e-2;
 	eps          = eps * eps;
 	double vslip = sqrt(dot(vt, vt) + eps);
-	D3 that      = vt / vslip;
+	D3 that      = vt * (1.0 / vslip); // one division; quadrature tolerance is 1e-8, not bit parity
 	double mu_r  = c.mu;
 	double s     = vslip / 1.0e-4;
 	if (s < 1)
@@ -242,7 +242,8 @@ __device__ __forceinline__ void integrate_polygon(Poly P, int n, D3 nhat, D3 gra
 	if (n == 3)
 		cen = ((p0 + p1) + pi) / 3.0;
 	else
-		cen = A2 != 0.0 ? csum / (3.0 * A2) : p0;
+		cen = A2 != 0.0 ? (TRI ? csum / (3.0 * A2) : csum * (1.0 / (3.0 * A2))) : p0; // TRI: the centroid becomes a
+		                                                                              // tactile vertex, keep it exact
 	double ec = e.get(0) + dot(grad, cen - p0);
 	cen_out   = cen;
 	ec_out    = ec;
@@ -259,7 +260,7 @@ __device__ __forceinline__ void integrate_polygon(Poly P, int n, D3 nhat, D3 gra
 			acc.ac = acc.ac + area * cW;
 		}
 		if (area > 1.0e-14 && !(gMf < 1.0e-14 || gNf < 1.0e-14)) {
-			double g   = 1.0 / (1.0 / gMf + 1.0 / gNf);
+			double g   = gNf == kInf ? gMf : 1.0 / (1.0 / gMf + 1.0 / gNf);
 			double fn0 = area * ec, k = area * g;
 			D3 nf      = sg * nW;
 			D3 f       = face_force(cW, nf, fn0, k, c);
@@ -286,13 +287,13 @@ __device__ __forceinline__ void integrate_polygon(Poly P, int n, D3 nhat, D3 gra
 		double sg   = a2 < 0 ? -1.0 : 1.0;
 		double area = 0.5 * (sg * a2);
 		double gMf = sg * gM, gNf = gN == kInf ? gN : sg * gN;
-		D3 fc = ((aW + bW) + cW) / 3.0;
+		D3 fc = ((aW + bW) + cW) * (1.0 / 3.0);
 		if (area > 0) {
 			acc.area += area;
 			acc.ac = acc.ac + area * fc;
 		}
 		if (area > 1.0e-14 && !(gMf < 1.0e-14 || gNf < 1.0e-14)) {
-			double g  = 1.0 / (1.0 / gMf + 1.0 / gNf);
+			double g  = gNf == kInf ? gMf : 1.0 / (1.0 / gMf + 1.0 / gNf);
 			double b3 = 1 / 3.;
 			double pc = b3 * ea;
 			pc += b3 * eb;
