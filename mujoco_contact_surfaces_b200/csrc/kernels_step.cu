@@ -30,6 +30,7 @@ template <int MV>
 struct WarpTile {
 	double xyz[2][MV][3][32];
 	double e[MV][32];
+	double ctx[40]; // WarpCtx block
 };
 
 // Explicit shared-window accesses: through a generic pointer stored in a struct the compiler emitted
@@ -66,12 +67,45 @@ __device__ __forceinline__ unsigned smem_addr(const void *p)
 	return (unsigned)(reinterpret_cast<const char *>(p) - reinterpret_cast<const char *>(smem_d));
 }
 
-struct WarpCtx { // warp-uniform per (env, pair) data
-	Xform X_WA;    // soft geom A (computation frame) -> world
-	D3 xA, wA, vA; // origin, angular, linear velocity of geom A (world)
-	D3 xB, wB, vB;
+// Warp-uniform per (env, pair) data.  The 39 doubles (poses, velocities, relative transform) live in SHARED
+// memory, not in registers: holding them in registers across the clip loop cost ~80 registers per thread and
+// capped the kernel at 3 warps per scheduler (profiles/r01_notes.md).  Uniform LDS reads are broadcasts.
+constexpr int CTX_DOUBLES = 40;
+struct WarpCtx {
+	unsigned a; // byte offset in smem_d of: R_WA[9], xA[3], wA[3], vA[3], xB[3], wB[3], vB[3], R_AB[9], p_AB[3]
 	double dissipation, mu, sign;
 	int apply, env, pair;
+	__device__ __forceinline__ D3 v(int i) const
+	{
+		const double *p = smem_d + (a >> 3) + i;
+		return mk(p[0], p[1], p[2]);
+	}
+	__device__ __forceinline__ Xform X_WA() const // soft geom A (computation frame) -> world
+	{
+		Xform X;
+		const double *p = smem_d + (a >> 3);
+#pragma unroll
+		for (int i = 0; i < 9; ++i)
+			X.R[i] = p[i];
+		X.p = mk(p[9], p[10], p[11]);
+		return X;
+	}
+	__device__ __forceinline__ Xform X_AB() const // geom B -> geom A
+	{
+		Xform X;
+		const double *p = smem_d + (a >> 3) + 27;
+#pragma unroll
+		for (int i = 0; i < 9; ++i)
+			X.R[i] = p[i];
+		X.p = mk(p[9], p[10], p[11]);
+		return X;
+	}
+	__device__ __forceinline__ D3 xA() const { return v(9); } // origin, angular, linear velocity of geom A (world)
+	__device__ __forceinline__ D3 wA() const { return v(12); }
+	__device__ __forceinline__ D3 vA() const { return v(15); }
+	__device__ __forceinline__ D3 xB() const { return v(18); }
+	__device__ __forceinline__ D3 wB() const { return v(21); }
+	__device__ __forceinline__ D3 vB() const { return v(24); }
 };
 
 struct Acc {
@@ -87,15 +121,34 @@ __device__ __forceinline__ void load_vel(const double *vel, int n_geoms, int env
 	v               = ld3(p + 3);
 }
 
-__device__ __forceinline__ WarpCtx make_ctx(const PairDesc &P, const StepIO &io, int env, const Xform &X_WA,
-                                            const Xform &X_WB)
+// Lane 0 loads the two poses and velocities, forms X_AB = X_WA^-1 X_WB and parks everything in the warp's
+// shared-memory context block.
+__device__ __forceinline__ WarpCtx make_ctx(const PairDesc &P, const StepIO &io, int env, double *block, int lane)
 {
 	WarpCtx c;
-	c.X_WA = X_WA;
-	c.xA   = X_WA.p;
-	c.xB   = X_WB.p;
-	load_vel(io.vel, io.n_geoms, env, P.gA, c.wA, c.vA);
-	load_vel(io.vel, io.n_geoms, env, P.gB, c.wB, c.vB);
+	c.a = smem_addr(block);
+	if (lane == 0) {
+		Xform X_WA = load_pose(io.xpos, io.xmat, io.n_geoms, env, P.gA);
+		Xform X_WB = load_pose(io.xpos, io.xmat, io.n_geoms, env, P.gB);
+		Xform X_AB = invert_and_compose(X_WA, X_WB);
+		D3 wA, vA, wB, vB;
+		load_vel(io.vel, io.n_geoms, env, P.gA, wA, vA);
+		load_vel(io.vel, io.n_geoms, env, P.gB, wB, vB);
+#pragma unroll
+		for (int i = 0; i < 9; ++i) {
+			block[i]      = X_WA.R[i];
+			block[27 + i] = X_AB.R[i];
+		}
+		const D3 trip[7] = { X_WA.p, wA, vA, X_WB.p, wB, vB, X_AB.p };
+		const int off[7] = { 9, 12, 15, 18, 21, 24, 36 };
+#pragma unroll
+		for (int k = 0; k < 7; ++k) {
+			block[off[k]]     = trip[k].x;
+			block[off[k] + 1] = trip[k].y;
+			block[off[k] + 2] = trip[k].z;
+		}
+	}
+	__syncwarp();
 	c.dissipation = P.dissipation;
 	c.mu          = P.mu;
 	c.sign        = P.sign;
@@ -108,8 +161,8 @@ __device__ __forceinline__ WarpCtx make_ctx(const PairDesc &P, const StepIO &io,
 // passiveCallback force law (plugin.cpp:440-475) for one quadrature point; A = M (unswapped labelling)
 __device__ __forceinline__ D3 face_force(D3 p, D3 n, double fn0, double k, const WarpCtx &c)
 {
-	D3 vAq    = c.vA + cross(c.wA, p - c.xA);
-	D3 vBq    = c.vB + cross(c.wB, p - c.xB);
+	D3 vAq    = c.vA() + cross(c.wA(), p - c.xA());
+	D3 vBq    = c.vB() + cross(c.wB(), p - c.xB());
 	D3 vrel   = vAq - vBq;
 	double vn = dot(vrel, n);
 	double fn = fmax(0., 1. - c.dissipation * vn) * (fn0 - 0.001 * k * vn);
@@ -221,7 +274,8 @@ __device__ __forceinline__ void integrate_polygon(Poly P, int n, D3 nhat, D3 gra
 {
 	const double kInf = __longlong_as_double(0x7ff0000000000000LL);
 	double gM         = dot(grad, nhat);
-	D3 nW             = IDENT ? nhat : rot(c.X_WA.R, nhat);
+	const Xform XW    = IDENT ? Xform() : c.X_WA();
+	D3 nW             = IDENT ? nhat : rot(XW.R, nhat);
 	acc.n_polygons += 1;
 	// polygon centroid (contact_surface_utility.cc CalcPolygonCentroid): fan about vertex 0, signed
 	// areas measured along nhat
@@ -247,7 +301,7 @@ __device__ __forceinline__ void integrate_polygon(Poly P, int n, D3 nhat, D3 gra
 	double ec = e.get(0) + dot(grad, cen - p0);
 	cen_out   = cen;
 	ec_out    = ec;
-	D3 cW     = IDENT ? cen : apply(c.X_WA, cen);
+	D3 cW     = IDENT ? cen : apply(XW, cen);
 	// A face whose winding opposes nhat (only possible for a negatively oriented tet of a user mesh) gets
 	// the flipped normal, like the mesh constructors that derive face normals from the winding.
 	if (!TRI) {
@@ -276,12 +330,12 @@ __device__ __forceinline__ void integrate_polygon(Poly P, int n, D3 nhat, D3 gra
 	acc.n_faces += n;
 	int cur   = n - 1;
 	D3 a      = P.get(cur);
-	D3 aW     = IDENT ? a : apply(c.X_WA, a);
+	D3 aW     = IDENT ? a : apply(XW, a);
 	double ea = e.get(cur);
 #pragma unroll 1
 	for (int i = 0; i < n; ++i) {
 		D3 b        = P.get(i);
-		D3 bW       = IDENT ? b : apply(c.X_WA, b);
+		D3 bW       = IDENT ? b : apply(XW, b);
 		double eb   = e.get(i);
 		double a2   = dot(cross(b - a, cen - a), nhat);
 		double sg   = a2 < 0 ? -1.0 : 1.0;
@@ -333,13 +387,14 @@ __device__ __forceinline__ void emit_tactile(int n_faces, Poly P, PressTile e, D
 	base    = __shfl_sync(FULL_MASK, base, 0);
 	int pos = base + incl - n_faces;
 	if (n_faces > 0) {
-		D3 cW     = IDENT ? cen : apply(c.X_WA, cen);
+		const Xform XW = IDENT ? Xform() : c.X_WA();
+		D3 cW     = IDENT ? cen : apply(XW, cen);
 		int cur   = n_faces - 1;
-		D3 aW     = IDENT ? P.get(cur) : apply(c.X_WA, P.get(cur));
+		D3 aW     = IDENT ? P.get(cur) : apply(XW, P.get(cur));
 		double ea = e.get(cur);
 #pragma unroll 1
 		for (int i = 0; i < n_faces; ++i, ++pos) {
-			D3 bW     = IDENT ? P.get(i) : apply(c.X_WA, P.get(i));
+			D3 bW     = IDENT ? P.get(i) : apply(XW, P.get(i));
 			double eb = e.get(i);
 			if (pos < io.max_tris) {
 				// (prev, next, centroid); the M/N swap of ContactSurface reverses winding by swapping the
@@ -411,7 +466,7 @@ __device__ __forceinline__ Acc zero_acc()
 // K4 soft-rigid narrowphase: one thread per (tet, triangle) candidate
 // =================================================================================================
 template <bool TRI>
-__global__ void __launch_bounds__(NP_BLOCK, 3) narrow_tet_tri_kernel(PairDesc P, StepIO io)
+__global__ void __launch_bounds__(NP_BLOCK, 4) narrow_tet_tri_kernel(PairDesc P, StepIO io)
 {
 	int warp = (blockIdx.x * NP_BLOCK + threadIdx.x) >> 5, lane = threadIdx.x & 31;
 	int n_units = io.n_env * P.n_slices;
@@ -428,10 +483,7 @@ __global__ void __launch_bounds__(NP_BLOCK, 3) narrow_tet_tri_kernel(PairDesc P,
 	const unsigned buf0 = smem_addr(&T.xyz[0][0][0][lane]), buf_stride = (unsigned)sizeof(T.xyz[0]);
 	PressTile e{ smem_addr(&T.e[0][lane]) };
 	Acc acc     = zero_acc();
-	Xform X_WS = load_pose(io.xpos, io.xmat, io.n_geoms, env, P.gA);
-	Xform X_WR = load_pose(io.xpos, io.xmat, io.n_geoms, env, P.gB);
-	Xform X_SR = invert_and_compose(X_WS, X_WR);
-	WarpCtx ctx = make_ctx(P, io, env, X_WS, X_WR);
+	WarpCtx ctx = make_ctx(P, io, env, T.ctx, lane);
 	const uint2 *slab = P.slab + (size_t)warp * P.cap;
 	uint8_t *nvout    = P.slab_nverts + (size_t)warp * P.cap;
 	const double kInf = __longlong_as_double(0x7ff0000000000000LL);
@@ -449,6 +501,7 @@ __global__ void __launch_bounds__(NP_BLOCK, 3) narrow_tet_tri_kernel(PairDesc P,
 			const TetField &tf = P.A.tet_field[tet];
 			const TriRec &tr   = P.B.tris[tri];
 			// the normal/gradient cull and the trivial reject already ran in the broadphase
+			const Xform X_SR = ctx.X_AB();
 			D3 nS = rot(X_SR.R, ld3(tr.n));
 #pragma unroll
 			for (int k = 0; k < 3; ++k)
@@ -502,11 +555,9 @@ __global__ void __launch_bounds__(NP_BLOCK, 3) narrow_tet_tet_kernel(PairDesc P,
 	const unsigned buf0 = smem_addr(&T.xyz[0][0][0][lane]), buf_stride = (unsigned)sizeof(T.xyz[0]);
 	PressTile e{ smem_addr(&T.e[0][lane]) };
 	Acc acc     = zero_acc();
-	Xform X_WM = load_pose(io.xpos, io.xmat, io.n_geoms, env, P.gA);
-	Xform X_WN = load_pose(io.xpos, io.xmat, io.n_geoms, env, P.gB);
-	Xform X_MN = invert_and_compose(X_WM, X_WN);
+	WarpCtx ctx = make_ctx(P, io, env, T.ctx, lane);
+	const Xform X_MN = ctx.X_AB();
 	D3 p_NMo   = -rotT(X_MN.R, X_MN.p);
-	WarpCtx ctx = make_ctx(P, io, env, X_WM, X_WN);
 	const uint2 *slab = P.slab + (size_t)warp * P.cap;
 	uint8_t *nvout    = P.slab_nverts + (size_t)warp * P.cap;
 #pragma unroll 1
@@ -628,13 +679,11 @@ __global__ void __launch_bounds__(NP_BLOCK, 3) narrow_tet_plane_kernel(PairDesc 
 	Poly poly{ smem_addr(&T.xyz[0][0][0][lane]) };
 	PressTile e{ smem_addr(&T.e[0][lane]) };
 	Acc acc     = zero_acc();
-	Xform X_WS = load_pose(io.xpos, io.xmat, io.n_geoms, env, P.gA);
-	Xform X_WR = load_pose(io.xpos, io.xmat, io.n_geoms, env, P.gB);
-	Xform X_SR = invert_and_compose(X_WS, X_WR);
+	WarpCtx ctx = make_ctx(P, io, env, T.ctx, lane);
+	const Xform X_WS = ctx.X_WA(), X_SR = ctx.X_AB();
 	D3 n_S     = mk(X_SR.R[2], X_SR.R[5], X_SR.R[8]);
 	double pd  = dot(n_S, X_SR.p);
 	D3 nhat_W  = rot(X_WS.R, n_S);
-	WarpCtx ctx = make_ctx(P, io, env, X_WS, X_WR);
 	const double kInf = __longlong_as_double(0x7ff0000000000000LL);
 	int q_begin = slice * P.slice_q, q_end = min(P.nq, q_begin + P.slice_q);
 	uint8_t *nvout = P.slab_nverts + (size_t)env * P.nq;
