@@ -335,7 +335,7 @@ static void build_pairs(hcs_ctx *c)
 	const int n_env = c->cfg.n_envs;
 	c->pair_desc.clear();
 	const char *tu_env = getenv("HCS_TARGET_UNITS"); // tuning knob: warps per launch the slicing aims for
-	const long target_units = tu_env ? atol(tu_env) : 16384;
+	const long target_units = tu_env ? atol(tu_env) : 4096;
 	for (size_t pi = 0; pi < c->pairs.size(); ++pi) {
 		int g1 = c->pairs[pi].first, g2 = c->pairs[pi].second;
 		const GeomHost *c1 = &c->geoms[g1], *c2 = &c->geoms[g2];

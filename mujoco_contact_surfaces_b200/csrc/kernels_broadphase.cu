@@ -28,15 +28,30 @@ struct __align__(16) WarpQueues {
 	uint2 leafq[LEAF_Q];
 	double qv[12][32];  // transformed query vertices (tri: 9 + rotated normal 3; tet: 12), lane-interleaved
 	float qbox[6][32];
+	float qpl[4][32]; // soft-rigid: the query triangle's plane (unit normal, offset) in A's frame
 	int qid[32];
 };
 
-__device__ __forceinline__ bool box_overlap(const float *q, float4 a, float4 b, float4 c, bool left)
+// Box overlap of the query with one child of a node; for triangle queries (PLANE) the child box must also
+// straddle the triangle's plane: a subtree entirely on one side of that plane cannot meet the triangle.
+// The single-interior-vertex sphere tets are slivers whose boxes all overlap a large rigid triangle's box;
+// the plane test prunes those whole subtrees (profiles/r01_notes.md).
+template <bool PLANE>
+__device__ __forceinline__ bool box_overlap(const float *q, const float *pl, float4 a, float4 b, float4 c, bool left)
 {
 	// node layout: llo[3] lhi[3] rlo[3] rhi[3]
 	float lo0 = left ? a.x : b.z, lo1 = left ? a.y : b.w, lo2 = left ? a.z : c.x;
 	float hi0 = left ? a.w : c.y, hi1 = left ? b.x : c.z, hi2 = left ? b.y : c.w;
-	return q[0] <= hi0 && q[3] >= lo0 && q[1] <= hi1 && q[4] >= lo1 && q[2] <= hi2 && q[5] >= lo2;
+	bool hit = q[0] <= hi0 && q[3] >= lo0 && q[1] <= hi1 && q[4] >= lo1 && q[2] <= hi2 && q[5] >= lo2;
+	if (PLANE && hit) {
+		float cx = 0.5f * (lo0 + hi0), cy = 0.5f * (lo1 + hi1), cz = 0.5f * (lo2 + hi2);
+		float hx = 0.5f * (hi0 - lo0), hy = 0.5f * (hi1 - lo1), hz = 0.5f * (hi2 - lo2);
+		float dist = pl[0] * cx + pl[1] * cy + pl[2] * cz - pl[3];
+		float rad  = fabsf(pl[0]) * hx + fabsf(pl[1]) * hy + fabsf(pl[2]) * hz;
+		// float rounding of the box/plane arithmetic is ~1e-7 relative; the margin is 1e-5 relative + 1e-7 m
+		hit = fabsf(dist) <= rad * 1.00001f + 1e-5f * (fabsf(pl[3]) + fabsf(cx) + fabsf(cy) + fabsf(cz)) + 1e-7f;
+	}
+	return hit;
 }
 
 // QTET: query elements are tets of B (soft-soft), otherwise triangles of B (soft-rigid)
@@ -115,6 +130,10 @@ __global__ void __launch_bounds__(BP_BLOCK) broadphase_kernel(PairDesc P, StepIO
 #pragma unroll
 			for (int k = 0; k < 6; ++k)
 				W.qbox[k][slot] = box[k];
+			if (!QTET) {
+				W.qpl[0][slot] = (float)v[9], W.qpl[1][slot] = (float)v[10], W.qpl[2][slot] = (float)v[11];
+				W.qpl[3][slot] = (float)(v[9] * v[0] + v[10] * v[1] + v[11] * v[2]);
+			}
 			W.qid[slot]   = q;
 			W.nodeq[slot] = make_uint2((unsigned)slot, 0u);
 		}
@@ -216,14 +235,20 @@ __global__ void __launch_bounds__(BP_BLOCK) broadphase_kernel(PairDesc P, StepIO
 #pragma unroll
 					for (int a = 0; a < 6; ++a)
 						qb[a] = W.qbox[a][s];
+					float pl[4] = { 0.f, 0.f, 0.f, 0.f };
+					if (!QTET) {
+#pragma unroll
+						for (int a = 0; a < 4; ++a)
+							pl[a] = W.qpl[a][s];
+					}
 					const float4 *nd = nodes4 + 4 * (size_t)it.y;
 					float4 a = nd[0], b = nd[1], c = nd[2], d = nd[3];
 					cl = __float_as_int(d.x), cr = __float_as_int(d.y);
-					if (box_overlap(qb, a, b, c, true)) {
+					if (box_overlap<!QTET>(qb, pl, a, b, c, true)) {
 						leafL = cl < 0;
 						pushL = !leafL;
 					}
-					if (box_overlap(qb, a, b, c, false)) {
+					if (box_overlap<!QTET>(qb, pl, a, b, c, false)) {
 						leafR = cr < 0;
 						pushR = !leafR;
 					}
