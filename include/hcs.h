@@ -176,6 +176,9 @@ int hcs_geom_info(const hcs_ctx *ctx, int geom, int info[3]);
 /* copies the device-resident mesh back: verts[nv*3], elems[ne*(4|3)], and for soft geoms
  * pressure[nv], grad[ne*3], e0[ne]; for rigid geoms grad receives the unit face normals */
 int hcs_get_mesh(hcs_ctx *ctx, int geom, double *verts, int32_t *elems, double *pressure, double *grad, double *e0);
+/* LBVH of a soft geom as resident on the GPU: 64-byte records {float llo[3], lhi[3], rlo[3], rhi[3]; int32 left,
+ * right; float pad[2]} (child >= 0: internal node, < 0: tet ~child); returns the node count (n_tets - 1, min 1) */
+int hcs_get_lbvh(hcs_ctx *ctx, int geom, void *out_nodes, int max_nodes);
 /* counters of the last step: {candidate pair-evals, polygons, faces, tactile triangles, kernels launched} */
 int hcs_get_counters(hcs_ctx *ctx, int64_t out[5]);
 /* per-stage GPU time of the last step in ms (CUDA events on the context stream); needs hcs_set_profiling(1):

@@ -14,7 +14,8 @@ CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libhcs_b200.so")
 OBJ = os.path.join(CSRC, "_build")
 
-SOURCES = ["engine.cu", "kernels_build.cu", "kernels_step.cu", "kernels_broadphase.cu", "kernels_tactile.cu", "mesh_host.cpp"]
+SOURCES = ["engine.cu", "kernels_build.cu", "kernels_step.cu", "kernels_broadphase.cu", "kernels_tactile.cu", "kernels_lbvh.cu",
+           "mesh_host.cpp"]
 
 NVCC = os.environ.get("HCS_NVCC", "/usr/local/cuda/bin/nvcc")
 NVCC_FLAGS = [

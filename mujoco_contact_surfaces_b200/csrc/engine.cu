@@ -7,6 +7,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <stdexcept>
@@ -280,14 +281,37 @@ static void upload_geom(hcs_ctx *c, GeomHost &g)
 			                   c->stream));
 			d.tet_geom  = dalloc<TetGeom>(g.allocs, d.n_elems);
 			d.tet_field = dalloc<TetField>(g.allocs, d.n_elems);
-			std::vector<BvhNode> nodes = build_lbvh(m);
-			d.nodes                     = dalloc<BvhNode>(g.allocs, nodes.size());
-			CK(cudaMemcpyAsync(d.nodes, nodes.data(), nodes.size() * sizeof(BvhNode), cudaMemcpyHostToDevice, c->stream));
-			for (int a = 0; a < 3; ++a) {
-				d.root_lo[a] = std::min(nodes[0].llo[a], nodes[0].rlo[a]);
-				d.root_hi[a] = std::max(nodes[0].lhi[a], nodes[0].rhi[a]);
+			d.nodes = dalloc<BvhNode>(g.allocs, std::max(1, d.n_elems - 1));
+			BvhNode root;
+			if (d.n_elems < 2 || std::getenv("HCS_LBVH_HOST")) { // host builder: single-tet trees and cross-checks
+				std::vector<BvhNode> nodes = build_lbvh(m);
+				CK(cudaMemcpyAsync(d.nodes, nodes.data(), nodes.size() * sizeof(BvhNode), cudaMemcpyHostToDevice, c->stream));
+				CK(cudaStreamSynchronize(c->stream)); // `nodes` is a local
+				root = nodes[0];
+			} else { // K2: Morton codes, sort, Karras tree and refit on the GPU
+				double glo[3] = { 1e300, 1e300, 1e300 }, ghi[3] = { -1e300, -1e300, -1e300 };
+				for (int t = 0; t < d.n_elems; ++t) { // centroid bounds fix the Morton quantisation grid
+					double cc[3] = { 0, 0, 0 };
+					for (int k = 0; k < 4; ++k)
+						for (int a = 0; a < 3; ++a)
+							cc[a] += 0.25 * m.verts[3 * (size_t)m.elems[4 * (size_t)t + k] + a];
+					for (int a = 0; a < 3; ++a) {
+						glo[a] = std::min(glo[a], cc[a]);
+						ghi[a] = std::max(ghi[a], cc[a]);
+					}
+				}
+				void *scratch = nullptr;
+				CK(cudaMalloc(&scratch, lbvh_scratch_bytes(d.n_elems)));
+				launch_build_lbvh(d, glo, ghi, scratch, c->stream);
+				CK(cudaMemcpyAsync(&root, d.nodes, sizeof(BvhNode), cudaMemcpyDeviceToHost, c->stream));
+				CK(cudaStreamSynchronize(c->stream));
+				CK(cudaGetLastError());
+				cudaFree(scratch);
 			}
-			CK(cudaStreamSynchronize(c->stream)); // `nodes` is a local
+			for (int a = 0; a < 3; ++a) {
+				d.root_lo[a] = std::min(root.llo[a], root.rlo[a]);
+				d.root_hi[a] = std::max(root.lhi[a], root.rhi[a]);
+			}
 			launch_build_tets(d, c->stream);
 		} else {
 			d.tris = dalloc<TriRec>(g.allocs, d.n_elems);
@@ -1127,6 +1151,24 @@ int hcs_get_mesh(hcs_ctx *c, int geom, double *verts, int32_t *elems, double *pr
 	}
 	CK(cudaStreamSynchronize(s));
 	return HCS_OK;
+	API_END(c)
+}
+
+int hcs_get_lbvh(hcs_ctx *c, int geom, void *out_nodes, int max_nodes)
+{
+	API_BEGIN(c)
+	if (!c->finalized || geom < 0 || geom >= (int)c->geoms.size() || c->geoms[geom].dev.kind != 1) {
+		c->err = "hcs_get_lbvh: needs a finalized context and a soft geom";
+		return HCS_E_INVALID;
+	}
+	const GeomDev &d = c->geoms[geom].dev;
+	int n            = std::max(1, d.n_elems - 1);
+	if (out_nodes && max_nodes > 0) {
+		CK(cudaMemcpyAsync(out_nodes, d.nodes, (size_t)std::min(n, max_nodes) * sizeof(BvhNode), cudaMemcpyDeviceToHost,
+		                   c->stream));
+		CK(cudaStreamSynchronize(c->stream));
+	}
+	return n;
 	API_END(c)
 }
 

@@ -118,6 +118,9 @@ struct SensorDev {
 // ---- launchers (definitions in the .cu files) ---------------------------------------------------
 void launch_build_tets(const GeomDev &g, cudaStream_t s);
 void launch_build_tris(const GeomDev &g, cudaStream_t s);
+// K2: LBVH of a soft geom on the GPU (g.nodes receives n_elems-1 records); glo/ghi = centroid bounds
+size_t lbvh_scratch_bytes(int n);
+void launch_build_lbvh(const GeomDev &g, const double glo[3], const double ghi[3], void *scratch, cudaStream_t s);
 
 void launch_broadphase(const PairDesc &P, const StepIO &io, cudaStream_t s);
 void launch_narrowphase(const PairDesc &P, const StepIO &io, cudaStream_t s);

@@ -40,7 +40,7 @@ ABI_SYMBOLS = [
     "hcs_step_device", "hcs_sync", "hcs_fetch_results", "hcs_n_geoms", "hcs_n_pairs", "hcs_get_pair_results",
     "hcs_get_geom_wrenches", "hcs_get_sensor_image", "hcs_device_pair_results", "hcs_device_geom_wrenches",
     "hcs_device_sensor_image", "hcs_get_faces", "hcs_get_emitted", "hcs_get_tactile_triangles", "hcs_geom_info",
-    "hcs_get_mesh", "hcs_get_counters", "hcs_set_profiling", "hcs_get_stage_ms", "hcs_version",
+    "hcs_get_mesh", "hcs_get_lbvh", "hcs_get_counters", "hcs_set_profiling", "hcs_get_stage_ms", "hcs_version",
 ]
 
 _LIB = None
@@ -239,6 +239,15 @@ class HydroelasticEngine:
             out.update(pressure=pressure, grad=grad, e0=e0)
         else:
             out.update(normal=grad)
+        return out
+
+    def lbvh(self, geom):
+        """The soft geom's GPU-resident LBVH as a structured array of 64-byte nodes."""
+        dt = np.dtype([("llo", "<f4", 3), ("lhi", "<f4", 3), ("rlo", "<f4", 3), ("rhi", "<f4", 3), ("left", "<i4"),
+                       ("right", "<i4"), ("pad", "<f4", 2)])
+        n = self._check(self.L.hcs_get_lbvh(self.h, int(geom), None, 0))
+        out = np.zeros(n, dtype=dt)
+        self._check(self.L.hcs_get_lbvh(self.h, int(geom), out.ctypes.data_as(C.c_void_p), n))
         return out
 
     def counters(self):

@@ -54,6 +54,34 @@ def test_meshes_match_oracle_bit_exact(hcs_lib):
         eng.close()
 
 
+def test_gpu_lbvh_build_equals_host_builder(hcs_lib, monkeypatch):
+    """K2: Morton sort + Karras tree + atomic refit on the GPU give the same 64-byte node records as the host
+    cross-check builder, and every tet is reachable exactly once with a box that contains it."""
+    scene = scenes.mixed_shapes()
+    scene.geoms.append(scenes.Geom("ell_fine", scenes.GEOM_ELLIPSOID, [0.05, 0.04, 0.03], [5e4, 5.0, 0.004, 0.3, 0.3]))
+    gpu = make_engine(scene, 1)
+    monkeypatch.setenv("HCS_LBVH_HOST", "1")
+    host = make_engine(scene, 1)
+    monkeypatch.delenv("HCS_LBVH_HOST")
+    checked = 0
+    for g in range(scene.n_geoms):
+        m = gpu.geom_mesh(g)
+        if m["kind"] != 1:
+            continue
+        a, b = gpu.lbvh(g), host.lbvh(g)
+        assert a.tobytes() == b.tobytes(), "LBVH of geom %d differs between GPU and host builders" % g
+        ntet = len(m["elems"])
+        leaves = np.concatenate([a["left"][a["left"] < 0], a["right"][a["right"] < 0]])
+        assert sorted((~leaves).tolist()) == list(range(ntet))
+        for side, lo, hi in (("left", "llo", "lhi"), ("right", "rlo", "rhi")):
+            sel = a[side] < 0
+            tv = m["verts"][m["elems"][~a[side][sel]]]
+            assert (tv.min(1) >= a[lo][sel] - 1e-12).all() and (tv.max(1) <= a[hi][sel] + 1e-12).all()
+        checked += 1
+    assert checked >= 5
+    gpu.close(), host.close()
+
+
 def test_c1_sphere_on_box_random_orientation(hcs_lib):
     worst = _run_scene(scenes.sphere_on_box(), 128, seed=1234, hcs_lib=hcs_lib)
     assert worst < 1e-8
