@@ -11,8 +11,11 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-OUT = os.path.join(HERE, "libhcs_b200.so")
-OBJ = os.path.join(CSRC, "_build")
+# tuning sweeps: HCS_VARIANT=name HCS_NVCC_DEFS="-DBP_CTAS_PER_SM=5 ..." builds variants/libhcs_b200.<name>.so,
+# which HCS_LIB=<path> makes engine.py load instead of the in-tree library
+VARIANT = os.environ.get("HCS_VARIANT", "")
+OUT = os.path.join(HERE, "variants", "libhcs_b200.%s.so" % VARIANT) if VARIANT else os.path.join(HERE, "libhcs_b200.so")
+OBJ = os.path.join(CSRC, "_build" + ("_" + VARIANT if VARIANT else ""))
 
 SOURCES = ["engine.cu", "kernels_build.cu", "kernels_step.cu", "kernels_broadphase.cu", "kernels_tactile.cu", "kernels_lbvh.cu",
            "mesh_host.cpp"]
@@ -21,7 +24,7 @@ NVCC = os.environ.get("HCS_NVCC", "/usr/local/cuda/bin/nvcc")
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-fmad=false",
     "-ccbin", "g++", "-Xcompiler", "-fPIC,-ffp-contract=off,-fno-fast-math,-O2", "-Xptxas", "-v",
-]
+] + os.environ.get("HCS_NVCC_DEFS", "").split()
 
 
 def _deps():
@@ -50,6 +53,7 @@ def _compile(src):
 
 def build(verbose=False, force=False):
     os.makedirs(OBJ, exist_ok=True)
+    os.makedirs(os.path.dirname(OUT), exist_ok=True)
     if force:
         for f in os.listdir(OBJ):
             os.remove(os.path.join(OBJ, f))

@@ -71,6 +71,8 @@ struct hcs_ctx {
 	std::vector<SensorHost> sensors;
 	std::vector<void *> step_allocs;
 	PairDesc *d_pairs = nullptr;
+	int32_t *d_counters = nullptr; // zeroed by ONE memset per step: flags[4], face count, tactile triangle count,
+	size_t n_counters   = 0;       // then {flat-list length, next chunk} per pair
 	StepIO io{};
 	double *d_xpos = nullptr, *d_xmat = nullptr, *d_vel = nullptr; // staging for the host entry point
 	hcs_pair_result *h_pair = nullptr;                             // pinned mirrors
@@ -412,6 +414,16 @@ static void build_pairs(hcs_ctx *c)
 				CK(cudaMemsetAsync(P.slab_evals, 0, units * sizeof(int32_t), c->stream));
 				P.slab_nverts = dalloc<uint8_t>(c->step_allocs, units * cap);
 				CK(cudaMemsetAsync(P.slab_count, 0, units * sizeof(int32_t), c->stream));
+				// flat narrowphase: offsets, work counter, per-env context blocks, per-candidate contributions
+				const char *mt_env = getenv("HCS_MAX_TOTAL_CANDIDATES");
+				long max_total     = mt_env ? atol(mt_env) : (32L << 20);
+				P.contrib_cap      = (int)std::max<long>(32, std::min<long>((long)units * cap, max_total));
+				P.slab_offset      = dalloc<int32_t>(c->step_allocs, units);
+				P.flat             = dalloc<uint4>(c->step_allocs, (size_t)P.contrib_cap);
+				P.counters         = c->d_counters + 6 + 3 * pi;
+				P.pair_ctx         = dalloc<double>(c->step_allocs, (size_t)n_env * PAIR_CTX_DOUBLES);
+				P.contrib          = dalloc<double>(c->step_allocs, (size_t)10 * P.contrib_cap);
+				CK(cudaMemsetAsync(P.slab_offset, 0, units * sizeof(int32_t), c->stream));
 			}
 		}
 		c->pair_desc.push_back(P);
@@ -503,15 +515,19 @@ static void finalize(hcs_ctx *c)
 		upload_geom(c, g);
 	for (SensorHost &s : c->sensors)
 		build_sensor(c, s);
+	c->n_counters = 6 + 3 * (size_t)np;
+	c->d_counters = dalloc<int32_t>(c->step_allocs, c->n_counters);
+	CK(cudaMemsetAsync(c->d_counters, 0, c->n_counters * sizeof(int32_t), c->stream));
 	build_pairs(c);
 	StepIO io{};
 	io.n_env = n_env, io.n_geoms = ng, io.n_pairs = np;
+	CK(cudaDeviceGetAttribute(&io.n_sms, cudaDevAttrMultiProcessorCount, c->cfg.device));
 	io.representation = c->cfg.representation;
 	io.apply_forces   = c->cfg.apply_contact_forces;
-	io.flags          = dalloc<int32_t>(c->step_allocs, 4);
+	io.flags          = c->d_counters;
 	io.max_faces      = std::max(0, c->cfg.max_faces);
 	io.faces          = dalloc<hcs_face>(c->step_allocs, io.max_faces);
-	io.face_count     = dalloc<int32_t>(c->step_allocs, 1);
+	io.face_count     = c->d_counters + 4;
 	bool tactile      = false;
 	for (const PairDesc &P : c->pair_desc)
 		tactile |= P.emit_tactile != 0;
@@ -532,12 +548,9 @@ static void finalize(hcs_ctx *c)
 		sh.dev.bin_items = dalloc<int32_t>(c->step_allocs, cap);
 	}
 	io.tri_pool    = dalloc<TactileTri>(c->step_allocs, io.max_tris);
-	io.tri_count   = dalloc<int32_t>(c->step_allocs, 1);
+	io.tri_count   = c->d_counters + 5;
 	io.pair_out    = dalloc<hcs_pair_result>(c->step_allocs, (size_t)n_env * np);
 	io.geom_wrench = dalloc<double>(c->step_allocs, (size_t)n_env * ng * 6);
-	CK(cudaMemsetAsync(io.flags, 0, 4 * sizeof(int32_t), c->stream));
-	CK(cudaMemsetAsync(io.face_count, 0, sizeof(int32_t), c->stream));
-	CK(cudaMemsetAsync(io.tri_count, 0, sizeof(int32_t), c->stream));
 	CK(cudaMemsetAsync(io.pair_out, 0, (size_t)n_env * np * sizeof(hcs_pair_result), c->stream));
 	CK(cudaMemsetAsync(io.geom_wrench, 0, (size_t)n_env * ng * 6 * sizeof(double), c->stream));
 	c->d_xpos = dalloc<double>(c->step_allocs, (size_t)n_env * ng * 3);
@@ -561,17 +574,15 @@ static void step_device(hcs_ctx *c, const double *xpos, const double *xmat, cons
 	bool prof      = c->profiling;
 	if (prof)
 		CK(cudaEventRecord(c->ev[0], s));
-	CK(cudaMemsetAsync(io.flags, 0, 4 * sizeof(int32_t), s));
-	if (io.max_faces > 0)
-		CK(cudaMemsetAsync(io.face_count, 0, sizeof(int32_t), s));
-	if (io.max_tris > 0)
-		CK(cudaMemsetAsync(io.tri_count, 0, sizeof(int32_t), s));
+	CK(cudaMemsetAsync(c->d_counters, 0, c->n_counters * sizeof(int32_t), s)); // flags, pool counts, flat-list counters
 	if (prof)
 		CK(cudaEventRecord(c->ev[1], s));
+	int list_slices = 0; // most slices among the candidate-list pairs
 	for (const PairDesc &P : c->pair_desc)
 		if (P.kind == PAIR_SOFT_RIGID || P.kind == PAIR_SOFT_SOFT) {
 			launch_broadphase(P, io, s);
 			++k;
+			list_slices = std::max(list_slices, P.n_slices);
 		}
 	if (prof)
 		CK(cudaEventRecord(c->ev[2], s));
@@ -582,7 +593,7 @@ static void step_device(hcs_ctx *c, const double *xpos, const double *xmat, cons
 		}
 	if (prof)
 		CK(cudaEventRecord(c->ev[3], s));
-	launch_finalize(c->d_pairs, io, s);
+	launch_finalize(c->d_pairs, io, list_slices, s);
 	k += 1;
 	if (prof)
 		CK(cudaEventRecord(c->ev[4], s));
@@ -629,6 +640,10 @@ static int check_flags(hcs_ctx *c)
 	}
 	if (c->h_flags[0] & 4) {
 		c->err = "tactile bin overflow: raise hcs_config.max_triangles_per_taxel (average bin depth)";
+		return HCS_E_CAPACITY;
+	}
+	if (c->h_flags[0] & 8) {
+		c->err = "per-candidate contribution pool overflow: raise HCS_MAX_TOTAL_CANDIDATES (candidates per pair and step)";
 		return HCS_E_CAPACITY;
 	}
 	return HCS_OK;
@@ -1057,8 +1072,8 @@ int hcs_get_emitted(hcs_ctx *c, int env, int pair, int32_t *out, int cap)
 		CK(cudaMemcpyAsync(nv.data(), P.slab_nverts + off, cnt, cudaMemcpyDeviceToHost, c->stream));
 		CK(cudaStreamSynchronize(c->stream));
 		for (int i = 0; i < cnt; ++i)
-			if (nv[i] >= 3)
-				put((int)cand[i].y, (int)cand[i].x, nv[i]); // (tree element of A, query element of B)
+			if ((nv[i] & 15) >= 3) // the high nibble holds the polygon's force-point count
+				put((int)cand[i].y, (int)cand[i].x, nv[i] & 15); // (tree element of A, query element of B)
 	}
 	return n;
 	API_END(c)

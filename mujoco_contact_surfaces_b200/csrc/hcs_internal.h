@@ -80,12 +80,27 @@ struct PairDesc {
 	uint2 *slab;           // [n_env * n_slices][cap] candidates (query, tree element)
 	int32_t *slab_count;   // [n_env * n_slices] candidates that survived the early-outs (need clipping)
 	int32_t *slab_evals;   // [n_env * n_slices] LBVH leaf hits = pair-evals started in the broadphase
-	uint8_t *slab_nverts;  // [n_env * n_slices][cap] polygon vertex count per candidate (plane: per tet)
+	uint8_t *slab_nverts;  // [n_env * n_slices][cap] polygon vertex count per candidate (plane: per tet); candidate
+	                       // lists keep the number of force points of the polygon in the high nibble
 	SlicePartial *partial; // [n_env * n_slices]
+	// flat narrowphase over the candidates of ALL (env, slice) units of the pair
+	int32_t *slab_offset;  // [n_env * n_slices] start of the unit's range in the flat list (reserved by the broadphase)
+	uint4 *flat;           // [contrib_cap] (query element, tree element, unit, index inside the unit)
+	int32_t *counters;     // [0] candidates in the flat list, [1] next 32-candidate chunk of the narrowphase,
+	                       // [2] next (env, slice) unit of the broadphase; zeroed per step
+	double *pair_ctx;      // [n_env][PAIR_CTX_DOUBLES] poses, velocities, X_AB written by the broadphase
+	double *contrib;       // [10][contrib_cap] per-candidate F, tau, area, area*centroid, candidate-major (SoA)
+	int contrib_cap;
 };
+
+constexpr int PAIR_CTX_DOUBLES = 48;
+// layout of one context block: R_WA[9] xA[3] wA[3] vA[3] xB[3] wB[3] vB[3] R_AB[9] p_AB[3] p_BAo[3]
+constexpr int CTX_XA = 9, CTX_WA = 12, CTX_VA = 15, CTX_XB = 18, CTX_WB = 21, CTX_VB = 24, CTX_RAB = 27, CTX_PAB = 36,
+              CTX_PBA = 39;
 
 struct StepIO {
 	int n_env, n_geoms, n_pairs;
+	int n_sms; // SMs of the device: persistent grids are sized in multiples of it
 	const double *xpos, *xmat, *vel;
 	int representation, apply_forces;
 	int32_t *flags;          // [0] capacity overflow bits, [1] traversal stack overflow
@@ -124,7 +139,7 @@ void launch_build_lbvh(const GeomDev &g, const double glo[3], const double ghi[3
 
 void launch_broadphase(const PairDesc &P, const StepIO &io, cudaStream_t s);
 void launch_narrowphase(const PairDesc &P, const StepIO &io, cudaStream_t s);
-void launch_finalize(const PairDesc *d_pairs, const StepIO &io, cudaStream_t s);
+void launch_finalize(const PairDesc *d_pairs, const StepIO &io, int max_list_slices, cudaStream_t s);
 
 // clear, count, scan, fill, rasterise; returns the number of kernels launched
 int launch_tactile(const SensorDev &sd, const StepIO &io, const PairDesc *d_pairs, cudaStream_t s);

@@ -12,20 +12,32 @@
 // in shared memory:  node items (query, internal node) and leaf items (query, tet).  Every iteration all
 // lanes pop one item each; children / survivors are appended with warp-ballot + popc prefix sums, which
 // also makes the emitted candidate order deterministic (no atomics anywhere).
+#include <algorithm>
+
 #include "dmath.cuh"
 #include "hcs_internal.h"
 
 namespace hcs {
 
 #define FULL_MASK 0xffffffffu
+#ifndef HCS_BP_CTAS_PER_SM // tuning sweeps (build.py HCS_NVCC_DEFS); 4 -> 127 registers, 6 -> 80 registers + spills
+#define HCS_BP_CTAS_PER_SM 4
+#endif
+#ifndef HCS_BP_PERSISTENT
+#define HCS_BP_PERSISTENT 1
+#endif
+constexpr int BP_CTAS_PER_SM = HCS_BP_CTAS_PER_SM;
 constexpr int BP_WARPS = 4;
 constexpr int BP_BLOCK = 32 * BP_WARPS;
 constexpr int NODE_Q   = 768; // LIFO of (query slot, node); grows by <= 32 per iteration
 constexpr int LEAF_Q   = 128; // (query slot, tet); drained in batches of 32
 
+constexpr int ITEM_SHIFT = 27; // queue item = query slot (5 bits) << 27 | node or tet index (27 bits)
+constexpr unsigned ITEM_MASK = (1u << ITEM_SHIFT) - 1u;
+
 struct __align__(16) WarpQueues {
-	uint2 nodeq[NODE_Q];
-	uint2 leafq[LEAF_Q];
+	unsigned nodeq[NODE_Q];
+	unsigned leafq[LEAF_Q];
 	double qv[12][32];  // transformed query vertices (tri: 9 + rotated normal 3; tet: 12), lane-interleaved
 	float qbox[6][32];
 	float qpl[4][32]; // soft-rigid: the query triangle's plane (unit normal, offset) in A's frame
@@ -56,14 +68,8 @@ __device__ __forceinline__ bool box_overlap(const float *q, const float *pl, flo
 
 // QTET: query elements are tets of B (soft-soft), otherwise triangles of B (soft-rigid)
 template <bool QTET>
-__global__ void __launch_bounds__(BP_BLOCK) broadphase_kernel(PairDesc P, StepIO io)
+__device__ __forceinline__ void broadphase_unit(const PairDesc &P, const StepIO &io, WarpQueues &W, int warp, int lane)
 {
-	__shared__ WarpQueues sm[BP_WARPS];
-	int warp = (blockIdx.x * BP_BLOCK + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-	int n_units = io.n_env * P.n_slices;
-	if (warp >= n_units)
-		return;
-	WarpQueues &W = sm[threadIdx.x >> 5];
 	int env = warp / P.n_slices, slice = warp - env * P.n_slices;
 	Xform X_WA = load_pose(io.xpos, io.xmat, io.n_geoms, env, P.gA);
 	Xform X_WB = load_pose(io.xpos, io.xmat, io.n_geoms, env, P.gB);
@@ -82,6 +88,25 @@ __global__ void __launch_bounds__(BP_BLOCK) broadphase_kernel(PairDesc P, StepIO
 	}
 	Xform X_AB  = invert_and_compose(X_WA, X_WB);
 	D3 p_BAo    = -rotT(X_AB.R, X_AB.p); // origin of A expressed in B (p_NMo of field_intersection.cc)
+	if (slice == 0 && lane == 0) { // per (env, pair) context block read by the flat narrowphase
+		double *cb = P.pair_ctx + (size_t)env * PAIR_CTX_DOUBLES;
+		const double *velA = io.vel + ((size_t)env * io.n_geoms + P.gA) * 6;
+		const double *velB = io.vel + ((size_t)env * io.n_geoms + P.gB) * 6;
+#pragma unroll
+		for (int i = 0; i < 9; ++i) {
+			cb[i]           = X_WA.R[i];
+			cb[CTX_RAB + i] = X_AB.R[i];
+		}
+#pragma unroll
+		for (int i = 0; i < 3; ++i) {
+			cb[CTX_WA + i] = velA[i], cb[CTX_VA + i] = velA[3 + i];
+			cb[CTX_WB + i] = velB[i], cb[CTX_VB + i] = velB[3 + i];
+		}
+		cb[CTX_XA] = X_WA.p.x, cb[CTX_XA + 1] = X_WA.p.y, cb[CTX_XA + 2] = X_WA.p.z;
+		cb[CTX_XB] = X_WB.p.x, cb[CTX_XB + 1] = X_WB.p.y, cb[CTX_XB + 2] = X_WB.p.z;
+		cb[CTX_PAB] = X_AB.p.x, cb[CTX_PAB + 1] = X_AB.p.y, cb[CTX_PAB + 2] = X_AB.p.z;
+		cb[CTX_PBA] = p_BAo.x, cb[CTX_PBA + 1] = p_BAo.y, cb[CTX_PBA + 2] = p_BAo.z;
+	}
 	uint2 *slab = P.slab + (size_t)warp * P.cap;
 	int count = 0, evals = 0; // warp-uniform
 	int q_begin = slice * P.slice_q, q_end = min(P.nq, q_begin + P.slice_q);
@@ -135,7 +160,7 @@ __global__ void __launch_bounds__(BP_BLOCK) broadphase_kernel(PairDesc P, StepIO
 				W.qpl[3][slot] = (float)(v[9] * v[0] + v[10] * v[1] + v[11] * v[2]);
 			}
 			W.qid[slot]   = q;
-			W.nodeq[slot] = make_uint2((unsigned)slot, 0u);
+			W.nodeq[slot] = (unsigned)slot << ITEM_SHIFT; // (slot, root)
 		}
 		__syncwarp();
 		int n_node = n_alive, n_leaf = 0;
@@ -148,8 +173,9 @@ __global__ void __launch_bounds__(BP_BLOCK) broadphase_kernel(PairDesc P, StepIO
 				bool keep = false;
 				uint2 it  = make_uint2(0, 0);
 				if (lane < k) {
-					it   = W.leafq[n_leaf - k + lane];
-					keep = true;
+					unsigned raw = W.leafq[n_leaf - k + lane];
+					it           = make_uint2(raw >> ITEM_SHIFT, raw & ITEM_MASK);
+					keep         = true;
 					if (!QTET) {
 						const TetField &tf = P.A.tet_field[it.y];
 						int s  = (int)it.x;
@@ -229,8 +255,9 @@ __global__ void __launch_bounds__(BP_BLOCK) broadphase_kernel(PairDesc P, StepIO
 				int cl = 0, cr = 0;
 				unsigned s = 0;
 				if (lane < k) {
-					uint2 it = W.nodeq[n_node - k + lane];
-					s        = it.x;
+					unsigned raw = W.nodeq[n_node - k + lane];
+					uint2 it     = make_uint2(raw >> ITEM_SHIFT, raw & ITEM_MASK);
+					s            = it.x;
 					float qb[6];
 #pragma unroll
 					for (int a = 0; a < 6; ++a)
@@ -266,27 +293,70 @@ __global__ void __launch_bounds__(BP_BLOCK) broadphase_kernel(PairDesc P, StepIO
 					break;
 				}
 				if (pushL)
-					W.nodeq[n_node + __popc(mL & lt_mask)] = make_uint2(s, (unsigned)cl);
+					W.nodeq[n_node + __popc(mL & lt_mask)] = (s << ITEM_SHIFT) | (unsigned)cl;
 				if (pushR)
-					W.nodeq[n_node + nL + __popc(mR & lt_mask)] = make_uint2(s, (unsigned)cr);
+					W.nodeq[n_node + nL + __popc(mR & lt_mask)] = (s << ITEM_SHIFT) | (unsigned)cr;
 				if (leafL)
-					W.leafq[n_leaf + __popc(lL & lt_mask)] = make_uint2(s, (unsigned)~cl);
+					W.leafq[n_leaf + __popc(lL & lt_mask)] = (s << ITEM_SHIFT) | (unsigned)~cl;
 				if (leafR)
-					W.leafq[n_leaf + nlL + __popc(lR & lt_mask)] = make_uint2(s, (unsigned)~cr);
+					W.leafq[n_leaf + nlL + __popc(lR & lt_mask)] = (s << ITEM_SHIFT) | (unsigned)~cr;
 				n_node += nL + nR;
 				n_leaf += nlL + nlR;
 				__syncwarp();
 			}
 		}
 	}
-	if (lane == 0) {
-		if (count > P.cap) {
+	if (count > P.cap) {
+		if (lane == 0)
 			atomicOr(io.flags, 1);
-			count = P.cap;
-		}
+		count = P.cap;
+	}
+	// Reserve a contiguous range of the pair's flat candidate list and publish (query, tet, unit, index) records:
+	// the flat narrowphase hands 32 consecutive records to a warp, whatever environments they belong to.  WHERE
+	// the range lands depends on the order in which warps finish; results do not (contributions are read back
+	// per unit, in index order).
+	int base = 0;
+	if (lane == 0) {
+		base               = count > 0 ? atomicAdd(P.counters, count) : 0;
 		P.slab_count[warp] = count;
 		P.slab_evals[warp] = evals;
+		P.slab_offset[warp] = base;
 	}
+	base = __shfl_sync(FULL_MASK, base, 0);
+	__syncwarp();
+	for (int i = lane; i < count; i += 32) {
+		if (base + i < P.contrib_cap) {
+			uint2 cd          = slab[i];
+			P.flat[base + i] = make_uint4(cd.x, cd.y, (unsigned)warp, (unsigned)i);
+		}
+	}
+}
+
+// Persistent warps: the resident CTAs of every SM pull (env, slice) units from a work counter, so the grid is
+// never a fractional number of waves and a slow unit does not hold three finished warps' resources.
+template <bool QTET>
+__global__ void __launch_bounds__(BP_BLOCK, BP_CTAS_PER_SM) broadphase_kernel(PairDesc P, StepIO io)
+{
+	__shared__ WarpQueues sm[BP_WARPS];
+	WarpQueues &W     = sm[threadIdx.x >> 5];
+	const int lane    = threadIdx.x & 31;
+	const int n_units = io.n_env * P.n_slices;
+#if HCS_BP_PERSISTENT
+	for (;;) {
+		int unit = 0;
+		if (lane == 0)
+			unit = atomicAdd(P.counters + 2, 1);
+		unit = __shfl_sync(FULL_MASK, unit, 0);
+		if (unit >= n_units)
+			break;
+		broadphase_unit<QTET>(P, io, W, unit, lane);
+		__syncwarp();
+	}
+#else
+	int unit = (blockIdx.x * BP_BLOCK + threadIdx.x) >> 5;
+	if (unit < n_units)
+		broadphase_unit<QTET>(P, io, W, unit, lane);
+#endif
 }
 
 void launch_broadphase(const PairDesc &P, const StepIO &io, cudaStream_t s)
@@ -295,6 +365,9 @@ void launch_broadphase(const PairDesc &P, const StepIO &io, cudaStream_t s)
 	if (units == 0)
 		return;
 	int grid = (int)((units + BP_WARPS - 1) / BP_WARPS);
+#if HCS_BP_PERSISTENT
+	grid = (int)std::min<long>(grid, (long)io.n_sms * BP_CTAS_PER_SM);
+#endif
 	if (P.kind == PAIR_SOFT_RIGID)
 		broadphase_kernel<false><<<grid, BP_BLOCK, 0, s>>>(P, io);
 	else if (P.kind == PAIR_SOFT_SOFT)

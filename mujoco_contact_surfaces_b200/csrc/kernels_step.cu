@@ -15,6 +15,8 @@
 // ~20k SASS instructions and stalled on instruction fetch (profiles/r01_notes.md).
 // The polygon vertex arithmetic follows the oracle's (= restated Drake) operation order exactly; the
 // quadrature uses the known unit normal instead of per-fan-triangle norms (differences ~1e-16 relative).
+#include <algorithm>
+
 #include "dmath.cuh"
 #include "hcs_internal.h"
 
@@ -30,7 +32,7 @@ template <int MV>
 struct WarpTile {
 	double xyz[2][MV][3][32];
 	double e[MV][32];
-	double ctx[40]; // WarpCtx block
+	double ctx[PAIR_CTX_DOUBLES]; // context block of the warp-per-slice plane kernel
 };
 
 // Explicit shared-window accesses: through a generic pointer stored in a struct the compiler emitted
@@ -67,46 +69,41 @@ __device__ __forceinline__ unsigned smem_addr(const void *p)
 	return (unsigned)(reinterpret_cast<const char *>(p) - reinterpret_cast<const char *>(smem_d));
 }
 
-// Warp-uniform per (env, pair) data.  The 39 doubles (poses, velocities, relative transform) live in SHARED
-// memory, not in registers: holding them in registers across the clip loop cost ~80 registers per thread and
-// capped the kernel at 3 warps per scheduler (profiles/r01_notes.md).  Uniform LDS reads are broadcasts.
-constexpr int CTX_DOUBLES = 40;
-struct WarpCtx {
-	unsigned a; // byte offset in smem_d of: R_WA[9], xA[3], wA[3], vA[3], xB[3], wB[3], vB[3], R_AB[9], p_AB[3]
+// Per (env, pair) data: poses, velocities, relative transform (PAIR_CTX_DOUBLES doubles, layout in
+// hcs_internal.h).  They are read on demand instead of being held in registers: holding them across the clip
+// loop cost ~80 registers per thread and capped the kernel at 3 warps per scheduler (profiles/r01_notes.md).
+//   GLOBAL = true : the block the broadphase wrote for the candidate's environment (flat narrowphase: the lanes of
+//                   a warp may belong to different environments; lanes of one environment read the same lines)
+//   GLOBAL = false: the warp's block in shared memory (warp-per-slice plane kernel; uniform LDS broadcasts)
+template <bool GLOBAL>
+struct PairCtx {
+	const double *g; // GLOBAL
+	unsigned a;      // !GLOBAL: byte offset of the block in smem_d
 	double dissipation, mu, sign;
 	int apply, env, pair;
-	__device__ __forceinline__ D3 v(int i) const
-	{
-		const double *p = smem_d + (a >> 3) + i;
-		return mk(p[0], p[1], p[2]);
-	}
-	__device__ __forceinline__ Xform X_WA() const // soft geom A (computation frame) -> world
+	__device__ __forceinline__ double ld(int i) const { return GLOBAL ? __ldg(g + i) : smem_d[(a >> 3) + i]; }
+	__device__ __forceinline__ D3 v(int i) const { return mk(ld(i), ld(i + 1), ld(i + 2)); }
+	__device__ __forceinline__ Xform xf(int r, int p) const
 	{
 		Xform X;
-		const double *p = smem_d + (a >> 3);
 #pragma unroll
 		for (int i = 0; i < 9; ++i)
-			X.R[i] = p[i];
-		X.p = mk(p[9], p[10], p[11]);
+			X.R[i] = ld(r + i);
+		X.p = v(p);
 		return X;
 	}
-	__device__ __forceinline__ Xform X_AB() const // geom B -> geom A
-	{
-		Xform X;
-		const double *p = smem_d + (a >> 3) + 27;
-#pragma unroll
-		for (int i = 0; i < 9; ++i)
-			X.R[i] = p[i];
-		X.p = mk(p[9], p[10], p[11]);
-		return X;
-	}
-	__device__ __forceinline__ D3 xA() const { return v(9); } // origin, angular, linear velocity of geom A (world)
-	__device__ __forceinline__ D3 wA() const { return v(12); }
-	__device__ __forceinline__ D3 vA() const { return v(15); }
-	__device__ __forceinline__ D3 xB() const { return v(18); }
-	__device__ __forceinline__ D3 wB() const { return v(21); }
-	__device__ __forceinline__ D3 vB() const { return v(24); }
+	__device__ __forceinline__ Xform X_WA() const { return xf(0, CTX_XA); }          // soft geom A -> world
+	__device__ __forceinline__ Xform X_AB() const { return xf(CTX_RAB, CTX_PAB); }   // geom B -> geom A
+	__device__ __forceinline__ D3 p_BAo() const { return v(CTX_PBA); }               // origin of A in B
+	__device__ __forceinline__ D3 xA() const { return v(CTX_XA); } // origin, angular, linear velocity (world)
+	__device__ __forceinline__ D3 wA() const { return v(CTX_WA); }
+	__device__ __forceinline__ D3 vA() const { return v(CTX_VA); }
+	__device__ __forceinline__ D3 xB() const { return v(CTX_XB); }
+	__device__ __forceinline__ D3 wB() const { return v(CTX_WB); }
+	__device__ __forceinline__ D3 vB() const { return v(CTX_VB); }
 };
+typedef PairCtx<false> WarpCtx;
+typedef PairCtx<true> CandCtx;
 
 struct Acc {
 	D3 F, tau, ac;
@@ -126,6 +123,7 @@ __device__ __forceinline__ void load_vel(const double *vel, int n_geoms, int env
 __device__ __forceinline__ WarpCtx make_ctx(const PairDesc &P, const StepIO &io, int env, double *block, int lane)
 {
 	WarpCtx c;
+	c.g = nullptr;
 	c.a = smem_addr(block);
 	if (lane == 0) {
 		Xform X_WA = load_pose(io.xpos, io.xmat, io.n_geoms, env, P.gA);
@@ -136,11 +134,11 @@ __device__ __forceinline__ WarpCtx make_ctx(const PairDesc &P, const StepIO &io,
 		load_vel(io.vel, io.n_geoms, env, P.gB, wB, vB);
 #pragma unroll
 		for (int i = 0; i < 9; ++i) {
-			block[i]      = X_WA.R[i];
-			block[27 + i] = X_AB.R[i];
+			block[i]           = X_WA.R[i];
+			block[CTX_RAB + i] = X_AB.R[i];
 		}
 		const D3 trip[7] = { X_WA.p, wA, vA, X_WB.p, wB, vB, X_AB.p };
-		const int off[7] = { 9, 12, 15, 18, 21, 24, 36 };
+		const int off[7] = { CTX_XA, CTX_WA, CTX_VA, CTX_XB, CTX_WB, CTX_VB, CTX_PAB };
 #pragma unroll
 		for (int k = 0; k < 7; ++k) {
 			block[off[k]]     = trip[k].x;
@@ -158,8 +156,24 @@ __device__ __forceinline__ WarpCtx make_ctx(const PairDesc &P, const StepIO &io,
 	return c;
 }
 
+// context of one candidate of the flat narrowphase: the block the broadphase wrote for its environment
+__device__ __forceinline__ CandCtx cand_ctx(const PairDesc &P, const StepIO &io, int env)
+{
+	CandCtx c;
+	c.g           = P.pair_ctx + (size_t)env * PAIR_CTX_DOUBLES;
+	c.a           = 0;
+	c.dissipation = P.dissipation;
+	c.mu          = P.mu;
+	c.sign        = P.sign;
+	c.apply       = io.apply_forces;
+	c.env         = env;
+	c.pair        = P.index;
+	return c;
+}
+
 // passiveCallback force law (plugin.cpp:440-475) for one quadrature point; A = M (unswapped labelling)
-__device__ __forceinline__ D3 face_force(D3 p, D3 n, double fn0, double k, const WarpCtx &c)
+template <class CTX>
+__device__ __forceinline__ D3 face_force(D3 p, D3 n, double fn0, double k, const CTX &c)
 {
 	D3 vAq    = c.vA() + cross(c.wA(), p - c.xA());
 	D3 vBq    = c.vB() + cross(c.wB(), p - c.xB());
@@ -244,19 +258,18 @@ __device__ __forceinline__ double pick4(const double *d, int i)
 }
 
 // optional per-face dump (PointCollision views for CPU sub-plugins); cold path, kept out of line
-__device__ __noinline__ void dump_face(const StepIO &io, const WarpCtx &c, D3 p, D3 n, double fn0, double k, D3 f,
-                                       int elemA, int elemB, int nverts, int face)
+__device__ __noinline__ void dump_face(const StepIO &io, double sg, double dissipation, int env, int pair, D3 p, D3 n,
+                                       double fn0, double k, D3 f, int elemA, int elemB, int nverts, int face)
 {
 	int slot = atomicAdd(io.face_count, 1);
 	if (slot >= io.max_faces)
 		return;
 	hcs_face &o = io.faces[slot];
-	double sg   = c.sign;
 	o.p[0] = p.x, o.p[1] = p.y, o.p[2] = p.z;
 	o.n[0] = sg * n.x, o.n[1] = sg * n.y, o.n[2] = sg * n.z;
-	o.fn0 = fn0, o.stiffness = k, o.damping = c.dissipation;
+	o.fn0 = fn0, o.stiffness = k, o.damping = dissipation;
 	o.f[0] = sg * f.x, o.f[1] = sg * f.y, o.f[2] = sg * f.z;
-	o.env = c.env, o.pair = c.pair;
+	o.env = env, o.pair = pair;
 	o.elemM  = sg > 0 ? elemA : elemB;
 	o.elemN  = sg > 0 ? elemB : elemA;
 	o.nverts = nverts, o.face = face;
@@ -267,9 +280,9 @@ __device__ __noinline__ void dump_face(const StepIO &io, const WarpCtx &c, D3 p,
 //   (unit, into A); e (shared tile): vertex pressures; grad: sampled-field gradient (builder frame);
 //   gN: -grad_N . nhat or +inf.  TRI selects kTriangle (centroid fan) vs kPolygon.
 //   Returns the polygon centroid (builder frame) and its pressure for the tactile emission.
-template <bool TRI, bool IDENT>
+template <bool TRI, bool IDENT, class CTX>
 __device__ __forceinline__ void integrate_polygon(Poly P, int n, D3 nhat, D3 grad, PressTile e, double gN,
-                                                  const WarpCtx &c, const StepIO &io, int elemA, int elemB, Acc &acc,
+                                                  const CTX &c, const StepIO &io, int elemA, int elemB, Acc &acc,
                                                   D3 &cen_out, double &ec_out)
 {
 	const double kInf = __longlong_as_double(0x7ff0000000000000LL);
@@ -322,7 +335,7 @@ __device__ __forceinline__ void integrate_polygon(Poly P, int n, D3 nhat, D3 gra
 			acc.tau    = acc.tau + cross(cW, f);
 			acc.n_points += 1;
 			if (io.max_faces > 0)
-				dump_face(io, c, cW, nf, fn0, k, f, elemA, elemB, n, 0);
+				dump_face(io, c.sign, c.dissipation, c.env, c.pair, cW, nf, fn0, k, f, elemA, elemB, n, 0);
 		}
 		return;
 	}
@@ -359,7 +372,7 @@ __device__ __forceinline__ void integrate_polygon(Poly P, int n, D3 nhat, D3 gra
 			acc.tau    = acc.tau + cross(fc, f);
 			acc.n_points += 1;
 			if (io.max_faces > 0)
-				dump_face(io, c, fc, nf, fn0, k, f, elemA, elemB, n, i);
+				dump_face(io, c.sign, c.dissipation, c.env, c.pair, fc, nf, fn0, k, f, elemA, elemB, n, i);
 		}
 		a = b, aW = bW, ea = eb;
 	}
@@ -367,8 +380,8 @@ __device__ __forceinline__ void integrate_polygon(Poly P, int n, D3 nhat, D3 gra
 
 // Warp-cooperative append of this lane's fan triangles to the tactile pool: exclusive scan over the lane
 // counts, ONE atomicAdd per warp.  World vertices are recomputed from the shared tile.
-template <bool IDENT>
-__device__ __forceinline__ void emit_tactile(int n_faces, Poly P, PressTile e, D3 cen, double ec, const WarpCtx &c,
+template <bool IDENT, class CTX>
+__device__ __forceinline__ void emit_tactile(int n_faces, Poly P, PressTile e, D3 cen, double ec, const CTX &c,
                                              const StepIO &io, int slot, int lane)
 {
 	int incl = n_faces;
@@ -465,39 +478,78 @@ __device__ __forceinline__ Acc zero_acc()
 // =================================================================================================
 // K4 soft-rigid narrowphase: one thread per (tet, triangle) candidate
 // =================================================================================================
+//
+// Flat over the candidates of the whole batch: the broadphase appended every (env, slice) unit's candidates to
+// one list per pair; a warp grabs the next chunk of 32 consecutive records from a work counter and each lane
+// reads its own environment's context block, so lane fill and load balance do not depend on how the candidates
+// are spread over the environments (warp-per-environment left 15 of 32 lanes and 47 % of the resident warps busy,
+// profiles/r01_notes.md).  Every candidate writes its own contribution (80 B), which K7 sums in an order that
+// depends only on the candidate's index inside its unit: results do not depend on the other environments of the
+// batch, on the grid size or on which warp processed the chunk.
+__device__ __forceinline__ int next_chunk(int32_t *counter, int lane)
+{
+	int chunk = 0;
+	if (lane == 0)
+		chunk = atomicAdd(counter, 1);
+	return __shfl_sync(FULL_MASK, chunk, 0);
+}
+
+// candidates in the flat list, clamped to the contribution pool (overflow is reported, not UB)
+__device__ __forceinline__ int flat_total(const PairDesc &P, const StepIO &io)
+{
+	int total = P.counters[0];
+	if (total > P.contrib_cap) {
+		if (blockIdx.x == 0 && threadIdx.x == 0)
+			atomicOr(io.flags, 8);
+		total = P.contrib_cap;
+	}
+	return total;
+}
+
+__device__ __forceinline__ void store_contrib(const PairDesc &P, int g, const Acc &acc)
+{
+	double *cp      = P.contrib + g;
+	const size_t st = (size_t)P.contrib_cap;
+	cp[0] = acc.F.x, cp[st] = acc.F.y, cp[2 * st] = acc.F.z;
+	cp[3 * st] = acc.tau.x, cp[4 * st] = acc.tau.y, cp[5 * st] = acc.tau.z;
+	cp[6 * st] = acc.area;
+	cp[7 * st] = acc.ac.x, cp[8 * st] = acc.ac.y, cp[9 * st] = acc.ac.z;
+}
+
 template <bool TRI>
 __global__ void __launch_bounds__(NP_BLOCK, 4) narrow_tet_tri_kernel(PairDesc P, StepIO io)
 {
-	int warp = (blockIdx.x * NP_BLOCK + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-	int n_units = io.n_env * P.n_slices;
-	if (warp >= n_units)
-		return;
-	int env = warp / P.n_slices;
-	int cnt = P.slab_count[warp];
-	if (cnt == 0) { // nothing to clip: most slices
-		if (lane == 0)
-			store_zero(P.partial + warp, P.slab_evals[warp]);
-		return;
-	}
+	const int lane = threadIdx.x & 31;
 	WarpTile<7> &T = reinterpret_cast<WarpTile<7> *>(smem_d)[threadIdx.x >> 5];
 	const unsigned buf0 = smem_addr(&T.xyz[0][0][0][lane]), buf_stride = (unsigned)sizeof(T.xyz[0]);
 	PressTile e{ smem_addr(&T.e[0][lane]) };
-	Acc acc     = zero_acc();
-	WarpCtx ctx = make_ctx(P, io, env, T.ctx, lane);
-	const uint2 *slab = P.slab + (size_t)warp * P.cap;
-	uint8_t *nvout    = P.slab_nverts + (size_t)warp * P.cap;
-	const double kInf = __longlong_as_double(0x7ff0000000000000LL);
+	const int total    = flat_total(P, io);
+	const int n_chunks = (total + 31) >> 5;
+	const double kInf  = __longlong_as_double(0x7ff0000000000000LL);
 #pragma unroll 1
-	for (int i0 = 0; i0 < cnt; i0 += 32) {
-		int i      = i0 + lane;
+	for (;;) {
+		int chunk = next_chunk(P.counters + 1, lane);
+		if (chunk >= n_chunks)
+			break;
+		int g      = chunk * 32 + lane;
 		int tfaces = 0;
 		int cur    = 0;
+		int slot   = 0;
 		D3 cen     = mk(0, 0, 0);
 		double ec  = 0;
-		if (i < cnt) {
-			uint2 cand = slab[i];
-			int tri = (int)cand.x, tet = (int)cand.y;
-			acc.n_clipped += 1;
+		int env    = 0;
+		size_t at  = 0; // position of the candidate in the slab: unit * cap + index inside the unit
+		uint4 rec  = make_uint4(0, 0, 0, 0);
+		if (g < total) {
+			rec   = P.flat[g];
+			env   = (int)rec.z / P.n_slices;
+			slot  = ((int)rec.z - env * P.n_slices) * P.cap + (int)rec.w;
+			at    = (size_t)rec.z * P.cap + rec.w;
+		}
+		CandCtx ctx = cand_ctx(P, io, env);
+		if (g < total) {
+			int tri = (int)rec.x, tet = (int)rec.y;
+			Acc acc = zero_acc();
 			const TetField &tf = P.A.tet_field[tet];
 			const TriRec &tr   = P.B.tris[tri];
 			// the normal/gradient cull and the trivial reject already ran in the broadphase
@@ -523,15 +575,13 @@ __global__ void __launch_bounds__(NP_BLOCK, 4) narrow_tet_tri_kernel(PairDesc P,
 					e.set(k, dot(grad, Poly{ buf0 + cur * buf_stride }.get(k)) + e0);
 				integrate_polygon<TRI, false>(Poly{ buf0 + cur * buf_stride }, n, nS, grad, e, kInf, ctx, io, tet, tri, acc, cen, ec);
 				tfaces = n;
+				store_contrib(P, g, acc);
 			}
-			nvout[i] = (uint8_t)nv;
+			P.slab_nverts[at] = (uint8_t)(nv | (acc.n_points << 4));
 		}
 		if (TRI && P.emit_tactile)
-			emit_tactile<false>(tfaces, Poly{ buf0 + cur * buf_stride }, e, cen, ec, ctx, io, (warp - env * P.n_slices) * P.cap + i, lane);
+			emit_tactile<false>(tfaces, Poly{ buf0 + cur * buf_stride }, e, cen, ec, ctx, io, slot, lane);
 	}
-	if (lane == 0)
-		acc.n_candidates = P.slab_evals[warp];
-	reduce_and_store(acc, P.partial + warp, lane);
 }
 
 // =================================================================================================
@@ -540,37 +590,38 @@ __global__ void __launch_bounds__(NP_BLOCK, 4) narrow_tet_tri_kernel(PairDesc P,
 template <bool TRI>
 __global__ void __launch_bounds__(NP_BLOCK, 3) narrow_tet_tet_kernel(PairDesc P, StepIO io)
 {
-	int warp = (blockIdx.x * NP_BLOCK + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-	int n_units = io.n_env * P.n_slices;
-	if (warp >= n_units)
-		return;
-	int env = warp / P.n_slices;
-	int cnt = P.slab_count[warp];
-	if (cnt == 0) {
-		if (lane == 0)
-			store_zero(P.partial + warp, P.slab_evals[warp]);
-		return;
-	}
+	const int lane = threadIdx.x & 31;
 	WarpTile<8> &T = reinterpret_cast<WarpTile<8> *>(smem_d)[threadIdx.x >> 5];
 	const unsigned buf0 = smem_addr(&T.xyz[0][0][0][lane]), buf_stride = (unsigned)sizeof(T.xyz[0]);
 	PressTile e{ smem_addr(&T.e[0][lane]) };
-	Acc acc     = zero_acc();
-	WarpCtx ctx = make_ctx(P, io, env, T.ctx, lane);
-	const Xform X_MN = ctx.X_AB();
-	D3 p_NMo   = -rotT(X_MN.R, X_MN.p);
-	const uint2 *slab = P.slab + (size_t)warp * P.cap;
-	uint8_t *nvout    = P.slab_nverts + (size_t)warp * P.cap;
+	const int total    = flat_total(P, io);
+	const int n_chunks = (total + 31) >> 5;
 #pragma unroll 1
-	for (int i0 = 0; i0 < cnt; i0 += 32) {
-		int i      = i0 + lane;
+	for (;;) { // flat over the candidates of the batch, see narrow_tet_tri_kernel
+		int chunk = next_chunk(P.counters + 1, lane);
+		if (chunk >= n_chunks)
+			break;
+		int g      = chunk * 32 + lane;
 		int tfaces = 0;
 		int cur    = 0;
+		int slot   = 0;
 		D3 cen     = mk(0, 0, 0);
 		double ec  = 0;
-		if (i < cnt) {
-			uint2 cand = slab[i];
-			int t1 = (int)cand.x, t0 = (int)cand.y;
-			acc.n_clipped += 1;
+		int env    = 0;
+		size_t at  = 0;
+		uint4 rec  = make_uint4(0, 0, 0, 0);
+		if (g < total) {
+			rec   = P.flat[g];
+			env   = (int)rec.z / P.n_slices;
+			slot  = ((int)rec.z - env * P.n_slices) * P.cap + (int)rec.w;
+			at    = (size_t)rec.z * P.cap + rec.w;
+		}
+		CandCtx ctx = cand_ctx(P, io, env);
+		if (g < total) {
+			int t1 = (int)rec.x, t0 = (int)rec.y;
+			Acc acc = zero_acc();
+			const Xform X_MN = ctx.X_AB();
+			D3 p_NMo         = ctx.p_BAo();
 			const TetField &f0 = P.A.tet_field[t0];
 			const TetField &f1 = P.B.tet_field[t1];
 			// CalcEquilibriumPlane
@@ -653,14 +704,59 @@ __global__ void __launch_bounds__(NP_BLOCK, 3) narrow_tet_tet_kernel(PairDesc P,
 				double gN = -dot(grad1_M, nhat);
 				integrate_polygon<TRI, false>(Poly{ buf0 + cur * buf_stride }, n, nhat, grad0, e, gN, ctx, io, t0, t1, acc, cen, ec);
 				tfaces = n;
+				store_contrib(P, g, acc);
 			}
-			nvout[i] = (uint8_t)nv;
+			P.slab_nverts[at] = (uint8_t)(nv | (acc.n_points << 4));
 		}
 		if (TRI && P.emit_tactile)
-			emit_tactile<false>(tfaces, Poly{ buf0 + cur * buf_stride }, e, cen, ec, ctx, io, (warp - env * P.n_slices) * P.cap + i, lane);
+			emit_tactile<false>(tfaces, Poly{ buf0 + cur * buf_stride }, e, cen, ec, ctx, io, slot, lane);
 	}
-	if (lane == 0)
-		acc.n_candidates = P.slab_evals[warp];
+}
+
+// =================================================================================================
+// K7 finalize, one CTA per environment.
+//   phase 1: per (env, slice) unit of a candidate-list pair, one warp sums the candidate contributions in a
+//            fixed order: lane l takes candidates l, l + 32, ... of the unit, then the xor-shuffle tree
+//   phase 2: one thread per pair adds the unit partials in slice order -> hcs_pair_result
+//   phase 3: one thread per geom adds its pairs' wrenches in pair order (replaces two mj_applyFT per face)
+// =================================================================================================
+__device__ __forceinline__ void reduce_unit(const PairDesc &P, const StepIO &io, int warp, int lane)
+{
+	// three independent loads in flight before anything depends on them
+	const int cnt = P.slab_count[warp], evals = P.slab_evals[warp], off = P.slab_offset[warp];
+	if (cnt == 0) { // nothing was clipped: most units
+		if (lane == 0)
+			store_zero(P.partial + warp, evals);
+		return;
+	}
+	const uint8_t *nv = P.slab_nverts + (size_t)warp * P.cap;
+	const size_t st   = (size_t)P.contrib_cap;
+	const bool tri    = io.representation == HCS_REP_TRIANGLE;
+	const int n_read  = min(cnt, P.contrib_cap - off);
+	Acc acc           = zero_acc();
+	for (int i = lane; i < n_read; i += 32) {
+		// the contribution is fetched together with the vertex count and discarded when the candidate produced
+		// no polygon (its slot was never written): one memory round trip per iteration instead of two
+		const double *cp = P.contrib + off + i;
+		int b            = nv[i];
+		D3 cF = mk(cp[0], cp[st], cp[2 * st]), cT = mk(cp[3 * st], cp[4 * st], cp[5 * st]);
+		double cA = cp[6 * st];
+		D3 cC     = mk(cp[7 * st], cp[8 * st], cp[9 * st]);
+		int n     = b & 15;
+		if (n >= 3) {
+			acc.n_polygons += 1;
+			acc.n_faces += tri ? n : 1;
+			acc.n_points += b >> 4;
+			acc.F   = acc.F + cF;
+			acc.tau = acc.tau + cT;
+			acc.area += cA;
+			acc.ac = acc.ac + cC;
+		}
+	}
+	if (lane == 0) {
+		acc.n_candidates = evals;
+		acc.n_clipped    = cnt;
+	}
 	reduce_and_store(acc, P.partial + warp, lane);
 }
 
@@ -779,25 +875,37 @@ __device__ __forceinline__ void finalize_pair(const PairDesc *pairs, const StepI
 	io.pair_out[idx] = r;
 }
 
-// K7: one thread per env reduces its pairs (slices in index order) and then its geoms
-__global__ void finalize_kernel(const PairDesc *pairs, StepIO io)
+// K7: one CTA per env (phases in the header comment above reduce_unit)
+__global__ void __launch_bounds__(128) finalize_kernel(const PairDesc *pairs, StepIO io)
 {
-	int env = blockIdx.x * blockDim.x + threadIdx.x;
-	if (env >= io.n_env)
-		return;
-	for (int p = 0; p < io.n_pairs; ++p)
-		finalize_pair(pairs, io, env, p);
-	double *w = io.geom_wrench + (size_t)env * io.n_geoms * 6;
-	for (int k = 0; k < io.n_geoms * 6; ++k)
-		w[k] = 0;
+	const int env = blockIdx.x, wid = threadIdx.x >> 5, lane = threadIdx.x & 31, n_warps = blockDim.x >> 5;
 	for (int p = 0; p < io.n_pairs; ++p) {
-		if (pairs[p].kind == PAIR_NONE)
+		const PairDesc &P = pairs[p];
+		if (P.kind != PAIR_SOFT_RIGID && P.kind != PAIR_SOFT_SOFT)
 			continue;
-		const hcs_pair_result &r = io.pair_out[(size_t)env * io.n_pairs + p];
-		for (int k = 0; k < 3; ++k) {
-			w[6 * r.gM + k] += r.F[k], w[6 * r.gM + 3 + k] += r.tau[k];
-			w[6 * r.gN + k] -= r.F[k], w[6 * r.gN + 3 + k] -= r.tau[k];
+		for (int s = wid; s < P.n_slices; s += n_warps)
+			reduce_unit(P, io, env * P.n_slices + s, lane);
+	}
+	__syncthreads(); // unit partials (global) are visible to the whole CTA
+	for (int p = threadIdx.x; p < io.n_pairs; p += blockDim.x)
+		finalize_pair(pairs, io, env, p);
+	__syncthreads();
+	for (int g = threadIdx.x; g < io.n_geoms; g += blockDim.x) {
+		double w[6] = { 0, 0, 0, 0, 0, 0 };
+		for (int p = 0; p < io.n_pairs; ++p) {
+			if (pairs[p].kind == PAIR_NONE)
+				continue;
+			const hcs_pair_result &r = io.pair_out[(size_t)env * io.n_pairs + p];
+			if (r.gM == g)
+				for (int k = 0; k < 3; ++k)
+					w[k] += r.F[k], w[3 + k] += r.tau[k];
+			if (r.gN == g)
+				for (int k = 0; k < 3; ++k)
+					w[k] -= r.F[k], w[3 + k] -= r.tau[k];
 		}
+		double *out = io.geom_wrench + ((size_t)env * io.n_geoms + g) * 6;
+		for (int k = 0; k < 6; ++k)
+			out[k] = w[k];
 	}
 }
 
@@ -820,18 +928,23 @@ void launch_narrowphase(const PairDesc &P, const StepIO &io, cudaStream_t s)
 		return;
 	int grid = (int)((units + NP_WARPS - 1) / NP_WARPS);
 	bool tri = io.representation == HCS_REP_TRIANGLE;
+	// flat kernels: resident CTAs of every SM pull chunks from the work counter; never more CTAs than chunks
+	long max_chunks = (std::min<long>(units * (long)P.cap, P.contrib_cap) + 31) / 32;
+	auto flat_grid  = [&](int ctas_per_sm) {
+		return (int)std::max<long>(1, std::min<long>((long)io.n_sms * ctas_per_sm, (max_chunks + NP_WARPS - 1) / NP_WARPS));
+	};
 	switch (P.kind) {
 		case PAIR_SOFT_RIGID:
 			if (tri)
-				launch_np<7>(narrow_tet_tri_kernel<true>, grid, P, io, s);
+				launch_np<7>(narrow_tet_tri_kernel<true>, flat_grid(4), P, io, s);
 			else
-				launch_np<7>(narrow_tet_tri_kernel<false>, grid, P, io, s);
+				launch_np<7>(narrow_tet_tri_kernel<false>, flat_grid(4), P, io, s);
 			break;
 		case PAIR_SOFT_SOFT:
 			if (tri)
-				launch_np<8>(narrow_tet_tet_kernel<true>, grid, P, io, s);
+				launch_np<8>(narrow_tet_tet_kernel<true>, flat_grid(3), P, io, s);
 			else
-				launch_np<8>(narrow_tet_tet_kernel<false>, grid, P, io, s);
+				launch_np<8>(narrow_tet_tet_kernel<false>, flat_grid(3), P, io, s);
 			break;
 		case PAIR_SOFT_PLANE:
 			if (tri)
@@ -844,10 +957,12 @@ void launch_narrowphase(const PairDesc &P, const StepIO &io, cudaStream_t s)
 	}
 }
 
-void launch_finalize(const PairDesc *d_pairs, const StepIO &io, cudaStream_t s)
+void launch_finalize(const PairDesc *d_pairs, const StepIO &io, int max_list_slices, cudaStream_t s)
 {
+	// one warp per slice of a candidate-list pair (up to 4), never fewer threads than pairs / geoms need
+	int warps = std::max(1, std::min(4, max_list_slices));
 	if (io.n_env > 0)
-		finalize_kernel<<<(io.n_env + 63) / 64, 64, 0, s>>>(d_pairs, io);
+		finalize_kernel<<<io.n_env, 32 * warps, 0, s>>>(d_pairs, io);
 }
 
 } // namespace hcs

@@ -10,7 +10,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libhcs_b200.so")
+LIB_PATH = os.environ.get("HCS_LIB") or os.path.join(_HERE, "libhcs_b200.so")  # HCS_LIB: tuning variants
 
 GEOM_PLANE, GEOM_HFIELD, GEOM_SPHERE, GEOM_CAPSULE, GEOM_ELLIPSOID, GEOM_CYLINDER, GEOM_BOX, GEOM_MESH = range(8)
 REP_POLYGON, REP_TRIANGLE = 0, 1
