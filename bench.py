@@ -200,8 +200,9 @@ def main():
     # a dedicated non-default stream shared by torch and the engine, so torch.cuda.Event times our kernels
     stream = torch.cuda.Stream(device=dev)
     torch.cuda.set_stream(stream)
-    eng =HydroelasticEngine(n_envs, representation=REP_TRIANGLE if scene.triangle else REP_POLYGON,
-                             apply_contact_forces=scene.apply_forces, device=local_rank, stream=stream.cuda_stream)
+    eng = HydroelasticEngine(n_envs, representation=REP_TRIANGLE if scene.triangle else REP_POLYGON,
+                             apply_contact_forces=scene.apply_forces, device=local_rank, stream=stream.cuda_stream,
+                             **scene.engine_kwargs(n_envs))
     S.configure(eng, scene)
     eng.finalize()
 

@@ -124,7 +124,8 @@ int hcs_set_pairs(hcs_ctx *ctx, const int32_t *g1, const int32_t *g2, int n_pair
 
 /* replaces FlatTactileSensor::load (SENS/src/flat_tactile_sensor.cpp:127-214): taxel grid
  * cx = floor(2*size[0]/resolution + 0.1), cy likewise, sampling_resolution^2 rays per taxel.
- * geom must be a box geom already added; returns the sensor index. */
+ * geom: a geom already added whose three size entries are positive (box, ellipsoid: the reference reads
+ * geom_size[0..2] of whatever geom carries the sensor, :192-197); returns the sensor index. */
 int hcs_add_flat_sensor(hcs_ctx *ctx, int geom, double resolution, int sampling_resolution, int window, float sigma);
 int hcs_sensor_dims(const hcs_ctx *ctx, int sensor, int *cx, int *cy);
 

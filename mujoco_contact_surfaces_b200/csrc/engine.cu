@@ -406,7 +406,9 @@ static void build_pairs(hcs_ctx *c)
 			} else {
 				long cap = c->cfg.max_candidates_per_slice > 0 ?
 				               c->cfg.max_candidates_per_slice :
-				               std::min<long>((long)P.slice_q * P.n_tree, std::max<long>(1024, 64L * P.slice_q));
+				               // a few coarse query elements can each overlap a large share of a fine tree
+				               std::min<long>((long)P.slice_q * P.n_tree,
+				                              std::max<long>(std::max<long>(1024, 64L * P.slice_q), P.n_tree / 4));
 				P.cap         = (int)cap;
 				P.slab        = dalloc<uint2>(c->step_allocs, units * cap);
 				P.slab_count  = dalloc<int32_t>(c->step_allocs, units);
@@ -577,12 +579,13 @@ static void step_device(hcs_ctx *c, const double *xpos, const double *xmat, cons
 	CK(cudaMemsetAsync(c->d_counters, 0, c->n_counters * sizeof(int32_t), s)); // flags, pool counts, flat-list counters
 	if (prof)
 		CK(cudaEventRecord(c->ev[1], s));
-	int list_slices = 0; // most slices among the candidate-list pairs
+	int list_slices = 0, list_units = 0; // most slices among the candidate-list pairs; their (pair, slice) units per env
 	for (const PairDesc &P : c->pair_desc)
 		if (P.kind == PAIR_SOFT_RIGID || P.kind == PAIR_SOFT_SOFT) {
 			launch_broadphase(P, io, s);
 			++k;
 			list_slices = std::max(list_slices, P.n_slices);
+			list_units += P.n_slices;
 		}
 	if (prof)
 		CK(cudaEventRecord(c->ev[2], s));
@@ -593,8 +596,7 @@ static void step_device(hcs_ctx *c, const double *xpos, const double *xmat, cons
 		}
 	if (prof)
 		CK(cudaEventRecord(c->ev[3], s));
-	launch_finalize(c->d_pairs, io, list_slices, s);
-	k += 1;
+	k += launch_finalize(c->d_pairs, io, list_slices, list_units, s);
 	if (prof)
 		CK(cudaEventRecord(c->ev[4], s));
 	if (with_sensors)
@@ -848,9 +850,13 @@ int hcs_set_pairs(hcs_ctx *c, const int32_t *g1, const int32_t *g2, int n_pairs)
 int hcs_add_flat_sensor(hcs_ctx *c, int geom, double resolution, int sampling_resolution, int window, float sigma)
 {
 	API_BEGIN(c)
-	if (geom < 0 || geom >= (int)c->geoms.size() || c->geoms[geom].mj_type != HCS_GEOM_BOX || !(resolution > 0) ||
-	    sampling_resolution < 1 || sampling_resolution > 32 || window < 0 || window > 3) {
-		c->err = "hcs_add_flat_sensor: needs a box geom, resolution > 0, 1 <= sampling_resolution <= 32, window in 0..3";
+	// the reference reads the three geom_size entries of whatever geom carries the sensor
+	// (flat_tactile_sensor.cpp:192-197, 265-267): boxes and ellipsoids have three positive ones
+	if (geom < 0 || geom >= (int)c->geoms.size() || !(c->geoms[geom].size[0] > 0) || !(c->geoms[geom].size[1] > 0) ||
+	    !(c->geoms[geom].size[2] > 0) || !(resolution > 0) || sampling_resolution < 1 || sampling_resolution > 32 ||
+	    window < 0 || window > 3) {
+		c->err = "hcs_add_flat_sensor: needs a geom with three positive sizes (box, ellipsoid), resolution > 0, "
+		         "1 <= sampling_resolution <= 32, window in 0..3";
 		return HCS_E_INVALID;
 	}
 	SensorHost s{};

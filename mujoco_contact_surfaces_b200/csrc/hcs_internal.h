@@ -139,7 +139,9 @@ void launch_build_lbvh(const GeomDev &g, const double glo[3], const double ghi[3
 
 void launch_broadphase(const PairDesc &P, const StepIO &io, cudaStream_t s);
 void launch_narrowphase(const PairDesc &P, const StepIO &io, cudaStream_t s);
-void launch_finalize(const PairDesc *d_pairs, const StepIO &io, int max_list_slices, cudaStream_t s);
+// returns the number of kernels launched
+int launch_finalize(const PairDesc *d_pairs, const StepIO &io, int max_list_slices, int list_units_per_env,
+                    cudaStream_t s);
 
 // clear, count, scan, fill, rasterise; returns the number of kernels launched
 int launch_tactile(const SensorDev &sd, const StepIO &io, const PairDesc *d_pairs, cudaStream_t s);

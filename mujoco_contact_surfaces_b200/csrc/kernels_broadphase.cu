@@ -250,7 +250,9 @@ __device__ __forceinline__ void broadphase_unit(const PairDesc &P, const StepIO 
 				count += __popc(mk_);
 				__syncwarp();
 			} else {
-				int k = min(32, n_node);
+				// pop k items, push <= 2k: the queue grows by <= k.  Near the capacity fewer items are popped,
+				// which turns the LIFO into a depth-first walk whose stack stays below the tree depth.
+				int k = max(1, min(min(32, n_node), NODE_Q - n_node));
 				bool pushL = false, pushR = false, leafL = false, leafR = false;
 				int cl = 0, cr = 0;
 				unsigned s = 0;

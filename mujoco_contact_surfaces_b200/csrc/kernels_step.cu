@@ -875,16 +875,30 @@ __device__ __forceinline__ void finalize_pair(const PairDesc *pairs, const StepI
 	io.pair_out[idx] = r;
 }
 
+// phase 1 as its own grid (one warp per unit, blockIdx.y = pair) for scenes with many units per environment,
+// where one CTA per environment would serialise them
+__global__ void __launch_bounds__(NP_BLOCK) reduce_units_kernel(const PairDesc *pairs, StepIO io)
+{
+	const PairDesc &P = pairs[blockIdx.y];
+	if (P.kind != PAIR_SOFT_RIGID && P.kind != PAIR_SOFT_SOFT)
+		return;
+	int warp = (blockIdx.x * NP_BLOCK + threadIdx.x) >> 5;
+	if (warp < io.n_env * P.n_slices)
+		reduce_unit(P, io, warp, threadIdx.x & 31);
+}
+
 // K7: one CTA per env (phases in the header comment above reduce_unit)
-__global__ void __launch_bounds__(128) finalize_kernel(const PairDesc *pairs, StepIO io)
+__global__ void __launch_bounds__(128) finalize_kernel(const PairDesc *pairs, StepIO io, int with_phase1)
 {
 	const int env = blockIdx.x, wid = threadIdx.x >> 5, lane = threadIdx.x & 31, n_warps = blockDim.x >> 5;
-	for (int p = 0; p < io.n_pairs; ++p) {
-		const PairDesc &P = pairs[p];
-		if (P.kind != PAIR_SOFT_RIGID && P.kind != PAIR_SOFT_SOFT)
-			continue;
-		for (int s = wid; s < P.n_slices; s += n_warps)
-			reduce_unit(P, io, env * P.n_slices + s, lane);
+	if (with_phase1) {
+		for (int p = 0; p < io.n_pairs; ++p) {
+			const PairDesc &P = pairs[p];
+			if (P.kind != PAIR_SOFT_RIGID && P.kind != PAIR_SOFT_SOFT)
+				continue;
+			for (int s = wid; s < P.n_slices; s += n_warps)
+				reduce_unit(P, io, env * P.n_slices + s, lane);
+		}
 	}
 	__syncthreads(); // unit partials (global) are visible to the whole CTA
 	for (int p = threadIdx.x; p < io.n_pairs; p += blockDim.x)
@@ -957,12 +971,22 @@ void launch_narrowphase(const PairDesc &P, const StepIO &io, cudaStream_t s)
 	}
 }
 
-void launch_finalize(const PairDesc *d_pairs, const StepIO &io, int max_list_slices, cudaStream_t s)
+int launch_finalize(const PairDesc *d_pairs, const StepIO &io, int max_list_slices, int list_units_per_env,
+                    cudaStream_t s)
 {
-	// one warp per slice of a candidate-list pair (up to 4), never fewer threads than pairs / geoms need
+	if (io.n_env <= 0)
+		return 0;
+	if (list_units_per_env > 4) { // many (pair, slice) units per environment: spread phase 1 over the whole GPU
+		long max_units = (long)io.n_env * max_list_slices;
+		dim3 grid((unsigned)((max_units + NP_WARPS - 1) / NP_WARPS), (unsigned)io.n_pairs);
+		reduce_units_kernel<<<grid, NP_BLOCK, 0, s>>>(d_pairs, io);
+		finalize_kernel<<<io.n_env, 32, 0, s>>>(d_pairs, io, 0);
+		return 2;
+	}
+	// one warp per slice of a candidate-list pair (up to 4)
 	int warps = std::max(1, std::min(4, max_list_slices));
-	if (io.n_env > 0)
-		finalize_kernel<<<io.n_env, 32 * warps, 0, s>>>(d_pairs, io);
+	finalize_kernel<<<io.n_env, 32 * warps, 0, s>>>(d_pairs, io, 1);
+	return 1;
 }
 
 } // namespace hcs

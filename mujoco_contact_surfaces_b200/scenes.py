@@ -28,6 +28,15 @@ class Scene:
         self.name, self.geoms, self.pairs = name, geoms, [tuple(p) for p in pairs]
         self.triangle, self.sensors, self.apply_forces = triangle, list(sensors), apply_forces
         self.pose_fn = None
+        # sizing hints for engine pools that cannot be derived from the geometry alone, per environment
+        # (e.g. {"tactile_triangles_per_env": n}); engine_kwargs() scales them to a batch
+        self.hints = {}
+
+    def engine_kwargs(self, n_envs):
+        kw = {}
+        if "tactile_triangles_per_env" in self.hints:
+            kw["max_tactile_triangles"] = int(self.hints["tactile_triangles_per_env"]) * n_envs
+        return kw
 
     @property
     def n_geoms(self):
@@ -217,6 +226,90 @@ def objects_on_plane(triangle=False):
     return sc
 
 
+# ---- C5: multi-finger grasp, high-resolution fingertip pads with one flat tactile array each --------------------
+def grasp(obj="box", pad_hint=0.00025, n_pads=5, sampling_resolution=8, pad_axes=(0.010, 0.010, 0.012)):
+    """`n_pads` soft ellipsoid pads (single-interior-vertex mesh; pad_hint 0.00025 -> refinement level 7 =
+    131072 tets, 65539 vertices) pressed 0.2-2 mm into a rigid object (cube of half size 0.03 with 3072
+    triangles, or the spot mesh), one pad per face.  Each pad carries a FlatTactileSensor: the sensor frame is the
+    pad's own frame (flat_tactile_sensor.cpp:290-340), so the pad's +z axis points at the object and the rays run
+    from 1.5 zs beyond the pad centre back through the contact patch.  Equal x/y semi-axes give the 16 x 16 array
+    BASELINE.json names (SURVEY.md 8d lists (0.010, 0.008, 0.012), which would be 16 x 12 taxels)."""
+    pad_axes = np.asarray(pad_axes, dtype=np.float64)
+    half = 0.03
+    if obj == "box":
+        og = Geom("object", GEOM_BOX, [half] * 3, [0, 1.0, 2 * half / 16, 0.8, 0.8])
+        pad_first = True  # mj_collideGeoms orders by geom type: ellipsoid (4) < box (6)
+    elif obj == "spot":
+        v, f = load_mesh_fixture("spot")
+        v = (v * np.float32(0.05)).astype(np.float32)
+        og = Geom("object", GEOM_MESH, [0, 0, 0], [0, 1.0, 0, 0.8, 0.8], v, f)
+        pad_first = True  # ellipsoid (4) < mesh (7)
+    else:
+        raise ValueError(obj)
+    geoms = [og] + [Geom("pad%d" % i, GEOM_ELLIPSOID, pad_axes, [5e4, 5.0, pad_hint, 0.8, 0.8]) for i in range(n_pads)]
+    pairs = [(1 + i, 0) if pad_first else (0, 1 + i) for i in range(n_pads)]
+    sensors = [dict(geom=1 + i, resolution=2 * pad_axes[0] / 16, sampling_resolution=sampling_resolution)
+               for i in range(n_pads)]
+    sc = Scene("c5_grasp_" + obj, geoms, pairs, triangle=True, sensors=sensors)
+    normals = np.array([[1, 0, 0], [-1, 0, 0], [0, 1, 0], [0, -1, 0], [0, 0, 1], [0, 0, -1]], dtype=np.float64)
+    spot_v = og.mesh_vert.astype(np.float64) if obj == "spot" else None
+    if spot_v is not None:
+        tri0, tri1, tri2 = (spot_v[og.mesh_face[:, k]] for k in range(3))
+
+    def mesh_height(o, n):
+        """Largest s with o + s n on the mesh surface (the point a finger moving along -n touches first)."""
+        e1, e2 = tri1 - tri0, tri2 - tri0
+        pv = np.cross(n, e2)
+        det = np.einsum("ij,ij->i", e1, pv)
+        ok = np.abs(det) > 1e-14
+        inv = np.where(ok, 1.0 / np.where(ok, det, 1.0), 0.0)
+        tv = o - tri0
+        u = np.einsum("ij,ij->i", tv, pv) * inv
+        qv = np.cross(tv, e1)
+        v = (qv @ n) * inv
+        s = np.einsum("ij,ij->i", qv, e2) * inv
+        hit = ok & (u >= 0) & (v >= 0) & (u + v <= 1)
+        return s[hit].max() if hit.any() else None
+
+    def pose(rng, env, xpos, xmat, vel):
+        R_W, p_W = random_rotation(rng), rng.uniform(-0.2, 0.2, size=3) + [0, 0, 0.5]
+        v_obj = random_velocity(rng, 0.05, 0.5)
+        xpos[0], xmat[0], vel[0] = p_W, R_W.reshape(-1), v_obj
+        for i in range(n_pads):
+            n = normals[i % 6]
+            t1 = np.roll(n, 1)  # two tangents of the face
+            t2 = np.cross(n, t1)
+            uv = rng.uniform(-0.4, 0.4, size=2) * half
+            if spot_v is None:
+                surf = half
+            else:  # first surface point met along -n at the chosen tangential offset (the mesh spans ~ +-0.03)
+                surf = mesh_height(uv[0] * t1 + uv[1] * t2, n)
+                if surf is None:
+                    uv = np.zeros(2)
+                    surf = mesh_height(np.zeros(3), n)
+            depth = rng.uniform(0.0002, 0.002)
+            yaw = rng.uniform(0, 2 * np.pi)
+            tilt = np.deg2rad(rng.uniform(-3, 3, size=2))
+            # pad frame in the object frame: local +z = -n (towards the object), then yaw / tilt about it
+            Rz = np.column_stack([t1, -t2, -n])
+            R_OP = Rz @ rot_zyx(yaw, tilt[0], tilt[1])
+            c_O = uv[0] * t1 + uv[1] * t2 + (surf + pad_axes[2] - depth) * n
+            xpos[1 + i] = p_W + R_W @ c_O
+            xmat[1 + i] = (R_W @ R_OP).reshape(-1)
+            v_rel = random_velocity(rng, 0.01, 0.1)
+            vel[1 + i] = v_obj + v_rel
+
+    # fan triangles per pad and env: tets under the largest contact patch (2 mm deep) x 1.5 (polygons split
+    # along the object's triangle edges) x 5 fan triangles per polygon
+    level = max(0, int(np.ceil(np.log2(np.pi * pad_axes.max() / (2 * pad_hint)))))
+    tet_area = 4 * np.pi * pad_axes.mean() ** 2 / (8 * 4 ** level)
+    # (the spot mesh has ~2 mm^2 triangles and concave regions: patches are larger and cut into more polygons)
+    per_patch = (30.0 if obj == "spot" else 7.5) * 2 * np.pi * pad_axes.max() * 0.002 / tet_area
+    sc.hints["tactile_triangles_per_env"] = int(n_pads * max(12000 if obj == "spot" else 2000, per_patch))
+    sc.pose_fn = pose
+    return sc
+
+
 SCENES = {
     "c1_sphere_on_box": sphere_on_box,
     "c2_myrmex_box": lambda: myrmex("box"),
@@ -224,6 +317,8 @@ SCENES = {
     "c2_myrmex_spot": lambda: myrmex("spot"),
     "c3_soft_soft": soft_soft,
     "c4_objects_on_plane": objects_on_plane,
+    "c5_grasp_box": lambda: grasp("box"),
+    "c5_grasp_spot": lambda: grasp("spot"),
 }
 
 

@@ -18,6 +18,7 @@ def make_oracle(scene):
 
 def make_engine(scene, n_envs, **kw):
     from mujoco_contact_surfaces_b200 import HydroelasticEngine, REP_POLYGON, REP_TRIANGLE
+    kw = dict(scene.engine_kwargs(n_envs), **kw)
     e = HydroelasticEngine(n_envs, representation=REP_TRIANGLE if scene.triangle else REP_POLYGON,
                            apply_contact_forces=scene.apply_forces, **kw)
     scenes.configure(e, scene)

@@ -119,6 +119,22 @@ def test_c2_myrmex_windows(hcs_lib, window, sigma):
                with_sensors=True)
 
 
+@pytest.mark.parametrize("obj", ["box", "spot"])
+def test_c5_grasp_five_pads_with_tactile_arrays(hcs_lib, obj):
+    """C5 at reduced pad resolution (level 4: 2048 tets per pad): five soft pads on one rigid object, five pairs,
+    one 16 x 16 flat sensor per pad whose frame is the pad's own (rays start beyond the pad centre)."""
+    _run_scene(scenes.grasp(obj, pad_hint=0.002), 6, seed=55, hcs_lib=hcs_lib, with_sensors=True)
+
+
+def test_c5_grasp_full_resolution_pads(hcs_lib):
+    """C5 at full pad resolution (level 7: 131072 tets, LBVH built on the GPU, ~10^4 polygons per pad)."""
+    scene = scenes.grasp("box", n_pads=2)
+    eng = make_engine(scene, 1)
+    assert len(eng.geom_mesh(1)["elems"]) == 131072
+    eng.close()
+    _run_scene(scene, 2, seed=56, hcs_lib=hcs_lib, with_sensors=True)
+
+
 @pytest.mark.parametrize("triangle", [False, True])
 def test_mixed_shapes_every_mesh_family(hcs_lib, triangle):
     """Soft MA cylinders (segment and disc regimes), soft grid box, soft MA cube, rigid box / sphere / ellipsoid /
