@@ -71,6 +71,8 @@ struct hcs_ctx {
 	std::vector<SensorHost> sensors;
 	std::vector<void *> step_allocs;
 	PairDesc *d_pairs = nullptr;
+	std::vector<SensorDev> sensor_dev; // device records of all sensors, host copy + device copy
+	SensorDev *d_sensors = nullptr;
 	int32_t *d_counters = nullptr; // zeroed by ONE memset per step: flags[4], face count, tactile triangle count,
 	size_t n_counters   = 0;       // then {flat-list length, next chunk} per pair
 	StepIO io{};
@@ -400,32 +402,32 @@ static void build_pairs(hcs_ctx *c)
 			size_t units = (size_t)n_env * P.n_slices;
 			P.partial    = dalloc<SlicePartial>(c->step_allocs, units);
 			if (P.kind == PAIR_SOFT_PLANE) {
-				P.cap         = 0;
-				P.slab_nverts = dalloc<uint8_t>(c->step_allocs, (size_t)n_env * P.nq);
-				CK(cudaMemsetAsync(P.slab_nverts, 0, (size_t)n_env * P.nq, c->stream));
+				P.nverts = dalloc<uint8_t>(c->step_allocs, (size_t)n_env * P.nq);
+				CK(cudaMemsetAsync(P.nverts, 0, (size_t)n_env * P.nq, c->stream));
 			} else {
-				long cap = c->cfg.max_candidates_per_slice > 0 ?
-				               c->cfg.max_candidates_per_slice :
-				               // a few coarse query elements can each overlap a large share of a fine tree
-				               std::min<long>((long)P.slice_q * P.n_tree,
-				                              std::max<long>(std::max<long>(1024, 64L * P.slice_q), P.n_tree / 4));
-				P.cap         = (int)cap;
-				P.slab        = dalloc<uint2>(c->step_allocs, units * cap);
-				P.slab_count  = dalloc<int32_t>(c->step_allocs, units);
-				P.slab_evals  = dalloc<int32_t>(c->step_allocs, units);
-				CK(cudaMemsetAsync(P.slab_evals, 0, units * sizeof(int32_t), c->stream));
-				P.slab_nverts = dalloc<uint8_t>(c->step_allocs, units * cap);
-				CK(cudaMemsetAsync(P.slab_count, 0, units * sizeof(int32_t), c->stream));
-				// flat narrowphase: offsets, work counter, per-env context blocks, per-candidate contributions
-				const char *mt_env = getenv("HCS_MAX_TOTAL_CANDIDATES");
-				long max_total     = mt_env ? atol(mt_env) : (32L << 20);
-				P.contrib_cap      = (int)std::max<long>(32, std::min<long>((long)units * cap, max_total));
-				P.slab_offset      = dalloc<int32_t>(c->step_allocs, units);
-				P.flat             = dalloc<uint4>(c->step_allocs, (size_t)P.contrib_cap);
-				P.counters         = c->d_counters + 6 + 3 * pi;
-				P.pair_ctx         = dalloc<double>(c->step_allocs, (size_t)n_env * PAIR_CTX_DOUBLES);
-				P.contrib          = dalloc<double>(c->step_allocs, (size_t)10 * P.contrib_cap);
-				CK(cudaMemsetAsync(P.slab_offset, 0, units * sizeof(int32_t), c->stream));
+				// ONE candidate pool per pair for the whole batch (flat list + per-candidate contributions, 97 B per
+				// entry).  Default size: per environment min(nq * n_tree, 16 (nq + n_tree)) candidates, at most 64 M
+				// entries; hcs_config.max_candidates_per_slice > 0 sizes it as that many per (env, slice) unit
+				// instead, HCS_MAX_TOTAL_CANDIDATES overrides both.  Overflow is reported by hcs_step, never UB.
+				long per_env = std::min<long>((long)P.nq * P.n_tree, 16L * ((long)P.nq + P.n_tree));
+				long total   = c->cfg.max_candidates_per_slice > 0 ? (long)c->cfg.max_candidates_per_slice * (long)units :
+				                                                     std::min<long>(per_env * n_env, 64L << 20);
+				if (const char *mt_env = getenv("HCS_MAX_TOTAL_CANDIDATES"))
+					total = atol(mt_env);
+				P.contrib_cap = (int)std::max<long>(1024, std::min<long>(total, 1L << 30));
+				P.range_cap   = (int)std::min<long>((long)units + P.contrib_cap / 128 + 64, 1L << 30);
+				P.flat        = dalloc<uint4>(c->step_allocs, (size_t)P.contrib_cap);
+				P.contrib     = dalloc<double>(c->step_allocs, (size_t)10 * P.contrib_cap); // 80-byte records
+				P.nverts      = dalloc<uint8_t>(c->step_allocs, (size_t)P.contrib_cap);
+				P.unit_range  = dalloc<int4>(c->step_allocs, units);
+				P.ranges      = dalloc<int4>(c->step_allocs, (size_t)P.range_cap);
+				P.unit_count  = dalloc<int32_t>(c->step_allocs, units);
+				P.unit_evals  = dalloc<int32_t>(c->step_allocs, units);
+				P.counters    = c->d_counters + 6 + PAIR_COUNTERS * pi;
+				P.pair_ctx    = dalloc<double>(c->step_allocs, (size_t)n_env * PAIR_CTX_DOUBLES);
+				CK(cudaMemsetAsync(P.unit_range, 0, units * sizeof(int4), c->stream));
+				CK(cudaMemsetAsync(P.unit_count, 0, units * sizeof(int32_t), c->stream));
+				CK(cudaMemsetAsync(P.unit_evals, 0, units * sizeof(int32_t), c->stream));
 			}
 		}
 		c->pair_desc.push_back(P);
@@ -517,7 +519,7 @@ static void finalize(hcs_ctx *c)
 		upload_geom(c, g);
 	for (SensorHost &s : c->sensors)
 		build_sensor(c, s);
-	c->n_counters = 6 + 3 * (size_t)np;
+	c->n_counters = 6 + PAIR_COUNTERS * (size_t)np;
 	c->d_counters = dalloc<int32_t>(c->step_allocs, c->n_counters);
 	CK(cudaMemsetAsync(c->d_counters, 0, c->n_counters * sizeof(int32_t), c->stream));
 	build_pairs(c);
@@ -549,6 +551,13 @@ static void finalize(hcs_ctx *c)
 		sh.dev.items_cap = (int)cap;
 		sh.dev.bin_items = dalloc<int32_t>(c->step_allocs, cap);
 	}
+	c->sensor_dev.clear();
+	for (SensorHost &sh : c->sensors)
+		c->sensor_dev.push_back(sh.dev);
+	c->d_sensors = dalloc<SensorDev>(c->step_allocs, c->sensor_dev.size());
+	if (!c->sensor_dev.empty())
+		CK(cudaMemcpyAsync(c->d_sensors, c->sensor_dev.data(), c->sensor_dev.size() * sizeof(SensorDev),
+		                   cudaMemcpyHostToDevice, c->stream));
 	io.tri_pool    = dalloc<TactileTri>(c->step_allocs, io.max_tris);
 	io.tri_count   = c->d_counters + 5;
 	io.pair_out    = dalloc<hcs_pair_result>(c->step_allocs, (size_t)n_env * np);
@@ -600,9 +609,7 @@ static void step_device(hcs_ctx *c, const double *xpos, const double *xmat, cons
 	if (prof)
 		CK(cudaEventRecord(c->ev[4], s));
 	if (with_sensors)
-		for (SensorHost &sh : c->sensors) {
-			k += launch_tactile(sh.dev, io, c->d_pairs, s);
-		}
+		k += launch_tactile(c->sensor_dev.data(), c->d_sensors, (int)c->sensor_dev.size(), io, c->d_pairs, s);
 	if (prof)
 		CK(cudaEventRecord(c->ev[5], s));
 	CK(cudaGetLastError());
@@ -633,7 +640,7 @@ static int check_flags(hcs_ctx *c)
 		return HCS_E_CAPACITY;
 	}
 	if (c->h_flags[0] & 1) {
-		c->err = "broadphase candidate slab overflow: raise hcs_config.max_candidates_per_slice";
+		c->err = "broadphase candidate overflow (unused since the per-unit slabs were removed)";
 		return HCS_E_CAPACITY;
 	}
 	if (c->h_flags[0] & 2) {
@@ -645,7 +652,8 @@ static int check_flags(hcs_ctx *c)
 		return HCS_E_CAPACITY;
 	}
 	if (c->h_flags[0] & 8) {
-		c->err = "per-candidate contribution pool overflow: raise HCS_MAX_TOTAL_CANDIDATES (candidates per pair and step)";
+		c->err = "candidate pool overflow: raise hcs_config.max_candidates_per_slice (average candidates per (env, slice) unit) "
+		         "or HCS_MAX_TOTAL_CANDIDATES (entries per pair)";
 		return HCS_E_CAPACITY;
 	}
 	return HCS_OK;
@@ -829,7 +837,7 @@ int hcs_update_geom(hcs_ctx *c, int geom, const double size[3])
 int hcs_set_pairs(hcs_ctx *c, const int32_t *g1, const int32_t *g2, int n_pairs)
 {
 	API_BEGIN(c)
-	if (n_pairs < 0 || (n_pairs > 0 && (!g1 || !g2))) {
+	if (n_pairs < 0 || n_pairs > (1 << (32 - TRI_SLICE_BITS)) || (n_pairs > 0 && (!g1 || !g2))) {
 		c->err = "hcs_set_pairs: bad arguments";
 		return HCS_E_INVALID;
 	}
@@ -1054,32 +1062,44 @@ int hcs_get_emitted(hcs_ctx *c, int env, int pair, int32_t *out, int cap)
 	};
 	if (P.kind == PAIR_SOFT_PLANE) {
 		std::vector<uint8_t> nv(P.nq);
-		CK(cudaMemcpyAsync(nv.data(), P.slab_nverts + (size_t)env * P.nq, P.nq, cudaMemcpyDeviceToHost, c->stream));
+		CK(cudaMemcpyAsync(nv.data(), P.nverts + (size_t)env * P.nq, P.nq, cudaMemcpyDeviceToHost, c->stream));
 		CK(cudaStreamSynchronize(c->stream));
 		for (int t = 0; t < P.nq; ++t)
 			if (nv[t] >= 3)
 				put(t, 0, nv[t]);
 		return n;
 	}
-	std::vector<int32_t> counts(P.n_slices);
-	CK(cudaMemcpyAsync(counts.data(), P.slab_count + (size_t)env * P.n_slices, P.n_slices * sizeof(int32_t),
+	// walk the range chains of the env's units: first range inline, further ranges in the pool
+	std::vector<int4> heads(P.n_slices), pool;
+	int32_t used[PAIR_COUNTERS] = { 0, 0, 0, 0 };
+	CK(cudaMemcpyAsync(heads.data(), P.unit_range + (size_t)env * P.n_slices, P.n_slices * sizeof(int4),
 	                   cudaMemcpyDeviceToHost, c->stream));
+	CK(cudaMemcpyAsync(used, P.counters, sizeof used, cudaMemcpyDeviceToHost, c->stream));
 	CK(cudaStreamSynchronize(c->stream));
-	std::vector<uint2> cand;
+	pool.resize(std::min(std::max(used[3], 0), P.range_cap));
+	if (!pool.empty()) {
+		CK(cudaMemcpyAsync(pool.data(), P.ranges, pool.size() * sizeof(int4), cudaMemcpyDeviceToHost, c->stream));
+		CK(cudaStreamSynchronize(c->stream));
+	}
+	std::vector<uint4> cand;
 	std::vector<uint8_t> nv;
 	for (int s = 0; s < P.n_slices; ++s) {
-		int cnt = counts[s];
-		if (cnt <= 0)
-			continue;
-		size_t off = ((size_t)env * P.n_slices + s) * P.cap;
-		cand.resize(cnt);
-		nv.resize(cnt);
-		CK(cudaMemcpyAsync(cand.data(), P.slab + off, cnt * sizeof(uint2), cudaMemcpyDeviceToHost, c->stream));
-		CK(cudaMemcpyAsync(nv.data(), P.slab_nverts + off, cnt, cudaMemcpyDeviceToHost, c->stream));
-		CK(cudaStreamSynchronize(c->stream));
-		for (int i = 0; i < cnt; ++i)
-			if ((nv[i] & 15) >= 3) // the high nibble holds the polygon's force-point count
-				put((int)cand[i].y, (int)cand[i].x, nv[i] & 15); // (tree element of A, query element of B)
+		for (int4 rg = heads[s]; rg.y > 0;) {
+			int cnt = std::min(rg.y, P.contrib_cap - rg.x);
+			if (cnt > 0) {
+				cand.resize(cnt);
+				nv.resize(cnt);
+				CK(cudaMemcpyAsync(cand.data(), P.flat + rg.x, cnt * sizeof(uint4), cudaMemcpyDeviceToHost, c->stream));
+				CK(cudaMemcpyAsync(nv.data(), P.nverts + rg.x, cnt, cudaMemcpyDeviceToHost, c->stream));
+				CK(cudaStreamSynchronize(c->stream));
+				for (int i = 0; i < cnt; ++i)
+					if ((nv[i] & 15) >= 3) // the high nibble holds the polygon's force-point count
+						put((int)cand[i].y, (int)cand[i].x, nv[i] & 15); // (tree element of A, query element of B)
+			}
+			if (rg.z < 0 || rg.z >= (int)pool.size())
+				break;
+			rg = pool[rg.z];
+		}
 	}
 	return n;
 	API_END(c)
@@ -1106,7 +1126,7 @@ int hcs_get_tactile_triangles(hcs_ctx *c, int env, double *out, int cap)
 		if (t.env == env)
 			mine.push_back(&t);
 	std::sort(mine.begin(), mine.end(), [](const TactileTri *a, const TactileTri *b) {
-		return a->pair != b->pair ? a->pair < b->pair : a->order < b->order;
+		return a->pair_slice != b->pair_slice ? a->pair_slice < b->pair_slice : a->idx8 < b->idx8;
 	});
 	int m = 0;
 	for (const TactileTri *t : mine) {

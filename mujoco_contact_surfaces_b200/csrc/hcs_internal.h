@@ -61,8 +61,11 @@ struct TactileTri { // kTriangle contact-surface triangle handed to the tactile 
 	float v[9];
 	int32_t env;
 	double e[3];
-	int32_t pair, order; // order = deterministic key inside (env, pair)
+	uint32_t pair_slice; // pair << TRI_SLICE_BITS | slice of the emitting unit
+	uint32_t idx8;       // (candidate index inside the unit, or tet index for half-space pairs) * 8 + fan triangle
+	// (pair_slice, idx8) is a deterministic total order of the triangles of one environment
 };
+constexpr int TRI_SLICE_BITS = 20; // <= 2^20 slices per pair and env, <= 2^12 pairs
 
 // Everything a step kernel needs to know about one configured geom pair (passed by value).
 struct PairDesc {
@@ -74,24 +77,29 @@ struct PairDesc {
 	double dissipation;  // calcCombinedDissipation (plugin.cpp:138-159)
 	double mu;           // combined dynamic friction
 	int nq, n_tree;      // query elements (of gB) / tree elements (tets of gA); plane: nq = tets of gA
-	int n_slices, slice_q, cap;
+	int n_slices, slice_q;
 	int emit_tactile;    // pair touches a sensor geom and representation is kTriangle
 	GeomDev A, B;
-	uint2 *slab;           // [n_env * n_slices][cap] candidates (query, tree element)
-	int32_t *slab_count;   // [n_env * n_slices] candidates that survived the early-outs (need clipping)
-	int32_t *slab_evals;   // [n_env * n_slices] LBVH leaf hits = pair-evals started in the broadphase
-	uint8_t *slab_nverts;  // [n_env * n_slices][cap] polygon vertex count per candidate (plane: per tet); candidate
-	                       // lists keep the number of force points of the polygon in the high nibble
-	SlicePartial *partial; // [n_env * n_slices]
-	// flat narrowphase over the candidates of ALL (env, slice) units of the pair
-	int32_t *slab_offset;  // [n_env * n_slices] start of the unit's range in the flat list (reserved by the broadphase)
+	SlicePartial *partial; // [n_env * n_slices] per-unit sums (K5 writes them directly, K7 for candidate lists)
+	uint8_t *nverts;       // polygon vertex count: half-space pairs [n_env][tet]; candidate lists [contrib_cap] by
+	                       // flat index, with the number of force points of the polygon in the high nibble
+	// ---- candidate lists (soft-rigid, soft-soft): ONE flat list per pair for the whole batch.  A broadphase warp
+	// stages its (env, slice) unit's candidates in shared memory and appends them in ranges of whole 32-candidate
+	// chunks; a unit's ranges are linked in emission order.  Nothing is sized per unit, so a few coarse query
+	// elements overlapping a large share of a fine tree cannot overflow a per-unit slab.
 	uint4 *flat;           // [contrib_cap] (query element, tree element, unit, index inside the unit)
-	int32_t *counters;     // [0] candidates in the flat list, [1] next 32-candidate chunk of the narrowphase,
-	                       // [2] next (env, slice) unit of the broadphase; zeroed per step
-	double *pair_ctx;      // [n_env][PAIR_CTX_DOUBLES] poses, velocities, X_AB written by the broadphase
-	double *contrib;       // [10][contrib_cap] per-candidate F, tau, area, area*centroid, candidate-major (SoA)
+	double *contrib;       // [contrib_cap][10] per-candidate F, tau, area, area*centroid (80-byte records)
 	int contrib_cap;
+	int4 *unit_range;      // [n_env * n_slices] first range of the unit {base, n, next range or -1, 0}
+	int4 *ranges;          // [range_cap] further ranges
+	int range_cap;
+	int32_t *unit_count;   // [n_env * n_slices] candidates that survived the early-outs (need clipping)
+	int32_t *unit_evals;   // [n_env * n_slices] LBVH leaf hits = pair-evals started in the broadphase
+	int32_t *counters;     // [0] candidates in the flat list, [1] next 32-candidate chunk of the narrowphase,
+	                       // [2] next (env, slice) unit of the broadphase, [3] ranges used; zeroed per step
+	double *pair_ctx;      // [n_env][PAIR_CTX_DOUBLES] poses, velocities, X_AB written by the broadphase
 };
+constexpr int PAIR_COUNTERS = 4;
 
 constexpr int PAIR_CTX_DOUBLES = 48;
 // layout of one context block: R_WA[9] xA[3] wA[3] vA[3] xB[3] wB[3] vB[3] R_AB[9] p_AB[3] p_BAo[3]
@@ -143,7 +151,9 @@ void launch_narrowphase(const PairDesc &P, const StepIO &io, cudaStream_t s);
 int launch_finalize(const PairDesc *d_pairs, const StepIO &io, int max_list_slices, int list_units_per_env,
                     cudaStream_t s);
 
-// clear, count, scan, fill, rasterise; returns the number of kernels launched
-int launch_tactile(const SensorDev &sd, const StepIO &io, const PairDesc *d_pairs, cudaStream_t s);
+// clear, count, scan, fill, rasterise for all sensors (host copy + device copy of the records); returns the number
+// of kernels launched
+int launch_tactile(const SensorDev *sensors, const SensorDev *d_sensors, int n_sensors, const StepIO &io,
+                   const PairDesc *d_pairs, cudaStream_t s);
 
 } // namespace hcs

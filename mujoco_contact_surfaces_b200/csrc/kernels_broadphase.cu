@@ -31,6 +31,7 @@ constexpr int BP_WARPS = 4;
 constexpr int BP_BLOCK = 32 * BP_WARPS;
 constexpr int NODE_Q   = 768; // LIFO of (query slot, node); grows by <= 32 per iteration
 constexpr int LEAF_Q   = 128; // (query slot, tet); drained in batches of 32
+constexpr int STAGE    = 256; // staged candidates per warp; flushed in whole 32-candidate chunks when nearly full
 
 constexpr int ITEM_SHIFT = 27; // queue item = query slot (5 bits) << 27 | node or tet index (27 bits)
 constexpr unsigned ITEM_MASK = (1u << ITEM_SHIFT) - 1u;
@@ -42,7 +43,55 @@ struct __align__(16) WarpQueues {
 	float qbox[6][32];
 	float qpl[4][32]; // soft-rigid: the query triangle's plane (unit normal, offset) in A's frame
 	int qid[32];
+	uint2 stage[STAGE]; // surviving (query, tet) candidates waiting to be appended to the pair's flat list
 };
+
+// Append the first n_flush staged candidates (a multiple of 32 except at the end of the unit) to the pair's flat
+// list as one range and link the range to the unit's chain.  WHERE the range lands depends on the order in which
+// warps get here; results do not: every record carries (unit, index inside the unit), contributions are read back
+// per unit along the chain, in index order.  `last`: -2 no range yet, -1 the inline first range, >= 0 pool range.
+__device__ __forceinline__ void flush_stage(const PairDesc &P, const StepIO &io, WarpQueues &W, int unit, int lane,
+                                            int n_flush, int &n_stage, int &i0, int &last)
+{
+	int base = 0;
+	if (lane == 0) {
+		base     = atomicAdd(P.counters, n_flush);
+		int4 rec = make_int4(base, n_flush, -1, 0);
+		if (last == -2) {
+			P.unit_range[unit] = rec;
+			last               = -1;
+		} else {
+			int r = atomicAdd(P.counters + 3, 1);
+			if (r < P.range_cap) {
+				P.ranges[r] = rec;
+				if (last == -1)
+					P.unit_range[unit].z = r;
+				else
+					P.ranges[last].z = r;
+				last = r;
+			} else {
+				atomicOr(io.flags, 8);
+			}
+		}
+	}
+	base = __shfl_sync(FULL_MASK, base, 0);
+	for (int j = lane; j < n_flush; j += 32)
+		if (base + j < P.contrib_cap) {
+			uint2 cd         = W.stage[j];
+			P.flat[base + j] = make_uint4(cd.x, cd.y, (unsigned)unit, (unsigned)(i0 + j));
+		}
+	__syncwarp();
+	int rem    = n_stage - n_flush; // < 32: slides to the front
+	uint2 keep = make_uint2(0, 0);
+	if (lane < rem)
+		keep = W.stage[n_flush + lane];
+	__syncwarp();
+	if (lane < rem)
+		W.stage[lane] = keep;
+	__syncwarp();
+	i0 += n_flush;
+	n_stage = rem;
+}
 
 // Box overlap of the query with one child of a node; for triangle queries (PLANE) the child box must also
 // straddle the triangle's plane: a subtree entirely on one side of that plane cannot meet the triangle.
@@ -80,8 +129,9 @@ __device__ __forceinline__ void broadphase_unit(const PairDesc &P, const StepIO 
 		double rr = P.A.bound_r + P.B.bound_r + 1e-9;
 		if (dot(d, d) > rr * rr) {
 			if (lane == 0) {
-				P.slab_count[warp] = 0;
-				P.slab_evals[warp] = 0;
+				P.unit_count[warp] = 0;
+				P.unit_evals[warp] = 0;
+				P.unit_range[warp] = make_int4(0, 0, -1, 0);
 			}
 			return;
 		}
@@ -107,8 +157,8 @@ __device__ __forceinline__ void broadphase_unit(const PairDesc &P, const StepIO 
 		cb[CTX_PAB] = X_AB.p.x, cb[CTX_PAB + 1] = X_AB.p.y, cb[CTX_PAB + 2] = X_AB.p.z;
 		cb[CTX_PBA] = p_BAo.x, cb[CTX_PBA + 1] = p_BAo.y, cb[CTX_PBA + 2] = p_BAo.z;
 	}
-	uint2 *slab = P.slab + (size_t)warp * P.cap;
-	int count = 0, evals = 0; // warp-uniform
+	int n_stage = 0, i0 = 0, evals = 0; // warp-uniform: staged candidates, candidates already flushed, leaf hits
+	int last_range = -2;                // lane 0 only
 	int q_begin = slice * P.slice_q, q_end = min(P.nq, q_begin + P.slice_q);
 	unsigned lt_mask = (1u << lane) - 1u;
 	const float4 *nodes4 = reinterpret_cast<const float4 *>(P.A.nodes);
@@ -242,13 +292,12 @@ __device__ __forceinline__ void broadphase_unit(const PairDesc &P, const StepIO 
 				n_leaf -= k;
 				evals += k;
 				unsigned mk_ = __ballot_sync(FULL_MASK, keep);
-				if (keep) {
-					int pos = count + __popc(mk_ & lt_mask);
-					if (pos < P.cap)
-						slab[pos] = make_uint2((unsigned)W.qid[it.x], it.y);
-				}
-				count += __popc(mk_);
+				if (keep)
+					W.stage[n_stage + __popc(mk_ & lt_mask)] = make_uint2((unsigned)W.qid[it.x], it.y);
+				n_stage += __popc(mk_);
 				__syncwarp();
+				if (n_stage > STAGE - 32) // the next drain may not fit: append the whole chunks
+					flush_stage(P, io, W, warp, lane, n_stage & ~31, n_stage, i0, last_range);
 			} else {
 				// pop k items, push <= 2k: the queue grows by <= k.  Near the capacity fewer items are popped,
 				// which turns the LIFO into a depth-first walk whose stack stays below the tree depth.
@@ -308,29 +357,13 @@ __device__ __forceinline__ void broadphase_unit(const PairDesc &P, const StepIO 
 			}
 		}
 	}
-	if (count > P.cap) {
-		if (lane == 0)
-			atomicOr(io.flags, 1);
-		count = P.cap;
-	}
-	// Reserve a contiguous range of the pair's flat candidate list and publish (query, tet, unit, index) records:
-	// the flat narrowphase hands 32 consecutive records to a warp, whatever environments they belong to.  WHERE
-	// the range lands depends on the order in which warps finish; results do not (contributions are read back
-	// per unit, in index order).
-	int base = 0;
+	if (n_stage > 0)
+		flush_stage(P, io, W, warp, lane, n_stage, n_stage, i0, last_range);
 	if (lane == 0) {
-		base               = count > 0 ? atomicAdd(P.counters, count) : 0;
-		P.slab_count[warp] = count;
-		P.slab_evals[warp] = evals;
-		P.slab_offset[warp] = base;
-	}
-	base = __shfl_sync(FULL_MASK, base, 0);
-	__syncwarp();
-	for (int i = lane; i < count; i += 32) {
-		if (base + i < P.contrib_cap) {
-			uint2 cd          = slab[i];
-			P.flat[base + i] = make_uint4(cd.x, cd.y, (unsigned)warp, (unsigned)i);
-		}
+		P.unit_count[warp] = i0;
+		P.unit_evals[warp] = evals;
+		if (last_range == -2)
+			P.unit_range[warp] = make_int4(0, 0, -1, 0);
 	}
 }
 

@@ -382,8 +382,8 @@ __device__ __forceinline__ void integrate_polygon(Poly P, int n, D3 nhat, D3 gra
 // counts, ONE atomicAdd per warp.  World vertices are recomputed from the shared tile.
 template <bool IDENT, class CTX>
 __device__ __forceinline__ void emit_tactile(int n_faces, Poly P, PressTile e, D3 cen, double ec, const CTX &c,
-                                             const StepIO &io, int slot, int lane)
-{
+                                             const StepIO &io, int slice, int index, int lane)
+{ // (slice, index): the emitting unit's slice and the candidate's index inside it (half space: 0 and the tet)
 	int incl = n_faces;
 #pragma unroll
 	for (int o = 1; o < 32; o <<= 1) {
@@ -419,7 +419,9 @@ __device__ __forceinline__ void emit_tactile(int n_faces, Poly P, PressTile e, D
 				t.v[3] = (float)v1.x, t.v[4] = (float)v1.y, t.v[5] = (float)v1.z;
 				t.v[6] = (float)cW.x, t.v[7] = (float)cW.y, t.v[8] = (float)cW.z;
 				t.e[0] = fwd ? ea : eb, t.e[1] = fwd ? eb : ea, t.e[2] = ec;
-				t.env = c.env, t.pair = c.pair, t.order = slot * 8 + i;
+				t.env        = c.env;
+				t.pair_slice = ((unsigned)c.pair << TRI_SLICE_BITS) | (unsigned)slice;
+				t.idx8       = (unsigned)index * 8u + (unsigned)i;
 				io.tri_pool[pos] = t;
 			} else {
 				atomicOr(io.flags, 2);
@@ -429,7 +431,8 @@ __device__ __forceinline__ void emit_tactile(int n_faces, Poly P, PressTile e, D
 	}
 }
 
-__device__ __forceinline__ void reduce_and_store(Acc acc, SlicePartial *out, int lane)
+// fixed xor-shuffle tree over the lanes; every lane ends up with the warp's totals
+__device__ __forceinline__ Acc warp_sum(Acc acc)
 {
 	double d[10] = { acc.F.x, acc.F.y, acc.F.z, acc.tau.x, acc.tau.y, acc.tau.z, acc.area, acc.ac.x, acc.ac.y, acc.ac.z };
 	int n[5]     = { acc.n_polygons, acc.n_faces, acc.n_points, acc.n_candidates, acc.n_clipped };
@@ -442,16 +445,30 @@ __device__ __forceinline__ void reduce_and_store(Acc acc, SlicePartial *out, int
 		for (int k = 0; k < 5; ++k)
 			n[k] += __shfl_xor_sync(FULL_MASK, n[k], o);
 	}
-	if (lane == 0) {
-		SlicePartial sp;
-		sp.F[0] = d[0], sp.F[1] = d[1], sp.F[2] = d[2];
-		sp.tau[0] = d[3], sp.tau[1] = d[4], sp.tau[2] = d[5];
-		sp.area = d[6];
-		sp.ac[0] = d[7], sp.ac[1] = d[8], sp.ac[2] = d[9];
-		sp.n_polygons = n[0], sp.n_faces = n[1], sp.n_points = n[2], sp.n_candidates = n[3], sp.n_clipped = n[4];
-		sp.pad = 0;
-		*out = sp;
-	}
+	Acc r;
+	r.F = mk(d[0], d[1], d[2]), r.tau = mk(d[3], d[4], d[5]), r.area = d[6], r.ac = mk(d[7], d[8], d[9]);
+	r.n_polygons = n[0], r.n_faces = n[1], r.n_points = n[2], r.n_candidates = n[3], r.n_clipped = n[4];
+	return r;
+}
+
+__device__ __forceinline__ void store_partial(const Acc &t, SlicePartial *out)
+{
+	SlicePartial sp;
+	sp.F[0] = t.F.x, sp.F[1] = t.F.y, sp.F[2] = t.F.z;
+	sp.tau[0] = t.tau.x, sp.tau[1] = t.tau.y, sp.tau[2] = t.tau.z;
+	sp.area = t.area;
+	sp.ac[0] = t.ac.x, sp.ac[1] = t.ac.y, sp.ac[2] = t.ac.z;
+	sp.n_polygons = t.n_polygons, sp.n_faces = t.n_faces, sp.n_points = t.n_points;
+	sp.n_candidates = t.n_candidates, sp.n_clipped = t.n_clipped;
+	sp.pad = 0;
+	*out   = sp;
+}
+
+__device__ __forceinline__ void reduce_and_store(Acc acc, SlicePartial *out, int lane)
+{
+	Acc t = warp_sum(acc);
+	if (lane == 0)
+		store_partial(t, out);
 }
 
 __device__ __forceinline__ void store_zero(SlicePartial *out, int n_candidates)
@@ -506,14 +523,19 @@ __device__ __forceinline__ int flat_total(const PairDesc &P, const StepIO &io)
 	return total;
 }
 
+// Contributions: one 80-byte record per candidate (F, tau, area, area*centroid), written and read with five
+// 16-byte accesses.  Measured on C1 / C3 (profiles/r01_notes.md): component-major over the whole pool put a
+// candidate's ten values ~100 MB apart and the reduction ran at 350 GB/s on TLB misses; 32-candidate tiles
+// [component][lane] were 45 % slower than plain records in the C1 finalize (units start at arbitrary offsets,
+// so every unit touched parts of several tiles).
 __device__ __forceinline__ void store_contrib(const PairDesc &P, int g, const Acc &acc)
 {
-	double *cp      = P.contrib + g;
-	const size_t st = (size_t)P.contrib_cap;
-	cp[0] = acc.F.x, cp[st] = acc.F.y, cp[2 * st] = acc.F.z;
-	cp[3 * st] = acc.tau.x, cp[4 * st] = acc.tau.y, cp[5 * st] = acc.tau.z;
-	cp[6 * st] = acc.area;
-	cp[7 * st] = acc.ac.x, cp[8 * st] = acc.ac.y, cp[9 * st] = acc.ac.z;
+	double2 *cp = reinterpret_cast<double2 *>(P.contrib + (size_t)g * 10);
+	cp[0]       = make_double2(acc.F.x, acc.F.y);
+	cp[1]       = make_double2(acc.F.z, acc.tau.x);
+	cp[2]       = make_double2(acc.tau.y, acc.tau.z);
+	cp[3]       = make_double2(acc.area, acc.ac.x);
+	cp[4]       = make_double2(acc.ac.y, acc.ac.z);
 }
 
 template <bool TRI>
@@ -534,17 +556,13 @@ __global__ void __launch_bounds__(NP_BLOCK, 4) narrow_tet_tri_kernel(PairDesc P,
 		int g      = chunk * 32 + lane;
 		int tfaces = 0;
 		int cur    = 0;
-		int slot   = 0;
 		D3 cen     = mk(0, 0, 0);
 		double ec  = 0;
 		int env    = 0;
-		size_t at  = 0; // position of the candidate in the slab: unit * cap + index inside the unit
-		uint4 rec  = make_uint4(0, 0, 0, 0);
+		uint4 rec  = make_uint4(0, 0, 0, 0); // (triangle, tet, unit, index inside the unit)
 		if (g < total) {
-			rec   = P.flat[g];
-			env   = (int)rec.z / P.n_slices;
-			slot  = ((int)rec.z - env * P.n_slices) * P.cap + (int)rec.w;
-			at    = (size_t)rec.z * P.cap + rec.w;
+			rec = P.flat[g];
+			env = (int)rec.z / P.n_slices;
 		}
 		CandCtx ctx = cand_ctx(P, io, env);
 		if (g < total) {
@@ -577,10 +595,11 @@ __global__ void __launch_bounds__(NP_BLOCK, 4) narrow_tet_tri_kernel(PairDesc P,
 				tfaces = n;
 				store_contrib(P, g, acc);
 			}
-			P.slab_nverts[at] = (uint8_t)(nv | (acc.n_points << 4));
+			P.nverts[g] = (uint8_t)(nv | (acc.n_points << 4));
 		}
 		if (TRI && P.emit_tactile)
-			emit_tactile<false>(tfaces, Poly{ buf0 + cur * buf_stride }, e, cen, ec, ctx, io, slot, lane);
+			emit_tactile<false>(tfaces, Poly{ buf0 + cur * buf_stride }, e, cen, ec, ctx, io,
+			                    (int)rec.z - env * P.n_slices, (int)rec.w, lane);
 	}
 }
 
@@ -604,17 +623,13 @@ __global__ void __launch_bounds__(NP_BLOCK, 3) narrow_tet_tet_kernel(PairDesc P,
 		int g      = chunk * 32 + lane;
 		int tfaces = 0;
 		int cur    = 0;
-		int slot   = 0;
 		D3 cen     = mk(0, 0, 0);
 		double ec  = 0;
 		int env    = 0;
-		size_t at  = 0;
-		uint4 rec  = make_uint4(0, 0, 0, 0);
+		uint4 rec  = make_uint4(0, 0, 0, 0); // (tet of B, tet of A, unit, index inside the unit)
 		if (g < total) {
-			rec   = P.flat[g];
-			env   = (int)rec.z / P.n_slices;
-			slot  = ((int)rec.z - env * P.n_slices) * P.cap + (int)rec.w;
-			at    = (size_t)rec.z * P.cap + rec.w;
+			rec = P.flat[g];
+			env = (int)rec.z / P.n_slices;
 		}
 		CandCtx ctx = cand_ctx(P, io, env);
 		if (g < total) {
@@ -706,10 +721,11 @@ __global__ void __launch_bounds__(NP_BLOCK, 3) narrow_tet_tet_kernel(PairDesc P,
 				tfaces = n;
 				store_contrib(P, g, acc);
 			}
-			P.slab_nverts[at] = (uint8_t)(nv | (acc.n_points << 4));
+			P.nverts[g] = (uint8_t)(nv | (acc.n_points << 4));
 		}
 		if (TRI && P.emit_tactile)
-			emit_tactile<false>(tfaces, Poly{ buf0 + cur * buf_stride }, e, cen, ec, ctx, io, slot, lane);
+			emit_tactile<false>(tfaces, Poly{ buf0 + cur * buf_stride }, e, cen, ec, ctx, io,
+			                    (int)rec.z - env * P.n_slices, (int)rec.w, lane);
 	}
 }
 
@@ -720,44 +736,77 @@ __global__ void __launch_bounds__(NP_BLOCK, 3) narrow_tet_tet_kernel(PairDesc P,
 //   phase 2: one thread per pair adds the unit partials in slice order -> hcs_pair_result
 //   phase 3: one thread per geom adds its pairs' wrenches in pair order (replaces two mj_applyFT per face)
 // =================================================================================================
-__device__ __forceinline__ void reduce_unit(const PairDesc &P, const StepIO &io, int warp, int lane)
+struct Contrib {
+	D3 F, tau, ac;
+	double area;
+};
+__device__ __forceinline__ Contrib load_contrib(const PairDesc &P, int g)
 {
-	// three independent loads in flight before anything depends on them
-	const int cnt = P.slab_count[warp], evals = P.slab_evals[warp], off = P.slab_offset[warp];
-	if (cnt == 0) { // nothing was clipped: most units
-		if (lane == 0)
-			store_zero(P.partial + warp, evals);
-		return;
+	const double2 *cp = reinterpret_cast<const double2 *>(P.contrib + (size_t)g * 10);
+	double2 a = cp[0], b = cp[1], c2 = cp[2], d = cp[3], e = cp[4];
+	Contrib c;
+	c.F    = mk(a.x, a.y, b.x);
+	c.tau  = mk(b.y, c2.x, c2.y);
+	c.area = d.x;
+	c.ac   = mk(d.y, e.x, e.y);
+	return c;
+}
+__device__ __forceinline__ void add_contrib(Acc &acc, const Contrib &c, int b, bool tri)
+{
+	int n = b & 15;
+	if (n >= 3) { // candidates without a polygon never wrote their slot: what was loaded from it is discarded
+		acc.n_polygons += 1;
+		acc.n_faces += tri ? n : 1;
+		acc.n_points += b >> 4;
+		acc.F   = acc.F + c.F;
+		acc.tau = acc.tau + c.tau;
+		acc.area += c.area;
+		acc.ac = acc.ac + c.ac;
 	}
-	const uint8_t *nv = P.slab_nverts + (size_t)warp * P.cap;
-	const size_t st   = (size_t)P.contrib_cap;
-	const bool tri    = io.representation == HCS_REP_TRIANGLE;
-	const int n_read  = min(cnt, P.contrib_cap - off);
-	Acc acc           = zero_acc();
-	for (int i = lane; i < n_read; i += 32) {
-		// the contribution is fetched together with the vertex count and discarded when the candidate produced
-		// no polygon (its slot was never written): one memory round trip per iteration instead of two
-		const double *cp = P.contrib + off + i;
-		int b            = nv[i];
-		D3 cF = mk(cp[0], cp[st], cp[2 * st]), cT = mk(cp[3 * st], cp[4 * st], cp[5 * st]);
-		double cA = cp[6 * st];
-		D3 cC     = mk(cp[7 * st], cp[8 * st], cp[9 * st]);
-		int n     = b & 15;
-		if (n >= 3) {
-			acc.n_polygons += 1;
-			acc.n_faces += tri ? n : 1;
-			acc.n_points += b >> 4;
-			acc.F   = acc.F + cF;
-			acc.tau = acc.tau + cT;
-			acc.area += cA;
-			acc.ac = acc.ac + cC;
+}
+
+// totals of one (env, slice) unit, on every lane
+__device__ __forceinline__ Acc unit_sums(const PairDesc &P, const StepIO &io, int unit, int lane)
+{
+	int4 rg         = P.unit_range[unit]; // {base, n, next, -}
+	const int evals = P.unit_evals[unit];
+	if (rg.y == 0) { // nothing was clipped: most units
+		Acc z          = zero_acc();
+		z.n_candidates = evals;
+		return z;
+	}
+	const bool tri = io.representation == HCS_REP_TRIANGLE;
+	Acc acc        = zero_acc();
+	int cnt        = 0;
+	for (;;) {
+		// every range but the last holds whole 32-candidate chunks, so lane l always sees the unit's candidates
+		// l, l + 32, ... in increasing order; two candidates per lane are fetched together (vertex count and
+		// contribution in one round trip each) and added in order
+		for (int j = lane; j < rg.y; j += 64) {
+			int g0 = rg.x + j, g1 = g0 + 32;
+			bool in0 = g0 < P.contrib_cap, in1 = j + 32 < rg.y && g1 < P.contrib_cap;
+			int b0 = in0 ? P.nverts[g0] : 0, b1 = in1 ? P.nverts[g1] : 0;
+			Contrib c0 = load_contrib(P, in0 ? g0 : 0), c1 = load_contrib(P, in1 ? g1 : 0);
+			add_contrib(acc, c0, b0, tri);
+			add_contrib(acc, c1, b1, tri);
 		}
+		cnt += rg.y;
+		if (rg.z < 0)
+			break;
+		rg = P.ranges[rg.z];
 	}
 	if (lane == 0) {
 		acc.n_candidates = evals;
 		acc.n_clipped    = cnt;
 	}
-	reduce_and_store(acc, P.partial + warp, lane);
+	return warp_sum(acc);
+}
+
+__device__ __forceinline__ void reduce_unit(const PairDesc &P, const StepIO &io, int unit, int lane)
+{
+	Acc t = unit_sums(P, io, unit, lane);
+	if (lane == 0)
+		store_partial(t, P.partial + unit);
 }
 
 // =================================================================================================
@@ -782,7 +831,7 @@ __global__ void __launch_bounds__(NP_BLOCK, 3) narrow_tet_plane_kernel(PairDesc 
 	D3 nhat_W  = rot(X_WS.R, n_S);
 	const double kInf = __longlong_as_double(0x7ff0000000000000LL);
 	int q_begin = slice * P.slice_q, q_end = min(P.nq, q_begin + P.slice_q);
-	uint8_t *nvout = P.slab_nverts + (size_t)env * P.nq;
+	uint8_t *nvout = P.nverts + (size_t)env * P.nq;
 #pragma unroll 1
 	for (int q0 = q_begin; q0 < q_end; q0 += 32) {
 		int t      = q0 + lane;
@@ -832,7 +881,7 @@ __global__ void __launch_bounds__(NP_BLOCK, 3) narrow_tet_plane_kernel(PairDesc 
 			nvout[t] = (uint8_t)nv;
 		}
 		if (TRI && P.emit_tactile)
-			emit_tactile<true>(tfaces, poly, e, cen, ec, ctx, io, t, lane);
+			emit_tactile<true>(tfaces, poly, e, cen, ec, ctx, io, 0, t, lane);
 	}
 	reduce_and_store(acc, P.partial + warp, lane);
 }
@@ -923,6 +972,73 @@ __global__ void __launch_bounds__(128) finalize_kernel(const PairDesc *pairs, St
 	}
 }
 
+// K7 fast path for scenes with few units per environment: one WARP per environment does all three phases with
+// the sums in registers / shared memory: no block barrier, nothing written to global memory is read back (the
+// CTA-per-environment kernel spent its time in that chain of dependent round trips).  Same additions in the same
+// order as finalize_pair + the geom loop above.
+constexpr int FIN_ENVS = 4;
+__global__ void __launch_bounds__(32 * FIN_ENVS) finalize_env_warp_kernel(const PairDesc *pairs, StepIO io)
+{
+	extern __shared__ double fin_smem[]; // [FIN_ENVS][n_geoms][6] wrench accumulators
+	const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	const int env = blockIdx.x * FIN_ENVS + wid;
+	if (env >= io.n_env)
+		return;
+	double *w = fin_smem + (size_t)wid * io.n_geoms * 6;
+	for (int k = lane; k < io.n_geoms * 6; k += 32)
+		w[k] = 0;
+	__syncwarp();
+	for (int p = 0; p < io.n_pairs; ++p) {
+		const PairDesc &P = pairs[p];
+		hcs_pair_result r;
+		for (int k = 0; k < 3; ++k)
+			r.F[k] = r.tau[k] = r.centroid[k] = 0;
+		r.area = 0;
+		r.gM = P.gM, r.gN = P.gN;
+		r.n_polygons = r.n_faces = r.n_points = r.n_candidates = r.n_clipped = r.reserved = 0;
+		if (P.kind != PAIR_NONE) {
+			const bool list = P.kind == PAIR_SOFT_RIGID || P.kind == PAIR_SOFT_SOFT;
+			double ac[3]    = { 0, 0, 0 };
+			for (int s = 0; s < P.n_slices; ++s) {
+				const int unit = env * P.n_slices + s;
+				Acc t;
+				if (list) {
+					t = unit_sums(P, io, unit, lane);
+				} else { // half-space pairs: K5 wrote the unit's sums
+					const SlicePartial &sp = P.partial[unit];
+					t.F = mk(sp.F[0], sp.F[1], sp.F[2]), t.tau = mk(sp.tau[0], sp.tau[1], sp.tau[2]);
+					t.ac = mk(sp.ac[0], sp.ac[1], sp.ac[2]), t.area = sp.area;
+					t.n_polygons = sp.n_polygons, t.n_faces = sp.n_faces, t.n_points = sp.n_points;
+					t.n_candidates = sp.n_candidates, t.n_clipped = sp.n_clipped;
+				}
+				r.F[0] += t.F.x, r.F[1] += t.F.y, r.F[2] += t.F.z;
+				r.tau[0] += t.tau.x, r.tau[1] += t.tau.y, r.tau[2] += t.tau.z;
+				ac[0] += t.ac.x, ac[1] += t.ac.y, ac[2] += t.ac.z;
+				r.area += t.area;
+				r.n_polygons += t.n_polygons, r.n_faces += t.n_faces, r.n_points += t.n_points;
+				r.n_candidates += t.n_candidates, r.n_clipped += t.n_clipped;
+			}
+			for (int k = 0; k < 3; ++k) {
+				r.F[k] *= P.sign;
+				r.tau[k] *= P.sign;
+				r.centroid[k] = r.area > 0 ? ac[k] / r.area : 0.0;
+			}
+		}
+		if (lane == 0) {
+			io.pair_out[(size_t)env * io.n_pairs + p] = r;
+			if (P.kind != PAIR_NONE)
+				for (int k = 0; k < 3; ++k) {
+					w[6 * r.gM + k] += r.F[k], w[6 * r.gM + 3 + k] += r.tau[k];
+					w[6 * r.gN + k] -= r.F[k], w[6 * r.gN + 3 + k] -= r.tau[k];
+				}
+		}
+		__syncwarp();
+	}
+	double *out = io.geom_wrench + (size_t)env * io.n_geoms * 6;
+	for (int k = lane; k < io.n_geoms * 6; k += 32)
+		out[k] = w[k];
+}
+
 // =================================================================================================
 // launchers
 // =================================================================================================
@@ -943,7 +1059,7 @@ void launch_narrowphase(const PairDesc &P, const StepIO &io, cudaStream_t s)
 	int grid = (int)((units + NP_WARPS - 1) / NP_WARPS);
 	bool tri = io.representation == HCS_REP_TRIANGLE;
 	// flat kernels: resident CTAs of every SM pull chunks from the work counter; never more CTAs than chunks
-	long max_chunks = (std::min<long>(units * (long)P.cap, P.contrib_cap) + 31) / 32;
+	long max_chunks = ((long)P.contrib_cap + 31) / 32;
 	auto flat_grid  = [&](int ctas_per_sm) {
 		return (int)std::max<long>(1, std::min<long>((long)io.n_sms * ctas_per_sm, (max_chunks + NP_WARPS - 1) / NP_WARPS));
 	};
@@ -976,12 +1092,17 @@ int launch_finalize(const PairDesc *d_pairs, const StepIO &io, int max_list_slic
 {
 	if (io.n_env <= 0)
 		return 0;
-	if (list_units_per_env > 4) { // many (pair, slice) units per environment: spread phase 1 over the whole GPU
+	if (list_units_per_env > 2) { // several (pair, slice) units per environment: spread phase 1 over the whole GPU
 		long max_units = (long)io.n_env * max_list_slices;
 		dim3 grid((unsigned)((max_units + NP_WARPS - 1) / NP_WARPS), (unsigned)io.n_pairs);
 		reduce_units_kernel<<<grid, NP_BLOCK, 0, s>>>(d_pairs, io);
 		finalize_kernel<<<io.n_env, 32, 0, s>>>(d_pairs, io, 0);
 		return 2;
+	}
+	size_t smem = (size_t)FIN_ENVS * io.n_geoms * 6 * sizeof(double);
+	if (smem <= 48 * 1024) { // one warp per environment, everything in registers / shared memory
+		finalize_env_warp_kernel<<<(io.n_env + FIN_ENVS - 1) / FIN_ENVS, 32 * FIN_ENVS, smem, s>>>(d_pairs, io);
+		return 1;
 	}
 	// one warp per slice of a candidate-list pair (up to 4)
 	int warps = std::max(1, std::min(4, max_list_slices));

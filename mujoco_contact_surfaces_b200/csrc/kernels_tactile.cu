@@ -12,6 +12,8 @@
 //                       sample pressures in a shared-memory tile and sums them in the reference's
 //                       (i, j) order, so the taxel value is bit-identical whenever the nearest hit is
 //                       unique (ties between coplanar neighbours carry the same pressure).
+#include <algorithm>
+
 #include "hcs_internal.h"
 
 namespace hcs {
@@ -28,17 +30,11 @@ __device__ __forceinline__ float dotf(F3 a, F3 b) { return a.x * b.x + a.y * b.y
 
 // FILL == false: count the (triangle, taxel) overlaps per taxel; FILL == true: write the triangle ids into
 // the exactly-sized bins delimited by the exclusive scan of the counts.
+// One pass over the triangle pool serves every sensor (a scene with five pads would otherwise read the whole
+// pool five times per pass); grid-stride over the triangles actually emitted this step.
 template <bool FILL>
-__global__ void __launch_bounds__(256) tactile_bin_kernel(SensorDev sd, StepIO io, const PairDesc *pairs)
+__device__ __forceinline__ void bin_triangle(const SensorDev &sd, const StepIO &io, const TactileTri &t, int i)
 {
-	int i = blockIdx.x * blockDim.x + threadIdx.x;
-	int n = min(*io.tri_count, io.max_tris);
-	if (i >= n)
-		return;
-	const TactileTri &t = io.tri_pool[i];
-	const PairDesc &P   = pairs[t.pair];
-	if (P.gM != sd.geom && P.gN != sd.geom)
-		return;
 	int env          = t.env;
 	const double *R  = io.xmat + ((size_t)env * io.n_geoms + sd.geom) * 9;
 	const double *xp = io.xpos + ((size_t)env * io.n_geoms + sd.geom) * 3;
@@ -73,6 +69,20 @@ __global__ void __launch_bounds__(256) tactile_bin_kernel(SensorDev sd, StepIO i
 					atomicOr(io.flags, 4);
 			}
 		}
+}
+
+template <bool FILL>
+__global__ void __launch_bounds__(256) tactile_bin_kernel(const SensorDev *sensors, int n_sensors, StepIO io,
+                                                          const PairDesc *pairs)
+{
+	const int n = min(*io.tri_count, io.max_tris);
+	for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+		const TactileTri &t = io.tri_pool[i];
+		const PairDesc &P   = pairs[t.pair_slice >> TRI_SLICE_BITS];
+		for (int k = 0; k < n_sensors; ++k)
+			if (P.gM == sensors[k].geom || P.gN == sensors[k].geom)
+				bin_triangle<FILL>(sensors[k], io, t, i);
+	}
 }
 
 // ---- exclusive scan of the per-taxel counts (3 phases, 1024-element tiles) ----------------------------------
@@ -296,7 +306,8 @@ __global__ void __launch_bounds__(32 * RASTER_WARPS) tactile_raster_kernel(Senso
 				r = 0;
 				for (int k2 = 0; k2 < n; ++k2) {
 					const TactileTri &o = io.tri_pool[items[k2]];
-					r += (o.pair < t.pair) || (o.pair == t.pair && (o.order < t.order || (o.order == t.order && items[k2] < items[k])));
+					r += (o.pair_slice < t.pair_slice) ||
+					     (o.pair_slice == t.pair_slice && (o.idx8 < t.idx8 || (o.idx8 == t.idx8 && items[k2] < items[k])));
 				}
 				rank_k[r] = k;
 			}
@@ -371,11 +382,27 @@ __global__ void __launch_bounds__(32 * RASTER_WARPS) tactile_raster_kernel(Senso
 			}
 			int ja = max(b.y, (int)ceilf((ymin - m2) / rS - 0.5f)), jb = min(b.z, (int)floorf((ymax + m2) / rS - 0.5f));
 			const TactileTri &t = io.tri_pool[items[c0 + lo_k]];
+			// moller_trumbore() with everything that depends only on (D, triangle) hoisted out of the row: all rays
+			// of a sensor are parallel, so h, a and f are computed once per item (same operations, same rounding)
+			F3 v0 = f3(t.v[0], t.v[1], t.v[2]), v1 = f3(t.v[3], t.v[4], t.v[5]), v2 = f3(t.v[6], t.v[7], t.v[8]);
+			F3 edge1 = v1 - v0, edge2 = v2 - v0;
+			F3 h     = crossf(D, edge2);
+			float a  = dotf(edge1, h);
+			if (fabsf(a) < 1e-10f)
+				continue;
+			float f = 1.0f / a;
 			for (int j = ja; j <= jb; ++j) {
-				int s = i * S + j;
-				F3 O  = f3(org[s], org[S2 + s], org[2 * S2 + s]);
-				float tt, u, v;
-				if (moller_trumbore(O, D, t, tt, u, v))
+				int s   = i * S + j;
+				F3 sv   = f3(org[s], org[S2 + s], org[2 * S2 + s]) - v0;
+				float u = f * dotf(sv, h);
+				if (u < 0.0f || u > 1.0f)
+					continue;
+				F3 q    = crossf(sv, edge1);
+				float v = f * dotf(D, q);
+				if (v < 0.0f || u + v > 1.0f)
+					continue;
+				float tt = f * dotf(edge2, q);
+				if (tt > 0.0f)
 					atomicMin(&key[s], ((unsigned long long)__float_as_uint(tt) << 32) | (unsigned)b.w);
 			}
 		}
@@ -423,24 +450,44 @@ __global__ void tactile_clear_kernel(SensorDev sd, int n)
 	}
 }
 
-// 7 launches: clear, count, 3-phase scan, fill, raster
-int launch_tactile(const SensorDev &sd, const StepIO &io, const PairDesc *d_pairs, cudaStream_t s)
+// per sensor: clear, 3-phase scan, raster; for all sensors together: one count pass and one fill pass over the pool
+int launch_tactile(const SensorDev *sensors, const SensorDev *d_sensors, int n_sensors, const StepIO &io,
+                   const PairDesc *d_pairs, cudaStream_t s)
 {
-	int ncell   = io.n_env * sd.cx * sd.cy;
-	int n_tiles = (ncell + SCAN_TILE - 1) / SCAN_TILE;
-	int tgrid   = (io.max_tris + 255) / 256;
-	tactile_clear_kernel<<<(ncell + 255) / 256, 256, 0, s>>>(sd, ncell);
-	if (io.max_tris > 0)
-		tactile_bin_kernel<false><<<tgrid, 256, 0, s>>>(sd, io, d_pairs);
-	scan_tiles_kernel<<<n_tiles, 256, 0, s>>>(sd.bin_count, sd.bin_offset, sd.scan_tmp, ncell);
-	scan_sums_kernel<<<1, 1024, 0, s>>>(sd.scan_tmp, n_tiles, sd.bin_offset + ncell);
-	scan_add_kernel<<<n_tiles, 256, 0, s>>>(sd.bin_offset, sd.scan_tmp, ncell);
-	if (io.max_tris > 0)
-		tactile_bin_kernel<true><<<tgrid, 256, 0, s>>>(sd, io, d_pairs);
-	int raster_smem = RASTER_WARPS * (int)raster_warp_bytes(sd.S);
-	cudaFuncSetAttribute(tactile_raster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, raster_smem);
-	tactile_raster_kernel<<<(ncell + RASTER_WARPS - 1) / RASTER_WARPS, 32 * RASTER_WARPS, raster_smem, s>>>(sd, io);
-	return 5 + (io.max_tris > 0 ? 2 : 0);
+	if (n_sensors <= 0)
+		return 0;
+	int launches = 0;
+	int tgrid    = (int)std::min<long>(((long)io.max_tris + 255) / 256, (long)io.n_sms * 8);
+	for (int k = 0; k < n_sensors; ++k) {
+		int ncell = io.n_env * sensors[k].cx * sensors[k].cy;
+		tactile_clear_kernel<<<(ncell + 255) / 256, 256, 0, s>>>(sensors[k], ncell);
+		++launches;
+	}
+	if (io.max_tris > 0) {
+		tactile_bin_kernel<false><<<tgrid, 256, 0, s>>>(d_sensors, n_sensors, io, d_pairs);
+		++launches;
+	}
+	for (int k = 0; k < n_sensors; ++k) {
+		const SensorDev &sd = sensors[k];
+		int ncell = io.n_env * sd.cx * sd.cy, n_tiles = (ncell + SCAN_TILE - 1) / SCAN_TILE;
+		scan_tiles_kernel<<<n_tiles, 256, 0, s>>>(sd.bin_count, sd.bin_offset, sd.scan_tmp, ncell);
+		scan_sums_kernel<<<1, 1024, 0, s>>>(sd.scan_tmp, n_tiles, sd.bin_offset + ncell);
+		scan_add_kernel<<<n_tiles, 256, 0, s>>>(sd.bin_offset, sd.scan_tmp, ncell);
+		launches += 3;
+	}
+	if (io.max_tris > 0) {
+		tactile_bin_kernel<true><<<tgrid, 256, 0, s>>>(d_sensors, n_sensors, io, d_pairs);
+		++launches;
+	}
+	for (int k = 0; k < n_sensors; ++k) {
+		const SensorDev &sd = sensors[k];
+		int ncell       = io.n_env * sd.cx * sd.cy;
+		int raster_smem = RASTER_WARPS * (int)raster_warp_bytes(sd.S);
+		cudaFuncSetAttribute(tactile_raster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, raster_smem);
+		tactile_raster_kernel<<<(ncell + RASTER_WARPS - 1) / RASTER_WARPS, 32 * RASTER_WARPS, raster_smem, s>>>(sd, io);
+		++launches;
+	}
+	return launches;
 }
 
 } // namespace hcs
