@@ -59,10 +59,11 @@ typedef struct hcs_config {
 	int n_envs;                   /* independent environments resident on this GPU */
 	int representation;           /* HCS_REP_* */
 	int apply_contact_forces;     /* cs::ApplyContactSurfaceForces (plugin.cpp:603-611) */
-	int max_candidates_per_slice; /* 0 = automatic; broadphase slab capacity */
+	int max_candidates_per_slice; /* 0 = automatic; >0: each pair's candidate pool holds this many candidates per
+	                               * (env, query slice) unit ON AVERAGE (the pool is shared by the whole batch) */
 	int max_faces;                /* >0: keep a per-face dump (PointCollision views) of that capacity */
-	int max_tactile_triangles;    /* 0 = automatic; triangle pool for the tactile stage */
-	int max_triangles_per_taxel;  /* 0 = automatic (64) */
+	int max_tactile_triangles;    /* 0 = automatic; triangle pool of the tactile stage, whole batch */
+	int max_triangles_per_taxel;  /* 0 = automatic (32); AVERAGE (triangle, taxel) overlaps per taxel the bins hold */
 	void *stream;                 /* cudaStream_t to run on, NULL = context-owned stream */
 } hcs_config;
 
