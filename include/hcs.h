@@ -130,6 +130,21 @@ int hcs_set_pairs(hcs_ctx *ctx, const int32_t *g1, const int32_t *g2, int n_pair
 int hcs_add_flat_sensor(hcs_ctx *ctx, int geom, double resolution, int sampling_resolution, int window, float sigma);
 int hcs_sensor_dims(const hcs_ctx *ctx, int sensor, int *cx, int *cy);
 
+/* replaces CurvedSensor (SENS/src/curved_sensor.cpp): load() :111-380 and internal_update() :388-481.
+ * taxel_pos / taxel_nrm: [n_taxels][3] in the sensor geom's frame (taxel_nrm may be NULL: no 45-degree test);
+ * sample_pos / sample_nrm: [n_samples][3] surface sample points with unit normals in the same frame.  The reference
+ * draws the samples with vcglib's Poisson-disk sampler (:271-283, un-vendored); here the caller supplies them, and
+ * the assignment of samples to taxels (distance < include_margin, normal within 45 degrees) and the weights
+ * (include_margin - distance)^2 are computed as in :337-360.  Every step (with_sensors != 0) each assigned sample
+ * casts one float32 ray from its world position along the inward normal; the nearest contact-surface triangle hit
+ * with 0 < t < include_margin contributes weight * e_MN(hit) to the taxel.  Returns the curved sensor index. */
+int hcs_add_curved_sensor(hcs_ctx *ctx, int geom, int n_taxels, const double *taxel_pos, const double *taxel_nrm,
+                          int n_samples, const double *sample_pos, const double *sample_nrm, double include_margin);
+int hcs_curved_sensor_info(const hcs_ctx *ctx, int sensor, int *n_taxels, int *n_rays, int *n_assignments);
+/* out: float [n_envs][n_taxels], TactileState.sensors[0].values of each environment (:479) */
+int hcs_get_curved_values(hcs_ctx *ctx, int sensor, float *out);
+const float *hcs_device_curved_values(hcs_ctx *ctx, int sensor);
+
 /* builds fields, tet half spaces and LBVHs on the GPU, allocates per-env buffers */
 int hcs_finalize(hcs_ctx *ctx);
 

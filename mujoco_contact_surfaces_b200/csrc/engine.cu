@@ -55,6 +55,20 @@ struct SensorHost {
 	float *h_image = nullptr; // pinned [n_env][cx*cy]
 };
 
+// CurvedSensor::load (SENS/src/curved_sensor.cpp:111-380) with caller-supplied surface samples
+struct CurvedHost {
+	int geom;
+	double include_margin;
+	std::vector<double> taxel_pos, taxel_nrm;   // [n][3]; zero normal = no 45 degree test
+	std::vector<double> ray_pos, ray_nrm;       // "close" samples in first-use order (:352-356)
+	std::vector<int32_t> taxel_off, taxel_ray;  // surface_idx as CSR
+	std::vector<double> taxel_w;                // surface_weight
+	int n_taxels() const { return (int)taxel_pos.size() / 3; }
+	int n_rays() const { return (int)ray_pos.size() / 3; }
+	CurvedDev dev{};
+	float *h_values = nullptr; // pinned [n_env][n_taxels]
+};
+
 } // namespace hcs
 
 using namespace hcs;
@@ -69,6 +83,7 @@ struct hcs_ctx {
 	std::vector<std::pair<int, int>> pairs;
 	std::vector<PairDesc> pair_desc;
 	std::vector<SensorHost> sensors;
+	std::vector<CurvedHost> curved;
 	std::vector<void *> step_allocs;
 	PairDesc *d_pairs = nullptr;
 	std::vector<SensorDev> sensor_dev; // device records of all sensors, host copy + device copy
@@ -355,6 +370,9 @@ static bool is_sensor_geom(const hcs_ctx *c, int g)
 	for (const SensorHost &s : c->sensors)
 		if (s.geom == g)
 			return true;
+	for (const CurvedHost &s : c->curved)
+		if (s.geom == g)
+			return true;
 	return false;
 }
 
@@ -494,6 +512,82 @@ static void build_sensor(hcs_ctx *c, SensorHost &s)
 	CK(cudaMallocHost((void **)&s.h_image, std::max<size_t>(ncell, 1) * sizeof(float)));
 }
 
+template <class T>
+static T *upload(hcs_ctx *c, const std::vector<T> &v)
+{
+	T *p = dalloc<T>(c->step_allocs, v.size());
+	if (!v.empty())
+		CK(cudaMemcpyAsync(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, c->stream));
+	return p;
+}
+
+// Static ray grid of a curved sensor (geom frame) + its per-step buffers.  Only cells that hold rays get an id;
+// the per-(env, cell) triangle bins are sized like the flat sensor's.
+static void build_curved(hcs_ctx *c, CurvedHost &s, int max_tris)
+{
+	const int n_env = c->cfg.n_envs, nr = s.n_rays(), nt = s.n_taxels();
+	CurvedDev d{};
+	d.geom = s.geom, d.n_rays = nr, d.n_taxels = nt, d.include_margin = s.include_margin;
+	double lo[3] = { 0, 0, 0 }, hi[3] = { 0, 0, 0 };
+	for (int r = 0; r < nr; ++r)
+		for (int a = 0; a < 3; ++a) {
+			double v = s.ray_pos[3 * (size_t)r + a];
+			lo[a]    = r == 0 ? v : std::min(lo[a], v);
+			hi[a]    = r == 0 ? v : std::max(hi[a], v);
+		}
+	double ext = std::max({ hi[0] - lo[0], hi[1] - lo[1], hi[2] - lo[2] });
+	d.cell     = std::max({ 2 * s.include_margin, ext / 48, 1e-9 });
+	for (int a = 0; a < 3; ++a) {
+		d.origin[a] = lo[a] - 1e-9;
+		d.dims[a]   = (int)std::floor((hi[a] - d.origin[a]) / d.cell) + 1;
+	}
+	std::vector<int32_t> lookup((size_t)d.dims[0] * d.dims[1] * d.dims[2], -1), ray_cell(nr);
+	int n_cells = 0;
+	for (int r = 0; r < nr; ++r) {
+		int ci[3];
+		for (int a = 0; a < 3; ++a)
+			ci[a] = std::min(d.dims[a] - 1, std::max(0, (int)std::floor((s.ray_pos[3 * (size_t)r + a] - d.origin[a]) / d.cell)));
+		size_t idx = ((size_t)ci[0] * d.dims[1] + ci[1]) * d.dims[2] + ci[2];
+		if (lookup[idx] < 0)
+			lookup[idx] = n_cells++;
+		ray_cell[r] = lookup[idx];
+	}
+	d.n_cells = n_cells;
+	std::vector<int32_t> cell_off(n_cells + 1, 0), cell_rays(nr);
+	for (int r = 0; r < nr; ++r)
+		cell_off[ray_cell[r] + 1]++;
+	for (int k = 0; k < n_cells; ++k)
+		cell_off[k + 1] += cell_off[k];
+	{
+		std::vector<int32_t> cur(cell_off.begin(), cell_off.end() - 1);
+		for (int r = 0; r < nr; ++r)
+			cell_rays[cur[ray_cell[r]]++] = r;
+	}
+	d.ray_pos      = upload(c, s.ray_pos);
+	d.ray_nrm      = upload(c, s.ray_nrm);
+	d.cell_lookup  = upload(c, lookup);
+	d.cell_ray_off = upload(c, cell_off);
+	d.cell_rays    = upload(c, cell_rays);
+	d.taxel_off    = upload(c, s.taxel_off);
+	d.taxel_ray    = upload(c, s.taxel_ray);
+	d.taxel_w      = upload(c, s.taxel_w);
+	size_t ncell   = (size_t)n_env * n_cells;
+	d.bin_count    = dalloc<int32_t>(c->step_allocs, ncell);
+	d.bin_offset   = dalloc<int32_t>(c->step_allocs, ncell + 1);
+	d.bin_cursor   = dalloc<int32_t>(c->step_allocs, ncell);
+	d.scan_tmp     = dalloc<int32_t>(c->step_allocs, ncell / 1024 + 2);
+	size_t cap     = std::min<size_t>(std::max<size_t>(8 * (size_t)max_tris, 32 * ncell), (size_t)1 << 30);
+	d.items_cap    = (int)cap;
+	d.bin_items    = dalloc<int32_t>(c->step_allocs, cap);
+	d.raw          = dalloc<double>(c->step_allocs, (size_t)n_env * nr);
+	d.values       = dalloc<float>(c->step_allocs, (size_t)n_env * nt);
+	CK(cudaMemsetAsync(d.raw, 0, std::max<size_t>((size_t)n_env * nr, 1) * sizeof(double), c->stream));
+	CK(cudaMemsetAsync(d.values, 0, std::max<size_t>((size_t)n_env * nt, 1) * sizeof(float), c->stream));
+	CK(cudaMallocHost((void **)&s.h_values, std::max<size_t>((size_t)n_env * nt, 1) * sizeof(float)));
+	memset(s.h_values, 0, std::max<size_t>((size_t)n_env * nt, 1) * sizeof(float));
+	s.dev = d;
+}
+
 static void release_step_buffers(hcs_ctx *c)
 {
 	free_bag(c->step_allocs);
@@ -501,6 +595,11 @@ static void release_step_buffers(hcs_ctx *c)
 		if (s.h_image) {
 			cudaFreeHost(s.h_image);
 			s.h_image = nullptr;
+		}
+	for (CurvedHost &s : c->curved)
+		if (s.h_values) {
+			cudaFreeHost(s.h_values);
+			s.h_values = nullptr;
 		}
 	if (c->h_pair)
 		cudaFreeHost(c->h_pair), c->h_pair = nullptr;
@@ -551,6 +650,8 @@ static void finalize(hcs_ctx *c)
 		sh.dev.items_cap = (int)cap;
 		sh.dev.bin_items = dalloc<int32_t>(c->step_allocs, cap);
 	}
+	for (CurvedHost &ch : c->curved)
+		build_curved(c, ch, io.max_tris);
 	c->sensor_dev.clear();
 	for (SensorHost &sh : c->sensors)
 		c->sensor_dev.push_back(sh.dev);
@@ -608,8 +709,11 @@ static void step_device(hcs_ctx *c, const double *xpos, const double *xmat, cons
 	k += launch_finalize(c->d_pairs, io, list_slices, list_units, s);
 	if (prof)
 		CK(cudaEventRecord(c->ev[4], s));
-	if (with_sensors)
+	if (with_sensors) {
 		k += launch_tactile(c->sensor_dev.data(), c->d_sensors, (int)c->sensor_dev.size(), io, c->d_pairs, s);
+		for (CurvedHost &ch : c->curved)
+			k += launch_curved(ch.dev, io, c->d_pairs, s);
+	}
 	if (prof)
 		CK(cudaEventRecord(c->ev[5], s));
 	CK(cudaGetLastError());
@@ -628,6 +732,10 @@ static void fetch(hcs_ctx *c, int with_sensors)
 	if (with_sensors)
 		for (SensorHost &sh : c->sensors)
 			CK(cudaMemcpyAsync(sh.h_image, sh.dev.image, (size_t)n_env * sh.cx * sh.cy * sizeof(float), cudaMemcpyDeviceToHost, s));
+	if (with_sensors)
+		for (CurvedHost &ch : c->curved)
+			CK(cudaMemcpyAsync(ch.h_values, ch.dev.values, (size_t)n_env * ch.n_taxels() * sizeof(float),
+			                   cudaMemcpyDeviceToHost, s));
 	CK(cudaStreamSynchronize(s));
 	c->results_on_host = true;
 	c->sensors_on_host = with_sensors != 0;
@@ -885,6 +993,102 @@ int hcs_add_flat_sensor(hcs_ctx *c, int geom, double resolution, int sampling_re
 	c->finalized = false;
 	return (int)c->sensors.size() - 1;
 	API_END(c)
+}
+
+int hcs_add_curved_sensor(hcs_ctx *c, int geom, int n_taxels, const double *taxel_pos, const double *taxel_nrm,
+                          int n_samples, const double *sample_pos, const double *sample_nrm, double include_margin)
+{
+	API_BEGIN(c)
+	if (geom < 0 || geom >= (int)c->geoms.size() || n_taxels < 1 || !taxel_pos || n_samples < 0 ||
+	    (n_samples > 0 && (!sample_pos || !sample_nrm)) || !(include_margin > 0)) {
+		c->err = "hcs_add_curved_sensor: needs a geom, >= 1 taxel, sample points with normals, include_margin > 0";
+		return HCS_E_INVALID;
+	}
+	CurvedHost s{};
+	s.geom = geom, s.include_margin = include_margin;
+	s.taxel_pos.assign(taxel_pos, taxel_pos + 3 * (size_t)n_taxels);
+	s.taxel_nrm.assign(3 * (size_t)n_taxels, 0.0);
+	if (taxel_nrm)
+		for (int i = 0; i < n_taxels; ++i) { // normalised like curved_sensor.cpp:187
+			const double *t = taxel_nrm + 3 * (size_t)i;
+			double l = std::sqrt(t[0] * t[0] + t[1] * t[1] + t[2] * t[2]);
+			for (int a = 0; a < 3; ++a)
+				s.taxel_nrm[3 * (size_t)i + a] = l > 0 ? t[a] / l : t[a];
+		}
+	// curved_sensor.cpp:325-368: every sample within include_margin of a taxel (and within 45 degrees of its normal,
+	// when it has one) is assigned to it with weight (include_margin - distance)^2; samples are kept in the order
+	// they are first used.  dist(i,j) is the reference's (-2 t.s + |t|^2) + |s|^2.
+	const double margin_sq = include_margin * include_margin;
+	std::vector<std::vector<int32_t>> idx(n_taxels);
+	std::vector<std::vector<double>> wgt(n_taxels);
+	for (int j = 0; j < n_samples; ++j) {
+		const double *sp = sample_pos + 3 * (size_t)j, *sn = sample_nrm + 3 * (size_t)j;
+		bool added = false;
+		for (int i = 0; i < n_taxels; ++i) {
+			const double *t = &s.taxel_pos[3 * (size_t)i], *tn = &s.taxel_nrm[3 * (size_t)i];
+			double dist = (-2 * (t[0] * sp[0] + t[1] * sp[1] + t[2] * sp[2]) + (t[0] * t[0] + t[1] * t[1] + t[2] * t[2])) +
+			              (sp[0] * sp[0] + sp[1] * sp[1] + sp[2] * sp[2]);
+			double nsq = tn[0] * tn[0] + tn[1] * tn[1] + tn[2] * tn[2];
+			if (dist < margin_sq &&
+			    (nsq == 0 || std::acos(tn[0] * sn[0] + tn[1] * sn[1] + tn[2] * sn[2]) < 45 * M_PI / 180.)) {
+				if (!added) {
+					s.ray_pos.insert(s.ray_pos.end(), sp, sp + 3);
+					s.ray_nrm.insert(s.ray_nrm.end(), sn, sn + 3);
+					added = true;
+				}
+				idx[i].push_back(s.n_rays() - 1);
+				wgt[i].push_back(std::pow(std::max(0.0, include_margin - std::sqrt(dist)), 2));
+			}
+		}
+	}
+	s.taxel_off.assign(1, 0);
+	for (int i = 0; i < n_taxels; ++i) {
+		s.taxel_ray.insert(s.taxel_ray.end(), idx[i].begin(), idx[i].end());
+		s.taxel_w.insert(s.taxel_w.end(), wgt[i].begin(), wgt[i].end());
+		s.taxel_off.push_back((int32_t)s.taxel_ray.size());
+	}
+	c->curved.push_back(std::move(s));
+	c->finalized = false;
+	return (int)c->curved.size() - 1;
+	API_END(c)
+}
+
+int hcs_curved_sensor_info(const hcs_ctx *c, int sensor, int *n_taxels, int *n_rays, int *n_assignments)
+{
+	if (!c || sensor < 0 || sensor >= (int)c->curved.size())
+		return HCS_E_INVALID;
+	const CurvedHost &s = c->curved[sensor];
+	if (n_taxels)
+		*n_taxels = s.n_taxels();
+	if (n_rays)
+		*n_rays = s.n_rays();
+	if (n_assignments)
+		*n_assignments = (int)s.taxel_ray.size();
+	return HCS_OK;
+}
+
+int hcs_get_curved_values(hcs_ctx *c, int sensor, float *out)
+{
+	API_BEGIN(c)
+	if (!c->finalized || !out || sensor < 0 || sensor >= (int)c->curved.size())
+		return HCS_E_INVALID;
+	if (!c->last_with_sensors) {
+		c->err = "hcs_get_curved_values: the last step ran with with_sensors == 0";
+		return HCS_E_INVALID;
+	}
+	if (!c->sensors_on_host)
+		fetch(c, 1);
+	CurvedHost &s = c->curved[sensor];
+	memcpy(out, s.h_values, (size_t)c->cfg.n_envs * s.n_taxels() * sizeof(float));
+	return HCS_OK;
+	API_END(c)
+}
+
+const float *hcs_device_curved_values(hcs_ctx *c, int sensor)
+{
+	if (!c || !c->finalized || sensor < 0 || sensor >= (int)c->curved.size())
+		return nullptr;
+	return c->curved[sensor].dev.values;
 }
 
 int hcs_sensor_dims(const hcs_ctx *c, int sensor, int *cx, int *cy)

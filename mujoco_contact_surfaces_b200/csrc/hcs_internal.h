@@ -138,6 +138,26 @@ struct SensorDev {
 	int items_cap;
 };
 
+// CurvedSensor (SENS/src/curved_sensor.cpp): rays from surface sample points along the inward normal, grouped into
+// taxels with weights.  The rays are static in the geom frame, so they sit in a static uniform grid (only cells
+// that hold rays get an id); every step the contact-surface triangles are binned into the cells whose box, grown
+// by the ray length, they overlap, and one warp per (env, cell) finds each ray's nearest hit in its cell's bin.
+struct CurvedDev {
+	int geom, n_rays, n_taxels, n_cells;   // n_cells = cells that hold rays
+	double include_margin;
+	double origin[3], cell;                // grid in the geom frame
+	int dims[3];
+	const double *ray_pos, *ray_nrm;       // [n_rays][3] geom frame
+	const int32_t *cell_lookup;            // [dims0*dims1*dims2] -> cell id or -1
+	const int32_t *cell_ray_off, *cell_rays; // CSR: rays of each cell
+	const int32_t *taxel_off, *taxel_ray;  // CSR: rays of each taxel (load(): surface_idx)
+	const double *taxel_w;                 //      and their weights (surface_weight)
+	double *raw;                           // [n_env][n_rays] e_MN at the accepted hit, else 0
+	float *values;                         // [n_env][n_taxels]
+	int32_t *bin_count, *bin_offset, *bin_cursor, *bin_items, *scan_tmp; // per (env, cell) triangle bins
+	int items_cap;
+};
+
 // ---- launchers (definitions in the .cu files) ---------------------------------------------------
 void launch_build_tets(const GeomDev &g, cudaStream_t s);
 void launch_build_tris(const GeomDev &g, cudaStream_t s);
@@ -155,5 +175,6 @@ int launch_finalize(const PairDesc *d_pairs, const StepIO &io, int max_list_slic
 // of kernels launched
 int launch_tactile(const SensorDev *sensors, const SensorDev *d_sensors, int n_sensors, const StepIO &io,
                    const PairDesc *d_pairs, cudaStream_t s);
+int launch_curved(const CurvedDev &cd, const StepIO &io, const PairDesc *d_pairs, cudaStream_t s);
 
 } // namespace hcs

@@ -490,4 +490,160 @@ int launch_tactile(const SensorDev *sensors, const SensorDev *d_sensors, int n_s
 	return launches;
 }
 
+// =====================================================================================================
+// K9 curved sensor (CurvedSensor::internal_update, SENS/src/curved_sensor.cpp:388-481).  The reference rebuilds a
+// BLAS/TLAS over the contact surfaces every update and casts one ray per (taxel, assigned surface sample); here
+// every distinct sample casts once: triangles are binned into the static ray grid (count, scan, fill), one warp
+// per (env, cell) finds the nearest hit of each of the cell's rays in the cell's bin with the reference's float32
+// Moeller-Trumbore (ties: smallest (pair, slice, index, fan triangle) key), then one thread per taxel adds
+// weight * pressure over its sample list in the reference's order.
+// =====================================================================================================
+__global__ void curved_clear_kernel(CurvedDev cd, int n)
+{
+	int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < n) {
+		cd.bin_count[i]  = 0;
+		cd.bin_cursor[i] = 0;
+	}
+}
+
+template <bool FILL>
+__global__ void __launch_bounds__(256) curved_bin_kernel(CurvedDev cd, StepIO io, const PairDesc *pairs)
+{
+	const int n = min(*io.tri_count, io.max_tris);
+	for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+		const TactileTri &t = io.tri_pool[i];
+		const PairDesc &P   = pairs[t.pair_slice >> TRI_SLICE_BITS];
+		if (P.gM != cd.geom && P.gN != cd.geom)
+			continue;
+		const int env    = t.env;
+		const double *R  = io.xmat + ((size_t)env * io.n_geoms + cd.geom) * 9;
+		const double *xp = io.xpos + ((size_t)env * io.n_geoms + cd.geom) * 3;
+		double lo[3] = { 1e300, 1e300, 1e300 }, hi[3] = { -1e300, -1e300, -1e300 };
+#pragma unroll
+		for (int k = 0; k < 3; ++k) {
+			double d[3] = { (double)t.v[3 * k] - xp[0], (double)t.v[3 * k + 1] - xp[1], (double)t.v[3 * k + 2] - xp[2] };
+			double l[3] = { R[0] * d[0] + R[3] * d[1] + R[6] * d[2], R[1] * d[0] + R[4] * d[1] + R[7] * d[2],
+				            R[2] * d[0] + R[5] * d[1] + R[8] * d[2] };
+#pragma unroll
+			for (int a = 0; a < 3; ++a)
+				lo[a] = fmin(lo[a], l[a]), hi[a] = fmax(hi[a], l[a]);
+		}
+		// a ray leaves its cell by at most its length: grow the triangle's box by that (+ float32 slack)
+		const double m = cd.include_margin * 1.001 + 1e-6;
+		int c0[3], c1[3];
+		bool out = false;
+#pragma unroll
+		for (int a = 0; a < 3; ++a) {
+			c0[a] = max((int)floor((lo[a] - m - cd.origin[a]) / cd.cell), 0);
+			c1[a] = min((int)floor((hi[a] + m - cd.origin[a]) / cd.cell), cd.dims[a] - 1);
+			out |= c0[a] > c1[a];
+		}
+		if (out)
+			continue;
+		for (int x = c0[0]; x <= c1[0]; ++x)
+			for (int y = c0[1]; y <= c1[1]; ++y)
+				for (int z = c0[2]; z <= c1[2]; ++z) {
+					int id = cd.cell_lookup[((size_t)x * cd.dims[1] + y) * cd.dims[2] + z];
+					if (id < 0)
+						continue;
+					int cell = env * cd.n_cells + id;
+					if (!FILL) {
+						atomicAdd(cd.bin_count + cell, 1);
+					} else {
+						int slot = cd.bin_offset[cell] + atomicAdd(cd.bin_cursor + cell, 1);
+						if (slot < cd.items_cap)
+							cd.bin_items[slot] = i;
+						else
+							atomicOr(io.flags, 4);
+					}
+				}
+	}
+}
+
+__global__ void __launch_bounds__(128) curved_cast_kernel(CurvedDev cd, StepIO io)
+{
+	const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	const long unit = (long)blockIdx.x * 4 + wib;
+	if (unit >= (long)io.n_env * cd.n_cells)
+		return;
+	const int env = (int)(unit / cd.n_cells), cell = (int)(unit - (long)env * cd.n_cells);
+	const int first = cd.bin_offset[unit];
+	const int n     = min(cd.bin_count[unit], max(cd.items_cap - first, 0));
+	const int32_t *items = cd.bin_items + first;
+	const double *R  = io.xmat + ((size_t)env * io.n_geoms + cd.geom) * 9;
+	const double *xp = io.xpos + ((size_t)env * io.n_geoms + cd.geom) * 3;
+	for (int k = cd.cell_ray_off[cell] + lane; k < cd.cell_ray_off[cell + 1]; k += 32) {
+		const int ray    = cd.cell_rays[k];
+		const double *p  = cd.ray_pos + 3 * (size_t)ray, *nn = cd.ray_nrm + 3 * (size_t)ray;
+		double w[3], wn[3]; // M * (p, 1), M * (n, 0) with M = [R | x], curved_sensor.cpp:391-399
+#pragma unroll
+		for (int r = 0; r < 3; ++r) {
+			w[r]  = R[3 * r] * p[0] + R[3 * r + 1] * p[1] + R[3 * r + 2] * p[2] + xp[r];
+			wn[r] = R[3 * r] * nn[0] + R[3 * r + 1] * nn[1] + R[3 * r + 2] * nn[2];
+		}
+		F3 normal = f3((float)wn[0], (float)wn[1], (float)wn[2]);
+		F3 O      = f3((float)w[0], (float)w[1], (float)w[2]) + normal * (float)1e-8;
+		F3 D      = f3(-normal.x, -normal.y, -normal.z);
+		float best_t = 1e30f, best_u = 0, best_v = 0;
+		unsigned best_ps = 0xffffffffu, best_idx = 0xffffffffu;
+		int best = -1;
+		for (int j = 0; j < n; ++j) { // every lane walks the same bin: the loads are broadcasts
+			const int item      = items[j];
+			const TactileTri &t = io.tri_pool[item];
+			float tt, u, v;
+			if (moller_trumbore(O, D, t, tt, u, v)) {
+				bool better = tt < best_t ||
+				              (tt == best_t && (t.pair_slice < best_ps || (t.pair_slice == best_ps && t.idx8 < best_idx)));
+				if (better)
+					best_t = tt, best_u = u, best_v = v, best_ps = t.pair_slice, best_idx = t.idx8, best = item;
+			}
+		}
+		double raw = 0;
+		if (best >= 0 && (double)best_t < cd.include_margin) { // t > 0 is part of the hit test
+			const TactileTri &t = io.tri_pool[best];
+			double b0 = (double)(1 - best_u - best_v), b1 = (double)best_u, b2 = (double)best_v;
+			raw = b0 * t.e[0];
+			raw += b1 * t.e[1];
+			raw += b2 * t.e[2];
+		}
+		cd.raw[(size_t)env * cd.n_rays + ray] = raw;
+	}
+}
+
+__global__ void __launch_bounds__(128) curved_taxel_kernel(CurvedDev cd, StepIO io)
+{
+	long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= (long)io.n_env * cd.n_taxels)
+		return;
+	int env = (int)(i / cd.n_taxels), taxel = (int)(i - (long)env * cd.n_taxels);
+	const double *raw = cd.raw + (size_t)env * cd.n_rays;
+	double pressure   = 0;
+	for (int k = cd.taxel_off[taxel]; k < cd.taxel_off[taxel + 1]; ++k) {
+		double r = raw[cd.taxel_ray[k]];
+		if (r != 0.0) // the reference adds only accepted hits
+			pressure += cd.taxel_w[k] * r;
+	}
+	cd.values[i] = (float)pressure;
+}
+
+int launch_curved(const CurvedDev &cd, const StepIO &io, const PairDesc *d_pairs, cudaStream_t s)
+{
+	const int ncell = io.n_env * cd.n_cells;
+	if (ncell <= 0 || cd.n_taxels <= 0)
+		return 0;
+	const int n_tiles = (ncell + SCAN_TILE - 1) / SCAN_TILE;
+	const int tgrid   = (int)std::max<long>(1, std::min<long>(((long)io.max_tris + 255) / 256, (long)io.n_sms * 8));
+	curved_clear_kernel<<<(ncell + 255) / 256, 256, 0, s>>>(cd, ncell);
+	curved_bin_kernel<false><<<tgrid, 256, 0, s>>>(cd, io, d_pairs);
+	scan_tiles_kernel<<<n_tiles, 256, 0, s>>>(cd.bin_count, cd.bin_offset, cd.scan_tmp, ncell);
+	scan_sums_kernel<<<1, 1024, 0, s>>>(cd.scan_tmp, n_tiles, cd.bin_offset + ncell);
+	scan_add_kernel<<<n_tiles, 256, 0, s>>>(cd.bin_offset, cd.scan_tmp, ncell);
+	curved_bin_kernel<true><<<tgrid, 256, 0, s>>>(cd, io, d_pairs);
+	curved_cast_kernel<<<(ncell + 3) / 4, 128, 0, s>>>(cd, io);
+	long nt = (long)io.n_env * cd.n_taxels;
+	curved_taxel_kernel<<<(unsigned)((nt + 127) / 128), 128, 0, s>>>(cd, io);
+	return 8;
+}
+
 } // namespace hcs

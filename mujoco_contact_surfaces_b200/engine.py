@@ -41,6 +41,7 @@ ABI_SYMBOLS = [
     "hcs_get_geom_wrenches", "hcs_get_sensor_image", "hcs_device_pair_results", "hcs_device_geom_wrenches",
     "hcs_device_sensor_image", "hcs_get_faces", "hcs_get_emitted", "hcs_get_tactile_triangles", "hcs_geom_info",
     "hcs_get_mesh", "hcs_get_lbvh", "hcs_get_counters", "hcs_set_profiling", "hcs_get_stage_ms", "hcs_version",
+    "hcs_add_curved_sensor", "hcs_curved_sensor_info", "hcs_get_curved_values", "hcs_device_curved_values",
 ]
 
 _LIB = None
@@ -65,8 +66,12 @@ def load_library():
         L.hcs_last_error.argtypes = [C.c_void_p]
         L.hcs_destroy.restype = None
         L.hcs_destroy.argtypes = [C.c_void_p]
-        for name in ("hcs_device_pair_results", "hcs_device_geom_wrenches", "hcs_device_sensor_image"):
+        for name in ("hcs_device_pair_results", "hcs_device_geom_wrenches", "hcs_device_sensor_image",
+                     "hcs_device_curved_values"):
             getattr(L, name).restype = C.c_void_p
+        L.hcs_device_curved_values.argtypes = [C.c_void_p, C.c_int]
+        L.hcs_add_curved_sensor.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p,
+                                            C.c_void_p, C.c_double]
         L.hcs_device_pair_results.argtypes = [C.c_void_p]
         L.hcs_device_geom_wrenches.argtypes = [C.c_void_p]
         L.hcs_device_sensor_image.argtypes = [C.c_void_p, C.c_int]
@@ -203,6 +208,28 @@ class HydroelasticEngine:
         cx, cy = self.sensors[sensor]
         out = np.zeros((self.n_envs, cx * cy), dtype=np.float32)
         self._check(self.L.hcs_get_sensor_image(self.h, int(sensor), _ptr(out, C.c_float)))
+        return out
+
+    def add_curved_sensor(self, geom, taxel_pos, taxel_nrm, sample_pos, sample_nrm, include_margin):
+        """CurvedSensor with caller-supplied surface samples (geom frame); returns the curved sensor index."""
+        tp, sp, sn = _f64(taxel_pos).reshape(-1, 3), _f64(sample_pos).reshape(-1, 3), _f64(sample_nrm).reshape(-1, 3)
+        tn = None if taxel_nrm is None else _f64(taxel_nrm).reshape(-1, 3)
+        s = self._check(self.L.hcs_add_curved_sensor(self.h, int(geom), len(tp), tp.ctypes.data,
+                                                     None if tn is None else tn.ctypes.data, len(sp), sp.ctypes.data,
+                                                     sn.ctypes.data, float(include_margin)))
+        if not hasattr(self, "curved"):
+            self.curved = []
+        self.curved.append(len(tp))
+        return s
+
+    def curved_info(self, sensor):
+        a, b, c = C.c_int(), C.c_int(), C.c_int()
+        self._check(self.L.hcs_curved_sensor_info(self.h, int(sensor), C.byref(a), C.byref(b), C.byref(c)))
+        return a.value, b.value, c.value  # taxels, rays (distinct assigned samples), (taxel, sample) assignments
+
+    def curved_values(self, sensor):
+        out = np.zeros((self.n_envs, self.curved[sensor]), dtype=np.float32)
+        self._check(self.L.hcs_get_curved_values(self.h, int(sensor), _ptr(out, C.c_float)))
         return out
 
     def faces(self, cap=1 << 20):

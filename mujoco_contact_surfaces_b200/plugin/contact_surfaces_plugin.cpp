@@ -12,6 +12,7 @@
 #include "contact_surfaces_plugin.h"
 
 #include <algorithm>
+#include <cctype>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -506,6 +507,116 @@ void FlatTactileSensor::internal_update(const mjModel *m, mjData *d, const std::
 				mjv_initGeom(vGeoms + n_vGeom++, mjGEOM_BOX, size, pos, rot, rgba);
 			}
 	}
+}
+
+static std::vector<double> parse_numbers(const std::string &text)
+{
+	std::vector<double> out;
+	std::string tok;
+	auto flush = [&] {
+		if (!tok.empty())
+			out.push_back(std::atof(tok.c_str())), tok.clear();
+	};
+	for (char ch : text) {
+		if (std::isdigit((unsigned char)ch) || ch == '-' || ch == '+' || ch == '.' || ch == 'e' || ch == 'E')
+			tok.push_back(ch);
+		else
+			flush();
+	}
+	flush();
+	return out;
+}
+
+// curved_sensor.cpp:111-380
+bool CurvedSensor::load(const mjModel *m, mjData *d)
+{
+	const PluginConfig &c = rosparam_config_;
+	if (!(TactileSensorBase::load(m, d) && has(c, "taxels") && has(c, "method") && has(c, "include_margin") &&
+	      has(c, "sample_resolution")) ||
+	    !owner_ || !owner_->context())
+		return false;
+	include_margin    = std::atof(c.at("include_margin").c_str());
+	sample_resolution = std::atof(c.at("sample_resolution").c_str());
+	const std::string &method = c.at("method"); // every method evaluates the same weighted ray sum (:443-479)
+	if (method != "closest" && method != "weighted" && method != "mean" && method != "squared")
+		return false;
+	taxel_pos_ = parse_numbers(c.at("taxels"));
+	if (taxel_pos_.empty() || taxel_pos_.size() % 3 != 0)
+		return false;
+	if (has(c, "normals")) {
+		taxel_nrm_ = parse_numbers(c.at("normals"));
+		if (taxel_nrm_.size() != taxel_pos_.size())
+			return false;
+	}
+	if (m->geom_type[geomID] != mjGEOM_MESH || m->geom_dataid[geomID] < 0)
+		return false; // the reference samples mesh geoms only (:241 "TODO implement methods to sample on primitive ...")
+	int cfg_idx = owner_->configIndex(geomID);
+	if (cfg_idx < 0)
+		return false;
+	// surface samples: area-weighted, fixed seed (see the class comment)
+	const int did = m->geom_dataid[geomID];
+	const int nf  = m->mesh_facenum[did];
+	const float *mv = m->mesh_vert + 3 * m->mesh_vertadr[did];
+	const int *mf   = m->mesh_face + 3 * m->mesh_faceadr[did];
+	std::vector<double> cum(nf);
+	double total = 0;
+	auto vert = [&](int v, double out[3]) {
+		for (int a = 0; a < 3; ++a)
+			out[a] = mv[3 * v + a];
+	};
+	for (int f = 0; f < nf; ++f) {
+		double a[3], b[3], cc[3];
+		vert(mf[3 * f], a), vert(mf[3 * f + 1], b), vert(mf[3 * f + 2], cc);
+		double u[3] = { b[0] - a[0], b[1] - a[1], b[2] - a[2] }, v[3] = { cc[0] - a[0], cc[1] - a[1], cc[2] - a[2] };
+		double n[3] = { u[1] * v[2] - u[2] * v[1], u[2] * v[0] - u[0] * v[2], u[0] * v[1] - u[1] * v[0] };
+		total += 0.5 * std::sqrt(n[0] * n[0] + n[1] * n[1] + n[2] * n[2]);
+		cum[f] = total;
+	}
+	long n_samples = std::max<long>(1, std::lround(total / (sample_resolution * sample_resolution)));
+	n_samples      = std::min<long>(n_samples, 1000000);
+	uint64_t state = 42; // splitmix64
+	auto uniform = [&]() {
+		uint64_t z = (state += 0x9e3779b97f4a7c15ULL);
+		z          = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ULL;
+		z          = (z ^ (z >> 27)) * 0x94d049bb133111ebULL;
+		z ^= z >> 31;
+		return (double)(z >> 11) * (1.0 / 9007199254740992.0);
+	};
+	for (long k = 0; k < n_samples; ++k) {
+		double r = uniform() * total;
+		int f    = (int)(std::lower_bound(cum.begin(), cum.end(), r) - cum.begin());
+		f        = std::min(f, nf - 1);
+		double a[3], b[3], cc[3];
+		vert(mf[3 * f], a), vert(mf[3 * f + 1], b), vert(mf[3 * f + 2], cc);
+		double s0 = 1.0 - std::sqrt(uniform()), s1 = (1.0 - s0) * uniform();
+		double u[3] = { b[0] - a[0], b[1] - a[1], b[2] - a[2] }, v[3] = { cc[0] - a[0], cc[1] - a[1], cc[2] - a[2] };
+		double n[3] = { u[1] * v[2] - u[2] * v[1], u[2] * v[0] - u[0] * v[2], u[0] * v[1] - u[1] * v[0] };
+		double l    = std::sqrt(n[0] * n[0] + n[1] * n[1] + n[2] * n[2]);
+		for (int ax = 0; ax < 3; ++ax) {
+			sample_pos_.push_back(s0 * a[ax] + (1 - s0 - s1) * b[ax] + s1 * cc[ax]);
+			sample_nrm_.push_back(l > 0 ? n[ax] / l : 0.0);
+		}
+	}
+	const int n_taxels = (int)taxel_pos_.size() / 3;
+	sensor_index_ = hcs_add_curved_sensor(owner_->context(), cfg_idx, n_taxels, taxel_pos_.data(),
+	                                      taxel_nrm_.empty() ? nullptr : taxel_nrm_.data(), (int)(sample_pos_.size() / 3),
+	                                      sample_pos_.data(), sample_nrm_.data(), include_margin);
+	if (sensor_index_ < 0) {
+		std::fprintf(stderr, "[mujoco_contact_surface_sensors] %s\n", hcs_last_error(owner_->context()));
+		return false;
+	}
+	tactile_state_values_.assign((size_t)n_taxels, 0.0f);
+	return true;
+}
+
+// curved_sensor.cpp:388-481, computed on the GPU by the curved-sensor kernels
+void CurvedSensor::internal_update(const mjModel *, mjData *, const std::vector<GeomCollisionPtr> &)
+{
+	if (!owner_->finalized()) { // no contact pair seen yet: zeros (:446-450)
+		std::fill(tactile_state_values_.begin(), tactile_state_values_.end(), 0.0f);
+		return;
+	}
+	hcs_get_curved_values(owner_->context(), sensor_index_, tactile_state_values_.data());
 }
 
 } // namespace sensors

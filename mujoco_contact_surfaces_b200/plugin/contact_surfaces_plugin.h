@@ -239,6 +239,32 @@ private:
 	int window              = HCS_WINDOW_NONE;
 };
 
+// curved_sensor.h / curved_sensor.cpp:111-380 (load), :388-481 (internal_update)
+// Config keys as in SENS/config/curved_fingertip.yaml; array values ("taxels", "normals") are whitespace / comma
+// separated numbers in this stand-in for XmlRpc.  Deviation (documented in DESIGN.md): the reference samples the
+// sensor mesh with vcglib's Poisson-disk sampler (seed 42, `(int)sample_resolution * area` samples, which is 0 for
+// the shipped configuration); vcglib is not available, so the adapter draws area-weighted uniform samples with a
+// fixed-seed generator, about one per sample_resolution^2 of surface, and exposes them for inspection.
+class CurvedSensor : public TactileSensorBase
+{
+public:
+	bool load(const mjModel *m, mjData *d) override;
+	const std::vector<double> &samplePoints() const { return sample_pos_; }   // [n][3] geom frame
+	const std::vector<double> &sampleNormals() const { return sample_nrm_; }
+	const std::vector<double> &taxelPoints() const { return taxel_pos_; }
+	const std::vector<double> &taxelNormals() const { return taxel_nrm_; }
+	double includeMargin() const { return include_margin; }
+
+protected:
+	void internal_update(const mjModel *m, mjData *d, const std::vector<GeomCollisionPtr> &geomCollisions) override;
+
+private:
+	int sensor_index_        = -1;
+	double include_margin    = 0;
+	double sample_resolution = 0;
+	std::vector<double> taxel_pos_, taxel_nrm_, sample_pos_, sample_nrm_;
+};
+
 } // namespace sensors
 } // namespace contact_surfaces
 } // namespace mujoco_ros

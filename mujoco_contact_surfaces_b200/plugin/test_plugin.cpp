@@ -32,9 +32,20 @@ struct ShimWorld {
 		xipos.insert(xipos.end(), com, com + 3);
 		return b;
 	}
-	int add_geom(const std::string &name, int type, int body, const double size[3], const double pos[3], const double mat[9])
+	std::vector<float> mesh_vert;
+	std::vector<int> mesh_face, mesh_vertadr, mesh_vertnum, mesh_faceadr, mesh_facenum;
+	int add_mesh(const std::vector<float> &v, const std::vector<int> &f)
 	{
-		geom_type.push_back(type), geom_bodyid.push_back(body), geom_dataid.push_back(-1);
+		mesh_vertadr.push_back((int)mesh_vert.size() / 3), mesh_vertnum.push_back((int)v.size() / 3);
+		mesh_faceadr.push_back((int)mesh_face.size() / 3), mesh_facenum.push_back((int)f.size() / 3);
+		mesh_vert.insert(mesh_vert.end(), v.begin(), v.end());
+		mesh_face.insert(mesh_face.end(), f.begin(), f.end());
+		return (int)mesh_vertadr.size() - 1;
+	}
+	int add_geom(const std::string &name, int type, int body, const double size[3], const double pos[3], const double mat[9],
+	             int dataid = -1)
+	{
+		geom_type.push_back(type), geom_bodyid.push_back(body), geom_dataid.push_back(dataid);
 		geom_size.insert(geom_size.end(), size, size + 3);
 		xpos.insert(xpos.end(), pos, pos + 3);
 		xmat.insert(xmat.end(), mat, mat + 9);
@@ -69,6 +80,9 @@ struct ShimWorld {
 		m.text_adr = text_adr.data(), m.text_size = text_size.data(), m.text_data = text_data.data();
 		m.geom_names = gptr.data(), m.numeric_names = nptr.data(), m.text_names = tptr.data();
 		m.body_dofadr = body_dofadr.data();
+		m.mesh_vert = mesh_vert.data(), m.mesh_face = mesh_face.data();
+		m.mesh_vertadr = mesh_vertadr.data(), m.mesh_vertnum = mesh_vertnum.data();
+		m.mesh_faceadr = mesh_faceadr.data(), m.mesh_facenum = mesh_facenum.data();
 		qfrc.assign(m.nv, 0.0);
 		d.geom_xpos = xpos.data(), d.geom_xmat = xmat.data(), d.xipos = xipos.data();
 		d.qfrc_passive = qfrc.data(), d.geom_vel6 = vel6.data();
@@ -223,9 +237,73 @@ static int scenario_myrmex()
 	return 0;
 }
 
+// CurvedSensor on a soft convex mesh geom (SENS/assets/fingertip_mocap.xml arrangement with a small octahedral tip)
+static int scenario_curved_tip()
+{
+	ShimWorld w;
+	const double zero[3] = { 0, 0, 0 };
+	// octahedron with semi-axes (8, 6, 10) mm, outward winding
+	std::vector<float> mv = { 0.008f, 0, 0, -0.008f, 0, 0, 0, 0.006f, 0, 0, -0.006f, 0, 0, 0, 0.010f, 0, 0, -0.010f };
+	std::vector<int> mf   = { 0, 2, 4, 2, 1, 4, 1, 3, 4, 3, 0, 4, 2, 0, 5, 1, 2, 5, 3, 1, 5, 0, 3, 5 };
+	double box_pos[3] = { 0, 0, 0.025 };
+	double R[9];
+	rot_zyx(0.3, 0.25, -0.2, R);
+	double low = 0; // lowest vertex of the rotated tip, 1.5 mm into the box top (z = 0.05)
+	for (size_t v = 0; v < mv.size() / 3; ++v)
+		low = std::fmin(low, R[6] * mv[3 * v] + R[7] * mv[3 * v + 1] + R[8] * mv[3 * v + 2]);
+	double tip_pos[3] = { 0.004, -0.003, 0.05 - 0.0015 - low };
+	int b0 = w.add_body(false, zero), b1 = w.add_body(true, tip_pos);
+	double s_box[3] = { 0.025, 0.025, 0.025 };
+	int did = w.add_mesh(mv, mf);
+	w.add_geom("box_geom", mjGEOM_BOX, b0, s_box, box_pos, I3);
+	w.add_geom("fingertip_geom", mjGEOM_MESH, b1, zero, tip_pos, R, did);
+	w.add_text("cs::HydroelasticContactRepresentation", "kTriangle");
+	w.add_numeric("cs::box_geom", { 0, 1.0, 0.01, 0.0, 0.0 });
+	w.add_numeric("cs::fingertip_geom", { 5e4, 5.0, 0.0, 0.0, 0.0 });
+	w.finish();
+
+	MujocoContactSurfacesPlugin plugin;
+	auto sensor = std::make_shared<sensors::CurvedSensor>();
+	// keys of config/curved_fingertip.yaml; taxels on the lower faces of the tip
+	PluginConfig cfg = { { "type", "mujoco_contact_surface_sensors/CurvedSensor" }, { "sensorName", "myrmex_fingertip" },
+		                 { "geomName", "fingertip_geom" }, { "topicName", "/myrmex_fingertip" }, { "updateRate", "4.0" },
+		                 { "include_margin", "0.006" }, { "method", "squared" }, { "sample_method", "area_importance" },
+		                 { "sample_resolution", "0.0008" },
+		                 { "taxels", "[[0.002, 0.0015, -0.005], [-0.002, 0.0015, -0.005], [0.002, -0.0015, -0.005], "
+		                             "[-0.002, -0.0015, -0.005], [0, 0, 0.010]]" },
+		                 { "normals", "[[0.5, 0.6, -0.6], [-0.5, 0.6, -0.6], [0.5, -0.6, -0.6], [-0.5, -0.6, -0.6], [0, 0, 1]]" } };
+	plugin.addSurfacePlugin(sensor, cfg);
+	if (!plugin.load(&w.m, &w.d)) {
+		std::printf("{\"scenario\": \"curved_tip\", \"error\": \"load failed\"}\n");
+		return 1;
+	}
+	for (int step = 0; step < 3; ++step) {
+		std::fill(w.qfrc.begin(), w.qfrc.end(), 0.0);
+		w.collision_pass();
+		plugin.passiveCallback(&w.m, &w.d);
+		w.d.time += 0.001;
+	}
+	std::printf("{\"scenario\": \"curved_tip\", ");
+	print_vec("tip_pos", tip_pos, 3);
+	print_vec("tip_mat", R, 9);
+	std::vector<double> mvd(mv.begin(), mv.end()), mfd(mf.begin(), mf.end());
+	print_vec("mesh_vert", mvd.data(), (int)mvd.size());
+	print_vec("mesh_face", mfd.data(), (int)mfd.size());
+	print_vec("taxels", sensor->taxelPoints().data(), (int)sensor->taxelPoints().size());
+	print_vec("normals", sensor->taxelNormals().data(), (int)sensor->taxelNormals().size());
+	print_vec("sample_pos", sensor->samplePoints().data(), (int)sensor->samplePoints().size());
+	print_vec("sample_nrm", sensor->sampleNormals().data(), (int)sensor->sampleNormals().size());
+	std::printf("\"publishes\": %d, ", sensor->publishCount());
+	std::vector<double> vals(sensor->lastMessage().begin(), sensor->lastMessage().end());
+	print_vec("values", vals.data(), (int)vals.size(), true);
+	std::printf("}\n");
+	return 0;
+}
+
 int main()
 {
 	int rc = scenario_sphere_on_box();
 	rc |= scenario_myrmex();
+	rc |= scenario_curved_tip();
 	return rc;
 }

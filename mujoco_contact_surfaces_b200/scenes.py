@@ -66,6 +66,9 @@ def configure(target, scene):
             target.add_flat_sensor(ids[s["geom"]], scene.geoms[s["geom"]].size, **kw)
         else:
             target.add_flat_sensor(ids[s["geom"]], **kw)
+    for s in getattr(scene, "curved_sensors", []):
+        target.add_curved_sensor(ids[s["geom"]], s["taxel_pos"], s.get("taxel_nrm"), s["sample_pos"], s["sample_nrm"],
+                                 s["include_margin"])
     return ids
 
 
@@ -306,6 +309,70 @@ def grasp(obj="box", pad_hint=0.00025, n_pads=5, sampling_resolution=8, pad_axes
     # (the spot mesh has ~2 mm^2 triangles and concave regions: patches are larger and cut into more polygons)
     per_patch = (30.0 if obj == "spot" else 7.5) * 2 * np.pi * pad_axes.max() * 0.002 / tet_area
     sc.hints["tactile_triangles_per_env"] = int(n_pads * max(12000 if obj == "spot" else 2000, per_patch))
+    sc.pose_fn = pose
+    return sc
+
+
+# ---- curved fingertip sensor (SENS/assets/fingertip_mocap.xml + SENS/config/curved_fingertip.yaml) ----------------
+# taxel positions / normals of the reference's fingertip configuration (geom frame of the ubi_tip mesh, metres)
+_TIP_TAXELS = np.array([
+    [0.00415178164, -0.00615073064, 0.01464621212], [0.008619488, 0.00046286059, 0.01316570371],
+    [0.00830223182, 0.00074051459, 0.01945107626], [0.00354169091, -0.00500616896, 0.0238568657],
+    [0.00266992694, 0.00055709812, 0.03028623604], [0.00713842137, 0.00097836545, 0.02588591432],
+    [-0.00713842136, 0.00097836546, 0.02588591435], [-0.00266992693, 0.00055709811, 0.030286236],
+    [-0.00354169087, -0.00500616897, 0.02385686587], [-0.00830223175, 0.00074051458, 0.01945107617],
+    [-0.00861948819, 0.00046286058, 0.01316570354], [-0.0041517816, -0.0061507306, 0.01464621205]])
+_TIP_NORMALS = np.array([
+    [0.37386554, -0.92331819, 0.08779566], [0.9989708, -0.03265917, 0.03147561], [0.99543803, -0.03717611, 0.08786959],
+    [0.36603357, -0.89345384, 0.26030685], [0.35214134, -0.13784856, 0.92573984], [0.9230213, -0.06311386, 0.37953699],
+    [-0.9230213, -0.06311386, 0.37953699], [-0.35214134, -0.13784856, 0.92573984], [-0.36603357, -0.89345384, 0.26030685],
+    [-0.99543803, -0.03717611, 0.08786959], [-0.9989708, -0.03265917, 0.03147561], [-0.37386554, -0.92331819, 0.08779566]])
+
+
+def surface_samples(verts, faces, n, seed=42):
+    """Area-weighted random points on a triangle mesh with the face normals of the winding (stand-in for the
+    reference's vcglib Poisson-disk sampling, curved_sensor.cpp:271-283, which is not reproducible here)."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    tri = verts[faces]
+    nrm = np.cross(tri[:, 1] - tri[:, 0], tri[:, 2] - tri[:, 0])
+    area = 0.5 * np.linalg.norm(nrm, axis=1)
+    pick = rng.choice(len(faces), size=n, p=area / area.sum())
+    u, v = rng.uniform(size=n), rng.uniform(size=n)
+    a = 1 - np.sqrt(u)
+    b = (1 - a) * v
+    pts = a[:, None] * tri[pick, 0] + (1 - a - b)[:, None] * tri[pick, 1] + b[:, None] * tri[pick, 2]
+    return pts, nrm[pick] / (2 * area[pick])[:, None]
+
+
+def fingertip(n_samples=3000, include_margin=0.006, with_normals=True):
+    """Soft ubi_tip fingertip (convex-mesh geom, centroid-fan tets) pressed onto a rigid box; CurvedSensor with the
+    reference's 12 taxels on the fingertip geom."""
+    tip_v, tip_f = load_mesh_fixture("ubi_tip")
+    tip_v = (tip_v * np.float32(0.001)).astype(np.float32)  # fingertip_mocap.xml:42
+    geoms = [Geom("box_geom", GEOM_BOX, [0.025] * 3, [0, 1.0, 0.01, 0.0, 0.0]),
+             Geom("fingertip_geom", GEOM_MESH, [0, 0, 0], [5e4, 5.0, 0.0, 0.0, 0.0], tip_v, tip_f)]
+    sc = Scene("fingertip_curved", geoms, [(0, 1)], triangle=True)
+    tv = tip_v.astype(np.float64)
+    pts, nrm = surface_samples(tv, tip_f, n_samples)
+    sc.curved_sensors = [dict(geom=1, taxel_pos=_TIP_TAXELS, taxel_nrm=_TIP_NORMALS if with_normals else None,
+                              sample_pos=pts, sample_nrm=nrm, include_margin=include_margin)]
+    sc.hints["tactile_triangles_per_env"] = 20000
+
+    def pose(rng, env, xpos, xmat, vel):
+        xpos[0], xmat[0] = [0, 0, 0.025], np.eye(3).reshape(-1)
+        n = _TIP_NORMALS[rng.integers(len(_TIP_NORMALS))]
+        n = n / np.linalg.norm(n)
+        # rotation taking the chosen taxel normal to -z, then yaw about z and a small tilt
+        t = np.cross(n, [0.3, 0.5, 0.8])
+        t /= np.linalg.norm(t)
+        B = np.column_stack([t, np.cross(-n, t), -n])  # local frame whose third axis is -n
+        R = rot_zyx(rng.uniform(0, 2 * np.pi), *np.deg2rad(rng.uniform(-8, 8, size=2))) @ B.T
+        depth = rng.uniform(0.0003, 0.002)
+        low = (tv @ R.T)[:, 2].min()
+        xy = rng.uniform(-0.01, 0.01, size=2)
+        xpos[1], xmat[1] = [xy[0], xy[1], 0.05 - depth - low], R.reshape(-1)
+        vel[1] = random_velocity(rng, 0.02, 0.2)
+
     sc.pose_fn = pose
     return sc
 

@@ -349,6 +349,47 @@ int orc_geom_wrench(void *h, int geom, double *out6)
 		out6[i] = sc.last.geom_wrench[geom][i];
 	return 0;
 }
+// curved_sensor.cpp:111-380 (load, with the surface samples supplied by the caller) and :388-481
+int orc_add_curved_sensor(void *h, int geom, int n_taxels, const double *taxel_pos, const double *taxel_nrm,
+                          int n_samples, const double *sample_pos, const double *sample_nrm, double include_margin)
+{
+	Scene &sc = *(Scene *)h;
+	CurvedSensor cs;
+	cs.geom           = geom;
+	cs.include_margin = include_margin;
+	for (int i = 0; i < n_taxels; ++i) {
+		cs.taxel_pos.push_back({ taxel_pos[3 * i], taxel_pos[3 * i + 1], taxel_pos[3 * i + 2] });
+		V3 nn{ 0, 0, 0 };
+		if (taxel_nrm) { // normalised like :187
+			nn = { taxel_nrm[3 * i], taxel_nrm[3 * i + 1], taxel_nrm[3 * i + 2] };
+			double l = std::sqrt(nn[0] * nn[0] + nn[1] * nn[1] + nn[2] * nn[2]);
+			if (l > 0)
+				nn = { nn[0] / l, nn[1] / l, nn[2] / l };
+		}
+		cs.taxel_nrm.push_back(nn);
+	}
+	curved_sensor_load(cs, sample_pos, sample_nrm, n_samples);
+	sc.curved.push_back(cs);
+	return (int)sc.curved.size() - 1;
+}
+int orc_curved_values(void *h, int sensor, float *out, int use_bvh)
+{
+	Scene &sc = *(Scene *)h;
+	curved_sensor_values(sc, sc.last, sensor, out, use_bvh != 0);
+	return 0;
+}
+int orc_curved_info(void *h, int sensor, int *n_close_n_assign)
+{
+	Scene &sc = *(Scene *)h;
+	const CurvedSensor &cs = sc.curved[sensor];
+	size_t a = 0;
+	for (const auto &v : cs.surface_idx)
+		a += v.size();
+	n_close_n_assign[0] = (int)cs.surf_pos.size();
+	n_close_n_assign[1] = (int)a;
+	return 0;
+}
+
 int orc_sensor_image(void *h, int sensor, float *out, int use_bvh, int parallel)
 {
 	Scene &sc = *(Scene *)h;

@@ -189,6 +189,20 @@ struct FlatSensor {
 	int cx, cy;
 };
 
+// CurvedSensor (mujoco_contact_surface_sensors/src/curved_sensor.cpp): taxels with optional normals, surface sample
+// points with normals (the reference draws them with vcglib's Poisson-disk sampler, seed 42 — absent here, so the
+// samples are an INPUT), the per-taxel sample lists and weights of load() :325-368, rays cast in internal_update
+// :388-481.
+struct CurvedSensor {
+	int geom;
+	double include_margin;
+	std::vector<V3> taxel_pos, taxel_nrm;        // geom frame; a zero normal disables the 45 degree test
+	std::vector<V3> surf_pos, surf_nrm;          // "close" sample points (kept in first-use order, :352-356)
+	std::vector<int> surf_src;                   // index of each close point in the caller's sample array
+	std::vector<std::vector<int>> surface_idx;   // per taxel: indices into surf_pos
+	std::vector<std::vector<double>> surface_weight;
+};
+
 struct PairOut {
 	bool has_surface = false;
 	int gM = -1, gN = -1;
@@ -212,6 +226,7 @@ struct Scene {
 	std::vector<Geom> geoms;
 	std::vector<std::array<int, 2>> pairs;
 	std::vector<FlatSensor> sensors;
+	std::vector<CurvedSensor> curved;
 	StepState last;
 };
 
@@ -227,6 +242,8 @@ void evaluate_contact_surface(const Scene &sc, PairOut &po); // plugin.cpp:320-4
 void passive_forces(const Scene &sc, PairOut &po, const double *xpos, const double *vel); // plugin.cpp:411-483
 void step(const Scene &sc, StepState &st, const double *xpos, const double *xmat, const double *vel, bool use_bvh);
 void flat_sensor_image(const Scene &sc, const StepState &st, int sensor, float *out, bool use_bvh, bool parallel);
+void curved_sensor_load(CurvedSensor &cs, const double *sample_pos, const double *sample_nrm, int n_samples);
+void curved_sensor_values(const Scene &sc, const StepState &st, int sensor, float *out, bool use_bvh);
 
 double combined_dissipation(const Geom &a, const Geom &b);
 double combined_friction_dynamic(const Geom &a, const Geom &b);

@@ -33,7 +33,7 @@ def lib():
         for name in ("orc_scene_destroy", "orc_add_geom", "orc_add_raw_soft", "orc_add_raw_rigid", "orc_geom_info",
                      "orc_geom_mesh", "orc_set_pairs", "orc_add_flat_sensor", "orc_sensor_dims", "orc_step",
                      "orc_pair_result", "orc_pair_emitted", "orc_pair_faces", "orc_pair_triangles", "orc_geom_wrench",
-                     "orc_sensor_image", "orc_bench"):
+                     "orc_sensor_image", "orc_bench", "orc_add_curved_sensor", "orc_curved_values", "orc_curved_info"):
             getattr(L, name).restype = C.c_int
         _LIB = L
     return _LIB
@@ -122,6 +122,28 @@ class OracleScene:
         r = self.L.orc_add_flat_sensor(self.h, int(geom), _p(gs, C.c_double), C.c_double(resolution),
                                        int(sampling_resolution), int(window), C.c_float(sigma))
         return r
+
+    def add_curved_sensor(self, geom, taxel_pos, taxel_nrm, sample_pos, sample_nrm, include_margin):
+        """CurvedSensor::load with caller-supplied surface samples; returns the sensor index."""
+        tp, sp, sn = _d(taxel_pos).reshape(-1, 3), _d(sample_pos).reshape(-1, 3), _d(sample_nrm).reshape(-1, 3)
+        tn = None if taxel_nrm is None else _d(taxel_nrm).reshape(-1, 3)
+        s = self.L.orc_add_curved_sensor(self.h, int(geom), len(tp), _p(tp, C.c_double),
+                                         None if tn is None else _p(tn, C.c_double), len(sp), _p(sp, C.c_double),
+                                         _p(sn, C.c_double), C.c_double(include_margin))
+        if not hasattr(self, "curved_taxels"):
+            self.curved_taxels = []
+        self.curved_taxels.append(len(tp))
+        return s
+
+    def curved_values(self, sensor, use_bvh=True):
+        out = np.zeros(self.curved_taxels[sensor], dtype=np.float32)
+        self.L.orc_curved_values(self.h, int(sensor), _p(out, C.c_float), int(use_bvh))
+        return out
+
+    def curved_info(self, sensor):
+        d = np.zeros(2, dtype=np.int32)
+        self.L.orc_curved_info(self.h, int(sensor), _p(d, C.c_int))
+        return int(d[0]), int(d[1])  # close sample points, (taxel, sample) assignments
 
     def sensor_dims(self, sensor):
         d = np.zeros(2, dtype=np.int32)

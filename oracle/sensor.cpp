@@ -452,4 +452,103 @@ void flat_sensor_image(const Scene &sc, const StepState &st, int sensor, float *
 	}
 }
 
+// curved_sensor.cpp:325-368: distance matrix taxel x sample, assignment of every sample within include_margin of a
+// taxel (and, when the taxel has a normal, within 45 degrees of it), weight (include_margin - distance)^2, "close"
+// samples kept in the order they are first used.  dist(i,j) is written as the reference's Eigen expression
+// (-2 t.s + |t|^2) + |s|^2; the summation order inside Eigen's product is not observable.
+void curved_sensor_load(CurvedSensor &cs, const double *sample_pos, const double *sample_nrm, int m)
+{
+	const int n = (int)cs.taxel_pos.size();
+	cs.surface_idx.assign(n, {});
+	cs.surface_weight.assign(n, {});
+	cs.surf_pos.clear(), cs.surf_nrm.clear(), cs.surf_src.clear();
+	const double margin_sq = cs.include_margin * cs.include_margin;
+	for (int j = 0; j < m; ++j) {
+		V3 s{ sample_pos[3 * j], sample_pos[3 * j + 1], sample_pos[3 * j + 2] };
+		V3 sn{ sample_nrm[3 * j], sample_nrm[3 * j + 1], sample_nrm[3 * j + 2] };
+		bool added = false;
+		for (int i = 0; i < n; ++i) {
+			const V3 &t = cs.taxel_pos[i], &tn = cs.taxel_nrm[i];
+			double dist = (-2 * (t[0] * s[0] + t[1] * s[1] + t[2] * s[2]) + (t[0] * t[0] + t[1] * t[1] + t[2] * t[2])) +
+			              (s[0] * s[0] + s[1] * s[1] + s[2] * s[2]);
+			double nsq = tn[0] * tn[0] + tn[1] * tn[1] + tn[2] * tn[2];
+			if (dist < margin_sq &&
+			    (nsq == 0 || std::acos(tn[0] * sn[0] + tn[1] * sn[1] + tn[2] * sn[2]) < 45 * M_PI / 180.)) {
+				if (!added) {
+					cs.surf_pos.push_back(s), cs.surf_nrm.push_back(sn), cs.surf_src.push_back(j);
+					added = true;
+				}
+				cs.surface_idx[i].push_back((int)cs.surf_pos.size() - 1);
+				cs.surface_weight[i].push_back(std::pow(std::max(0.0, cs.include_margin - std::sqrt(dist)), 2));
+			}
+		}
+	}
+}
+
+// curved_sensor.cpp:388-481 internal_update: one ray per (taxel, assigned sample) from the sample point along the
+// inward normal, nearest hit with 0 < t < include_margin, pressure = sum of weight * e_MN(hit).
+void curved_sensor_values(const Scene &sc, const StepState &st, int sensor, float *out, bool use_bvh)
+{
+	const CurvedSensor &cs = sc.curved[sensor];
+	const int id = cs.geom, n = (int)cs.taxel_pos.size();
+	double rot[9];
+	std::memcpy(rot, &st.xmat[9 * id], sizeof(rot));
+	const double *xp = &st.xpos[3 * id];
+	std::fill(out, out + n, 0.0f);
+	std::vector<Blas> blas;
+	for (const PairOut &po : st.out)
+		if (po.has_surface && (po.gM == id || po.gN == id) && po.s->tri)
+			blas.emplace_back();
+	{
+		int b = 0;
+		for (const PairOut &po : st.out)
+			if (po.has_surface && (po.gM == id || po.gN == id) && po.s->tri)
+				blas[b++].build(*po.s);
+	}
+	if (blas.empty())
+		return;
+	Tlas tlas;
+	tlas.build(blas);
+	for (int i = 0; i < n; ++i) {
+		double pressure = 0;
+		for (size_t j0 = 0; j0 < cs.surface_idx[i].size(); ++j0) {
+			int j = cs.surface_idx[i][j0];
+			const V3 &p = cs.surf_pos[j], &nn = cs.surf_nrm[j];
+			// M * (p, 1) and M * (n, 0) with M = [R | x] (:391-399)
+			double w[3], wn[3];
+			for (int r = 0; r < 3; ++r) {
+				w[r]  = rot[3 * r] * p[0] + rot[3 * r + 1] * p[1] + rot[3 * r + 2] * p[2] + xp[r];
+				wn[r] = rot[3 * r] * nn[0] + rot[3 * r + 1] * nn[1] + rot[3 * r + 2] * nn[2];
+			}
+			F3 normal{ (float)wn[0], (float)wn[1], (float)wn[2] };
+			F3 surface_point{ (float)w[0], (float)w[1], (float)w[2] };
+			Ray ray;
+			ray.O   = surface_point + normal * (float)1e-8;
+			ray.D   = -normal;
+			ray.t   = 1e30f;
+			ray.u = ray.v = 0;
+			ray.hit = 0;
+			if (use_bvh) {
+				tlas.intersect(ray);
+			} else {
+				ray.rD = { 1.0f / ray.D.x, 1.0f / ray.D.y, 1.0f / ray.D.z };
+				for (unsigned b = 0; b < blas.size(); ++b)
+					for (unsigned t = 0; t < blas[b].tri.size(); ++t)
+						intersect_triangle(ray, blas[b].tri[t], (b << 20) + t);
+			}
+			if (ray.t < cs.include_margin && ray.t > 0.0f) {
+				double bary[3]   = { (double)(1 - ray.u - ray.v), (double)ray.u, (double)ray.v };
+				unsigned tri_idx = ray.hit & 0xFFFFF, blas_idx = ray.hit >> 20;
+				const Surface &s = *blas[blas_idx].surface;
+				const int *f     = &s.face_idx[s.face_first[tri_idx]];
+				double raw       = bary[0] * s.e[f[0]];
+				raw += bary[1] * s.e[f[1]];
+				raw += bary[2] * s.e[f[2]];
+				pressure += cs.surface_weight[i][j0] * raw;
+			}
+		}
+		out[i] = (float)pressure;
+	}
+}
+
 } // namespace orc

@@ -135,6 +135,31 @@ def test_c5_grasp_full_resolution_pads(hcs_lib):
     _run_scene(scene, 2, seed=56, hcs_lib=hcs_lib, with_sensors=True)
 
 
+@pytest.mark.parametrize("with_normals", [True, False])
+def test_curved_fingertip_sensor(hcs_lib, with_normals):
+    """CurvedSensor on the soft ubi_tip fingertip (reference taxel layout): sample-to-taxel assignment and the
+    per-taxel weighted ray pressures against the oracle's restatement of curved_sensor.cpp."""
+    scene = scenes.fingertip(with_normals=with_normals)
+    n_envs = 12
+    eng, orc = make_engine(scene, n_envs), make_oracle(scene)
+    n_tax, n_rays, n_assign = eng.curved_info(0)
+    assert (n_rays, n_assign) == orc.curved_info(0) and n_tax == 12 and n_rays > 500
+    xpos, xmat, vel = scene.poses(n_envs, seed=9)
+    eng.step(xpos, xmat, vel, with_sensors=True)
+    vals = eng.curved_values(0)
+    res = eng.pair_results()
+    touched = 0
+    for e in range(n_envs):
+        ref_pairs, _ = oracle_env(orc, scene, xpos[e], xmat[e], vel[e], sensors=False)
+        compare_env(res[e], [eng.emitted(e, 0)], ref_pairs)
+        ref = orc.curved_values(0)
+        err, nbad = compare_images(vals[e], ref)
+        assert nbad == 0, "curved sensor: %d taxels beyond %.0e (max rel err %.3e)" % (nbad, TAXEL_RTOL, err)
+        touched += int((ref > 0).sum())
+    assert touched >= n_envs, "the taxels barely respond: the test would be vacuous"
+    eng.close()
+
+
 @pytest.mark.parametrize("triangle", [False, True])
 def test_mixed_shapes_every_mesh_family(hcs_lib, triangle):
     """Soft MA cylinders (segment and disc regimes), soft grid box, soft MA cube, rigid box / sphere / ellipsoid /

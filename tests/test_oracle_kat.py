@@ -395,3 +395,43 @@ def test_flat_sensor_zero_without_contact_and_window_weights():
     # gaussian window: every weight <= 1, so each taxel is attenuated by the same factor (uniform pressure)
     ratio = g[4:12, 4:12] / plain[4:12, 4:12]
     assert (ratio < 1).all() and np.allclose(ratio, ratio[0, 0], rtol=1e-5)
+
+
+def test_curved_sensor_assignment_weights_and_flat_press():
+    """CurvedSensor (curved_sensor.cpp): samples within include_margin of a taxel (and within 45 degrees of its
+    normal) are assigned with weight (margin - distance)^2; under a flat press of depth d every ray that starts on
+    the foam's top face inside the contact patch reads p = E d / zs."""
+    s = OracleScene(triangle_representation=True)
+    box = s.add_geom(GEOM_BOX, [0.1, 0.1, 0.1], [0, 1, 0.05, 0.3, 0.3])
+    foam = s.add_geom(GEOM_BOX, [0.2, 0.2, 0.02], [5e4, 5, 0, 0.3, 0.3])
+    s.set_pairs([[box, foam]])
+    margin = 0.005
+    # (positions off the mesh's symmetry axes: a ray that starts exactly above a triangle edge can slip between the two
+    # float32 Moeller-Trumbore tests, in the reference as well)
+    taxels = np.array([[0.0113, 0.0071, 0.02], [0.0513, 0.0037, 0.02], [0.19, 0.19, 0.02]])  # third: outside the patch
+    normals = np.array([[0, 0, 1.0], [0, 0, 1.0], [0, 0, 1.0]])
+    offs = np.array([[0, 0], [0.001, 0], [0, 0.002], [-0.003, 0], [0.0, -0.0045], [0.004, 0.004]])  # last: 5.66 mm away
+    offs = offs + 1e-6 * np.array([[0.3, 0.7]])  # every sample a hair off the taxel: distances stay as listed to 1e-3
+    samples = np.concatenate([np.c_[t[0] + offs[:, 0], t[1] + offs[:, 1], np.full(len(offs), 0.02)] for t in taxels])
+    snorm = np.tile([0, 0, 1.0], (len(samples), 1))
+    snorm[1] = [0, 1, 0]  # 90 degrees off the taxel normal: rejected by the 45 degree test
+    cs = s.add_curved_sensor(foam, taxels, normals, samples, snorm, margin)
+    n_close, n_assign = s.curved_info(cs)
+    assert (n_close, n_assign) == (3 * 5 - 1, 3 * 5 - 1)
+    depth = 0.002
+    s.step(np.array([[0, 0, 0.053 - depth + 0.1], [0, 0, 0.033]]), np.stack([I3, I3]))
+    v = s.curved_values(cs)
+    p = 5e4 * depth / 0.02
+    d = np.linalg.norm(offs[:5], axis=1)
+    w = (margin - d) ** 2
+    assert np.isclose(v[0], p * (w.sum() - w[1]), rtol=1e-5)   # sample 1 of taxel 0 was rejected
+    assert np.isclose(v[1], p * w.sum(), rtol=1e-5)
+    assert v[2] == 0                                            # no contact under that taxel
+    assert np.allclose(v, s.curved_values(cs, use_bvh=False), rtol=1e-6)
+    # without taxel normals the 45 degree test is off
+    s2 = OracleScene(triangle_representation=True)
+    b2 = s2.add_geom(GEOM_BOX, [0.1, 0.1, 0.1], [0, 1, 0.05, 0.3, 0.3])
+    f2 = s2.add_geom(GEOM_BOX, [0.2, 0.2, 0.02], [5e4, 5, 0, 0.3, 0.3])
+    s2.set_pairs([[b2, f2]])
+    c2 = s2.add_curved_sensor(f2, taxels, None, samples, snorm, margin)
+    assert s2.curved_info(c2) == (15, 15)

@@ -81,3 +81,28 @@ def test_adapter_sphere_on_box_and_myrmex_match_the_oracle(plugin_built):
     q = np.array(r["qfrc_passive"])
     assert np.allclose(q[:3], w[:3], rtol=1e-8)
     assert np.allclose(q[3:6], w[3:] - np.cross(xpos[0], w[:3]), rtol=1e-8, atol=1e-10)
+
+
+@pytest.mark.gpu
+def test_adapter_curved_sensor_matches_the_oracle(plugin_built):
+    """CurvedSensor adapter class on a soft convex-mesh tip: the samples it drew go to the oracle unchanged."""
+    r = _run(plugin_built)["curved_tip"]
+    I3 = np.eye(3).reshape(-1)
+    GEOM_MESH = 7
+    o = OracleScene(triangle_representation=True)
+    box = o.add_geom(GEOM_BOX, [0.025] * 3, [0, 1.0, 0.01, 0.0, 0.0])
+    mv = np.array(r["mesh_vert"], dtype=np.float32).reshape(-1, 3)
+    mf = np.array(r["mesh_face"], dtype=np.int32).reshape(-1, 3)
+    tip = o.add_geom(GEOM_MESH, [0, 0, 0], [5e4, 5.0, 0.0, 0.0, 0.0], mv, mf)
+    o.set_pairs([[box, tip]])
+    taxels = np.array(r["taxels"]).reshape(-1, 3)
+    cs = o.add_curved_sensor(tip, taxels, np.array(r["normals"]).reshape(-1, 3), np.array(r["sample_pos"]).reshape(-1, 3),
+                             np.array(r["sample_nrm"]).reshape(-1, 3), 0.006)
+    assert len(taxels) == 5 and len(r["sample_pos"]) // 3 > 300 and o.curved_info(cs)[0] > 50
+    o.step(np.array([[0, 0, 0.025], r["tip_pos"]]), np.stack([I3, np.array(r["tip_mat"])]))
+    assert o.pair_result(0)["n_polygons"] > 0
+    ref = o.curved_values(cs)
+    val = np.array(r["values"], dtype=np.float32)
+    assert r["publishes"] == 1 and ref.max() > 0 and ref[4] == 0  # the taxel on the far side feels nothing
+    err = np.abs(val - ref) / np.maximum(np.abs(ref), 1e-3 * ref.max())
+    assert err.max() < 1e-6
