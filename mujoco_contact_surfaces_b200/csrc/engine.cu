@@ -69,6 +69,16 @@ struct CurvedHost {
 	float *h_values = nullptr; // pinned [n_env][n_taxels]
 };
 
+// TaxelSensor::load (SENS/src/taxel_sensor.cpp:45-156), sample_method "default"
+struct TaxelHost {
+	int geom, method, visualize;
+	double include_margin, sample_resolution;
+	std::vector<double> taxel_pos; // [n][3] geom frame
+	int n_taxels() const { return (int)taxel_pos.size() / 3; }
+	TaxelDev dev{};
+	float *h_values = nullptr; // pinned [n_env][n_taxels]
+};
+
 } // namespace hcs
 
 using namespace hcs;
@@ -84,6 +94,7 @@ struct hcs_ctx {
 	std::vector<PairDesc> pair_desc;
 	std::vector<SensorHost> sensors;
 	std::vector<CurvedHost> curved;
+	std::vector<TaxelHost> taxel;
 	std::vector<void *> step_allocs;
 	PairDesc *d_pairs = nullptr;
 	std::vector<SensorDev> sensor_dev; // device records of all sensors, host copy + device copy
@@ -373,6 +384,9 @@ static bool is_sensor_geom(const hcs_ctx *c, int g)
 	for (const CurvedHost &s : c->curved)
 		if (s.geom == g)
 			return true;
+	for (const TaxelHost &s : c->taxel)
+		if (s.geom == g)
+			return true;
 	return false;
 }
 
@@ -601,6 +615,11 @@ static void release_step_buffers(hcs_ctx *c)
 			cudaFreeHost(s.h_values);
 			s.h_values = nullptr;
 		}
+	for (TaxelHost &s : c->taxel)
+		if (s.h_values) {
+			cudaFreeHost(s.h_values);
+			s.h_values = nullptr;
+		}
 	if (c->h_pair)
 		cudaFreeHost(c->h_pair), c->h_pair = nullptr;
 	if (c->h_wrench)
@@ -652,6 +671,30 @@ static void finalize(hcs_ctx *c)
 	}
 	for (CurvedHost &ch : c->curved)
 		build_curved(c, ch, io.max_tris);
+	io.tri_vd = nullptr;
+	if (!c->taxel.empty() && io.max_tris > 0)
+		io.tri_vd = dalloc<double>(c->step_allocs, (size_t)9 * io.max_tris);
+	for (TaxelHost &th : c->taxel) {
+		const int nt = th.n_taxels();
+		TaxelDev d{};
+		d.geom = th.geom, d.n_taxels = nt, d.method = th.method, d.visualize = th.visualize;
+		d.include_margin = th.include_margin, d.sample_resolution = th.sample_resolution;
+		d.taxel_pos   = upload(c, th.taxel_pos);
+		size_t ncell  = (size_t)n_env * nt;
+		d.values      = dalloc<float>(c->step_allocs, ncell);
+		d.env_tris    = dalloc<int32_t>(c->step_allocs, n_env);
+		d.bin_count   = dalloc<int32_t>(c->step_allocs, ncell);
+		d.bin_offset  = dalloc<int32_t>(c->step_allocs, ncell + 1);
+		d.bin_cursor  = dalloc<int32_t>(c->step_allocs, ncell);
+		d.scan_tmp    = dalloc<int32_t>(c->step_allocs, ncell / 1024 + 2);
+		size_t cap    = std::min<size_t>(std::max<size_t>(16 * (size_t)io.max_tris, 32 * ncell), (size_t)1 << 30);
+		d.items_cap   = (int)cap;
+		d.bin_items   = dalloc<int32_t>(c->step_allocs, cap);
+		CK(cudaMemsetAsync(d.values, 0, std::max<size_t>(ncell, 1) * sizeof(float), c->stream)); // channel.values.resize(n)
+		CK(cudaMallocHost((void **)&th.h_values, std::max<size_t>(ncell, 1) * sizeof(float)));
+		memset(th.h_values, 0, std::max<size_t>(ncell, 1) * sizeof(float));
+		th.dev = d;
+	}
 	c->sensor_dev.clear();
 	for (SensorHost &sh : c->sensors)
 		c->sensor_dev.push_back(sh.dev);
@@ -713,6 +756,8 @@ static void step_device(hcs_ctx *c, const double *xpos, const double *xmat, cons
 		k += launch_tactile(c->sensor_dev.data(), c->d_sensors, (int)c->sensor_dev.size(), io, c->d_pairs, s);
 		for (CurvedHost &ch : c->curved)
 			k += launch_curved(ch.dev, io, c->d_pairs, s);
+		for (TaxelHost &th : c->taxel)
+			k += launch_taxel(th.dev, io, c->d_pairs, s);
 	}
 	if (prof)
 		CK(cudaEventRecord(c->ev[5], s));
@@ -735,6 +780,10 @@ static void fetch(hcs_ctx *c, int with_sensors)
 	if (with_sensors)
 		for (CurvedHost &ch : c->curved)
 			CK(cudaMemcpyAsync(ch.h_values, ch.dev.values, (size_t)n_env * ch.n_taxels() * sizeof(float),
+			                   cudaMemcpyDeviceToHost, s));
+	if (with_sensors)
+		for (TaxelHost &th : c->taxel)
+			CK(cudaMemcpyAsync(th.h_values, th.dev.values, (size_t)n_env * th.n_taxels() * sizeof(float),
 			                   cudaMemcpyDeviceToHost, s));
 	CK(cudaStreamSynchronize(s));
 	c->results_on_host = true;
@@ -1089,6 +1138,49 @@ const float *hcs_device_curved_values(hcs_ctx *c, int sensor)
 	if (!c || !c->finalized || sensor < 0 || sensor >= (int)c->curved.size())
 		return nullptr;
 	return c->curved[sensor].dev.values;
+}
+
+int hcs_add_taxel_sensor(hcs_ctx *c, int geom, int n_taxels, const double *taxel_pos, double include_margin,
+                         double sample_resolution, int method, int visualize)
+{
+	API_BEGIN(c)
+	if (geom < 0 || geom >= (int)c->geoms.size() || n_taxels < 1 || !taxel_pos || !(include_margin > 0) ||
+	    !(sample_resolution > 0) || method < 0 || method > 3) {
+		c->err = "hcs_add_taxel_sensor: needs a geom, >= 1 taxel, include_margin > 0, sample_resolution > 0, method in 0..3";
+		return HCS_E_INVALID;
+	}
+	TaxelHost s{};
+	s.geom = geom, s.method = method, s.visualize = visualize != 0;
+	s.include_margin = include_margin, s.sample_resolution = sample_resolution;
+	s.taxel_pos.assign(taxel_pos, taxel_pos + 3 * (size_t)n_taxels);
+	c->taxel.push_back(std::move(s));
+	c->finalized = false;
+	return (int)c->taxel.size() - 1;
+	API_END(c)
+}
+
+int hcs_get_taxel_values(hcs_ctx *c, int sensor, float *out)
+{
+	API_BEGIN(c)
+	if (!c->finalized || !out || sensor < 0 || sensor >= (int)c->taxel.size())
+		return HCS_E_INVALID;
+	if (!c->last_with_sensors) {
+		c->err = "hcs_get_taxel_values: the last step ran with with_sensors == 0";
+		return HCS_E_INVALID;
+	}
+	if (!c->sensors_on_host)
+		fetch(c, 1);
+	TaxelHost &s = c->taxel[sensor];
+	memcpy(out, s.h_values, (size_t)c->cfg.n_envs * s.n_taxels() * sizeof(float));
+	return HCS_OK;
+	API_END(c)
+}
+
+const float *hcs_device_taxel_values(hcs_ctx *c, int sensor)
+{
+	if (!c || !c->finalized || sensor < 0 || sensor >= (int)c->taxel.size())
+		return nullptr;
+	return c->taxel[sensor].dev.values;
 }
 
 int hcs_sensor_dims(const hcs_ctx *c, int sensor, int *cx, int *cy)

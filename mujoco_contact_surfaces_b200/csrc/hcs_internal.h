@@ -118,6 +118,8 @@ struct StepIO {
 	TactileTri *tri_pool;
 	int32_t *tri_count;
 	int max_tris;
+	double *tri_vd;            // [max_tris][9] the same triangles' world vertices in double, or NULL (only taxel
+	                           // sensors need them: their sample lattice is evaluated in double)
 	hcs_pair_result *pair_out; // [n_env][n_pairs]
 	double *geom_wrench;       // [n_env][n_geoms][6]
 };
@@ -158,6 +160,19 @@ struct CurvedDev {
 	int items_cap;
 };
 
+// TaxelSensor (SENS/src/taxel_sensor.cpp, sample_method "default"): a barycentric lattice of samples on every
+// contact-surface triangle, taxel values from the samples within include_margin.  Triangles are binned per
+// (env, taxel); one warp per (env, taxel) walks its bin in a canonical order.
+struct TaxelDev {
+	int geom, n_taxels, method, visualize; // method: 0 closest 1 weighted 2 mean 3 squared (:79-91)
+	double include_margin, sample_resolution;
+	const double *taxel_pos; // [n_taxels][3] geom frame
+	float *values;           // [n_env][n_taxels]; persistent: taxels without a sample in range keep their value
+	int32_t *env_tris;       // [n_env] triangles of this sensor's contact surfaces (0: the message is zeroed)
+	int32_t *bin_count, *bin_offset, *bin_cursor, *bin_items, *scan_tmp; // per (env, taxel) triangle bins
+	int items_cap;
+};
+
 // ---- launchers (definitions in the .cu files) ---------------------------------------------------
 void launch_build_tets(const GeomDev &g, cudaStream_t s);
 void launch_build_tris(const GeomDev &g, cudaStream_t s);
@@ -176,5 +191,6 @@ int launch_finalize(const PairDesc *d_pairs, const StepIO &io, int max_list_slic
 int launch_tactile(const SensorDev *sensors, const SensorDev *d_sensors, int n_sensors, const StepIO &io,
                    const PairDesc *d_pairs, cudaStream_t s);
 int launch_curved(const CurvedDev &cd, const StepIO &io, const PairDesc *d_pairs, cudaStream_t s);
+int launch_taxel(const TaxelDev &td, const StepIO &io, const PairDesc *d_pairs, cudaStream_t s);
 
 } // namespace hcs

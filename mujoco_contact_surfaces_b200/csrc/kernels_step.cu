@@ -423,6 +423,11 @@ __device__ __forceinline__ void emit_tactile(int n_faces, Poly P, PressTile e, D
 				t.pair_slice = ((unsigned)c.pair << TRI_SLICE_BITS) | (unsigned)slice;
 				t.idx8       = (unsigned)index * 8u + (unsigned)i;
 				io.tri_pool[pos] = t;
+				if (io.tri_vd) { // taxel sensors sample the triangle in double
+					double *vd = io.tri_vd + 9 * (size_t)pos;
+					vd[0] = v0.x, vd[1] = v0.y, vd[2] = v0.z, vd[3] = v1.x, vd[4] = v1.y, vd[5] = v1.z;
+					vd[6] = cW.x, vd[7] = cW.y, vd[8] = cW.z;
+				}
 			} else {
 				atomicOr(io.flags, 2);
 			}

@@ -646,4 +646,183 @@ int launch_curved(const CurvedDev &cd, const StepIO &io, const PairDesc *d_pairs
 	return 8;
 }
 
+// =====================================================================================================
+// K10 taxel sensor (TaxelSensor::internal_update, SENS/src/taxel_sensor.cpp:158-478, sample_method "default").
+// The reference samples every contact-surface triangle on a barycentric lattice, builds the dense taxel x sample
+// distance matrix and loops over it per taxel.  Here triangles are binned per (env, taxel) by their box grown by
+// include_margin; one warp per (env, taxel) walks its bin in a canonical triangle order, each lane regenerating its
+// triangles' samples with the reference's double arithmetic.  Quirk Q12 is reproduced: weighted / mean fall
+// through to squared, closest keeps the pressure only with visualize, taxels without a sample in range keep their
+// previous value, an update without any sample zeroes the message.
+// =====================================================================================================
+__global__ void taxel_clear_kernel(TaxelDev td, int n_cells, int n_env)
+{
+	int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < n_cells) {
+		td.bin_count[i]  = 0;
+		td.bin_cursor[i] = 0;
+	}
+	if (i < n_env)
+		td.env_tris[i] = 0;
+}
+
+__device__ __forceinline__ void taxel_world(const TaxelDev &td, const double *R, const double *xp, int i, double tw[3])
+{
+	const double *t = td.taxel_pos + 3 * (size_t)i; // M * (t, 1), taxel_sensor.cpp:273-280
+#pragma unroll
+	for (int r = 0; r < 3; ++r)
+		tw[r] = R[3 * r] * t[0] + R[3 * r + 1] * t[1] + R[3 * r + 2] * t[2] + xp[r];
+}
+
+template <bool FILL>
+__global__ void __launch_bounds__(256) taxel_bin_kernel(TaxelDev td, StepIO io, const PairDesc *pairs)
+{
+	const int n = min(*io.tri_count, io.max_tris);
+	for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+		const TactileTri &t = io.tri_pool[i];
+		const PairDesc &P   = pairs[t.pair_slice >> TRI_SLICE_BITS];
+		if (P.gM != td.geom && P.gN != td.geom)
+			continue;
+		const int env = t.env;
+		if (!FILL)
+			atomicAdd(td.env_tris + env, 1);
+		const double *vd = io.tri_vd + 9 * (size_t)i;
+		const double m   = td.include_margin * (1 + 1e-9) + 1e-12; // every sample lies inside the triangle's box
+		double lo[3], hi[3];
+#pragma unroll
+		for (int a = 0; a < 3; ++a) {
+			lo[a] = fmin(fmin(vd[a], vd[3 + a]), vd[6 + a]) - m;
+			hi[a] = fmax(fmax(vd[a], vd[3 + a]), vd[6 + a]) + m;
+		}
+		const double *R  = io.xmat + ((size_t)env * io.n_geoms + td.geom) * 9;
+		const double *xp = io.xpos + ((size_t)env * io.n_geoms + td.geom) * 3;
+		for (int k = 0; k < td.n_taxels; ++k) {
+			double tw[3];
+			taxel_world(td, R, xp, k, tw);
+			if (tw[0] < lo[0] || tw[0] > hi[0] || tw[1] < lo[1] || tw[1] > hi[1] || tw[2] < lo[2] || tw[2] > hi[2])
+				continue;
+			int cell = env * td.n_taxels + k;
+			if (!FILL) {
+				atomicAdd(td.bin_count + cell, 1);
+			} else {
+				int slot = td.bin_offset[cell] + atomicAdd(td.bin_cursor + cell, 1);
+				if (slot < td.items_cap)
+					td.bin_items[slot] = i;
+				else
+					atomicOr(io.flags, 4);
+			}
+		}
+	}
+}
+
+constexpr int TAXEL_RANK_MAX = 256;
+__global__ void __launch_bounds__(128) taxel_gather_kernel(TaxelDev td, StepIO io)
+{
+	__shared__ int order_s[4][TAXEL_RANK_MAX];
+	const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	const long unit = (long)blockIdx.x * 4 + wib;
+	if (unit >= (long)io.n_env * td.n_taxels)
+		return;
+	const int env = (int)(unit / td.n_taxels), taxel = (int)(unit - (long)env * td.n_taxels);
+	float *out = td.values + unit;
+	if (td.env_tris[env] == 0) { // no sample at all: the message is zeroed (:455-477)
+		if (lane == 0)
+			*out = 0.0f;
+		return;
+	}
+	const int first = td.bin_offset[unit];
+	const int n     = min(td.bin_count[unit], max(td.items_cap - first, 0));
+	if (n == 0)
+		return; // no sample in range: the previous value stays
+	const int32_t *items = td.bin_items + first;
+	int *order           = order_s[wib];
+	const bool ranked    = n <= TAXEL_RANK_MAX;
+	if (ranked) { // canonical order of the bin: by the triangles' (pair, slice, index, fan triangle) key
+		for (int k = lane; k < n; k += 32) {
+			const TactileTri &t = io.tri_pool[items[k]];
+			int r = 0;
+			for (int k2 = 0; k2 < n; ++k2) {
+				const TactileTri &o = io.tri_pool[items[k2]];
+				r += (o.pair_slice < t.pair_slice) || (o.pair_slice == t.pair_slice && o.idx8 < t.idx8);
+			}
+			order[r] = items[k];
+		}
+		__syncwarp();
+	}
+	const double *R  = io.xmat + ((size_t)env * io.n_geoms + td.geom) * 9;
+	const double *xp = io.xpos + ((size_t)env * io.n_geoms + td.geom) * 3;
+	double tw[3];
+	taxel_world(td, R, xp, taxel, tw);
+	const double tsq = tw[0] * tw[0] + tw[1] * tw[1] + tw[2] * tw[2];
+	const double margin = td.include_margin, margin_sq = margin * margin, res = td.sample_resolution;
+	double pressure = 0, dmin = 1e300, pmin = 0;
+	int ws = 0, kmin = 0x7fffffff;
+	for (int k = lane; k < n; k += 32) {
+		const int item      = ranked ? order[k] : items[k];
+		const TactileTri &t = io.tri_pool[item];
+		const double *v     = io.tri_vd + 9 * (size_t)item;
+		double e10 = sqrt((v[3] - v[0]) * (v[3] - v[0]) + (v[4] - v[1]) * (v[4] - v[1]) + (v[5] - v[2]) * (v[5] - v[2]));
+		double e20 = sqrt((v[6] - v[0]) * (v[6] - v[0]) + (v[7] - v[1]) * (v[7] - v[1]) + (v[8] - v[2]) * (v[8] - v[2]));
+		int st0 = (int)(e10 / res) + 1, st1 = (int)(e20 / res) + 1, st2 = st1; // :191-194 (st2 repeats st1)
+		int stm = max(st0, st1);
+		const double da = 1. / stm, db = 1. / st2;
+		for (double a = 0; a <= 1; a += da)
+			for (double b = 0; b <= 1; b += db) {
+				double b0 = a, b1 = (1 - a) * (1 - b), b2 = (1 - a) * b;
+				double p[3];
+#pragma unroll
+				for (int c = 0; c < 3; ++c)
+					p[c] = b0 * v[c] + b1 * v[3 + c] + b2 * v[6 + c];
+				double dj = (-2 * (tw[0] * p[0] + tw[1] * p[1] + tw[2] * p[2]) + tsq) + (p[0] * p[0] + p[1] * p[1] + p[2] * p[2]);
+				double pj = b0 * t.e[0] + b1 * t.e[1] + b2 * t.e[2];
+				if (td.method == 0) {
+					if (dj < dmin) // first minimum in (triangle order, sample order)
+						dmin = dj, pmin = pj, kmin = k;
+				} else if (dj < margin_sq) {
+					double w = fmax(0.0, margin - sqrt(dj));
+					pressure += (w * w) * fabs(pj);
+					ws += 1;
+				}
+			}
+	}
+	if (td.method == 0) {
+#pragma unroll
+		for (int o = 16; o > 0; o >>= 1) {
+			double d2 = __shfl_xor_sync(0xffffffffu, dmin, o), p2 = __shfl_xor_sync(0xffffffffu, pmin, o);
+			int k2 = __shfl_xor_sync(0xffffffffu, kmin, o);
+			if (d2 < dmin || (d2 == dmin && k2 < kmin))
+				dmin = d2, pmin = p2, kmin = k2;
+		}
+		if (lane == 0 && dmin < margin_sq)
+			*out = (td.visualize && fabs(pmin) > 1e-6) ? (float)pmin : 0.0f; // :312-328
+		return;
+	}
+#pragma unroll
+	for (int o = 16; o > 0; o >>= 1) {
+		pressure += __shfl_xor_sync(0xffffffffu, pressure, o);
+		ws += __shfl_xor_sync(0xffffffffu, ws, o);
+	}
+	if (lane == 0 && ws > 0)
+		*out = (float)(pressure * res); // :409-412
+}
+
+int launch_taxel(const TaxelDev &td, const StepIO &io, const PairDesc *d_pairs, cudaStream_t s)
+{
+	const int ncell = io.n_env * td.n_taxels;
+	if (ncell <= 0)
+		return 0;
+	const int n_tiles = (ncell + SCAN_TILE - 1) / SCAN_TILE;
+	const int tgrid   = (int)std::max<long>(1, std::min<long>(((long)io.max_tris + 255) / 256, (long)io.n_sms * 8));
+	taxel_clear_kernel<<<(std::max(ncell, io.n_env) + 255) / 256, 256, 0, s>>>(td, ncell, io.n_env);
+	if (io.max_tris > 0 && io.tri_vd)
+		taxel_bin_kernel<false><<<tgrid, 256, 0, s>>>(td, io, d_pairs);
+	scan_tiles_kernel<<<n_tiles, 256, 0, s>>>(td.bin_count, td.bin_offset, td.scan_tmp, ncell);
+	scan_sums_kernel<<<1, 1024, 0, s>>>(td.scan_tmp, n_tiles, td.bin_offset + ncell);
+	scan_add_kernel<<<n_tiles, 256, 0, s>>>(td.bin_offset, td.scan_tmp, ncell);
+	if (io.max_tris > 0 && io.tri_vd)
+		taxel_bin_kernel<true><<<tgrid, 256, 0, s>>>(td, io, d_pairs);
+	taxel_gather_kernel<<<(ncell + 3) / 4, 128, 0, s>>>(td, io);
+	return 7;
+}
+
 } // namespace hcs

@@ -42,6 +42,7 @@ ABI_SYMBOLS = [
     "hcs_device_sensor_image", "hcs_get_faces", "hcs_get_emitted", "hcs_get_tactile_triangles", "hcs_geom_info",
     "hcs_get_mesh", "hcs_get_lbvh", "hcs_get_counters", "hcs_set_profiling", "hcs_get_stage_ms", "hcs_version",
     "hcs_add_curved_sensor", "hcs_curved_sensor_info", "hcs_get_curved_values", "hcs_device_curved_values",
+    "hcs_add_taxel_sensor", "hcs_get_taxel_values", "hcs_device_taxel_values",
 ]
 
 _LIB = None
@@ -67,8 +68,11 @@ def load_library():
         L.hcs_destroy.restype = None
         L.hcs_destroy.argtypes = [C.c_void_p]
         for name in ("hcs_device_pair_results", "hcs_device_geom_wrenches", "hcs_device_sensor_image",
-                     "hcs_device_curved_values"):
+                     "hcs_device_curved_values", "hcs_device_taxel_values"):
             getattr(L, name).restype = C.c_void_p
+        L.hcs_device_taxel_values.argtypes = [C.c_void_p, C.c_int]
+        L.hcs_add_taxel_sensor.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_double, C.c_double, C.c_int,
+                                           C.c_int]
         L.hcs_device_curved_values.argtypes = [C.c_void_p, C.c_int]
         L.hcs_add_curved_sensor.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p,
                                             C.c_void_p, C.c_double]
@@ -221,6 +225,22 @@ class HydroelasticEngine:
             self.curved = []
         self.curved.append(len(tp))
         return s
+
+    def add_taxel_sensor(self, geom, taxel_pos, include_margin, sample_resolution, method="squared", visualize=False):
+        """TaxelSensor (sample_method "default"); method: closest | weighted | mean | squared."""
+        tp = _f64(taxel_pos).reshape(-1, 3)
+        code = {"closest": 0, "weighted": 1, "mean": 2, "squared": 3}[method]
+        s = self._check(self.L.hcs_add_taxel_sensor(self.h, int(geom), len(tp), tp.ctypes.data, float(include_margin),
+                                                    float(sample_resolution), code, int(visualize)))
+        if not hasattr(self, "taxel"):
+            self.taxel = []
+        self.taxel.append(len(tp))
+        return s
+
+    def taxel_values(self, sensor):
+        out = np.zeros((self.n_envs, self.taxel[sensor]), dtype=np.float32)
+        self._check(self.L.hcs_get_taxel_values(self.h, int(sensor), _ptr(out, C.c_float)))
+        return out
 
     def curved_info(self, sensor):
         a, b, c = C.c_int(), C.c_int(), C.c_int()

@@ -619,5 +619,50 @@ void CurvedSensor::internal_update(const mjModel *, mjData *, const std::vector<
 	hcs_get_curved_values(owner_->context(), sensor_index_, tactile_state_values_.data());
 }
 
+// taxel_sensor.cpp:45-156
+bool TaxelSensor::load(const mjModel *m, mjData *d)
+{
+	const PluginConfig &c = rosparam_config_;
+	if (!(TactileSensorBase::load(m, d) && has(c, "taxels") && has(c, "method") && has(c, "include_margin") &&
+	      has(c, "sample_resolution")) ||
+	    !owner_ || !owner_->context())
+		return false;
+	include_margin    = std::atof(c.at("include_margin").c_str());
+	sample_resolution = std::atof(c.at("sample_resolution").c_str());
+	if (has(c, "sample_method") && c.at("sample_method") != "default") {
+		std::fprintf(stderr, "[mujoco_contact_surface_sensors] TaxelSensor '%s': sample_method '%s' is not offered "
+		                     "(only 'default')\n", sensorName.c_str(), c.at("sample_method").c_str());
+		return false;
+	}
+	const std::string &ms = c.at("method");
+	int method = ms == "closest" ? 0 : ms == "weighted" ? 1 : ms == "mean" ? 2 : ms == "squared" ? 3 : -1;
+	if (method < 0)
+		return false;
+	taxel_pos_ = parse_numbers(c.at("taxels"));
+	if (taxel_pos_.empty() || taxel_pos_.size() % 3 != 0)
+		return false;
+	int cfg_idx = owner_->configIndex(geomID);
+	if (cfg_idx < 0)
+		return false;
+	sensor_index_ = hcs_add_taxel_sensor(owner_->context(), cfg_idx, (int)taxel_pos_.size() / 3, taxel_pos_.data(),
+	                                     include_margin, sample_resolution, method, visualize ? 1 : 0);
+	if (sensor_index_ < 0) {
+		std::fprintf(stderr, "[mujoco_contact_surface_sensors] %s\n", hcs_last_error(owner_->context()));
+		return false;
+	}
+	tactile_state_values_.assign(taxel_pos_.size() / 3, 0.0f);
+	return true;
+}
+
+// taxel_sensor.cpp:158-478, computed on the GPU by the taxel-sensor kernels
+void TaxelSensor::internal_update(const mjModel *, mjData *, const std::vector<GeomCollisionPtr> &)
+{
+	if (!owner_->finalized()) { // no contact pair seen yet: zeros (:455-477)
+		std::fill(tactile_state_values_.begin(), tactile_state_values_.end(), 0.0f);
+		return;
+	}
+	hcs_get_taxel_values(owner_->context(), sensor_index_, tactile_state_values_.data());
+}
+
 } // namespace sensors
 } // namespace mujoco_ros::contact_surfaces

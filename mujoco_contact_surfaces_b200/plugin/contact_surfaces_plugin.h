@@ -265,6 +265,23 @@ private:
 	std::vector<double> taxel_pos_, taxel_nrm_, sample_pos_, sample_nrm_;
 };
 
+// taxel_sensor.h / taxel_sensor.cpp:45-156 (load), :158-478 (internal_update); keys of SENS/config/fingertip.yaml
+// and flat_taxel_sensor.yaml.  sample_method "default" only (see hcs_add_taxel_sensor in include/hcs.h).
+class TaxelSensor : public TactileSensorBase
+{
+public:
+	bool load(const mjModel *m, mjData *d) override;
+
+protected:
+	void internal_update(const mjModel *m, mjData *d, const std::vector<GeomCollisionPtr> &geomCollisions) override;
+
+private:
+	int sensor_index_        = -1;
+	double include_margin    = 0;
+	double sample_resolution = 0;
+	std::vector<double> taxel_pos_;
+};
+
 } // namespace sensors
 } // namespace contact_surfaces
 } // namespace mujoco_ros

@@ -203,6 +203,16 @@ struct CurvedSensor {
 	std::vector<std::vector<double>> surface_weight;
 };
 
+// TaxelSensor (mujoco_contact_surface_sensors/src/taxel_sensor.cpp), sample_method "default" (:173-213): a
+// barycentric lattice on every contact-surface triangle, taxel values from the samples within include_margin.
+struct TaxelSensor {
+	int geom;
+	double include_margin, sample_resolution;
+	int method;      // 0 closest, 1 weighted, 2 mean, 3 squared (:79-91)
+	bool visualize;  // changes the VALUE of the closest method (:312-328), quirk Q12
+	std::vector<V3> taxels; // geom frame
+};
+
 struct PairOut {
 	bool has_surface = false;
 	int gM = -1, gN = -1;
@@ -227,6 +237,7 @@ struct Scene {
 	std::vector<std::array<int, 2>> pairs;
 	std::vector<FlatSensor> sensors;
 	std::vector<CurvedSensor> curved;
+	std::vector<TaxelSensor> taxel;
 	StepState last;
 };
 
@@ -244,6 +255,8 @@ void step(const Scene &sc, StepState &st, const double *xpos, const double *xmat
 void flat_sensor_image(const Scene &sc, const StepState &st, int sensor, float *out, bool use_bvh, bool parallel);
 void curved_sensor_load(CurvedSensor &cs, const double *sample_pos, const double *sample_nrm, int n_samples);
 void curved_sensor_values(const Scene &sc, const StepState &st, int sensor, float *out, bool use_bvh);
+// values: the message of the previous update on entry (taxels without a sample in range keep it), updated in place
+void taxel_sensor_values(const Scene &sc, const StepState &st, int sensor, float *values);
 
 double combined_dissipation(const Geom &a, const Geom &b);
 double combined_friction_dynamic(const Geom &a, const Geom &b);

@@ -33,7 +33,8 @@ def lib():
         for name in ("orc_scene_destroy", "orc_add_geom", "orc_add_raw_soft", "orc_add_raw_rigid", "orc_geom_info",
                      "orc_geom_mesh", "orc_set_pairs", "orc_add_flat_sensor", "orc_sensor_dims", "orc_step",
                      "orc_pair_result", "orc_pair_emitted", "orc_pair_faces", "orc_pair_triangles", "orc_geom_wrench",
-                     "orc_sensor_image", "orc_bench", "orc_add_curved_sensor", "orc_curved_values", "orc_curved_info"):
+                     "orc_sensor_image", "orc_bench", "orc_add_curved_sensor", "orc_curved_values", "orc_curved_info",
+                     "orc_add_taxel_sensor", "orc_taxel_values"):
             getattr(L, name).restype = C.c_int
         _LIB = L
     return _LIB
@@ -144,6 +145,25 @@ class OracleScene:
         d = np.zeros(2, dtype=np.int32)
         self.L.orc_curved_info(self.h, int(sensor), _p(d, C.c_int))
         return int(d[0]), int(d[1])  # close sample points, (taxel, sample) assignments
+
+    def add_taxel_sensor(self, geom, taxel_pos, include_margin, sample_resolution, method="squared", visualize=False):
+        """TaxelSensor::load (sample_method "default"); method: closest | weighted | mean | squared."""
+        tp = _d(taxel_pos).reshape(-1, 3)
+        code = {"closest": 0, "weighted": 1, "mean": 2, "squared": 3}[method]
+        s = self.L.orc_add_taxel_sensor(self.h, int(geom), len(tp), _p(tp, C.c_double), C.c_double(include_margin),
+                                        C.c_double(sample_resolution), code, int(visualize))
+        if not hasattr(self, "taxel_counts"):
+            self.taxel_counts = []
+        self.taxel_counts.append(len(tp))
+        return s
+
+    def taxel_values(self, sensor, previous=None):
+        """One update of the sensor; `previous` = the message of the last update (taxels without a sample in range
+        keep it), zeros when omitted."""
+        out = np.zeros(self.taxel_counts[sensor], dtype=np.float32) if previous is None else \
+            np.array(previous, dtype=np.float32).copy()
+        self.L.orc_taxel_values(self.h, int(sensor), _p(out, C.c_float))
+        return out
 
     def sensor_dims(self, sensor):
         d = np.zeros(2, dtype=np.int32)

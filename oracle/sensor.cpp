@@ -551,4 +551,89 @@ void curved_sensor_values(const Scene &sc, const StepState &st, int sensor, floa
 	}
 }
 
+// taxel_sensor.cpp:158-478 internal_update, DEFAULT sampling.  Reproduced as written, including quirk Q12: the
+// method switch has no breaks (weighted -> mean -> squared: all three end with the squared result), closest keeps
+// the pressure only when visualize is on, st2 is computed from the same edge as st1, and taxels without a sample in
+// range keep the value of the previous update (only "no sample at all" writes zeros).
+void taxel_sensor_values(const Scene &sc, const StepState &st, int sensor, float *values)
+{
+	const TaxelSensor &ts = sc.taxel[sensor];
+	const int id = ts.geom, n = (int)ts.taxels.size();
+	const double margin = ts.include_margin, margin_sq = margin * margin, res = ts.sample_resolution;
+	std::vector<V3> spoints;
+	std::vector<double> spress; // s->tri_e_MN().Evaluate(t, bary) of each sample
+	for (const PairOut &po : st.out) {
+		if (!(po.has_surface && (po.gM == id || po.gN == id) && po.s->tri))
+			continue;
+		const Surface &s = *po.s;
+		for (int t = 0; t < s.num_faces(); ++t) {
+			const int *f = &s.face_idx[s.face_first[t]];
+			const V3 &v0 = s.v[f[0]], &v1 = s.v[f[1]], &v2 = s.v[f[2]];
+			auto norm = [](const V3 &a, const V3 &b) {
+				double d0 = a[0] - b[0], d1 = a[1] - b[1], d2 = a[2] - b[2];
+				return std::sqrt(d0 * d0 + d1 * d1 + d2 * d2);
+			};
+			int st0 = (int)(norm(v1, v0) / res) + 1;
+			int st1 = (int)(norm(v2, v0) / res) + 1;
+			int st2 = (int)(norm(v2, v0) / res) + 1;
+			int stm = std::max(st0, st1);
+			for (double a = 0; a <= 1; a += 1. / stm)
+				for (double b = 0; b <= 1; b += 1. / st2) {
+					double bary[3] = { a, (1 - a) * (1 - b), (1 - a) * b };
+					V3 p;
+					for (int k = 0; k < 3; ++k)
+						p.at(k) = bary[0] * v0[k] + bary[1] * v1[k] + bary[2] * v2[k];
+					spoints.push_back(p);
+					spress.push_back(bary[0] * s.e[f[0]] + bary[1] * s.e[f[1]] + bary[2] * s.e[f[2]]);
+				}
+		}
+	}
+	const int m = (int)spoints.size();
+	if (m == 0) {
+		std::fill(values, values + n, 0.0f);
+		return;
+	}
+	const double *R = &st.xmat[9 * id], *xp = &st.xpos[3 * id];
+	for (int i = 0; i < n; ++i) {
+		V3 tw;
+		for (int r = 0; r < 3; ++r)
+			tw.at(r) = R[3 * r] * ts.taxels[i][0] + R[3 * r + 1] * ts.taxels[i][1] + R[3 * r + 2] * ts.taxels[i][2] + xp[r];
+		auto dist = [&](int j) { // (-2 t.s + |t|^2) + |s|^2, :286-289
+			const V3 &sp = spoints[j];
+			return (-2 * (tw[0] * sp[0] + tw[1] * sp[1] + tw[2] * sp[2]) + (tw[0] * tw[0] + tw[1] * tw[1] + tw[2] * tw[2])) +
+			       (sp[0] * sp[0] + sp[1] * sp[1] + sp[2] * sp[2]);
+		};
+		if (ts.method == 0) { // closest
+			int jmin = 0;
+			double dmin = dist(0);
+			for (int j = 1; j < m; ++j) {
+				double dj = dist(j);
+				if (dj < dmin)
+					dmin = dj, jmin = j;
+			}
+			if (dmin < margin_sq) {
+				double pressure = spress[jmin];
+				values[i]       = (float)pressure;
+				if (!(ts.visualize && std::abs(pressure) > 1e-6))
+					values[i] = 0;
+			}
+			continue;
+		}
+		// weighted / mean fall through to squared: only its assignment survives
+		double ws = 0, pressure = 0;
+		for (int j = 0; j < m; ++j) {
+			double dj = dist(j);
+			if (dj < margin_sq) {
+				double w = std::pow(std::max(0.0, margin - std::sqrt(dj)), 2);
+				pressure += w * std::abs(spress[j]);
+				ws += 1;
+			}
+		}
+		if (ws > 0) {
+			pressure *= res;
+			values[i] = (float)pressure;
+		}
+	}
+}
+
 } // namespace orc

@@ -160,6 +160,53 @@ def test_curved_fingertip_sensor(hcs_lib, with_normals):
     eng.close()
 
 
+@pytest.mark.parametrize("presser,method,visualize", [("box", "weighted", False), ("spot", "squared", False),
+                                                      ("box", "closest", True), ("box", "closest", False)])
+def test_taxel_sensor_on_the_myrmex_foam(hcs_lib, presser, method, visualize):
+    """TaxelSensor (flat_taxel_sensor.yaml lattice): two consecutive updates with different poses, so that taxels
+    that lose their samples keep the previous value like the reference's message buffer does."""
+    scene = scenes.myrmex_taxels(presser, method, visualize)
+    n_envs = 6
+    eng, orc = make_engine(scene, n_envs), make_oracle(scene)
+    prev = np.zeros((n_envs, 256), dtype=np.float32)
+    moved = 0
+    for seed in (31, 32):
+        xpos, xmat, vel = scene.poses(n_envs, seed=seed)
+        eng.step(xpos, xmat, vel, with_sensors=True)
+        vals = eng.taxel_values(0)
+        for e in range(n_envs):
+            oracle_env(orc, scene, xpos[e], xmat[e], vel[e], sensors=False)
+            ref = orc.taxel_values(0, previous=prev[e])
+            err, nbad = compare_images(vals[e], ref)
+            assert nbad == 0, "taxel sensor: %d taxels beyond %.0e (max rel err %.3e)" % (nbad, TAXEL_RTOL, err)
+            moved += int((ref != prev[e]).sum())
+            prev[e] = ref
+    assert moved > 0 or (method == "closest" and not visualize)  # closest without visualize writes zeros (Q12)
+    eng.close()
+
+
+def test_taxel_sensor_on_the_fingertip(hcs_lib):
+    """SENS/config/fingertip.yaml taxels on the soft ubi_tip mesh (method squared), next to the curved sensor."""
+    scene = scenes.fingertip()
+    scene.taxel_sensors = [dict(geom=1, taxel_pos=scenes._TIP_TAXELS, include_margin=0.006, sample_resolution=0.001,
+                                method="squared")]
+    n_envs = 8
+    eng, orc = make_engine(scene, n_envs), make_oracle(scene)
+    xpos, xmat, vel = scene.poses(n_envs, seed=10)
+    eng.step(xpos, xmat, vel, with_sensors=True)
+    vals, cvals = eng.taxel_values(0), eng.curved_values(0)
+    hit = 0
+    for e in range(n_envs):
+        oracle_env(orc, scene, xpos[e], xmat[e], vel[e], sensors=False)
+        ref = orc.taxel_values(0)
+        err, nbad = compare_images(vals[e], ref)
+        assert nbad == 0, "taxel sensor: %d taxels beyond %.0e (max rel err %.3e)" % (nbad, TAXEL_RTOL, err)
+        assert compare_images(cvals[e], orc.curved_values(0))[1] == 0
+        hit += int((ref > 0).sum())
+    assert hit >= n_envs
+    eng.close()
+
+
 @pytest.mark.parametrize("triangle", [False, True])
 def test_mixed_shapes_every_mesh_family(hcs_lib, triangle):
     """Soft MA cylinders (segment and disc regimes), soft grid box, soft MA cube, rigid box / sphere / ellipsoid /

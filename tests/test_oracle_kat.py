@@ -435,3 +435,64 @@ def test_curved_sensor_assignment_weights_and_flat_press():
     s2.set_pairs([[b2, f2]])
     c2 = s2.add_curved_sensor(f2, taxels, None, samples, snorm, margin)
     assert s2.curved_info(c2) == (15, 15)
+
+
+def _taxel_reference(tris, taxel_w, margin, res, method, visualize, previous):
+    """Independent numpy restatement of TaxelSensor::internal_update (default sampling) for one taxel."""
+    pts, prs = [], []
+    for t in tris:
+        v0, v1, v2, e = t[0:3], t[3:6], t[6:9], t[9:12]
+        st0 = int(np.linalg.norm(v1 - v0) / res) + 1
+        st1 = int(np.linalg.norm(v2 - v0) / res) + 1
+        st, st2 = max(st0, st1), st1
+        a = 0.0
+        while a <= 1:
+            b = 0.0
+            while b <= 1:
+                bary = np.array([a, (1 - a) * (1 - b), (1 - a) * b])
+                pts.append(bary[0] * v0 + bary[1] * v1 + bary[2] * v2)
+                prs.append(bary @ e)
+                b += 1. / st2
+            a += 1. / st
+    if not pts:
+        return 0.0
+    pts, prs = np.array(pts), np.array(prs)
+    d2 = ((pts - taxel_w) ** 2).sum(1)
+    if method == "closest":
+        j = d2.argmin()
+        if d2[j] < margin ** 2:
+            return prs[j] if (visualize and abs(prs[j]) > 1e-6) else 0.0
+        return previous
+    sel = d2 < margin ** 2
+    if not sel.any():
+        return previous
+    return res * (((margin - np.sqrt(d2[sel])) ** 2) * np.abs(prs[sel])).sum()
+
+
+def test_taxel_sensor_methods_and_their_quirks():
+    s = OracleScene(triangle_representation=True)
+    box = s.add_geom(GEOM_BOX, [0.1, 0.1, 0.1], [0, 1, 0.05, 0.3, 0.3])
+    foam = s.add_geom(GEOM_BOX, [0.2, 0.2, 0.02], [5e4, 5, 0, 0.3, 0.3])
+    s.set_pairs([[box, foam]])
+    taxels = np.array([[0.013, 0.007, 0.02], [0.09, -0.05, 0.02], [0.19, 0.19, 0.02]])  # the last one is out of reach
+    margin, res = 0.0126, 0.01
+    ids = {m: s.add_taxel_sensor(foam, taxels, margin, res, m, vis)
+           for m, vis in (("weighted", False), ("mean", False), ("squared", False), ("closest", False))}
+    ids["closest_vis"] = s.add_taxel_sensor(foam, taxels, margin, res, "closest", True)
+    R = np.array([[np.cos(0.3), -np.sin(0.3), 0], [np.sin(0.3), np.cos(0.3), 0], [0, 0, 1]])
+    s.step(np.array([[0.01, 0.02, 0.053 - 0.002 + 0.1], [0, 0, 0.033]]), np.stack([R.reshape(-1), I3]))
+    tris = s.pair_triangles(0)
+    assert len(tris) > 10
+    prev = np.array([7.0, 8.0, 9.0], dtype=np.float32)
+    world = taxels + [0, 0, 0.033]
+    out = {k: s.taxel_values(i, previous=prev) for k, i in ids.items()}
+    # the missing breaks: weighted and mean end with the squared result
+    assert np.array_equal(out["weighted"], out["squared"]) and np.array_equal(out["mean"], out["squared"])
+    for k, (m, vis) in {"squared": ("squared", False), "closest": ("closest", False), "closest_vis": ("closest", True)}.items():
+        ref = [_taxel_reference(tris, world[i], margin, res, m, vis, float(prev[i])) for i in range(3)]
+        assert np.allclose(out[k], ref, rtol=1e-6), (k, out[k], ref)
+    assert out["squared"][2] == 9.0 and out["closest"][2] == 9.0      # no sample in range: the old value stays
+    assert out["closest"][0] == 0.0 and out["closest_vis"][0] > 100   # closest keeps the pressure only with visualize
+    # no sample at all: zeros
+    s.step(np.array([[0, 0, 0.5], [0, 0, 0.033]]), np.stack([I3, I3]))
+    assert not s.taxel_values(ids["squared"], previous=prev).any()
