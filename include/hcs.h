@@ -168,7 +168,10 @@ int hcs_finalize(hcs_ctx *ctx);
 /* replaces, for all envs at once: every collision_cb (plugin.cpp:255-318) + evaluateContactSurface
  * (:320-409) + the force loop of passiveCallback (:411-483) + FlatTactileSensor::bvh_update
  * (SENS/src/flat_tactile_sensor.cpp:262-402) when sensors exist and with_sensors != 0.
- * HOST pointers; copies in/out are part of the call (this is the end-to-end entry point). */
+ * HOST pointers; copies in/out are part of the call (this is the end-to-end entry point): poses and velocities
+ * go to the device, the per-geom wrenches (what passiveCallback applies) and, with with_sensors, the sensor
+ * outputs come back before the call returns.  The per-pair results are diagnostics without a counterpart in the
+ * reference: they stay on the device until hcs_get_pair_results / hcs_get_counters / hcs_fetch_results ask. */
 int hcs_step(hcs_ctx *ctx, const double *xpos, const double *xmat, const double *vel, int with_sensors);
 /* same with DEVICE pointers; asynchronous on the context stream, results stay on the GPU */
 int hcs_step_device(hcs_ctx *ctx, const double *d_xpos, const double *d_xmat, const double *d_vel,

@@ -110,7 +110,7 @@ struct hcs_ctx {
 	bool profiling = false;
 	cudaEvent_t ev[8]{};
 	float stage_ms[7]{};
-	bool results_on_host = false, sensors_on_host = false, last_with_sensors = false;
+	bool results_on_host = false, pairs_on_host = false, sensors_on_host = false, last_with_sensors = false;
 };
 
 namespace hcs {
@@ -763,15 +763,19 @@ static void step_device(hcs_ctx *c, const double *xpos, const double *xmat, cons
 		CK(cudaEventRecord(c->ev[5], s));
 	CK(cudaGetLastError());
 	c->kernels_last_step = k;
-	c->results_on_host = c->sensors_on_host = false;
+	c->results_on_host = c->pairs_on_host = c->sensors_on_host = false;
 	c->last_with_sensors                   = with_sensors != 0;
 }
 
-static void fetch(hcs_ctx *c, int with_sensors)
+// D2H of what the caller applies: per-geom wrenches, flags and (when computed) the sensor outputs.  The per-pair
+// results are diagnostics (the reference has no such output): they are copied only when asked for
+// (hcs_get_pair_results, hcs_get_counters, hcs_fetch_results), so hcs_step does not pay for them every step.
+static void fetch(hcs_ctx *c, int with_sensors, bool with_pairs = true)
 {
 	const int n_env = c->cfg.n_envs, ng = (int)c->geoms.size(), np = (int)c->pairs.size();
 	cudaStream_t s = c->stream;
-	CK(cudaMemcpyAsync(c->h_pair, c->io.pair_out, (size_t)n_env * np * sizeof(hcs_pair_result), cudaMemcpyDeviceToHost, s));
+	if (with_pairs)
+		CK(cudaMemcpyAsync(c->h_pair, c->io.pair_out, (size_t)n_env * np * sizeof(hcs_pair_result), cudaMemcpyDeviceToHost, s));
 	CK(cudaMemcpyAsync(c->h_wrench, c->io.geom_wrench, (size_t)n_env * ng * 6 * sizeof(double), cudaMemcpyDeviceToHost, s));
 	CK(cudaMemcpyAsync(c->h_flags, c->io.flags, 4 * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
 	if (with_sensors)
@@ -787,6 +791,7 @@ static void fetch(hcs_ctx *c, int with_sensors)
 			                   cudaMemcpyDeviceToHost, s));
 	CK(cudaStreamSynchronize(s));
 	c->results_on_host = true;
+	c->pairs_on_host   = c->pairs_on_host || with_pairs;
 	c->sensors_on_host = with_sensors != 0;
 }
 
@@ -1233,7 +1238,7 @@ int hcs_step(hcs_ctx *c, const double *xpos, const double *xmat, const double *v
 	CK(cudaMemcpyAsync(c->d_xmat, xmat, n * 9 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
 	CK(cudaMemcpyAsync(c->d_vel, vel, n * 6 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
 	step_device(c, c->d_xpos, c->d_xmat, c->d_vel, with_sensors);
-	fetch(c, with_sensors);
+	fetch(c, with_sensors, /*with_pairs=*/false);
 	return check_flags(c);
 	API_END(c)
 }
@@ -1271,8 +1276,8 @@ int hcs_get_pair_results(hcs_ctx *c, hcs_pair_result *out)
 	API_BEGIN(c)
 	if (!c->finalized || !out)
 		return HCS_E_INVALID;
-	if (!c->results_on_host)
-		fetch(c, 0);
+	if (!c->pairs_on_host)
+		fetch(c, c->sensors_on_host ? 1 : 0);
 	memcpy(out, c->h_pair, (size_t)c->cfg.n_envs * c->pairs.size() * sizeof(hcs_pair_result));
 	return HCS_OK;
 	API_END(c)
@@ -1514,8 +1519,8 @@ int hcs_get_counters(hcs_ctx *c, int64_t out[5])
 	API_BEGIN(c)
 	if (!c->finalized || !out)
 		return HCS_E_INVALID;
-	if (!c->results_on_host)
-		fetch(c, 0);
+	if (!c->pairs_on_host)
+		fetch(c, c->sensors_on_host ? 1 : 0);
 	int64_t cand = 0, poly = 0, faces = 0;
 	size_t n = (size_t)c->cfg.n_envs * c->pairs.size();
 	for (size_t i = 0; i < n; ++i) {
