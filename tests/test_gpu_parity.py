@@ -246,3 +246,22 @@ def test_batch_is_env_independent(hcs_lib):
     half.step(xpos[32:], xmat[32:], vel[32:])
     r_half = half.pair_results()
     assert r_full[32:].tobytes() == r_half.tobytes()
+
+
+def test_candidate_pool_overflow_is_reported_not_undefined(hcs_lib, monkeypatch):
+    """Capacity errors come back through the C ABI (SURVEY.md 8b "Errors"): a pool that cannot hold the step's
+    candidates makes hcs_step fail with HCS_E_CAPACITY and a message naming the knob; a larger pool recovers."""
+    from mujoco_contact_surfaces_b200.engine import HcsError
+    scene = scenes.sphere_on_box()
+    xpos, xmat, vel = scene.poses(64, seed=3)
+    monkeypatch.setenv("HCS_MAX_TOTAL_CANDIDATES", "1024")  # 64 envs x ~47 candidates do not fit
+    eng = make_engine(scene, 64)
+    with pytest.raises(HcsError) as err:
+        eng.step(xpos, xmat, vel)
+    assert "candidate pool overflow" in str(err.value)
+    eng.close()
+    monkeypatch.delenv("HCS_MAX_TOTAL_CANDIDATES")
+    eng = make_engine(scene, 64)
+    eng.step(xpos, xmat, vel)
+    assert eng.pair_results()["n_polygons"].sum() > 0
+    eng.close()
