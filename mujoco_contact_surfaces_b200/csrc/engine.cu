@@ -733,12 +733,14 @@ static void step_device(hcs_ctx *c, const double *xpos, const double *xmat, cons
 	if (prof)
 		CK(cudaEventRecord(c->ev[1], s));
 	int list_slices = 0, list_units = 0; // most slices among the candidate-list pairs; their (pair, slice) units per env
+	bool small_units = true;
 	for (const PairDesc &P : c->pair_desc)
 		if (P.kind == PAIR_SOFT_RIGID || P.kind == PAIR_SOFT_SOFT) {
 			launch_broadphase(P, io, s);
 			++k;
 			list_slices = std::max(list_slices, P.n_slices);
 			list_units += P.n_slices;
+			small_units = small_units && std::min(P.nq, P.n_tree) <= 256;
 		}
 	if (prof)
 		CK(cudaEventRecord(c->ev[2], s));
@@ -749,7 +751,7 @@ static void step_device(hcs_ctx *c, const double *xpos, const double *xmat, cons
 		}
 	if (prof)
 		CK(cudaEventRecord(c->ev[3], s));
-	k += launch_finalize(c->d_pairs, io, list_slices, list_units, s);
+	k += launch_finalize(c->d_pairs, io, list_slices, list_units, small_units, s);
 	if (prof)
 		CK(cudaEventRecord(c->ev[4], s));
 	if (with_sensors) {

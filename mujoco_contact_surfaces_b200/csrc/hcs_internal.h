@@ -183,8 +183,9 @@ void launch_build_lbvh(const GeomDev &g, const double glo[3], const double ghi[3
 void launch_broadphase(const PairDesc &P, const StepIO &io, cudaStream_t s);
 void launch_narrowphase(const PairDesc &P, const StepIO &io, cudaStream_t s);
 // returns the number of kernels launched
+// small_units: every candidate-list pair has few elements on one side (units hold tens of candidates, not thousands)
 int launch_finalize(const PairDesc *d_pairs, const StepIO &io, int max_list_slices, int list_units_per_env,
-                    cudaStream_t s);
+                    bool small_units, cudaStream_t s);
 
 // clear, count, scan, fill, rasterise for all sensors (host copy + device copy of the records); returns the number
 // of kernels launched

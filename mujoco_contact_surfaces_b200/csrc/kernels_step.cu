@@ -598,8 +598,10 @@ __global__ void __launch_bounds__(NP_BLOCK, 4) narrow_tet_tri_kernel(PairDesc P,
 					e.set(k, dot(grad, Poly{ buf0 + cur * buf_stride }.get(k)) + e0);
 				integrate_polygon<TRI, false>(Poly{ buf0 + cur * buf_stride }, n, nS, grad, e, kInf, ctx, io, tet, tri, acc, cen, ec);
 				tfaces = n;
-				store_contrib(P, g, acc);
 			}
+			// every candidate writes its record (zeros without a polygon): a 32-byte sector that is only partly
+			// written in L2 has to be completed from DRAM when K7 reads it, and records share sectors
+			store_contrib(P, g, acc);
 			P.nverts[g] = (uint8_t)(nv | (acc.n_points << 4));
 		}
 		if (TRI && P.emit_tactile)
@@ -724,8 +726,8 @@ __global__ void __launch_bounds__(NP_BLOCK, 3) narrow_tet_tet_kernel(PairDesc P,
 				double gN = -dot(grad1_M, nhat);
 				integrate_polygon<TRI, false>(Poly{ buf0 + cur * buf_stride }, n, nhat, grad0, e, gN, ctx, io, t0, t1, acc, cen, ec);
 				tfaces = n;
-				store_contrib(P, g, acc);
 			}
+			store_contrib(P, g, acc); // always: see narrow_tet_tri_kernel
 			P.nverts[g] = (uint8_t)(nv | (acc.n_points << 4));
 		}
 		if (TRI && P.emit_tactile)
@@ -770,46 +772,70 @@ __device__ __forceinline__ void add_contrib(Acc &acc, const Contrib &c, int b, b
 	}
 }
 
-// totals of one (env, slice) unit, on every lane
-__device__ __forceinline__ Acc unit_sums(const PairDesc &P, const StepIO &io, int unit, int lane)
+// xor-shuffle tree over groups of W consecutive lanes (W = 32: the whole warp); all 32 lanes must call it
+template <int W>
+__device__ __forceinline__ Acc group_sum(Acc acc)
 {
-	int4 rg         = P.unit_range[unit]; // {base, n, next, -}
-	const int evals = P.unit_evals[unit];
-	if (rg.y == 0) { // nothing was clipped: most units
-		Acc z          = zero_acc();
-		z.n_candidates = evals;
-		return z;
+	double d[10] = { acc.F.x, acc.F.y, acc.F.z, acc.tau.x, acc.tau.y, acc.tau.z, acc.area, acc.ac.x, acc.ac.y, acc.ac.z };
+	int n[5]     = { acc.n_polygons, acc.n_faces, acc.n_points, acc.n_candidates, acc.n_clipped };
+#pragma unroll
+	for (int o = W / 2; o > 0; o >>= 1) {
+#pragma unroll
+		for (int k = 0; k < 10; ++k)
+			d[k] += __shfl_xor_sync(FULL_MASK, d[k], o);
+#pragma unroll
+		for (int k = 0; k < 5; ++k)
+			n[k] += __shfl_xor_sync(FULL_MASK, n[k], o);
 	}
-	const bool tri = io.representation == HCS_REP_TRIANGLE;
-	Acc acc        = zero_acc();
-	int cnt        = 0;
-	for (;;) {
-		// every range but the last holds whole 32-candidate chunks, so lane l always sees the unit's candidates
-		// l, l + 32, ... in increasing order; two candidates per lane are fetched together (vertex count and
-		// contribution in one round trip each) and added in order
-		for (int j = lane; j < rg.y; j += 64) {
-			int g0 = rg.x + j, g1 = g0 + 32;
-			bool in0 = g0 < P.contrib_cap, in1 = j + 32 < rg.y && g1 < P.contrib_cap;
-			int b0 = in0 ? P.nverts[g0] : 0, b1 = in1 ? P.nverts[g1] : 0;
-			Contrib c0 = load_contrib(P, in0 ? g0 : 0), c1 = load_contrib(P, in1 ? g1 : 0);
-			add_contrib(acc, c0, b0, tri);
-			add_contrib(acc, c1, b1, tri);
+	Acc r;
+	r.F = mk(d[0], d[1], d[2]), r.tau = mk(d[3], d[4], d[5]), r.area = d[6], r.ac = mk(d[7], d[8], d[9]);
+	r.n_polygons = n[0], r.n_faces = n[1], r.n_points = n[2], r.n_candidates = n[3], r.n_clipped = n[4];
+	return r;
+}
+
+// Totals of one (env, slice) unit on every lane of the group of W lanes that owns it (`sub` = lane inside the group;
+// groups of a warp may own different units, `valid` = this group has one).  Every range but a unit's last holds whole
+// 32-candidate chunks, so lane `sub` always sees the unit's candidates sub, sub + W, ... in increasing order; two
+// candidates per lane are fetched together (vertex count and contribution in one round trip each) and added in order.
+template <int W>
+__device__ __forceinline__ Acc unit_sums(const PairDesc &P, const StepIO &io, int unit, int sub, bool valid = true)
+{
+	Acc acc   = zero_acc();
+	int evals = 0, cnt = 0;
+	if (valid) {
+		int4 rg = P.unit_range[unit]; // {base, n, next, -}
+		evals   = P.unit_evals[unit];
+		if (W == 32 && rg.y == 0) { // nothing was clipped: most units of a multi-slice scene (warp-uniform exit)
+			acc.n_candidates = evals;
+			return acc;
 		}
-		cnt += rg.y;
-		if (rg.z < 0)
-			break;
-		rg = P.ranges[rg.z];
+		const bool tri = io.representation == HCS_REP_TRIANGLE;
+		while (rg.y > 0) {
+			for (int j = sub; j < rg.y; j += 2 * W) {
+				int g0 = rg.x + j, g1 = g0 + W;
+				bool in0 = g0 < P.contrib_cap, in1 = j + W < rg.y && g1 < P.contrib_cap;
+				int b0 = in0 ? P.nverts[g0] : 0, b1 = in1 ? P.nverts[g1] : 0;
+				Contrib c0 = load_contrib(P, in0 ? g0 : 0), c1 = load_contrib(P, in1 ? g1 : 0);
+				add_contrib(acc, c0, b0, tri);
+				add_contrib(acc, c1, b1, tri);
+			}
+			cnt += rg.y;
+			if (rg.z < 0)
+				break;
+			rg = P.ranges[rg.z];
+		}
 	}
-	if (lane == 0) {
+	if (sub == 0) {
 		acc.n_candidates = evals;
 		acc.n_clipped    = cnt;
 	}
-	return warp_sum(acc);
+	__syncwarp();
+	return group_sum<W>(acc);
 }
 
 __device__ __forceinline__ void reduce_unit(const PairDesc &P, const StepIO &io, int unit, int lane)
 {
-	Acc t = unit_sums(P, io, unit, lane);
+	Acc t = unit_sums<32>(P, io, unit, lane);
 	if (lane == 0)
 		store_partial(t, P.partial + unit);
 }
@@ -977,20 +1003,23 @@ __global__ void __launch_bounds__(128) finalize_kernel(const PairDesc *pairs, St
 	}
 }
 
-// K7 fast path for scenes with few units per environment: one WARP per environment does all three phases with
-// the sums in registers / shared memory: no block barrier, nothing written to global memory is read back (the
-// CTA-per-environment kernel spent its time in that chain of dependent round trips).  Same additions in the same
-// order as finalize_pair + the geom loop above.
-constexpr int FIN_ENVS = 4;
-__global__ void __launch_bounds__(32 * FIN_ENVS) finalize_env_warp_kernel(const PairDesc *pairs, StepIO io)
+// K7 fast path for scenes with few units per environment: a group of W lanes (a whole warp, or 8 lanes when the
+// units hold few candidates: 4 environments per warp) does all three phases of one environment with the sums in
+// registers / shared memory: no block barrier, nothing written to global memory is read back (the CTA-per-environment
+// kernel spent its time in that chain of dependent round trips, the warp-per-environment version in a 5-step shuffle
+// tree over 15 values that mostly added zeros).  Slices in slice order, pairs in pair order, like finalize_pair + the
+// geom loop above.
+constexpr int FIN_WARPS = 4;
+template <int W>
+__global__ void __launch_bounds__(32 * FIN_WARPS) finalize_env_group_kernel(const PairDesc *pairs, StepIO io)
 {
-	extern __shared__ double fin_smem[]; // [FIN_ENVS][n_geoms][6] wrench accumulators
-	const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
-	const int env = blockIdx.x * FIN_ENVS + wid;
-	if (env >= io.n_env)
-		return;
-	double *w = fin_smem + (size_t)wid * io.n_geoms * 6;
-	for (int k = lane; k < io.n_geoms * 6; k += 32)
+	extern __shared__ double fin_smem[]; // [FIN_WARPS * 32 / W][n_geoms][6] wrench accumulators
+	constexpr int G = 32 / W;            // environments per warp
+	const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31, grp = lane / W, sub = lane % W;
+	const int env    = (blockIdx.x * FIN_WARPS + wid) * G + grp;
+	const bool valid = env < io.n_env;
+	double *w = fin_smem + (size_t)(wid * G + grp) * io.n_geoms * 6;
+	for (int k = sub; k < io.n_geoms * 6; k += W)
 		w[k] = 0;
 	__syncwarp();
 	for (int p = 0; p < io.n_pairs; ++p) {
@@ -1006,10 +1035,10 @@ __global__ void __launch_bounds__(32 * FIN_ENVS) finalize_env_warp_kernel(const 
 			double ac[3]    = { 0, 0, 0 };
 			for (int s = 0; s < P.n_slices; ++s) {
 				const int unit = env * P.n_slices + s;
-				Acc t;
+				Acc t          = zero_acc();
 				if (list) {
-					t = unit_sums(P, io, unit, lane);
-				} else { // half-space pairs: K5 wrote the unit's sums
+					t = unit_sums<W>(P, io, unit, sub, valid);
+				} else if (valid) { // half-space pairs: K5 wrote the unit's sums
 					const SlicePartial &sp = P.partial[unit];
 					t.F = mk(sp.F[0], sp.F[1], sp.F[2]), t.tau = mk(sp.tau[0], sp.tau[1], sp.tau[2]);
 					t.ac = mk(sp.ac[0], sp.ac[1], sp.ac[2]), t.area = sp.area;
@@ -1029,7 +1058,7 @@ __global__ void __launch_bounds__(32 * FIN_ENVS) finalize_env_warp_kernel(const 
 				r.centroid[k] = r.area > 0 ? ac[k] / r.area : 0.0;
 			}
 		}
-		if (lane == 0) {
+		if (sub == 0 && valid) {
 			io.pair_out[(size_t)env * io.n_pairs + p] = r;
 			if (P.kind != PAIR_NONE)
 				for (int k = 0; k < 3; ++k) {
@@ -1039,9 +1068,11 @@ __global__ void __launch_bounds__(32 * FIN_ENVS) finalize_env_warp_kernel(const 
 		}
 		__syncwarp();
 	}
-	double *out = io.geom_wrench + (size_t)env * io.n_geoms * 6;
-	for (int k = lane; k < io.n_geoms * 6; k += 32)
-		out[k] = w[k];
+	if (valid) {
+		double *out = io.geom_wrench + (size_t)env * io.n_geoms * 6;
+		for (int k = sub; k < io.n_geoms * 6; k += W)
+			out[k] = w[k];
+	}
 }
 
 // =================================================================================================
@@ -1093,7 +1124,7 @@ void launch_narrowphase(const PairDesc &P, const StepIO &io, cudaStream_t s)
 }
 
 int launch_finalize(const PairDesc *d_pairs, const StepIO &io, int max_list_slices, int list_units_per_env,
-                    cudaStream_t s)
+                    bool small_units, cudaStream_t s)
 {
 	if (io.n_env <= 0)
 		return 0;
@@ -1104,9 +1135,19 @@ int launch_finalize(const PairDesc *d_pairs, const StepIO &io, int max_list_slic
 		finalize_kernel<<<io.n_env, 32, 0, s>>>(d_pairs, io, 0);
 		return 2;
 	}
-	size_t smem = (size_t)FIN_ENVS * io.n_geoms * 6 * sizeof(double);
-	if (smem <= 48 * 1024) { // one warp per environment, everything in registers / shared memory
-		finalize_env_warp_kernel<<<(io.n_env + FIN_ENVS - 1) / FIN_ENVS, 32 * FIN_ENVS, smem, s>>>(d_pairs, io);
+	// one group of lanes per environment, everything in registers / shared memory: 8 lanes when the units are small
+#ifdef HCS_FIN_FORCE_W32 // tuning sweeps
+	small_units = false;
+#endif
+	const int W     = small_units ? 8 : 32;
+	const int per   = FIN_WARPS * 32 / W; // environments per CTA
+	size_t smem     = (size_t)per * io.n_geoms * 6 * sizeof(double);
+	if (smem <= 48 * 1024) {
+		int grid = (io.n_env + per - 1) / per;
+		if (W == 8)
+			finalize_env_group_kernel<8><<<grid, 32 * FIN_WARPS, smem, s>>>(d_pairs, io);
+		else
+			finalize_env_group_kernel<32><<<grid, 32 * FIN_WARPS, smem, s>>>(d_pairs, io);
 		return 1;
 	}
 	// one warp per slice of a candidate-list pair (up to 4)
