@@ -106,6 +106,8 @@ struct hcs_ctx {
 	hcs_pair_result *h_pair = nullptr;                             // pinned mirrors
 	double *h_wrench        = nullptr;
 	int32_t *h_flags        = nullptr;
+	double *dh_wrench       = nullptr; // device addresses of h_wrench / h_flags (zero-copy end-to-end path)
+	int32_t *dh_flags       = nullptr;
 	int64_t kernels_last_step = 0;
 	bool profiling = false;
 	cudaEvent_t ev[8]{};
@@ -715,15 +717,27 @@ static void finalize(hcs_ctx *c)
 	CK(cudaMallocHost((void **)&c->h_wrench, std::max<size_t>((size_t)n_env * ng * 6, 1) * sizeof(double)));
 	CK(cudaMallocHost((void **)&c->h_flags, 4 * sizeof(int32_t)));
 	memset(c->h_flags, 0, 4 * sizeof(int32_t));
+	// device addresses of the pinned mirrors (pinned allocations are mapped under unified addressing)
+	c->dh_wrench = nullptr, c->dh_flags = nullptr;
+	if (cudaHostGetDevicePointer((void **)&c->dh_wrench, c->h_wrench, 0) != cudaSuccess ||
+	    cudaHostGetDevicePointer((void **)&c->dh_flags, c->h_flags, 0) != cudaSuccess) {
+		c->dh_wrench = nullptr, c->dh_flags = nullptr;
+		cudaGetLastError();
+	}
+	io.geom_wrench_host = nullptr, io.flags_host = nullptr;
 	c->io = io;
 	CK(cudaStreamSynchronize(c->stream));
 	c->finalized = true;
 }
 
-static void step_device(hcs_ctx *c, const double *xpos, const double *xmat, const double *vel, int with_sensors)
+static void step_device(hcs_ctx *c, const double *xpos, const double *xmat, const double *vel, int with_sensors,
+                        bool direct_out = false)
 {
 	StepIO io = c->io;
 	io.xpos = xpos, io.xmat = xmat, io.vel = vel;
+	// direct_out: the finalize kernel also writes wrenches and flags into the context's mapped pinned mirrors
+	io.geom_wrench_host = direct_out ? c->dh_wrench : nullptr;
+	io.flags_host       = direct_out ? c->dh_flags : nullptr;
 	cudaStream_t s = c->stream;
 	int64_t k      = 0;
 	bool prof      = c->profiling;
@@ -1236,10 +1250,47 @@ int hcs_step(hcs_ctx *c, const double *xpos, const double *xmat, const double *v
 		return HCS_E_INVALID;
 	}
 	size_t n = (size_t)c->cfg.n_envs * c->geoms.size();
-	CK(cudaMemcpyAsync(c->d_xpos, xpos, n * 3 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
-	CK(cudaMemcpyAsync(c->d_xmat, xmat, n * 9 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
-	CK(cudaMemcpyAsync(c->d_vel, vel, n * 6 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
-	step_device(c, c->d_xpos, c->d_xmat, c->d_vel, with_sensors);
+	// Inputs are staged with three DMA copies.  Reading the poses straight from pinned host memory inside the kernels
+	// (zero-copy) was measured and dropped as the default: the reads are 8-byte uniform loads, which PCIe serves far
+	// below its copy bandwidth (C1 +3 % end to end, C4 with five geoms -9 %); HCS_ZERO_COPY_IN=1 keeps the experiment.
+	// Outputs: without sensors the finalize kernel is the last kernel of the step and writes the per-geom wrenches
+	// and the flags into the context's mapped pinned mirrors itself (posted PCIe writes), so nothing is copied
+	// after the kernels; with sensors the images are copied back behind the sensor kernels as before.
+	const double *in[3] = { c->d_xpos, c->d_xmat, c->d_vel };
+	static const bool zero_copy_in = getenv("HCS_ZERO_COPY_IN") != nullptr;
+	bool staged = true;
+	if (zero_copy_in && !with_sensors) {
+		const double *host[3] = { xpos, xmat, vel }, *dev[3] = { nullptr, nullptr, nullptr };
+		bool pinned = true;
+		for (int k = 0; k < 3 && pinned; ++k) {
+			cudaPointerAttributes attr{};
+			if (cudaPointerGetAttributes(&attr, host[k]) != cudaSuccess) {
+				cudaGetLastError();
+				pinned = false;
+			} else {
+				pinned = attr.type == cudaMemoryTypeHost && attr.devicePointer != nullptr;
+				dev[k] = (const double *)attr.devicePointer;
+			}
+		}
+		if (pinned)
+			in[0] = dev[0], in[1] = dev[1], in[2] = dev[2], staged = false;
+	}
+	if (staged) {
+		CK(cudaMemcpyAsync(c->d_xpos, xpos, n * 3 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+		CK(cudaMemcpyAsync(c->d_xmat, xmat, n * 9 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+		CK(cudaMemcpyAsync(c->d_vel, vel, n * 6 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+	}
+	static const bool direct_out_ok = getenv("HCS_NO_DIRECT_OUT") == nullptr;
+	// (measured: 393 KB of wrenches on C1: +6 % end to end; 983 KB on C4: -3 %, the 8-byte posted writes lose to one
+	// DMA burst once the output is large)
+	const size_t wrench_bytes = n * 6 * sizeof(double);
+	if (direct_out_ok && !with_sensors && c->dh_wrench && c->dh_flags && wrench_bytes <= (512u << 10)) {
+		step_device(c, in[0], in[1], in[2], 0, /*direct_out=*/true);
+		CK(cudaStreamSynchronize(c->stream));
+		c->results_on_host = true; // wrenches and flags are in the pinned mirrors; pair results stay on the device
+		return check_flags(c);
+	}
+	step_device(c, in[0], in[1], in[2], with_sensors);
 	fetch(c, with_sensors, /*with_pairs=*/false);
 	return check_flags(c);
 	API_END(c)

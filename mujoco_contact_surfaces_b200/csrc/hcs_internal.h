@@ -122,6 +122,10 @@ struct StepIO {
 	                           // sensors need them: their sample lattice is evaluated in double)
 	hcs_pair_result *pair_out; // [n_env][n_pairs]
 	double *geom_wrench;       // [n_env][n_geoms][6]
+	// end-to-end path without sensors: device addresses of the context's mapped pinned mirrors (else NULL); the
+	// finalize kernel writes the wrenches and the flags there itself, so no copy follows the kernels
+	double *geom_wrench_host;
+	int32_t *flags_host;
 };
 
 struct SensorDev {

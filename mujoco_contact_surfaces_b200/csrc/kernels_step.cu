@@ -955,6 +955,16 @@ __device__ __forceinline__ void finalize_pair(const PairDesc *pairs, const StepI
 	io.pair_out[idx] = r;
 }
 
+// The finalize kernel is the last kernel of a step without sensors: one thread mirrors the error flags into the
+// caller's mapped pinned memory, so that the end-to-end path needs no copy after the kernels (every kernel that can
+// raise a flag has finished: stream order).
+__device__ __forceinline__ void publish_flags(const StepIO &io)
+{
+	if (io.flags_host && blockIdx.x == 0 && threadIdx.x == 0)
+		for (int k = 0; k < 4; ++k)
+			io.flags_host[k] = io.flags[k];
+}
+
 // phase 1 as its own grid (one warp per unit, blockIdx.y = pair) for scenes with many units per environment,
 // where one CTA per environment would serialise them
 __global__ void __launch_bounds__(NP_BLOCK) reduce_units_kernel(const PairDesc *pairs, StepIO io)
@@ -1000,7 +1010,11 @@ __global__ void __launch_bounds__(128) finalize_kernel(const PairDesc *pairs, St
 		double *out = io.geom_wrench + ((size_t)env * io.n_geoms + g) * 6;
 		for (int k = 0; k < 6; ++k)
 			out[k] = w[k];
+		if (io.geom_wrench_host) // end-to-end path: the caller's copy is written straight into mapped pinned memory
+			for (int k = 0; k < 6; ++k)
+				io.geom_wrench_host[((size_t)env * io.n_geoms + g) * 6 + k] = w[k];
 	}
+	publish_flags(io);
 }
 
 // K7 fast path for scenes with few units per environment: a group of W lanes (a whole warp, or 8 lanes when the
@@ -1072,7 +1086,11 @@ __global__ void __launch_bounds__(32 * FIN_WARPS) finalize_env_group_kernel(cons
 		double *out = io.geom_wrench + (size_t)env * io.n_geoms * 6;
 		for (int k = sub; k < io.n_geoms * 6; k += W)
 			out[k] = w[k];
+		if (io.geom_wrench_host) // end-to-end path: the caller's copy is written straight into mapped pinned memory
+			for (int k = sub; k < io.n_geoms * 6; k += W)
+				io.geom_wrench_host[(size_t)env * io.n_geoms * 6 + k] = w[k];
 	}
+	publish_flags(io);
 }
 
 // =================================================================================================
