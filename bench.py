@@ -312,14 +312,14 @@ def main():
         kinds = workload_kinds(scene)
         # Algorithmic bytes (DESIGN.md "Roofline"), rank 0, last step.  The dominant kernel is the
         # narrowphase: its launches process the pairs that survived the broadphase early-outs (soft-rigid,
-        # soft-soft) or every tet of the soft geom (half space); each unit moves 232 / 264 / 132 B + 80 B per
-        # emitted polygon.  The whole pair-eval pipeline (LBVH leaf hits decided by broadphase + narrowphase)
-        # is reported next to it against the time of both kernels.
+        # soft-soft) or the tets the plane cuts (half space); each unit moves 232 / 264 / 132 B + 80 B per
+        # emitted polygon.  The whole pair-eval pipeline (LBVH leaf hits / classified tets decided by broadphase +
+        # narrowphase) is reported next to it against the time of both kernels.
         res = eng.pair_results()
         alg = alg_pipeline = 0.0
         for p, kind in enumerate(kinds):
             if kind:
-                units = res["n_candidates"][:, p] if kind == "soft_plane" else res["n_clipped"][:, p]
+                units = res["n_clipped"][:, p]
                 alg += float(units.sum()) * BYTES_PER_PAIR[kind] + float(res["n_polygons"][:, p].sum()) * BYTES_PER_POLYGON
                 alg_pipeline += float(res["n_candidates"][:, p].sum()) * BYTES_PER_PAIR[kind] + float(res["n_polygons"][:, p].sum()) * BYTES_PER_POLYGON
         n_narrow = sum(1 for k in kinds if k)

@@ -28,6 +28,15 @@ __host__ __device__ __forceinline__ D3 normalized(D3 a)
 }
 __host__ __device__ __forceinline__ D3 ld3(const double *p) { return mk(p[0], p[1], p[2]); }
 
+// Four doubles fetched with ONE 256-bit load (LDG.E.256 on sm_100a; p must be 32-byte aligned).  The gather kernels
+// read per-lane records (every lane another tet / triangle): an 8-byte load touches 32 different lines and costs
+// 32 L1 wavefronts per instruction whatever its width, so the records are laid out in 32-byte groups and read whole.
+struct __align__(32) D4 {
+	double x, y, z, w;
+};
+__device__ __forceinline__ D4 ld4(const double *p) { return *reinterpret_cast<const D4 *>(p); }
+__host__ __device__ __forceinline__ D3 xyz(const D4 &q) { return mk(q.x, q.y, q.z); }
+
 struct Xform { // p_A = R * p_B + p, R row-major
 	double R[9];
 	D3 p;

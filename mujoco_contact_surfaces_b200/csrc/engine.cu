@@ -435,15 +435,14 @@ static void build_pairs(hcs_ctx *c)
 			P.n_slices   = (P.nq + P.slice_q - 1) / P.slice_q;
 			size_t units = (size_t)n_env * P.n_slices;
 			P.partial    = dalloc<SlicePartial>(c->step_allocs, units);
-			if (P.kind == PAIR_SOFT_PLANE) {
-				P.nverts = dalloc<uint8_t>(c->step_allocs, (size_t)n_env * P.nq);
-				CK(cudaMemsetAsync(P.nverts, 0, (size_t)n_env * P.nq, c->stream));
-			} else {
+			{
 				// ONE candidate pool per pair for the whole batch (flat list + per-candidate contributions, 97 B per
 				// entry).  Default size: per environment min(nq * n_tree, 16 (nq + n_tree)) candidates, at most 64 M
 				// entries; hcs_config.max_candidates_per_slice > 0 sizes it as that many per (env, slice) unit
 				// instead, HCS_MAX_TOTAL_CANDIDATES overrides both.  Overflow is reported by hcs_step, never UB.
-				long per_env = std::min<long>((long)P.nq * P.n_tree, 16L * ((long)P.nq + P.n_tree));
+				// (half-space pairs: the candidates are the tets the plane cuts, at most all of them)
+				long per_env = P.kind == PAIR_SOFT_PLANE ? (long)P.nq :
+				                                           std::min<long>((long)P.nq * P.n_tree, 16L * ((long)P.nq + P.n_tree));
 				long total   = c->cfg.max_candidates_per_slice > 0 ? (long)c->cfg.max_candidates_per_slice * (long)units :
 				                                                     std::min<long>(per_env * n_env, 64L << 20);
 				if (const char *mt_env = getenv("HCS_MAX_TOTAL_CANDIDATES"))
@@ -749,7 +748,7 @@ static void step_device(hcs_ctx *c, const double *xpos, const double *xmat, cons
 	int list_slices = 0, list_units = 0; // most slices among the candidate-list pairs; their (pair, slice) units per env
 	bool small_units = true;
 	for (const PairDesc &P : c->pair_desc)
-		if (P.kind == PAIR_SOFT_RIGID || P.kind == PAIR_SOFT_SOFT) {
+		if (P.kind != PAIR_NONE) {
 			launch_broadphase(P, io, s);
 			++k;
 			list_slices = std::max(list_slices, P.n_slices);
@@ -1414,15 +1413,6 @@ int hcs_get_emitted(hcs_ctx *c, int env, int pair, int32_t *out, int cap)
 		}
 		++n;
 	};
-	if (P.kind == PAIR_SOFT_PLANE) {
-		std::vector<uint8_t> nv(P.nq);
-		CK(cudaMemcpyAsync(nv.data(), P.nverts + (size_t)env * P.nq, P.nq, cudaMemcpyDeviceToHost, c->stream));
-		CK(cudaStreamSynchronize(c->stream));
-		for (int t = 0; t < P.nq; ++t)
-			if (nv[t] >= 3)
-				put(t, 0, nv[t]);
-		return n;
-	}
 	// walk the range chains of the env's units: first range inline, further ranges in the pool
 	std::vector<int4> heads(P.n_slices), pool;
 	int32_t used[PAIR_COUNTERS] = { 0, 0, 0, 0 };

@@ -11,21 +11,21 @@
 namespace hcs {
 
 // ---- resident geometry records (HBM) ---------------------------------------------------------
-// Gather records are padded to whole 32-B sectors and 16-B aligned so that one thread fetches its
-// element with double2 loads; consecutive lanes of the streaming kernels read consecutive records.
+// Gather records are made of whole 32-byte groups and 32-byte aligned so that one thread fetches its element with
+// 256-bit loads (dmath.cuh ld4); consecutive lanes of the streaming kernels read consecutive records.
 
-struct __align__(16) TetGeom { // 128 B = one cache line: tet vertices + vertex pressures
+struct __align__(32) TetGeom { // 128 B = one cache line = 4 x 32 B: tet vertices (3 groups) + vertex pressures (1)
 	double v[4][3];
 	double e[4];
 };
-struct __align__(16) TetField { // 192 B: what the tet contributes to a (tet, triangle) clip
+struct __align__(32) TetField { // 192 B = 6 x 32 B: what the tet contributes to a (tet, triangle) clip
 	double plane[4][4]; // outward unit normal + offset of faces {1,2,3},{0,3,2},{0,1,3},{0,2,1}
 	double grad[3];     // pressure gradient
 	double e0;          // pressure at the geom-frame origin
 	double ghat[3];     // normalized gradient (cull direction)
 	double pad;
 };
-struct __align__(16) TriRec { // 96 B: rigid triangle vertices + unit normal
+struct __align__(32) TriRec { // 96 B = 3 x 32 B: rigid triangle vertices + unit normal
 	double v[3][3];
 	double n[3];
 };
@@ -102,9 +102,10 @@ struct PairDesc {
 constexpr int PAIR_COUNTERS = 4;
 
 constexpr int PAIR_CTX_DOUBLES = 48;
-// layout of one context block: R_WA[9] xA[3] wA[3] vA[3] xB[3] wB[3] vB[3] R_AB[9] p_AB[3] p_BAo[3]
-constexpr int CTX_XA = 9, CTX_WA = 12, CTX_VA = 15, CTX_XB = 18, CTX_WB = 21, CTX_VB = 24, CTX_RAB = 27, CTX_PAB = 36,
-              CTX_PBA = 39;
+// layout of one context block, in 32-byte groups: R_WA[9] xA[3] | R_AB[9] p_AB[3] | wA[3] - | vA[3] - | xB[3] - | wB[3] - |
+// vB[3] - | p_BAo[3] -
+constexpr int CTX_XA = 9, CTX_RAB = 12, CTX_PAB = 21, CTX_WA = 24, CTX_VA = 28, CTX_XB = 32, CTX_WB = 36, CTX_VB = 40,
+              CTX_PBA = 44;
 
 struct StepIO {
 	int n_env, n_geoms, n_pairs;

@@ -16,6 +16,7 @@
 
 #include "dmath.cuh"
 #include "hcs_internal.h"
+#include "records.cuh"
 
 namespace hcs {
 
@@ -115,6 +116,83 @@ __device__ __forceinline__ bool box_overlap(const float *q, const float *pl, flo
 	return hit;
 }
 
+// per (env, pair) context block read by the flat narrowphase (layout: hcs_internal.h)
+__device__ __forceinline__ void write_pair_ctx(const PairDesc &P, const StepIO &io, int env, const Xform &X_WA,
+                                               const Xform &X_WB, const Xform &X_AB, D3 p_BAo)
+{
+	double *cb = P.pair_ctx + (size_t)env * PAIR_CTX_DOUBLES;
+	const double *velA = io.vel + ((size_t)env * io.n_geoms + P.gA) * 6;
+	const double *velB = io.vel + ((size_t)env * io.n_geoms + P.gB) * 6;
+#pragma unroll
+	for (int i = 0; i < 9; ++i) {
+		cb[i]           = X_WA.R[i];
+		cb[CTX_RAB + i] = X_AB.R[i];
+	}
+#pragma unroll
+	for (int i = 0; i < 3; ++i) {
+		cb[CTX_WA + i] = velA[i], cb[CTX_VA + i] = velA[3 + i];
+		cb[CTX_WB + i] = velB[i], cb[CTX_VB + i] = velB[3 + i];
+	}
+	cb[CTX_XA] = X_WA.p.x, cb[CTX_XA + 1] = X_WA.p.y, cb[CTX_XA + 2] = X_WA.p.z;
+	cb[CTX_XB] = X_WB.p.x, cb[CTX_XB + 1] = X_WB.p.y, cb[CTX_XB + 2] = X_WB.p.z;
+	cb[CTX_PAB] = X_AB.p.x, cb[CTX_PAB + 1] = X_AB.p.y, cb[CTX_PAB + 2] = X_AB.p.z;
+	cb[CTX_PBA] = p_BAo.x, cb[CTX_PBA + 1] = p_BAo.y, cb[CTX_PBA + 2] = p_BAo.z;
+	// the pad of every 32-byte group too: a sector that is only partly written is completed from DRAM when it is read
+	cb[CTX_WA + 3] = cb[CTX_VA + 3] = cb[CTX_XB + 3] = cb[CTX_WB + 3] = cb[CTX_VB + 3] = cb[CTX_PBA + 3] = 0.0;
+}
+
+// Soft geom against a rigid half space (the query the reference calls at plugin.cpp:298-299): every tet of the
+// unit's slice is classified against the plane, the tets it cuts become the unit's candidates.  On the mixed-objects
+// scene 13 % of the tets are cut: clipping them in the flat narrowphase keeps whole warps busy, where the
+// one-thread-per-tet kernel ran the whole slice-and-integrate path for the few cut tets of each 32-tet group.
+__device__ __forceinline__ void plane_unit(const PairDesc &P, const StepIO &io, WarpQueues &W, int warp, int lane)
+{
+	int env = warp / P.n_slices, slice = warp - env * P.n_slices;
+	Xform X_WA = load_pose(io.xpos, io.xmat, io.n_geoms, env, P.gA);
+	Xform X_WB = load_pose(io.xpos, io.xmat, io.n_geoms, env, P.gB);
+	Xform X_AB = invert_and_compose(X_WA, X_WB);
+	D3 p_BAo   = -rotT(X_AB.R, X_AB.p);
+	if (slice == 0 && lane == 0)
+		write_pair_ctx(P, io, env, X_WA, X_WB, X_AB, p_BAo);
+	// the half space in A's frame: normal = z column of R_AB, through p_AB (mesh_half_space_intersection.cc)
+	D3 n_S    = mk(X_AB.R[2], X_AB.R[5], X_AB.R[8]);
+	double pd = dot(n_S, X_AB.p);
+	int n_stage = 0, i0 = 0;
+	int last_range = -2;
+	const int q_begin = slice * P.slice_q, q_end = min(P.nq, q_begin + P.slice_q);
+	const unsigned lt_mask = (1u << lane) - 1u;
+	// the whole geom above the plane: nothing can be cut
+	bool above = dot(n_S, mk(P.A.bound_c[0], P.A.bound_c[1], P.A.bound_c[2])) - pd > P.A.bound_r + 1e-9;
+	for (int q0 = q_begin; q0 < q_end && !above; q0 += 32) {
+		int t     = q0 + lane;
+		bool keep = false;
+		if (t < q_end) {
+			const TetVerts g = load_tet_verts(P.A.tet_geom + t);
+			int code = 0;
+#pragma unroll
+			for (int k = 0; k < 4; ++k)
+				if (dot(n_S, g.at(k)) - pd > 0)
+					code |= 1 << k;
+			keep = code != 0 && code != 15;
+		}
+		unsigned mk_ = __ballot_sync(FULL_MASK, keep);
+		if (keep)
+			W.stage[n_stage + __popc(mk_ & lt_mask)] = make_uint2(0u, (unsigned)t);
+		n_stage += __popc(mk_);
+		__syncwarp();
+		if (n_stage > STAGE - 32)
+			flush_stage(P, io, W, warp, lane, n_stage & ~31, n_stage, i0, last_range);
+	}
+	if (n_stage > 0)
+		flush_stage(P, io, W, warp, lane, n_stage, n_stage, i0, last_range);
+	if (lane == 0) {
+		P.unit_count[warp] = i0;
+		P.unit_evals[warp] = q_end - q_begin; // tets examined
+		if (last_range == -2)
+			P.unit_range[warp] = make_int4(0, 0, -1, 0);
+	}
+}
+
 // QTET: query elements are tets of B (soft-soft), otherwise triangles of B (soft-rigid)
 template <bool QTET>
 __device__ __forceinline__ void broadphase_unit(const PairDesc &P, const StepIO &io, WarpQueues &W, int warp, int lane)
@@ -138,25 +216,8 @@ __device__ __forceinline__ void broadphase_unit(const PairDesc &P, const StepIO 
 	}
 	Xform X_AB  = invert_and_compose(X_WA, X_WB);
 	D3 p_BAo    = -rotT(X_AB.R, X_AB.p); // origin of A expressed in B (p_NMo of field_intersection.cc)
-	if (slice == 0 && lane == 0) { // per (env, pair) context block read by the flat narrowphase
-		double *cb = P.pair_ctx + (size_t)env * PAIR_CTX_DOUBLES;
-		const double *velA = io.vel + ((size_t)env * io.n_geoms + P.gA) * 6;
-		const double *velB = io.vel + ((size_t)env * io.n_geoms + P.gB) * 6;
-#pragma unroll
-		for (int i = 0; i < 9; ++i) {
-			cb[i]           = X_WA.R[i];
-			cb[CTX_RAB + i] = X_AB.R[i];
-		}
-#pragma unroll
-		for (int i = 0; i < 3; ++i) {
-			cb[CTX_WA + i] = velA[i], cb[CTX_VA + i] = velA[3 + i];
-			cb[CTX_WB + i] = velB[i], cb[CTX_VB + i] = velB[3 + i];
-		}
-		cb[CTX_XA] = X_WA.p.x, cb[CTX_XA + 1] = X_WA.p.y, cb[CTX_XA + 2] = X_WA.p.z;
-		cb[CTX_XB] = X_WB.p.x, cb[CTX_XB + 1] = X_WB.p.y, cb[CTX_XB + 2] = X_WB.p.z;
-		cb[CTX_PAB] = X_AB.p.x, cb[CTX_PAB + 1] = X_AB.p.y, cb[CTX_PAB + 2] = X_AB.p.z;
-		cb[CTX_PBA] = p_BAo.x, cb[CTX_PBA + 1] = p_BAo.y, cb[CTX_PBA + 2] = p_BAo.z;
-	}
+	if (slice == 0 && lane == 0)
+		write_pair_ctx(P, io, env, X_WA, X_WB, X_AB, p_BAo);
 	int n_stage = 0, i0 = 0, evals = 0; // warp-uniform: staged candidates, candidates already flushed, leaf hits
 	int last_range = -2;                // lane 0 only
 	int q_begin = slice * P.slice_q, q_end = min(P.nq, q_begin + P.slice_q);
@@ -171,17 +232,21 @@ __device__ __forceinline__ void broadphase_unit(const PairDesc &P, const StepIO 
 		float box[6];
 		if (alive) {
 			double lo[3] = { 1e300, 1e300, 1e300 }, hi[3] = { -1e300, -1e300, -1e300 };
-			const double *vp = QTET ? &P.B.tet_geom[q].v[0][0] : &P.B.tris[q].v[0][0];
-			const int nv     = QTET ? 4 : 3;
+			// 12 doubles = three 256-bit loads: the tet's vertices, or the triangle's vertices + normal
+			const double *vp = QTET ? reinterpret_cast<const double *>(P.B.tet_geom + q) :
+			                          reinterpret_cast<const double *>(P.B.tris + q);
+			const D4 r0 = ld4(vp), r1 = ld4(vp + 4), r2 = ld4(vp + 8);
+			const D3 qv[4] = { mk(r0.x, r0.y, r0.z), mk(r0.w, r1.x, r1.y), mk(r1.z, r1.w, r2.x), mk(r2.y, r2.z, r2.w) };
+			const int nv   = QTET ? 4 : 3;
 #pragma unroll
 			for (int i = 0; i < nv; ++i) {
-				D3 p = apply(X_AB, ld3(vp + 3 * i));
+				D3 p = apply(X_AB, qv[i]);
 				v[3 * i] = p.x, v[3 * i + 1] = p.y, v[3 * i + 2] = p.z;
 				lo[0] = fmin(lo[0], p.x), lo[1] = fmin(lo[1], p.y), lo[2] = fmin(lo[2], p.z);
 				hi[0] = fmax(hi[0], p.x), hi[1] = fmax(hi[1], p.y), hi[2] = fmax(hi[2], p.z);
 			}
 			if (!QTET) {
-				D3 nS = rot(X_AB.R, ld3(P.B.tris[q].n));
+				D3 nS = rot(X_AB.R, qv[3]);
 				v[9] = nS.x, v[10] = nS.y, v[11] = nS.z;
 			}
 #pragma unroll
@@ -227,26 +292,27 @@ __device__ __forceinline__ void broadphase_unit(const PairDesc &P, const StepIO 
 					it           = make_uint2(raw >> ITEM_SHIFT, raw & ITEM_MASK);
 					keep         = true;
 					if (!QTET) {
-						const TetField &tf = P.A.tet_field[it.y];
+						const TetField *tf = P.A.tet_field + it.y;
 						int s  = (int)it.x;
 						D3 nS  = mk(W.qv[9][s], W.qv[10][s], W.qv[11][s]);
-						keep   = dot(ld3(tf.ghat), nS) > HCS_COS_ALPHA;
+						keep   = dot(load_ghat(tf), nS) > HCS_COS_ALPHA;
 						if (keep) {
 							D3 a = mk(W.qv[0][s], W.qv[1][s], W.qv[2][s]), b = mk(W.qv[3][s], W.qv[4][s], W.qv[5][s]),
 							   c = mk(W.qv[6][s], W.qv[7][s], W.qv[8][s]);
 #pragma unroll
 							for (int f = 0; f < 4; ++f) {
-								D3 nh = ld3(tf.plane[f]);
-								double d = tf.plane[f][3];
+								const D4 pl = load_plane(tf, f);
+								D3 nh       = xyz(pl);
+								double d    = pl.w;
 								double sa = dot(nh, a) - d, sb = dot(nh, b) - d, sc = dot(nh, c) - d;
 								if (sa > 1e-12 && sb > 1e-12 && sc > 1e-12)
 									keep = false;
 							}
 							// the triangle's plane must cut the tet: all four tet vertices strictly on one side => empty
-							const TetGeom &tg = P.A.tet_geom[it.y];
+							const TetVerts tg = load_tet_verts(P.A.tet_geom + it.y);
 							double dt = dot(nS, a);
-							double h0 = dot(nS, ld3(tg.v[0])) - dt, h1 = dot(nS, ld3(tg.v[1])) - dt,
-							       h2 = dot(nS, ld3(tg.v[2])) - dt, h3 = dot(nS, ld3(tg.v[3])) - dt;
+							double h0 = dot(nS, tg.v0) - dt, h1 = dot(nS, tg.v1) - dt, h2 = dot(nS, tg.v2) - dt,
+							       h3 = dot(nS, tg.v3) - dt;
 							if ((h0 > 1e-12 && h1 > 1e-12 && h2 > 1e-12 && h3 > 1e-12) ||
 							    (h0 < -1e-12 && h1 < -1e-12 && h2 < -1e-12 && h3 < -1e-12))
 								keep = false;
@@ -255,26 +321,26 @@ __device__ __forceinline__ void broadphase_unit(const PairDesc &P, const StepIO 
 						// soft-soft: CalcEquilibriumPlane + the two IsPlaneNormalAlongPressureGradient culls of
 						// field_intersection.cc (same arithmetic as the clip kernel), then: the equal-pressure plane
 						// must cut BOTH tets, otherwise slice-and-clip is empty.
-						const TetField &f0 = P.A.tet_field[it.y];
-						const TetField &f1 = P.B.tet_field[W.qid[it.x]];
+						const TetField *f0 = P.A.tet_field + it.y, *f1 = P.B.tet_field + W.qid[it.x];
 						int s      = (int)it.x;
-						D3 grad0 = ld3(f0.grad), grad1_N = ld3(f1.grad);
+						const D4 ge0 = load_grad_e0(f0), ge1 = load_grad_e0(f1);
+						D3 grad0 = xyz(ge0), grad1_N = xyz(ge1);
 						D3 grad1_M   = rot(X_AB.R, grad1_N);
-						double f1_Mo = dot(grad1_N, p_BAo) + f1.e0;
+						double f1_Mo = dot(grad1_N, p_BAo) + ge1.w;
 						D3 n_M       = grad0 - grad1_M;
 						double mag   = sqrt(dot(n_M, n_M));
 						keep         = mag > 0.0;
 						if (keep) {
 							D3 nhat   = n_M / mag;
-							D3 p_MQ   = -((f0.e0 - f1_Mo) / mag) * nhat;
+							D3 p_MQ   = -((ge0.w - f1_Mo) / mag) * nhat;
 							double pd = dot(nhat, p_MQ);
-							keep      = dot(nhat, ld3(f0.ghat)) > HCS_COS_ALPHA;
+							keep      = dot(nhat, load_ghat(f0)) > HCS_COS_ALPHA;
 							if (keep)
-								keep = dot(rotT(X_AB.R, -nhat), ld3(f1.ghat)) > HCS_COS_ALPHA;
+								keep = dot(rotT(X_AB.R, -nhat), load_ghat(f1)) > HCS_COS_ALPHA;
 							if (keep) {
-								const TetGeom &tg = P.A.tet_geom[it.y];
-								double h0 = dot(nhat, ld3(tg.v[0])) - pd, h1 = dot(nhat, ld3(tg.v[1])) - pd,
-								       h2 = dot(nhat, ld3(tg.v[2])) - pd, h3 = dot(nhat, ld3(tg.v[3])) - pd;
+								const TetVerts tg = load_tet_verts(P.A.tet_geom + it.y);
+								double h0 = dot(nhat, tg.v0) - pd, h1 = dot(nhat, tg.v1) - pd, h2 = dot(nhat, tg.v2) - pd,
+								       h3 = dot(nhat, tg.v3) - pd;
 								if ((h0 > 1e-12 && h1 > 1e-12 && h2 > 1e-12 && h3 > 1e-12) ||
 								    (h0 < -1e-12 && h1 < -1e-12 && h2 < -1e-12 && h3 < -1e-12))
 									keep = false;
@@ -369,7 +435,8 @@ __device__ __forceinline__ void broadphase_unit(const PairDesc &P, const StepIO 
 
 // Persistent warps: the resident CTAs of every SM pull (env, slice) units from a work counter, so the grid is
 // never a fractional number of waves and a slow unit does not hold three finished warps' resources.
-template <bool QTET>
+// KIND: 0 triangles of B against the tet tree of A, 1 tets of B against it, 2 the tets of A against a half space
+template <int KIND>
 __global__ void __launch_bounds__(BP_BLOCK, BP_CTAS_PER_SM) broadphase_kernel(PairDesc P, StepIO io)
 {
 	__shared__ WarpQueues sm[BP_WARPS];
@@ -384,13 +451,20 @@ __global__ void __launch_bounds__(BP_BLOCK, BP_CTAS_PER_SM) broadphase_kernel(Pa
 		unit = __shfl_sync(FULL_MASK, unit, 0);
 		if (unit >= n_units)
 			break;
-		broadphase_unit<QTET>(P, io, W, unit, lane);
+		if (KIND == 2)
+			plane_unit(P, io, W, unit, lane);
+		else
+			broadphase_unit<KIND == 1>(P, io, W, unit, lane);
 		__syncwarp();
 	}
 #else
 	int unit = (blockIdx.x * BP_BLOCK + threadIdx.x) >> 5;
-	if (unit < n_units)
-		broadphase_unit<QTET>(P, io, W, unit, lane);
+	if (unit < n_units) {
+		if (KIND == 2)
+			plane_unit(P, io, W, unit, lane);
+		else
+			broadphase_unit<KIND == 1>(P, io, W, unit, lane);
+	}
 #endif
 }
 
@@ -404,9 +478,11 @@ void launch_broadphase(const PairDesc &P, const StepIO &io, cudaStream_t s)
 	grid = (int)std::min<long>(grid, (long)io.n_sms * BP_CTAS_PER_SM);
 #endif
 	if (P.kind == PAIR_SOFT_RIGID)
-		broadphase_kernel<false><<<grid, BP_BLOCK, 0, s>>>(P, io);
+		broadphase_kernel<0><<<grid, BP_BLOCK, 0, s>>>(P, io);
 	else if (P.kind == PAIR_SOFT_SOFT)
-		broadphase_kernel<true><<<grid, BP_BLOCK, 0, s>>>(P, io);
+		broadphase_kernel<1><<<grid, BP_BLOCK, 0, s>>>(P, io);
+	else if (P.kind == PAIR_SOFT_PLANE)
+		broadphase_kernel<2><<<grid, BP_BLOCK, 0, s>>>(P, io);
 }
 
 } // namespace hcs

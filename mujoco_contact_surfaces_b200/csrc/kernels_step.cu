@@ -19,6 +19,7 @@
 
 #include "dmath.cuh"
 #include "hcs_internal.h"
+#include "records.cuh"
 
 namespace hcs {
 
@@ -32,7 +33,6 @@ template <int MV>
 struct WarpTile {
 	double xyz[2][MV][3][32];
 	double e[MV][32];
-	double ctx[PAIR_CTX_DOUBLES]; // context block of the warp-per-slice plane kernel
 };
 
 // Explicit shared-window accesses: through a generic pointer stored in a struct the compiler emitted
@@ -69,41 +69,40 @@ __device__ __forceinline__ unsigned smem_addr(const void *p)
 	return (unsigned)(reinterpret_cast<const char *>(p) - reinterpret_cast<const char *>(smem_d));
 }
 
-// Per (env, pair) data: poses, velocities, relative transform (PAIR_CTX_DOUBLES doubles, layout in
-// hcs_internal.h).  They are read on demand instead of being held in registers: holding them across the clip
-// loop cost ~80 registers per thread and capped the kernel at 3 warps per scheduler (profiles/r01_notes.md).
-//   GLOBAL = true : the block the broadphase wrote for the candidate's environment (flat narrowphase: the lanes of
-//                   a warp may belong to different environments; lanes of one environment read the same lines)
-//   GLOBAL = false: the warp's block in shared memory (warp-per-slice plane kernel; uniform LDS broadcasts)
-template <bool GLOBAL>
-struct PairCtx {
-	const double *g; // GLOBAL
-	unsigned a;      // !GLOBAL: byte offset of the block in smem_d
+// Per (env, pair) data: poses, velocities, relative transform (PAIR_CTX_DOUBLES doubles in 32-byte groups, layout
+// in hcs_internal.h), written by the broadphase.  They are read on demand with 256-bit loads instead of being held
+// in registers: holding them across the clip loop cost ~80 registers per thread and capped the kernel at 3 warps
+// per scheduler (profiles/r01_notes.md).  The lanes of a warp may belong to different environments; lanes of one
+// environment read the same lines.
+struct CandCtx {
+	const double *g;
 	double dissipation, mu, sign;
 	int apply, env, pair;
-	__device__ __forceinline__ double ld(int i) const { return GLOBAL ? __ldg(g + i) : smem_d[(a >> 3) + i]; }
-	__device__ __forceinline__ D3 v(int i) const { return mk(ld(i), ld(i + 1), ld(i + 2)); }
-	__device__ __forceinline__ Xform xf(int r, int p) const
+	__device__ __forceinline__ D3 v(int i) const { return xyz(ld4(g + i)); } // groups that start a 32-byte group
+	__device__ __forceinline__ Xform xf(int r) const                        // R[9] + p[3] = three groups
 	{
+		D4 a = ld4(g + r), b = ld4(g + r + 4), c = ld4(g + r + 8);
 		Xform X;
-#pragma unroll
-		for (int i = 0; i < 9; ++i)
-			X.R[i] = ld(r + i);
-		X.p = v(p);
+		X.R[0] = a.x, X.R[1] = a.y, X.R[2] = a.z, X.R[3] = a.w;
+		X.R[4] = b.x, X.R[5] = b.y, X.R[6] = b.z, X.R[7] = b.w;
+		X.R[8] = c.x;
+		X.p    = mk(c.y, c.z, c.w);
 		return X;
 	}
-	__device__ __forceinline__ Xform X_WA() const { return xf(0, CTX_XA); }          // soft geom A -> world
-	__device__ __forceinline__ Xform X_AB() const { return xf(CTX_RAB, CTX_PAB); }   // geom B -> geom A
-	__device__ __forceinline__ D3 p_BAo() const { return v(CTX_PBA); }               // origin of A in B
-	__device__ __forceinline__ D3 xA() const { return v(CTX_XA); } // origin, angular, linear velocity (world)
+	__device__ __forceinline__ Xform X_WA() const { return xf(0); }        // soft geom A -> world
+	__device__ __forceinline__ Xform X_AB() const { return xf(CTX_RAB); }  // geom B -> geom A
+	__device__ __forceinline__ D3 p_BAo() const { return v(CTX_PBA); }     // origin of A in B
+	__device__ __forceinline__ D3 xA() const                               // origin, angular, linear velocity (world)
+	{
+		D4 c = ld4(g + 8);
+		return mk(c.y, c.z, c.w);
+	}
 	__device__ __forceinline__ D3 wA() const { return v(CTX_WA); }
 	__device__ __forceinline__ D3 vA() const { return v(CTX_VA); }
 	__device__ __forceinline__ D3 xB() const { return v(CTX_XB); }
 	__device__ __forceinline__ D3 wB() const { return v(CTX_WB); }
 	__device__ __forceinline__ D3 vB() const { return v(CTX_VB); }
 };
-typedef PairCtx<false> WarpCtx;
-typedef PairCtx<true> CandCtx;
 
 struct Acc {
 	D3 F, tau, ac;
@@ -111,57 +110,11 @@ struct Acc {
 	int n_polygons, n_faces, n_points, n_candidates, n_clipped;
 };
 
-__device__ __forceinline__ void load_vel(const double *vel, int n_geoms, int env, int g, D3 &w, D3 &v)
-{
-	const double *p = vel + ((size_t)env * n_geoms + g) * 6;
-	w               = ld3(p);
-	v               = ld3(p + 3);
-}
-
-// Lane 0 loads the two poses and velocities, forms X_AB = X_WA^-1 X_WB and parks everything in the warp's
-// shared-memory context block.
-__device__ __forceinline__ WarpCtx make_ctx(const PairDesc &P, const StepIO &io, int env, double *block, int lane)
-{
-	WarpCtx c;
-	c.g = nullptr;
-	c.a = smem_addr(block);
-	if (lane == 0) {
-		Xform X_WA = load_pose(io.xpos, io.xmat, io.n_geoms, env, P.gA);
-		Xform X_WB = load_pose(io.xpos, io.xmat, io.n_geoms, env, P.gB);
-		Xform X_AB = invert_and_compose(X_WA, X_WB);
-		D3 wA, vA, wB, vB;
-		load_vel(io.vel, io.n_geoms, env, P.gA, wA, vA);
-		load_vel(io.vel, io.n_geoms, env, P.gB, wB, vB);
-#pragma unroll
-		for (int i = 0; i < 9; ++i) {
-			block[i]           = X_WA.R[i];
-			block[CTX_RAB + i] = X_AB.R[i];
-		}
-		const D3 trip[7] = { X_WA.p, wA, vA, X_WB.p, wB, vB, X_AB.p };
-		const int off[7] = { CTX_XA, CTX_WA, CTX_VA, CTX_XB, CTX_WB, CTX_VB, CTX_PAB };
-#pragma unroll
-		for (int k = 0; k < 7; ++k) {
-			block[off[k]]     = trip[k].x;
-			block[off[k] + 1] = trip[k].y;
-			block[off[k] + 2] = trip[k].z;
-		}
-	}
-	__syncwarp();
-	c.dissipation = P.dissipation;
-	c.mu          = P.mu;
-	c.sign        = P.sign;
-	c.apply       = io.apply_forces;
-	c.env         = env;
-	c.pair        = P.index;
-	return c;
-}
-
 // context of one candidate of the flat narrowphase: the block the broadphase wrote for its environment
 __device__ __forceinline__ CandCtx cand_ctx(const PairDesc &P, const StepIO &io, int env)
 {
 	CandCtx c;
 	c.g           = P.pair_ctx + (size_t)env * PAIR_CTX_DOUBLES;
-	c.a           = 0;
 	c.dissipation = P.dissipation;
 	c.mu          = P.mu;
 	c.sign        = P.sign;
@@ -573,26 +526,28 @@ __global__ void __launch_bounds__(NP_BLOCK, 4) narrow_tet_tri_kernel(PairDesc P,
 		if (g < total) {
 			int tri = (int)rec.x, tet = (int)rec.y;
 			Acc acc = zero_acc();
-			const TetField &tf = P.A.tet_field[tet];
-			const TriRec &tr   = P.B.tris[tri];
+			const TetField *tf = P.A.tet_field + tet;
+			const TriVerts tr  = load_tri(P.B.tris + tri);
 			// the normal/gradient cull and the trivial reject already ran in the broadphase
 			const Xform X_SR = ctx.X_AB();
-			D3 nS = rot(X_SR.R, ld3(tr.n));
-#pragma unroll
-			for (int k = 0; k < 3; ++k)
-				Poly{ buf0 }.set(k, apply(X_SR, ld3(tr.v[k])));
+			D3 nS = rot(X_SR.R, tr.n);
+			Poly{ buf0 }.set(0, apply(X_SR, tr.v0));
+			Poly{ buf0 }.set(1, apply(X_SR, tr.v1));
+			Poly{ buf0 }.set(2, apply(X_SR, tr.v2));
 			int n = 3;
 #pragma unroll 1
 			for (int k = 0; k < 4; ++k) {
-				n = clip_halfspace(Poly{ buf0 + cur * buf_stride }, n, ld3(tf.plane[k]), tf.plane[k][3], Poly{ buf0 + (cur ^ 1) * buf_stride });
+				D4 pl = load_plane(tf, k);
+				n = clip_halfspace(Poly{ buf0 + cur * buf_stride }, n, xyz(pl), pl.w, Poly{ buf0 + (cur ^ 1) * buf_stride });
 				cur ^= 1;
 			}
 			n      = remove_duplicates(Poly{ buf0 + cur * buf_stride }, n);
 			int nv = 0;
 			if (n >= 3) {
 				nv        = n;
-				D3 grad   = ld3(tf.grad);
-				double e0 = tf.e0;
+				D4 ge     = load_grad_e0(tf);
+				D3 grad   = xyz(ge);
+				double e0 = ge.w;
 #pragma unroll 1
 				for (int k = 0; k < n; ++k)
 					e.set(k, dot(grad, Poly{ buf0 + cur * buf_stride }.get(k)) + e0);
@@ -644,13 +599,13 @@ __global__ void __launch_bounds__(NP_BLOCK, 3) narrow_tet_tet_kernel(PairDesc P,
 			Acc acc = zero_acc();
 			const Xform X_MN = ctx.X_AB();
 			D3 p_NMo         = ctx.p_BAo();
-			const TetField &f0 = P.A.tet_field[t0];
-			const TetField &f1 = P.B.tet_field[t1];
+			const TetField *f0 = P.A.tet_field + t0, *f1 = P.B.tet_field + t1;
 			// CalcEquilibriumPlane
-			D3 grad0 = ld3(f0.grad), grad1_N = ld3(f1.grad);
-			double f0_Mo = f0.e0;
+			const D4 ge0 = load_grad_e0(f0), ge1 = load_grad_e0(f1);
+			D3 grad0 = xyz(ge0), grad1_N = xyz(ge1);
+			double f0_Mo = ge0.w;
 			D3 grad1_M   = rot(X_MN.R, grad1_N);
-			double f1_Mo = dot(grad1_N, p_NMo) + f1.e0;
+			double f1_Mo = dot(grad1_N, p_NMo) + ge1.w;
 			D3 n_M       = grad0 - grad1_M;
 			double mag   = sqrt(dot(n_M, n_M));
 			bool ok      = mag > 0.0;
@@ -660,20 +615,20 @@ __global__ void __launch_bounds__(NP_BLOCK, 3) narrow_tet_tet_kernel(PairDesc P,
 				nhat    = n_M / mag;
 				D3 p_MQ = -((f0_Mo - f1_Mo) / mag) * nhat;
 				pd      = dot(nhat, p_MQ);
-				ok      = dot(nhat, ld3(f0.ghat)) > HCS_COS_ALPHA;
+				ok      = dot(nhat, load_ghat(f0)) > HCS_COS_ALPHA;
 			}
 			if (ok) {
 				D3 rev_N = rotT(X_MN.R, -nhat);
-				ok       = dot(rev_N, ld3(f1.ghat)) > HCS_COS_ALPHA;
+				ok       = dot(rev_N, load_ghat(f1)) > HCS_COS_ALPHA;
 			}
 			int n = 0;
 			if (ok) { // SliceTetrahedronWithPlane(tet0)
-				const TetGeom &g0 = P.A.tet_geom[t0];
+				const TetVerts g0 = load_tet_verts(P.A.tet_geom + t0);
 				double dist[4];
 				int code = 0;
 #pragma unroll
 				for (int k = 0; k < 4; ++k) {
-					dist[k] = dot(nhat, ld3(g0.v[k])) - pd;
+					dist[k] = dot(nhat, g0.at(k)) - pd;
 					if (dist[k] > 0)
 						code |= 1 << k;
 				}
@@ -683,7 +638,7 @@ __global__ void __launch_bounds__(NP_BLOCK, 3) narrow_tet_tet_kernel(PairDesc P,
 					if (edge < 0)
 						break;
 					int l0 = c_tet_edges[edge][0], l1 = c_tet_edges[edge][1];
-					D3 a = ld3(g0.v[l0]), b = ld3(g0.v[l1]);
+					D3 a = g0.at(l0), b = g0.at(l1);
 					double d0 = pick4(dist, l0), d1 = pick4(dist, l1);
 					double t  = d0 / (d0 - d1);
 					Poly{ buf0 }.set(n++, a + t * (b - a));
@@ -692,11 +647,11 @@ __global__ void __launch_bounds__(NP_BLOCK, 3) narrow_tet_tet_kernel(PairDesc P,
 				ok = n >= 3;
 			}
 			if (ok) { // clip by the four half spaces of tet1 expressed in M
-				const TetGeom &g1 = P.B.tet_geom[t1];
+				const TetVerts g1 = load_tet_verts(P.B.tet_geom + t1);
 				D3 pv[4];
 #pragma unroll
 				for (int k = 0; k < 4; ++k)
-					pv[k] = apply(X_MN, ld3(g1.v[k]));
+					pv[k] = apply(X_MN, g1.at(k));
 #pragma unroll
 				for (int k = 0; k < 4; ++k) {
 					if (ok) {
@@ -841,80 +796,86 @@ __device__ __forceinline__ void reduce_unit(const PairDesc &P, const StepIO &io,
 }
 
 // =================================================================================================
-// K5 soft-half-space narrowphase: one thread per tet of the soft geom (no candidate list needed)
+// K5 soft-half-space narrowphase: one thread per tet the plane cuts (classified by the broadphase's plane units):
+// marching-tets slice, cut points along the canonical edge direction, polygon built in the world frame
 // =================================================================================================
 template <bool TRI>
-__global__ void __launch_bounds__(NP_BLOCK, 3) narrow_tet_plane_kernel(PairDesc P, StepIO io)
+__global__ void __launch_bounds__(NP_BLOCK, 4) narrow_tet_plane_kernel(PairDesc P, StepIO io)
 {
-	int warp = (blockIdx.x * NP_BLOCK + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-	int n_units = io.n_env * P.n_slices;
-	if (warp >= n_units)
-		return;
-	int env = warp / P.n_slices, slice = warp - env * P.n_slices;
+	const int lane = threadIdx.x & 31;
 	WarpTile<4> &T = reinterpret_cast<WarpTile<4> *>(smem_d)[threadIdx.x >> 5];
 	Poly poly{ smem_addr(&T.xyz[0][0][0][lane]) };
 	PressTile e{ smem_addr(&T.e[0][lane]) };
-	Acc acc     = zero_acc();
-	WarpCtx ctx = make_ctx(P, io, env, T.ctx, lane);
-	const Xform X_WS = ctx.X_WA(), X_SR = ctx.X_AB();
-	D3 n_S     = mk(X_SR.R[2], X_SR.R[5], X_SR.R[8]);
-	double pd  = dot(n_S, X_SR.p);
-	D3 nhat_W  = rot(X_WS.R, n_S);
-	const double kInf = __longlong_as_double(0x7ff0000000000000LL);
-	int q_begin = slice * P.slice_q, q_end = min(P.nq, q_begin + P.slice_q);
-	uint8_t *nvout = P.nverts + (size_t)env * P.nq;
+	const int total    = flat_total(P, io);
+	const int n_chunks = (total + 31) >> 5;
+	const double kInf  = __longlong_as_double(0x7ff0000000000000LL);
 #pragma unroll 1
-	for (int q0 = q_begin; q0 < q_end; q0 += 32) {
-		int t      = q0 + lane;
+	for (;;) { // flat over the cut tets of the batch, see narrow_tet_tri_kernel
+		int chunk = next_chunk(P.counters + 1, lane);
+		if (chunk >= n_chunks)
+			break;
+		int g      = chunk * 32 + lane;
 		int tfaces = 0;
 		D3 cen     = mk(0, 0, 0);
 		double ec  = 0;
-		if (t < q_end) {
-			acc.n_candidates += 1;
-			const TetGeom &g = P.A.tet_geom[t];
+		int env    = 0;
+		uint4 rec  = make_uint4(0, 0, 0, 0); // (-, tet, unit, index inside the unit)
+		if (g < total) {
+			rec = P.flat[g];
+			env = (int)rec.z / P.n_slices;
+		}
+		CandCtx ctx = cand_ctx(P, io, env);
+		if (g < total) {
+			const int t = (int)rec.y;
+			Acc acc     = zero_acc();
+			const Xform X_WS = ctx.X_WA(), X_SR = ctx.X_AB();
+			D3 n_S     = mk(X_SR.R[2], X_SR.R[5], X_SR.R[8]);
+			double pd  = dot(n_S, X_SR.p);
+			D3 nhat_W  = rot(X_WS.R, n_S);
+			const TetVerts tg = load_tet_verts(P.A.tet_geom + t);
+			const D4 te       = load_tet_pressures(P.A.tet_geom + t);
 			double dist[4];
 			int code = 0;
 #pragma unroll
 			for (int k = 0; k < 4; ++k) {
-				dist[k] = dot(n_S, ld3(g.v[k])) - pd;
+				dist[k] = dot(n_S, tg.at(k)) - pd;
 				if (dist[k] > 0)
 					code |= 1 << k;
 			}
-			int nv = 0;
-			if (code != 0 && code != 15) {
-				acc.n_clipped += 1;
-				int4 gid4 = reinterpret_cast<const int4 *>(P.A.elems)[t];
+			int nv    = 0;
+			int4 gid4 = reinterpret_cast<const int4 *>(P.A.elems)[t];
 #pragma unroll 1
-				for (int ed = 0; ed < 4; ++ed) {
-					int edge = c_marching_tets[code][ed];
-					if (edge < 0)
-						break;
-					int l0 = c_tet_edges[edge][0], l1 = c_tet_edges[edge][1];
-					int g0 = l0 == 0 ? gid4.x : (l0 == 1 ? gid4.y : (l0 == 2 ? gid4.z : gid4.w));
-					int g1 = l1 == 0 ? gid4.x : (l1 == 1 ? gid4.y : (l1 == 2 ? gid4.z : gid4.w));
-					if (g0 > g1) { // canonical direction: lower global vertex id first
-						int tmp = l0;
-						l0      = l1;
-						l1      = tmp;
-					}
-					double d0 = pick4(dist, l0), d1 = pick4(dist, l1);
-					D3 a = ld3(g.v[l0]), b = ld3(g.v[l1]);
-					double tt  = d0 / (d0 - d1);
-					D3 pc      = a + tt * (b - a);
-					e.set(nv, g.e[l0] + tt * (g.e[l1] - g.e[l0]));
-					poly.set(nv, apply(X_WS, pc));
-					++nv;
+			for (int ed = 0; ed < 4; ++ed) {
+				int edge = c_marching_tets[code][ed];
+				if (edge < 0)
+					break;
+				int l0 = c_tet_edges[edge][0], l1 = c_tet_edges[edge][1];
+				int g0 = l0 == 0 ? gid4.x : (l0 == 1 ? gid4.y : (l0 == 2 ? gid4.z : gid4.w));
+				int g1 = l1 == 0 ? gid4.x : (l1 == 1 ? gid4.y : (l1 == 2 ? gid4.z : gid4.w));
+				if (g0 > g1) { // canonical direction: lower global vertex id first
+					int tmp = l0;
+					l0      = l1;
+					l1      = tmp;
 				}
-				D3 grad_W = rot(X_WS.R, ld3(P.A.tet_field[t].grad));
+				double d0 = pick4(dist, l0), d1 = pick4(dist, l1);
+				D3 a = tg.at(l0), b = tg.at(l1);
+				double tt = d0 / (d0 - d1);
+				D3 pc     = a + tt * (b - a);
+				e.set(nv, pick(te, l0) + tt * (pick(te, l1) - pick(te, l0)));
+				poly.set(nv, apply(X_WS, pc));
+				++nv;
+			}
+			if (nv >= 3) {
+				D3 grad_W = rot(X_WS.R, xyz(load_grad_e0(P.A.tet_field + t)));
 				integrate_polygon<TRI, true>(poly, nv, nhat_W, grad_W, e, kInf, ctx, io, t, 0, acc, cen, ec);
 				tfaces = nv;
 			}
-			nvout[t] = (uint8_t)nv;
+			store_contrib(P, g, acc); // always: see narrow_tet_tri_kernel
+			P.nverts[g] = (uint8_t)(nv | (acc.n_points << 4));
 		}
 		if (TRI && P.emit_tactile)
-			emit_tactile<true>(tfaces, poly, e, cen, ec, ctx, io, 0, t, lane);
+			emit_tactile<true>(tfaces, poly, e, cen, ec, ctx, io, (int)rec.z - env * P.n_slices, (int)rec.w, lane);
 	}
-	reduce_and_store(acc, P.partial + warp, lane);
 }
 
 // =================================================================================================
@@ -970,7 +931,7 @@ __device__ __forceinline__ void publish_flags(const StepIO &io)
 __global__ void __launch_bounds__(NP_BLOCK) reduce_units_kernel(const PairDesc *pairs, StepIO io)
 {
 	const PairDesc &P = pairs[blockIdx.y];
-	if (P.kind != PAIR_SOFT_RIGID && P.kind != PAIR_SOFT_SOFT)
+	if (P.kind == PAIR_NONE)
 		return;
 	int warp = (blockIdx.x * NP_BLOCK + threadIdx.x) >> 5;
 	if (warp < io.n_env * P.n_slices)
@@ -984,7 +945,7 @@ __global__ void __launch_bounds__(128) finalize_kernel(const PairDesc *pairs, St
 	if (with_phase1) {
 		for (int p = 0; p < io.n_pairs; ++p) {
 			const PairDesc &P = pairs[p];
-			if (P.kind != PAIR_SOFT_RIGID && P.kind != PAIR_SOFT_SOFT)
+			if (P.kind == PAIR_NONE)
 				continue;
 			for (int s = wid; s < P.n_slices; s += n_warps)
 				reduce_unit(P, io, env * P.n_slices + s, lane);
@@ -1045,20 +1006,10 @@ __global__ void __launch_bounds__(32 * FIN_WARPS) finalize_env_group_kernel(cons
 		r.gM = P.gM, r.gN = P.gN;
 		r.n_polygons = r.n_faces = r.n_points = r.n_candidates = r.n_clipped = r.reserved = 0;
 		if (P.kind != PAIR_NONE) {
-			const bool list = P.kind == PAIR_SOFT_RIGID || P.kind == PAIR_SOFT_SOFT;
-			double ac[3]    = { 0, 0, 0 };
+			double ac[3] = { 0, 0, 0 };
 			for (int s = 0; s < P.n_slices; ++s) {
 				const int unit = env * P.n_slices + s;
-				Acc t          = zero_acc();
-				if (list) {
-					t = unit_sums<W>(P, io, unit, sub, valid);
-				} else if (valid) { // half-space pairs: K5 wrote the unit's sums
-					const SlicePartial &sp = P.partial[unit];
-					t.F = mk(sp.F[0], sp.F[1], sp.F[2]), t.tau = mk(sp.tau[0], sp.tau[1], sp.tau[2]);
-					t.ac = mk(sp.ac[0], sp.ac[1], sp.ac[2]), t.area = sp.area;
-					t.n_polygons = sp.n_polygons, t.n_faces = sp.n_faces, t.n_points = sp.n_points;
-					t.n_candidates = sp.n_candidates, t.n_clipped = sp.n_clipped;
-				}
+				Acc t          = unit_sums<W>(P, io, unit, sub, valid);
 				r.F[0] += t.F.x, r.F[1] += t.F.y, r.F[2] += t.F.z;
 				r.tau[0] += t.tau.x, r.tau[1] += t.tau.y, r.tau[2] += t.tau.z;
 				ac[0] += t.ac.x, ac[1] += t.ac.y, ac[2] += t.ac.z;
@@ -1110,7 +1061,6 @@ void launch_narrowphase(const PairDesc &P, const StepIO &io, cudaStream_t s)
 	long units = (long)io.n_env * P.n_slices;
 	if (units == 0)
 		return;
-	int grid = (int)((units + NP_WARPS - 1) / NP_WARPS);
 	bool tri = io.representation == HCS_REP_TRIANGLE;
 	// flat kernels: resident CTAs of every SM pull chunks from the work counter; never more CTAs than chunks
 	long max_chunks = ((long)P.contrib_cap + 31) / 32;
@@ -1132,9 +1082,9 @@ void launch_narrowphase(const PairDesc &P, const StepIO &io, cudaStream_t s)
 			break;
 		case PAIR_SOFT_PLANE:
 			if (tri)
-				launch_np<4>(narrow_tet_plane_kernel<true>, grid, P, io, s);
+				launch_np<4>(narrow_tet_plane_kernel<true>, flat_grid(4), P, io, s);
 			else
-				launch_np<4>(narrow_tet_plane_kernel<false>, grid, P, io, s);
+				launch_np<4>(narrow_tet_plane_kernel<false>, flat_grid(4), P, io, s);
 			break;
 		default:
 			break;

@@ -1,0 +1,45 @@
+// 256-bit gathers of the resident geometry records (hcs_internal.h): one LDG.E.256 per 32-byte group.
+// Every lane of a gather kernel reads another record, so each load instruction costs 32 L1 wavefronts whatever
+// its width; reading a 192-byte TetField with 6 loads instead of 24 is what matters (profiles/r01_notes.md).
+#pragma once
+#include "dmath.cuh"
+#include "hcs_internal.h"
+
+namespace hcs {
+
+struct TetVerts {
+	D3 v0, v1, v2, v3;
+	__device__ __forceinline__ D3 at(int i) const { return i == 0 ? v0 : (i == 1 ? v1 : (i == 2 ? v2 : v3)); }
+};
+__device__ __forceinline__ TetVerts load_tet_verts(const TetGeom *g) // v[4][3] = three groups
+{
+	const double *p = reinterpret_cast<const double *>(g);
+	D4 a = ld4(p), b = ld4(p + 4), c = ld4(p + 8);
+	TetVerts t;
+	t.v0 = mk(a.x, a.y, a.z), t.v1 = mk(a.w, b.x, b.y), t.v2 = mk(b.z, b.w, c.x), t.v3 = mk(c.y, c.z, c.w);
+	return t;
+}
+__device__ __forceinline__ D4 load_tet_pressures(const TetGeom *g) // e[4] = the fourth group
+{
+	return ld4(reinterpret_cast<const double *>(g) + 12);
+}
+__device__ __forceinline__ double pick(const D4 &q, int i) { return i == 0 ? q.x : (i == 1 ? q.y : (i == 2 ? q.z : q.w)); }
+
+struct TriVerts {
+	D3 v0, v1, v2, n;
+};
+__device__ __forceinline__ TriVerts load_tri(const TriRec *r) // v[3][3] + n[3] = three groups
+{
+	const double *p = reinterpret_cast<const double *>(r);
+	D4 a = ld4(p), b = ld4(p + 4), c = ld4(p + 8);
+	TriVerts t;
+	t.v0 = mk(a.x, a.y, a.z), t.v1 = mk(a.w, b.x, b.y), t.v2 = mk(b.z, b.w, c.x), t.n = mk(c.y, c.z, c.w);
+	return t;
+}
+
+// TetField groups: plane[0..3] (unit normal + offset), {grad, e0}, {ghat, -}
+__device__ __forceinline__ D4 load_plane(const TetField *f, int k) { return ld4(reinterpret_cast<const double *>(f) + 4 * k); }
+__device__ __forceinline__ D4 load_grad_e0(const TetField *f) { return ld4(reinterpret_cast<const double *>(f) + 16); }
+__device__ __forceinline__ D3 load_ghat(const TetField *f) { return xyz(ld4(reinterpret_cast<const double *>(f) + 20)); }
+
+} // namespace hcs
