@@ -29,7 +29,7 @@ struct __align__(32) TriRec { // 96 B = 3 x 32 B: rigid triangle vertices + unit
 	double v[3][3];
 	double n[3];
 };
-struct __align__(16) BvhNode { // 64 B: both children's boxes live in the parent
+struct __align__(32) BvhNode { // 64 B = 2 x 32 B: both children's boxes live in the parent
 	float llo[3], lhi[3], rlo[3], rhi[3];
 	int32_t left, right; // >= 0 internal node, < 0 leaf holding element ~child
 	float pad[2];
