@@ -110,6 +110,9 @@ struct hcs_ctx {
 	int32_t *dh_flags       = nullptr;
 	int64_t kernels_last_step = 0;
 	bool profiling = false;
+	static constexpr int N_AUX = 4;
+	cudaStream_t aux[N_AUX]{};
+	cudaEvent_t ev_join[N_AUX]{}, ev_fork = nullptr;
 	cudaEvent_t ev[8]{};
 	float stage_ms[7]{};
 	bool results_on_host = false, pairs_on_host = false, sensors_on_host = false, last_with_sensors = false;
@@ -745,25 +748,53 @@ static void step_device(hcs_ctx *c, const double *xpos, const double *xmat, cons
 	CK(cudaMemsetAsync(c->d_counters, 0, c->n_counters * sizeof(int32_t), s)); // flags, pool counts, flat-list counters
 	if (prof)
 		CK(cudaEventRecord(c->ev[1], s));
-	int list_slices = 0, list_units = 0; // most slices among the candidate-list pairs; their (pair, slice) units per env
+	int list_slices = 0, list_units = 0, n_active = 0; // most slices among the pairs; their (pair, slice) units per env
 	bool small_units = true;
 	for (const PairDesc &P : c->pair_desc)
 		if (P.kind != PAIR_NONE) {
-			launch_broadphase(P, io, s);
-			++k;
+			++n_active;
 			list_slices = std::max(list_slices, P.n_slices);
 			list_units += P.n_slices;
 			small_units = small_units && std::min(P.nq, P.n_tree) <= 256;
 		}
-	if (prof)
-		CK(cudaEventRecord(c->ev[2], s));
-	for (const PairDesc &P : c->pair_desc)
-		if (P.kind != PAIR_NONE) {
-			launch_narrowphase(P, io, s);
-			++k;
+	// Scenes with several pairs: each pair's broadphase -> narrowphase chain goes to one of N_AUX side streams, so
+	// the pairs' kernels overlap (launch latencies, ramp-up and tails of one pair are filled by the others) instead
+	// of running as 2 x n_pairs serialised launches; the main stream joins them before the finalize.  With stage
+	// profiling on, everything stays on the main stream so that the stage events mean what they say.
+	static const bool allow_fork = getenv("HCS_NO_FORK") == nullptr;
+	if (allow_fork && !prof && n_active > 1) {
+		CK(cudaEventRecord(c->ev_fork, s));
+		int j = 0;
+		for (const PairDesc &P : c->pair_desc)
+			if (P.kind != PAIR_NONE) {
+				cudaStream_t st = c->aux[j % hcs_ctx::N_AUX];
+				if (j < hcs_ctx::N_AUX)
+					CK(cudaStreamWaitEvent(st, c->ev_fork, 0));
+				launch_broadphase(P, io, st);
+				launch_narrowphase(P, io, st);
+				k += 2;
+				++j;
+			}
+		for (int i = 0; i < std::min(j, (int)hcs_ctx::N_AUX); ++i) {
+			CK(cudaEventRecord(c->ev_join[i], c->aux[i]));
+			CK(cudaStreamWaitEvent(s, c->ev_join[i], 0));
 		}
-	if (prof)
-		CK(cudaEventRecord(c->ev[3], s));
+	} else {
+		for (const PairDesc &P : c->pair_desc)
+			if (P.kind != PAIR_NONE) {
+				launch_broadphase(P, io, s);
+				++k;
+			}
+		if (prof)
+			CK(cudaEventRecord(c->ev[2], s));
+		for (const PairDesc &P : c->pair_desc)
+			if (P.kind != PAIR_NONE) {
+				launch_narrowphase(P, io, s);
+				++k;
+			}
+		if (prof)
+			CK(cudaEventRecord(c->ev[3], s));
+	}
 	k += launch_finalize(c->d_pairs, io, list_slices, list_units, small_units, s);
 	if (prof)
 		CK(cudaEventRecord(c->ev[4], s));
@@ -888,6 +919,11 @@ int hcs_create(const hcs_config *cfg, hcs_ctx **out)
 		}
 		for (auto &ev : c->ev)
 			CK(cudaEventCreate(&ev));
+		for (int i = 0; i < hcs_ctx::N_AUX; ++i) { // side streams for the per-pair kernels of multi-pair scenes
+			CK(cudaStreamCreateWithFlags(&c->aux[i], cudaStreamNonBlocking));
+			CK(cudaEventCreateWithFlags(&c->ev_join[i], cudaEventDisableTiming));
+		}
+		CK(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
 	} catch (const std::exception &ex) {
 		g_create_error = ex.what();
 		delete c;
@@ -909,6 +945,14 @@ void hcs_destroy(hcs_ctx *c)
 	for (auto &ev : c->ev)
 		if (ev)
 			cudaEventDestroy(ev);
+	for (int i = 0; i < hcs_ctx::N_AUX; ++i) {
+		if (c->aux[i])
+			cudaStreamDestroy(c->aux[i]);
+		if (c->ev_join[i])
+			cudaEventDestroy(c->ev_join[i]);
+	}
+	if (c->ev_fork)
+		cudaEventDestroy(c->ev_fork);
 	if (c->own_stream)
 		cudaStreamDestroy(c->stream);
 	delete c;

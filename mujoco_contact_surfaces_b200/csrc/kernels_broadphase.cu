@@ -163,18 +163,37 @@ __device__ __forceinline__ void plane_unit(const PairDesc &P, const StepIO &io, 
 	const unsigned lt_mask = (1u << lane) - 1u;
 	// the whole geom above the plane: nothing can be cut
 	bool above = dot(n_S, mk(P.A.bound_c[0], P.A.bound_c[1], P.A.bound_c[2])) - pd > P.A.bound_r + 1e-9;
+	// 32 consecutive tets = 32 x 96 bytes of vertices at a 128-byte stride.  Lane-per-record loads touch 32 lines per
+	// instruction; instead the warp reads the 96 groups of 32 bytes in index order (11 lines per instruction) and
+	// transposes them through shared memory (rows padded to 13 doubles: conflict-free column reads).
+	constexpr int ROW = 13;
+	double *rows      = reinterpret_cast<double *>(W.nodeq); // 32 x 13 doubles = 3328 B of the (unused) queues
+	static_assert(sizeof(W.nodeq) + sizeof(W.leafq) >= 32 * ROW * sizeof(double), "transpose buffer");
 	for (int q0 = q_begin; q0 < q_end && !above; q0 += 32) {
+		const int n_here = min(32, q_end - q0);
+		const double *base = reinterpret_cast<const double *>(P.A.tet_geom + q0);
+#pragma unroll
+		for (int k = 0; k < 3; ++k) {
+			int j = lane + 32 * k, r = j / 3, part = j - 3 * r; // group j = (record r, 32-byte part)
+			if (r < n_here) {
+				D4 gq     = ld4(base + 16 * r + 4 * part);
+				double *o = rows + ROW * r + 4 * part;
+				o[0] = gq.x, o[1] = gq.y, o[2] = gq.z, o[3] = gq.w;
+			}
+		}
+		__syncwarp();
 		int t     = q0 + lane;
 		bool keep = false;
 		if (t < q_end) {
-			const TetVerts g = load_tet_verts(P.A.tet_geom + t);
+			const double *gv = rows + ROW * lane;
 			int code = 0;
 #pragma unroll
 			for (int k = 0; k < 4; ++k)
-				if (dot(n_S, g.at(k)) - pd > 0)
+				if (dot(n_S, mk(gv[3 * k], gv[3 * k + 1], gv[3 * k + 2])) - pd > 0)
 					code |= 1 << k;
 			keep = code != 0 && code != 15;
 		}
+		__syncwarp();
 		unsigned mk_ = __ballot_sync(FULL_MASK, keep);
 		if (keep)
 			W.stage[n_stage + __popc(mk_ & lt_mask)] = make_uint2(0u, (unsigned)t);
