@@ -5,10 +5,12 @@
 //                              spaces, duplicate removal, polygon quadrature (mujoco_contact_surfaces_plugin.
 //                              cpp:320-409) and the force law (plugin.cpp:411-483).  Restates Drake
 //                              mesh_intersection.cc.
-//   K5 narrow_tet_plane_kernel one thread per (tet, half space): marching-tets slice (App. A.5).
+//   K5 narrow_tet_plane_kernel one thread per tet the half space cuts (classified by the broadphase's plane units):
+//                              marching-tets slice (App. A.5).
 //   K6 narrow_tet_tet_kernel   one thread per (tet, tet) candidate: equal-pressure plane, slice + clip (A.6).
-//   K7 finalize kernels        fixed-order reduction of the per-warp partial sums to per-pair wrenches and
+//   K7 finalize kernels        fixed-order reduction of the per-candidate contributions to per-pair wrenches and
 //                              per-geom wrenches (replaces two mj_applyFT per face, plugin.cpp:477-482).
+// All three narrowphase kernels are flat over the batch: warps pull 32-candidate chunks of the pair's candidate list.
 //
 // Polygon vertices live in a lane-interleaved shared-memory tile ([vertex][coord][lane], conflict free),
 // loops over vertices / planes are deliberately NOT unrolled: the first version inlined everything into
@@ -24,7 +26,6 @@
 namespace hcs {
 
 #define FULL_MASK 0xffffffffu
-constexpr int MAXV     = 8; // tet-tet; tet-triangle polygons have <= 7 vertices, plane slices <= 4
 constexpr int NP_WARPS = 4;
 constexpr int NP_BLOCK = 32 * NP_WARPS;
 
@@ -389,26 +390,6 @@ __device__ __forceinline__ void emit_tactile(int n_faces, Poly P, PressTile e, D
 	}
 }
 
-// fixed xor-shuffle tree over the lanes; every lane ends up with the warp's totals
-__device__ __forceinline__ Acc warp_sum(Acc acc)
-{
-	double d[10] = { acc.F.x, acc.F.y, acc.F.z, acc.tau.x, acc.tau.y, acc.tau.z, acc.area, acc.ac.x, acc.ac.y, acc.ac.z };
-	int n[5]     = { acc.n_polygons, acc.n_faces, acc.n_points, acc.n_candidates, acc.n_clipped };
-#pragma unroll
-	for (int o = 16; o > 0; o >>= 1) {
-#pragma unroll
-		for (int k = 0; k < 10; ++k)
-			d[k] += __shfl_xor_sync(FULL_MASK, d[k], o);
-#pragma unroll
-		for (int k = 0; k < 5; ++k)
-			n[k] += __shfl_xor_sync(FULL_MASK, n[k], o);
-	}
-	Acc r;
-	r.F = mk(d[0], d[1], d[2]), r.tau = mk(d[3], d[4], d[5]), r.area = d[6], r.ac = mk(d[7], d[8], d[9]);
-	r.n_polygons = n[0], r.n_faces = n[1], r.n_points = n[2], r.n_candidates = n[3], r.n_clipped = n[4];
-	return r;
-}
-
 __device__ __forceinline__ void store_partial(const Acc &t, SlicePartial *out)
 {
 	SlicePartial sp;
@@ -420,25 +401,6 @@ __device__ __forceinline__ void store_partial(const Acc &t, SlicePartial *out)
 	sp.n_candidates = t.n_candidates, sp.n_clipped = t.n_clipped;
 	sp.pad = 0;
 	*out   = sp;
-}
-
-__device__ __forceinline__ void reduce_and_store(Acc acc, SlicePartial *out, int lane)
-{
-	Acc t = warp_sum(acc);
-	if (lane == 0)
-		store_partial(t, out);
-}
-
-__device__ __forceinline__ void store_zero(SlicePartial *out, int n_candidates)
-{
-	SlicePartial sp;
-	for (int k = 0; k < 3; ++k)
-		sp.F[k] = sp.tau[k] = sp.ac[k] = 0;
-	sp.area = 0;
-	sp.n_polygons = sp.n_faces = sp.n_points = 0;
-	sp.n_candidates = n_candidates;
-	sp.n_clipped = sp.pad = 0;
-	*out = sp;
 }
 
 __device__ __forceinline__ Acc zero_acc()
@@ -716,7 +678,7 @@ __device__ __forceinline__ Contrib load_contrib(const PairDesc &P, int g)
 __device__ __forceinline__ void add_contrib(Acc &acc, const Contrib &c, int b, bool tri)
 {
 	int n = b & 15;
-	if (n >= 3) { // candidates without a polygon never wrote their slot: what was loaded from it is discarded
+	if (n >= 3) { // candidates without a polygon wrote a record of zeros
 		acc.n_polygons += 1;
 		acc.n_faces += tri ? n : 1;
 		acc.n_points += b >> 4;
