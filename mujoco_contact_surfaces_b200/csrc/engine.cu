@@ -762,7 +762,8 @@ static void step_device(hcs_ctx *c, const double *xpos, const double *xmat, cons
 	// of running as 2 x n_pairs serialised launches; the main stream joins them before the finalize.  With stage
 	// profiling on, everything stays on the main stream so that the stage events mean what they say.
 	static const bool allow_fork = getenv("HCS_NO_FORK") == nullptr;
-	if (allow_fork && !prof && n_active > 1) {
+	const bool forked = allow_fork && !prof && n_active > 1;
+	if (forked) {
 		CK(cudaEventRecord(c->ev_fork, s));
 		int j = 0;
 		for (const PairDesc &P : c->pair_desc)
@@ -771,7 +772,7 @@ static void step_device(hcs_ctx *c, const double *xpos, const double *xmat, cons
 				if (j < hcs_ctx::N_AUX)
 					CK(cudaStreamWaitEvent(st, c->ev_fork, 0));
 				launch_broadphase(P, io, st);
-				launch_narrowphase(P, io, st);
+				launch_narrowphase(P, io, st, /*chained=*/true);
 				k += 2;
 				++j;
 			}
@@ -789,13 +790,13 @@ static void step_device(hcs_ctx *c, const double *xpos, const double *xmat, cons
 			CK(cudaEventRecord(c->ev[2], s));
 		for (const PairDesc &P : c->pair_desc)
 			if (P.kind != PAIR_NONE) {
-				launch_narrowphase(P, io, s);
+				launch_narrowphase(P, io, s, /*chained=*/!prof);
 				++k;
 			}
 		if (prof)
 			CK(cudaEventRecord(c->ev[3], s));
 	}
-	k += launch_finalize(c->d_pairs, io, list_slices, list_units, small_units, s);
+	k += launch_finalize(c->d_pairs, io, list_slices, list_units, small_units, s, /*chained=*/!prof && !forked);
 	if (prof)
 		CK(cudaEventRecord(c->ev[4], s));
 	if (with_sensors) {

@@ -178,6 +178,34 @@ struct TaxelDev {
 	int items_cap;
 };
 
+// ---- programmatic dependent launch (sm_90+) -------------------------------------------------------
+// The step is a chain of short kernels (C1: 50 + 39 + 14 us).  A kernel launched with launch_chained may become
+// resident while its predecessor in the stream is still draining: the predecessor's CTAs call pdl_release() on entry,
+// the successor's CTAs fill the SMs as those CTAs exit and block in pdl_wait() until the predecessor grid has
+// completed and its writes are visible.  Nothing before pdl_wait() may touch data the predecessor produces.
+// Launched the ordinary way (HCS_NO_PDL=1, or with stage events in between) both calls are no-ops.
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_release() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+template <class... KArgs, class... Args>
+static inline void launch_chained(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args... args)
+{
+	static const bool use_pdl = getenv("HCS_NO_PDL") == nullptr;
+	cudaLaunchConfig_t cfg{};
+	cfg.gridDim          = grid;
+	cfg.blockDim         = block;
+	cfg.dynamicSmemBytes = smem;
+	cfg.stream           = s;
+	cudaLaunchAttribute at[1];
+	at[0].id                                         = cudaLaunchAttributeProgrammaticStreamSerialization;
+	at[0].val.programmaticStreamSerializationAllowed = 1;
+	cfg.attrs    = at;
+	cfg.numAttrs = use_pdl ? 1 : 0;
+	cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+#endif
+
 // ---- launchers (definitions in the .cu files) ---------------------------------------------------
 void launch_build_tets(const GeomDev &g, cudaStream_t s);
 void launch_build_tris(const GeomDev &g, cudaStream_t s);
@@ -186,11 +214,12 @@ size_t lbvh_scratch_bytes(int n);
 void launch_build_lbvh(const GeomDev &g, const double glo[3], const double ghi[3], void *scratch, cudaStream_t s);
 
 void launch_broadphase(const PairDesc &P, const StepIO &io, cudaStream_t s);
-void launch_narrowphase(const PairDesc &P, const StepIO &io, cudaStream_t s);
+// chained: the kernel directly behind it in the stream is the one whose output it consumes (launch_chained above)
+void launch_narrowphase(const PairDesc &P, const StepIO &io, cudaStream_t s, bool chained);
 // returns the number of kernels launched
 // small_units: every candidate-list pair has few elements on one side (units hold tens of candidates, not thousands)
 int launch_finalize(const PairDesc *d_pairs, const StepIO &io, int max_list_slices, int list_units_per_env,
-                    bool small_units, cudaStream_t s);
+                    bool small_units, cudaStream_t s, bool chained);
 
 // clear, count, scan, fill, rasterise for all sensors (host copy + device copy of the records); returns the number
 // of kernels launched

@@ -212,6 +212,20 @@ __device__ __forceinline__ void plane_unit(const PairDesc &P, const StepIO &io, 
 	}
 }
 
+// records the leaf test of tet t will gather: TetField (192 bytes, two lines; soft-soft reads only the second: gradient
+// and ghat) and the tet's vertices
+template <bool QTET>
+__device__ __forceinline__ void prefetch_leaf(const PairDesc &P, int t)
+{
+#if HCS_BP_PREFETCH
+	const char *tf = reinterpret_cast<const char *>(P.A.tet_field + t);
+	if (!QTET)
+		asm volatile("prefetch.global.L1 [%0];" ::"l"(tf));
+	asm volatile("prefetch.global.L1 [%0];" ::"l"(tf + 128));
+	asm volatile("prefetch.global.L1 [%0];" ::"l"(P.A.tet_geom + t));
+#endif
+}
+
 // QTET: query elements are tets of B (soft-soft), otherwise triangles of B (soft-rigid)
 template <bool QTET>
 __device__ __forceinline__ void broadphase_unit(const PairDesc &P, const StepIO &io, WarpQueues &W, int warp, int lane)
@@ -432,10 +446,15 @@ __device__ __forceinline__ void broadphase_unit(const PairDesc &P, const StepIO 
 					W.nodeq[n_node + __popc(mL & lt_mask)] = (s << ITEM_SHIFT) | (unsigned)cl;
 				if (pushR)
 					W.nodeq[n_node + nL + __popc(mR & lt_mask)] = (s << ITEM_SHIFT) | (unsigned)cr;
-				if (leafL)
+				// leaf items wait in the queue for an iteration or more: their records travel meanwhile
+				if (leafL) {
 					W.leafq[n_leaf + __popc(lL & lt_mask)] = (s << ITEM_SHIFT) | (unsigned)~cl;
-				if (leafR)
+					prefetch_leaf<QTET>(P, ~cl);
+				}
+				if (leafR) {
 					W.leafq[n_leaf + nlL + __popc(lR & lt_mask)] = (s << ITEM_SHIFT) | (unsigned)~cr;
+					prefetch_leaf<QTET>(P, ~cr);
+				}
 				n_node += nL + nR;
 				n_leaf += nlL + nlR;
 				__syncwarp();
@@ -452,6 +471,27 @@ __device__ __forceinline__ void broadphase_unit(const PairDesc &P, const StepIO 
 	}
 }
 
+__device__ __forceinline__ int claim_unit(int32_t *counter, int lane)
+{
+	int u = 0;
+	if (lane == 0)
+		u = atomicAdd(counter, 1);
+	return __shfl_sync(FULL_MASK, u, 0);
+}
+// Prefetches (next unit's poses, leaf records at push time) were measured and are off: the L1 data pipe is the busiest
+// unit of this kernel and the extra wavefronts cost more than the latency they hide (C1 broadphase 0.050 -> 0.075 ms).
+#ifndef HCS_BP_PREFETCH
+#define HCS_BP_PREFETCH 0
+#endif
+#ifndef HCS_EARLY_CLAIM
+#define HCS_EARLY_CLAIM 0
+#endif
+__device__ __forceinline__ void prefetch_l1(const void *p)
+{
+#if HCS_BP_PREFETCH
+	asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+#endif
+}
 // Persistent warps: the resident CTAs of every SM pull (env, slice) units from a work counter, so the grid is
 // never a fractional number of waves and a slow unit does not hold three finished warps' resources.
 // KIND: 0 triangles of B against the tet tree of A, 1 tets of B against it, 2 the tets of A against a half space
@@ -462,12 +502,24 @@ __global__ void __launch_bounds__(BP_BLOCK, BP_CTAS_PER_SM) broadphase_kernel(Pa
 	WarpQueues &W     = sm[threadIdx.x >> 5];
 	const int lane    = threadIdx.x & 31;
 	const int n_units = io.n_env * P.n_slices;
+	pdl_release(); // the pair's narrowphase may become resident while this grid drains (it waits for our completion)
 #if HCS_BP_PERSISTENT
+	// HCS_EARLY_CLAIM=1 issues the work-counter atomic for the next unit before the current unit starts (its round
+	// trip is 4 % of the stall samples); measured slower (0.0503 -> 0.0550 ms on C1) and off by default.
+#if HCS_EARLY_CLAIM
+	int unit = claim_unit(P.counters + 2, lane);
+	while (unit < n_units) {
+		const int requested = lane == 0 ? atomicAdd(P.counters + 2, 1) : 0;
+		if (KIND == 2)
+			plane_unit(P, io, W, unit, lane);
+		else
+			broadphase_unit<KIND == 1>(P, io, W, unit, lane);
+		__syncwarp();
+		unit = __shfl_sync(FULL_MASK, requested, 0);
+	}
+#else
 	for (;;) {
-		int unit = 0;
-		if (lane == 0)
-			unit = atomicAdd(P.counters + 2, 1);
-		unit = __shfl_sync(FULL_MASK, unit, 0);
+		int unit = claim_unit(P.counters + 2, lane);
 		if (unit >= n_units)
 			break;
 		if (KIND == 2)
@@ -476,6 +528,7 @@ __global__ void __launch_bounds__(BP_BLOCK, BP_CTAS_PER_SM) broadphase_kernel(Pa
 			broadphase_unit<KIND == 1>(P, io, W, unit, lane);
 		__syncwarp();
 	}
+#endif
 #else
 	int unit = (blockIdx.x * BP_BLOCK + threadIdx.x) >> 5;
 	if (unit < n_units) {

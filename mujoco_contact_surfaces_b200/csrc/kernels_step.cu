@@ -29,12 +29,28 @@ namespace hcs {
 constexpr int NP_WARPS = 4;
 constexpr int NP_BLOCK = 32 * NP_WARPS;
 
-// per-warp shared-memory tile: two polygon buffers + vertex pressures, lane-interleaved
-template <int MV>
+// per-warp shared-memory tile: two polygon buffers, lane-interleaved.  The vertex pressures of the finished polygon
+// go into the buffer the clip no longer needs (MV doubles per lane of its 3 * MV): 43 KB per CTA instead of 50 KB,
+// which is what lets a fifth CTA of the tet-triangle kernel fit into an SM's shared memory.
+// MV1: the second buffer of a clip chain that ends in the first holds one vertex less (tet-triangle: 3 -> 4 -> 5 -> 6
+// -> 7 vertices alternate between the buffers, so the second never holds more than 6; tet-tet: 4 -> ... -> 8, 7).
+template <int MV, int MV1 = MV>
 struct WarpTile {
-	double xyz[2][MV][3][32];
-	double e[MV][32];
+	double xyz[MV][3][32];
+	double xyz1[MV1][3][32];
 };
+#ifndef HCS_NP_TRI_CTAS // resident CTAs per SM the narrowphase kernels are compiled for (tuning sweeps: build.py)
+#define HCS_NP_TRI_CTAS 4
+#endif
+#ifndef HCS_NP_TRI_WARPS // warps per CTA of the tet-triangle kernel
+#define HCS_NP_TRI_WARPS 4
+#endif
+#ifndef HCS_NP_TET_CTAS // 4: 128 registers with ~100 B of spills, C3 narrowphase 1.026 -> 0.946 ms (profiles/r01_notes.md)
+#define HCS_NP_TET_CTAS 4
+#endif
+#ifndef HCS_NP_PLANE_CTAS
+#define HCS_NP_PLANE_CTAS 4
+#endif
 
 // Explicit shared-window accesses: through a generic pointer stored in a struct the compiler emitted
 // generic LD/ST with 64-bit address arithmetic in the clip loop (profiles/r01_notes.md).
@@ -430,6 +446,43 @@ __device__ __forceinline__ int next_chunk(int32_t *counter, int lane)
 		chunk = atomicAdd(counter, 1);
 	return __shfl_sync(FULL_MASK, chunk, 0);
 }
+// The round trip of the work-counter atomic is 7 % of the tet-triangle kernel's stall samples (the warp sits in the
+// shuffle that broadcasts the result).  Asking for the NEXT chunk before the warp starts on the current one
+// (HCS_EARLY_CLAIM=1) was measured and is off: holding the pending atomic across the body made every kernel slower
+// (C1 broadphase 0.0503 -> 0.0550 ms, narrowphase 0.0398 -> 0.0416 ms; profiles/r01_notes.md).
+#ifndef HCS_EARLY_CLAIM
+#define HCS_EARLY_CLAIM 0
+#endif
+__device__ __forceinline__ int request_chunk(int32_t *counter, int lane)
+{
+#if HCS_EARLY_CLAIM
+	return lane == 0 ? atomicAdd(counter, 1) : 0;
+#else
+	return 0;
+#endif
+}
+__device__ __forceinline__ int granted_chunk(int32_t *counter, int requested, int lane)
+{
+#if HCS_EARLY_CLAIM
+	return __shfl_sync(FULL_MASK, requested, 0);
+#else
+	return next_chunk(counter, lane);
+#endif
+}
+// Non-binding L1 prefetch of a line a later, dependent part of the candidate's work will gather (the plane records
+// inside the clip loop, the velocities in the force law): no register is held while the line travels.
+// Measured and left off (HCS_NP_PREFETCH=1 builds it in): every lane prefetches another record, a prefetch costs the
+// L1 data pipe as many wavefronts as the load it anticipates, and that pipe is the busiest unit of these kernels
+// (48 % of peak, ncu); with the prefetches the tet-triangle kernel went from 0.0392 to 0.0412 ms on C1.
+#ifndef HCS_NP_PREFETCH
+#define HCS_NP_PREFETCH 0
+#endif
+__device__ __forceinline__ void prefetch_l1(const void *p)
+{
+#if HCS_NP_PREFETCH
+	asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+#endif
+}
 
 // candidates in the flat list, clamped to the contribution pool (overflow is reported, not UB)
 __device__ __forceinline__ int flat_total(const PairDesc &P, const StepIO &io)
@@ -459,20 +512,20 @@ __device__ __forceinline__ void store_contrib(const PairDesc &P, int g, const Ac
 }
 
 template <bool TRI>
-__global__ void __launch_bounds__(NP_BLOCK, 4) narrow_tet_tri_kernel(PairDesc P, StepIO io)
+__global__ void __launch_bounds__(32 * HCS_NP_TRI_WARPS, HCS_NP_TRI_CTAS) narrow_tet_tri_kernel(PairDesc P, StepIO io)
 {
+	pdl_release(); // the finalize kernel may become resident while this grid drains
+	pdl_wait();    // the broadphase grid has completed: flat list, counters and context blocks are visible
 	const int lane = threadIdx.x & 31;
-	WarpTile<7> &T = reinterpret_cast<WarpTile<7> *>(smem_d)[threadIdx.x >> 5];
-	const unsigned buf0 = smem_addr(&T.xyz[0][0][0][lane]), buf_stride = (unsigned)sizeof(T.xyz[0]);
-	PressTile e{ smem_addr(&T.e[0][lane]) };
+	WarpTile<7, 6> &T = reinterpret_cast<WarpTile<7, 6> *>(smem_d)[threadIdx.x >> 5];
+	const unsigned buf0 = smem_addr(&T.xyz[0][0][lane]), buf_stride = (unsigned)sizeof(T.xyz);
 	const int total    = flat_total(P, io);
 	const int n_chunks = (total + 31) >> 5;
 	const double kInf  = __longlong_as_double(0x7ff0000000000000LL);
+	int chunk = next_chunk(P.counters + 1, lane);
 #pragma unroll 1
-	for (;;) {
-		int chunk = next_chunk(P.counters + 1, lane);
-		if (chunk >= n_chunks)
-			break;
+	while (chunk < n_chunks) {
+		const int requested = request_chunk(P.counters + 1, lane);
 		int g      = chunk * 32 + lane;
 		int tfaces = 0;
 		int cur    = 0;
@@ -489,6 +542,9 @@ __global__ void __launch_bounds__(NP_BLOCK, 4) narrow_tet_tri_kernel(PairDesc P,
 			int tri = (int)rec.x, tet = (int)rec.y;
 			Acc acc = zero_acc();
 			const TetField *tf = P.A.tet_field + tet;
+			prefetch_l1(tf); // 192 bytes = two lines: the four planes of the clip loop, gradient and e0
+			prefetch_l1(reinterpret_cast<const char *>(tf) + 128);
+			prefetch_l1(ctx.g + 32); // third line of the context block: the velocities of the force law
 			const TriVerts tr  = load_tri(P.B.tris + tri);
 			// the normal/gradient cull and the trivial reject already ran in the broadphase
 			const Xform X_SR = ctx.X_AB();
@@ -512,8 +568,9 @@ __global__ void __launch_bounds__(NP_BLOCK, 4) narrow_tet_tri_kernel(PairDesc P,
 				double e0 = ge.w;
 #pragma unroll 1
 				for (int k = 0; k < n; ++k)
-					e.set(k, dot(grad, Poly{ buf0 + cur * buf_stride }.get(k)) + e0);
-				integrate_polygon<TRI, false>(Poly{ buf0 + cur * buf_stride }, n, nS, grad, e, kInf, ctx, io, tet, tri, acc, cen, ec);
+					PressTile{ buf0 + (cur ^ 1) * buf_stride }.set(k, dot(grad, Poly{ buf0 + cur * buf_stride }.get(k)) + e0);
+				integrate_polygon<TRI, false>(Poly{ buf0 + cur * buf_stride }, n, nS, grad, PressTile{ buf0 + (cur ^ 1) * buf_stride },
+				                              kInf, ctx, io, tet, tri, acc, cen, ec);
 				tfaces = n;
 			}
 			// every candidate writes its record (zeros without a polygon): a 32-byte sector that is only partly
@@ -522,8 +579,9 @@ __global__ void __launch_bounds__(NP_BLOCK, 4) narrow_tet_tri_kernel(PairDesc P,
 			P.nverts[g] = (uint8_t)(nv | (acc.n_points << 4));
 		}
 		if (TRI && P.emit_tactile)
-			emit_tactile<false>(tfaces, Poly{ buf0 + cur * buf_stride }, e, cen, ec, ctx, io,
+			emit_tactile<false>(tfaces, Poly{ buf0 + cur * buf_stride }, PressTile{ buf0 + (cur ^ 1) * buf_stride }, cen, ec, ctx, io,
 			                    (int)rec.z - env * P.n_slices, (int)rec.w, lane);
+		chunk = granted_chunk(P.counters + 1, requested, lane);
 	}
 }
 
@@ -531,19 +589,19 @@ __global__ void __launch_bounds__(NP_BLOCK, 4) narrow_tet_tri_kernel(PairDesc P,
 // K6 soft-soft narrowphase: one thread per (tet of A, tet of B) candidate
 // =================================================================================================
 template <bool TRI>
-__global__ void __launch_bounds__(NP_BLOCK, 3) narrow_tet_tet_kernel(PairDesc P, StepIO io)
+__global__ void __launch_bounds__(NP_BLOCK, HCS_NP_TET_CTAS) narrow_tet_tet_kernel(PairDesc P, StepIO io)
 {
+	pdl_release(); // the finalize kernel may become resident while this grid drains
+	pdl_wait();    // the broadphase grid has completed: flat list, counters and context blocks are visible
 	const int lane = threadIdx.x & 31;
-	WarpTile<8> &T = reinterpret_cast<WarpTile<8> *>(smem_d)[threadIdx.x >> 5];
-	const unsigned buf0 = smem_addr(&T.xyz[0][0][0][lane]), buf_stride = (unsigned)sizeof(T.xyz[0]);
-	PressTile e{ smem_addr(&T.e[0][lane]) };
+	WarpTile<8, 7> &T = reinterpret_cast<WarpTile<8, 7> *>(smem_d)[threadIdx.x >> 5];
+	const unsigned buf0 = smem_addr(&T.xyz[0][0][lane]), buf_stride = (unsigned)sizeof(T.xyz);
 	const int total    = flat_total(P, io);
 	const int n_chunks = (total + 31) >> 5;
+	int chunk = next_chunk(P.counters + 1, lane);
 #pragma unroll 1
-	for (;;) { // flat over the candidates of the batch, see narrow_tet_tri_kernel
-		int chunk = next_chunk(P.counters + 1, lane);
-		if (chunk >= n_chunks)
-			break;
+	while (chunk < n_chunks) { // flat over the candidates of the batch, see narrow_tet_tri_kernel
+		const int requested = request_chunk(P.counters + 1, lane);
 		int g      = chunk * 32 + lane;
 		int tfaces = 0;
 		int cur    = 0;
@@ -562,6 +620,9 @@ __global__ void __launch_bounds__(NP_BLOCK, 3) narrow_tet_tet_kernel(PairDesc P,
 			const Xform X_MN = ctx.X_AB();
 			D3 p_NMo         = ctx.p_BAo();
 			const TetField *f0 = P.A.tet_field + t0, *f1 = P.B.tet_field + t1;
+			prefetch_l1(P.A.tet_geom + t0); // sliced / clipped against further down, behind dependent branches
+			prefetch_l1(P.B.tet_geom + t1);
+			prefetch_l1(ctx.g + 32);        // velocities of the force law
 			// CalcEquilibriumPlane
 			const D4 ge0 = load_grad_e0(f0), ge1 = load_grad_e0(f1);
 			D3 grad0 = xyz(ge0), grad1_N = xyz(ge1);
@@ -639,17 +700,19 @@ __global__ void __launch_bounds__(NP_BLOCK, 3) narrow_tet_tet_kernel(PairDesc P,
 				nv = n;
 #pragma unroll 1
 				for (int k = 0; k < n; ++k)
-					e.set(k, dot(grad0, Poly{ buf0 + cur * buf_stride }.get(k)) + f0_Mo);
+					PressTile{ buf0 + (cur ^ 1) * buf_stride }.set(k, dot(grad0, Poly{ buf0 + cur * buf_stride }.get(k)) + f0_Mo);
 				double gN = -dot(grad1_M, nhat);
-				integrate_polygon<TRI, false>(Poly{ buf0 + cur * buf_stride }, n, nhat, grad0, e, gN, ctx, io, t0, t1, acc, cen, ec);
+				integrate_polygon<TRI, false>(Poly{ buf0 + cur * buf_stride }, n, nhat, grad0, PressTile{ buf0 + (cur ^ 1) * buf_stride },
+				                              gN, ctx, io, t0, t1, acc, cen, ec);
 				tfaces = n;
 			}
 			store_contrib(P, g, acc); // always: see narrow_tet_tri_kernel
 			P.nverts[g] = (uint8_t)(nv | (acc.n_points << 4));
 		}
 		if (TRI && P.emit_tactile)
-			emit_tactile<false>(tfaces, Poly{ buf0 + cur * buf_stride }, e, cen, ec, ctx, io,
+			emit_tactile<false>(tfaces, Poly{ buf0 + cur * buf_stride }, PressTile{ buf0 + (cur ^ 1) * buf_stride }, cen, ec, ctx, io,
 			                    (int)rec.z - env * P.n_slices, (int)rec.w, lane);
+		chunk = granted_chunk(P.counters + 1, requested, lane);
 	}
 }
 
@@ -710,6 +773,12 @@ __device__ __forceinline__ Acc group_sum(Acc acc)
 	return r;
 }
 
+#ifndef HCS_FIN_UNROLL
+#define HCS_FIN_UNROLL 2
+#endif
+#ifndef HCS_FIN_SMALL_W // lanes per environment when the units hold few candidates (C1: 8 -> 0.0147 ms, 16 -> 0.0127 ms)
+#define HCS_FIN_SMALL_W 16
+#endif
 // Totals of one (env, slice) unit on every lane of the group of W lanes that owns it (`sub` = lane inside the group;
 // groups of a warp may own different units, `valid` = this group has one).  Every range but a unit's last holds whole
 // 32-candidate chunks, so lane `sub` always sees the unit's candidates sub, sub + W, ... in increasing order; two
@@ -728,13 +797,20 @@ __device__ __forceinline__ Acc unit_sums(const PairDesc &P, const StepIO &io, in
 		}
 		const bool tri = io.representation == HCS_REP_TRIANGLE;
 		while (rg.y > 0) {
-			for (int j = sub; j < rg.y; j += 2 * W) {
-				int g0 = rg.x + j, g1 = g0 + W;
-				bool in0 = g0 < P.contrib_cap, in1 = j + W < rg.y && g1 < P.contrib_cap;
-				int b0 = in0 ? P.nverts[g0] : 0, b1 = in1 ? P.nverts[g1] : 0;
-				Contrib c0 = load_contrib(P, in0 ? g0 : 0), c1 = load_contrib(P, in1 ? g1 : 0);
-				add_contrib(acc, c0, b0, tri);
-				add_contrib(acc, c1, b1, tri);
+			constexpr int U = HCS_FIN_UNROLL; // candidates per lane in flight; added in index order whatever U is
+			for (int j = sub; j < rg.y; j += U * W) {
+				int b[U];
+				Contrib c[U];
+#pragma unroll
+				for (int u = 0; u < U; ++u) {
+					int g   = rg.x + j + u * W;
+					bool in = j + u * W < rg.y && g < P.contrib_cap;
+					b[u]    = in ? P.nverts[g] : 0;
+					c[u]    = load_contrib(P, in ? g : 0);
+				}
+#pragma unroll
+				for (int u = 0; u < U; ++u)
+					add_contrib(acc, c[u], b[u], tri);
 			}
 			cnt += rg.y;
 			if (rg.z < 0)
@@ -762,20 +838,21 @@ __device__ __forceinline__ void reduce_unit(const PairDesc &P, const StepIO &io,
 // marching-tets slice, cut points along the canonical edge direction, polygon built in the world frame
 // =================================================================================================
 template <bool TRI>
-__global__ void __launch_bounds__(NP_BLOCK, 4) narrow_tet_plane_kernel(PairDesc P, StepIO io)
+__global__ void __launch_bounds__(NP_BLOCK, HCS_NP_PLANE_CTAS) narrow_tet_plane_kernel(PairDesc P, StepIO io)
 {
+	pdl_release(); // the finalize kernel may become resident while this grid drains
+	pdl_wait();    // the broadphase grid has completed: flat list, counters and context blocks are visible
 	const int lane = threadIdx.x & 31;
-	WarpTile<4> &T = reinterpret_cast<WarpTile<4> *>(smem_d)[threadIdx.x >> 5];
-	Poly poly{ smem_addr(&T.xyz[0][0][0][lane]) };
-	PressTile e{ smem_addr(&T.e[0][lane]) };
+	WarpTile<4, 2> &T = reinterpret_cast<WarpTile<4, 2> *>(smem_d)[threadIdx.x >> 5];
+	Poly poly{ smem_addr(&T.xyz[0][0][lane]) };
+	PressTile e{ smem_addr(&T.xyz1[0][0][lane]) }; // the slice needs one polygon buffer; 4 pressures fit 2 vertex rows
 	const int total    = flat_total(P, io);
 	const int n_chunks = (total + 31) >> 5;
 	const double kInf  = __longlong_as_double(0x7ff0000000000000LL);
+	int chunk = next_chunk(P.counters + 1, lane);
 #pragma unroll 1
-	for (;;) { // flat over the cut tets of the batch, see narrow_tet_tri_kernel
-		int chunk = next_chunk(P.counters + 1, lane);
-		if (chunk >= n_chunks)
-			break;
+	while (chunk < n_chunks) { // flat over the cut tets of the batch, see narrow_tet_tri_kernel
+		const int requested = request_chunk(P.counters + 1, lane);
 		int g      = chunk * 32 + lane;
 		int tfaces = 0;
 		D3 cen     = mk(0, 0, 0);
@@ -790,6 +867,8 @@ __global__ void __launch_bounds__(NP_BLOCK, 4) narrow_tet_plane_kernel(PairDesc 
 		if (g < total) {
 			const int t = (int)rec.y;
 			Acc acc     = zero_acc();
+			prefetch_l1(reinterpret_cast<const char *>(P.A.tet_field + t) + 128); // gradient, read after the slice
+			prefetch_l1(ctx.g + 32);                                              // velocities of the force law
 			const Xform X_WS = ctx.X_WA(), X_SR = ctx.X_AB();
 			D3 n_S     = mk(X_SR.R[2], X_SR.R[5], X_SR.R[8]);
 			double pd  = dot(n_S, X_SR.p);
@@ -837,6 +916,7 @@ __global__ void __launch_bounds__(NP_BLOCK, 4) narrow_tet_plane_kernel(PairDesc 
 		}
 		if (TRI && P.emit_tactile)
 			emit_tactile<true>(tfaces, poly, e, cen, ec, ctx, io, (int)rec.z - env * P.n_slices, (int)rec.w, lane);
+		chunk = granted_chunk(P.counters + 1, requested, lane);
 	}
 }
 
@@ -904,6 +984,7 @@ __global__ void __launch_bounds__(NP_BLOCK) reduce_units_kernel(const PairDesc *
 __global__ void __launch_bounds__(128) finalize_kernel(const PairDesc *pairs, StepIO io, int with_phase1)
 {
 	const int env = blockIdx.x, wid = threadIdx.x >> 5, lane = threadIdx.x & 31, n_warps = blockDim.x >> 5;
+	pdl_wait(); // chained behind the last narrowphase kernel when with_phase1 (no-op otherwise)
 	if (with_phase1) {
 		for (int p = 0; p < io.n_pairs; ++p) {
 			const PairDesc &P = pairs[p];
@@ -940,7 +1021,7 @@ __global__ void __launch_bounds__(128) finalize_kernel(const PairDesc *pairs, St
 	publish_flags(io);
 }
 
-// K7 fast path for scenes with few units per environment: a group of W lanes (a whole warp, or 8 lanes when the
+// K7 fast path for scenes with few units per environment: a group of W lanes (a whole warp, or 16 lanes when the
 // units hold few candidates: 4 environments per warp) does all three phases of one environment with the sums in
 // registers / shared memory: no block barrier, nothing written to global memory is read back (the CTA-per-environment
 // kernel spent its time in that chain of dependent round trips, the warp-per-environment version in a 5-step shuffle
@@ -951,6 +1032,7 @@ template <int W>
 __global__ void __launch_bounds__(32 * FIN_WARPS) finalize_env_group_kernel(const PairDesc *pairs, StepIO io)
 {
 	extern __shared__ double fin_smem[]; // [FIN_WARPS * 32 / W][n_geoms][6] wrench accumulators
+	pdl_wait(); // chained behind the last narrowphase kernel (no-op otherwise)
 	constexpr int G = 32 / W;            // environments per warp
 	const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31, grp = lane / W, sub = lane % W;
 	const int env    = (blockIdx.x * FIN_WARPS + wid) * G + grp;
@@ -1009,16 +1091,19 @@ __global__ void __launch_bounds__(32 * FIN_WARPS) finalize_env_group_kernel(cons
 // =================================================================================================
 // launchers
 // =================================================================================================
-template <int MV, class K>
-static void launch_np(K kernel, int grid, const PairDesc &P, const StepIO &io, cudaStream_t s)
+template <class TILE, int WARPS, class K>
+static void launch_np(K kernel, int grid, const PairDesc &P, const StepIO &io, cudaStream_t s, bool chained)
 {
 	// opt in to > 48 KB dynamic shared memory (idempotent and cheap; contexts may live on several devices)
-	const int smem = (int)sizeof(WarpTile<MV>) * NP_WARPS;
+	const int smem = (int)sizeof(TILE) * WARPS;
 	cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-	kernel<<<grid, NP_BLOCK, smem, s>>>(P, io);
+	if (chained)
+		launch_chained(kernel, dim3(grid), dim3(32 * WARPS), (size_t)smem, s, P, io);
+	else
+		kernel<<<grid, 32 * WARPS, smem, s>>>(P, io);
 }
 
-void launch_narrowphase(const PairDesc &P, const StepIO &io, cudaStream_t s)
+void launch_narrowphase(const PairDesc &P, const StepIO &io, cudaStream_t s, bool chained)
 {
 	long units = (long)io.n_env * P.n_slices;
 	if (units == 0)
@@ -1026,27 +1111,27 @@ void launch_narrowphase(const PairDesc &P, const StepIO &io, cudaStream_t s)
 	bool tri = io.representation == HCS_REP_TRIANGLE;
 	// flat kernels: resident CTAs of every SM pull chunks from the work counter; never more CTAs than chunks
 	long max_chunks = ((long)P.contrib_cap + 31) / 32;
-	auto flat_grid  = [&](int ctas_per_sm) {
-		return (int)std::max<long>(1, std::min<long>((long)io.n_sms * ctas_per_sm, (max_chunks + NP_WARPS - 1) / NP_WARPS));
+	auto flat_grid  = [&](int ctas_per_sm, int warps = NP_WARPS) {
+		return (int)std::max<long>(1, std::min<long>((long)io.n_sms * ctas_per_sm, (max_chunks + warps - 1) / warps));
 	};
 	switch (P.kind) {
 		case PAIR_SOFT_RIGID:
 			if (tri)
-				launch_np<7>(narrow_tet_tri_kernel<true>, flat_grid(4), P, io, s);
+				launch_np<WarpTile<7, 6>, HCS_NP_TRI_WARPS>(narrow_tet_tri_kernel<true>, flat_grid(HCS_NP_TRI_CTAS, HCS_NP_TRI_WARPS), P, io, s, chained);
 			else
-				launch_np<7>(narrow_tet_tri_kernel<false>, flat_grid(4), P, io, s);
+				launch_np<WarpTile<7, 6>, HCS_NP_TRI_WARPS>(narrow_tet_tri_kernel<false>, flat_grid(HCS_NP_TRI_CTAS, HCS_NP_TRI_WARPS), P, io, s, chained);
 			break;
 		case PAIR_SOFT_SOFT:
 			if (tri)
-				launch_np<8>(narrow_tet_tet_kernel<true>, flat_grid(3), P, io, s);
+				launch_np<WarpTile<8, 7>, NP_WARPS>(narrow_tet_tet_kernel<true>, flat_grid(HCS_NP_TET_CTAS), P, io, s, chained);
 			else
-				launch_np<8>(narrow_tet_tet_kernel<false>, flat_grid(3), P, io, s);
+				launch_np<WarpTile<8, 7>, NP_WARPS>(narrow_tet_tet_kernel<false>, flat_grid(HCS_NP_TET_CTAS), P, io, s, chained);
 			break;
 		case PAIR_SOFT_PLANE:
 			if (tri)
-				launch_np<4>(narrow_tet_plane_kernel<true>, flat_grid(4), P, io, s);
+				launch_np<WarpTile<4, 2>, NP_WARPS>(narrow_tet_plane_kernel<true>, flat_grid(HCS_NP_PLANE_CTAS), P, io, s, chained);
 			else
-				launch_np<4>(narrow_tet_plane_kernel<false>, flat_grid(4), P, io, s);
+				launch_np<WarpTile<4, 2>, NP_WARPS>(narrow_tet_plane_kernel<false>, flat_grid(HCS_NP_PLANE_CTAS), P, io, s, chained);
 			break;
 		default:
 			break;
@@ -1054,7 +1139,7 @@ void launch_narrowphase(const PairDesc &P, const StepIO &io, cudaStream_t s)
 }
 
 int launch_finalize(const PairDesc *d_pairs, const StepIO &io, int max_list_slices, int list_units_per_env,
-                    bool small_units, cudaStream_t s)
+                    bool small_units, cudaStream_t s, bool chained)
 {
 	if (io.n_env <= 0)
 		return 0;
@@ -1065,24 +1150,31 @@ int launch_finalize(const PairDesc *d_pairs, const StepIO &io, int max_list_slic
 		finalize_kernel<<<io.n_env, 32, 0, s>>>(d_pairs, io, 0);
 		return 2;
 	}
-	// one group of lanes per environment, everything in registers / shared memory: 8 lanes when the units are small
+	// one group of lanes per environment, everything in registers / shared memory: 16 lanes when the units are small
 #ifdef HCS_FIN_FORCE_W32 // tuning sweeps
 	small_units = false;
 #endif
-	const int W     = small_units ? 8 : 32;
+	const int W     = small_units ? HCS_FIN_SMALL_W : 32;
 	const int per   = FIN_WARPS * 32 / W; // environments per CTA
 	size_t smem     = (size_t)per * io.n_geoms * 6 * sizeof(double);
 	if (smem <= 48 * 1024) {
 		int grid = (io.n_env + per - 1) / per;
-		if (W == 8)
-			finalize_env_group_kernel<8><<<grid, 32 * FIN_WARPS, smem, s>>>(d_pairs, io);
+		if (W == HCS_FIN_SMALL_W && chained)
+			launch_chained(finalize_env_group_kernel<HCS_FIN_SMALL_W>, dim3(grid), dim3(32 * FIN_WARPS), smem, s, d_pairs, io);
+		else if (W == HCS_FIN_SMALL_W)
+			finalize_env_group_kernel<HCS_FIN_SMALL_W><<<grid, 32 * FIN_WARPS, smem, s>>>(d_pairs, io);
+		else if (chained)
+			launch_chained(finalize_env_group_kernel<32>, dim3(grid), dim3(32 * FIN_WARPS), smem, s, d_pairs, io);
 		else
 			finalize_env_group_kernel<32><<<grid, 32 * FIN_WARPS, smem, s>>>(d_pairs, io);
 		return 1;
 	}
 	// one warp per slice of a candidate-list pair (up to 4)
 	int warps = std::max(1, std::min(4, max_list_slices));
-	finalize_kernel<<<io.n_env, 32 * warps, 0, s>>>(d_pairs, io, 1);
+	if (chained)
+		launch_chained(finalize_kernel, dim3(io.n_env), dim3(32 * warps), (size_t)0, s, d_pairs, io, 1);
+	else
+		finalize_kernel<<<io.n_env, 32 * warps, 0, s>>>(d_pairs, io, 1);
 	return 1;
 }
 

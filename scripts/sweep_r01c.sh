@@ -1,0 +1,21 @@
+# one-box A/B: programmatic dependent launch on/off (HCS_NO_PDL=1), tet-triangle occupancy at a many-wave batch
+run() { # name lib workload envs [env assignments...]
+  n=$1; lib=$2; w=$3; envs=$4; shift 4
+  env "$@" HCS_LIB=$lib timeout 300 python bench.py --no-cpu-baseline --workload $w --envs $envs --steps 300 --warmup 10 2>&1 | tail -1 | python -c "
+import json,sys
+d=json.loads(sys.stdin.read()); s=d['stage_ms_per_step']; print('$n', '$w', $envs, round(d['value']/1e6,3), 'M', round(d['ms_per_step'],4), 'bp %.4f np %.4f red %.4f'%(s['broadphase'],s['narrowphase'],s['reduce']), 'e2e', round(d['e2e']['value']/1e6,3))"
+}
+D=$PWD/mujoco_contact_surfaces_b200/libhcs_b200.so
+V=$PWD/mujoco_contact_surfaces_b200/variants
+run pdl $D c1_sphere_on_box 4096 X=1
+run nopdl $D c1_sphere_on_box 4096 HCS_NO_PDL=1
+run pdl $D c1_sphere_on_box 4096 X=1
+run nopdl $D c1_sphere_on_box 4096 HCS_NO_PDL=1
+run pdl $D c3_soft_soft 4096 X=1
+run nopdl $D c3_soft_soft 4096 HCS_NO_PDL=1
+run pdl $D c4_objects_on_plane 4096 X=1
+run nopdl $D c4_objects_on_plane 4096 HCS_NO_PDL=1
+run pdl $D c2_myrmex_spot 1024 X=1
+run nopdl $D c2_myrmex_spot 1024 HCS_NO_PDL=1
+run default $D c1_sphere_on_box 16384 X=1
+run tri5 $V/libhcs_b200.tri5.so c1_sphere_on_box 16384 X=1

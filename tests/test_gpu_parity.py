@@ -265,3 +265,91 @@ def test_candidate_pool_overflow_is_reported_not_undefined(hcs_lib, monkeypatch)
     eng.step(xpos, xmat, vel)
     assert eng.pair_results()["n_polygons"].sum() > 0
     eng.close()
+
+
+# ---------------------------------------------------------------------------------------------------------
+# BASELINE.json's full sizes: the oracle cannot walk 4096 environments within the suite's budget, so the whole
+# batch is checked through properties that do not depend on its size, and a seeded sample of it against the oracle.
+# ---------------------------------------------------------------------------------------------------------
+def _random_rigid_motion(rng):
+    q = rng.normal(size=4)
+    q /= np.linalg.norm(q)
+    w, x, y, z = q
+    Q = np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)],
+                  [2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)],
+                  [2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)]])
+    return Q, rng.uniform(-0.3, 0.3, size=3)
+
+
+@pytest.mark.parametrize("factory,n_envs,seed", [(scenes.sphere_on_box, 4096, 1234), (scenes.objects_on_plane, 4096, 4096)])
+def test_full_size_batch_properties(hcs_lib, factory, n_envs, seed):
+    scene = factory()
+    n_pairs = len(scene.pairs)
+    xpos, xmat, vel = scene.poses(n_envs, seed)
+    eng = make_engine(scene, n_envs)
+    eng.step(xpos, xmat, vel)
+    res, wrench = eng.pair_results().copy(), eng.geom_wrenches().copy()
+    assert int(res["n_polygons"].sum()) > 10 * n_envs
+
+    # 1. the same inputs again: bit-identical (fixed-order sums; where a candidate lands in the pool is decided by
+    #    atomics, what is added to what is not)
+    eng.step(xpos, xmat, vel)
+    assert eng.pair_results().tobytes() == res.tobytes() and eng.geom_wrenches().tobytes() == wrench.tobytes()
+
+    # 2. environments exchange nothing: permuting the batch permutes the results, bit for bit
+    perm = np.random.default_rng(seed).permutation(n_envs)
+    eng.step(xpos[perm], xmat[perm], vel[perm])
+    assert eng.pair_results().tobytes() == res[perm].tobytes()
+    assert eng.geom_wrenches().tobytes() == wrench[perm].tobytes()
+
+    # 3. action = -reaction: every pair adds (F, tau) to geom M and subtracts the same numbers from geom N
+    #    (plugin.cpp:477-482 applies +f and -f at the same point); the per-geom wrenches of an env sum to zero exactly
+    #    when each geom is in one pair, and always to rounding
+    total = wrench.sum(axis=1)
+    scale = np.abs(wrench).max(axis=(1, 2)) + 1e-300
+    assert np.all(np.abs(total).max(axis=1) <= 1e-12 * scale)
+    acc = np.zeros_like(wrench)
+    for p in range(n_pairs):
+        for e_idx, sign in (("gM", 1.0), ("gN", -1.0)):
+            g = res[e_idx][:, p].astype(np.int64)
+            np.add.at(acc, (np.arange(n_envs), g), sign * np.concatenate([res["F"][:, p], res["tau"][:, p]], axis=1))
+    assert np.all(np.abs(acc - wrench) <= 1e-12 * scale[:, None, None])
+
+    # 4. a seeded sample of the full batch against the oracle (same bars as the small-batch tests)
+    eng.step(xpos, xmat, vel)  # the emitted lists on the device are those of the last step: back to the original order
+    orc = make_oracle(scene)
+    for e in np.random.default_rng(seed + 1).choice(n_envs, size=24, replace=False):
+        ref_pairs, _ = oracle_env(orc, scene, xpos[e], xmat[e], vel[e], sensors=False)
+        compare_env(res[e], [eng.emitted(int(e), p) for p in range(n_pairs)], ref_pairs)
+    eng.close()
+
+
+def test_full_size_rigid_motion_invariance(hcs_lib):
+    """Moving the whole world by one rigid motion rotates every force and leaves areas and counts alone (the engine
+    works in the soft geom's frame, so this exercises the pose algebra rather than the clipper). Half-space normals
+    and friction directions rotate with the world; torques are about the world origin: tau' = Q tau + t x (Q F)."""
+    scene = scenes.sphere_on_box()
+    n_envs = 4096
+    xpos, xmat, vel = scene.poses(n_envs, 99)
+    Q, t = _random_rigid_motion(np.random.default_rng(11))
+    R = xmat.reshape(n_envs, -1, 3, 3)
+    xpos2 = xpos.reshape(n_envs, -1, 3) @ Q.T + t
+    xmat2 = (Q @ R).reshape(xmat.shape)
+    v6 = vel.reshape(n_envs, -1, 2, 3) @ Q.T  # [omega, v] of the geom origin, world aligned (plugin.cpp:107-114)
+    eng = make_engine(scene, n_envs)
+    eng.step(xpos, xmat, vel)
+    a = eng.pair_results().copy()
+    eng.step(xpos2.reshape(xpos.shape), xmat2, v6.reshape(vel.shape))
+    b = eng.pair_results().copy()
+    eng.close()
+    assert np.array_equal(a["n_polygons"], b["n_polygons"]) and np.array_equal(a["n_faces"], b["n_faces"])
+    hit = a["n_polygons"][:, 0] > 0
+    assert hit.sum() > n_envs // 2
+    F, Fq = a["F"][hit, 0] @ Q.T, b["F"][hit, 0]
+    fs = np.linalg.norm(F, axis=1)
+    assert np.all(np.linalg.norm(Fq - F, axis=1) <= 1e-8 * fs)
+    tau = a["tau"][hit, 0] @ Q.T + np.cross(t, F)
+    assert np.all(np.linalg.norm(b["tau"][hit, 0] - tau, axis=1) <= 1e-8 * np.maximum(np.linalg.norm(tau, axis=1), 0.1 * fs))
+    assert np.all(np.abs(a["area"][hit, 0] - b["area"][hit, 0]) <= 1e-8 * a["area"][hit, 0])
+    cen = a["centroid"][hit, 0] @ Q.T + t
+    assert np.all(np.linalg.norm(b["centroid"][hit, 0] - cen, axis=1) <= 1e-8)
