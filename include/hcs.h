@@ -65,6 +65,8 @@ typedef struct hcs_config {
 	int max_tactile_triangles;    /* 0 = automatic; triangle pool of the tactile stage, whole batch */
 	int max_triangles_per_taxel;  /* 0 = automatic (32); AVERAGE (triangle, taxel) overlaps per taxel the bins hold */
 	void *stream;                 /* cudaStream_t to run on, NULL = context-owned stream */
+	int face_vertices;            /* != 0 (needs max_faces > 0): the per-face dump also keeps every face's vertices
+	                               * (what visualizeMeshElement draws, plugin.cpp:525-555); see hcs_get_face_vertices */
 } hcs_config;
 
 /* result of one geom pair in one env: what passiveCallback applies (plugin.cpp:411-483), reduced.
@@ -200,6 +202,13 @@ const float *hcs_device_sensor_image(hcs_ctx *ctx, int sensor);
  * (CS/include/mujoco_contact_surfaces/plugin_utils.h:94); needs cfg.max_faces > 0.
  * returns the number of faces written (<= cap) or a negative status. Order is unspecified. */
 int hcs_get_faces(hcs_ctx *ctx, hcs_face *out, int cap);
+/* vertices of the dumped faces (world frame), the element of ContactSurface::poly_mesh_W() / tri_mesh_W() that
+ * visualizeMeshElement(pc.face, mesh, fn) walks (plugin.cpp:509-516, 525-555); needs cfg.face_vertices != 0.
+ * out[i*24 .. i*24+3*nv) = the nv vertices of face i of hcs_get_faces (same order of faces, same step), wound
+ * counter-clockwise about the face normal hcs_face.n; nv = hcs_face.nverts (kPolygon, <= 8) or 3 (kTriangle:
+ * TriMeshBuilder's fan triangle (previous, next, centroid)).  Returns the number of faces (as hcs_get_faces). */
+#define HCS_FACE_VERTEX_STRIDE 24
+int hcs_get_face_vertices(hcs_ctx *ctx, double *out, int cap);
 /* emitted candidate set of one pair in one env: triples (elemM, elemN, nverts); returns count */
 int hcs_get_emitted(hcs_ctx *ctx, int env, int pair, int32_t *out, int cap);
 /* kTriangle contact-surface triangle soup of one env (world frame), 12 doubles per triangle:

@@ -654,6 +654,8 @@ static void finalize(hcs_ctx *c)
 	io.max_faces      = std::max(0, c->cfg.max_faces);
 	io.faces          = dalloc<hcs_face>(c->step_allocs, io.max_faces);
 	io.face_count     = c->d_counters + 4;
+	io.face_verts     = c->cfg.face_vertices && io.max_faces > 0 ?
+	                        dalloc<double>(c->step_allocs, (size_t)io.max_faces * HCS_FACE_VERTEX_STRIDE) : nullptr;
 	bool tactile      = false;
 	for (const PairDesc &P : c->pair_desc)
 		tactile |= P.emit_tactile != 0;
@@ -1435,6 +1437,30 @@ int hcs_get_faces(hcs_ctx *c, hcs_face *out, int cap)
 	int m = std::min<int>(n, cap);
 	if (m > 0 && out) {
 		CK(cudaMemcpyAsync(out, c->io.faces, (size_t)m * sizeof(hcs_face), cudaMemcpyDeviceToHost, c->stream));
+		CK(cudaStreamSynchronize(c->stream));
+	}
+	return n;
+	API_END(c)
+}
+
+int hcs_get_face_vertices(hcs_ctx *c, double *out, int cap)
+{
+	API_BEGIN(c)
+	if (!c->finalized || !c->io.face_verts) {
+		c->err = "hcs_get_face_vertices: needs hcs_config.max_faces > 0 and hcs_config.face_vertices";
+		return HCS_E_INVALID;
+	}
+	int32_t n = 0;
+	CK(cudaMemcpyAsync(&n, c->io.face_count, sizeof n, cudaMemcpyDeviceToHost, c->stream));
+	CK(cudaStreamSynchronize(c->stream));
+	if (n > c->io.max_faces) {
+		c->err = "per-face dump overflow: raise hcs_config.max_faces";
+		return HCS_E_CAPACITY;
+	}
+	int m = std::min<int>(n, cap);
+	if (m > 0 && out) {
+		CK(cudaMemcpyAsync(out, c->io.face_verts, (size_t)m * HCS_FACE_VERTEX_STRIDE * sizeof(double),
+		                   cudaMemcpyDeviceToHost, c->stream));
 		CK(cudaStreamSynchronize(c->stream));
 	}
 	return n;

@@ -116,6 +116,7 @@ struct StepIO {
 	hcs_face *faces;         // optional per-face dump
 	int32_t *face_count;
 	int max_faces;
+	double *face_verts;      // [max_faces][24] world vertices of the dumped faces, or NULL (hcs_config.face_vertices)
 	TactileTri *tri_pool;
 	int32_t *tri_count;
 	int max_tris;

@@ -228,12 +228,13 @@ __device__ __forceinline__ double pick4(const double *d, int i)
 }
 
 // optional per-face dump (PointCollision views for CPU sub-plugins); cold path, kept out of line
-__device__ __noinline__ void dump_face(const StepIO &io, double sg, double dissipation, int env, int pair, D3 p, D3 n,
-                                       double fn0, double k, D3 f, int elemA, int elemB, int nverts, int face)
+// Returns the face's slot when its vertices are wanted too (hcs_config.face_vertices), else -1.
+__device__ __noinline__ int dump_face(const StepIO &io, double sg, double dissipation, int env, int pair, D3 p, D3 n,
+                                      double fn0, double k, D3 f, int elemA, int elemB, int nverts, int face)
 {
 	int slot = atomicAdd(io.face_count, 1);
 	if (slot >= io.max_faces)
-		return;
+		return -1;
 	hcs_face &o = io.faces[slot];
 	o.p[0] = p.x, o.p[1] = p.y, o.p[2] = p.z;
 	o.n[0] = sg * n.x, o.n[1] = sg * n.y, o.n[2] = sg * n.z;
@@ -243,6 +244,36 @@ __device__ __noinline__ void dump_face(const StepIO &io, double sg, double dissi
 	o.elemM  = sg > 0 ? elemA : elemB;
 	o.elemN  = sg > 0 ? elemB : elemA;
 	o.nverts = nverts, o.face = face;
+	return io.face_verts ? slot : -1;
+}
+
+// World vertices of a dumped face: what visualizeMeshElement walks (plugin.cpp:525-555).  kPolygon (b < 0): the
+// polygon's n vertices; kTriangle: TriMeshBuilder's fan triangle (vertex a, vertex b, centroid).  g: the candidate's
+// context block (polygon in A's frame) or NULL (polygon already in the world frame); reverse: the surface was
+// swapped to (M, N) = (B, A), which reverses the winding (contact_surface.cc SwapMAndN -> ReverseFaceWinding).  Cold path, out of line.
+__device__ __noinline__ void dump_face_vertices(double *dst, unsigned poly, int n, int a, int b, D3 cen, const double *g,
+                                                bool reverse)
+{
+	Xform XW = Xform();
+	if (g) {
+		CandCtx c;
+		c.g = g;
+		XW  = c.X_WA();
+	}
+	const int nv = b < 0 ? n : 3;
+#pragma unroll 1
+	for (int i = 0; i < nv; ++i) {
+		D3 v = b < 0 ? Poly{ poly }.get(i) : (i == 0 ? Poly{ poly }.get(a) : (i == 1 ? Poly{ poly }.get(b) : cen));
+		if (g)
+			v = apply(XW, v);
+		// SwapMAndN keeps a polygon's first vertex and reverses the rest; a triangle gets its first two swapped
+		const int j = !reverse ? i : (b < 0 ? (i == 0 ? 0 : nv - i) : (i == 2 ? 2 : 1 - i));
+		double *o   = dst + 3 * j;
+		o[0] = v.x, o[1] = v.y, o[2] = v.z;
+	}
+#pragma unroll 1
+	for (int i = 3 * nv; i < HCS_FACE_VERTEX_STRIDE; ++i)
+		dst[i] = 0.0;
 }
 
 // Quadrature + force accumulation of one contact polygon.
@@ -304,8 +335,12 @@ __device__ __forceinline__ void integrate_polygon(Poly P, int n, D3 nhat, D3 gra
 			acc.F      = acc.F + f;
 			acc.tau    = acc.tau + cross(cW, f);
 			acc.n_points += 1;
-			if (io.max_faces > 0)
-				dump_face(io, c.sign, c.dissipation, c.env, c.pair, cW, nf, fn0, k, f, elemA, elemB, n, 0);
+			if (io.max_faces > 0) {
+				int slot = dump_face(io, c.sign, c.dissipation, c.env, c.pair, cW, nf, fn0, k, f, elemA, elemB, n, 0);
+				if (slot >= 0)
+					dump_face_vertices(io.face_verts + (size_t)slot * HCS_FACE_VERTEX_STRIDE, P.a, n, 0, -1, cen,
+					                   IDENT ? nullptr : c.g, c.sign < 0);
+			}
 		}
 		return;
 	}
@@ -341,8 +376,12 @@ __device__ __forceinline__ void integrate_polygon(Poly P, int n, D3 nhat, D3 gra
 			acc.F      = acc.F + f;
 			acc.tau    = acc.tau + cross(fc, f);
 			acc.n_points += 1;
-			if (io.max_faces > 0)
-				dump_face(io, c.sign, c.dissipation, c.env, c.pair, fc, nf, fn0, k, f, elemA, elemB, n, i);
+			if (io.max_faces > 0) {
+				int slot = dump_face(io, c.sign, c.dissipation, c.env, c.pair, fc, nf, fn0, k, f, elemA, elemB, n, i);
+				if (slot >= 0)
+					dump_face_vertices(io.face_verts + (size_t)slot * HCS_FACE_VERTEX_STRIDE, P.a, n, i == 0 ? n - 1 : i - 1, i,
+					                   cen, IDENT ? nullptr : c.g, c.sign < 0);
+			}
 		}
 		a = b, aW = bW, ea = eb;
 	}

@@ -21,7 +21,8 @@ HCS_OK, HCS_E_INVALID, HCS_E_UNSUPPORTED, HCS_E_CUDA, HCS_E_CAPACITY, HCS_E_NOT_
 class HcsConfig(C.Structure):
     _fields_ = [("device", C.c_int), ("n_envs", C.c_int), ("representation", C.c_int),
                 ("apply_contact_forces", C.c_int), ("max_candidates_per_slice", C.c_int), ("max_faces", C.c_int),
-                ("max_tactile_triangles", C.c_int), ("max_triangles_per_taxel", C.c_int), ("stream", C.c_void_p)]
+                ("max_tactile_triangles", C.c_int), ("max_triangles_per_taxel", C.c_int), ("stream", C.c_void_p),
+                ("face_vertices", C.c_int)]
 
 
 PAIR_RESULT_DTYPE = np.dtype([("F", "<f8", 3), ("tau", "<f8", 3), ("centroid", "<f8", 3), ("area", "<f8"),
@@ -42,7 +43,7 @@ ABI_SYMBOLS = [
     "hcs_device_sensor_image", "hcs_get_faces", "hcs_get_emitted", "hcs_get_tactile_triangles", "hcs_geom_info",
     "hcs_get_mesh", "hcs_get_lbvh", "hcs_get_counters", "hcs_set_profiling", "hcs_get_stage_ms", "hcs_version",
     "hcs_add_curved_sensor", "hcs_curved_sensor_info", "hcs_get_curved_values", "hcs_device_curved_values",
-    "hcs_add_taxel_sensor", "hcs_get_taxel_values", "hcs_device_taxel_values",
+    "hcs_add_taxel_sensor", "hcs_get_taxel_values", "hcs_device_taxel_values", "hcs_get_face_vertices",
 ]
 
 _LIB = None
@@ -104,10 +105,11 @@ class HydroelasticEngine:
     """
 
     def __init__(self, n_envs, representation=REP_POLYGON, apply_contact_forces=True, device=0, max_faces=0,
-                 max_candidates_per_slice=0, max_tactile_triangles=0, max_triangles_per_taxel=0, stream=None):
+                 max_candidates_per_slice=0, max_tactile_triangles=0, max_triangles_per_taxel=0, stream=None,
+                 face_vertices=False):
         self.L = load_library()
         cfg = HcsConfig(device, n_envs, representation, int(apply_contact_forces), max_candidates_per_slice, max_faces,
-                        max_tactile_triangles, max_triangles_per_taxel, stream)
+                        max_tactile_triangles, max_triangles_per_taxel, stream, int(face_vertices))
         h = C.c_void_p()
         st = self.L.hcs_create(C.byref(cfg), C.byref(h))
         if st != HCS_OK:
@@ -256,6 +258,14 @@ class HydroelasticEngine:
         buf = np.zeros(cap, dtype=FACE_DTYPE)
         n = self._check(self.L.hcs_get_faces(self.h, buf.ctypes.data_as(C.c_void_p), cap))
         return buf[:min(n, cap)]
+
+    def face_vertices(self, cap=1 << 20):
+        """(n_faces, 8, 3) world vertices of the faces of faces(), same order; rows beyond a face's vertex count are 0"""
+        n = self._check(self.L.hcs_get_faces(self.h, None, 0))
+        n = min(n, cap)
+        buf = np.zeros((max(n, 1), 8, 3))
+        self._check(self.L.hcs_get_face_vertices(self.h, _ptr(buf, C.c_double), n))
+        return buf[:n]
 
     def emitted(self, env, pair):
         n = self._check(self.L.hcs_get_emitted(self.h, int(env), int(pair), None, 0))

@@ -133,6 +133,7 @@ void MujocoContactSurfacesPlugin::parseMujocoCustomFields(const mjModel *m)
 	cfg.representation       = hydroelastic_contact_representation;
 	cfg.apply_contact_forces = applyContactSurfaceForces;
 	cfg.max_faces            = 1 << 16; // GeomCollision views for sub-plugins / visualisation
+	cfg.face_vertices        = visualizeContactSurfaces ? 1 : 0;
 	if (hcs_create(&cfg, &ctx_) != HCS_OK) {
 		std::fprintf(stderr, "[mujoco_contact_surfaces] %s\n", hcs_last_error(nullptr));
 		ctx_ = nullptr;
@@ -264,7 +265,17 @@ void MujocoContactSurfacesPlugin::buildGeomCollisions()
 	if (nf < 0)
 		nf = 0;
 	nf = std::min<int>(nf, (int)faces.size());
-	std::stable_sort(faces.begin(), faces.begin() + nf, [](const hcs_face &a, const hcs_face &b) {
+	std::vector<double> fverts; // the same faces' world vertices (only kept when the surfaces are drawn)
+	if (visualizeContactSurfaces && nf > 0) {
+		fverts.resize((size_t)nf * HCS_FACE_VERTEX_STRIDE);
+		if (hcs_get_face_vertices(ctx_, fverts.data(), nf) < 0)
+			fverts.clear();
+	}
+	std::vector<int> order(nf); // the dump's order is unspecified: (pair, elemM, elemN, face) is Drake's face order
+	for (int i = 0; i < nf; ++i)
+		order[i] = i;
+	std::stable_sort(order.begin(), order.end(), [&faces](int ia, int ib) {
+		const hcs_face &a = faces[ia], &b = faces[ib];
 		if (a.pair != b.pair) return a.pair < b.pair;
 		if (a.elemM != b.elemM) return a.elemM < b.elemM;
 		if (a.elemN != b.elemN) return a.elemN < b.elemN;
@@ -292,16 +303,51 @@ void MujocoContactSurfacesPlugin::buildGeomCollisions()
 			view->triangles = tris; // single-pair scenes: the whole soup belongs to this surface
 		GeomCollisionPtr gc(new GeomCollision(cfg_to_mj[r.gM], cfg_to_mj[r.gN], view));
 		int k = 0;
-		for (int i = 0; i < nf; ++i)
-			if (faces[i].pair == p) {
-				PointCollision pc;
-				std::memcpy(pc.p, faces[i].p, sizeof pc.p);
-				std::memcpy(pc.n, faces[i].n, sizeof pc.n);
-				pc.fn0 = faces[i].fn0, pc.stiffness = faces[i].stiffness, pc.damping = faces[i].damping;
-				pc.face = k++;
-				gc->pointCollisions.push_back(pc);
+		for (int j = 0; j < nf; ++j) {
+			const hcs_face &f = faces[order[j]];
+			if (f.pair != p)
+				continue;
+			PointCollision pc;
+			std::memcpy(pc.p, f.p, sizeof pc.p);
+			std::memcpy(pc.n, f.n, sizeof pc.n);
+			pc.fn0 = f.fn0, pc.stiffness = f.stiffness, pc.damping = f.damping;
+			pc.face = k++;
+			gc->pointCollisions.push_back(pc);
+			// fn of plugin.cpp:470 (the friction part of f is tangential)
+			view->face_fn.push_back(f.f[0] * f.n[0] + f.f[1] * f.n[1] + f.f[2] * f.n[2]);
+			if (!fverts.empty()) {
+				view->face_nverts.push_back(view->is_triangle ? 3 : f.nverts);
+				const double *v = &fverts[(size_t)order[j] * HCS_FACE_VERTEX_STRIDE];
+				view->face_vertices.insert(view->face_vertices.end(), v, v + HCS_FACE_VERTEX_STRIDE);
 			}
+		}
 		geomCollisions.push_back(gc);
+	}
+}
+
+// plugin.cpp:525-555: the outline of one face of the contact surface, one thin cylinder per edge
+void MujocoContactSurfacesPlugin::visualizeMeshElement(int face, const ContactSurfaceView &mesh, double /*fn*/)
+{
+	if (face >= (int)mesh.face_nverts.size())
+		return;
+	if (n_vGeom >= MAX_VGEOM) {
+		std::fprintf(stderr, "n_vGeom too big\n");
+		return;
+	}
+	const float rgba[4] = { 0.3f, 0.3f, 0.3f, 0.8f };
+	const int nv        = mesh.face_nverts[face];
+	const double *v     = &mesh.face_vertices[(size_t)face * HCS_FACE_VERTEX_STRIDE];
+	const double *vp0   = v + 3 * (nv - 1);
+	for (int i = 0; i < nv; ++i) {
+		const double *vp1 = v + 3 * i;
+		if (n_vGeom == MAX_VGEOM) {
+			std::fprintf(stderr, "n_vGeom too big\n");
+			break;
+		}
+		mjvGeom *g = vGeoms + n_vGeom++;
+		mjv_initGeom(g, mjGEOM_CYLINDER, nullptr, nullptr, nullptr, rgba);
+		mjv_makeConnector(g, mjGEOM_CYLINDER, 0.000015, vp0[0], vp0[1], vp0[2], vp1[0], vp1[1], vp1[2]);
+		vp0 = vp1;
 	}
 }
 
@@ -322,15 +368,12 @@ void MujocoContactSurfacesPlugin::passiveCallback(const mjModel *m, mjData *d)
 	if (finalized_ && !pair_list_.empty()) {
 		evaluateAndApply(m, d, with_sensors);
 		buildGeomCollisions();
-		if (visualizeContactSurfaces) { // one marker per quadrature point (plugin.cpp:509-516 draws the face wireframe)
+		if (visualizeContactSurfaces) { // plugin.cpp:509-516
 			for (const auto &gc : geomCollisions)
 				for (const auto &pc : gc->pointCollisions) {
-					if (n_vGeom >= MAX_VGEOM)
-						break;
-					current_scale        = std::max(current_scale, std::fabs(pc.fn0));
-					const mjtNum size[3] = { 0.00015, 0.00015, 0.00015 };
-					const float rgba[4]  = { 0.3f, 0.3f, 0.3f, 0.8f };
-					mjv_initGeom(vGeoms + n_vGeom++, mjGEOM_SPHERE, size, pc.p, nullptr, rgba);
+					const double fn = gc->s->face_fn[pc.face];
+					current_scale   = std::max(current_scale, std::fabs(fn));
+					visualizeMeshElement(pc.face, *gc->s, fn);
 				}
 		}
 	}

@@ -49,6 +49,11 @@ struct ContactSurfaceView {
 	double total_area = 0;
 	double centroid[3] = { 0, 0, 0 };
 	int num_faces = 0;
+	// per PointCollision (index = PointCollision::face): the normal force fn of plugin.cpp:470 and, when the surfaces
+	// are drawn (cs::VisualizeSurfaces), the face's world vertices, HCS_FACE_VERTEX_STRIDE doubles each
+	std::vector<double> face_fn;
+	std::vector<int> face_nverts;
+	std::vector<double> face_vertices;
 };
 
 // common_types.h:48-56
@@ -173,6 +178,7 @@ private:
 	void ensurePairs();
 	void evaluateAndApply(const mjModel *m, mjData *d, bool with_sensors);
 	void buildGeomCollisions();
+	void visualizeMeshElement(int face, const ContactSurfaceView &mesh, double fn); // plugin.cpp:525-555
 
 	hcs_ctx *ctx_   = nullptr;
 	bool finalized_ = false;

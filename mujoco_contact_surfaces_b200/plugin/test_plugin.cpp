@@ -165,16 +165,23 @@ static int scenario_sphere_on_box()
 		plugin.passiveCallback(&w.m, &w.d);
 		w.d.time += 0.001;
 	}
-	mjvGeom scene_geoms[256];
-	mjvScene scene{ 256, 0, scene_geoms };
+	static mjvGeom scene_geoms[4096];
+	mjvScene scene{ 4096, 0, scene_geoms };
 	plugin.renderCallback(&w.m, &w.d, &scene);
 	n_geoms_seen = scene.ngeom;
+	double outline = 0; // the contact surface is drawn as one connector per face edge (plugin.cpp:525-555)
+	int n_cyl      = 0;
+	for (int i = 0; i < scene.ngeom; ++i)
+		if (scene.geoms[i].type == mjGEOM_CYLINDER) {
+			outline += 2.0 * scene.geoms[i].size[2];
+			++n_cyl;
+		}
 	std::printf("{\"scenario\": \"sphere_on_box\", ");
 	print_vec("box_pos", box_pos, 3);
 	print_vec("sphere_pos", sph_pos, 3);
 	print_vec("sphere_mat", R, 9);
 	print_vec("sphere_vel6", v, 6);
-	std::printf("\"vgeoms\": %d, ", n_geoms_seen);
+	std::printf("\"vgeoms\": %d, \"connectors\": %d, \"outline_length\": %.9g, ", n_geoms_seen, n_cyl, outline);
 	print_vec("qfrc_passive", w.qfrc.data(), (int)w.qfrc.size(), true);
 	std::printf("}\n");
 	return 0;

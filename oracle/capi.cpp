@@ -342,6 +342,26 @@ int orc_pair_triangles(void *h, int pair, double *buf, int cap)
 	}
 	return n;
 }
+// The faces visualizeMeshElement(pc.face, mesh_W, fn) outlines (plugin.cpp:509-516, 525-555): per PointCollision
+// 25 doubles = vertex count + up to 8 world vertices of face pc.face of the contact surface, in the face's winding.
+int orc_pair_face_vertices(void *h, int pair, double *buf, int cap)
+{
+	Scene &sc         = *(Scene *)h;
+	const PairOut &po = sc.last.out[pair];
+	int n             = (int)po.pcs.size();
+	for (int i = 0; i < n && i < cap; ++i) {
+		const Surface &s = *po.s;
+		int face = po.pcs[i].face, nv = s.face_n[face];
+		const int *f = &s.face_idx[s.face_first[face]];
+		double *o    = buf + 25 * i;
+		for (int k = 0; k < 25; ++k)
+			o[k] = 0;
+		o[0] = nv;
+		for (int k = 0; k < nv && k < 8; ++k)
+			o[1 + 3 * k] = s.v[f[k]].x, o[2 + 3 * k] = s.v[f[k]].y, o[3 + 3 * k] = s.v[f[k]].z;
+	}
+	return n;
+}
 int orc_geom_wrench(void *h, int geom, double *out6)
 {
 	Scene &sc = *(Scene *)h;

@@ -33,6 +33,7 @@ def lib():
         for name in ("orc_scene_destroy", "orc_add_geom", "orc_add_raw_soft", "orc_add_raw_rigid", "orc_geom_info",
                      "orc_geom_mesh", "orc_set_pairs", "orc_add_flat_sensor", "orc_sensor_dims", "orc_step",
                      "orc_pair_result", "orc_pair_emitted", "orc_pair_faces", "orc_pair_triangles", "orc_geom_wrench",
+                     "orc_pair_face_vertices",
                      "orc_sensor_image", "orc_bench", "orc_add_curved_sensor", "orc_curved_values", "orc_curved_info",
                      "orc_add_taxel_sensor", "orc_taxel_values"):
             getattr(L, name).restype = C.c_int
@@ -195,6 +196,13 @@ class OracleScene:
         buf = np.zeros((max(n, 1), 13))
         self.L.orc_pair_faces(self.h, pair, _p(buf, C.c_double), n)
         return buf[:n]
+
+    def pair_face_vertices(self, pair):
+        """per PointCollision: (vertex count, (8, 3) world vertices of its face)"""
+        n = self.L.orc_pair_face_vertices(self.h, pair, None, 0)
+        buf = np.zeros((max(n, 1), 25))
+        self.L.orc_pair_face_vertices(self.h, pair, _p(buf, C.c_double), n)
+        return buf[:n, 0].astype(int), buf[:n, 1:].reshape(-1, 8, 3)
 
     def pair_triangles(self, pair):
         n = self.L.orc_pair_triangles(self.h, pair, None, 0)

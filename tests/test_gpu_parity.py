@@ -353,3 +353,57 @@ def test_full_size_rigid_motion_invariance(hcs_lib):
     assert np.all(np.abs(a["area"][hit, 0] - b["area"][hit, 0]) <= 1e-8 * a["area"][hit, 0])
     cen = a["centroid"][hit, 0] @ Q.T + t
     assert np.all(np.linalg.norm(b["centroid"][hit, 0] - cen, axis=1) <= 1e-8)
+
+
+@pytest.mark.parametrize("name,triangle", [("sphere_on_box", False), ("sphere_on_box", True), ("soft_soft", False),
+                                           ("objects_on_plane", False), ("objects_on_plane", True), ("myrmex", True)])
+def test_face_vertices_are_the_faces_the_reference_outlines(hcs_lib, name, triangle):
+    """f4 (plugin.cpp:509-516, 525-555): visualizeMeshElement walks the vertices of face pc.face of the surface's
+    mesh_W.  The per-face dump with hcs_config.face_vertices returns those vertices: same faces, same vertices, same
+    winding as the oracle's surface (kPolygon polygons, kTriangle fan triangles; M/N-swapped pairs reversed the way
+    SwapMAndN does), and they are consistent with the PointCollision of the face (centroid, normal)."""
+    scene = {"sphere_on_box": scenes.sphere_on_box, "soft_soft": scenes.soft_soft,
+             "objects_on_plane": scenes.objects_on_plane, "myrmex": lambda: scenes.myrmex("box", 8)}[name]()
+    scene.triangle = triangle
+    n_envs = 3
+    eng = make_engine(scene, n_envs, max_faces=1 << 16, face_vertices=True)
+    orc = make_oracle(scene)
+    xpos, xmat, vel = scene.poses(n_envs, 99)
+    eng.step(xpos, xmat, vel)
+    faces, verts = eng.faces(), eng.face_vertices()
+    assert len(faces) == len(verts) > 0
+    n_checked = 0
+    for e in range(n_envs):
+        orc.step(xpos[e], xmat[e], vel[e])
+        for p in range(len(scene.pairs)):
+            ref_nv, ref_v = orc.pair_face_vertices(p)
+            ref_pc = orc.pair_faces(p)
+            sel = np.flatnonzero((faces["env"] == e) & (faces["pair"] == p))
+            assert len(sel) == len(ref_nv)
+            if not len(sel):
+                continue
+            # match faces by their quadrature point (distinct per face)
+            key_g = np.lexsort(np.round(faces["p"][sel], 9).T[::-1])
+            key_o = np.lexsort(np.round(ref_pc[:, 0:3], 9).T[::-1])
+            for ig, io in zip(sel[key_g], key_o):
+                nv = 3 if scene.triangle else int(faces["nverts"][ig])
+                assert nv == ref_nv[io]
+                assert np.allclose(faces["p"][ig], ref_pc[io, 0:3], rtol=0, atol=1e-12)
+                assert np.allclose(verts[ig, :nv], ref_v[io, :nv], rtol=0, atol=1e-12), (e, p, verts[ig, :nv], ref_v[io, :nv])
+                assert np.all(verts[ig, nv:] == 0)
+                # the outline is wound counter-clockwise about the PointCollision normal
+                v = verts[ig, :nv]
+                nrm = sum(np.cross(v[i] - v[0], v[i + 1] - v[0]) for i in range(1, nv - 1))
+                assert np.dot(nrm, faces["n"][ig]) > 0.999999 * np.linalg.norm(nrm)
+                n_checked += 1
+    assert n_checked > 10
+    eng.close()
+
+
+def test_face_vertices_need_the_config_flag(hcs_lib):
+    from mujoco_contact_surfaces_b200.engine import HcsError
+    eng = make_engine(scenes.sphere_on_box(), 1, max_faces=1024)
+    eng.step(*scenes.sphere_on_box().poses(1, 1))
+    with pytest.raises(HcsError):
+        eng.face_vertices()
+    eng.close()

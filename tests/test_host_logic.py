@@ -30,7 +30,7 @@ def test_struct_layouts_match_the_header(hcs_lib):
     from mujoco_contact_surfaces_b200 import engine
     assert engine.PAIR_RESULT_DTYPE.itemsize == 112  # 10 doubles + 8 int32
     assert engine.FACE_DTYPE.itemsize == 120  # 12 doubles + 6 int32
-    assert ctypes.sizeof(engine.HcsConfig) == 8 * 4 + 8
+    assert ctypes.sizeof(engine.HcsConfig) == 8 * 4 + 8 + 8  # 8 ints, stream pointer, face_vertices + padding
 
 
 def test_product_fails_loudly_without_a_gpu(hcs_lib):

@@ -62,6 +62,12 @@ def test_adapter_sphere_on_box_and_myrmex_match_the_oracle(plugin_built):
         assert np.allclose(dofs[:3], w[:3], rtol=1e-8, atol=1e-12)
         assert np.allclose(dofs[3:], tau_com, rtol=1e-8, atol=1e-10)
     assert np.linalg.norm(q[:3]) > 1.0  # there is contact
+    # cs::VisualizeSurfaces = 1: every face with a PointCollision is outlined, one connector per edge
+    # (plugin.cpp:509-516, 525-555)
+    nv, fv = o.pair_face_vertices(0)
+    perimeter = sum(np.linalg.norm(fv[i, (k + 1) % n] - fv[i, k]) for i, n in enumerate(nv) for k in range(n))
+    assert r["vgeoms"] == r["connectors"] == int(nv.sum()) and len(nv) > 10
+    assert abs(r["outline_length"] - perimeter) < 1e-5 * perimeter
 
     r = res["myrmex_box"]
     o = OracleScene(triangle_representation=True)
