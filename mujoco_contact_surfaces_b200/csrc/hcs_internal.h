@@ -25,6 +25,12 @@ struct __align__(32) TetField { // 192 B = 6 x 32 B: what the tet contributes to
 	double ghat[3];     // normalized gradient (cull direction)
 	double pad;
 };
+struct __align__(32) TetLeaf32 { // 128 B = one line: float copy of what the broadphase leaf filter reads (records.cuh)
+	float plane[4][4]; // as TetField::plane, rounded to nearest
+	float ghat[3];
+	float pad;
+	float v[4][3]; // tet vertices
+};
 struct __align__(32) TriRec { // 96 B = 3 x 32 B: rigid triangle vertices + unit normal
 	double v[3][3];
 	double n[3];
@@ -43,6 +49,7 @@ struct GeomDev {
 	double *pressure;   // [nv]
 	TetGeom *tet_geom;  // soft
 	TetField *tet_field;
+	TetLeaf32 *tet_leaf32;
 	TriRec *tris;       // rigid
 	BvhNode *nodes;     // soft: LBVH over tets (root = node 0)
 	double bound_c[3];  // bounding sphere in the geom frame

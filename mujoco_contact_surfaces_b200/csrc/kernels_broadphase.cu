@@ -27,6 +27,9 @@ namespace hcs {
 #ifndef HCS_BP_PERSISTENT
 #define HCS_BP_PERSISTENT 1
 #endif
+#ifndef HCS_BP_LEAF32 // soft-rigid leaf test: conservative float filter in front of the exact fp64 early-outs
+#define HCS_BP_LEAF32 1
+#endif
 constexpr int BP_CTAS_PER_SM = HCS_BP_CTAS_PER_SM;
 constexpr int BP_WARPS = 4;
 constexpr int BP_BLOCK = 32 * BP_WARPS;
@@ -43,6 +46,8 @@ struct __align__(16) WarpQueues {
 	double qv[12][32];  // transformed query vertices (tri: 9 + rotated normal 3; tet: 12), lane-interleaved
 	float qbox[6][32];
 	float qpl[4][32]; // soft-rigid: the query triangle's plane (unit normal, offset) in A's frame
+	float qvf[9][32]; // soft-rigid: the query triangle's vertices in A's frame, rounded to float (leaf filter)
+	float qm[32];     // soft-rigid: the filter's margin for this query (4e-6 x the largest coordinate involved)
 	int qid[32];
 	uint2 stage[STAGE]; // surviving (query, tet) candidates waiting to be appended to the pair's flat list
 };
@@ -256,6 +261,8 @@ __device__ __forceinline__ void broadphase_unit(const PairDesc &P, const StepIO 
 	int q_begin = slice * P.slice_q, q_end = min(P.nq, q_begin + P.slice_q);
 	unsigned lt_mask = (1u << lane) - 1u;
 	const float4 *nodes4 = reinterpret_cast<const float4 *>(P.A.nodes);
+	// largest coordinate of A's geometry in its own frame (bounding sphere), for the float filter's margin
+	const float leaf_scale = (float)(fmax(fmax(fabs(P.A.bound_c[0]), fabs(P.A.bound_c[1])), fabs(P.A.bound_c[2])) + P.A.bound_r);
 
 	for (int q0 = q_begin; q0 < q_end; q0 += 32) {
 		// ---- load + transform this chunk's queries, test against the root box, compact survivors ----
@@ -306,6 +313,13 @@ __device__ __forceinline__ void broadphase_unit(const PairDesc &P, const StepIO 
 			if (!QTET) {
 				W.qpl[0][slot] = (float)v[9], W.qpl[1][slot] = (float)v[10], W.qpl[2][slot] = (float)v[11];
 				W.qpl[3][slot] = (float)(v[9] * v[0] + v[10] * v[1] + v[11] * v[2]);
+				float big = leaf_scale;
+#pragma unroll
+				for (int k = 0; k < 9; ++k) {
+					W.qvf[k][slot] = (float)v[k];
+					big            = fmaxf(big, fabsf((float)v[k]));
+				}
+				W.qm[slot] = 4e-6f * big + 1e-30f;
 			}
 			W.qid[slot]   = q;
 			W.nodeq[slot] = (unsigned)slot << ITEM_SHIFT; // (slot, root)
@@ -327,6 +341,45 @@ __device__ __forceinline__ void broadphase_unit(const PairDesc &P, const StepIO 
 					if (!QTET) {
 						const TetField *tf = P.A.tet_field + it.y;
 						int s  = (int)it.x;
+#if HCS_BP_LEAF32
+						// Conservative float filter.  The exact tests below are early-outs: a pair they reject clips to
+						// nothing, so rejecting a SUBSET of those pairs here changes no result, and a pair that slips
+						// through is clipped (to nothing) by the narrowphase.  One 128-byte TetLeaf32 line replaces the
+						// 192 + 96 bytes of fp64 records per leaf hit; the margin qm = 4e-6 x (largest coordinate
+						// involved) is > 5x the worst rounding of the float dot products and of the inputs' conversion,
+						// so "outside by more than qm in float" implies "outside by more than 1e-12 in double".  NaNs
+						// (degenerate tets) compare false and fall through to the exact path.  Only the gradient cull
+						// is a semantic filter, not an early-out: it is decided in float only when it is clear by 1e-5.
+						const TetLeaf32 *tl = P.A.tet_leaf32 + it.y;
+						const F8 l0 = ld8f(tl, 0), l1 = ld8f(tl, 1), l2 = ld8f(tl, 2), l3 = ld8f(tl, 3);
+						const float nx = W.qpl[0][s], ny = W.qpl[1][s], nz = W.qpl[2][s], dtf = W.qpl[3][s], m = W.qm[s];
+						const float cosg = fdot3(l2.a[0], l2.a[1], l2.a[2], nx, ny, nz);
+						if (cosg < (float)HCS_COS_ALPHA - 1e-5f)
+							keep = false;
+						else if (cosg < (float)HCS_COS_ALPHA + 1e-5f)
+							keep = dot(load_ghat(tf), mk(W.qv[9][s], W.qv[10][s], W.qv[11][s])) > HCS_COS_ALPHA;
+						if (keep) {
+							const float ax = W.qvf[0][s], ay = W.qvf[1][s], az = W.qvf[2][s], bx = W.qvf[3][s], by = W.qvf[4][s],
+							            bz = W.qvf[5][s], cx = W.qvf[6][s], cy = W.qvf[7][s], cz = W.qvf[8][s];
+							const float pl[4][4] = { { l0.a[0], l0.a[1], l0.a[2], l0.a[3] }, { l0.a[4], l0.a[5], l0.a[6], l0.a[7] },
+								                     { l1.a[0], l1.a[1], l1.a[2], l1.a[3] }, { l1.a[4], l1.a[5], l1.a[6], l1.a[7] } };
+#pragma unroll
+							for (int f = 0; f < 4; ++f) {
+								float sa = fdot3(pl[f][0], pl[f][1], pl[f][2], ax, ay, az) - pl[f][3];
+								float sb = fdot3(pl[f][0], pl[f][1], pl[f][2], bx, by, bz) - pl[f][3];
+								float sc = fdot3(pl[f][0], pl[f][1], pl[f][2], cx, cy, cz) - pl[f][3];
+								if (sa > m && sb > m && sc > m)
+									keep = false;
+							}
+							// tet vertices: l2.a[4..7], l3.a[0..7]
+							float h0 = fdot3(nx, ny, nz, l2.a[4], l2.a[5], l2.a[6]) - dtf;
+							float h1 = fdot3(nx, ny, nz, l2.a[7], l3.a[0], l3.a[1]) - dtf;
+							float h2 = fdot3(nx, ny, nz, l3.a[2], l3.a[3], l3.a[4]) - dtf;
+							float h3 = fdot3(nx, ny, nz, l3.a[5], l3.a[6], l3.a[7]) - dtf;
+							if ((h0 > m && h1 > m && h2 > m && h3 > m) || (h0 < -m && h1 < -m && h2 < -m && h3 < -m))
+								keep = false;
+						}
+#else
 						D3 nS  = mk(W.qv[9][s], W.qv[10][s], W.qv[11][s]);
 						keep   = dot(load_ghat(tf), nS) > HCS_COS_ALPHA;
 						if (keep) {
@@ -350,6 +403,7 @@ __device__ __forceinline__ void broadphase_unit(const PairDesc &P, const StepIO 
 							    (h0 < -1e-12 && h1 < -1e-12 && h2 < -1e-12 && h3 < -1e-12))
 								keep = false;
 						}
+#endif
 					} else {
 						// soft-soft: CalcEquilibriumPlane + the two IsPlaneNormalAlongPressureGradient culls of
 						// field_intersection.cc (same arithmetic as the clip kernel), then: the equal-pressure plane

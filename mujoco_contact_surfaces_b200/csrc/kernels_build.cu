@@ -57,6 +57,22 @@ __global__ void __launch_bounds__(128) build_tets_kernel(GeomDev g)
 		tf.plane[k][3] = dot(n, A);
 	}
 	g.tet_field[t] = tf;
+
+	// float copy for the conservative leaf filter of the broadphase (kernels_broadphase.cu): it only rejects pairs
+	// the exact fp64 tests reject with a margin far above the rounding of these values
+	TetLeaf32 tl;
+#pragma unroll
+	for (int k = 0; k < 4; ++k) {
+#pragma unroll
+		for (int a = 0; a < 4; ++a)
+			tl.plane[k][a] = (float)tf.plane[k][a];
+#pragma unroll
+		for (int a = 0; a < 3; ++a)
+			tl.v[k][a] = (float)tg.v[k][a];
+	}
+	tl.ghat[0] = (float)gh.x, tl.ghat[1] = (float)gh.y, tl.ghat[2] = (float)gh.z;
+	tl.pad = 0.f;
+	g.tet_leaf32[t] = tl;
 }
 
 __global__ void __launch_bounds__(128) build_tris_kernel(GeomDev g)

@@ -37,6 +37,16 @@ __device__ __forceinline__ TriVerts load_tri(const TriRec *r) // v[3][3] + n[3] 
 	return t;
 }
 
+// TetLeaf32: four 32-byte groups of eight floats: planes 0-1 | planes 2-3 | ghat, -, v0, v1.x | v1.yz, v2, v3
+struct __align__(32) F8 {
+	float a[8];
+};
+__device__ __forceinline__ F8 ld8f(const TetLeaf32 *t, int group) { return reinterpret_cast<const F8 *>(t)[group]; }
+__device__ __forceinline__ float fdot3(float ax, float ay, float az, float bx, float by, float bz)
+{
+	return __fmaf_rn(ax, bx, __fmaf_rn(ay, by, az * bz));
+}
+
 // TetField groups: plane[0..3] (unit normal + offset), {grad, e0}, {ghat, -}
 __device__ __forceinline__ D4 load_plane(const TetField *f, int k) { return ld4(reinterpret_cast<const double *>(f) + 4 * k); }
 __device__ __forceinline__ D4 load_grad_e0(const TetField *f) { return ld4(reinterpret_cast<const double *>(f) + 16); }
