@@ -27,6 +27,12 @@ namespace hcs {
 #ifndef HCS_BP_PERSISTENT
 #define HCS_BP_PERSISTENT 1
 #endif
+// Node iterations with <= 16 items popped with two lanes per item (one per child).  Measured and off
+// (scripts/sweep_r01h.sh): C1 broadphase 0.0450 -> 0.0455 ms, C5 17.9 -> 18.4 ms, C3 0.795 -> 0.760 ms; the
+// iterations are bound by their dependent chain (queue pop -> node load -> ballots -> push), not by the box tests.
+#ifndef HCS_BP_PAIRED_POP
+#define HCS_BP_PAIRED_POP 0
+#endif
 #ifndef HCS_BP_LEAF32 // soft-rigid leaf test: conservative float filter in front of the exact fp64 early-outs
 #define HCS_BP_LEAF32 1
 #endif
@@ -454,12 +460,21 @@ __device__ __forceinline__ void broadphase_unit(const PairDesc &P, const StepIO 
 			} else {
 				// pop k items, push <= 2k: the queue grows by <= k.  Near the capacity fewer items are popped,
 				// which turns the LIFO into a depth-first walk whose stack stays below the tree depth.
-				int k = max(1, min(min(32, n_node), NODE_Q - n_node));
+				// A small frontier (one environment of the sphere-on-box scene offers 12 items on average) is popped with
+				// TWO lanes per item, one per child: each lane runs one box test instead of two, twice as many lanes
+				// work.  Which mode runs depends on n_node only, so the candidate order stays a function of the unit.
+#if HCS_BP_PAIRED_POP
+				const bool paired = n_node <= 16;
+#else
+				const bool paired = false;
+#endif
+				int k = paired ? n_node : max(1, min(min(32, n_node), NODE_Q - n_node));
 				bool pushL = false, pushR = false, leafL = false, leafR = false;
 				int cl = 0, cr = 0;
 				unsigned s = 0;
-				if (lane < k) {
-					unsigned raw = W.nodeq[n_node - k + lane];
+				const int item = paired ? lane >> 1 : lane;
+				if (item < k) {
+					unsigned raw = W.nodeq[n_node - k + item];
 					uint2 it     = make_uint2(raw >> ITEM_SHIFT, raw & ITEM_MASK);
 					s            = it.x;
 					float qb[6];
@@ -475,13 +490,23 @@ __device__ __forceinline__ void broadphase_unit(const PairDesc &P, const StepIO 
 					const float4 *nd = nodes4 + 4 * (size_t)it.y;
 					float4 a = nd[0], b = nd[1], c = nd[2], d = nd[3];
 					cl = __float_as_int(d.x), cr = __float_as_int(d.y);
-					if (box_overlap<!QTET>(qb, pl, a, b, c, true)) {
-						leafL = cl < 0;
-						pushL = !leafL;
-					}
-					if (box_overlap<!QTET>(qb, pl, a, b, c, false)) {
-						leafR = cr < 0;
-						pushR = !leafR;
+					if (paired) { // even lane: left child, odd lane: right child; reported through the "L" slots
+						const bool left = !(lane & 1);
+						if (!left)
+							cl = cr;
+						if (box_overlap<!QTET>(qb, pl, a, b, c, left)) {
+							leafL = cl < 0;
+							pushL = !leafL;
+						}
+					} else {
+						if (box_overlap<!QTET>(qb, pl, a, b, c, true)) {
+							leafL = cl < 0;
+							pushL = !leafL;
+						}
+						if (box_overlap<!QTET>(qb, pl, a, b, c, false)) {
+							leafR = cr < 0;
+							pushR = !leafR;
+						}
 					}
 				}
 				n_node -= k;
