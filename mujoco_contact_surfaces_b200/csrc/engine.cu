@@ -317,6 +317,7 @@ static void upload_geom(hcs_ctx *c, GeomHost &g)
 			d.tet_geom  = dalloc<TetGeom>(g.allocs, d.n_elems);
 			d.tet_field = dalloc<TetField>(g.allocs, d.n_elems);
 			d.tet_leaf32 = dalloc<TetLeaf32>(g.allocs, d.n_elems);
+			d.tet_leafss32 = dalloc<TetLeafSS32>(g.allocs, d.n_elems);
 			d.nodes = dalloc<BvhNode>(g.allocs, std::max(1, d.n_elems - 1));
 			BvhNode root;
 			if (d.n_elems < 2 || std::getenv("HCS_LBVH_HOST")) { // host builder: single-tet trees and cross-checks

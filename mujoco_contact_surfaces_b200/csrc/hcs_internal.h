@@ -31,6 +31,12 @@ struct __align__(32) TetLeaf32 { // 128 B = one line: float copy of what the bro
 	float pad;
 	float v[4][3]; // tet vertices
 };
+struct __align__(32) TetLeafSS32 { // 96 B: float copy of what the soft-soft leaf filter reads of the tree-side tet
+	float grad[3], e0; // as TetField::grad / e0
+	float ghat[3], pad;
+	float v[4][3];
+	float pad2[4];
+};
 struct __align__(32) TriRec { // 96 B = 3 x 32 B: rigid triangle vertices + unit normal
 	double v[3][3];
 	double n[3];
@@ -50,6 +56,7 @@ struct GeomDev {
 	TetGeom *tet_geom;  // soft
 	TetField *tet_field;
 	TetLeaf32 *tet_leaf32;
+	TetLeafSS32 *tet_leafss32;
 	TriRec *tris;       // rigid
 	BvhNode *nodes;     // soft: LBVH over tets (root = node 0)
 	double bound_c[3];  // bounding sphere in the geom frame

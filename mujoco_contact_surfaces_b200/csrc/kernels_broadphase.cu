@@ -51,12 +51,16 @@ struct __align__(16) WarpQueues {
 	unsigned leafq[LEAF_Q];
 	double qv[12][32];  // transformed query vertices (tri: 9 + rotated normal 3; tet: 12), lane-interleaved
 	float qbox[6][32];
-	float qpl[4][32]; // soft-rigid: the query triangle's plane (unit normal, offset) in A's frame
-	float qvf[9][32]; // soft-rigid: the query triangle's vertices in A's frame, rounded to float (leaf filter)
-	float qm[32];     // soft-rigid: the filter's margin for this query (4e-6 x the largest coordinate involved)
+	float qpl[4][32]; // soft-rigid: the query triangle's plane (unit normal, offset) in A's frame;
+	                  // soft-soft: the query tet's pressure gradient in A's frame (0..2), its field at A's origin (3)
+	float qvf[12][32]; // the query's vertices in A's frame, rounded to float (leaf filters)
+	float qm[32];     // soft-rigid: the filter's margin for this query (4e-6 x the largest coordinate involved);
+	                  // soft-soft: the largest coordinate involved
+	float qx[4][32];  // soft-soft: the query tet's unit gradient in A's frame (0..2), L1 norm of its gradient (3)
 	int qid[32];
 	uint2 stage[STAGE]; // surviving (query, tet) candidates waiting to be appended to the pair's flat list
 };
+static_assert(sizeof(WarpQueues) * BP_WARPS <= 48 * 1024, "static shared memory of a broadphase CTA");
 
 // Append the first n_flush staged candidates (a multiple of 32 except at the end of the unit) to the pair's flat
 // list as one range and link the range to the unit's chain.  WHERE the range lands depends on the order in which
@@ -326,6 +330,25 @@ __device__ __forceinline__ void broadphase_unit(const PairDesc &P, const StepIO 
 					big            = fmaxf(big, fabsf((float)v[k]));
 				}
 				W.qm[slot] = 4e-6f * big + 1e-30f;
+			} else {
+#if HCS_BP_LEAF32
+				// what the float filter of the soft-soft leaf test needs of the query tet, computed once per query in
+				// double: gradient and unit gradient rotated into A's frame, field value at A's origin
+				const TetField *f1 = P.B.tet_field + q;
+				const D4 ge1       = load_grad_e0(f1);
+				const D3 g1M = rot(X_AB.R, xyz(ge1)), gh1M = rot(X_AB.R, load_ghat(f1));
+				W.qpl[0][slot] = (float)g1M.x, W.qpl[1][slot] = (float)g1M.y, W.qpl[2][slot] = (float)g1M.z;
+				W.qpl[3][slot] = (float)(dot(xyz(ge1), p_BAo) + ge1.w);
+				W.qx[0][slot] = (float)gh1M.x, W.qx[1][slot] = (float)gh1M.y, W.qx[2][slot] = (float)gh1M.z;
+				W.qx[3][slot] = (float)(fabs(g1M.x) + fabs(g1M.y) + fabs(g1M.z));
+				float big = leaf_scale;
+#pragma unroll
+				for (int k = 0; k < 12; ++k) {
+					W.qvf[k][slot] = (float)v[k];
+					big            = fmaxf(big, fabsf((float)v[k]));
+				}
+				W.qm[slot] = big;
+#endif
 			}
 			W.qid[slot]   = q;
 			W.nodeq[slot] = (unsigned)slot << ITEM_SHIFT; // (slot, root)
@@ -411,6 +434,55 @@ __device__ __forceinline__ void broadphase_unit(const PairDesc &P, const StepIO 
 						}
 #endif
 					} else {
+						bool need_exact = true;
+#if HCS_BP_LEAF32
+						// Float filter (see the soft-rigid one above): equal-pressure plane n = grad0 - grad1, offset
+						// -(e0 - f1(Mo)) / |n| in float with explicit error bounds.  en bounds the direction error of the
+						// unit normal (the gradients cancel: relative error ~ eps (|grad0| + |grad1|) / |n|), epd the
+						// error of the offset; both blow up when the gradients nearly cancel, and then nothing is
+						// rejected here.  The two gradient culls are semantic filters: they are decided in float only
+						// when clear by en + 1e-5, otherwise the pair takes the exact path below.  Every comparison is
+						// written so that a NaN or an infinity leads to the exact path.
+						{
+							const int s = (int)it.x;
+							const TetLeafSS32 *tl = P.A.tet_leafss32 + it.y;
+							const F8 l0 = ld8f(tl, 0), l1 = ld8f(tl, 1), l2 = ld8f(tl, 2);
+							const float nx = l0.a[0] - W.qpl[0][s], ny = l0.a[1] - W.qpl[1][s], nz = l0.a[2] - W.qpl[2][s];
+							const float mag2 = fdot3(nx, ny, nz, nx, ny, nz);
+							if (mag2 > 1e-30f && mag2 < 1e30f) {
+								const float r  = rsqrtf(mag2);
+								const float hx = nx * r, hy = ny * r, hz = nz * r;
+								const float f1o = W.qpl[3][s];
+								const float G   = fabsf(l0.a[0]) + fabsf(l0.a[1]) + fabsf(l0.a[2]) + W.qx[3][s];
+								const float en  = 1e-6f * G * r;
+								const float pd  = -(l0.a[3] - f1o) * r;
+								const float epd = 1e-6f * (fabsf(l0.a[3]) + fabsf(f1o)) * r + fabsf(pd) * (en + 1e-6f);
+								const float c0  = fdot3(hx, hy, hz, l0.a[4], l0.a[5], l0.a[6]);
+								const float c1  = -fdot3(hx, hy, hz, W.qx[0][s], W.qx[1][s], W.qx[2][s]);
+								const float ec  = en + 1e-5f, cosa = (float)HCS_COS_ALPHA;
+								if (c0 >= cosa + ec && c1 >= cosa + ec) { // both culls clearly pass
+									need_exact    = false;
+									const float m = epd + (en + 4e-6f) * W.qm[s];
+									float h0 = fdot3(hx, hy, hz, l1.a[0], l1.a[1], l1.a[2]) - pd;
+									float h1 = fdot3(hx, hy, hz, l1.a[3], l1.a[4], l1.a[5]) - pd;
+									float h2 = fdot3(hx, hy, hz, l1.a[6], l1.a[7], l2.a[0]) - pd;
+									float h3 = fdot3(hx, hy, hz, l2.a[1], l2.a[2], l2.a[3]) - pd;
+									if ((h0 > m && h1 > m && h2 > m && h3 > m) || (h0 < -m && h1 < -m && h2 < -m && h3 < -m))
+										keep = false;
+									float g0 = fdot3(hx, hy, hz, W.qvf[0][s], W.qvf[1][s], W.qvf[2][s]) - pd;
+									float g1 = fdot3(hx, hy, hz, W.qvf[3][s], W.qvf[4][s], W.qvf[5][s]) - pd;
+									float g2 = fdot3(hx, hy, hz, W.qvf[6][s], W.qvf[7][s], W.qvf[8][s]) - pd;
+									float g3 = fdot3(hx, hy, hz, W.qvf[9][s], W.qvf[10][s], W.qvf[11][s]) - pd;
+									if ((g0 > m && g1 > m && g2 > m && g3 > m) || (g0 < -m && g1 < -m && g2 < -m && g3 < -m))
+										keep = false;
+								} else if (c0 < cosa - ec || c1 < cosa - ec) { // one cull clearly fails
+									need_exact = false;
+									keep       = false;
+								}
+							}
+						}
+#endif
+						if (need_exact) {
 						// soft-soft: CalcEquilibriumPlane + the two IsPlaneNormalAlongPressureGradient culls of
 						// field_intersection.cc (same arithmetic as the clip kernel), then: the equal-pressure plane
 						// must cut BOTH tets, otherwise slice-and-clip is empty.
@@ -446,6 +518,7 @@ __device__ __forceinline__ void broadphase_unit(const PairDesc &P, const StepIO 
 									keep = false;
 							}
 						}
+						} // need_exact
 					}
 				}
 				n_leaf -= k;

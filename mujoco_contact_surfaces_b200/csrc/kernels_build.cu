@@ -73,6 +73,17 @@ __global__ void __launch_bounds__(128) build_tets_kernel(GeomDev g)
 	tl.ghat[0] = (float)gh.x, tl.ghat[1] = (float)gh.y, tl.ghat[2] = (float)gh.z;
 	tl.pad = 0.f;
 	g.tet_leaf32[t] = tl;
+	TetLeafSS32 ts;
+	ts.grad[0] = (float)grad.x, ts.grad[1] = (float)grad.y, ts.grad[2] = (float)grad.z, ts.e0 = (float)tf.e0;
+	ts.ghat[0] = tl.ghat[0], ts.ghat[1] = tl.ghat[1], ts.ghat[2] = tl.ghat[2], ts.pad = 0.f;
+#pragma unroll
+	for (int k = 0; k < 4; ++k) {
+		ts.pad2[k] = 0.f;
+#pragma unroll
+		for (int a = 0; a < 3; ++a)
+			ts.v[k][a] = tl.v[k][a];
+	}
+	g.tet_leafss32[t] = ts;
 }
 
 __global__ void __launch_bounds__(128) build_tris_kernel(GeomDev g)

@@ -42,6 +42,8 @@ struct __align__(32) F8 {
 	float a[8];
 };
 __device__ __forceinline__ F8 ld8f(const TetLeaf32 *t, int group) { return reinterpret_cast<const F8 *>(t)[group]; }
+// TetLeafSS32: grad, e0, ghat, - | v0, v1, v2.xy | v2.z, v3, -
+__device__ __forceinline__ F8 ld8f(const TetLeafSS32 *t, int group) { return reinterpret_cast<const F8 *>(t)[group]; }
 __device__ __forceinline__ float fdot3(float ax, float ay, float az, float bx, float by, float bz)
 {
 	return __fmaf_rn(ax, bx, __fmaf_rn(ay, by, az * bz));
