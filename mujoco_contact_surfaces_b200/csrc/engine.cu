@@ -437,6 +437,19 @@ static void build_pairs(hcs_ctx *c)
 			int S        = (int)std::min<long>(chunks, want);
 			S            = std::max(S, 1);
 			P.slice_q    = 32 * ((chunks + S - 1) / S);
+			// Small batches against a LARGE tree (the reference's own case is ONE mjData; C5: 131 072-tet pads): a unit is
+			// walked by one warp, and the few query elements that touch the other geom are neighbours in the element
+			// order, so with 32 queries per unit one or two warps did all the work of an environment.  When the batch
+			// cannot fill the GPU with 32-query units the slices shrink, down to a single query element (its tree walk
+			// still pops up to 32 nodes per iteration): C5 x 1 env 4.74 -> 2.62 ms.  Small trees keep whole chunks: there
+			// the extra units cost more in the finalize than the walk gains (C1 x 1 env 0.028 -> 0.037 ms, C3 x 1 env
+			// 0.075 -> 0.34 ms; scripts/sweep_r01j.sh).  HCS_FINE_SLICES=0/1 overrides.
+			{
+				const char *fs = getenv("HCS_FINE_SLICES");
+				const bool fine = fs ? atoi(fs) != 0 : P.n_tree >= 16384;
+				if (fine && P.kind != PAIR_SOFT_PLANE && want > chunks)
+					P.slice_q = (int)std::max<long>(1, (P.nq + want - 1) / want);
+			}
 			P.n_slices   = (P.nq + P.slice_q - 1) / P.slice_q;
 			size_t units = (size_t)n_env * P.n_slices;
 			P.partial    = dalloc<SlicePartial>(c->step_allocs, units);

@@ -60,8 +60,31 @@ extern __shared__ __align__(16) double smem_d[];
 __device__ __forceinline__ double lds_f64(unsigned a) { return smem_d[a >> 3]; }
 __device__ __forceinline__ void sts_f64(unsigned a, double v) { smem_d[a >> 3] = v; }
 
-struct Poly { // view of one lane's polygon buffer: 32-bit shared address of vertex 0, x; stride 256 B per scalar
+// x and y of a vertex in one 16-byte shared access (2 instead of 3 accesses per vertex, 12 % fewer instructions in
+// the tet-triangle kernel).  Measured and off (scripts/sweep_r01j.sh): C1 narrowphase 0.0400 -> 0.0399 ms, C3 0.956 ->
+// 0.935 ms, C5 18.7 -> 19.1 ms: the kernels wait on dependent fp64 results, not on issue slots.
+#ifndef HCS_POLY_XY128
+#define HCS_POLY_XY128 0
+#endif
+// view of one lane's polygon buffer: a = 32-bit shared address of the buffer + 8 * lane; 768 bytes per vertex.
+// HCS_POLY_XY128: a vertex block holds the 32 lanes' (x, y) pairs (16 bytes each) and then their z (8 bytes each), so a
+// vertex moves with one 128-bit and one 64-bit access; otherwise three 256-byte rows x, y, z.
+struct Poly {
 	unsigned a;
+#if HCS_POLY_XY128
+	__device__ __forceinline__ D3 get(int i) const
+	{
+		unsigned p      = a + 768u * i;
+		const double2 q = reinterpret_cast<const double2 *>(smem_d)[(p + 8u * (threadIdx.x & 31u)) >> 4];
+		return mk(q.x, q.y, lds_f64(p + 512u));
+	}
+	__device__ __forceinline__ void set(int i, D3 v) const
+	{
+		unsigned p = a + 768u * i;
+		reinterpret_cast<double2 *>(smem_d)[(p + 8u * (threadIdx.x & 31u)) >> 4] = make_double2(v.x, v.y);
+		sts_f64(p + 512u, v.z);
+	}
+#else
 	__device__ __forceinline__ D3 get(int i) const
 	{
 		unsigned p = a + 768u * i;
@@ -74,6 +97,7 @@ struct Poly { // view of one lane's polygon buffer: 32-bit shared address of ver
 		sts_f64(p + 256u, v.y);
 		sts_f64(p + 512u, v.z);
 	}
+#endif
 };
 struct PressTile { // vertex pressures of one lane
 	unsigned a;
