@@ -1021,6 +1021,39 @@ __device__ __forceinline__ void finalize_pair(const PairDesc *pairs, const StepI
 	io.pair_out[idx] = r;
 }
 
+// A pair with many slices per environment (small batches against large trees, engine.cu build_pairs): the whole warp
+// adds the unit partials, lane l the slices l, l + 32, ... in increasing order, then the fixed xor-shuffle tree.
+__device__ __forceinline__ void finalize_pair_warp(const PairDesc *pairs, const StepIO &io, int env, int p, int lane)
+{
+	const PairDesc &P      = pairs[p];
+	const SlicePartial *sp = P.partial + (size_t)env * P.n_slices;
+	Acc acc = zero_acc();
+	for (int s = lane; s < P.n_slices; s += 32) {
+		const SlicePartial q = sp[s];
+		acc.F   = acc.F + mk(q.F[0], q.F[1], q.F[2]);
+		acc.tau = acc.tau + mk(q.tau[0], q.tau[1], q.tau[2]);
+		acc.ac  = acc.ac + mk(q.ac[0], q.ac[1], q.ac[2]);
+		acc.area += q.area;
+		acc.n_polygons += q.n_polygons, acc.n_faces += q.n_faces, acc.n_points += q.n_points;
+		acc.n_candidates += q.n_candidates, acc.n_clipped += q.n_clipped;
+	}
+	acc = group_sum<32>(acc);
+	if (lane == 0) {
+		hcs_pair_result r;
+		r.F[0] = P.sign * acc.F.x, r.F[1] = P.sign * acc.F.y, r.F[2] = P.sign * acc.F.z;
+		r.tau[0] = P.sign * acc.tau.x, r.tau[1] = P.sign * acc.tau.y, r.tau[2] = P.sign * acc.tau.z;
+		r.area        = acc.area;
+		r.centroid[0] = acc.area > 0 ? acc.ac.x / acc.area : 0.0;
+		r.centroid[1] = acc.area > 0 ? acc.ac.y / acc.area : 0.0;
+		r.centroid[2] = acc.area > 0 ? acc.ac.z / acc.area : 0.0;
+		r.gM = P.gM, r.gN = P.gN;
+		r.n_polygons = acc.n_polygons, r.n_faces = acc.n_faces, r.n_points = acc.n_points;
+		r.n_candidates = acc.n_candidates, r.n_clipped = acc.n_clipped, r.reserved = 0;
+		io.pair_out[env * io.n_pairs + p] = r;
+	}
+}
+constexpr int FIN_COOP_SLICES = 32; // more slices than this: finalize_pair_warp
+
 // The finalize kernel is the last kernel of a step without sensors: one thread mirrors the error flags into the
 // caller's mapped pinned memory, so that the end-to-end path needs no copy after the kernels (every kernel that can
 // raise a flag has finished: stream order).
@@ -1058,8 +1091,12 @@ __global__ void __launch_bounds__(128) finalize_kernel(const PairDesc *pairs, St
 		}
 	}
 	__syncthreads(); // unit partials (global) are visible to the whole CTA
+	for (int p = wid; p < io.n_pairs; p += n_warps)
+		if (pairs[p].kind != PAIR_NONE && pairs[p].n_slices > FIN_COOP_SLICES)
+			finalize_pair_warp(pairs, io, env, p, lane);
 	for (int p = threadIdx.x; p < io.n_pairs; p += blockDim.x)
-		finalize_pair(pairs, io, env, p);
+		if (!(pairs[p].kind != PAIR_NONE && pairs[p].n_slices > FIN_COOP_SLICES))
+			finalize_pair(pairs, io, env, p);
 	__syncthreads();
 	for (int g = threadIdx.x; g < io.n_geoms; g += blockDim.x) {
 		double w[6] = { 0, 0, 0, 0, 0, 0 };
