@@ -113,7 +113,7 @@ def cpu_baseline(scene, seed, sample_envs, with_sensors, threads_all=True):
     from oracle import oracle
     orc = oracle.OracleScene(scene.triangle, scene.apply_forces)
     S.configure(orc, scene)
-    n_threads = oracle.num_threads()
+    n_threads = max(oracle.num_threads(), len(os.sched_getaffinity(0)))  # OMP_NUM_THREADS=1 under torchrun
     # calibrate
     xp, xm, ve = scene.poses(8, seed)
     t8, _, _ = orc.bench(xp, xm, ve, use_bvh=True, with_sensors=with_sensors, threads=1)
@@ -146,7 +146,9 @@ def run_reference(args, scene, with_sensors):
     from oracle import oracle
     orc = oracle.OracleScene(scene.triangle, scene.apply_forces)
     S.configure(orc, scene)
-    threads = oracle.num_threads()
+    # all the host threads this process may run on: torchrun exports OMP_NUM_THREADS=1 to its workers, which would
+    # silently turn this arm into the one-thread variant for N > 1
+    threads = max(oracle.num_threads(), len(os.sched_getaffinity(0)))
     xp, xm, ve = scene.poses(8, 1234)
     t8, _, _ = orc.bench(xp, xm, ve, True, with_sensors, 1)
     per_env = max(t8 / 8, 1e-7)
