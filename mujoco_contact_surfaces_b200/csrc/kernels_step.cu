@@ -190,6 +190,22 @@ __device__ __forceinline__ D3 face_force(D3 p, D3 n, double fn0, double k, const
 }
 
 // ---- Sutherland-Hodgman step: ClipPolygonByHalfSpace + CalcIntersection (mesh_intersection.cc) ----
+// CalcIntersection(current, previous) with a = sd(current), b = sd(previous): wa = b / (b - a), wa * current + wb * previous
+__device__ __forceinline__ D3 clip_crossing(D3 pc, double sc, D3 pprev, double sprev)
+{
+	double wa = sprev / (sprev - sc);
+	double wb = 1.0 - wa;
+	return wa * pc + wb * pprev;
+}
+// HCS_CLIP_DEFER=1: a plane cuts a convex polygon in at most two edges, but inside the vertex loop the crossing block (an
+// IEEE division and a lerp) runs in every iteration in which any lane of the warp has a crossing.  The variant only
+// reserves the output slot in the loop and computes the first two crossings of a lane after it (same operands, same
+// operations: bit-identical vertices, parity green).  Measured and off (scripts/sweep_r01k.sh): C1 narrowphase 0.0400 ->
+// 0.0419 ms, C3 0.958 -> 1.044 ms, C5 18.8 -> 19.4 ms: reloading the two vertices and recomputing their signed distances
+// costs more than the divergent block did.  (The clip is 33 of the kernel's 40 us on C1; quadrature + force law 8.)
+#ifndef HCS_CLIP_DEFER
+#define HCS_CLIP_DEFER 0
+#endif
 __device__ __forceinline__ int clip_halfspace(Poly in, int n, D3 nh, double d, Poly out)
 {
 	if (n == 0)
@@ -197,21 +213,39 @@ __device__ __forceinline__ int clip_halfspace(Poly in, int n, D3 nh, double d, P
 	D3 pprev     = in.get(n - 1);
 	double sprev = dot(nh, pprev) - d;
 	int m        = 0;
+#if HCS_CLIP_DEFER
+	unsigned pending = 0; // per deferred crossing one byte: output slot | input vertex << 4
+	int n_pending    = 0;
+#endif
 #pragma unroll 1
 	for (int i = 0; i < n; ++i) {
 		D3 pc     = in.get(i);
 		double sc = dot(nh, pc) - d;
 		bool cin = sc <= 0, pin = sprev <= 0;
-		if (cin != pin) { // CalcIntersection(current, previous): a = sd(current), b = sd(previous)
-			double wa = sprev / (sprev - sc);
-			double wb = 1.0 - wa;
-			out.set(m++, wa * pc + wb * pprev);
+		if (cin != pin) {
+#if HCS_CLIP_DEFER
+			if (n_pending < 2) {
+				pending |= (unsigned)(m | (i << 4)) << (8 * n_pending);
+				++n_pending;
+				++m;
+			} else
+#endif
+				out.set(m++, clip_crossing(pc, sc, pprev, sprev));
 		}
 		if (cin)
 			out.set(m++, pc);
 		pprev = pc;
 		sprev = sc;
 	}
+#if HCS_CLIP_DEFER
+#pragma unroll
+	for (int c = 0; c < 2; ++c)
+		if (c < n_pending) {
+			const int slot = (pending >> (8 * c)) & 15, i = (pending >> (8 * c + 4)) & 15;
+			const D3 pc = in.get(i), pp = in.get(i == 0 ? n - 1 : i - 1);
+			out.set(slot, clip_crossing(pc, dot(nh, pc) - d, pp, dot(nh, pp) - d));
+		}
+#endif
 	return m;
 }
 
