@@ -148,11 +148,19 @@ def myrmex(presser="box", sampling_resolution=20, window=0, sigma=-1.0, resoluti
         v, f = load_mesh_fixture("spot")
         v = (v * np.float32(0.05)).astype(np.float32)
         pg, pverts = Geom("spot", GEOM_MESH, [0, 0, 0], [0, 1.0, 0, 0.3, 0.3], v, f), v.astype(np.float64)
+    elif presser == "soft_tip":
+        # C2b (BASELINE.json words config 2 as "pressed by soft mesh objects"): a SOFT convex-mesh presser,
+        # the fingertip mesh of SENS/assets (ubi_tip_collision.stl, millimetres) four times life size so that it covers
+        # several 25 mm taxels; centroid-fan tets (plugin.cpp:161-187, 767-787) => the soft-soft query (a7) feeds the sensor
+        v, f = load_mesh_fixture("ubi_tip")
+        v = (v * np.float32(0.004)).astype(np.float32)
+        pg, pverts = Geom("soft_tip", GEOM_MESH, [0, 0, 0], [1e5, 2.0, 0, 0.6, 0.6], v, f), v.astype(np.float64)
     else:
         raise ValueError(presser)
     foam = Geom("myrmex_foam", GEOM_BOX, [0.2, 0.2, 0.02], [5e4, 5.0, 0, 0.3, 0.3])
     sensors = [dict(geom=1, resolution=resolution, sampling_resolution=sampling_resolution, window=window, sigma=sigma)]
-    sc = Scene("c2_myrmex_" + presser, [pg, foam], [(0, 1)], triangle=True, sensors=sensors)
+    sc = Scene(("c2b_myrmex_" if presser.startswith("soft") else "c2_myrmex_") + presser, [pg, foam], [(0, 1)], triangle=True,
+               sensors=sensors)
     foam_top = 0.033 + 0.02
 
     def pose(rng, env, xpos, xmat, vel):
@@ -397,6 +405,7 @@ SCENES = {
     "c2_myrmex_box": lambda: myrmex("box"),
     "c2_myrmex_plate": lambda: myrmex("plate"),
     "c2_myrmex_spot": lambda: myrmex("spot"),
+    "c2b_myrmex_soft_tip": lambda: myrmex("soft_tip"),
     "c3_soft_soft": soft_soft,
     "c4_objects_on_plane": objects_on_plane,
     "c5_grasp_box": lambda: grasp("box"),

@@ -108,8 +108,9 @@ def test_c4_objects_on_plane_triangle(hcs_lib):
     _run_scene(scenes.objects_on_plane(triangle=True), 16, seed=4097, hcs_lib=hcs_lib)
 
 
-@pytest.mark.parametrize("presser,S", [("box", 4), ("box", 20), ("plate", 8), ("spot", 8)])
+@pytest.mark.parametrize("presser,S", [("box", 4), ("box", 20), ("plate", 8), ("spot", 8), ("soft_tip", 8), ("soft_tip", 20)])
 def test_c2_myrmex_taxel_image(hcs_lib, presser, S):
+    # soft_tip = C2b: a SOFT convex-mesh presser (soft-soft query feeding the flat sensor)
     _run_scene(scenes.myrmex(presser, sampling_resolution=S), 8, seed=7, hcs_lib=hcs_lib, with_sensors=True)
 
 
