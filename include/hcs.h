@@ -147,18 +147,23 @@ int hcs_curved_sensor_info(const hcs_ctx *ctx, int sensor, int *n_taxels, int *n
 int hcs_get_curved_values(hcs_ctx *ctx, int sensor, float *out);
 const float *hcs_device_curved_values(hcs_ctx *ctx, int sensor);
 
-/* replaces TaxelSensor (SENS/src/taxel_sensor.cpp) with sample_method "default": load() :45-156, internal_update()
- * :158-478.  taxel_pos: [n_taxels][3] in the sensor geom's frame.  method: 0 closest, 1 weighted, 2 mean,
- * 3 squared (:79-91).  Every step (with_sensors != 0) each contact-surface triangle of the sensor geom is sampled on
- * the barycentric lattice of :191-211 and every taxel is evaluated from the samples within include_margin.
- * The reference's observable behaviour is reproduced, including its quirks: weighted and mean fall
- * through to squared (value = sample_resolution * sum (include_margin - d)^2 |p|), closest keeps the pressure only
- * when `visualize` is on (else 0), taxels without a sample in range keep the value of the previous update, an update
- * without any sample zeroes the message.  sample_method "area_importance" is not offered: it consumes one random
- * stream along the triangle order of Drake's mesh builder, which is not observable through the reference.
- * Returns the taxel sensor index. */
+/* replaces TaxelSensor (SENS/src/taxel_sensor.cpp): load() :45-156, internal_update() :158-478.
+ * taxel_pos: [n_taxels][3] in the sensor geom's frame.  method: 0 closest, 1 weighted, 2 mean, 3 squared (:79-91).
+ * sample_method 0 = "default": every step (with_sensors != 0) each contact-surface triangle of the sensor geom is
+ * sampled on the barycentric lattice of :191-211.  sample_method 1 = "area_importance" (:211-254, the method the
+ * reference's fingertip.yaml uses): one sample per stratum of sample_resolution * total_area along the cumulative
+ * triangle area of every surface, uniform in the owning triangle, drawn from one std::default_random_engine
+ * (minstd_rand0, default seed, libstdc++ generate_canonical) that restarts every update.  Which random numbers a
+ * triangle gets depends on the triangle order; Drake's is not observable through the reference, ours is canonical
+ * (pairs in pair order, polygons by (elemM, elemN), fan triangles in fan order), so values agree with the reference
+ * in distribution, and with this repo's oracle to 1e-6.
+ * Every taxel is evaluated from the samples within include_margin.  The reference's observable behaviour is
+ * reproduced, including its quirks: weighted and mean fall through to squared (value =
+ * sample_resolution * sum (include_margin - d)^2 |p|), closest keeps the pressure only when `visualize` is on (else 0),
+ * taxels without a sample in range keep the value of the previous update, an update without any sample zeroes the
+ * message.  Returns the taxel sensor index. */
 int hcs_add_taxel_sensor(hcs_ctx *ctx, int geom, int n_taxels, const double *taxel_pos, double include_margin,
-                         double sample_resolution, int method, int visualize);
+                         double sample_resolution, int method, int visualize, int sample_method);
 /* out: float [n_envs][n_taxels] */
 int hcs_get_taxel_values(hcs_ctx *ctx, int sensor, float *out);
 const float *hcs_device_taxel_values(hcs_ctx *ctx, int sensor);

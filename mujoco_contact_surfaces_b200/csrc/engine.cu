@@ -72,6 +72,7 @@ struct CurvedHost {
 // TaxelSensor::load (SENS/src/taxel_sensor.cpp:45-156), sample_method "default"
 struct TaxelHost {
 	int geom, method, visualize;
+	int sample_method = 0; // 0 default, 1 area_importance
 	double include_margin, sample_resolution;
 	std::vector<double> taxel_pos; // [n][3] geom frame
 	int n_taxels() const { return (int)taxel_pos.size() / 3; }
@@ -695,10 +696,24 @@ static void finalize(hcs_ctx *c)
 	io.tri_vd = nullptr;
 	if (!c->taxel.empty() && io.max_tris > 0)
 		io.tri_vd = dalloc<double>(c->step_allocs, (size_t)9 * io.max_tris);
+	io.tri_elem = nullptr;
+	for (const TaxelHost &th : c->taxel)
+		if (th.sample_method == 1 && io.max_tris > 0 && !io.tri_elem)
+			io.tri_elem = dalloc<uint2>(c->step_allocs, (size_t)io.max_tris);
 	for (TaxelHost &th : c->taxel) {
 		const int nt = th.n_taxels();
 		TaxelDev d{};
 		d.geom = th.geom, d.n_taxels = nt, d.method = th.method, d.visualize = th.visualize;
+		d.sample_method = th.sample_method;
+		if (th.sample_method == 1) { // one stratum of sample_resolution * total_area per sample and surface
+			long per_surface = (long)std::ceil(1.0 / th.sample_resolution) + 2;
+			d.max_samples    = (int)std::min<long>(std::max<long>(per_surface * (long)std::max<size_t>(c->pairs.size(), 1), 16), 1L << 20);
+			d.samples        = dalloc<double>(c->step_allocs, (size_t)n_env * d.max_samples * 4);
+			d.n_samples      = dalloc<int32_t>(c->step_allocs, n_env);
+			d.env_offset     = dalloc<int32_t>(c->step_allocs, (size_t)n_env + 1);
+			d.env_cursor     = dalloc<int32_t>(c->step_allocs, n_env);
+			d.env_items      = dalloc<int32_t>(c->step_allocs, (size_t)std::max(io.max_tris, 1));
+		}
 		d.include_margin = th.include_margin, d.sample_resolution = th.sample_resolution;
 		d.taxel_pos   = upload(c, th.taxel_pos);
 		size_t ncell  = (size_t)n_env * nt;
@@ -1223,16 +1238,17 @@ const float *hcs_device_curved_values(hcs_ctx *c, int sensor)
 }
 
 int hcs_add_taxel_sensor(hcs_ctx *c, int geom, int n_taxels, const double *taxel_pos, double include_margin,
-                         double sample_resolution, int method, int visualize)
+                         double sample_resolution, int method, int visualize, int sample_method)
 {
 	API_BEGIN(c)
 	if (geom < 0 || geom >= (int)c->geoms.size() || n_taxels < 1 || !taxel_pos || !(include_margin > 0) ||
-	    !(sample_resolution > 0) || method < 0 || method > 3) {
-		c->err = "hcs_add_taxel_sensor: needs a geom, >= 1 taxel, include_margin > 0, sample_resolution > 0, method in 0..3";
+	    !(sample_resolution > 0) || method < 0 || method > 3 || sample_method < 0 || sample_method > 1) {
+		c->err = "hcs_add_taxel_sensor: needs a geom, >= 1 taxel, include_margin > 0, sample_resolution > 0, method in "
+		         "0..3, sample_method in 0..1";
 		return HCS_E_INVALID;
 	}
 	TaxelHost s{};
-	s.geom = geom, s.method = method, s.visualize = visualize != 0;
+	s.geom = geom, s.method = method, s.visualize = visualize != 0, s.sample_method = sample_method;
 	s.include_margin = include_margin, s.sample_resolution = sample_resolution;
 	s.taxel_pos.assign(taxel_pos, taxel_pos + 3 * (size_t)n_taxels);
 	c->taxel.push_back(std::move(s));

@@ -136,6 +136,8 @@ struct StepIO {
 	int max_tris;
 	double *tri_vd;            // [max_tris][9] the same triangles' world vertices in double, or NULL (only taxel
 	                           // sensors need them: their sample lattice is evaluated in double)
+	uint2 *tri_elem;           // [max_tris] (elemM, elemN) of the polygon a triangle fans, or NULL (only area-importance
+	                           // taxel sensors need them: their triangle order is (pair, elemM, elemN, fan triangle))
 	hcs_pair_result *pair_out; // [n_env][n_pairs]
 	double *geom_wrench;       // [n_env][n_geoms][6]
 	// end-to-end path without sensors: device addresses of the context's mapped pinned mirrors (else NULL); the
@@ -191,6 +193,12 @@ struct TaxelDev {
 	int32_t *env_tris;       // [n_env] triangles of this sensor's contact surfaces (0: the message is zeroed)
 	int32_t *bin_count, *bin_offset, *bin_cursor, *bin_items, *scan_tmp; // per (env, taxel) triangle bins
 	int items_cap;
+	// sample_method AREA_IMPORTANCE (taxel_sensor.cpp:211-254): per-environment triangle lists and sample records
+	int sample_method;                            // 0 DEFAULT, 1 AREA_IMPORTANCE
+	int32_t *env_offset, *env_cursor, *env_items; // [n_env + 1], [n_env], [max_tris]
+	int32_t *n_samples;                           // [n_env]
+	double *samples;                              // [n_env][max_samples][4]: world point, pressure
+	int max_samples;
 };
 
 // ---- programmatic dependent launch (sm_90+) -------------------------------------------------------

@@ -449,8 +449,9 @@ __device__ __forceinline__ void integrate_polygon(Poly P, int n, D3 nhat, D3 gra
 // counts, ONE atomicAdd per warp.  World vertices are recomputed from the shared tile.
 template <bool IDENT, class CTX>
 __device__ __forceinline__ void emit_tactile(int n_faces, Poly P, PressTile e, D3 cen, double ec, const CTX &c,
-                                             const StepIO &io, int slice, int index, int lane)
-{ // (slice, index): the emitting unit's slice and the candidate's index inside it (half space: 0 and the tet)
+                                             const StepIO &io, int slice, int index, int lane, int elemA, int elemB)
+{ // (slice, index): the emitting unit's slice and the candidate's index inside it (half space: 0 and the tet);
+  // (elemA, elemB): the elements of geom A / geom B that produced the polygon
 	int incl = n_faces;
 #pragma unroll
 	for (int o = 1; o < 32; o <<= 1) {
@@ -495,6 +496,8 @@ __device__ __forceinline__ void emit_tactile(int n_faces, Poly P, PressTile e, D
 					vd[0] = v0.x, vd[1] = v0.y, vd[2] = v0.z, vd[3] = v1.x, vd[4] = v1.y, vd[5] = v1.z;
 					vd[6] = cW.x, vd[7] = cW.y, vd[8] = cW.z;
 				}
+				if (io.tri_elem)
+					io.tri_elem[pos] = fwd ? make_uint2((unsigned)elemA, (unsigned)elemB) : make_uint2((unsigned)elemB, (unsigned)elemA);
 			} else {
 				atomicOr(io.flags, 2);
 			}
@@ -677,7 +680,7 @@ __global__ void __launch_bounds__(32 * HCS_NP_TRI_WARPS, HCS_NP_TRI_CTAS) narrow
 		}
 		if (TRI && P.emit_tactile)
 			emit_tactile<false>(tfaces, Poly{ buf0 + cur * buf_stride }, PressTile{ buf0 + (cur ^ 1) * buf_stride }, cen, ec, ctx, io,
-			                    (int)rec.z - env * P.n_slices, (int)rec.w, lane);
+			                    (int)rec.z - env * P.n_slices, (int)rec.w, lane, (int)rec.y, (int)rec.x);
 		chunk = granted_chunk(P.counters + 1, requested, lane);
 	}
 }
@@ -808,7 +811,7 @@ __global__ void __launch_bounds__(NP_BLOCK, HCS_NP_TET_CTAS) narrow_tet_tet_kern
 		}
 		if (TRI && P.emit_tactile)
 			emit_tactile<false>(tfaces, Poly{ buf0 + cur * buf_stride }, PressTile{ buf0 + (cur ^ 1) * buf_stride }, cen, ec, ctx, io,
-			                    (int)rec.z - env * P.n_slices, (int)rec.w, lane);
+			                    (int)rec.z - env * P.n_slices, (int)rec.w, lane, (int)rec.y, (int)rec.x);
 		chunk = granted_chunk(P.counters + 1, requested, lane);
 	}
 }
@@ -1012,7 +1015,7 @@ __global__ void __launch_bounds__(NP_BLOCK, HCS_NP_PLANE_CTAS) narrow_tet_plane_
 			P.nverts[g] = (uint8_t)(nv | (acc.n_points << 4));
 		}
 		if (TRI && P.emit_tactile)
-			emit_tactile<true>(tfaces, poly, e, cen, ec, ctx, io, (int)rec.z - env * P.n_slices, (int)rec.w, lane);
+			emit_tactile<true>(tfaces, poly, e, cen, ec, ctx, io, (int)rec.z - env * P.n_slices, (int)rec.w, lane, (int)rec.y, 0);
 		chunk = granted_chunk(P.counters + 1, requested, lane);
 	}
 }

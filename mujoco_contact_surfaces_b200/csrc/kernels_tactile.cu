@@ -14,6 +14,7 @@
 //                       unique (ties between coplanar neighbours carry the same pressure).
 #include <algorithm>
 
+#include "dmath.cuh"
 #include "hcs_internal.h"
 
 namespace hcs {
@@ -806,8 +807,257 @@ __global__ void __launch_bounds__(128) taxel_gather_kernel(TaxelDev td, StepIO i
 		*out = (float)(pressure * res); // :409-412
 }
 
+// ---- sample_method AREA_IMPORTANCE (taxel_sensor.cpp:211-254) ------------------------------------------------------
+// The reference walks the triangles of every contact surface of the sensor geom once, spends one stratum of
+// sample_resolution * total_area per sample along the cumulative area and draws a uniform barycentric point in the
+// triangle that owns the stratum's start, all from ONE std::default_random_engine (minstd_rand0, default seed) that is
+// created anew in every update.  Which random numbers a triangle gets depends on the triangle order, and Drake's is
+// not observable; ours is canonical: pairs in pair order, polygons by (elemM, elemN), fan triangles in fan order,
+// area(t) = |(b - a) x (c - a)| / 2 of the world vertices.  The walk is inherently sequential (one accumulator, one
+// random stream): one CTA per environment sorts the environment's triangles in shared memory, thread 0 walks them
+// and records (triangle, generator state) per sample, then all threads turn the records into points and pressures
+// with libstdc++'s generate_canonical<double, 53> arithmetic (two 31-bit draws per double).
+constexpr int TAXEL_AI_CAP = 4096; // triangles per (environment, sensor) the shared-memory sort holds
+
+template <bool FILL>
+__global__ void __launch_bounds__(256) taxel_ai_list_kernel(TaxelDev td, StepIO io, const PairDesc *pairs)
+{
+	const int n = min(*io.tri_count, io.max_tris);
+	for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+		const TactileTri &t = io.tri_pool[i];
+		const PairDesc &P   = pairs[t.pair_slice >> TRI_SLICE_BITS];
+		if (P.gM != td.geom && P.gN != td.geom)
+			continue;
+		if (!FILL)
+			atomicAdd(td.env_tris + t.env, 1);
+		else
+			td.env_items[td.env_offset[t.env] + atomicAdd(td.env_cursor + t.env, 1)] = i;
+	}
+}
+
+__device__ __forceinline__ unsigned minstd_next(unsigned x) { return (unsigned)((16807ull * x) % 2147483647ull); }
+// std::generate_canonical<double, 53>(minstd_rand0) as libstdc++ evaluates it, = uniform_real_distribution(0, 1)
+__device__ __forceinline__ double minstd_canonical(unsigned &x)
+{
+	const double r = 2147483646.0; // max() - min() + 1
+	x              = minstd_next(x);
+	double sum     = (double)(x - 1u);
+	x              = minstd_next(x);
+	sum += (double)(x - 1u) * r;
+	double ret = sum / (r * r);
+	return ret >= 1.0 ? 0.99999999999999988897769753748 : ret; // nextafter(1, 0)
+}
+
+__global__ void __launch_bounds__(256) taxel_ai_sample_kernel(TaxelDev td, StepIO io)
+{
+	extern __shared__ __align__(16) unsigned char ai_smem[];
+	unsigned long long *key = reinterpret_cast<unsigned long long *>(ai_smem); // [CAP]
+	double *area            = reinterpret_cast<double *>(key + TAXEL_AI_CAP);  // [CAP]
+	int *item               = reinterpret_cast<int *>(area + TAXEL_AI_CAP);    // [CAP]
+	__shared__ int n_out;
+	const int env = blockIdx.x, tid = threadIdx.x;
+	const int first = td.env_offset[env];
+	int n           = td.env_tris[env];
+	if (n > TAXEL_AI_CAP) { // reported, not UB
+		if (tid == 0) {
+			atomicOr(io.flags, 4);
+			td.n_samples[env] = 0;
+		}
+		return;
+	}
+	int np2 = 1;
+	while (np2 < n)
+		np2 <<= 1;
+	for (int i = tid; i < np2; i += blockDim.x) {
+		if (i < n) {
+			const int it        = td.env_items[first + i];
+			const TactileTri &t = io.tri_pool[it];
+			const uint2 el      = io.tri_elem[it];
+			key[i]  = ((unsigned long long)(t.pair_slice >> TRI_SLICE_BITS) << 55) | ((unsigned long long)el.x << 29) |
+			         ((unsigned long long)el.y << 3) | (unsigned long long)(t.idx8 & 7u);
+			item[i] = it;
+		} else {
+			key[i]  = ~0ull;
+			item[i] = -1;
+		}
+	}
+	__syncthreads();
+	for (int k = 2; k <= np2; k <<= 1) // bitonic sort by key (keys are distinct)
+		for (int j = k >> 1; j > 0; j >>= 1) {
+			for (int i = tid; i < np2; i += blockDim.x) {
+				int l = i ^ j;
+				if (l > i) {
+					bool up = (i & k) == 0;
+					unsigned long long a = key[i], b = key[l];
+					if ((a > b) == up) {
+						key[i] = b, key[l] = a;
+						int t = item[i];
+						item[i] = item[l], item[l] = t;
+					}
+				}
+			}
+			__syncthreads();
+		}
+	for (int i = tid; i < n; i += blockDim.x) {
+		const double *v = io.tri_vd + 9 * (size_t)item[i];
+		D3 a = mk(v[0], v[1], v[2]), b = mk(v[3], v[4], v[5]), c = mk(v[6], v[7], v[8]);
+		D3 cr   = cross(b - a, c - a);
+		area[i] = 0.5 * sqrt(dot(cr, cr));
+	}
+	__syncthreads();
+	int32_t *s_item    = td.env_items + first; // reused: the environment's own slots now hold the sorted order
+	double *samp       = td.samples + (size_t)env * td.max_samples * 4;
+	unsigned *s_state  = reinterpret_cast<unsigned *>(samp); // records first (8 bytes per sample), points later
+	if (tid == 0) {
+		unsigned x = 1u; // std::default_random_engine generator;
+		int m      = 0;
+		bool full  = false;
+		for (int i0 = 0; i0 < n && !full;) {
+			const unsigned long long pair = key[i0] >> 55;
+			int i1 = i0;
+			double total = 0;
+			while (i1 < n && (key[i1] >> 55) == pair)
+				total += area[i1++];
+			const double area_resolution = td.sample_resolution * total;
+			double acc = 0, at = 0;
+			if (area_resolution > 0)
+				for (int i = i0; i < i1 && !full; ++i) {
+					at += area[i];
+					while (acc < at) {
+						acc += area_resolution;
+						if (m >= td.max_samples) {
+							full = true;
+							break;
+						}
+						s_state[2 * m]     = x;
+						s_state[2 * m + 1] = (unsigned)i;
+						++m;
+						x = minstd_next(minstd_next(minstd_next(minstd_next(x)))); // two doubles = four draws
+					}
+				}
+			i0 = i1;
+		}
+		if (full)
+			atomicOr(io.flags, 4);
+		n_out             = m;
+		td.n_samples[env] = m;
+	}
+	__syncthreads();
+	const int m = n_out;
+	// records -> (point, pressure); a record is read before its slot range [4k, 4k + 4) doubles is overwritten only by
+	// the thread that owns sample k, and records live in the first m doubles: go from the back in rounds so that no
+	// record is overwritten before it is read
+	for (int base = ((m - 1) / (int)blockDim.x) * (int)blockDim.x; base >= 0; base -= blockDim.x) {
+		const int k = base + tid;
+		unsigned x = 0, i = 0;
+		if (k < m)
+			x = s_state[2 * k], i = s_state[2 * k + 1];
+		__syncthreads();
+		if (k < m) {
+			const int it        = item[i];
+			const TactileTri &t = io.tri_pool[it];
+			const double *v     = io.tri_vd + 9 * (size_t)it;
+			const double u0 = minstd_canonical(x), u1 = minstd_canonical(x);
+			const double a = 1.0 - sqrt(u0), b = (1.0 - a) * u1;
+			const double b0 = a, b1 = (1 - a) * (1 - b), b2 = (1 - a) * b;
+			double *o = samp + 4 * (size_t)k;
+#pragma unroll
+			for (int c = 0; c < 3; ++c)
+				o[c] = b0 * v[c] + b1 * v[3 + c] + b2 * v[6 + c];
+			o[3] = b0 * t.e[0] + b1 * t.e[1] + b2 * t.e[2];
+		}
+		__syncthreads();
+	}
+	(void)s_item;
+}
+
+// one warp per (env, taxel): the environment's samples in order, same per-sample arithmetic as taxel_gather_kernel
+__global__ void __launch_bounds__(128) taxel_ai_gather_kernel(TaxelDev td, StepIO io)
+{
+	const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	const long unit = (long)blockIdx.x * 4 + wib;
+	if (unit >= (long)io.n_env * td.n_taxels)
+		return;
+	const int env = (int)(unit / td.n_taxels), taxel = (int)(unit - (long)env * td.n_taxels);
+	float *out  = td.values + unit;
+	const int m = td.n_samples[env];
+	if (m == 0) { // no sample at all: the message is zeroed (:455-477)
+		if (lane == 0)
+			*out = 0.0f;
+		return;
+	}
+	const double *R  = io.xmat + ((size_t)env * io.n_geoms + td.geom) * 9;
+	const double *xp = io.xpos + ((size_t)env * io.n_geoms + td.geom) * 3;
+	double tw[3];
+	taxel_world(td, R, xp, taxel, tw);
+	const double tsq = tw[0] * tw[0] + tw[1] * tw[1] + tw[2] * tw[2];
+	const double margin = td.include_margin, margin_sq = margin * margin, res = td.sample_resolution;
+	const double *samp = td.samples + (size_t)env * td.max_samples * 4;
+	double pressure = 0, dmin = 1e300, pmin = 0;
+	int ws = 0, kmin = 0x7fffffff;
+	for (int k = lane; k < m; k += 32) {
+		const double *p = samp + 4 * (size_t)k;
+		double dj = (-2 * (tw[0] * p[0] + tw[1] * p[1] + tw[2] * p[2]) + tsq) + (p[0] * p[0] + p[1] * p[1] + p[2] * p[2]);
+		double pj = p[3];
+		if (td.method == 0) {
+			if (dj < dmin)
+				dmin = dj, pmin = pj, kmin = k;
+		} else if (dj < margin_sq) {
+			double w = fmax(0.0, margin - sqrt(dj));
+			pressure += (w * w) * fabs(pj);
+			ws += 1;
+		}
+	}
+	if (td.method == 0) {
+#pragma unroll
+		for (int o = 16; o > 0; o >>= 1) {
+			double d2 = __shfl_xor_sync(0xffffffffu, dmin, o), p2 = __shfl_xor_sync(0xffffffffu, pmin, o);
+			int k2 = __shfl_xor_sync(0xffffffffu, kmin, o);
+			if (d2 < dmin || (d2 == dmin && k2 < kmin))
+				dmin = d2, pmin = p2, kmin = k2;
+		}
+		if (lane == 0 && dmin < margin_sq)
+			*out = (td.visualize && fabs(pmin) > 1e-6) ? (float)pmin : 0.0f; // :312-328
+		return;
+	}
+#pragma unroll
+	for (int o = 16; o > 0; o >>= 1) {
+		pressure += __shfl_xor_sync(0xffffffffu, pressure, o);
+		ws += __shfl_xor_sync(0xffffffffu, ws, o);
+	}
+	if (lane == 0 && ws > 0)
+		*out = (float)(pressure * res); // :409-412
+}
+
+static int launch_taxel_area_importance(const TaxelDev &td, const StepIO &io, const PairDesc *d_pairs, cudaStream_t s)
+{
+	const int n_tiles = (io.n_env + SCAN_TILE - 1) / SCAN_TILE;
+	const int tgrid   = (int)std::max<long>(1, std::min<long>(((long)io.max_tris + 255) / 256, (long)io.n_sms * 8));
+	const size_t smem = (size_t)TAXEL_AI_CAP * (sizeof(unsigned long long) + sizeof(double) + sizeof(int));
+	static bool attr_set = false;
+	if (!attr_set) {
+		cudaFuncSetAttribute(taxel_ai_sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+		attr_set = true;
+	}
+	cudaMemsetAsync(td.env_tris, 0, (size_t)io.n_env * sizeof(int32_t), s);
+	cudaMemsetAsync(td.env_cursor, 0, (size_t)io.n_env * sizeof(int32_t), s);
+	taxel_ai_list_kernel<false><<<tgrid, 256, 0, s>>>(td, io, d_pairs);
+	scan_tiles_kernel<<<n_tiles, 256, 0, s>>>(td.env_tris, td.env_offset, td.scan_tmp, io.n_env);
+	scan_sums_kernel<<<1, 1024, 0, s>>>(td.scan_tmp, n_tiles, td.env_offset + io.n_env);
+	scan_add_kernel<<<n_tiles, 256, 0, s>>>(td.env_offset, td.scan_tmp, io.n_env);
+	taxel_ai_list_kernel<true><<<tgrid, 256, 0, s>>>(td, io, d_pairs);
+	taxel_ai_sample_kernel<<<io.n_env, 256, smem, s>>>(td, io);
+	taxel_ai_gather_kernel<<<(io.n_env * td.n_taxels + 3) / 4, 128, 0, s>>>(td, io);
+	return 7;
+}
+
 int launch_taxel(const TaxelDev &td, const StepIO &io, const PairDesc *d_pairs, cudaStream_t s)
 {
+	if (td.sample_method == 1) {
+		if (io.n_env * td.n_taxels <= 0 || io.max_tris <= 0 || !io.tri_vd || !io.tri_elem)
+			return 0;
+		return launch_taxel_area_importance(td, io, d_pairs, s);
+	}
 	const int ncell = io.n_env * td.n_taxels;
 	if (ncell <= 0)
 		return 0;

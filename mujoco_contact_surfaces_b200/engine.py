@@ -73,7 +73,7 @@ def load_library():
             getattr(L, name).restype = C.c_void_p
         L.hcs_device_taxel_values.argtypes = [C.c_void_p, C.c_int]
         L.hcs_add_taxel_sensor.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_double, C.c_double, C.c_int,
-                                           C.c_int]
+                                           C.c_int, C.c_int]
         L.hcs_device_curved_values.argtypes = [C.c_void_p, C.c_int]
         L.hcs_add_curved_sensor.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p,
                                             C.c_void_p, C.c_double]
@@ -228,12 +228,14 @@ class HydroelasticEngine:
         self.curved.append(len(tp))
         return s
 
-    def add_taxel_sensor(self, geom, taxel_pos, include_margin, sample_resolution, method="squared", visualize=False):
-        """TaxelSensor (sample_method "default"); method: closest | weighted | mean | squared."""
+    def add_taxel_sensor(self, geom, taxel_pos, include_margin, sample_resolution, method="squared", visualize=False,
+                         sample_method="default"):
+        """TaxelSensor; method: closest | weighted | mean | squared; sample_method: default | area_importance."""
         tp = _f64(taxel_pos).reshape(-1, 3)
         code = {"closest": 0, "weighted": 1, "mean": 2, "squared": 3}[method]
+        sm = {"default": 0, "area_importance": 1}[sample_method]
         s = self._check(self.L.hcs_add_taxel_sensor(self.h, int(geom), len(tp), tp.ctypes.data, float(include_margin),
-                                                    float(sample_resolution), code, int(visualize)))
+                                                    float(sample_resolution), code, int(visualize), sm))
         if not hasattr(self, "taxel"):
             self.taxel = []
         self.taxel.append(len(tp))

@@ -672,10 +672,17 @@ bool TaxelSensor::load(const mjModel *m, mjData *d)
 		return false;
 	include_margin    = std::atof(c.at("include_margin").c_str());
 	sample_resolution = std::atof(c.at("sample_resolution").c_str());
-	if (has(c, "sample_method") && c.at("sample_method") != "default") {
-		std::fprintf(stderr, "[mujoco_contact_surface_sensors] TaxelSensor '%s': sample_method '%s' is not offered "
-		                     "(only 'default')\n", sensorName.c_str(), c.at("sample_method").c_str());
-		return false;
+	int sample_method = 0; // taxel_sensor.cpp:54-67
+	if (has(c, "sample_method")) {
+		const std::string &sm = c.at("sample_method");
+		if (sm == "default")
+			sample_method = 0;
+		else if (sm == "area_importance")
+			sample_method = 1;
+		else {
+			std::fprintf(stderr, "[mujoco_contact_surface_sensors] Could not find any match for sample_method: %s\n", sm.c_str());
+			return false;
+		}
 	}
 	const std::string &ms = c.at("method");
 	int method = ms == "closest" ? 0 : ms == "weighted" ? 1 : ms == "mean" ? 2 : ms == "squared" ? 3 : -1;
@@ -688,7 +695,7 @@ bool TaxelSensor::load(const mjModel *m, mjData *d)
 	if (cfg_idx < 0)
 		return false;
 	sensor_index_ = hcs_add_taxel_sensor(owner_->context(), cfg_idx, (int)taxel_pos_.size() / 3, taxel_pos_.data(),
-	                                     include_margin, sample_resolution, method, visualize ? 1 : 0);
+	                                     include_margin, sample_resolution, method, visualize ? 1 : 0, sample_method);
 	if (sensor_index_ < 0) {
 		std::fprintf(stderr, "[mujoco_contact_surface_sensors] %s\n", hcs_last_error(owner_->context()));
 		return false;

@@ -68,7 +68,7 @@ def configure(target, scene):
             target.add_flat_sensor(ids[s["geom"]], **kw)
     for s in getattr(scene, "taxel_sensors", []):
         target.add_taxel_sensor(ids[s["geom"]], s["taxel_pos"], s["include_margin"], s["sample_resolution"],
-                                s.get("method", "squared"), s.get("visualize", False))
+                                s.get("method", "squared"), s.get("visualize", False), s.get("sample_method", "default"))
     for s in getattr(scene, "curved_sensors", []):
         target.add_curved_sensor(ids[s["geom"]], s["taxel_pos"], s.get("taxel_nrm"), s["sample_pos"], s["sample_nrm"],
                                  s["include_margin"])
@@ -355,15 +355,16 @@ def surface_samples(verts, faces, n, seed=42):
     return pts, nrm[pick] / (2 * area[pick])[:, None]
 
 
-def myrmex_taxels(presser="box", method="weighted", visualize=False):
+def myrmex_taxels(presser="box", method="weighted", visualize=False, sample_method="default", sample_resolution=0.01):
     """SENS/config/flat_taxel_sensor.yaml: the Myrmex foam read by a TaxelSensor with a 16 x 16 taxel lattice on the
     foam's top face (include_margin = half the taxel pitch, sample_resolution 0.01)."""
     sc = myrmex(presser, sampling_resolution=4)
     sc.name = "taxel_myrmex_" + presser
     g = np.linspace(-0.19, 0.19, 16)
     taxels = np.array([[x, y, 0.02] for x in g for y in g])
-    sc.taxel_sensors = [dict(geom=1, taxel_pos=taxels, include_margin=0.01266666666666666, sample_resolution=0.01,
-                             method=method, visualize=visualize)]
+    sc.taxel_sensors = [dict(geom=1, taxel_pos=taxels, include_margin=0.01266666666666666,
+                             sample_resolution=sample_resolution, method=method, visualize=visualize,
+                             sample_method=sample_method)]
     return sc
 
 

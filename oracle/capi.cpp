@@ -412,12 +412,12 @@ int orc_curved_info(void *h, int sensor, int *n_close_n_assign)
 
 // taxel_sensor.cpp:45-156 (load) and :158-478
 int orc_add_taxel_sensor(void *h, int geom, int n_taxels, const double *taxel_pos, double include_margin,
-                         double sample_resolution, int method, int visualize)
+                         double sample_resolution, int method, int visualize, int sample_method)
 {
 	Scene &sc = *(Scene *)h;
 	TaxelSensor ts;
 	ts.geom = geom, ts.include_margin = include_margin, ts.sample_resolution = sample_resolution;
-	ts.method = method, ts.visualize = visualize != 0;
+	ts.method = method, ts.visualize = visualize != 0, ts.sample_method = sample_method;
 	for (int i = 0; i < n_taxels; ++i)
 		ts.taxels.push_back({ taxel_pos[3 * i], taxel_pos[3 * i + 1], taxel_pos[3 * i + 2] });
 	sc.taxel.push_back(ts);

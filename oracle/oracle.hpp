@@ -210,6 +210,7 @@ struct TaxelSensor {
 	double include_margin, sample_resolution;
 	int method;      // 0 closest, 1 weighted, 2 mean, 3 squared (:79-91)
 	bool visualize;  // changes the VALUE of the closest method (:312-328), quirk Q12
+	int sample_method = 0; // 0 DEFAULT (barycentric lattice, :174-209), 1 AREA_IMPORTANCE (:211-254)
 	std::vector<V3> taxels; // geom frame
 };
 

@@ -147,12 +147,14 @@ class OracleScene:
         self.L.orc_curved_info(self.h, int(sensor), _p(d, C.c_int))
         return int(d[0]), int(d[1])  # close sample points, (taxel, sample) assignments
 
-    def add_taxel_sensor(self, geom, taxel_pos, include_margin, sample_resolution, method="squared", visualize=False):
-        """TaxelSensor::load (sample_method "default"); method: closest | weighted | mean | squared."""
+    def add_taxel_sensor(self, geom, taxel_pos, include_margin, sample_resolution, method="squared", visualize=False,
+                         sample_method="default"):
+        """TaxelSensor::load; method: closest | weighted | mean | squared; sample_method: default | area_importance."""
         tp = _d(taxel_pos).reshape(-1, 3)
         code = {"closest": 0, "weighted": 1, "mean": 2, "squared": 3}[method]
+        sm = {"default": 0, "area_importance": 1}[sample_method]
         s = self.L.orc_add_taxel_sensor(self.h, int(geom), len(tp), _p(tp, C.c_double), C.c_double(include_margin),
-                                        C.c_double(sample_resolution), code, int(visualize))
+                                        C.c_double(sample_resolution), code, int(visualize), sm)
         if not hasattr(self, "taxel_counts"):
             self.taxel_counts = []
         self.taxel_counts.append(len(tp))

@@ -8,6 +8,9 @@
 // evaluated alias-safe (the mathematically intended rotation).
 #include "oracle.hpp"
 
+#include <array>
+#include <random>
+
 #include <algorithm>
 #include <cstring>
 
@@ -562,7 +565,58 @@ void taxel_sensor_values(const Scene &sc, const StepState &st, int sensor, float
 	const double margin = ts.include_margin, margin_sq = margin * margin, res = ts.sample_resolution;
 	std::vector<V3> spoints;
 	std::vector<double> spress; // s->tri_e_MN().Evaluate(t, bary) of each sample
+	// AREA_IMPORTANCE (taxel_sensor.cpp:211-254): ONE std::default_random_engine per update (default seed, so every
+	// update draws the same stream), one stratum of sample_resolution * total_area per sample along the cumulative
+	// triangle area, uniform barycentric point inside the triangle that owns the stratum's start.  Which random numbers
+	// a triangle gets depends on the triangle ORDER, and Drake's is unobservable; the order here is canonical: pairs in
+	// pair order, polygons by (elemM, elemN), fan triangles in fan order, and area(t) = |(b - a) x (c - a)| / 2 of the
+	// WORLD vertices (Drake computes it in the builder frame: ulps), total_area their sum in that order.
+	std::default_random_engine generator;
+	std::uniform_real_distribution<double> distribution(0.0, 1.0);
 	for (const PairOut &po : st.out) {
+		if (ts.sample_method != 1)
+			break;
+		if (!(po.has_surface && (po.gM == id || po.gN == id) && po.s->tri))
+			continue;
+		const Surface &s = *po.s;
+		std::vector<std::array<int, 4>> polys; // (elemM, elemN, first fan triangle, fan size)
+		for (const Emitted &em : s.emitted)
+			polys.push_back({ em.elemM, em.elemN, em.first_face, em.n_faces });
+		std::sort(polys.begin(), polys.end());
+		std::vector<int> order;
+		for (const auto &pl : polys)
+			for (int i = 0; i < pl[3]; ++i)
+				order.push_back(pl[2] + i);
+		auto tri_area = [&](int t) {
+			const int *f = &s.face_idx[s.face_first[t]];
+			return 0.5 * norm(cross(s.v[f[1]] - s.v[f[0]], s.v[f[2]] - s.v[f[0]]));
+		};
+		double total = 0;
+		for (int t : order)
+			total += tri_area(t);
+		const double area_resolution = res * total;
+		if (!(area_resolution > 0))
+			continue;
+		double area = 0, at = 0;
+		for (int t : order) {
+			const int *f = &s.face_idx[s.face_first[t]];
+			at += tri_area(t);
+			while (area < at) {
+				area += area_resolution;
+				double u0 = distribution(generator), u1 = distribution(generator);
+				double a = 1.0 - std::sqrt(u0), b = (1.0 - a) * u1;
+				double bary[3] = { a, (1 - a) * (1 - b), (1 - a) * b };
+				V3 p;
+				for (int k = 0; k < 3; ++k)
+					p.at(k) = bary[0] * s.v[f[0]][k] + bary[1] * s.v[f[1]][k] + bary[2] * s.v[f[2]][k];
+				spoints.push_back(p);
+				spress.push_back(bary[0] * s.e[f[0]] + bary[1] * s.e[f[1]] + bary[2] * s.e[f[2]]);
+			}
+		}
+	}
+	for (const PairOut &po : st.out) {
+		if (ts.sample_method != 0)
+			break;
 		if (!(po.has_surface && (po.gM == id || po.gN == id) && po.s->tri))
 			continue;
 		const Surface &s = *po.s;

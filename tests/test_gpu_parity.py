@@ -161,12 +161,17 @@ def test_curved_fingertip_sensor(hcs_lib, with_normals):
     eng.close()
 
 
-@pytest.mark.parametrize("presser,method,visualize", [("box", "weighted", False), ("spot", "squared", False),
-                                                      ("box", "closest", True), ("box", "closest", False)])
-def test_taxel_sensor_on_the_myrmex_foam(hcs_lib, presser, method, visualize):
+@pytest.mark.parametrize("presser,method,visualize,sample_method",
+                         [("box", "weighted", False, "default"), ("spot", "squared", False, "default"),
+                          ("box", "closest", True, "default"), ("box", "closest", False, "default"),
+                          ("box", "squared", False, "area_importance"), ("spot", "squared", False, "area_importance"),
+                          ("soft_tip", "closest", True, "area_importance")])
+def test_taxel_sensor_on_the_myrmex_foam(hcs_lib, presser, method, visualize, sample_method):
     """TaxelSensor (flat_taxel_sensor.yaml lattice): two consecutive updates with different poses, so that taxels
-    that lose their samples keep the previous value like the reference's message buffer does."""
-    scene = scenes.myrmex_taxels(presser, method, visualize)
+    that lose their samples keep the previous value like the reference's message buffer does.  area_importance: the
+    stratified random sampling of taxel_sensor.cpp:211-254 (soft_tip: a soft-soft surface, M/N swapped windings)."""
+    scene = scenes.myrmex_taxels(presser, method, visualize, sample_method,
+                                 0.002 if sample_method == "area_importance" else 0.01)
     n_envs = 6
     eng, orc = make_engine(scene, n_envs), make_oracle(scene)
     prev = np.zeros((n_envs, 256), dtype=np.float32)
@@ -186,11 +191,13 @@ def test_taxel_sensor_on_the_myrmex_foam(hcs_lib, presser, method, visualize):
     eng.close()
 
 
-def test_taxel_sensor_on_the_fingertip(hcs_lib):
-    """SENS/config/fingertip.yaml taxels on the soft ubi_tip mesh (method squared), next to the curved sensor."""
+@pytest.mark.parametrize("sample_method", ["default", "area_importance"])
+def test_taxel_sensor_on_the_fingertip(hcs_lib, sample_method):
+    """SENS/config/fingertip.yaml on the soft ubi_tip mesh: its taxels, method squared, sample_resolution 0.001 and (second
+    case) its sample_method area_importance, next to the curved sensor."""
     scene = scenes.fingertip()
     scene.taxel_sensors = [dict(geom=1, taxel_pos=scenes._TIP_TAXELS, include_margin=0.006, sample_resolution=0.001,
-                                method="squared")]
+                                method="squared", sample_method=sample_method)]
     n_envs = 8
     eng, orc = make_engine(scene, n_envs), make_oracle(scene)
     xpos, xmat, vel = scene.poses(n_envs, seed=10)

@@ -496,3 +496,76 @@ def test_taxel_sensor_methods_and_their_quirks():
     # no sample at all: zeros
     s.step(np.array([[0, 0, 0.5], [0, 0, 0.033]]), np.stack([I3, I3]))
     assert not s.taxel_values(ids["squared"], previous=prev).any()
+
+
+def _minstd_canonical(state):
+    """std::generate_canonical<double, 53>(std::minstd_rand0) as libstdc++ evaluates it (two 31-bit draws per double);
+    independent of the oracle, which calls the C++ standard library itself."""
+    r = 2147483646.0
+    state = (16807 * state) % 2147483647
+    s = float(state - 1)
+    state = (16807 * state) % 2147483647
+    s += float(state - 1) * r
+    u = s / (r * r)
+    return (np.nextafter(1.0, 0.0) if u >= 1.0 else u), state
+
+
+def _area_importance_reference(tris, emitted, taxel_w, margin, res, previous):
+    """taxel_sensor.cpp:211-254 + the squared method, in numpy: triangles in the canonical order (polygons by
+    (elemM, elemN), fan triangles in fan order), strata of res * total_area, one minstd_rand0 stream."""
+    order, first = [], 0
+    firsts = []
+    for em in emitted:
+        firsts.append(first)
+        first += int(em[2])
+    for q in sorted(range(len(emitted)), key=lambda q: (int(emitted[q][0]), int(emitted[q][1]))):
+        order += list(range(firsts[q], firsts[q] + int(emitted[q][2])))
+    area_of = lambda t: 0.5 * np.linalg.norm(np.cross(t[3:6] - t[0:3], t[6:9] - t[0:3]))
+    total = 0.0
+    for i in order:
+        total += area_of(tris[i])
+    step, acc, at, state = res * total, 0.0, 0.0, 1
+    pts, prs = [], []
+    for i in order:
+        t = tris[i]
+        at += area_of(t)
+        while acc < at:
+            acc += step
+            u0, state = _minstd_canonical(state)
+            u1, state = _minstd_canonical(state)
+            a = 1.0 - np.sqrt(u0)
+            b = (1.0 - a) * u1
+            bary = np.array([a, (1 - a) * (1 - b), (1 - a) * b])
+            pts.append(bary[0] * t[0:3] + bary[1] * t[3:6] + bary[2] * t[6:9])
+            prs.append(bary @ t[9:12])
+    pts, prs = np.array(pts), np.array(prs)
+    d2 = ((pts - taxel_w) ** 2).sum(1)
+    sel = d2 < margin ** 2
+    if not sel.any():
+        return previous, len(pts)
+    return res * (((margin - np.sqrt(d2[sel])) ** 2) * np.abs(prs[sel])).sum(), len(pts)
+
+
+def test_taxel_sensor_area_importance_sampling():
+    """sample_method "area_importance" (the one the reference's fingertip.yaml uses): oracle (std::default_random_engine)
+    against an independent numpy restatement with its own minstd_rand0 / generate_canonical."""
+    s = OracleScene(triangle_representation=True)
+    box = s.add_geom(GEOM_BOX, [0.1, 0.1, 0.1], [0, 1, 0.05, 0.3, 0.3])
+    foam = s.add_geom(GEOM_BOX, [0.2, 0.2, 0.02], [5e4, 5, 0, 0.3, 0.3])
+    s.set_pairs([[box, foam]])
+    taxels = np.array([[0.013, 0.007, 0.02], [0.09, -0.05, 0.02], [0.19, 0.19, 0.02]])
+    margin, res = 0.0126, 0.002
+    sid = s.add_taxel_sensor(foam, taxels, margin, res, "squared", False, "area_importance")
+    R = np.array([[np.cos(0.3), -np.sin(0.3), 0], [np.sin(0.3), np.cos(0.3), 0], [0, 0, 1]])
+    s.step(np.array([[0.01, 0.02, 0.053 - 0.002 + 0.1], [0, 0, 0.033]]), np.stack([R.reshape(-1), I3]))
+    tris, emitted = s.pair_triangles(0), s.pair_emitted(0)
+    assert len(tris) == emitted[:, 2].sum() > 10
+    prev = np.array([7.0, 8.0, 9.0], dtype=np.float32)
+    out = s.taxel_values(sid, previous=prev)
+    world = taxels + [0, 0, 0.033]
+    ref = [_area_importance_reference(tris, emitted, world[i], margin, res, float(prev[i])) for i in range(3)]
+    assert 500 <= ref[0][1] <= 502  # one sample per stratum of res * total_area
+    assert np.allclose(out, [r[0] for r in ref], rtol=1e-6), (out, ref)
+    assert out[2] == 9.0 and out[0] > 0
+    # the generator restarts every update: the same contact gives the same message
+    assert np.array_equal(out, s.taxel_values(sid, previous=prev))
