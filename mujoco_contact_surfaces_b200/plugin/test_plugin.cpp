@@ -307,10 +307,68 @@ static int scenario_curved_tip()
 	return 0;
 }
 
+// TaxelSensor with the keys of SENS/config/fingertip.yaml (method squared, sample_method area_importance, sample_resolution
+// 0.001, include_margin 0.006) on the same small soft tip
+static int scenario_taxel_tip()
+{
+	ShimWorld w;
+	const double zero[3] = { 0, 0, 0 };
+	std::vector<float> mv = { 0.008f, 0, 0, -0.008f, 0, 0, 0, 0.006f, 0, 0, -0.006f, 0, 0, 0, 0.010f, 0, 0, -0.010f };
+	std::vector<int> mf   = { 0, 2, 4, 2, 1, 4, 1, 3, 4, 3, 0, 4, 2, 0, 5, 1, 2, 5, 3, 1, 5, 0, 3, 5 };
+	double box_pos[3] = { 0, 0, 0.025 };
+	double R[9];
+	rot_zyx(-0.4, 0.2, 0.15, R);
+	double low = 0;
+	for (size_t v = 0; v < mv.size() / 3; ++v)
+		low = std::fmin(low, R[6] * mv[3 * v] + R[7] * mv[3 * v + 1] + R[8] * mv[3 * v + 2]);
+	double tip_pos[3] = { -0.002, 0.005, 0.05 - 0.002 - low };
+	int b0 = w.add_body(false, zero), b1 = w.add_body(true, tip_pos);
+	double s_box[3] = { 0.025, 0.025, 0.025 };
+	int did = w.add_mesh(mv, mf);
+	w.add_geom("box_geom", mjGEOM_BOX, b0, s_box, box_pos, I3);
+	w.add_geom("fingertip_geom", mjGEOM_MESH, b1, zero, tip_pos, R, did);
+	w.add_text("cs::HydroelasticContactRepresentation", "kTriangle");
+	w.add_numeric("cs::box_geom", { 0, 1.0, 0.01, 0.0, 0.0 });
+	w.add_numeric("cs::fingertip_geom", { 5e4, 5.0, 0.0, 0.0, 0.0 });
+	w.finish();
+
+	MujocoContactSurfacesPlugin plugin;
+	auto sensor = std::make_shared<sensors::TaxelSensor>();
+	PluginConfig cfg = { { "type", "mujoco_contact_surface_sensors/TaxelSensor" }, { "sensorName", "myrmex_fingertip" },
+		                 { "geomName", "fingertip_geom" }, { "topicName", "/myrmex_fingertip" }, { "updateRate", "4.0" },
+		                 { "include_margin", "0.006" }, { "method", "squared" }, { "sample_method", "area_importance" },
+		                 { "sample_resolution", "0.001" },
+		                 { "taxels", "[[0.002, 0.0015, -0.005], [-0.002, 0.0015, -0.005], [0.002, -0.0015, -0.005], "
+		                             "[-0.002, -0.0015, -0.005], [0, 0, 0.010]]" } };
+	plugin.addSurfacePlugin(sensor, cfg);
+	if (!plugin.load(&w.m, &w.d)) {
+		std::printf("{\"scenario\": \"taxel_tip\", \"error\": \"load failed\"}\n");
+		return 1;
+	}
+	for (int step = 0; step < 3; ++step) {
+		std::fill(w.qfrc.begin(), w.qfrc.end(), 0.0);
+		w.collision_pass();
+		plugin.passiveCallback(&w.m, &w.d);
+		w.d.time += 0.001;
+	}
+	std::printf("{\"scenario\": \"taxel_tip\", ");
+	print_vec("tip_pos", tip_pos, 3);
+	print_vec("tip_mat", R, 9);
+	std::vector<double> mvd(mv.begin(), mv.end()), mfd(mf.begin(), mf.end());
+	print_vec("mesh_vert", mvd.data(), (int)mvd.size());
+	print_vec("mesh_face", mfd.data(), (int)mfd.size());
+	std::printf("\"publishes\": %d, ", sensor->publishCount());
+	std::vector<double> vals(sensor->lastMessage().begin(), sensor->lastMessage().end());
+	print_vec("values", vals.data(), (int)vals.size(), true);
+	std::printf("}\n");
+	return 0;
+}
+
 int main()
 {
 	int rc = scenario_sphere_on_box();
 	rc |= scenario_myrmex();
 	rc |= scenario_curved_tip();
+	rc |= scenario_taxel_tip();
 	return rc;
 }

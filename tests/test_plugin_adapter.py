@@ -112,3 +112,27 @@ def test_adapter_curved_sensor_matches_the_oracle(plugin_built):
     assert r["publishes"] == 1 and ref.max() > 0 and ref[4] == 0  # the taxel on the far side feels nothing
     err = np.abs(val - ref) / np.maximum(np.abs(ref), 1e-3 * ref.max())
     assert err.max() < 1e-6
+
+
+@pytest.mark.gpu
+def test_adapter_taxel_sensor_with_the_fingertip_yaml_keys(plugin_built):
+    """TaxelSensor adapter class configured like SENS/config/fingertip.yaml (method squared, sample_method
+    area_importance): the published values equal the oracle's."""
+    r = _run(plugin_built)["taxel_tip"]
+    I3 = np.eye(3).reshape(-1)
+    o = OracleScene(triangle_representation=True)
+    box = o.add_geom(GEOM_BOX, [0.025] * 3, [0, 1.0, 0.01, 0.0, 0.0])
+    mv = np.array(r["mesh_vert"], dtype=np.float32).reshape(-1, 3)
+    mf = np.array(r["mesh_face"], dtype=np.int32).reshape(-1, 3)
+    tip = o.add_geom(7, [0, 0, 0], [5e4, 5.0, 0.0, 0.0, 0.0], mv, mf)
+    o.set_pairs([[box, tip]])
+    taxels = np.array([[0.002, 0.0015, -0.005], [-0.002, 0.0015, -0.005], [0.002, -0.0015, -0.005],
+                       [-0.002, -0.0015, -0.005], [0, 0, 0.010]])
+    ts = o.add_taxel_sensor(tip, taxels, 0.006, 0.001, "squared", False, "area_importance")
+    o.step(np.array([[0, 0, 0.025], r["tip_pos"]]), np.stack([I3, np.array(r["tip_mat"])]))
+    assert o.pair_result(0)["n_polygons"] > 0
+    ref = o.taxel_values(ts)
+    val = np.array(r["values"], dtype=np.float32)
+    assert r["publishes"] == 1 and ref.max() > 0
+    err = np.abs(val - ref) / np.maximum(np.abs(ref), 1e-3 * ref.max())
+    assert err.max() < 1e-6
