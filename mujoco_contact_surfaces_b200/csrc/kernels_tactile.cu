@@ -1034,11 +1034,8 @@ static int launch_taxel_area_importance(const TaxelDev &td, const StepIO &io, co
 	const int n_tiles = (io.n_env + SCAN_TILE - 1) / SCAN_TILE;
 	const int tgrid   = (int)std::max<long>(1, std::min<long>(((long)io.max_tris + 255) / 256, (long)io.n_sms * 8));
 	const size_t smem = (size_t)TAXEL_AI_CAP * (sizeof(unsigned long long) + sizeof(double) + sizeof(int));
-	static bool attr_set = false;
-	if (!attr_set) {
-		cudaFuncSetAttribute(taxel_ai_sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-		attr_set = true;
-	}
+	// opt in to > 48 KB dynamic shared memory (idempotent and cheap; contexts may live on several devices)
+	cudaFuncSetAttribute(taxel_ai_sample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 	cudaMemsetAsync(td.env_tris, 0, (size_t)io.n_env * sizeof(int32_t), s);
 	cudaMemsetAsync(td.env_cursor, 0, (size_t)io.n_env * sizeof(int32_t), s);
 	taxel_ai_list_kernel<false><<<tgrid, 256, 0, s>>>(td, io, d_pairs);
