@@ -426,7 +426,12 @@ bool TactileSensorBase::load(const mjModel *m, mjData *)
 	updateRate   = std::atof(c.at("updateRate").c_str());
 	updatePeriod = 1.0 / updateRate;
 	if (has(c, "visualize"))
-		visualize = c.at("visualize") == "true" || c.at("visualize") == "1";
+	{ // YAML booleans as the reference's configs write them (fingertip.yaml: "visualize: True")
+		std::string v = c.at("visualize");
+		for (char &ch : v)
+			ch = (char)std::tolower((unsigned char)ch);
+		visualize = v == "true" || v == "1" || v == "yes" || v == "on";
+	}
 	return true;
 }
 
@@ -701,17 +706,40 @@ bool TaxelSensor::load(const mjModel *m, mjData *d)
 		return false;
 	}
 	tactile_state_values_.assign(taxel_pos_.size() / 3, 0.0f);
+	if (has(c, "visualize_max_pressure"))
+		max_pressure = std::atof(c.at("visualize_max_pressure").c_str());
+	if (visualize)
+		vGeoms = new mjvGeom[taxel_pos_.size() / 3 + 1];
 	return true;
 }
 
 // taxel_sensor.cpp:158-478, computed on the GPU by the taxel-sensor kernels
-void TaxelSensor::internal_update(const mjModel *, mjData *, const std::vector<GeomCollisionPtr> &)
+void TaxelSensor::internal_update(const mjModel *, mjData *d, const std::vector<GeomCollisionPtr> &)
 {
-	if (!owner_->finalized()) { // no contact pair seen yet: zeros (:455-477)
+	if (!owner_->finalized()) // no contact pair seen yet: zeros (:455-477)
 		std::fill(tactile_state_values_.begin(), tactile_state_values_.end(), 0.0f);
-		return;
+	else
+		hcs_get_taxel_values(owner_->context(), sensor_index_, tactile_state_values_.data());
+	if (visualize && vGeoms) {
+		// one sphere per taxel at its world position, colour and size by pressure / visualize_max_pressure
+		// (:447-455 and the same block in every method; without samples: blue spheres of 0.5 mm, :470-476, which is what
+		// scale 0 gives).  The 0.1 mm markers of the in-range sample points (:397-402) stay on the GPU and are not drawn.
+		const int id = geomID;
+		const mjtNum *R = d->geom_xmat + 9 * id, *xp = d->geom_xpos + 3 * id;
+		const int n = (int)taxel_pos_.size() / 3;
+		for (int i = 0; i < n; ++i) {
+			const double *t = &taxel_pos_[3 * (size_t)i];
+			mjtNum pos[3];
+			for (int r = 0; r < 3; ++r)
+				pos[r] = R[3 * r] * t[0] + R[3 * r + 1] * t[1] + R[3 * r + 2] * t[2] + xp[r];
+			const double pressure = tactile_state_values_[i];
+			const float scale     = (float)(std::min(std::max(pressure, 0.0), max_pressure) / max_pressure);
+			const float color[4]  = { scale, 0, 1.0f - scale, 1 };
+			const mjtNum sz       = 0.0005 + scale * 0.002;
+			const mjtNum size[3]  = { sz, sz, sz };
+			mjv_initGeom(vGeoms + n_vGeom++, mjGEOM_SPHERE, size, pos, nullptr, color);
+		}
 	}
-	hcs_get_taxel_values(owner_->context(), sensor_index_, tactile_state_values_.data());
 }
 
 } // namespace sensors

@@ -285,6 +285,7 @@ private:
 	int sensor_index_        = -1;
 	double include_margin    = 0;
 	double sample_resolution = 0;
+	double max_pressure      = 0.04; // visualize_max_pressure (taxel_sensor.h:84, taxel_sensor.cpp:70-72)
 	std::vector<double> taxel_pos_;
 };
 

@@ -337,7 +337,7 @@ static int scenario_taxel_tip()
 	PluginConfig cfg = { { "type", "mujoco_contact_surface_sensors/TaxelSensor" }, { "sensorName", "myrmex_fingertip" },
 		                 { "geomName", "fingertip_geom" }, { "topicName", "/myrmex_fingertip" }, { "updateRate", "4.0" },
 		                 { "include_margin", "0.006" }, { "method", "squared" }, { "sample_method", "area_importance" },
-		                 { "sample_resolution", "0.001" },
+		                 { "sample_resolution", "0.001" }, { "visualize", "True" }, { "visualize_max_pressure", "0.04" },
 		                 { "taxels", "[[0.002, 0.0015, -0.005], [-0.002, 0.0015, -0.005], [0.002, -0.0015, -0.005], "
 		                             "[-0.002, -0.0015, -0.005], [0, 0, 0.010]]" } };
 	plugin.addSurfacePlugin(sensor, cfg);
@@ -351,7 +351,17 @@ static int scenario_taxel_tip()
 		plugin.passiveCallback(&w.m, &w.d);
 		w.d.time += 0.001;
 	}
-	std::printf("{\"scenario\": \"taxel_tip\", ");
+	static mjvGeom scene_geoms[64];
+	mjvScene scene{ 64, 0, scene_geoms };
+	plugin.renderCallback(&w.m, &w.d, &scene);
+	int n_spheres = 0;
+	double max_size = 0;
+	for (int i = 0; i < scene.ngeom; ++i)
+		if (scene.geoms[i].type == mjGEOM_SPHERE) {
+			++n_spheres;
+			max_size = std::fmax(max_size, scene.geoms[i].size[0]);
+		}
+	std::printf("{\"scenario\": \"taxel_tip\", \"taxel_markers\": %d, \"max_marker_size\": %.9g, ", n_spheres, max_size);
 	print_vec("tip_pos", tip_pos, 3);
 	print_vec("tip_mat", R, 9);
 	std::vector<double> mvd(mv.begin(), mv.end()), mfd(mf.begin(), mf.end());

@@ -136,3 +136,6 @@ def test_adapter_taxel_sensor_with_the_fingertip_yaml_keys(plugin_built):
     assert r["publishes"] == 1 and ref.max() > 0
     err = np.abs(val - ref) / np.maximum(np.abs(ref), 1e-3 * ref.max())
     assert err.max() < 1e-6
+    # visualize: one sphere per taxel, 0.5 mm .. 2.5 mm by pressure / visualize_max_pressure (taxel_sensor.cpp:447-455)
+    scale = min(max(float(ref.max()), 0.0), 0.04) / 0.04
+    assert r["taxel_markers"] == 5 and abs(r["max_marker_size"] - (0.0005 + scale * 0.002)) < 1e-7
