@@ -28,6 +28,9 @@ CASES = {
     "c3_soft_soft": (lambda: scenes.soft_soft(), 2, 3, False),
     "c3_soft_soft_triangle": (lambda: scenes.soft_soft(triangle=True), 2, 3, False),
     "c4_objects_on_plane": (lambda: scenes.objects_on_plane(), 4, 4096, False),
+    "c2b_myrmex_soft_tip_s4": (lambda: scenes.myrmex("soft_tip", 4), 2, 7, True),
+    # TaxelSensor with the reference's fingertip.yaml settings (sample_method area_importance) on the Myrmex foam
+    "taxel_area_importance": (lambda: scenes.myrmex_taxels("box", "squared", False, "area_importance", 0.002), 2, 31, False),
 }
 PAIR_FIELDS = ("has_surface", "F", "tau", "area", "centroid", "n_polygons", "n_faces", "n_points", "gM", "gN")
 
@@ -55,6 +58,10 @@ def run_case(name):
             emitted_off.append(emitted_off[-1] + len(rows))
         for s, img in enumerate(imgs):
             images[s].append(np.asarray(img, dtype=np.float32))
+        for s in range(len(getattr(scene, "taxel_sensors", []))):  # first update: the previous message is all zeros
+            out.setdefault("taxel%d" % s, []).append(orc.taxel_values(s))
+    for s in range(len(getattr(scene, "taxel_sensors", []))):
+        out["taxel%d" % s] = np.asarray(out["taxel%d" % s], dtype=np.float32)
     for f in PAIR_FIELDS:
         out["pair_" + f] = np.asarray(acc[f])
     out["geom_wrench"] = wrench

@@ -47,6 +47,10 @@ def test_oracle_and_scene_generators_reproduce_the_fixtures(golden, name):
                 assert rel_err(pairs[p][f], golden[name + "/pair_" + f][e, p], floor=1e-300) < 1e-12, (f, e, p)
         for s, img in enumerate(imgs):
             np.testing.assert_allclose(img, golden[name + "/image%d" % s][e], rtol=1e-6, atol=0)
+        for s in range(len(getattr(scene, "taxel_sensors", []))):
+            ref = golden[name + "/taxel%d" % s][e]
+            assert ref.max() > 0
+            np.testing.assert_allclose(orc.taxel_values(s), ref, rtol=1e-6, atol=1e-6 * ref.max())
 
 
 @pytest.mark.gpu
@@ -55,7 +59,8 @@ def test_golden_steps(hcs_lib, golden, name):
     factory, n_envs, seed, sensors = fixtures.CASES[name]
     scene = factory()
     eng = make_engine(scene, n_envs)
-    eng.step(golden[name + "/xpos"], golden[name + "/xmat"], golden[name + "/vel"], with_sensors=sensors)
+    n_taxel = len(getattr(scene, "taxel_sensors", []))
+    eng.step(golden[name + "/xpos"], golden[name + "/xmat"], golden[name + "/vel"], with_sensors=sensors or n_taxel > 0)
     res, wrench = eng.pair_results(), eng.geom_wrenches()
     n_pairs = len(scene.pairs)
     n_poly = 0
@@ -83,5 +88,8 @@ def test_golden_steps(hcs_lib, golden, name):
             for s in range(len(scene.sensors)):
                 err, nbad = compare_images(eng.sensor_image(s)[e], golden[name + "/image%d" % s][e])
                 assert nbad == 0, "taxel image: %d taxels off (max rel err %.3e)" % (nbad, err)
+        for s in range(n_taxel):
+            err, nbad = compare_images(eng.taxel_values(s)[e], golden[name + "/taxel%d" % s][e])
+            assert nbad == 0, "taxel sensor: %d taxels off (max rel err %.3e)" % (nbad, err)
     assert n_poly > 0
     eng.close()
