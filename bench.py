@@ -178,7 +178,34 @@ def run_reference(args, scene, with_sensors):
     print(json.dumps(line))
 
 
+def cpu_flat(mesh, resolution, sampling, seconds):
+    """CPU leg of benchmark_flat.py (the reference's benchmark_flat.cpp grid): ONE environment through the oracle,
+    contact surface + flat-sensor update, use_parallel off / on (OpenMP over the taxels, flat_tactile_sensor.cpp:316)."""
+    from mujoco_contact_surfaces_b200 import scenes as S
+    from oracle import oracle
+    scene = S.myrmex(mesh, sampling_resolution=sampling, resolution=resolution)
+    orc = oracle.OracleScene(True, scene.apply_forces)
+    S.configure(orc, scene)
+    xp, xm, ve = scene.poses(4, seed=7)
+    for mode, parallel in (("cpu_serial", False), ("cpu_parallel", True)):
+        t, n, ts = 0.0, 0, 0.0
+        while t < seconds and n < 100:
+            e = n % 4
+            t0 = time.perf_counter()
+            orc.step(xp[e], xm[e], ve[e])
+            t1 = time.perf_counter()
+            orc.sensor_image(0, use_bvh=True, parallel=parallel)
+            t2 = time.perf_counter()
+            t, ts, n = t + (t2 - t0), ts + (t2 - t1), n + 1
+        print(json.dumps(dict(impl=mode, n_envs=1, resolution=resolution, sampling_resolution=sampling, mesh=mesh,
+                              surface_ms=1e3 * (t - ts) / n, sensor_ms=1e3 * ts / n, total_ms=1e3 * t / n,
+                              ms_per_env=1e3 * t / n, nrays=0, ntri=len(orc.pair_triangles(0)))))
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "--cpu-flat":
+        cpu_flat(sys.argv[2], float(sys.argv[3]), int(sys.argv[4]), float(sys.argv[5]))
+        return
     args = parse()
     from mujoco_contact_surfaces_b200 import scenes as S
     scene = S.SCENES[args.workload]()
