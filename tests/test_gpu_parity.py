@@ -114,6 +114,15 @@ def test_c2_myrmex_taxel_image(hcs_lib, presser, S):
     _run_scene(scenes.myrmex(presser, sampling_resolution=S), 8, seed=7, hcs_lib=hcs_lib, with_sensors=True)
 
 
+@pytest.mark.parametrize("presser,resolution,S", [("box", 0.025, 32), ("spot", 0.025, 32), ("plate", 0.0025, 4),
+                                                  ("spot", 0.0025, 8)])
+def test_c2_benchmark_flat_grid_corners(hcs_lib, presser, resolution, S):
+    """The corners of the reference's own benchmark grid (benchmark_flat.cpp:282-373): 32 x 32 rays per taxel, and the
+    160 x 160 taxel image of resolution 0.0025."""
+    _run_scene(scenes.myrmex(presser, sampling_resolution=S, resolution=resolution), 2, seed=7, hcs_lib=hcs_lib,
+               with_sensors=True)
+
+
 @pytest.mark.parametrize("window,sigma", [(1, 0.1), (2, 0.3), (3, -1.0)])
 def test_c2_myrmex_windows(hcs_lib, window, sigma):
     _run_scene(scenes.myrmex("box", sampling_resolution=8, window=window, sigma=sigma), 4, seed=8, hcs_lib=hcs_lib,
