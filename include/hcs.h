@@ -131,6 +131,11 @@ int hcs_set_pairs(hcs_ctx *ctx, const int32_t *g1, const int32_t *g2, int n_pair
  * geom_size[0..2] of whatever geom carries the sensor, :192-197); returns the sensor index. */
 int hcs_add_flat_sensor(hcs_ctx *ctx, int geom, double resolution, int sampling_resolution, int window, float sigma);
 int hcs_sensor_dims(const hcs_ctx *ctx, int sensor, int *cx, int *cy);
+/* replaces the part of FlatTactileSensor::dynamicParamCallback (flat_tactile_sensor.cpp:48-125, the dynamic_reconfigure
+ * set of SENS/config/DynamicFlatTactile.cfg) that changes the computation: sampling_resolution, window, sigma (the
+ * resolution is fixed after load in the reference too, :66; update_rate / visualize / use_parallel are host-side
+ * state of the adapter).  The sensor's ray grid and window table are rebuilt; a finalized context stays finalized. */
+int hcs_update_flat_sensor(hcs_ctx *ctx, int sensor, int sampling_resolution, int window, float sigma);
 
 /* replaces CurvedSensor (SENS/src/curved_sensor.cpp): load() :111-380 and internal_update() :388-481.
  * taxel_pos / taxel_nrm: [n_taxels][3] in the sensor geom's frame (taxel_nrm may be NULL: no 45-degree test);

@@ -1141,6 +1141,29 @@ int hcs_add_flat_sensor(hcs_ctx *c, int geom, double resolution, int sampling_re
 	API_END(c)
 }
 
+int hcs_update_flat_sensor(hcs_ctx *c, int sensor, int sampling_resolution, int window, float sigma)
+{
+	API_BEGIN(c)
+	if (sensor < 0 || sensor >= (int)c->sensors.size() || sampling_resolution < 1 || sampling_resolution > 32 || window < 0 ||
+	    window > 3) {
+		c->err = "hcs_update_flat_sensor: needs a flat sensor index, 1 <= sampling_resolution <= 32, window in 0..3";
+		return HCS_E_INVALID;
+	}
+	SensorHost &s = c->sensors[sensor];
+	s.S = sampling_resolution, s.window = window, s.sigma = sigma;
+	if (window == HCS_WINDOW_GAUSS && sigma == -1.0f) // defaults of flat_tactile_sensor.cpp:148-160
+		s.sigma = 0.1;
+	if (window == HCS_WINDOW_TUKEY && sigma == -1.0f)
+		s.sigma = 0.3;
+	if (c->finalized) { // rebuild the step buffers with the new ray grid (rare: a reconfigure request)
+		c->finalized = false;
+		CK(cudaSetDevice(c->cfg.device));
+		finalize(c);
+	}
+	return HCS_OK;
+	API_END(c)
+}
+
 int hcs_add_curved_sensor(hcs_ctx *c, int geom, int n_taxels, const double *taxel_pos, const double *taxel_nrm,
                           int n_samples, const double *sample_pos, const double *sample_nrm, double include_margin)
 {

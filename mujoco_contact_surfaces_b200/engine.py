@@ -44,6 +44,7 @@ ABI_SYMBOLS = [
     "hcs_get_mesh", "hcs_get_lbvh", "hcs_get_counters", "hcs_set_profiling", "hcs_get_stage_ms", "hcs_version",
     "hcs_add_curved_sensor", "hcs_curved_sensor_info", "hcs_get_curved_values", "hcs_device_curved_values",
     "hcs_add_taxel_sensor", "hcs_get_taxel_values", "hcs_device_taxel_values", "hcs_get_face_vertices",
+    "hcs_update_flat_sensor",
 ]
 
 _LIB = None
@@ -83,6 +84,7 @@ def load_library():
         L.hcs_step_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
         L.hcs_step.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
         L.hcs_add_flat_sensor.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_int, C.c_int, C.c_float]
+        L.hcs_update_flat_sensor.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float]
         _LIB = L
     return _LIB
 
@@ -170,6 +172,11 @@ class HydroelasticEngine:
         self._check(self.L.hcs_sensor_dims(self.h, s, C.byref(cx), C.byref(cy)))
         self.sensors.append((cx.value, cy.value))
         return s
+
+    def update_flat_sensor(self, sensor, sampling_resolution, window=WINDOW_NONE, sigma=-1.0):
+        """FlatTactileSensor::dynamicParamCallback: new sampling_resolution / window / sigma for an existing sensor."""
+        self._check(self.L.hcs_update_flat_sensor(self.h, int(sensor), int(sampling_resolution), int(window),
+                                                  C.c_float(sigma)))
 
     def finalize(self):
         self._check(self.L.hcs_finalize(self.h))

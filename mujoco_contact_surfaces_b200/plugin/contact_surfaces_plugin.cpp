@@ -525,6 +525,32 @@ bool FlatTactileSensor::load(const mjModel *m, mjData *d)
 	return true;
 }
 
+// flat_tactile_sensor.cpp:48-125.  As in the reference the taxel resolution is NOT changed by a request (:66 is commented
+// out there); update_rate and visualize are host-side state, sampling_resolution / window / sigma go to the engine.
+void FlatTactileSensor::dynamicParamCallback(DynamicFlatTactileConfig &config, uint32_t level, const mjModel *)
+{
+	if (level == (uint32_t)-1) { // when initializing fetch current config instead of overriding
+		config.update_rate         = 1.0 / updatePeriod;
+		config.visualize           = visualize;
+		config.resolution          = resolution;
+		config.sampling_resolution = sampling_resolution;
+		config.window              = window;
+		config.sigma               = sigma;
+		return;
+	}
+	std::lock_guard<std::mutex> lock(pause_mutex); // the update loop holds it while it runs
+	updateRate          = config.update_rate;
+	updatePeriod        = 1.0 / config.update_rate;
+	visualize           = config.visualize;
+	sampling_resolution = config.sampling_resolution;
+	sigma               = (float)config.sigma;
+	window              = config.window >= 1 && config.window <= 3 ? config.window : HCS_WINDOW_NONE;
+	if (hcs_update_flat_sensor(owner_->context(), sensor_index_, sampling_resolution, window, sigma) != HCS_OK)
+		std::fprintf(stderr, "[mujoco_contact_surface_sensors] %s\n", hcs_last_error(owner_->context()));
+	n_vGeom = 0;
+	std::fill(tactile_state_values_.begin(), tactile_state_values_.end(), 0.0f); // channel.values.resize(cx * cy), :121-124
+}
+
 // flat_tactile_sensor.cpp:216-221 -> bvh_update (:262-402), computed on the GPU by the tactile kernels
 void FlatTactileSensor::internal_update(const mjModel *m, mjData *d, const std::vector<GeomCollisionPtr> &)
 {

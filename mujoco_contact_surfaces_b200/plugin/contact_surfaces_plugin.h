@@ -228,10 +228,24 @@ protected:
 };
 
 // flat_tactile_sensor.h / flat_tactile_sensor.cpp:127-214, 262-402
+// SENS/config/DynamicFlatTactile.cfg:9-23, the dynamic_reconfigure parameter set of the flat sensor (plain struct:
+// ROS is not required to change the parameters at run time)
+struct DynamicFlatTactileConfig {
+	double update_rate      = 50.0;
+	bool visualize          = false;
+	bool use_parallel       = true; // kept for interface parity; the GPU path has no serial mode
+	double resolution       = 0.025;
+	int sampling_resolution = 5;
+	int window              = 0; // 0 none, 1 gauss, 2 tukey, 3 square
+	double sigma            = -1.0;
+};
+
 class FlatTactileSensor : public TactileSensorBase
 {
 public:
 	bool load(const mjModel *m, mjData *d) override;
+	// flat_tactile_sensor.cpp:48-125; level == -1 (uint32 max): fetch the current configuration instead of applying one
+	void dynamicParamCallback(DynamicFlatTactileConfig &config, uint32_t level, const mjModel *m);
 	int cx = 0, cy = 0;
 
 protected:

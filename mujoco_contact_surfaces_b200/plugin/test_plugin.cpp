@@ -233,12 +233,27 @@ static int scenario_myrmex()
 		plugin.passiveCallback(&w.m, &w.d);
 		w.d.time += 0.001;
 	}
-	std::printf("{\"scenario\": \"myrmex_box\", ");
+	// dynamic_reconfigure request (DynamicFlatTactile.cfg): 8 x 8 rays per taxel, gauss window, then one more update
+	std::vector<double> img_before(sensor->lastMessage().begin(), sensor->lastMessage().end());
+	sensors::DynamicFlatTactileConfig dyn;
+	sensor->dynamicParamCallback(dyn, (uint32_t)-1, &w.m); // fetch
+	const int fetched_sampling = dyn.sampling_resolution;
+	dyn.sampling_resolution = 8, dyn.window = 1, dyn.sigma = 0.1;
+	sensor->dynamicParamCallback(dyn, 0, &w.m);
+	const int publishes_before = sensor->publishCount();
+	for (int step = 0; step < 25 && sensor->publishCount() == publishes_before; ++step) {
+		std::fill(w.qfrc.begin(), w.qfrc.end(), 0.0);
+		w.collision_pass();
+		plugin.passiveCallback(&w.m, &w.d);
+		w.d.time += 0.001;
+	}
+	std::vector<double> img_reconf(sensor->lastMessage().begin(), sensor->lastMessage().end());
+	std::printf("{\"scenario\": \"myrmex_box\", \"fetched_sampling\": %d, ", fetched_sampling);
+	print_vec("image_reconfigured", img_reconf.data(), (int)img_reconf.size());
 	print_vec("box_pos", box_pos, 3);
 	print_vec("box_mat", R, 9);
 	std::printf("\"cx\": %d, \"cy\": %d, \"publishes\": %d, ", sensor->cx, sensor->cy, sensor->publishCount());
-	std::vector<double> img(sensor->lastMessage().begin(), sensor->lastMessage().end());
-	print_vec("image", img.data(), (int)img.size());
+	print_vec("image", img_before.data(), (int)img_before.size());
 	print_vec("qfrc_passive", w.qfrc.data(), (int)w.qfrc.size(), true);
 	std::printf("}\n");
 	return 0;

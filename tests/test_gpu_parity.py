@@ -482,3 +482,25 @@ def test_float_leaf_filters_do_not_change_results(hcs_lib, scene_fn):
     kw = dict(max_candidates_per_slice=100000) if scene.name == "near_equal_soft_spheres" else {}
     worst = _run_scene(scene, 8 if kw else 32, seed=5, hcs_lib=hcs_lib, **kw)
     assert worst < 1e-8
+
+
+def test_flat_sensor_reconfigure(hcs_lib):
+    """FlatTactileSensor::dynamicParamCallback (flat_tactile_sensor.cpp:48-125): sampling_resolution, window and sigma of
+    an existing sensor change at run time; the next image equals the one of a sensor that was loaded that way."""
+    n_envs = 3
+    scene = scenes.myrmex("box", sampling_resolution=4)
+    eng = make_engine(scene, n_envs)
+    xpos, xmat, vel = scene.poses(n_envs, seed=7)
+    eng.step(xpos, xmat, vel, with_sensors=True)
+    before = eng.sensor_image(0).copy()
+    eng.update_flat_sensor(0, 8, 1, 0.1)  # 8 x 8 rays per taxel, gauss window
+    eng.step(xpos, xmat, vel, with_sensors=True)
+    after = eng.sensor_image(0)
+    target = scenes.myrmex("box", sampling_resolution=8, window=1, sigma=0.1)
+    orc = make_oracle(target)
+    for e in range(n_envs):
+        _, imgs = oracle_env(orc, target, xpos[e], xmat[e], vel[e], sensors=True)
+        err, nbad = compare_images(after[e], imgs[0])
+        assert nbad == 0, "reconfigured image: %d taxels beyond %.0e (max rel err %.3e)" % (nbad, TAXEL_RTOL, err)
+    assert not np.array_equal(before, after)
+    eng.close()

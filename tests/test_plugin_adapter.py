@@ -79,10 +79,22 @@ def test_adapter_sphere_on_box_and_myrmex_match_the_oracle(plugin_built):
     o.step(xpos, np.stack([np.array(r["box_mat"]), I3]))
     ref = o.sensor_image(0)
     img = np.array(r["image"], dtype=np.float32)
-    assert (r["cx"], r["cy"]) == (16, 16) and r["publishes"] == 3  # 50 Hz over 45 ms of 1 ms steps
+    # 50 Hz over 45 ms of 1 ms steps: three messages, plus the one after the reconfigure request
+    assert (r["cx"], r["cy"]) == (16, 16) and r["publishes"] == 4 and r["fetched_sampling"] == 20
     assert ref.max() > 0
     err = np.abs(img - ref) / np.maximum(np.abs(ref), 1e-3 * ref.max())
     assert err.max() < 1e-6
+    # dynamic_reconfigure request (flat_tactile_sensor.cpp:48-125): 8 x 8 rays per taxel and a gauss window
+    o2 = OracleScene(triangle_representation=True)
+    c1 = o2.add_geom(GEOM_BOX, [0.1, 0.1, 0.1], [0, 1.0, 0.05, 0.3, 0.3])
+    foam2 = o2.add_geom(GEOM_BOX, [0.2, 0.2, 0.02], [5e4, 5.0, 0, 0.3, 0.3])
+    o2.set_pairs([[c1, foam2]])
+    o2.add_flat_sensor(foam2, [0.2, 0.2, 0.02], 0.025, 8, 1, 0.1)
+    o2.step(xpos, np.stack([np.array(r["box_mat"]), I3]))
+    ref2 = o2.sensor_image(0)
+    img2 = np.array(r["image_reconfigured"], dtype=np.float32)
+    assert ref2.max() > 0 and not np.array_equal(img2, img)
+    assert (np.abs(img2 - ref2) / np.maximum(np.abs(ref2), 1e-3 * ref2.max())).max() < 1e-6
     w = o.geom_wrench(b1)
     q = np.array(r["qfrc_passive"])
     assert np.allclose(q[:3], w[:3], rtol=1e-8)
