@@ -133,3 +133,39 @@ def test_env_sharding_world_size_2_gloo(tmp_path):
         got = np.load(os.path.join(str(tmp_path), "rank%d.npy" % r))
         assert got.shape == single.res.shape
         assert got.tobytes() == single.res.tobytes()  # bit-identical to the unsharded batch
+
+
+def _run_bench(*argv, env=None):
+    import json
+    import subprocess
+    e = dict(os.environ)
+    e.update(env or {})
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py")] + list(argv), capture_output=True, text=True,
+                         timeout=600, env=e)
+    assert out.returncode == 0, out.stderr[-2000:]
+    return [json.loads(line) for line in out.stdout.strip().splitlines()]
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (the CPU arm the driver times next to ours): one JSON line with the contract's keys,
+    and every host thread in use even when the launcher exports OMP_NUM_THREADS=1 like torchrun does."""
+    (line,) = _run_bench("--impl", "reference", "--steps", "2", "--warmup", "1", "--envs", "64", env={"OMP_NUM_THREADS": "1"})
+    for key in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+                "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert key in line, key
+    assert line["impl"] == "reference" and line["unit"] == "env-steps/s" and line["value"] > 0
+    assert line["config"]["workload"] == "c1_sphere_on_box" and line["vs_baseline"] is None
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] == len(os.sched_getaffinity(0))
+    assert line["e2e"] == {"value": line["value"], "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+
+
+def test_bench_reference_arm_other_ranks_stay_silent():
+    assert _run_bench("--impl", "reference", "--steps", "1", "--warmup", "0", env={"RANK": "1", "WORLD_SIZE": "2"}) == []
+
+
+def test_benchmark_flat_cpu_leg():
+    """CPU leg of benchmark_flat.py (the grid of the reference's benchmark_flat.cpp): serial and use_parallel rows."""
+    rows = _run_bench("--cpu-flat", "box", "0.025", "4", "0.05")
+    assert [r["impl"] for r in rows] == ["cpu_serial", "cpu_parallel"]
+    for r in rows:
+        assert r["mesh"] == "box" and r["sampling_resolution"] == 4 and r["ntri"] > 0 and r["total_ms"] > r["sensor_ms"] > 0
