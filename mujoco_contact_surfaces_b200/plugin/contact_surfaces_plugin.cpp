@@ -14,6 +14,7 @@
 #include <algorithm>
 #include <cctype>
 #include <cmath>
+#include <unordered_map>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -646,8 +647,23 @@ bool CurvedSensor::load(const mjModel *m, mjData *d)
 		total += 0.5 * std::sqrt(n[0] * n[0] + n[1] * n[1] + n[2] * n[2]);
 		cum[f] = total;
 	}
-	long n_samples = std::max<long>(1, std::lround(total / (sample_resolution * sample_resolution)));
-	n_samples      = std::min<long>(n_samples, 1000000);
+	// curved_sensor.cpp:276-283: sampleNum = (int)sample_resolution * total_area (the cast comes first: 0 for the shipped
+	// sample_resolution 0.0005), then vcg::tri::PoissonSampling(mesh, points, sampleNum, radius = 0).  vcglib (un-vendored;
+	// restated from its documented behaviour): a Monte-Carlo pool of max(10000, 40 * sampleNum) area-weighted uniform
+	// points is pruned to a Poisson-disk set of radius sqrt(area / (0.7 pi sampleNum)); with sampleNum == 0 the radius
+	// is 0 and the whole pool of 10000 points survives.  Which points the pruning keeps is vcglib's business (its
+	// generator, seed 42, and its visiting order); here: splitmix64 seed 42, greedy in generation order.
+	const int sample_num  = (int)((int)sample_resolution * total);
+	const long n_samples  = std::min<long>(std::max<long>(10000, 40L * sample_num), 4000000);
+	const double p_radius = sample_num > 0 ? std::sqrt(total / (0.7 * 3.14159265358979323846 * sample_num)) : 0.0;
+	std::unordered_map<uint64_t, std::vector<int>> grid; // Poisson-disk pruning: accepted samples by cell of size radius
+	auto cell_of = [&](const double *p, int o[3]) {
+		for (int a = 0; a < 3; ++a)
+			o[a] = (int)std::floor(p[a] / p_radius);
+	};
+	auto cell_key = [](int x, int y, int z) {
+		return ((uint64_t)(uint32_t)(x + (1 << 20)) << 42) ^ ((uint64_t)(uint32_t)(y + (1 << 20)) << 21) ^ (uint64_t)(uint32_t)(z + (1 << 20));
+	};
 	uint64_t state = 42; // splitmix64
 	auto uniform = [&]() {
 		uint64_t z = (state += 0x9e3779b97f4a7c15ULL);
@@ -666,8 +682,34 @@ bool CurvedSensor::load(const mjModel *m, mjData *d)
 		double u[3] = { b[0] - a[0], b[1] - a[1], b[2] - a[2] }, v[3] = { cc[0] - a[0], cc[1] - a[1], cc[2] - a[2] };
 		double n[3] = { u[1] * v[2] - u[2] * v[1], u[2] * v[0] - u[0] * v[2], u[0] * v[1] - u[1] * v[0] };
 		double l    = std::sqrt(n[0] * n[0] + n[1] * n[1] + n[2] * n[2]);
+		double p[3];
+		for (int ax = 0; ax < 3; ++ax)
+			p[ax] = s0 * a[ax] + (1 - s0 - s1) * b[ax] + s1 * cc[ax];
+		if (p_radius > 0) { // keep the point only if no accepted point lies within the disk radius
+			int c0[3];
+			cell_of(p, c0);
+			bool free_spot = true;
+			for (int dx = -1; dx <= 1 && free_spot; ++dx)
+				for (int dy = -1; dy <= 1 && free_spot; ++dy)
+					for (int dz = -1; dz <= 1 && free_spot; ++dz) {
+						auto it = grid.find(cell_key(c0[0] + dx, c0[1] + dy, c0[2] + dz));
+						if (it == grid.end())
+							continue;
+						for (int j : it->second) {
+							const double *q = &sample_pos_[3 * (size_t)j];
+							double d2 = (p[0] - q[0]) * (p[0] - q[0]) + (p[1] - q[1]) * (p[1] - q[1]) + (p[2] - q[2]) * (p[2] - q[2]);
+							if (d2 < p_radius * p_radius) {
+								free_spot = false;
+								break;
+							}
+						}
+					}
+			if (!free_spot)
+				continue;
+			grid[cell_key(c0[0], c0[1], c0[2])].push_back((int)(sample_pos_.size() / 3));
+		}
 		for (int ax = 0; ax < 3; ++ax) {
-			sample_pos_.push_back(s0 * a[ax] + (1 - s0 - s1) * b[ax] + s1 * cc[ax]);
+			sample_pos_.push_back(p[ax]);
 			sample_nrm_.push_back(l > 0 ? n[ax] / l : 0.0);
 		}
 	}

@@ -261,10 +261,12 @@ private:
 
 // curved_sensor.h / curved_sensor.cpp:111-380 (load), :388-481 (internal_update)
 // Config keys as in SENS/config/curved_fingertip.yaml; array values ("taxels", "normals") are whitespace / comma
-// separated numbers in this stand-in for XmlRpc.  Deviation (documented in DESIGN.md): the reference samples the
-// sensor mesh with vcglib's Poisson-disk sampler (seed 42, `(int)sample_resolution * area` samples, which is 0 for
-// the shipped configuration); vcglib is not available, so the adapter draws area-weighted uniform samples with a
-// fixed-seed generator, about one per sample_resolution^2 of surface, and exposes them for inspection.
+// separated numbers in this stand-in for XmlRpc.  Surface samples (curved_sensor.cpp:276-283): the reference asks
+// vcglib's PoissonSampling for sampleNum = (int)sample_resolution * area points (the cast comes first: 0 for the
+// shipped configuration, for which vcglib returns its whole Monte-Carlo pool of 10000 uniform points).  vcglib is
+// un-vendored; the adapter restates that behaviour (pool of max(10000, 40 sampleNum) area-weighted uniform points,
+// greedy Poisson-disk pruning at radius sqrt(area / (0.7 pi sampleNum)) when sampleNum > 0) with its own fixed-seed
+// generator, and exposes the samples for inspection: they are an INPUT of the sensor, not part of the parity claim.
 class CurvedSensor : public TactileSensorBase
 {
 public:

@@ -389,11 +389,67 @@ static int scenario_taxel_tip()
 	return 0;
 }
 
+// CurvedSensor::load with an integer-valued sample_resolution: (int)sample_resolution * area > 0, so the surface samples
+// are a Poisson-disk set (curved_sensor.cpp:276-283)
+static int scenario_curved_poisson()
+{
+	ShimWorld w;
+	const double zero[3] = { 0, 0, 0 };
+	std::vector<float> mv = { 0.008f, 0, 0, -0.008f, 0, 0, 0, 0.006f, 0, 0, -0.006f, 0, 0, 0, 0.010f, 0, 0, -0.010f };
+	std::vector<int> mf   = { 0, 2, 4, 2, 1, 4, 1, 3, 4, 3, 0, 4, 2, 0, 5, 1, 2, 5, 3, 1, 5, 0, 3, 5 };
+	double box_pos[3] = { 0, 0, 0.025 }, tip_pos[3] = { 0, 0, 0.058 };
+	int b0 = w.add_body(false, zero), b1 = w.add_body(true, tip_pos);
+	double s_box[3] = { 0.025, 0.025, 0.025 };
+	int did = w.add_mesh(mv, mf);
+	w.add_geom("box_geom", mjGEOM_BOX, b0, s_box, box_pos, I3);
+	w.add_geom("fingertip_geom", mjGEOM_MESH, b1, zero, tip_pos, I3, did);
+	w.add_text("cs::HydroelasticContactRepresentation", "kTriangle");
+	w.add_numeric("cs::box_geom", { 0, 1.0, 0.01, 0.0, 0.0 });
+	w.add_numeric("cs::fingertip_geom", { 5e4, 5.0, 0.0, 0.0, 0.0 });
+	w.finish();
+	MujocoContactSurfacesPlugin plugin;
+	auto sensor = std::make_shared<sensors::CurvedSensor>();
+	PluginConfig cfg = { { "type", "mujoco_contact_surface_sensors/CurvedSensor" }, { "sensorName", "tip" },
+		                 { "geomName", "fingertip_geom" }, { "topicName", "/tip" }, { "updateRate", "4.0" },
+		                 { "include_margin", "0.006" }, { "method", "squared" }, { "sample_resolution", "3000000" },
+		                 { "taxels", "[[0.002, 0.0015, -0.005], [0, 0, 0.010]]" } };
+	plugin.addSurfacePlugin(sensor, cfg);
+	if (!plugin.load(&w.m, &w.d)) {
+		std::printf("{\"scenario\": \"curved_poisson\", \"error\": \"load failed\"}\n");
+		return 1;
+	}
+	const std::vector<double> &p = sensor->samplePoints();
+	const int n = (int)p.size() / 3;
+	double dmin = 1e300;
+	for (int i = 0; i < n; ++i)
+		for (int j = i + 1; j < n; ++j) {
+			double d2 = 0;
+			for (int a = 0; a < 3; ++a)
+				d2 += (p[3 * i + a] - p[3 * j + a]) * (p[3 * i + a] - p[3 * j + a]);
+			dmin = std::fmin(dmin, d2);
+		}
+	double area = 0;
+	for (size_t f = 0; f < mf.size() / 3; ++f) {
+		double a[3], u[3], v[3];
+		for (int k = 0; k < 3; ++k) {
+			a[k] = mv[3 * mf[3 * f] + k];
+			u[k] = mv[3 * mf[3 * f + 1] + k] - a[k];
+			v[k] = mv[3 * mf[3 * f + 2] + k] - a[k];
+		}
+		double c[3] = { u[1] * v[2] - u[2] * v[1], u[2] * v[0] - u[0] * v[2], u[0] * v[1] - u[1] * v[0] };
+		area += 0.5 * std::sqrt(c[0] * c[0] + c[1] * c[1] + c[2] * c[2]);
+	}
+	std::printf("{\"scenario\": \"curved_poisson\", \"n_samples\": %d, \"min_distance\": %.9g, \"area\": %.9g}\n", n,
+	            std::sqrt(dmin), area);
+	return 0;
+}
+
 int main()
 {
 	int rc = scenario_sphere_on_box();
 	rc |= scenario_myrmex();
 	rc |= scenario_curved_tip();
 	rc |= scenario_taxel_tip();
+	rc |= scenario_curved_poisson();
 	return rc;
 }

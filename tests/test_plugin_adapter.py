@@ -116,7 +116,8 @@ def test_adapter_curved_sensor_matches_the_oracle(plugin_built):
     taxels = np.array(r["taxels"]).reshape(-1, 3)
     cs = o.add_curved_sensor(tip, taxels, np.array(r["normals"]).reshape(-1, 3), np.array(r["sample_pos"]).reshape(-1, 3),
                              np.array(r["sample_nrm"]).reshape(-1, 3), 0.006)
-    assert len(taxels) == 5 and len(r["sample_pos"]) // 3 > 300 and o.curved_info(cs)[0] > 50
+    # (int)0.0008 * area == 0 samples requested: vcglib hands back its whole Monte-Carlo pool (curved_sensor.cpp:280-282)
+    assert len(taxels) == 5 and len(r["sample_pos"]) // 3 == 10000 and o.curved_info(cs)[0] > 50
     o.step(np.array([[0, 0, 0.025], r["tip_pos"]]), np.stack([I3, np.array(r["tip_mat"])]))
     assert o.pair_result(0)["n_polygons"] > 0
     ref = o.curved_values(cs)
@@ -151,3 +152,14 @@ def test_adapter_taxel_sensor_with_the_fingertip_yaml_keys(plugin_built):
     # visualize: one sphere per taxel, 0.5 mm .. 2.5 mm by pressure / visualize_max_pressure (taxel_sensor.cpp:447-455)
     scale = min(max(float(ref.max()), 0.0), 0.04) / 0.04
     assert r["taxel_markers"] == 5 and abs(r["max_marker_size"] - (0.0005 + scale * 0.002)) < 1e-7
+
+
+@pytest.mark.gpu
+def test_adapter_curved_sensor_poisson_disk_samples(plugin_built):
+    """An integer-valued sample_resolution asks for (int)sample_resolution * area samples (curved_sensor.cpp:280): the
+    adapter's restatement of vcglib's Poisson-disk sampling keeps every pair of samples at least one disk radius apart."""
+    r = _run(plugin_built)["curved_poisson"]
+    sample_num = int(3000000 * r["area"])
+    radius = np.sqrt(r["area"] / (0.7 * np.pi * sample_num))
+    assert sample_num > 1000 and r["min_distance"] >= radius
+    assert 0.5 * sample_num < r["n_samples"] < 2.0 * sample_num
