@@ -161,7 +161,8 @@ const float *hcs_device_curved_values(hcs_ctx *ctx, int sensor);
  * (minstd_rand0, default seed, libstdc++ generate_canonical) that restarts every update.  Which random numbers a
  * triangle gets depends on the triangle order; Drake's is not observable through the reference, ours is canonical
  * (pairs in pair order, polygons by (elemM, elemN), fan triangles in fan order), so values agree with the reference
- * in distribution, and with this repo's oracle to 1e-6.
+ * in distribution, and with this repo's oracle to 1e-6.  Limits of this method: at most 4096 contact-surface triangles
+ * of the sensor geom per environment (they are ordered in shared memory), HCS_E_CAPACITY beyond.
  * Every taxel is evaluated from the samples within include_margin.  The reference's observable behaviour is
  * reproduced, including its quirks: weighted and mean fall through to squared (value =
  * sample_resolution * sum (include_margin - d)^2 |p|), closest keeps the pressure only when `visualize` is on (else 0),

@@ -889,7 +889,9 @@ static int check_flags(hcs_ctx *c)
 		return HCS_E_CAPACITY;
 	}
 	if (c->h_flags[0] & 4) {
-		c->err = "tactile bin overflow: raise hcs_config.max_triangles_per_taxel (average bin depth)";
+		c->err = "tactile bin overflow: raise hcs_config.max_triangles_per_taxel (average bin depth); for a taxel sensor with "
+		         "sample_method area_importance: more than 4096 contact-surface triangles in one environment, or more samples "
+		         "than 1 / sample_resolution + 2 per surface";
 		return HCS_E_CAPACITY;
 	}
 	if (c->h_flags[0] & 8) {
