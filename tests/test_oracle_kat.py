@@ -569,3 +569,29 @@ def test_taxel_sensor_area_importance_sampling():
     assert out[2] == 9.0 and out[0] > 0
     # the generator restarts every update: the same contact gives the same message
     assert np.array_equal(out, s.taxel_values(sid, previous=prev))
+
+
+@pytest.mark.parametrize("triangle", [False, True])
+def test_face_vertices_export_is_consistent_with_the_point_collisions(triangle):
+    """orc_pair_face_vertices (the faces visualizeMeshElement outlines, plugin.cpp:525-555): every face's area-weighted
+    centroid is its PointCollision's p, its right-hand normal is n, and area x pressure at the centroid is fn0."""
+    s = OracleScene(triangle_representation=triangle)
+    box = s.add_geom(GEOM_BOX, [0.1, 0.1, 0.1], [0, 1, 0.1, 0.3, 0.3])
+    sph = s.add_geom(GEOM_SPHERE, [0.08], [5e4, 5, 0.05, 0.3, 0.3])
+    s.set_pairs([[sph, box]])
+    R = np.array([[np.cos(0.4), 0, np.sin(0.4)], [0, 1, 0], [-np.sin(0.4), 0, np.cos(0.4)]])
+    s.step(np.array([[0, 0, 0.1], [0.01, -0.02, 0.2 + 0.08 - 0.012]]), np.stack([I3, R.reshape(-1)]))
+    nv, fv = s.pair_face_vertices(0)
+    pcs = s.pair_faces(0)
+    assert len(nv) == len(pcs) > 10 and (nv == 3).all() == triangle
+    total = 0.0
+    for k in range(len(nv)):
+        v = fv[k, :nv[k]]
+        a2 = [np.cross(v[i] - v[0], v[i + 1] - v[0]) for i in range(1, nv[k] - 1)]
+        nrm = np.sum(a2, axis=0)
+        area = 0.5 * np.linalg.norm(nrm)
+        cen = sum(np.linalg.norm(a) * (v[0] + v[i + 1] + v[i + 2]) / 3 for i, a in enumerate(a2)) / (2 * area)
+        assert np.allclose(cen, pcs[k, 0:3], atol=1e-12)
+        assert np.allclose(nrm / (2 * area), pcs[k, 3:6], atol=1e-9)
+        total += area
+    assert abs(total - s.pair_result(0)["area"]) < 1e-12
