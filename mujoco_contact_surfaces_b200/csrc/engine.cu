@@ -705,6 +705,8 @@ static void finalize(hcs_ctx *c)
 		TaxelDev d{};
 		d.geom = th.geom, d.n_taxels = nt, d.method = th.method, d.visualize = th.visualize;
 		d.sample_method = th.sample_method;
+		if (th.sample_method == 1 && c->pairs.size() > 512)
+			throw std::runtime_error("taxel sensor with sample_method area_importance: at most 512 geom pairs (sort key layout)");
 		if (th.sample_method == 1) { // one stratum of sample_resolution * total_area per sample and surface
 			long per_surface = (long)std::ceil(1.0 / th.sample_resolution) + 2;
 			d.max_samples    = (int)std::min<long>(std::max<long>(per_surface * (long)std::max<size_t>(c->pairs.size(), 1), 16), 1L << 20);
