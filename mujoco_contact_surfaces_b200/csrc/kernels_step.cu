@@ -57,8 +57,24 @@ struct WarpTile {
 // All accesses index the one dynamic shared array directly, so the compiler emits LDS/STS and keeps its
 // freedom to schedule them (inline-asm volatile accessors serialised the loop and were slower).
 extern __shared__ __align__(16) double smem_d[];
+// HCS_SMEM_INDEX: tile positions are carried as INDICES of doubles inside the dynamic shared array, not as byte offsets.
+// With byte offsets every access went through `smem_d[a >> 3]`: the compiler cannot know that `a` is a multiple of 8,
+// so each LDS/STS got its own add + `LOP3 & ~7` + add in front of it (three dependent integer instructions per access,
+// nine per vertex; SASS of the clip loop, profiles/r01_notes.md).  With indices a vertex is one IMAD and three accesses
+// with immediate offsets.
+#ifndef HCS_SMEM_INDEX
+#define HCS_SMEM_INDEX 1
+#endif
+#if HCS_SMEM_INDEX
+constexpr unsigned SM_UNIT = 1u; // tile positions count doubles
+__device__ __forceinline__ double lds_f64(unsigned a) { return smem_d[a]; }
+__device__ __forceinline__ void sts_f64(unsigned a, double v) { smem_d[a] = v; }
+#else
+constexpr unsigned SM_UNIT = 8u; // tile positions count bytes
 __device__ __forceinline__ double lds_f64(unsigned a) { return smem_d[a >> 3]; }
 __device__ __forceinline__ void sts_f64(unsigned a, double v) { smem_d[a >> 3] = v; }
+#endif
+constexpr unsigned SM_ROW = 32u * SM_UNIT, SM_VERT = 96u * SM_UNIT; // one scalar of all 32 lanes; one vertex (x, y, z rows)
 
 // x and y of a vertex in one 16-byte shared access (2 instead of 3 accesses per vertex, 12 % fewer instructions in
 // the tet-triangle kernel).  Measured and off (scripts/sweep_r01j.sh): C1 narrowphase 0.0400 -> 0.0399 ms, C3 0.956 ->
@@ -66,7 +82,7 @@ __device__ __forceinline__ void sts_f64(unsigned a, double v) { smem_d[a >> 3] =
 #ifndef HCS_POLY_XY128
 #define HCS_POLY_XY128 0
 #endif
-// view of one lane's polygon buffer: a = 32-bit shared address of the buffer + 8 * lane; 768 bytes per vertex.
+// view of one lane's polygon buffer: a = position of the buffer + lane; one vertex = 96 doubles (768 bytes).
 // HCS_POLY_XY128: a vertex block holds the 32 lanes' (x, y) pairs (16 bytes each) and then their z (8 bytes each), so a
 // vertex moves with one 128-bit and one 64-bit access; otherwise three 256-byte rows x, y, z.
 struct Poly {
@@ -74,40 +90,40 @@ struct Poly {
 #if HCS_POLY_XY128
 	__device__ __forceinline__ D3 get(int i) const
 	{
-		unsigned p      = a + 768u * i;
-		const double2 q = reinterpret_cast<const double2 *>(smem_d)[(p + 8u * (threadIdx.x & 31u)) >> 4];
-		return mk(q.x, q.y, lds_f64(p + 512u));
+		unsigned p      = a + SM_VERT * i;
+		const double2 q = reinterpret_cast<const double2 *>(smem_d)[(p + SM_UNIT * (threadIdx.x & 31u)) / (2u * SM_UNIT)];
+		return mk(q.x, q.y, lds_f64(p + 2u * SM_ROW));
 	}
 	__device__ __forceinline__ void set(int i, D3 v) const
 	{
-		unsigned p = a + 768u * i;
-		reinterpret_cast<double2 *>(smem_d)[(p + 8u * (threadIdx.x & 31u)) >> 4] = make_double2(v.x, v.y);
-		sts_f64(p + 512u, v.z);
+		unsigned p = a + SM_VERT * i;
+		reinterpret_cast<double2 *>(smem_d)[(p + SM_UNIT * (threadIdx.x & 31u)) / (2u * SM_UNIT)] = make_double2(v.x, v.y);
+		sts_f64(p + 2u * SM_ROW, v.z);
 	}
 #else
 	__device__ __forceinline__ D3 get(int i) const
 	{
-		unsigned p = a + 768u * i;
-		return mk(lds_f64(p), lds_f64(p + 256u), lds_f64(p + 512u));
+		unsigned p = a + SM_VERT * i;
+		return mk(lds_f64(p), lds_f64(p + SM_ROW), lds_f64(p + 2u * SM_ROW));
 	}
 	__device__ __forceinline__ void set(int i, D3 v) const
 	{
-		unsigned p = a + 768u * i;
+		unsigned p = a + SM_VERT * i;
 		sts_f64(p, v.x);
-		sts_f64(p + 256u, v.y);
-		sts_f64(p + 512u, v.z);
+		sts_f64(p + SM_ROW, v.y);
+		sts_f64(p + 2u * SM_ROW, v.z);
 	}
 #endif
 };
 struct PressTile { // vertex pressures of one lane
 	unsigned a;
-	__device__ __forceinline__ double get(int i) const { return lds_f64(a + 256u * i); }
-	__device__ __forceinline__ void set(int i, double v) const { sts_f64(a + 256u * i, v); }
+	__device__ __forceinline__ double get(int i) const { return lds_f64(a + SM_ROW * i); }
+	__device__ __forceinline__ void set(int i, double v) const { sts_f64(a + SM_ROW * i, v); }
 };
-// byte offset of p inside the dynamic shared array
+// position of p inside the dynamic shared array (in SM_UNITs)
 __device__ __forceinline__ unsigned smem_addr(const void *p)
 {
-	return (unsigned)(reinterpret_cast<const char *>(p) - reinterpret_cast<const char *>(smem_d));
+	return (unsigned)(reinterpret_cast<const char *>(p) - reinterpret_cast<const char *>(smem_d)) / (8u / SM_UNIT);
 }
 
 // Per (env, pair) data: poses, velocities, relative transform (PAIR_CTX_DOUBLES doubles in 32-byte groups, layout
@@ -618,7 +634,7 @@ __global__ void __launch_bounds__(32 * HCS_NP_TRI_WARPS, HCS_NP_TRI_CTAS) narrow
 	pdl_wait();    // the broadphase grid has completed: flat list, counters and context blocks are visible
 	const int lane = threadIdx.x & 31;
 	WarpTile<7, 6> &T = reinterpret_cast<WarpTile<7, 6> *>(smem_d)[threadIdx.x >> 5];
-	const unsigned buf0 = smem_addr(&T.xyz[0][0][lane]), buf_stride = (unsigned)sizeof(T.xyz);
+	const unsigned buf0 = smem_addr(&T.xyz[0][0][lane]), buf_stride = (unsigned)sizeof(T.xyz) / (8u / SM_UNIT);
 	const int total    = flat_total(P, io);
 	const int n_chunks = (total + 31) >> 5;
 	const double kInf  = __longlong_as_double(0x7ff0000000000000LL);
@@ -695,7 +711,7 @@ __global__ void __launch_bounds__(NP_BLOCK, HCS_NP_TET_CTAS) narrow_tet_tet_kern
 	pdl_wait();    // the broadphase grid has completed: flat list, counters and context blocks are visible
 	const int lane = threadIdx.x & 31;
 	WarpTile<8, 7> &T = reinterpret_cast<WarpTile<8, 7> *>(smem_d)[threadIdx.x >> 5];
-	const unsigned buf0 = smem_addr(&T.xyz[0][0][lane]), buf_stride = (unsigned)sizeof(T.xyz);
+	const unsigned buf0 = smem_addr(&T.xyz[0][0][lane]), buf_stride = (unsigned)sizeof(T.xyz) / (8u / SM_UNIT);
 	const int total    = flat_total(P, io);
 	const int n_chunks = (total + 31) >> 5;
 	int chunk = next_chunk(P.counters + 1, lane);
