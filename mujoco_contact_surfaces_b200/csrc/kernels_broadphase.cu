@@ -33,6 +33,9 @@ namespace hcs {
 #ifndef HCS_BP_PAIRED_POP
 #define HCS_BP_PAIRED_POP 0
 #endif
+#ifndef HCS_BP_NODE256
+#define HCS_BP_NODE256 0
+#endif
 #ifndef HCS_BP_LEAF32 // soft-rigid leaf test: conservative float filter in front of the exact fp64 early-outs
 #define HCS_BP_LEAF32 1
 #endif
@@ -561,7 +564,13 @@ __device__ __forceinline__ void broadphase_unit(const PairDesc &P, const StepIO 
 							pl[a] = W.qpl[a][s];
 					}
 					const float4 *nd = nodes4 + 4 * (size_t)it.y;
+#if HCS_BP_NODE256 // the 64-byte node as two 256-bit loads instead of 3 x 128 + 64 bits (round-2 candidate, unmeasured)
+					const F8 n0 = reinterpret_cast<const F8 *>(nd)[0], n1 = reinterpret_cast<const F8 *>(nd)[1];
+					float4 a = make_float4(n0.a[0], n0.a[1], n0.a[2], n0.a[3]), b = make_float4(n0.a[4], n0.a[5], n0.a[6], n0.a[7]);
+					float4 c = make_float4(n1.a[0], n1.a[1], n1.a[2], n1.a[3]), d = make_float4(n1.a[4], n1.a[5], n1.a[6], n1.a[7]);
+#else
 					float4 a = nd[0], b = nd[1], c = nd[2], d = nd[3];
+#endif
 					cl = __float_as_int(d.x), cr = __float_as_int(d.y);
 					if (paired) { // even lane: left child, odd lane: right child; reported through the "L" slots
 						const bool left = !(lane & 1);

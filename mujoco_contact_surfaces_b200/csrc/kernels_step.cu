@@ -222,6 +222,12 @@ __device__ __forceinline__ D3 clip_crossing(D3 pc, double sc, D3 pprev, double s
 #ifndef HCS_CLIP_DEFER
 #define HCS_CLIP_DEFER 0
 #endif
+// 2 would remove the eight register moves per iteration that rotate (previous vertex, previous distance) (round-2
+// candidate read off the SASS, unmeasured; the loop's code doubles)
+#ifndef HCS_CLIP_UNROLL
+#define HCS_CLIP_UNROLL 1
+#endif
+constexpr int CLIP_UNROLL = HCS_CLIP_UNROLL; // (#pragma unroll takes a constant expression, not a macro)
 __device__ __forceinline__ int clip_halfspace(Poly in, int n, D3 nh, double d, Poly out)
 {
 	if (n == 0)
@@ -233,7 +239,7 @@ __device__ __forceinline__ int clip_halfspace(Poly in, int n, D3 nh, double d, P
 	unsigned pending = 0; // per deferred crossing one byte: output slot | input vertex << 4
 	int n_pending    = 0;
 #endif
-#pragma unroll 1
+#pragma unroll CLIP_UNROLL
 	for (int i = 0; i < n; ++i) {
 		D3 pc     = in.get(i);
 		double sc = dot(nh, pc) - d;
