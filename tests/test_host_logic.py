@@ -169,3 +169,11 @@ def test_benchmark_flat_cpu_leg():
     assert [r["impl"] for r in rows] == ["cpu_serial", "cpu_parallel"]
     for r in rows:
         assert r["mesh"] == "box" and r["sampling_resolution"] == 4 and r["ntri"] > 0 and r["total_ms"] > r["sensor_ms"] > 0
+
+
+def test_abi_header_is_plain_c():
+    """include/hcs.h is the drop-in boundary: it must compile as C99 (and as C++) on its own."""
+    import subprocess
+    hdr = os.path.join(ROOT, "include", "hcs.h")
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-fsyntax-only", "-x", "c", hdr])
+    subprocess.check_call(["g++", "-std=c++17", "-fsyntax-only", "-x", "c++", hdr])
