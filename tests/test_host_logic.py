@@ -177,3 +177,19 @@ def test_abi_header_is_plain_c():
     hdr = os.path.join(ROOT, "include", "hcs.h")
     subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-fsyntax-only", "-x", "c", hdr])
     subprocess.check_call(["g++", "-std=c++17", "-fsyntax-only", "-x", "c++", hdr])
+
+
+def test_plain_c_example_links_against_the_abi(hcs_lib, tmp_path):
+    """examples/sphere_on_box.c uses the library from C99 through include/hcs.h alone; without a CUDA device it must
+    fail loudly in hcs_create (no CPU fallback behind the boundary either)."""
+    import subprocess
+    import torch
+    exe = str(tmp_path / "sphere_on_box")
+    libdir = os.path.join(ROOT, "mujoco_contact_surfaces_b200")
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "examples", "sphere_on_box.c"), "-L", libdir, "-lhcs_b200",
+                           "-Wl,-rpath," + libdir, "-o", exe])
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present: the run itself is covered by the GPU tests")
+    out = subprocess.run([exe], capture_output=True, text=True)
+    assert out.returncode == 1 and "no usable CUDA device" in out.stderr
