@@ -180,6 +180,30 @@ def myrmex(presser="box", sampling_resolution=20, window=0, sigma=-1.0, resoluti
     return sc
 
 
+def myrmex_multi(pressers=("box", "spot", "soft_tip"), sampling_resolution=8, resolution=0.025):
+    """Several pressers on one Myrmex foam: one contact surface per presser, i.e. several BLAS under the sensor's TLAS
+    (SENS/src/flat_tactile_sensor.cpp:285-302 builds one BVH per GeomCollision that touches the sensor geom)."""
+    base = [myrmex(p, sampling_resolution, resolution=resolution) for p in pressers]
+    geoms = [b.geoms[0] for b in base] + [base[0].geoms[1]]
+    for i, g in enumerate(geoms[:-1]):
+        g.name = "%s_%d" % (g.name, i)
+    nf = len(geoms) - 1
+    sensors = [dict(geom=nf, resolution=resolution, sampling_resolution=sampling_resolution, window=0, sigma=-1.0)]
+    sc = Scene("c2_myrmex_multi", geoms, [(i, nf) for i in range(nf)], triangle=True, sensors=sensors)
+    offsets = [np.array([0.11 * np.cos(a), 0.11 * np.sin(a)]) for a in np.linspace(0, 2 * np.pi, nf, endpoint=False)]
+
+    def pose(rng, env, xpos, xmat, vel):
+        xp, xm, ve = np.zeros((2, 3)), np.zeros((2, 9)), np.zeros((2, 6))
+        for i, b in enumerate(base):
+            b.pose_fn(rng, env, xp, xm, ve)
+            xpos[i] = xp[0] * [0.3, 0.3, 1.0] + [offsets[i][0], offsets[i][1], 0.0]
+            xmat[i], vel[i] = xm[0], ve[0]
+        xpos[nf], xmat[nf] = xp[1], xm[1]
+
+    sc.pose_fn = pose
+    return sc
+
+
 # ---- C3: two soft ellipsoids, equal-pressure-plane intersection -----------------------------------------
 def soft_soft(hint=0.01, triangle=False):
     a, b = np.array([0.05, 0.04, 0.03]), np.array([0.04, 0.04, 0.06])

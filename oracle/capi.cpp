@@ -1,4 +1,4 @@
-// CPU ORACLE (test infrastructure, parity unpinned) — C entry points for ctypes (oracle/oracle.py).
+// CPU ORACLE (test infrastructure; ray caster pinned to oracle/_ref, the rest unpinned: oracle.hpp) — C entry points for ctypes (oracle/oracle.py).
 // Geometry configuration mirrors parseMujocoCustomFields (plugin.cpp:613-812): one call per
 // `cs::<geom>` numeric in configuration order; the returned index plays the role of drake_id.
 #include "oracle.hpp"
@@ -395,7 +395,7 @@ int orc_add_curved_sensor(void *h, int geom, int n_taxels, const double *taxel_p
 int orc_curved_values(void *h, int sensor, float *out, int use_bvh)
 {
 	Scene &sc = *(Scene *)h;
-	curved_sensor_values(sc, sc.last, sensor, out, use_bvh != 0);
+	curved_sensor_values(sc, sc.last, sensor, out, use_bvh);
 	return 0;
 }
 int orc_curved_info(void *h, int sensor, int *n_close_n_assign)
@@ -430,11 +430,71 @@ int orc_taxel_values(void *h, int sensor, float *values_inout)
 	return 0;
 }
 
+// use_bvh: 0 linear scan, 1 the oracle's BVH/TLAS restatement, 2 the reference's compiled ray caster (oracle/_ref,
+// installed with orc_set_external_caster)
 int orc_sensor_image(void *h, int sensor, float *out, int use_bvh, int parallel)
 {
 	Scene &sc = *(Scene *)h;
-	flat_sensor_image(sc, sc.last, sensor, out, use_bvh != 0, parallel != 0);
+	try {
+		flat_sensor_image(sc, sc.last, sensor, out, use_bvh, parallel != 0);
+	} catch (const std::exception &e) {
+		g_err = e.what();
+		return -1;
+	}
 	return 0;
+}
+
+// as orc_sensor_image, plus every ray and its nearest hit: rays[n][6] = (O, D), tuv[n][3], id[n], n = cx*cy*S*S in
+// (x, y, i, j) order
+int orc_sensor_image_trace(void *h, int sensor, float *out, int use_bvh, float *rays, float *tuv, uint32_t *id)
+{
+	Scene &sc = *(Scene *)h;
+	try {
+		FlatTrace tr;
+		flat_sensor_image(sc, sc.last, sensor, out, use_bvh, false, &tr);
+		if (tr.id.empty()) { // no surface touches the sensor
+			const FlatSensor &fs = sc.sensors[sensor];
+			size_t n             = (size_t)fs.cx * fs.cy * fs.S * fs.S;
+			std::fill(rays, rays + 6 * n, 0.0f);
+			for (size_t i = 0; i < n; ++i)
+				tuv[3 * i] = 1e30f, tuv[3 * i + 1] = tuv[3 * i + 2] = 0, id[i] = 0;
+			return 0;
+		}
+		std::copy(tr.rays.begin(), tr.rays.end(), rays);
+		std::copy(tr.tuv.begin(), tr.tuv.end(), tuv);
+		std::copy(tr.id.begin(), tr.id.end(), id);
+	} catch (const std::exception &e) {
+		g_err = e.what();
+		return -1;
+	}
+	return 0;
+}
+
+// the three entry points of oracle/_ref/libref_bvh*.so (ref_tlas_create / ref_tlas_cast / ref_tlas_destroy)
+int orc_set_external_caster(void *create, void *cast, void *destroy)
+{
+	ExternalCaster c;
+	c.create  = (decltype(c.create))create;
+	c.cast    = (decltype(c.cast))cast;
+	c.destroy = (decltype(c.destroy))destroy;
+	set_external_caster(c);
+	return 0;
+}
+
+int orc_cast_rays(int n_surf, const int *n_tri, const double *verts, int n_rays, const float *O, const float *D,
+                  float *tuv, uint32_t *id)
+{
+	cast_rays(n_surf, n_tri, verts, n_rays, O, D, tuv, id);
+	return 0;
+}
+void orc_intersect_triangle(const float *O, const float *D, const float *v0, const float *v1, const float *v2, float t_in,
+                            float *tuv_out, int *hit_out)
+{
+	intersect_triangle_one(O, D, v0, v1, v2, t_in, tuv_out, hit_out);
+}
+float orc_intersect_aabb(const float *O, const float *D, float t_in, const float *bmin, const float *bmax)
+{
+	return intersect_aabb_one(O, D, t_in, bmin, bmax);
 }
 
 // CPU baseline: n_env independent env steps (plus every sensor image when with_sensors), envs

@@ -1,4 +1,5 @@
-// CPU ORACLE — TEST INFRASTRUCTURE ONLY.  **PARITY UNPINNED.**
+// CPU ORACLE — TEST INFRASTRUCTURE ONLY.  **PARITY: tactile ray caster PINNED to the reference's compiled code;
+// Drake share UNPINNED.**
 //
 // This directory is a dependency-free C++17/fp64 restatement of the hot path of
 // ubi-agni/mujoco_contact_surfaces: the Drake v1.8.0 `geometry/proximity` arithmetic the
@@ -10,9 +11,16 @@
 // Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
 // load this library.  The product (mujoco_contact_surfaces_b200/) never links, imports or calls it.
 //
-// "Parity unpinned": the reference has no tests and no golden vectors, and Drake / MuJoCo / ROS
-// cannot be built or imported in this environment, so this restatement is checked
-// against analytic known-answer tests (tests/test_oracle_*.py) and not against reference outputs.
+// What pins it:
+// * PINNED — the float32 BVH / TLAS / Moeller-Trumbore / slab-test ray caster under the flat and curved sensors
+//   (sensor.cpp: Blas, Tlas, intersect_triangle, intersect_aabb): the reference's own bvh.cpp + bvh.h + float3.h
+//   compile unmodified against container-only shim headers (oracle/ref_shim) into oracle/_ref/, and
+//   tests/test_ref_pinning.py holds this restatement to that compiled code bit for bit — live, and through the vectors
+//   scripts/make_ref_golden.py made with it (tests/golden/ref_bvh_vectors.npz).
+// * UNPINNED — everything Drake computes (meshes, fields, the three contact queries, ContactSurface) and the plugin's
+//   force loop: the reference has no tests and no golden vectors, and Drake / MuJoCo / ROS cannot be built or imported in
+//   this environment, so that share is checked against analytic known-answer tests
+//   (tests/test_oracle_kat.py) and not against reference outputs.
 //
 // Build: `make -C oracle` (g++ -O2 -ffp-contract=off; x86-64 SSE2 IEEE double, no FMA contraction).
 #pragma once
@@ -253,9 +261,28 @@ std::shared_ptr<Surface> soft_soft(const Geom &A, int gA, const Xf &X_WA, const 
 void evaluate_contact_surface(const Scene &sc, PairOut &po); // plugin.cpp:320-409
 void passive_forces(const Scene &sc, PairOut &po, const double *xpos, const double *vel); // plugin.cpp:411-483
 void step(const Scene &sc, StepState &st, const double *xpos, const double *xmat, const double *vel, bool use_bvh);
-void flat_sensor_image(const Scene &sc, const StepState &st, int sensor, float *out, bool use_bvh, bool parallel);
+// caster: 0 = linear scan over all triangles, 1 = the oracle's own restatement of the reference's BVH/TLAS,
+// 2 = the reference's compiled ray caster (oracle/_ref) installed with set_external_caster.  trace (optional): every
+// ray (O, D) in (x, y, i, j) order with its nearest hit (t, u, v, (blas << 20) + triangle).
+struct FlatTrace {
+	std::vector<float> rays, tuv;
+	std::vector<uint32_t> id;
+};
+struct ExternalCaster { // signatures of oracle/ref_shim/ref_capi.cpp
+	void *(*create)(int n_surf, const int *n_tri, const double *verts, const double *press);
+	void (*cast)(void *h, int n, const float *O, const float *D, float *tuv, uint32_t *id);
+	void (*destroy)(void *h);
+};
+void set_external_caster(const ExternalCaster &c);
+void flat_sensor_image(const Scene &sc, const StepState &st, int sensor, float *out, int caster, bool parallel,
+                       FlatTrace *trace = nullptr);
+void cast_rays(int n_surf, const int *n_tri, const double *verts, int n_rays, const float *O, const float *D, float *tuv,
+               uint32_t *id);
+void intersect_triangle_one(const float *O, const float *D, const float *v0, const float *v1, const float *v2, float t_in,
+                            float *tuv_out, int *hit_out);
+float intersect_aabb_one(const float *O, const float *D, float t_in, const float *bmin, const float *bmax);
 void curved_sensor_load(CurvedSensor &cs, const double *sample_pos, const double *sample_nrm, int n_samples);
-void curved_sensor_values(const Scene &sc, const StepState &st, int sensor, float *out, bool use_bvh);
+void curved_sensor_values(const Scene &sc, const StepState &st, int sensor, float *out, int caster); // caster as above
 // values: the message of the previous update on entry (taxels without a sample in range keep it), updated in place
 void taxel_sensor_values(const Scene &sc, const StepState &st, int sensor, float *values);
 

@@ -35,10 +35,88 @@ def lib():
                      "orc_pair_result", "orc_pair_emitted", "orc_pair_faces", "orc_pair_triangles", "orc_geom_wrench",
                      "orc_pair_face_vertices",
                      "orc_sensor_image", "orc_bench", "orc_add_curved_sensor", "orc_curved_values", "orc_curved_info",
-                     "orc_add_taxel_sensor", "orc_taxel_values"):
+                     "orc_add_taxel_sensor", "orc_taxel_values", "orc_sensor_image_trace", "orc_set_external_caster",
+                     "orc_cast_rays"):
             getattr(L, name).restype = C.c_int
+        L.orc_set_external_caster.argtypes = [C.c_void_p] * 3
+        L.orc_intersect_aabb.restype = C.c_float
+        L.orc_intersect_aabb.argtypes = [C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_float, C.POINTER(C.c_float),
+                                         C.POINTER(C.c_float)]
+        L.orc_intersect_triangle.argtypes = [C.POINTER(C.c_float)] * 5 + [C.c_float, C.POINTER(C.c_float), C.POINTER(C.c_int)]
+        L.orc_intersect_triangle.restype = None
         _LIB = L
     return _LIB
+
+
+REF_SOURCE = "/root/reference/mujoco_contact_surface_sensors"
+_REF = {}
+
+
+def build_ref():
+    """Compiles the REFERENCE's own ray caster (bvh.cpp, unmodified, where it lies under /root/reference) against the
+    shim headers of oracle/ref_shim into oracle/_ref/ — only where the reference is present (this container).  On the
+    GPU box the prebuilt libraries that travelled with the snapshot are used.  Returns True when oracle/_ref exists."""
+    if os.path.exists(os.path.join(REF_SOURCE, "src", "bvh.cpp")):
+        subprocess.check_call(["make", "-C", os.path.join(_HERE, "ref_shim"), "-s"])
+    return ref_available()
+
+
+def ref_available(sse=False):
+    return os.path.exists(os.path.join(_HERE, "_ref", "libref_bvh_sse.so" if sse else "libref_bvh.so"))
+
+
+def ref_lib(sse=False):
+    """oracle/_ref/libref_bvh.so (scalar code path) or libref_bvh_sse.so (-DUSE_SSE, the reference's CMake default)."""
+    if sse not in _REF:
+        R = C.CDLL(os.path.join(_HERE, "_ref", "libref_bvh_sse.so" if sse else "libref_bvh.so"))
+        R.ref_tlas_create.restype = C.c_void_p
+        R.ref_tlas_create.argtypes = [C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_double), C.POINTER(C.c_double)]
+        R.ref_tlas_cast.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float),
+                                    C.POINTER(C.c_uint32)]
+        R.ref_tlas_destroy.argtypes = [C.c_void_p]
+        R.ref_evaluate.restype = C.c_double
+        R.ref_intersect_aabb.restype = C.c_float
+        R.ref_intersect_aabb.argtypes = [C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_float, C.POINTER(C.c_float),
+                                         C.POINTER(C.c_float)]
+        R.ref_intersect_triangle.argtypes = [C.POINTER(C.c_float)] * 5 + [C.c_float, C.POINTER(C.c_float), C.POINTER(C.c_int)]
+        assert R.ref_use_sse() == int(sse)
+        _REF[sse] = R
+    return _REF[sse]
+
+
+def use_reference_caster(sse=False):
+    """Routes caster mode 2 of the oracle's sensors (sensor_image(use_bvh=2), curved_values(use_bvh=2)) through the
+    reference's compiled BVH/TLAS."""
+    R, L = ref_lib(sse), lib()
+    L.orc_set_external_caster(C.cast(R.ref_tlas_create, C.c_void_p), C.cast(R.ref_tlas_cast, C.c_void_p),
+                              C.cast(R.ref_tlas_destroy, C.c_void_p))
+
+
+def _f(a):
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+def ref_cast_rays(n_tri, verts, O, D, sse=False):
+    """The reference's ray caster on triangle soups: n_tri[s] triangles per surface, verts [sum n_tri][3][3] doubles."""
+    R = ref_lib(sse)
+    n_tri, verts, O, D = np.ascontiguousarray(n_tri, dtype=np.int32), _d(verts), _f(O), _f(D)
+    n = len(O)
+    tuv, hid = np.empty((n, 3), np.float32), np.empty(n, np.uint32)
+    h = C.c_void_p(R.ref_tlas_create(len(n_tri), _p(n_tri, C.c_int), _p(verts, C.c_double), None))
+    R.ref_tlas_cast(h, n, _p(O, C.c_float), _p(D, C.c_float), _p(tuv, C.c_float), _p(hid, C.c_uint32))
+    R.ref_tlas_destroy(h)
+    return tuv, hid
+
+
+def oracle_cast_rays(n_tri, verts, O, D):
+    """The oracle's restatement of the same ray caster, same arguments."""
+    L = lib()
+    n_tri, verts, O, D = np.ascontiguousarray(n_tri, dtype=np.int32), _d(verts), _f(O), _f(D)
+    n = len(O)
+    tuv, hid = np.empty((n, 3), np.float32), np.empty(n, np.uint32)
+    L.orc_cast_rays(len(n_tri), _p(n_tri, C.c_int), _p(verts, C.c_double), n, _p(O, C.c_float), _p(D, C.c_float),
+                    _p(tuv, C.c_float), _p(hid, C.c_uint32))
+    return tuv, hid
 
 
 def _p(a, t):
@@ -218,10 +296,24 @@ class OracleScene:
         return o
 
     def sensor_image(self, sensor, use_bvh=True, parallel=False):
+        """use_bvh: False/0 linear scan, True/1 the oracle's BVH restatement, 2 the reference's compiled ray caster
+        (needs use_reference_caster() first)."""
         cx, cy = self.sensor_dims(sensor)
         img = np.zeros(cx * cy, dtype=np.float32)
-        self.L.orc_sensor_image(self.h, sensor, _p(img, C.c_float), int(use_bvh), int(parallel))
+        if self.L.orc_sensor_image(self.h, sensor, _p(img, C.c_float), int(use_bvh), int(parallel)):
+            raise RuntimeError(self.L.orc_last_error().decode())
         return img
+
+    def sensor_image_trace(self, sensor, S, use_bvh=True):
+        """Image plus every ray (O, D) and its nearest hit (t, u, v, id) in (x, y, i, j) order."""
+        cx, cy = self.sensor_dims(sensor)
+        n = cx * cy * S * S
+        img = np.zeros(cx * cy, dtype=np.float32)
+        rays, tuv, hid = np.zeros((n, 6), np.float32), np.zeros((n, 3), np.float32), np.zeros(n, np.uint32)
+        if self.L.orc_sensor_image_trace(self.h, sensor, _p(img, C.c_float), int(use_bvh), _p(rays, C.c_float),
+                                         _p(tuv, C.c_float), _p(hid, C.c_uint32)):
+            raise RuntimeError(self.L.orc_last_error().decode())
+        return img, rays, tuv, hid
 
     def bench(self, xpos, xmat, vel, use_bvh=True, with_sensors=False, threads=1):
         """Time n_env env steps on the host; returns (seconds, candidate pair-evals, checksum)."""

@@ -1,4 +1,4 @@
-// CPU ORACLE (test infrastructure, parity unpinned) — Myrmex flat tactile sensor.
+// CPU ORACLE (test infrastructure; ray caster pinned to oracle/_ref, the rest unpinned: oracle.hpp) — Myrmex flat tactile sensor.
 //
 // Restates mujoco_contact_surface_sensors/src/flat_tactile_sensor.cpp:127-214 (load constants),
 // :262-402 (bvh_update) and the float32 ray caster of src/bvh.cpp:49-476 +
@@ -13,6 +13,7 @@
 
 #include <algorithm>
 #include <cstring>
+#include <stdexcept>
 
 namespace orc {
 
@@ -346,13 +347,47 @@ struct Tlas {
 
 const float SQRT_2f = 1.41421356237; // flat_tactile_sensor.h:47 (float)
 
+ExternalCaster g_ext{ nullptr, nullptr, nullptr };
+
 } // namespace
+
+// caster == 2: the same surfaces handed to the REFERENCE's own BVH/TLAS (oracle/_ref, compiled from
+// mujoco_contact_surface_sensors/src/bvh.cpp) as triangle soups in double, the way bvh.cpp:92-105 reads them
+static void *make_external_tlas(const std::vector<Blas> &blas)
+{
+	if (!g_ext.create)
+		throw std::runtime_error("no external ray caster installed (oracle/_ref not loaded)");
+	std::vector<int> n_tri;
+	std::vector<double> soup, press;
+	for (const Blas &b : blas) {
+		const Surface &s = *b.surface;
+		n_tri.push_back(s.num_faces());
+		for (int f = 0; f < s.num_faces(); ++f)
+			for (int k = 0; k < 3; ++k) {
+				int v = s.face_idx[s.face_first[f] + k];
+				soup.push_back(s.v[v].x), soup.push_back(s.v[v].y), soup.push_back(s.v[v].z);
+				press.push_back(s.e[v]);
+			}
+	}
+	return g_ext.create((int)blas.size(), n_tri.data(), soup.data(), press.data());
+}
+static void external_cast(void *ext, Ray &ray)
+{
+	float O[3] = { ray.O.x, ray.O.y, ray.O.z }, D[3] = { ray.D.x, ray.D.y, ray.D.z }, tuv[3];
+	uint32_t hid;
+	g_ext.cast(ext, 1, O, D, tuv, &hid);
+	ray.t = tuv[0], ray.u = tuv[1], ray.v = tuv[2], ray.hit = hid;
+}
 
 // flat_tactile_sensor.cpp:262-402 bvh_update.  use_bvh=false replaces the TLAS/BLAS traversal by a
 // linear scan over all triangles in surface order (same Möller–Trumbore arithmetic, same strict
 // `t < hit.t` rule) and is used to bound tie-breaking effects.
-void flat_sensor_image(const Scene &sc, const StepState &st, int sensor, float *out, bool use_bvh, bool parallel)
+void flat_sensor_image(const Scene &sc, const StepState &st, int sensor, float *out, int caster, bool parallel,
+                       FlatTrace *trace)
 {
+	const bool use_bvh = caster == 1;
+	const bool use_ext = caster == 2;
+
 	const FlatSensor &fs = sc.sensors[sensor];
 	int id = fs.geom, cx = fs.cx, cy = fs.cy, S = fs.S;
 	float xs = (float)fs.size[0], ys = (float)fs.size[1], zs = (float)fs.size[2];
@@ -387,6 +422,12 @@ void flat_sensor_image(const Scene &sc, const StepState &st, int sensor, float *
 		return;
 	Tlas tlas;
 	tlas.build(blas);
+	void *ext = use_ext ? make_external_tlas(blas) : nullptr;
+	if (trace) {
+		trace->rays.assign((size_t)cx * cy * S * S * 6, 0.0f);
+		trace->tuv.assign((size_t)cx * cy * S * S * 3, 0.0f);
+		trace->id.assign((size_t)cx * cy * S * S, 0u);
+	}
 
 	float rsigma_squared = 0, rtukey = 0;
 	if (use_gaussian)
@@ -415,13 +456,22 @@ void flat_sensor_image(const Scene &sc, const StepState &st, int sensor, float *
 					ray.t   = 1e30f;
 					ray.u = ray.v = 0;
 					ray.hit = 0;
-					if (use_bvh) {
+					if (use_ext) {
+						external_cast(ext, ray);
+					} else if (use_bvh) {
 						tlas.intersect(ray);
 					} else {
 						ray.rD = { 1.0f / ray.D.x, 1.0f / ray.D.y, 1.0f / ray.D.z };
 						for (unsigned b = 0; b < blas.size(); ++b)
 							for (unsigned t = 0; t < blas[b].tri.size(); ++t)
 								intersect_triangle(ray, blas[b].tri[t], (b << 20) + t);
+					}
+					if (trace) {
+						size_t r = (((size_t)x * cy + y) * S + i) * S + j;
+						float *q = &trace->rays[6 * r];
+						q[0] = ray.O.x, q[1] = ray.O.y, q[2] = ray.O.z, q[3] = ray.D.x, q[4] = ray.D.y, q[5] = ray.D.z;
+						trace->tuv[3 * r] = ray.t, trace->tuv[3 * r + 1] = ray.u, trace->tuv[3 * r + 2] = ray.v;
+						trace->id[r] = ray.hit;
 					}
 					if (ray.t < 1.5 * zs && ray.t > 0.0f) {
 						double bary[3]   = { (double)(1 - ray.u - ray.v), (double)ray.u, (double)ray.v };
@@ -453,6 +503,67 @@ void flat_sensor_image(const Scene &sc, const StepState &st, int sensor, float *
 			out[x + cy * y] = avg_pressure;
 		}
 	}
+	if (ext)
+		g_ext.destroy(ext);
+}
+
+void set_external_caster(const ExternalCaster &c) { g_ext = c; }
+
+// The oracle's own BLAS/TLAS/Moeller-Trumbore restatement on caller-supplied triangle soups and rays: the entry the
+// tests use to hold it against the reference's compiled ray caster (oracle/_ref) and the vectors made with it
+// (tests/golden/ref_bvh_*.npz).  Same argument layout as ref_tlas_create / ref_tlas_cast (oracle/ref_shim/ref_capi.cpp).
+void cast_rays(int n_surf, const int *n_tri, const double *verts, int n_rays, const float *O, const float *D,
+               float *tuv, uint32_t *id)
+{
+	std::vector<Surface> surf(n_surf);
+	size_t off = 0;
+	for (int s = 0; s < n_surf; ++s) {
+		Surface &sf = surf[s];
+		sf.tri      = true;
+		for (int t = 0; t < n_tri[s]; ++t, ++off) {
+			sf.face_first.push_back((int)sf.face_idx.size());
+			sf.face_n.push_back(3);
+			for (int k = 0; k < 3; ++k) {
+				sf.face_idx.push_back((int)sf.v.size());
+				sf.v.push_back({ verts[9 * off + 3 * k], verts[9 * off + 3 * k + 1], verts[9 * off + 3 * k + 2] });
+			}
+		}
+	}
+	std::vector<Blas> blas(n_surf);
+	for (int s = 0; s < n_surf; ++s)
+		blas[s].build(surf[s]);
+	Tlas tlas;
+	tlas.build(blas);
+	for (int i = 0; i < n_rays; ++i) {
+		Ray ray;
+		ray.O = { O[3 * i], O[3 * i + 1], O[3 * i + 2] };
+		ray.D = { D[3 * i], D[3 * i + 1], D[3 * i + 2] };
+		ray.t = 1e30f, ray.u = ray.v = 0, ray.hit = 0;
+		tlas.intersect(ray);
+		tuv[3 * i] = ray.t, tuv[3 * i + 1] = ray.u, tuv[3 * i + 2] = ray.v;
+		id[i] = ray.hit;
+	}
+}
+
+// single primitives (bvh.cpp:49-74, bvh.h:157-176), for the known-answer comparison with oracle/_ref
+void intersect_triangle_one(const float *O, const float *D, const float *v0, const float *v1, const float *v2, float t_in,
+                            float *tuv_out, int *hit_out)
+{
+	Ray ray;
+	ray.O = { O[0], O[1], O[2] }, ray.D = { D[0], D[1], D[2] };
+	ray.t = t_in, ray.u = ray.v = 0, ray.hit = 0xffffffffu;
+	Tri tri{ { v0[0], v0[1], v0[2] }, { v1[0], v1[1], v1[2] }, { v2[0], v2[1], v2[2] }, { 0, 0, 0 } };
+	intersect_triangle(ray, tri, 7u);
+	tuv_out[0] = ray.t, tuv_out[1] = ray.u, tuv_out[2] = ray.v;
+	*hit_out   = ray.hit == 7u;
+}
+float intersect_aabb_one(const float *O, const float *D, float t_in, const float *bmin, const float *bmax)
+{
+	Ray ray;
+	ray.O = { O[0], O[1], O[2] }, ray.D = { D[0], D[1], D[2] };
+	ray.rD = { 1.0f / D[0], 1.0f / D[1], 1.0f / D[2] };
+	ray.t  = t_in;
+	return intersect_aabb(ray, { bmin[0], bmin[1], bmin[2] }, { bmax[0], bmax[1], bmax[2] });
 }
 
 // curved_sensor.cpp:325-368: distance matrix taxel x sample, assignment of every sample within include_margin of a
@@ -490,8 +601,9 @@ void curved_sensor_load(CurvedSensor &cs, const double *sample_pos, const double
 
 // curved_sensor.cpp:388-481 internal_update: one ray per (taxel, assigned sample) from the sample point along the
 // inward normal, nearest hit with 0 < t < include_margin, pressure = sum of weight * e_MN(hit).
-void curved_sensor_values(const Scene &sc, const StepState &st, int sensor, float *out, bool use_bvh)
+void curved_sensor_values(const Scene &sc, const StepState &st, int sensor, float *out, int caster)
 {
+	const bool use_bvh = caster == 1, use_ext = caster == 2;
 	const CurvedSensor &cs = sc.curved[sensor];
 	const int id = cs.geom, n = (int)cs.taxel_pos.size();
 	double rot[9];
@@ -512,6 +624,7 @@ void curved_sensor_values(const Scene &sc, const StepState &st, int sensor, floa
 		return;
 	Tlas tlas;
 	tlas.build(blas);
+	void *ext = use_ext ? make_external_tlas(blas) : nullptr;
 	for (int i = 0; i < n; ++i) {
 		double pressure = 0;
 		for (size_t j0 = 0; j0 < cs.surface_idx[i].size(); ++j0) {
@@ -531,7 +644,9 @@ void curved_sensor_values(const Scene &sc, const StepState &st, int sensor, floa
 			ray.t   = 1e30f;
 			ray.u = ray.v = 0;
 			ray.hit = 0;
-			if (use_bvh) {
+			if (use_ext) {
+				external_cast(ext, ray);
+			} else if (use_bvh) {
 				tlas.intersect(ray);
 			} else {
 				ray.rD = { 1.0f / ray.D.x, 1.0f / ray.D.y, 1.0f / ray.D.z };
@@ -552,6 +667,8 @@ void curved_sensor_values(const Scene &sc, const StepState &st, int sensor, floa
 		}
 		out[i] = (float)pressure;
 	}
+	if (ext)
+		g_ext.destroy(ext);
 }
 
 // taxel_sensor.cpp:158-478 internal_update, DEFAULT sampling.  Reproduced as written, including quirk Q12: the

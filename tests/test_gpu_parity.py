@@ -5,7 +5,7 @@ import numpy as np
 import pytest
 
 from mujoco_contact_surfaces_b200 import scenes
-from parity_utils import (TAXEL_RTOL, compare_env, compare_images, make_engine, make_oracle, oracle_env)
+from parity_utils import (TAXEL_RTOL, compare_env, compare_images, compare_wrench, make_engine, make_oracle, oracle_env)
 
 pytestmark = pytest.mark.gpu
 
@@ -25,9 +25,7 @@ def _run_scene(scene, n_envs, seed, hcs_lib, with_sensors=False, check_images=Tr
         worst = max(worst, compare_env(res[e], emitted, ref_pairs))
         n_poly += sum(r["n_polygons"] for r in ref_pairs)
         for g in range(scene.n_geoms):
-            ref_w = orc.geom_wrench(g)
-            scale = max(np.linalg.norm(ref_w), 1e-12)
-            assert np.linalg.norm(wrench[e, g] - ref_w) / scale < 1e-8 or np.linalg.norm(ref_w) < 1e-9
+            compare_wrench(wrench[e, g], orc.geom_wrench(g))
         if with_sensors and check_images:
             for s, ref_img in enumerate(ref_imgs):
                 err, nbad = compare_images(imgs[s][e], ref_img)
@@ -332,12 +330,16 @@ def test_full_size_batch_properties(hcs_lib, factory, n_envs, seed):
             np.add.at(acc, (np.arange(n_envs), g), sign * np.concatenate([res["F"][:, p], res["tau"][:, p]], axis=1))
     assert np.all(np.abs(acc - wrench) <= 1e-12 * scale[:, None, None])
 
-    # 4. a seeded sample of the full batch against the oracle (same bars as the small-batch tests)
+    # 4. EVERY environment of the full batch against the oracle (same bars as the small-batch tests; round 1 sampled 24)
     eng.step(xpos, xmat, vel)  # the emitted lists on the device are those of the last step: back to the original order
     orc = make_oracle(scene)
-    for e in np.random.default_rng(seed + 1).choice(n_envs, size=24, replace=False):
+    worst = 0.0
+    for e in range(n_envs):
         ref_pairs, _ = oracle_env(orc, scene, xpos[e], xmat[e], vel[e], sensors=False)
-        compare_env(res[e], [eng.emitted(int(e), p) for p in range(n_pairs)], ref_pairs)
+        worst = max(worst, compare_env(res[e], [eng.emitted(e, p) for p in range(n_pairs)], ref_pairs))
+        for g in range(scene.n_geoms):
+            worst = max(worst, compare_wrench(wrench[e, g], orc.geom_wrench(g)))
+    print("full batch %s: %d envs against the oracle, worst relative error %.2e" % (scene.name, n_envs, worst))
     eng.close()
 
 
@@ -503,4 +505,63 @@ def test_flat_sensor_reconfigure(hcs_lib):
         err, nbad = compare_images(after[e], imgs[0])
         assert nbad == 0, "reconfigured image: %d taxels beyond %.0e (max rel err %.3e)" % (nbad, TAXEL_RTOL, err)
     assert not np.array_equal(before, after)
+    eng.close()
+
+
+# ---- reference-pinned: the CUDA raster against the REFERENCE's compiled ray caster --------------------------------------
+def _ref_cases():
+    import os
+    with np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_bvh_vectors.npz")) as z:
+        return [c.split(":") for c in z["cases"]], {k: z[k] for k in z.files if k.endswith(("_image", "_meta"))}
+
+
+def _ref_scene(presser, resolution, S):
+    if presser == "multi":
+        return scenes.myrmex_multi(sampling_resolution=S, resolution=resolution)
+    return scenes.myrmex(presser, S, resolution=resolution)
+
+
+@pytest.mark.parametrize("name,presser", _ref_cases()[0])
+def test_cuda_raster_matches_the_reference_ray_caster_vectors(hcs_lib, name, presser):
+    """tests/golden/ref_bvh_vectors.npz holds taxel images made with the reference's own compiled BVH/TLAS
+    (oracle/_ref, scripts/make_ref_golden.py) inside the flat-sensor loop, at the corners of the benchmark grid of
+    benchmark_flat.cpp:282-373 plus a soft presser and a three-surface TLAS case.  1e-6 per taxel, no floor."""
+    gold = _ref_cases()[1]
+    res, S, seed, env = gold[name + "_meta"]
+    S, seed, env = int(S), int(seed), int(env)
+    scene = _ref_scene(presser, float(res), S)
+    xpos, xmat, vel = scene.poses(env + 1, seed=seed)
+    eng = make_engine(scene, env + 1)
+    eng.step(xpos, xmat, vel, with_sensors=True)
+    img = eng.sensor_image(0)[env]
+    eng.close()
+    ref = gold[name + "_image"]
+    assert (ref > 0).sum() >= 3
+    err, nbad = compare_images(img, ref)
+    assert nbad == 0, "taxel image vs reference ray caster: %d taxels beyond %.0e (max rel err %.3e)" % (nbad, TAXEL_RTOL, err)
+
+
+@pytest.mark.parametrize("sse", [False, True])
+@pytest.mark.parametrize("presser,resolution,S", [("box", 0.025, 20), ("plate", 0.025, 16), ("spot", 0.025, 8), ("box", 0.0025, 4),
+                                                   ("multi", 0.025, 8)])
+def test_cuda_raster_matches_the_live_reference_ray_caster(hcs_lib, presser, resolution, S, sse):
+    """The same against oracle/_ref live (the prebuilt libraries travel to the GPU box), fresh seeds, both builds."""
+    from oracle import oracle as O
+    if not O.ref_available(sse):
+        pytest.skip("oracle/_ref not present")
+    O.use_reference_caster(sse)
+    scene = _ref_scene(presser, resolution, S)
+    n_envs = 3
+    xpos, xmat, vel = scene.poses(n_envs, seed=515)
+    eng, orc = make_engine(scene, n_envs), make_oracle(scene)
+    eng.step(xpos, xmat, vel, with_sensors=True)
+    imgs = eng.sensor_image(0)
+    lit = 0
+    for e in range(n_envs):
+        orc.step(xpos[e], xmat[e], vel[e])
+        ref = orc.sensor_image(0, use_bvh=2)
+        lit += int((ref > 0).sum())
+        err, nbad = compare_images(imgs[e], ref)
+        assert nbad == 0, "env %d: %d taxels beyond %.0e (max rel err %.3e)" % (e, nbad, TAXEL_RTOL, err)
+    assert lit > 0
     eng.close()
