@@ -452,6 +452,10 @@ static void build_pairs(hcs_ctx *c)
 					P.slice_q = (int)std::max<long>(1, (P.nq + want - 1) / want);
 			}
 			P.n_slices   = (P.nq + P.slice_q - 1) / P.slice_q;
+			if (P.n_slices > (1 << TRI_SLICE_BITS)) { // the slice index is part of the triangle ordering key
+				P.slice_q  = (P.nq + (1 << TRI_SLICE_BITS) - 1) >> TRI_SLICE_BITS;
+				P.n_slices = (P.nq + P.slice_q - 1) / P.slice_q;
+			}
 			size_t units = (size_t)n_env * P.n_slices;
 			P.partial    = dalloc<SlicePartial>(c->step_allocs, units);
 			{
@@ -464,8 +468,13 @@ static void build_pairs(hcs_ctx *c)
 				                                           std::min<long>((long)P.nq * P.n_tree, 16L * ((long)P.nq + P.n_tree));
 				long total   = c->cfg.max_candidates_per_slice > 0 ? (long)c->cfg.max_candidates_per_slice * (long)units :
 				                                                     std::min<long>(per_env * n_env, 64L << 20);
-				if (const char *mt_env = getenv("HCS_MAX_TOTAL_CANDIDATES"))
-					total = atol(mt_env);
+				if (const char *mt_env = getenv("HCS_MAX_TOTAL_CANDIDATES")) {
+					char *end = nullptr;
+					long v    = strtol(mt_env, &end, 10);
+					if (end == mt_env || *end != 0 || v < 1)
+						throw std::runtime_error("HCS_MAX_TOTAL_CANDIDATES must be a positive integer");
+					total = v;
+				}
 				P.contrib_cap = (int)std::max<long>(1024, std::min<long>(total, 1L << 30));
 				P.range_cap   = (int)std::min<long>((long)units + P.contrib_cap / 128 + 64, 1L << 30);
 				P.flat        = dalloc<uint4>(c->step_allocs, (size_t)P.contrib_cap);
@@ -651,6 +660,9 @@ static void release_step_buffers(hcs_ctx *c)
 
 static void finalize(hcs_ctx *c)
 {
+	// not finalized until the very end: if anything below throws (mesh rebuild, cudaMalloc, a sensor limit) the step
+	// entry points refuse to run on the freed buffers instead of launching kernels on them
+	c->finalized = false;
 	release_step_buffers(c);
 	const int n_env = c->cfg.n_envs, ng = (int)c->geoms.size(), np = (int)c->pairs.size();
 	for (GeomHost &g : c->geoms)
@@ -879,7 +891,7 @@ static void fetch(hcs_ctx *c, int with_sensors, bool with_pairs = true)
 static int check_flags(hcs_ctx *c)
 {
 	if (c->h_flags[1]) {
-		c->err = "LBVH traversal stack overflow (tree deeper than 64)";
+		c->err = "broadphase work queue overflow (shared-memory LIFO queues of a unit full)";
 		return HCS_E_CAPACITY;
 	}
 	if (c->h_flags[0] & 1) {
@@ -909,10 +921,29 @@ static int check_flags(hcs_ctx *c)
 // =====================================================================================================
 // C ABI
 // =====================================================================================================
+// Every entry point that touches CUDA runs with the context's device current and restores the caller's device on
+// the way out: contexts on different GPUs can be driven from one thread (or from one thread per device) in any order.
+struct DeviceGuard {
+	int prev = -1, dev;
+	explicit DeviceGuard(int d) : dev(d)
+	{
+		if (cudaGetDevice(&prev) != cudaSuccess)
+			prev = -1;
+		if (prev != dev && cudaSetDevice(dev) != cudaSuccess)
+			throw std::runtime_error("cudaSetDevice failed for the context's device");
+	}
+	~DeviceGuard()
+	{
+		if (prev >= 0 && prev != dev)
+			cudaSetDevice(prev);
+	}
+};
+
 #define API_BEGIN(ctx_)            \
 	if (!(ctx_))                   \
 		return HCS_E_INVALID;      \
-	try {
+	try {                          \
+		DeviceGuard device_guard_((ctx_)->cfg.device);
 #define API_END(ctx_)                        \
 	}                                        \
 	catch (const std::exception &e)          \
@@ -1003,6 +1034,12 @@ int hcs_add_geom(hcs_ctx *c, int mj_geom_type, const double size[3], const float
 		c->err = "hcs_add_geom: size/props required";
 		return HCS_E_INVALID;
 	}
+	if (mj_geom_type == HCS_GEOM_MESH && mesh_face)
+		for (size_t i = 0; i < 3 * (size_t)std::max(n_face, 0); ++i)
+			if (mesh_face[i] < 0 || mesh_face[i] >= n_vert) {
+				c->err = "hcs_add_geom: mesh face index out of range";
+				return HCS_E_INVALID;
+			}
 	GeomHost g;
 	g.mj_type = mj_geom_type;
 	for (int i = 0; i < 3; ++i)
@@ -1028,6 +1065,11 @@ int hcs_add_soft_mesh(hcs_ctx *c, const double *verts, int n_vert, const int32_t
 		c->err = "hcs_add_soft_mesh: bad arguments (modulus must be > 0)";
 		return HCS_E_INVALID;
 	}
+	for (size_t i = 0; i < 4 * (size_t)n_tet; ++i)
+		if (tets[i] < 0 || tets[i] >= n_vert) {
+			c->err = "hcs_add_soft_mesh: tet vertex index out of range";
+			return HCS_E_INVALID;
+		}
 	GeomHost g;
 	g.mj_type = HCS_GEOM_MESH;
 	g.custom  = true;
@@ -1050,6 +1092,11 @@ int hcs_add_rigid_mesh(hcs_ctx *c, const double *verts, int n_vert, const int32_
 		c->err = "hcs_add_rigid_mesh: bad arguments";
 		return HCS_E_INVALID;
 	}
+	for (size_t i = 0; i < 3 * (size_t)n_tri; ++i)
+		if (tris[i] < 0 || tris[i] >= n_vert) {
+			c->err = "hcs_add_rigid_mesh: triangle vertex index out of range";
+			return HCS_E_INVALID;
+		}
 	GeomHost g;
 	g.mj_type = HCS_GEOM_MESH;
 	g.custom  = true;
@@ -1160,8 +1207,7 @@ int hcs_update_flat_sensor(hcs_ctx *c, int sensor, int sampling_resolution, int 
 	if (window == HCS_WINDOW_TUKEY && sigma == -1.0f)
 		s.sigma = 0.3;
 	if (c->finalized) { // rebuild the step buffers with the new ray grid (rare: a reconfigure request)
-		c->finalized = false;
-		CK(cudaSetDevice(c->cfg.device));
+		CK(cudaStreamSynchronize(c->stream));
 		finalize(c);
 	}
 	return HCS_OK;
@@ -1320,7 +1366,6 @@ int hcs_sensor_dims(const hcs_ctx *c, int sensor, int *cx, int *cy)
 int hcs_finalize(hcs_ctx *c)
 {
 	API_BEGIN(c)
-	CK(cudaSetDevice(c->cfg.device));
 	finalize(c);
 	return HCS_OK;
 	API_END(c)
