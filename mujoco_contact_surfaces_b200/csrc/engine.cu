@@ -20,6 +20,7 @@
 namespace hcs {
 
 static thread_local std::string g_create_error;
+constexpr long ITEM_LIMIT = 1L << 26; // broadphase queue items address 2^26 nodes / elements (kernels_broadphase.cu)
 
 #define CK(call)                                                                                        \
 	do {                                                                                                \
@@ -80,6 +81,12 @@ struct TaxelHost {
 	float *h_values = nullptr; // pinned [n_env][n_taxels]
 };
 
+struct EmittedCache {
+	int64_t step = -1;
+	std::vector<int> offset;       // [n_envs + 1]
+	std::vector<int32_t> triples;  // (elemM, elemN, nverts)
+};
+
 } // namespace hcs
 
 using namespace hcs;
@@ -117,6 +124,8 @@ struct hcs_ctx {
 	cudaEvent_t ev[8]{};
 	float stage_ms[7]{};
 	bool results_on_host = false, pairs_on_host = false, sensors_on_host = false, last_with_sensors = false;
+	int64_t step_counter = 0;                 // steps launched so far
+	std::vector<EmittedCache> emitted_cache;  // hcs_get_emitted: per pair, the last step's list indexed by environment
 };
 
 namespace hcs {
@@ -319,6 +328,7 @@ static void upload_geom(hcs_ctx *c, GeomHost &g)
 			d.tet_field = dalloc<TetField>(g.allocs, d.n_elems);
 			d.tet_leaf32 = dalloc<TetLeaf32>(g.allocs, d.n_elems);
 			d.tet_leafss32 = dalloc<TetLeafSS32>(g.allocs, d.n_elems);
+			d.tet_box32 = dalloc<TetBox32>(g.allocs, d.n_elems);
 			d.nodes = dalloc<BvhNode>(g.allocs, std::max(1, d.n_elems - 1));
 			BvhNode root;
 			if (d.n_elems < 2 || std::getenv("HCS_LBVH_HOST")) { // host builder: single-tet trees and cross-checks
@@ -456,13 +466,14 @@ static void build_pairs(hcs_ctx *c)
 				P.slice_q  = (P.nq + (1 << TRI_SLICE_BITS) - 1) >> TRI_SLICE_BITS;
 				P.n_slices = (P.nq + P.slice_q - 1) / P.slice_q;
 			}
-			size_t units = (size_t)n_env * P.n_slices;
-			P.partial    = dalloc<SlicePartial>(c->step_allocs, units);
+			if (P.nq > (1 << 24) || P.n_tree > (int)ITEM_LIMIT)
+				throw std::runtime_error("geom pair too large: at most 2^24 query elements and 2^26 tree elements");
 			{
-				// ONE candidate pool per pair for the whole batch (flat list + per-candidate contributions, 97 B per
-				// entry).  Default size: per environment min(nq * n_tree, 16 (nq + n_tree)) candidates, at most 64 M
-				// entries; hcs_config.max_candidates_per_slice > 0 sizes it as that many per (env, slice) unit
-				// instead, HCS_MAX_TOTAL_CANDIDATES overrides both.  Overflow is reported by hcs_step, never UB.
+				size_t units = (size_t)n_env * P.n_slices;
+				// ONE candidate list per pair for the whole batch (16-byte records + 1 byte each).  Default size: per
+				// environment min(nq * n_tree, 16 (nq + n_tree)) candidates, at most 64 M entries;
+				// hcs_config.max_candidates_per_slice > 0 sizes it as that many per (env, slice) unit instead,
+				// HCS_MAX_TOTAL_CANDIDATES overrides both.  Overflow is reported by hcs_step, never UB.
 				// (half-space pairs: the candidates are the tets the plane cuts, at most all of them)
 				long per_env = P.kind == PAIR_SOFT_PLANE ? (long)P.nq :
 				                                           std::min<long>((long)P.nq * P.n_tree, 16L * ((long)P.nq + P.n_tree));
@@ -476,19 +487,30 @@ static void build_pairs(hcs_ctx *c)
 					total = v;
 				}
 				P.contrib_cap = (int)std::max<long>(1024, std::min<long>(total, 1L << 30));
-				P.range_cap   = (int)std::min<long>((long)units + P.contrib_cap / 128 + 64, 1L << 30);
 				P.flat        = dalloc<uint4>(c->step_allocs, (size_t)P.contrib_cap);
-				P.contrib     = dalloc<double>(c->step_allocs, (size_t)10 * P.contrib_cap); // 80-byte records
 				P.nverts      = dalloc<uint8_t>(c->step_allocs, (size_t)P.contrib_cap);
-				P.unit_range  = dalloc<int4>(c->step_allocs, units);
-				P.ranges      = dalloc<int4>(c->step_allocs, (size_t)P.range_cap);
-				P.unit_count  = dalloc<int32_t>(c->step_allocs, units);
-				P.unit_evals  = dalloc<int32_t>(c->step_allocs, units);
+				P.accum       = dalloc<int64_t>(c->step_allocs, (size_t)n_env * ACC_WORDS);
+				{
+					// Power-of-two scale of the exact accumulators (hcs_internal.h): the pair's force scale is modulus x
+					// contact area bound (pi R^2 of the smaller geom); torques and area moments about the world origin get
+					// 2^10 m of lever arm, and 2^14 on top of that is left for dissipation factors and rough estimates.
+					const double inf = std::numeric_limits<double>::infinity();
+					double E = std::min(A.E(), B.E());
+					if (!(E > 0) || E == inf)
+						E = 1.0;
+					double R = A.dev.bound_r;
+					if (B.dev.bound_r < R && B.dev.bound_r > 0)
+						R = B.dev.bound_r;
+					const double F0 = std::max(E, 1.0) * M_PI * R * R * 1024.0;
+					int k = 0;
+					std::frexp(F0, &k); // F0 < 2^k
+					k -= 12;
+					P.acc_scale   = std::ldexp(1.0, -k);
+					P.acc_unscale = std::ldexp(1.0, k);
+				}
 				P.counters    = c->d_counters + 6 + PAIR_COUNTERS * pi;
 				P.pair_ctx    = dalloc<double>(c->step_allocs, (size_t)n_env * PAIR_CTX_DOUBLES);
-				CK(cudaMemsetAsync(P.unit_range, 0, units * sizeof(int4), c->stream));
-				CK(cudaMemsetAsync(P.unit_count, 0, units * sizeof(int32_t), c->stream));
-				CK(cudaMemsetAsync(P.unit_evals, 0, units * sizeof(int32_t), c->stream));
+				CK(cudaMemsetAsync(P.accum, 0, (size_t)n_env * ACC_WORDS * sizeof(int64_t), c->stream)); // the finalize kernel keeps them zero
 			}
 		}
 		c->pair_desc.push_back(P);
@@ -794,15 +816,9 @@ static void step_device(hcs_ctx *c, const double *xpos, const double *xmat, cons
 	CK(cudaMemsetAsync(c->d_counters, 0, c->n_counters * sizeof(int32_t), s)); // flags, pool counts, flat-list counters
 	if (prof)
 		CK(cudaEventRecord(c->ev[1], s));
-	int list_slices = 0, list_units = 0, n_active = 0; // most slices among the pairs; their (pair, slice) units per env
-	bool small_units = true;
+	int n_active = 0;
 	for (const PairDesc &P : c->pair_desc)
-		if (P.kind != PAIR_NONE) {
-			++n_active;
-			list_slices = std::max(list_slices, P.n_slices);
-			list_units += P.n_slices;
-			small_units = small_units && std::min(P.nq, P.n_tree) <= 256;
-		}
+		n_active += P.kind != PAIR_NONE;
 	// Scenes with several pairs: each pair's broadphase -> narrowphase chain goes to one of N_AUX side streams, so
 	// the pairs' kernels overlap (launch latencies, ramp-up and tails of one pair are filled by the others) instead
 	// of running as 2 x n_pairs serialised launches; the main stream joins them before the finalize.  With stage
@@ -842,7 +858,7 @@ static void step_device(hcs_ctx *c, const double *xpos, const double *xmat, cons
 		if (prof)
 			CK(cudaEventRecord(c->ev[3], s));
 	}
-	k += launch_finalize(c->d_pairs, io, list_slices, list_units, small_units, s, /*chained=*/!prof && !forked);
+	k += launch_finalize(c->d_pairs, io, s, /*chained=*/!prof && !forked);
 	if (prof)
 		CK(cudaEventRecord(c->ev[4], s));
 	if (with_sensors) {
@@ -856,6 +872,7 @@ static void step_device(hcs_ctx *c, const double *xpos, const double *xmat, cons
 		CK(cudaEventRecord(c->ev[5], s));
 	CK(cudaGetLastError());
 	c->kernels_last_step = k;
+	c->step_counter++;
 	c->results_on_host = c->pairs_on_host = c->sensors_on_host = false;
 	c->last_with_sensors                   = with_sensors != 0;
 }
@@ -912,6 +929,11 @@ static int check_flags(hcs_ctx *c)
 		c->err = "candidate pool overflow: raise hcs_config.max_candidates_per_slice (average candidates per (env, slice) unit) "
 		         "or HCS_MAX_TOTAL_CANDIDATES (entries per pair)";
 		return HCS_E_CAPACITY;
+	}
+	if (c->h_flags[0] & 16) {
+		c->err = "a contact polygon's contribution (force, torque, area) was not finite or beyond 2^26 SI units: the exact "
+		         "accumulators cannot hold it (check poses and velocities for NaN / infinity)";
+		return HCS_E_INVALID;
 	}
 	return HCS_OK;
 }
@@ -1578,47 +1600,42 @@ int hcs_get_emitted(hcs_ctx *c, int env, int pair, int32_t *out, int cap)
 	const PairDesc &P = c->pair_desc[pair];
 	if (P.kind == PAIR_NONE)
 		return 0;
-	int n = 0;
-	auto put = [&](int eA, int eB, int nv) {
-		if (n < cap && out) {
-			out[3 * n]     = P.sign > 0 ? eA : eB;
-			out[3 * n + 1] = P.sign > 0 ? eB : eA;
-			out[3 * n + 2] = nv;
-		}
-		++n;
-	};
-	// walk the range chains of the env's units: first range inline, further ranges in the pool
-	std::vector<int4> heads(P.n_slices), pool;
-	int32_t used[PAIR_COUNTERS] = { 0, 0, 0, 0 };
-	CK(cudaMemcpyAsync(heads.data(), P.unit_range + (size_t)env * P.n_slices, P.n_slices * sizeof(int4),
-	                   cudaMemcpyDeviceToHost, c->stream));
-	CK(cudaMemcpyAsync(used, P.counters, sizeof used, cudaMemcpyDeviceToHost, c->stream));
-	CK(cudaStreamSynchronize(c->stream));
-	pool.resize(std::min(std::max(used[3], 0), P.range_cap));
-	if (!pool.empty()) {
-		CK(cudaMemcpyAsync(pool.data(), P.ranges, pool.size() * sizeof(int4), cudaMemcpyDeviceToHost, c->stream));
+	// The pair's flat candidate list of the last step holds the whole batch in no particular order: it is copied once
+	// per step and indexed by environment, so that asking for every environment in turn costs one copy.
+	if (c->emitted_cache.size() != c->pairs.size())
+		c->emitted_cache.assign(c->pairs.size(), EmittedCache());
+	EmittedCache &E = c->emitted_cache[pair];
+	if (E.step != c->step_counter) {
+		int32_t used[PAIR_COUNTERS] = { 0, 0, 0, 0 };
+		CK(cudaMemcpyAsync(used, P.counters, sizeof used, cudaMemcpyDeviceToHost, c->stream));
 		CK(cudaStreamSynchronize(c->stream));
-	}
-	std::vector<uint4> cand;
-	std::vector<uint8_t> nv;
-	for (int s = 0; s < P.n_slices; ++s) {
-		for (int4 rg = heads[s]; rg.y > 0;) {
-			int cnt = std::min(rg.y, P.contrib_cap - rg.x);
-			if (cnt > 0) {
-				cand.resize(cnt);
-				nv.resize(cnt);
-				CK(cudaMemcpyAsync(cand.data(), P.flat + rg.x, cnt * sizeof(uint4), cudaMemcpyDeviceToHost, c->stream));
-				CK(cudaMemcpyAsync(nv.data(), P.nverts + rg.x, cnt, cudaMemcpyDeviceToHost, c->stream));
-				CK(cudaStreamSynchronize(c->stream));
-				for (int i = 0; i < cnt; ++i)
-					if ((nv[i] & 15) >= 3) // the high nibble holds the polygon's force-point count
-						put((int)cand[i].y, (int)cand[i].x, nv[i] & 15); // (tree element of A, query element of B)
-			}
-			if (rg.z < 0 || rg.z >= (int)pool.size())
-				break;
-			rg = pool[rg.z];
+		const int total = std::min(std::max(used[0], 0), P.contrib_cap);
+		std::vector<uint4> flat(total);
+		std::vector<uint8_t> nv(total);
+		if (total > 0) {
+			CK(cudaMemcpyAsync(flat.data(), P.flat, (size_t)total * sizeof(uint4), cudaMemcpyDeviceToHost, c->stream));
+			CK(cudaMemcpyAsync(nv.data(), P.nverts, (size_t)total, cudaMemcpyDeviceToHost, c->stream));
+			CK(cudaStreamSynchronize(c->stream));
 		}
+		E.offset.assign((size_t)c->cfg.n_envs + 1, 0);
+		for (int i = 0; i < total; ++i)
+			if ((nv[i] & 15) >= 3 && (int)flat[i].z < c->cfg.n_envs)
+				E.offset[flat[i].z + 1]++;
+		for (int e = 0; e < c->cfg.n_envs; ++e)
+			E.offset[e + 1] += E.offset[e];
+		E.triples.assign(3 * (size_t)E.offset[c->cfg.n_envs], 0);
+		std::vector<int> cur(E.offset.begin(), E.offset.end() - 1);
+		for (int i = 0; i < total; ++i)
+			if ((nv[i] & 15) >= 3 && (int)flat[i].z < c->cfg.n_envs) {
+				const int eA = (int)(flat[i].y & CAND_ELEM_MASK), eB = (int)flat[i].x; // (tree element of A, query element of B)
+				int32_t *o = &E.triples[3 * (size_t)cur[flat[i].z]++];
+				o[0] = P.sign > 0 ? eA : eB, o[1] = P.sign > 0 ? eB : eA, o[2] = nv[i] & 15;
+			}
+		E.step = c->step_counter;
 	}
+	const int n = E.offset[env + 1] - E.offset[env];
+	if (out && cap > 0 && n > 0)
+		memcpy(out, &E.triples[3 * (size_t)E.offset[env]], (size_t)std::min(n, cap) * 3 * sizeof(int32_t));
 	return n;
 	API_END(c)
 }
@@ -1644,7 +1661,7 @@ int hcs_get_tactile_triangles(hcs_ctx *c, int env, double *out, int cap)
 		if (t.env == env)
 			mine.push_back(&t);
 	std::sort(mine.begin(), mine.end(), [](const TactileTri *a, const TactileTri *b) {
-		return a->pair_slice != b->pair_slice ? a->pair_slice < b->pair_slice : a->idx8 < b->idx8;
+		return a->key_hi != b->key_hi ? a->key_hi < b->key_hi : a->key_lo < b->key_lo;
 	});
 	int m = 0;
 	for (const TactileTri *t : mine) {

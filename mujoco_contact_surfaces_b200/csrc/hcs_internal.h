@@ -37,6 +37,10 @@ struct __align__(32) TetLeafSS32 { // 96 B: float copy of what the soft-soft lea
 	float v[4][3];
 	float pad2[4];
 };
+struct __align__(32) TetBox32 { // 32 B: the tet's box in the geom frame, rounded outward (broadphase sweep of small geoms)
+	float lo[3], hi[3];
+	float pad[2];
+};
 struct __align__(32) TriRec { // 96 B = 3 x 32 B: rigid triangle vertices + unit normal
 	double v[3][3];
 	double n[3];
@@ -57,6 +61,7 @@ struct GeomDev {
 	TetField *tet_field;
 	TetLeaf32 *tet_leaf32;
 	TetLeafSS32 *tet_leafss32;
+	TetBox32 *tet_box32;
 	TriRec *tris;       // rigid
 	BvhNode *nodes;     // soft: LBVH over tets (root = node 0)
 	double bound_c[3];  // bounding sphere in the geom frame
@@ -66,20 +71,34 @@ struct GeomDev {
 
 enum PairKind { PAIR_NONE = 0, PAIR_SOFT_RIGID = 1, PAIR_SOFT_PLANE = 2, PAIR_SOFT_SOFT = 3 };
 
-struct SlicePartial { // one warp's deterministic partial sums
-	double F[3], tau[3], area, ac[3];
-	int32_t n_polygons, n_faces, n_points, n_candidates, n_clipped, pad;
-};
-
 struct TactileTri { // kTriangle contact-surface triangle handed to the tactile stage (72 B)
 	float v[9];
 	int32_t env;
 	double e[3];
-	uint32_t pair_slice; // pair << TRI_SLICE_BITS | slice of the emitting unit
-	uint32_t idx8;       // (candidate index inside the unit, or tet index for half-space pairs) * 8 + fan triangle
-	// (pair_slice, idx8) is a deterministic total order of the triangles of one environment
+	uint32_t key_hi; // pair << TRI_PAIR_SHIFT | query element >> 2
+	uint32_t key_lo; // (query element & 3) << 30 | tree element << 3 | fan triangle
+	// (key_hi, key_lo) = (pair, query element of B, tree element of A, fan triangle) is a canonical total order of the
+	// triangles of one environment: it does not depend on the order in which candidates were found or clipped
 };
-constexpr int TRI_SLICE_BITS = 20; // <= 2^20 slices per pair and env, <= 2^12 pairs
+constexpr int TRI_PAIR_SHIFT = 22;   // <= 2^10 pairs, <= 2^24 query elements, <= 2^27 tree elements
+constexpr int TRI_SLICE_BITS = TRI_PAIR_SHIFT; // (name kept for the pair-count limit in hcs_set_pairs)
+
+// ---- exact per-(env, pair) accumulators ------------------------------------------------------------------
+// Every contribution of a contact polygon (F, tau, area, area * centroid) is added to its (env, pair) record as a
+// two-limb fixed-point integer (hi: units of 2^-36, lo: units of 2^-80 of the SI value) with 64-bit integer atomics.
+// Integer addition is associative and commutative, so the sums do not depend on the order in which candidates are
+// found, clipped or added: results are bit-reproducible whatever the batch composition, grid size or scheduling, without
+// any ordered per-candidate records.  Range: |scaled sum| < 2^26, resolution 2^-80, up to 2^19 contributions per
+// record before the low limb could overflow.
+// Per pair the values are first scaled by a power of two (PairDesc::acc_scale, exact) chosen from the pair's size and
+// stiffness, so that the range follows the scene: metres and newtons, or millimetre fingertips, or a 1000x model.
+constexpr int ACC_LIMBS = 20;   // 10 components x (hi, lo)
+constexpr int ACC_COUNTS = 20;  // faces (bits 0..21) | polygons (22..42) | force points (43..63) of the pair's surface
+constexpr int ACC_NCLIPPED = 21; // candidates that reached the clipper
+constexpr int ACC_NEVALS = 22;  // pair-evals started in the broadphase: LBVH leaf hits / tets classified
+constexpr int ACC_WORDS = 24;   // int64 words per (env, pair) record (192 B)
+constexpr int ACC_POLY_SHIFT = 22, ACC_POINT_SHIFT = 43;
+constexpr double ACC_HI_SCALE = 0x1p36, ACC_LO_SCALE = 0x1p80;
 
 // Everything a step kernel needs to know about one configured geom pair (passed by value).
 struct PairDesc {
@@ -94,26 +113,22 @@ struct PairDesc {
 	int n_slices, slice_q;
 	int emit_tactile;    // pair touches a sensor geom and representation is kTriangle
 	GeomDev A, B;
-	SlicePartial *partial; // [n_env * n_slices] per-unit sums (K5 writes them directly, K7 for candidate lists)
-	uint8_t *nverts;       // polygon vertex count: half-space pairs [n_env][tet]; candidate lists [contrib_cap] by
-	                       // flat index, with the number of force points of the polygon in the high nibble
-	// ---- candidate lists (soft-rigid, soft-soft): ONE flat list per pair for the whole batch.  A broadphase warp
-	// stages its (env, slice) unit's candidates in shared memory and appends them in ranges of whole 32-candidate
-	// chunks; a unit's ranges are linked in emission order.  Nothing is sized per unit, so a few coarse query
-	// elements overlapping a large share of a fine tree cannot overflow a per-unit slab.
-	uint4 *flat;           // [contrib_cap] (query element, tree element, unit, index inside the unit)
-	double *contrib;       // [contrib_cap][10] per-candidate F, tau, area, area*centroid (80-byte records)
+	uint8_t *nverts;       // [contrib_cap] polygon vertex count of flat-list candidate g (diagnostics: hcs_get_emitted)
+	// ---- candidates (all three pair kinds): ONE flat list per pair for the whole batch, in no particular order.  A
+	// broadphase warp stages the candidates of its units in shared memory and appends them with one atomicAdd.
+	uint4 *flat;           // [contrib_cap] (query element, tree element | skip mask << 28, env, 0)
 	int contrib_cap;
-	int4 *unit_range;      // [n_env * n_slices] first range of the unit {base, n, next range or -1, 0}
-	int4 *ranges;          // [range_cap] further ranges
-	int range_cap;
-	int32_t *unit_count;   // [n_env * n_slices] candidates that survived the early-outs (need clipping)
-	int32_t *unit_evals;   // [n_env * n_slices] LBVH leaf hits = pair-evals started in the broadphase
+	int64_t *accum;        // [n_env][ACC_WORDS] exact accumulators (above), zero between steps (the finalize kernel
+	                       // clears what it has read)
+	double acc_scale, acc_unscale; // 2^-k / 2^k: contributions are scaled into the accumulators' range (exact)
 	int32_t *counters;     // [0] candidates in the flat list, [1] next 32-candidate chunk of the narrowphase,
-	                       // [2] next (env, slice) unit of the broadphase, [3] ranges used; zeroed per step
+	                       // [2] next (env, slice) unit of the broadphase, [3] -; zeroed per step
 	double *pair_ctx;      // [n_env][PAIR_CTX_DOUBLES] poses, velocities, X_AB written by the broadphase
 };
 constexpr int PAIR_COUNTERS = 4;
+// candidate record .y = tree element | skip mask << 28: planes of the tet the clip may leave out (narrow.cuh cand_tet_tri)
+constexpr int CAND_MASK_SHIFT      = 28;
+constexpr unsigned CAND_ELEM_MASK  = (1u << CAND_MASK_SHIFT) - 1u;
 
 constexpr int PAIR_CTX_DOUBLES = 48;
 // layout of one context block, in 32-byte groups: R_WA[9] xA[3] | R_AB[9] p_AB[3] | wA[3] - | vA[3] - | xB[3] - | wB[3] - |
@@ -126,7 +141,8 @@ struct StepIO {
 	int n_sms; // SMs of the device: persistent grids are sized in multiples of it
 	const double *xpos, *xmat, *vel;
 	int representation, apply_forces;
-	int32_t *flags;          // [0] capacity overflow bits, [1] traversal stack overflow
+	int32_t *flags;          // [0] capacity overflow bits (16: a contribution was not finite or out of the accumulators'
+	                         // range), [1] broadphase queue overflow
 	hcs_face *faces;         // optional per-face dump
 	int32_t *face_count;
 	int max_faces;
@@ -211,6 +227,21 @@ struct TaxelDev {
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_release() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
+// Opt a kernel in to its dynamic shared memory size once per device (contexts may live on several devices; the call
+// costs a microsecond or two of host time, which the end-to-end path of small steps notices).
+template <class K>
+static inline void ensure_dynamic_smem(K kernel, int bytes)
+{
+	static int done[64] = { 0 };
+	int dev = 0;
+	cudaGetDevice(&dev);
+	if (dev < 0 || dev >= 64 || done[dev] < bytes) {
+		cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+		if (dev >= 0 && dev < 64)
+			done[dev] = bytes;
+	}
+}
+
 template <class... KArgs, class... Args>
 static inline void launch_chained(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args... args)
 {
@@ -239,10 +270,8 @@ void launch_build_lbvh(const GeomDev &g, const double glo[3], const double ghi[3
 void launch_broadphase(const PairDesc &P, const StepIO &io, cudaStream_t s);
 // chained: the kernel directly behind it in the stream is the one whose output it consumes (launch_chained above)
 void launch_narrowphase(const PairDesc &P, const StepIO &io, cudaStream_t s, bool chained);
-// returns the number of kernels launched
-// small_units: every candidate-list pair has few elements on one side (units hold tens of candidates, not thousands)
-int launch_finalize(const PairDesc *d_pairs, const StepIO &io, int max_list_slices, int list_units_per_env,
-                    bool small_units, cudaStream_t s, bool chained);
+// pair results and per-geom wrenches from the exact accumulators; returns the number of kernels launched
+int launch_finalize(const PairDesc *d_pairs, const StepIO &io, cudaStream_t s, bool chained);
 
 // clear, count, scan, fill, rasterise for all sensors (host copy + device copy of the records); returns the number
 // of kernels launched

@@ -1,18 +1,27 @@
-// K3 broadphase — warp-cooperative LBVH traversal with shared-memory work queues (sm_100a).
+// K3 broadphase — warp-cooperative LBVH traversal with work queues POOLED over several units (sm_100a).
 //
 // Replaces Bvh<Obb,.>::Collide inside the Drake queries the reference calls at
-// mujoco_contact_surfaces_plugin.cpp:284-303 (candidate generation), and hoists the two exact early-outs
-// of mesh_intersection.cc into the traversal so the clipping kernel only sees pairs that need clipping:
-//   * IsFaceNormalAlongPressureGradient:  ghat . (R_SR n) > cos(5 pi / 8)
-//   * trivial reject: all three triangle vertices strictly outside one tet half space (then the
-//     Sutherland-Hodgman clip is empty; a 1e-12 margin keeps the decision identical to the clip's).
+// mujoco_contact_surfaces_plugin.cpp:284-303 (candidate generation), and hoists the early-outs of
+// mesh_intersection.cc / field_intersection.cc into the traversal so that the clipping kernel only sees pairs that need
+// clipping:
+//   * IsFaceNormalAlongPressureGradient / IsPlaneNormalAlongPressureGradient:  ghat . n > cos(5 pi / 8)  (a semantic
+//     filter: decided in float only when clear, otherwise by the reference's fp64 expression);
+//   * trivial rejects of pairs that clip to nothing (conservative float filter): all triangle
+//     vertices outside one tet half space; all tet vertices on one side of the triangle's / the equal-pressure plane;
+//     new in round 2, all tet vertices outside the plane through a triangle EDGE along the triangle normal;
+//   * new in round 2: a 4-bit mask of tet planes that cannot cut the triangle, which the clip then skips.
 //
-// One warp owns one (env, pair, query slice).  Lane-per-query traversal left 3 of 32 lanes busy on the
-// sphere-on-box scene (most query triangles die at the root), so the warp instead shares two LIFO queues
-// in shared memory:  node items (query, internal node) and leaf items (query, tet).  Every iteration all
-// lanes pop one item each; children / survivors are appended with warp-ballot + popc prefix sums, which
-// also makes the emitted candidate order deterministic (no atomics anywhere).
+// One warp owns one (env, pair, query slice) unit.  Lane-per-query traversal left 3 of 32 lanes busy on the sphere-on-box
+// scene (most query triangles die at the root), so the warp shares two LIFO queues in shared memory: node items (query
+// slot, internal node) and leaf items (query slot, tet).  Every iteration all lanes pop one item each; children /
+// survivors are appended with warp-ballot + popc prefix sums.
+// Tried in round 2 and dropped (profiles/r02_notes.md): pooling the queues of several units in one warp (more lanes per
+// iteration, fewer warps: C1 x 4096 broadphase 49 / 45 / 55 / 88 us for 1 / 2 / 4 / 8 units per warp: the kernel is bound
+// by the latency of its dependent pop -> load -> test -> push chain at 16 warps per SM, not by lanes), sub-warp groups
+// in lockstep (a group waits for the slowest of its warp), a flat sweep instead of the walk for 128-tet trees.
+// Candidates leave in no particular order: nothing downstream depends on it (exact accumulators, hcs_internal.h).
 #include <algorithm>
+#include <type_traits>
 
 #include "dmath.cuh"
 #include "hcs_internal.h"
@@ -21,107 +30,63 @@
 namespace hcs {
 
 #define FULL_MASK 0xffffffffu
-#ifndef HCS_BP_CTAS_PER_SM // tuning sweeps (build.py HCS_NVCC_DEFS); 4 -> 127 registers, 6 -> 80 registers + spills
+#ifndef HCS_BP_CTAS_PER_SM
 #define HCS_BP_CTAS_PER_SM 4
-#endif
-#ifndef HCS_BP_PERSISTENT
-#define HCS_BP_PERSISTENT 1
-#endif
-// Node iterations with <= 16 items popped with two lanes per item (one per child).  Measured and off
-// (scripts/sweep_r01h.sh): C1 broadphase 0.0450 -> 0.0455 ms, C5 17.9 -> 18.4 ms, C3 0.795 -> 0.760 ms; the
-// iterations are bound by their dependent chain (queue pop -> node load -> ballots -> push), not by the box tests.
-#ifndef HCS_BP_PAIRED_POP
-#define HCS_BP_PAIRED_POP 0
-#endif
-#ifndef HCS_BP_NODE256
-#define HCS_BP_NODE256 0
-#endif
-#ifndef HCS_BP_LEAF32 // soft-rigid leaf test: conservative float filter in front of the exact fp64 early-outs
-#define HCS_BP_LEAF32 1
 #endif
 constexpr int BP_CTAS_PER_SM = HCS_BP_CTAS_PER_SM;
 constexpr int BP_WARPS = 4;
 constexpr int BP_BLOCK = 32 * BP_WARPS;
-constexpr int NODE_Q   = 768; // LIFO of (query slot, node); grows by <= 32 per iteration
-constexpr int LEAF_Q   = 128; // (query slot, tet); drained in batches of 32
-constexpr int STAGE    = 256; // staged candidates per warp; flushed in whole 32-candidate chunks when nearly full
+constexpr int BP_SLOTS = 32;  // alive-query slots per warp: one batch
+constexpr int NODE_Q   = 768; // LIFO of (slot, node); grows by <= 32 per iteration
+constexpr int LEAF_Q   = 256; // (slot, tet); drained in batches of 32
+constexpr int STAGE    = 256; // staged candidates per warp
+// Prism test in the soft-rigid leaf filter (below).  Measured and OFF: it removes 20-29 % of the candidates that reach the
+// clipper (C1 47.1 -> 37.5 per env, C5 93.4 k -> 66.5 k) but costs the leaf test ~35 warp instructions per drain:
+// C1 broadphase +4 us / narrowphase -4 us, C5 broadphase +41 % instructions (+6 ms at 1024 envs) / narrowphase -2.3 ms
+// (profiles/r02_notes.md).
+#ifndef HCS_BP_PRISM_TEST
+#define HCS_BP_PRISM_TEST 0
+#endif
+// Mask of tet planes the clip may skip (all triangle vertices strictly inside): measured and OFF, the narrowphase did
+// not get faster (C1 0.0540 vs 0.0544 ms) and the leaf test pays ~16 instructions per hit for it.
+#ifndef HCS_BP_SKIP_MASK
+#define HCS_BP_SKIP_MASK 0
+#endif
+#ifndef HCS_SWEEP_MAX_TREE
+#define HCS_SWEEP_MAX_TREE 32
+#endif
+constexpr int SWEEP_MAX_TREE = HCS_SWEEP_MAX_TREE; // trees up to this many tets are swept instead of walked
 
-constexpr int ITEM_SHIFT = 27; // queue item = query slot (5 bits) << 27 | node or tet index (27 bits)
+constexpr int ITEM_SHIFT = 26; // queue item = slot (6 bits) << 26 | node or tet index (26 bits)
 constexpr unsigned ITEM_MASK = (1u << ITEM_SHIFT) - 1u;
 
+// QF = floats kept per query (9: triangle vertices, 12: tet vertices), QX = extra rows (soft-soft)
+template <int QF, int QX>
 struct __align__(16) WarpQueues {
 	unsigned nodeq[NODE_Q];
 	unsigned leafq[LEAF_Q];
-	double qv[12][32];  // transformed query vertices (tri: 9 + rotated normal 3; tet: 12), lane-interleaved
-	float qbox[6][32];
-	float qpl[4][32]; // soft-rigid: the query triangle's plane (unit normal, offset) in A's frame;
-	                  // soft-soft: the query tet's pressure gradient in A's frame (0..2), its field at A's origin (3)
-	float qvf[12][32]; // the query's vertices in A's frame, rounded to float (leaf filters)
-	float qm[32];     // soft-rigid: the filter's margin for this query (4e-6 x the largest coordinate involved);
-	                  // soft-soft: the largest coordinate involved
-	float qx[4][32];  // soft-soft: the query tet's unit gradient in A's frame (0..2), L1 norm of its gradient (3)
-	int qid[32];
-	uint2 stage[STAGE]; // surviving (query, tet) candidates waiting to be appended to the pair's flat list
+	float qbox[6][BP_SLOTS];
+	float qpl[4][BP_SLOTS];  // soft-rigid: the query triangle's plane (unit normal, offset) in A's frame;
+	                         // soft-soft: the query tet's pressure gradient in A's frame (0..2), its field at A's origin (3)
+	float qvf[QF][BP_SLOTS]; // the query's vertices in A's frame, rounded to float (leaf filters)
+	float qm[BP_SLOTS];      // soft-rigid: the filter's margin (4e-6 x the largest coordinate involved); soft-soft: that coordinate
+	float qx[QX > 0 ? QX : 1][BP_SLOTS]; // soft-soft: the query tet's unit gradient in A's frame (0..2), L1 norm of its gradient (3)
+	int qid[BP_SLOTS];
+	uint2 stage[STAGE];  // (query, tet | skip << 28) waiting to be appended to the pair's flat list
+	double xab[12];      // R_AB (row-major) + p_AB of the unit, for the exact fallbacks of the leaf tests
+	double pba[4];       // origin of A in B (p_NMo of field_intersection.cc)
 };
-static_assert(sizeof(WarpQueues) * BP_WARPS <= 48 * 1024, "static shared memory of a broadphase CTA");
+typedef WarpQueues<9, 0> QueuesRigid;
+typedef WarpQueues<12, 4> QueuesSoft;
 
-// Append the first n_flush staged candidates (a multiple of 32 except at the end of the unit) to the pair's flat
-// list as one range and link the range to the unit's chain.  WHERE the range lands depends on the order in which
-// warps get here; results do not: every record carries (unit, index inside the unit), contributions are read back
-// per unit along the chain, in index order.  `last`: -2 no range yet, -1 the inline first range, >= 0 pool range.
-__device__ __forceinline__ void flush_stage(const PairDesc &P, const StepIO &io, WarpQueues &W, int unit, int lane,
-                                            int n_flush, int &n_stage, int &i0, int &last)
-{
-	int base = 0;
-	if (lane == 0) {
-		base     = atomicAdd(P.counters, n_flush);
-		int4 rec = make_int4(base, n_flush, -1, 0);
-		if (last == -2) {
-			P.unit_range[unit] = rec;
-			last               = -1;
-		} else {
-			int r = atomicAdd(P.counters + 3, 1);
-			if (r < P.range_cap) {
-				P.ranges[r] = rec;
-				if (last == -1)
-					P.unit_range[unit].z = r;
-				else
-					P.ranges[last].z = r;
-				last = r;
-			} else {
-				atomicOr(io.flags, 8);
-			}
-		}
-	}
-	base = __shfl_sync(FULL_MASK, base, 0);
-	for (int j = lane; j < n_flush; j += 32)
-		if (base + j < P.contrib_cap) {
-			uint2 cd         = W.stage[j];
-			P.flat[base + j] = make_uint4(cd.x, cd.y, (unsigned)unit, (unsigned)(i0 + j));
-		}
-	__syncwarp();
-	int rem    = n_stage - n_flush; // < 32: slides to the front
-	uint2 keep = make_uint2(0, 0);
-	if (lane < rem)
-		keep = W.stage[n_flush + lane];
-	__syncwarp();
-	if (lane < rem)
-		W.stage[lane] = keep;
-	__syncwarp();
-	i0 += n_flush;
-	n_stage = rem;
-}
+extern __shared__ __align__(16) unsigned char bp_smem[];
 
 // Box overlap of the query with one child of a node; for triangle queries (PLANE) the child box must also
 // straddle the triangle's plane: a subtree entirely on one side of that plane cannot meet the triangle.
-// The single-interior-vertex sphere tets are slivers whose boxes all overlap a large rigid triangle's box;
-// the plane test prunes those whole subtrees (profiles/r01_notes.md).
 template <bool PLANE>
-__device__ __forceinline__ bool box_overlap(const float *q, const float *pl, float4 a, float4 b, float4 c, bool left)
+__device__ __forceinline__ bool child_overlap(const float *q, const float *pl, float lo0, float lo1, float lo2, float hi0,
+                                              float hi1, float hi2)
 {
-	// node layout: llo[3] lhi[3] rlo[3] rhi[3]
-	float lo0 = left ? a.x : b.z, lo1 = left ? a.y : b.w, lo2 = left ? a.z : c.x;
-	float hi0 = left ? a.w : c.y, hi1 = left ? b.x : c.z, hi2 = left ? b.y : c.w;
 	bool hit = q[0] <= hi0 && q[3] >= lo0 && q[1] <= hi1 && q[4] >= lo1 && q[2] <= hi2 && q[5] >= lo2;
 	if (PLANE && hit) {
 		float cx = 0.5f * (lo0 + hi0), cy = 0.5f * (lo1 + hi1), cz = 0.5f * (lo2 + hi2);
@@ -134,9 +99,9 @@ __device__ __forceinline__ bool box_overlap(const float *q, const float *pl, flo
 	return hit;
 }
 
-// per (env, pair) context block read by the flat narrowphase (layout: hcs_internal.h)
-__device__ __forceinline__ void write_pair_ctx(const PairDesc &P, const StepIO &io, int env, const Xform &X_WA,
-                                               const Xform &X_WB, const Xform &X_AB, D3 p_BAo)
+// per (env, pair) context block read by the narrowphase (layout: hcs_internal.h)
+__device__ __forceinline__ void write_pair_ctx(const PairDesc &P, const StepIO &io, int env, const Xform &X_WA, const Xform &X_WB,
+                                               const Xform &X_AB, D3 p_BAo)
 {
 	double *cb = P.pair_ctx + (size_t)env * PAIR_CTX_DOUBLES;
 	const double *velA = io.vel + ((size_t)env * io.n_geoms + P.gA) * 6;
@@ -159,563 +124,497 @@ __device__ __forceinline__ void write_pair_ctx(const PairDesc &P, const StepIO &
 	cb[CTX_WA + 3] = cb[CTX_VA + 3] = cb[CTX_XB + 3] = cb[CTX_WB + 3] = cb[CTX_VB + 3] = cb[CTX_PBA + 3] = 0.0;
 }
 
-// Soft geom against a rigid half space (the query the reference calls at plugin.cpp:298-299): every tet of the
-// unit's slice is classified against the plane, the tets it cuts become the unit's candidates.  On the mixed-objects
-// scene 13 % of the tets are cut: clipping them in the flat narrowphase keeps whole warps busy, where the
-// one-thread-per-tet kernel ran the whole slice-and-integrate path for the few cut tets of each 32-tet group.
-__device__ __forceinline__ void plane_unit(const PairDesc &P, const StepIO &io, WarpQueues &W, int warp, int lane)
+template <class Q>
+__device__ __forceinline__ Xform unit_xab(const Q &W)
 {
-	int env = warp / P.n_slices, slice = warp - env * P.n_slices;
-	Xform X_WA = load_pose(io.xpos, io.xmat, io.n_geoms, env, P.gA);
-	Xform X_WB = load_pose(io.xpos, io.xmat, io.n_geoms, env, P.gB);
-	Xform X_AB = invert_and_compose(X_WA, X_WB);
-	D3 p_BAo   = -rotT(X_AB.R, X_AB.p);
-	if (slice == 0 && lane == 0)
-		write_pair_ctx(P, io, env, X_WA, X_WB, X_AB, p_BAo);
-	// the half space in A's frame: normal = z column of R_AB, through p_AB (mesh_half_space_intersection.cc)
-	D3 n_S    = mk(X_AB.R[2], X_AB.R[5], X_AB.R[8]);
-	double pd = dot(n_S, X_AB.p);
-	int n_stage = 0, i0 = 0;
-	int last_range = -2;
-	const int q_begin = slice * P.slice_q, q_end = min(P.nq, q_begin + P.slice_q);
-	const unsigned lt_mask = (1u << lane) - 1u;
-	// the whole geom above the plane: nothing can be cut
-	bool above = dot(n_S, mk(P.A.bound_c[0], P.A.bound_c[1], P.A.bound_c[2])) - pd > P.A.bound_r + 1e-9;
-	// 32 consecutive tets = 32 x 96 bytes of vertices at a 128-byte stride.  Lane-per-record loads touch 32 lines per
-	// instruction; instead the warp reads the 96 groups of 32 bytes in index order (11 lines per instruction) and
-	// transposes them through shared memory (rows padded to 13 doubles: conflict-free column reads).
-	constexpr int ROW = 13;
-	double *rows      = reinterpret_cast<double *>(W.nodeq); // 32 x 13 doubles = 3328 B of the (unused) queues
-	static_assert(sizeof(W.nodeq) + sizeof(W.leafq) >= 32 * ROW * sizeof(double), "transpose buffer");
-	for (int q0 = q_begin; q0 < q_end && !above; q0 += 32) {
-		const int n_here = min(32, q_end - q0);
-		const double *base = reinterpret_cast<const double *>(P.A.tet_geom + q0);
+	Xform X;
 #pragma unroll
-		for (int k = 0; k < 3; ++k) {
-			int j = lane + 32 * k, r = j / 3, part = j - 3 * r; // group j = (record r, 32-byte part)
-			if (r < n_here) {
-				D4 gq     = ld4(base + 16 * r + 4 * part);
-				double *o = rows + ROW * r + 4 * part;
-				o[0] = gq.x, o[1] = gq.y, o[2] = gq.z, o[3] = gq.w;
-			}
-		}
-		__syncwarp();
-		int t     = q0 + lane;
-		bool keep = false;
-		if (t < q_end) {
-			const double *gv = rows + ROW * lane;
-			int code = 0;
+	for (int i = 0; i < 9; ++i)
+		X.R[i] = W.xab[i];
+	X.p = mk(W.xab[9], W.xab[10], W.xab[11]);
+	return X;
+}
+
+// ---- leaf tests ------------------------------------------------------------------------------------
+// Soft-rigid.  Conservative float filter: the exact tests it stands for are early-outs, i.e. a pair
+// they reject clips to nothing, so rejecting a SUBSET of those pairs changes no result, and a pair that slips through is
+// clipped (to nothing) by the narrowphase.  One 128-byte TetLeaf32 line per leaf hit; the margin qm = 4e-6 x (largest
+// coordinate involved) is > 5x the worst rounding of the float dot products and of the inputs' conversion.  NaNs compare
+// false and fall through.  Only the gradient cull is a semantic filter: it is decided in float when clear by 1e-5,
+// otherwise by the reference's fp64 expression.  s: slot of the query; skip: tet planes the clip may leave out.
+__device__ __forceinline__ bool leaf_test_rigid(const PairDesc &P, const QueuesRigid &W, int s, int tet, int &skip)
+{
+	skip = 0;
+	const TetLeaf32 *tl = P.A.tet_leaf32 + tet;
+	const F8 l0 = ld8f(tl, 0), l1 = ld8f(tl, 1), l2 = ld8f(tl, 2), l3 = ld8f(tl, 3);
+	const float nx = W.qpl[0][s], ny = W.qpl[1][s], nz = W.qpl[2][s], dtf = W.qpl[3][s], m = W.qm[s];
+	const float cosg = fdot3(l2.a[0], l2.a[1], l2.a[2], nx, ny, nz);
+	if (cosg < (float)HCS_COS_ALPHA - 1e-5f)
+		return false;
+	if (cosg < (float)HCS_COS_ALPHA + 1e-5f) { // undecided in float: the reference's expression in double
+		const TriVerts tr = load_tri(P.B.tris + W.qid[s]);
+		const Xform X_AB  = unit_xab(W);
+		if (!(dot(load_ghat(P.A.tet_field + tet), rot(X_AB.R, tr.n)) > HCS_COS_ALPHA))
+			return false;
+	}
+	const float ax = W.qvf[0][s], ay = W.qvf[1][s], az = W.qvf[2][s], bx = W.qvf[3][s], by = W.qvf[4][s], bz = W.qvf[5][s],
+	            cx = W.qvf[6][s], cy = W.qvf[7][s], cz = W.qvf[8][s];
+	const float pl[4][4] = { { l0.a[0], l0.a[1], l0.a[2], l0.a[3] }, { l0.a[4], l0.a[5], l0.a[6], l0.a[7] },
+		                     { l1.a[0], l1.a[1], l1.a[2], l1.a[3] }, { l1.a[4], l1.a[5], l1.a[6], l1.a[7] } };
+	bool keep = true;
+#pragma unroll
+	for (int f = 0; f < 4; ++f) {
+		float sa = fdot3(pl[f][0], pl[f][1], pl[f][2], ax, ay, az) - pl[f][3];
+		float sb = fdot3(pl[f][0], pl[f][1], pl[f][2], bx, by, bz) - pl[f][3];
+		float sc = fdot3(pl[f][0], pl[f][1], pl[f][2], cx, cy, cz) - pl[f][3];
+		if (sa > m && sb > m && sc > m)
+			keep = false;
+#if HCS_BP_SKIP_MASK
+		// The whole triangle is strictly inside this half space (by more than the float error): every polygon the clip
+		// builds consists of convex combinations of its vertices, signed distances are affine, so clipping by this plane
+		// would copy its input.  The narrowphase leaves that pass out (narrow.cuh cand_tet_tri).
+		if (sa < -m && sb < -m && sc < -m)
+			skip |= 1 << f;
+#endif
+	}
+	if (!keep)
+		return false;
+	// tet vertices: l2.a[4..7], l3.a[0..7]
+	const float tv[4][3] = { { l2.a[4], l2.a[5], l2.a[6] }, { l2.a[7], l3.a[0], l3.a[1] }, { l3.a[2], l3.a[3], l3.a[4] },
+		                     { l3.a[5], l3.a[6], l3.a[7] } };
+	float h0 = fdot3(nx, ny, nz, tv[0][0], tv[0][1], tv[0][2]) - dtf, h1 = fdot3(nx, ny, nz, tv[1][0], tv[1][1], tv[1][2]) - dtf;
+	float h2 = fdot3(nx, ny, nz, tv[2][0], tv[2][1], tv[2][2]) - dtf, h3 = fdot3(nx, ny, nz, tv[3][0], tv[3][1], tv[3][2]) - dtf;
+	if ((h0 > m && h1 > m && h2 > m && h3 > m) || (h0 < -m && h1 < -m && h2 < -m && h3 < -m))
+		return false;
+#if HCS_BP_PRISM_TEST
+	// Prism test (off by default, see HCS_BP_PRISM_TEST): the plane through a triangle edge e = q - p along the triangle normal n has the (unnormalised) outward
+	// normal me = e x n, |me| = |e|.  All four tet vertices beyond it by more than m |e|_1 (>= m |e|: the float error of
+	// the expression is < m |e| / 4) => tet and triangle are separated by that plane => the clip is empty.
+	{
+		const float px[3] = { ax, bx, cx }, py[3] = { ay, by, cy }, pz[3] = { az, bz, cz };
+#pragma unroll
+		for (int e = 0; e < 3; ++e) {
+			const int e1   = e == 2 ? 0 : e + 1;
+			const float ex = px[e1] - px[e], ey = py[e1] - py[e], ez = pz[e1] - pz[e];
+			const float mx = ey * nz - ez * ny, my = ez * nx - ex * nz, mz = ex * ny - ey * nx;
+			const float mm = m * (fabsf(ex) + fabsf(ey) + fabsf(ez));
+			bool out = true;
 #pragma unroll
 			for (int k = 0; k < 4; ++k)
-				if (dot(n_S, mk(gv[3 * k], gv[3 * k + 1], gv[3 * k + 2])) - pd > 0)
-					code |= 1 << k;
-			keep = code != 0 && code != 15;
+				out = out && fdot3(mx, my, mz, tv[k][0] - px[e], tv[k][1] - py[e], tv[k][2] - pz[e]) > mm;
+			if (out)
+				return false;
 		}
-		__syncwarp();
-		unsigned mk_ = __ballot_sync(FULL_MASK, keep);
-		if (keep)
-			W.stage[n_stage + __popc(mk_ & lt_mask)] = make_uint2(0u, (unsigned)t);
-		n_stage += __popc(mk_);
-		__syncwarp();
-		if (n_stage > STAGE - 32)
-			flush_stage(P, io, W, warp, lane, n_stage & ~31, n_stage, i0, last_range);
 	}
-	if (n_stage > 0)
-		flush_stage(P, io, W, warp, lane, n_stage, n_stage, i0, last_range);
-	if (lane == 0) {
-		P.unit_count[warp] = i0;
-		P.unit_evals[warp] = q_end - q_begin; // tets examined
-		if (last_range == -2)
-			P.unit_range[warp] = make_int4(0, 0, -1, 0);
-	}
-}
-
-// records the leaf test of tet t will gather: TetField (192 bytes, two lines; soft-soft reads only the second: gradient
-// and ghat) and the tet's vertices
-template <bool QTET>
-__device__ __forceinline__ void prefetch_leaf(const PairDesc &P, int t)
-{
-#if HCS_BP_PREFETCH
-	const char *tf = reinterpret_cast<const char *>(P.A.tet_field + t);
-	if (!QTET)
-		asm volatile("prefetch.global.L1 [%0];" ::"l"(tf));
-	asm volatile("prefetch.global.L1 [%0];" ::"l"(tf + 128));
-	asm volatile("prefetch.global.L1 [%0];" ::"l"(P.A.tet_geom + t));
 #endif
+	return true;
 }
 
-// QTET: query elements are tets of B (soft-soft), otherwise triangles of B (soft-rigid)
-template <bool QTET>
-__device__ __forceinline__ void broadphase_unit(const PairDesc &P, const StepIO &io, WarpQueues &W, int warp, int lane)
+// Soft-soft.  Float filter: equal-pressure plane n = grad0 - grad1, offset -(e0 - f1(Mo)) / |n| in float with explicit
+// error bounds.  en bounds the direction error of the unit normal (the gradients cancel: relative error ~ eps (|grad0| +
+// |grad1|) / |n|), epd the error of the offset; both blow up when the gradients nearly cancel, and then nothing is
+// rejected here.  The two gradient culls are semantic filters: they are decided in float only when clear by en + 1e-5,
+// otherwise the pair takes the exact path: CalcEquilibriumPlane + the two IsPlaneNormalAlongPressureGradient culls of
+// field_intersection.cc (same arithmetic as the clip kernel), then: the equal-pressure plane must cut BOTH tets.
+// Every comparison is written so that a NaN or an infinity leads to the exact path.
+__device__ __forceinline__ bool leaf_test_soft(const PairDesc &P, const QueuesSoft &W, int s, int tet)
 {
-	int env = warp / P.n_slices, slice = warp - env * P.n_slices;
-	Xform X_WA = load_pose(io.xpos, io.xmat, io.n_geoms, env, P.gA);
-	Xform X_WB = load_pose(io.xpos, io.xmat, io.n_geoms, env, P.gB);
-	{ // pair-level reject on bounding spheres
-		D3 ca = apply(X_WA, mk(P.A.bound_c[0], P.A.bound_c[1], P.A.bound_c[2]));
-		D3 cb = apply(X_WB, mk(P.B.bound_c[0], P.B.bound_c[1], P.B.bound_c[2]));
-		D3 d  = ca - cb;
-		double rr = P.A.bound_r + P.B.bound_r + 1e-9;
-		if (dot(d, d) > rr * rr) {
-			if (lane == 0) {
-				P.unit_count[warp] = 0;
-				P.unit_evals[warp] = 0;
-				P.unit_range[warp] = make_int4(0, 0, -1, 0);
+	bool keep = true, need_exact = true;
+	{
+		const TetLeafSS32 *tl = P.A.tet_leafss32 + tet;
+		const F8 l0 = ld8f(tl, 0), l1 = ld8f(tl, 1), l2 = ld8f(tl, 2);
+		const float nx = l0.a[0] - W.qpl[0][s], ny = l0.a[1] - W.qpl[1][s], nz = l0.a[2] - W.qpl[2][s];
+		const float mag2 = fdot3(nx, ny, nz, nx, ny, nz);
+		if (mag2 > 1e-30f && mag2 < 1e30f) {
+			const float r  = rsqrtf(mag2);
+			const float hx = nx * r, hy = ny * r, hz = nz * r;
+			const float f1o = W.qpl[3][s];
+			const float G   = fabsf(l0.a[0]) + fabsf(l0.a[1]) + fabsf(l0.a[2]) + W.qx[3][s];
+			const float en  = 1e-6f * G * r;
+			const float pd  = -(l0.a[3] - f1o) * r;
+			const float epd = 1e-6f * (fabsf(l0.a[3]) + fabsf(f1o)) * r + fabsf(pd) * (en + 1e-6f);
+			const float c0  = fdot3(hx, hy, hz, l0.a[4], l0.a[5], l0.a[6]);
+			const float c1  = -fdot3(hx, hy, hz, W.qx[0][s], W.qx[1][s], W.qx[2][s]);
+			const float ec  = en + 1e-5f, cosa = (float)HCS_COS_ALPHA;
+			if (c0 >= cosa + ec && c1 >= cosa + ec) { // both culls clearly pass
+				need_exact    = false;
+				const float m = epd + (en + 4e-6f) * W.qm[s];
+				float h0 = fdot3(hx, hy, hz, l1.a[0], l1.a[1], l1.a[2]) - pd;
+				float h1 = fdot3(hx, hy, hz, l1.a[3], l1.a[4], l1.a[5]) - pd;
+				float h2 = fdot3(hx, hy, hz, l1.a[6], l1.a[7], l2.a[0]) - pd;
+				float h3 = fdot3(hx, hy, hz, l2.a[1], l2.a[2], l2.a[3]) - pd;
+				if ((h0 > m && h1 > m && h2 > m && h3 > m) || (h0 < -m && h1 < -m && h2 < -m && h3 < -m))
+					keep = false;
+				float g0 = fdot3(hx, hy, hz, W.qvf[0][s], W.qvf[1][s], W.qvf[2][s]) - pd;
+				float g1 = fdot3(hx, hy, hz, W.qvf[3][s], W.qvf[4][s], W.qvf[5][s]) - pd;
+				float g2 = fdot3(hx, hy, hz, W.qvf[6][s], W.qvf[7][s], W.qvf[8][s]) - pd;
+				float g3 = fdot3(hx, hy, hz, W.qvf[9][s], W.qvf[10][s], W.qvf[11][s]) - pd;
+				if ((g0 > m && g1 > m && g2 > m && g3 > m) || (g0 < -m && g1 < -m && g2 < -m && g3 < -m))
+					keep = false;
+			} else if (c0 < cosa - ec || c1 < cosa - ec) { // one cull clearly fails
+				need_exact = false;
+				keep       = false;
 			}
-			return;
 		}
 	}
-	Xform X_AB  = invert_and_compose(X_WA, X_WB);
-	D3 p_BAo    = -rotT(X_AB.R, X_AB.p); // origin of A expressed in B (p_NMo of field_intersection.cc)
-	if (slice == 0 && lane == 0)
-		write_pair_ctx(P, io, env, X_WA, X_WB, X_AB, p_BAo);
-	int n_stage = 0, i0 = 0, evals = 0; // warp-uniform: staged candidates, candidates already flushed, leaf hits
-	int last_range = -2;                // lane 0 only
-	int q_begin = slice * P.slice_q, q_end = min(P.nq, q_begin + P.slice_q);
-	unsigned lt_mask = (1u << lane) - 1u;
-	const float4 *nodes4 = reinterpret_cast<const float4 *>(P.A.nodes);
+	if (!need_exact)
+		return keep;
+	const Xform X_AB   = unit_xab(W);
+	const D3 p_BAo     = mk(W.pba[0], W.pba[1], W.pba[2]);
+	const TetField *f0 = P.A.tet_field + tet, *f1 = P.B.tet_field + W.qid[s];
+	const D4 ge0 = load_grad_e0(f0), ge1 = load_grad_e0(f1);
+	D3 grad0 = xyz(ge0), grad1_N = xyz(ge1);
+	D3 grad1_M   = rot(X_AB.R, grad1_N);
+	double f1_Mo = dot(grad1_N, p_BAo) + ge1.w;
+	D3 n_M       = grad0 - grad1_M;
+	double mag   = sqrt(dot(n_M, n_M));
+	if (!(mag > 0.0))
+		return false;
+	D3 nhat   = n_M / mag;
+	D3 p_MQ   = -((ge0.w - f1_Mo) / mag) * nhat;
+	double pd = dot(nhat, p_MQ);
+	if (!(dot(nhat, load_ghat(f0)) > HCS_COS_ALPHA))
+		return false;
+	if (!(dot(rotT(X_AB.R, -nhat), load_ghat(f1)) > HCS_COS_ALPHA))
+		return false;
+	const TetVerts tg = load_tet_verts(P.A.tet_geom + tet);
+	double h0 = dot(nhat, tg.v0) - pd, h1 = dot(nhat, tg.v1) - pd, h2 = dot(nhat, tg.v2) - pd, h3 = dot(nhat, tg.v3) - pd;
+	if ((h0 > 1e-12 && h1 > 1e-12 && h2 > 1e-12 && h3 > 1e-12) || (h0 < -1e-12 && h1 < -1e-12 && h2 < -1e-12 && h3 < -1e-12))
+		return false;
+	const TetVerts tq = load_tet_verts(P.B.tet_geom + W.qid[s]);
+	double g0 = dot(nhat, apply(X_AB, tq.v0)) - pd, g1 = dot(nhat, apply(X_AB, tq.v1)) - pd,
+	       g2 = dot(nhat, apply(X_AB, tq.v2)) - pd, g3 = dot(nhat, apply(X_AB, tq.v3)) - pd;
+	if ((g0 > 1e-12 && g1 > 1e-12 && g2 > 1e-12 && g3 > 1e-12) || (g0 < -1e-12 && g1 < -1e-12 && g2 < -1e-12 && g3 < -1e-12))
+		return false;
+	return true;
+}
+
+// Append the staged candidates to the pair's flat list: one atomicAdd per flush.  The record carries its environment;
+// where it lands does not matter (nothing downstream depends on candidate order).
+template <class Q>
+__device__ __forceinline__ void flush_stage(const PairDesc &P, const StepIO &io, Q &W, int lane, int env, int &n_stage)
+{
+	int base = 0;
+	if (lane == 0)
+		base = atomicAdd(P.counters, n_stage);
+	base = __shfl_sync(FULL_MASK, base, 0);
+	for (int j = lane; j < n_stage; j += 32) {
+		if (base + j < P.contrib_cap) {
+			const uint2 cd   = W.stage[j];
+			P.flat[base + j] = make_uint4(cd.x, cd.y, (unsigned)env, 0u);
+		} else {
+			atomicOr(io.flags, 8);
+		}
+	}
+	__syncwarp();
+	n_stage = 0;
+}
+
+// KIND: 0 triangles of B against the tet tree of A, 1 tets of B against it, 2 the tets of A against a half space.
+// Persistent warps: the resident CTAs of every SM pull (env, slice) units from a work counter, so the grid is never a
+// fractional number of waves and a slow unit does not hold three finished warps' resources.
+template <int KIND, bool SWEEP>
+__global__ void __launch_bounds__(BP_BLOCK, BP_CTAS_PER_SM) broadphase_kernel(PairDesc P, StepIO io)
+{
+	typedef typename std::conditional<KIND == 1, QueuesSoft, QueuesRigid>::type Queues;
+	constexpr bool QTET = KIND == 1;
+	Queues &W         = reinterpret_cast<Queues *>(bp_smem)[threadIdx.x >> 5];
+	const int lane    = threadIdx.x & 31;
+	const int n_units = io.n_env * P.n_slices;
+	const unsigned lt_mask = (1u << lane) - 1u;
+	const float4 *nodes4   = reinterpret_cast<const float4 *>(P.A.nodes);
 	// largest coordinate of A's geometry in its own frame (bounding sphere), for the float filter's margin
-	const float leaf_scale = (float)(fmax(fmax(fabs(P.A.bound_c[0]), fabs(P.A.bound_c[1])), fabs(P.A.bound_c[2])) + P.A.bound_r);
+	const float leaf_scale =
+	    (float)(fmax(fmax(fabs(P.A.bound_c[0]), fabs(P.A.bound_c[1])), fabs(P.A.bound_c[2])) + P.A.bound_r);
+	// Small trees are swept, not walked: every alive query against every tet box, 32 tets per pass (the 24-tet foam of the
+	// Myrmex worlds: one pass per alive triangle).  Measured on the 128-tet sphere of config 1: 4 passes per alive triangle
+	// lose to the ~27 node iterations of the walk (broadphase 0.068 vs 0.049 ms), hence the low limit.
+	constexpr bool sweep = SWEEP;
+	pdl_release(); // the pair's narrowphase may become resident while this grid drains (it waits for our completion)
 
-	for (int q0 = q_begin; q0 < q_end; q0 += 32) {
-		// ---- load + transform this chunk's queries, test against the root box, compact survivors ----
-		int q = q0 + lane;
-		bool alive = q < q_end;
-		double v[12];
-		float box[6];
-		if (alive) {
-			double lo[3] = { 1e300, 1e300, 1e300 }, hi[3] = { -1e300, -1e300, -1e300 };
-			// 12 doubles = three 256-bit loads: the tet's vertices, or the triangle's vertices + normal
-			const double *vp = QTET ? reinterpret_cast<const double *>(P.B.tet_geom + q) :
-			                          reinterpret_cast<const double *>(P.B.tris + q);
-			const D4 r0 = ld4(vp), r1 = ld4(vp + 4), r2 = ld4(vp + 8);
-			const D3 qv[4] = { mk(r0.x, r0.y, r0.z), mk(r0.w, r1.x, r1.y), mk(r1.z, r1.w, r2.x), mk(r2.y, r2.z, r2.w) };
-			const int nv   = QTET ? 4 : 3;
-#pragma unroll
-			for (int i = 0; i < nv; ++i) {
-				D3 p = apply(X_AB, qv[i]);
-				v[3 * i] = p.x, v[3 * i + 1] = p.y, v[3 * i + 2] = p.z;
-				lo[0] = fmin(lo[0], p.x), lo[1] = fmin(lo[1], p.y), lo[2] = fmin(lo[2], p.z);
-				hi[0] = fmax(hi[0], p.x), hi[1] = fmax(hi[1], p.y), hi[2] = fmax(hi[2], p.z);
-			}
-			if (!QTET) {
-				D3 nS = rot(X_AB.R, qv[3]);
-				v[9] = nS.x, v[10] = nS.y, v[11] = nS.z;
-			}
-#pragma unroll
-			for (int a = 0; a < 3; ++a) {
-				box[a]     = __double2float_rd(lo[a] - 1e-9);
-				box[3 + a] = __double2float_ru(hi[a] + 1e-9);
-			}
-			alive = box[0] <= P.A.root_hi[0] && box[3] >= P.A.root_lo[0] && box[1] <= P.A.root_hi[1] &&
-			        box[4] >= P.A.root_lo[1] && box[2] <= P.A.root_hi[2] && box[5] >= P.A.root_lo[2];
+	for (;;) {
+		int unit = 0;
+		if (lane == 0)
+			unit = atomicAdd(P.counters + 2, 1);
+		unit = __shfl_sync(FULL_MASK, unit, 0);
+		if (unit >= n_units)
+			break;
+		const int env = unit / P.n_slices, slice = unit - env * P.n_slices;
+		const Xform X_WA = load_pose(io.xpos, io.xmat, io.n_geoms, env, P.gA);
+		const Xform X_WB = load_pose(io.xpos, io.xmat, io.n_geoms, env, P.gB);
+		const Xform X_AB = invert_and_compose(X_WA, X_WB);
+		const D3 p_BAo   = -rotT(X_AB.R, X_AB.p); // origin of A expressed in B (p_NMo of field_intersection.cc)
+		bool active      = true;
+		D3 n_S    = mk(0, 0, 1);
+		double pd = 0;
+		if (KIND != 2) { // pair-level reject on bounding spheres
+			D3 ca = apply(X_WA, mk(P.A.bound_c[0], P.A.bound_c[1], P.A.bound_c[2]));
+			D3 cb = apply(X_WB, mk(P.B.bound_c[0], P.B.bound_c[1], P.B.bound_c[2]));
+			D3 d  = ca - cb;
+			double rr = P.A.bound_r + P.B.bound_r + 1e-9;
+			active    = !(dot(d, d) > rr * rr);
+		} else {
+			// the half space in A's frame: normal = z column of R_AB, through p_AB (mesh_half_space_intersection.cc)
+			n_S = mk(X_AB.R[2], X_AB.R[5], X_AB.R[8]);
+			pd  = dot(n_S, X_AB.p);
+			// the whole geom above the plane: nothing can be cut
+			active = !(dot(n_S, mk(P.A.bound_c[0], P.A.bound_c[1], P.A.bound_c[2])) - pd > P.A.bound_r + 1e-9);
 		}
-		unsigned m_alive = __ballot_sync(FULL_MASK, alive);
-		int n_alive      = __popc(m_alive);
-		if (n_alive == 0)
-			continue;
-		__syncwarp();
-		if (alive) {
-			int slot = __popc(m_alive & lt_mask);
+		if (lane == 0) { // what the exact fallbacks of the leaf tests read back (rare paths)
 #pragma unroll
-			for (int k = 0; k < 12; ++k)
-				W.qv[k][slot] = v[k];
-#pragma unroll
-			for (int k = 0; k < 6; ++k)
-				W.qbox[k][slot] = box[k];
-			if (!QTET) {
-				W.qpl[0][slot] = (float)v[9], W.qpl[1][slot] = (float)v[10], W.qpl[2][slot] = (float)v[11];
-				W.qpl[3][slot] = (float)(v[9] * v[0] + v[10] * v[1] + v[11] * v[2]);
-				float big = leaf_scale;
-#pragma unroll
-				for (int k = 0; k < 9; ++k) {
-					W.qvf[k][slot] = (float)v[k];
-					big            = fmaxf(big, fabsf((float)v[k]));
-				}
-				W.qm[slot] = 4e-6f * big + 1e-30f;
-			} else {
-#if HCS_BP_LEAF32
-				// what the float filter of the soft-soft leaf test needs of the query tet, computed once per query in
-				// double: gradient and unit gradient rotated into A's frame, field value at A's origin
-				const TetField *f1 = P.B.tet_field + q;
-				const D4 ge1       = load_grad_e0(f1);
-				const D3 g1M = rot(X_AB.R, xyz(ge1)), gh1M = rot(X_AB.R, load_ghat(f1));
-				W.qpl[0][slot] = (float)g1M.x, W.qpl[1][slot] = (float)g1M.y, W.qpl[2][slot] = (float)g1M.z;
-				W.qpl[3][slot] = (float)(dot(xyz(ge1), p_BAo) + ge1.w);
-				W.qx[0][slot] = (float)gh1M.x, W.qx[1][slot] = (float)gh1M.y, W.qx[2][slot] = (float)gh1M.z;
-				W.qx[3][slot] = (float)(fabs(g1M.x) + fabs(g1M.y) + fabs(g1M.z));
-				float big = leaf_scale;
-#pragma unroll
-				for (int k = 0; k < 12; ++k) {
-					W.qvf[k][slot] = (float)v[k];
-					big            = fmaxf(big, fabsf((float)v[k]));
-				}
-				W.qm[slot] = big;
-#endif
-			}
-			W.qid[slot]   = q;
-			W.nodeq[slot] = (unsigned)slot << ITEM_SHIFT; // (slot, root)
+			for (int i = 0; i < 9; ++i)
+				W.xab[i] = X_AB.R[i];
+			W.xab[9] = X_AB.p.x, W.xab[10] = X_AB.p.y, W.xab[11] = X_AB.p.z;
+			W.pba[0] = p_BAo.x, W.pba[1] = p_BAo.y, W.pba[2] = p_BAo.z;
+			if (slice == 0)
+				write_pair_ctx(P, io, env, X_WA, X_WB, X_AB, p_BAo);
 		}
 		__syncwarp();
-		int n_node = n_alive, n_leaf = 0;
+		const int q_begin = slice * P.slice_q, q_end = active ? min(P.nq, q_begin + P.slice_q) : q_begin;
+		int n_stage = 0, n_node = 0, n_leaf = 0, evals = 0; // warp-uniform
+		if (KIND == 2)
+			evals = q_end - q_begin; // half space: tets examined
 
-		// ---- shared-queue traversal ----
-		while (n_node > 0 || n_leaf > 0) {
-			if (n_leaf >= 32 || n_node == 0) {
-				// drain up to 32 leaf items: exact early-outs, survivors go to the candidate slab
-				int k     = min(32, n_leaf);
+#pragma unroll 1
+		for (int q0 = q_begin; q0 < q_end; q0 += 32) {
+			const int q = q0 + lane;
+			bool alive  = q < q_end;
+			if (KIND == 2) {
+				// ---- half space: classify tet q of A; the tets the plane cuts are the unit's candidates ----
 				bool keep = false;
-				uint2 it  = make_uint2(0, 0);
-				if (lane < k) {
-					unsigned raw = W.leafq[n_leaf - k + lane];
-					it           = make_uint2(raw >> ITEM_SHIFT, raw & ITEM_MASK);
-					keep         = true;
-					if (!QTET) {
-						const TetField *tf = P.A.tet_field + it.y;
-						int s  = (int)it.x;
-#if HCS_BP_LEAF32
-						// Conservative float filter.  The exact tests below are early-outs: a pair they reject clips to
-						// nothing, so rejecting a SUBSET of those pairs here changes no result, and a pair that slips
-						// through is clipped (to nothing) by the narrowphase.  One 128-byte TetLeaf32 line replaces the
-						// 192 + 96 bytes of fp64 records per leaf hit; the margin qm = 4e-6 x (largest coordinate
-						// involved) is > 5x the worst rounding of the float dot products and of the inputs' conversion,
-						// so "outside by more than qm in float" implies "outside by more than 1e-12 in double".  NaNs
-						// (degenerate tets) compare false and fall through to the exact path.  Only the gradient cull
-						// is a semantic filter, not an early-out: it is decided in float only when it is clear by 1e-5.
-						const TetLeaf32 *tl = P.A.tet_leaf32 + it.y;
-						const F8 l0 = ld8f(tl, 0), l1 = ld8f(tl, 1), l2 = ld8f(tl, 2), l3 = ld8f(tl, 3);
-						const float nx = W.qpl[0][s], ny = W.qpl[1][s], nz = W.qpl[2][s], dtf = W.qpl[3][s], m = W.qm[s];
-						const float cosg = fdot3(l2.a[0], l2.a[1], l2.a[2], nx, ny, nz);
-						if (cosg < (float)HCS_COS_ALPHA - 1e-5f)
-							keep = false;
-						else if (cosg < (float)HCS_COS_ALPHA + 1e-5f)
-							keep = dot(load_ghat(tf), mk(W.qv[9][s], W.qv[10][s], W.qv[11][s])) > HCS_COS_ALPHA;
-						if (keep) {
-							const float ax = W.qvf[0][s], ay = W.qvf[1][s], az = W.qvf[2][s], bx = W.qvf[3][s], by = W.qvf[4][s],
-							            bz = W.qvf[5][s], cx = W.qvf[6][s], cy = W.qvf[7][s], cz = W.qvf[8][s];
-							const float pl[4][4] = { { l0.a[0], l0.a[1], l0.a[2], l0.a[3] }, { l0.a[4], l0.a[5], l0.a[6], l0.a[7] },
-								                     { l1.a[0], l1.a[1], l1.a[2], l1.a[3] }, { l1.a[4], l1.a[5], l1.a[6], l1.a[7] } };
+				if (alive) {
+					const TetVerts tg = load_tet_verts(P.A.tet_geom + q);
+					int code = 0;
 #pragma unroll
-							for (int f = 0; f < 4; ++f) {
-								float sa = fdot3(pl[f][0], pl[f][1], pl[f][2], ax, ay, az) - pl[f][3];
-								float sb = fdot3(pl[f][0], pl[f][1], pl[f][2], bx, by, bz) - pl[f][3];
-								float sc = fdot3(pl[f][0], pl[f][1], pl[f][2], cx, cy, cz) - pl[f][3];
-								if (sa > m && sb > m && sc > m)
-									keep = false;
-							}
-							// tet vertices: l2.a[4..7], l3.a[0..7]
-							float h0 = fdot3(nx, ny, nz, l2.a[4], l2.a[5], l2.a[6]) - dtf;
-							float h1 = fdot3(nx, ny, nz, l2.a[7], l3.a[0], l3.a[1]) - dtf;
-							float h2 = fdot3(nx, ny, nz, l3.a[2], l3.a[3], l3.a[4]) - dtf;
-							float h3 = fdot3(nx, ny, nz, l3.a[5], l3.a[6], l3.a[7]) - dtf;
-							if ((h0 > m && h1 > m && h2 > m && h3 > m) || (h0 < -m && h1 < -m && h2 < -m && h3 < -m))
-								keep = false;
-						}
-#else
-						D3 nS  = mk(W.qv[9][s], W.qv[10][s], W.qv[11][s]);
-						keep   = dot(load_ghat(tf), nS) > HCS_COS_ALPHA;
-						if (keep) {
-							D3 a = mk(W.qv[0][s], W.qv[1][s], W.qv[2][s]), b = mk(W.qv[3][s], W.qv[4][s], W.qv[5][s]),
-							   c = mk(W.qv[6][s], W.qv[7][s], W.qv[8][s]);
-#pragma unroll
-							for (int f = 0; f < 4; ++f) {
-								const D4 pl = load_plane(tf, f);
-								D3 nh       = xyz(pl);
-								double d    = pl.w;
-								double sa = dot(nh, a) - d, sb = dot(nh, b) - d, sc = dot(nh, c) - d;
-								if (sa > 1e-12 && sb > 1e-12 && sc > 1e-12)
-									keep = false;
-							}
-							// the triangle's plane must cut the tet: all four tet vertices strictly on one side => empty
-							const TetVerts tg = load_tet_verts(P.A.tet_geom + it.y);
-							double dt = dot(nS, a);
-							double h0 = dot(nS, tg.v0) - dt, h1 = dot(nS, tg.v1) - dt, h2 = dot(nS, tg.v2) - dt,
-							       h3 = dot(nS, tg.v3) - dt;
-							if ((h0 > 1e-12 && h1 > 1e-12 && h2 > 1e-12 && h3 > 1e-12) ||
-							    (h0 < -1e-12 && h1 < -1e-12 && h2 < -1e-12 && h3 < -1e-12))
-								keep = false;
-						}
-#endif
-					} else {
-						bool need_exact = true;
-#if HCS_BP_LEAF32
-						// Float filter (see the soft-rigid one above): equal-pressure plane n = grad0 - grad1, offset
-						// -(e0 - f1(Mo)) / |n| in float with explicit error bounds.  en bounds the direction error of the
-						// unit normal (the gradients cancel: relative error ~ eps (|grad0| + |grad1|) / |n|), epd the
-						// error of the offset; both blow up when the gradients nearly cancel, and then nothing is
-						// rejected here.  The two gradient culls are semantic filters: they are decided in float only
-						// when clear by en + 1e-5, otherwise the pair takes the exact path below.  Every comparison is
-						// written so that a NaN or an infinity leads to the exact path.
-						{
-							const int s = (int)it.x;
-							const TetLeafSS32 *tl = P.A.tet_leafss32 + it.y;
-							const F8 l0 = ld8f(tl, 0), l1 = ld8f(tl, 1), l2 = ld8f(tl, 2);
-							const float nx = l0.a[0] - W.qpl[0][s], ny = l0.a[1] - W.qpl[1][s], nz = l0.a[2] - W.qpl[2][s];
-							const float mag2 = fdot3(nx, ny, nz, nx, ny, nz);
-							if (mag2 > 1e-30f && mag2 < 1e30f) {
-								const float r  = rsqrtf(mag2);
-								const float hx = nx * r, hy = ny * r, hz = nz * r;
-								const float f1o = W.qpl[3][s];
-								const float G   = fabsf(l0.a[0]) + fabsf(l0.a[1]) + fabsf(l0.a[2]) + W.qx[3][s];
-								const float en  = 1e-6f * G * r;
-								const float pd  = -(l0.a[3] - f1o) * r;
-								const float epd = 1e-6f * (fabsf(l0.a[3]) + fabsf(f1o)) * r + fabsf(pd) * (en + 1e-6f);
-								const float c0  = fdot3(hx, hy, hz, l0.a[4], l0.a[5], l0.a[6]);
-								const float c1  = -fdot3(hx, hy, hz, W.qx[0][s], W.qx[1][s], W.qx[2][s]);
-								const float ec  = en + 1e-5f, cosa = (float)HCS_COS_ALPHA;
-								if (c0 >= cosa + ec && c1 >= cosa + ec) { // both culls clearly pass
-									need_exact    = false;
-									const float m = epd + (en + 4e-6f) * W.qm[s];
-									float h0 = fdot3(hx, hy, hz, l1.a[0], l1.a[1], l1.a[2]) - pd;
-									float h1 = fdot3(hx, hy, hz, l1.a[3], l1.a[4], l1.a[5]) - pd;
-									float h2 = fdot3(hx, hy, hz, l1.a[6], l1.a[7], l2.a[0]) - pd;
-									float h3 = fdot3(hx, hy, hz, l2.a[1], l2.a[2], l2.a[3]) - pd;
-									if ((h0 > m && h1 > m && h2 > m && h3 > m) || (h0 < -m && h1 < -m && h2 < -m && h3 < -m))
-										keep = false;
-									float g0 = fdot3(hx, hy, hz, W.qvf[0][s], W.qvf[1][s], W.qvf[2][s]) - pd;
-									float g1 = fdot3(hx, hy, hz, W.qvf[3][s], W.qvf[4][s], W.qvf[5][s]) - pd;
-									float g2 = fdot3(hx, hy, hz, W.qvf[6][s], W.qvf[7][s], W.qvf[8][s]) - pd;
-									float g3 = fdot3(hx, hy, hz, W.qvf[9][s], W.qvf[10][s], W.qvf[11][s]) - pd;
-									if ((g0 > m && g1 > m && g2 > m && g3 > m) || (g0 < -m && g1 < -m && g2 < -m && g3 < -m))
-										keep = false;
-								} else if (c0 < cosa - ec || c1 < cosa - ec) { // one cull clearly fails
-									need_exact = false;
-									keep       = false;
-								}
-							}
-						}
-#endif
-						if (need_exact) {
-						// soft-soft: CalcEquilibriumPlane + the two IsPlaneNormalAlongPressureGradient culls of
-						// field_intersection.cc (same arithmetic as the clip kernel), then: the equal-pressure plane
-						// must cut BOTH tets, otherwise slice-and-clip is empty.
-						const TetField *f0 = P.A.tet_field + it.y, *f1 = P.B.tet_field + W.qid[it.x];
-						int s      = (int)it.x;
-						const D4 ge0 = load_grad_e0(f0), ge1 = load_grad_e0(f1);
-						D3 grad0 = xyz(ge0), grad1_N = xyz(ge1);
-						D3 grad1_M   = rot(X_AB.R, grad1_N);
-						double f1_Mo = dot(grad1_N, p_BAo) + ge1.w;
-						D3 n_M       = grad0 - grad1_M;
-						double mag   = sqrt(dot(n_M, n_M));
-						keep         = mag > 0.0;
-						if (keep) {
-							D3 nhat   = n_M / mag;
-							D3 p_MQ   = -((ge0.w - f1_Mo) / mag) * nhat;
-							double pd = dot(nhat, p_MQ);
-							keep      = dot(nhat, load_ghat(f0)) > HCS_COS_ALPHA;
-							if (keep)
-								keep = dot(rotT(X_AB.R, -nhat), load_ghat(f1)) > HCS_COS_ALPHA;
-							if (keep) {
-								const TetVerts tg = load_tet_verts(P.A.tet_geom + it.y);
-								double h0 = dot(nhat, tg.v0) - pd, h1 = dot(nhat, tg.v1) - pd, h2 = dot(nhat, tg.v2) - pd,
-								       h3 = dot(nhat, tg.v3) - pd;
-								if ((h0 > 1e-12 && h1 > 1e-12 && h2 > 1e-12 && h3 > 1e-12) ||
-								    (h0 < -1e-12 && h1 < -1e-12 && h2 < -1e-12 && h3 < -1e-12))
-									keep = false;
-								double g0 = dot(nhat, mk(W.qv[0][s], W.qv[1][s], W.qv[2][s])) - pd,
-								       g1 = dot(nhat, mk(W.qv[3][s], W.qv[4][s], W.qv[5][s])) - pd,
-								       g2 = dot(nhat, mk(W.qv[6][s], W.qv[7][s], W.qv[8][s])) - pd,
-								       g3 = dot(nhat, mk(W.qv[9][s], W.qv[10][s], W.qv[11][s])) - pd;
-								if ((g0 > 1e-12 && g1 > 1e-12 && g2 > 1e-12 && g3 > 1e-12) ||
-								    (g0 < -1e-12 && g1 < -1e-12 && g2 < -1e-12 && g3 < -1e-12))
-									keep = false;
-							}
-						}
-						} // need_exact
-					}
+					for (int k = 0; k < 4; ++k)
+						if (dot(n_S, tg.at(k)) - pd > 0)
+							code |= 1 << k;
+					keep = code != 0 && code != 15;
 				}
-				n_leaf -= k;
-				evals += k;
-				unsigned mk_ = __ballot_sync(FULL_MASK, keep);
+				const unsigned mk_ = __ballot_sync(FULL_MASK, keep);
 				if (keep)
-					W.stage[n_stage + __popc(mk_ & lt_mask)] = make_uint2((unsigned)W.qid[it.x], it.y);
+					W.stage[n_stage + __popc(mk_ & lt_mask)] = make_uint2(0u, (unsigned)q);
 				n_stage += __popc(mk_);
 				__syncwarp();
-				if (n_stage > STAGE - 32) // the next drain may not fit: append the whole chunks
-					flush_stage(P, io, W, warp, lane, n_stage & ~31, n_stage, i0, last_range);
-			} else {
-				// pop k items, push <= 2k: the queue grows by <= k.  Near the capacity fewer items are popped,
-				// which turns the LIFO into a depth-first walk whose stack stays below the tree depth.
-				// A small frontier (one environment of the sphere-on-box scene offers 12 items on average) is popped with
-				// TWO lanes per item, one per child: each lane runs one box test instead of two, twice as many lanes
-				// work.  Which mode runs depends on n_node only, so the candidate order stays a function of the unit.
-#if HCS_BP_PAIRED_POP
-				const bool paired = n_node <= 16;
-#else
-				const bool paired = false;
-#endif
-				int k = paired ? n_node : max(1, min(min(32, n_node), NODE_Q - n_node));
-				bool pushL = false, pushR = false, leafL = false, leafR = false;
-				int cl = 0, cr = 0;
-				unsigned s = 0;
-				const int item = paired ? lane >> 1 : lane;
-				if (item < k) {
-					unsigned raw = W.nodeq[n_node - k + item];
-					uint2 it     = make_uint2(raw >> ITEM_SHIFT, raw & ITEM_MASK);
-					s            = it.x;
-					float qb[6];
+				if (n_stage > STAGE - 32)
+					flush_stage(P, io, W, lane, env, n_stage);
+				continue;
+			}
+			// ---- tree kinds: transform this batch's queries, test against the root box, give the alive ones a slot ----
+			double v[12];
+			float box[6];
+			if (alive) {
+				double lo[3] = { 1e300, 1e300, 1e300 }, hi[3] = { -1e300, -1e300, -1e300 };
+				// 12 doubles = three 256-bit loads: the tet's vertices, or the triangle's vertices + normal
+				const double *vp = QTET ? reinterpret_cast<const double *>(P.B.tet_geom + q) :
+				                          reinterpret_cast<const double *>(P.B.tris + q);
+				const D4 r0 = ld4(vp), r1 = ld4(vp + 4), r2 = ld4(vp + 8);
+				const D3 qv[4] = { mk(r0.x, r0.y, r0.z), mk(r0.w, r1.x, r1.y), mk(r1.z, r1.w, r2.x), mk(r2.y, r2.z, r2.w) };
+				constexpr int nvq = QTET ? 4 : 3;
 #pragma unroll
-					for (int a = 0; a < 6; ++a)
-						qb[a] = W.qbox[a][s];
-					float pl[4] = { 0.f, 0.f, 0.f, 0.f };
-					if (!QTET) {
+				for (int i = 0; i < nvq; ++i) {
+					D3 p = apply(X_AB, qv[i]);
+					v[3 * i] = p.x, v[3 * i + 1] = p.y, v[3 * i + 2] = p.z;
+					lo[0] = fmin(lo[0], p.x), lo[1] = fmin(lo[1], p.y), lo[2] = fmin(lo[2], p.z);
+					hi[0] = fmax(hi[0], p.x), hi[1] = fmax(hi[1], p.y), hi[2] = fmax(hi[2], p.z);
+				}
+				if (!QTET) {
+					const D3 nS = rot(X_AB.R, qv[3]);
+					v[9] = nS.x, v[10] = nS.y, v[11] = nS.z;
+				}
 #pragma unroll
-						for (int a = 0; a < 4; ++a)
-							pl[a] = W.qpl[a][s];
+				for (int a = 0; a < 3; ++a) {
+					box[a]     = __double2float_rd(lo[a] - 1e-9);
+					box[3 + a] = __double2float_ru(hi[a] + 1e-9);
+				}
+				alive = box[0] <= P.A.root_hi[0] && box[3] >= P.A.root_lo[0] && box[1] <= P.A.root_hi[1] &&
+				        box[4] >= P.A.root_lo[1] && box[2] <= P.A.root_hi[2] && box[5] >= P.A.root_lo[2];
+			}
+			const unsigned m_alive = __ballot_sync(FULL_MASK, alive);
+			const int n_slots      = __popc(m_alive);
+			if (n_slots == 0)
+				continue;
+			__syncwarp();
+			if (alive) {
+				const int s = __popc(m_alive & lt_mask);
+#pragma unroll
+				for (int k = 0; k < 6; ++k)
+					W.qbox[k][s] = box[k];
+				float big = leaf_scale;
+				constexpr int nf = QTET ? 12 : 9;
+#pragma unroll
+				for (int k = 0; k < nf; ++k) {
+					W.qvf[k][s] = (float)v[k];
+					big         = fmaxf(big, fabsf((float)v[k]));
+				}
+				if (!QTET) {
+					W.qpl[0][s] = (float)v[9], W.qpl[1][s] = (float)v[10], W.qpl[2][s] = (float)v[11];
+					W.qpl[3][s] = (float)(v[9] * v[0] + v[10] * v[1] + v[11] * v[2]);
+					W.qm[s]     = 4e-6f * big + 1e-30f;
+				} else {
+					// what the float filter of the soft-soft leaf test needs of the query tet, computed once per query in
+					// double: gradient and unit gradient rotated into A's frame, field value at A's origin
+					const TetField *f1 = P.B.tet_field + q;
+					const D4 ge1       = load_grad_e0(f1);
+					const D3 g1M = rot(X_AB.R, xyz(ge1)), gh1M = rot(X_AB.R, load_ghat(f1));
+					W.qpl[0][s] = (float)g1M.x, W.qpl[1][s] = (float)g1M.y, W.qpl[2][s] = (float)g1M.z;
+					W.qpl[3][s] = (float)(dot(xyz(ge1), p_BAo) + ge1.w);
+					W.qx[0][s] = (float)gh1M.x, W.qx[1][s] = (float)gh1M.y, W.qx[2][s] = (float)gh1M.z;
+					W.qx[3][s] = (float)(fabs(g1M.x) + fabs(g1M.y) + fabs(g1M.z));
+					W.qm[s]    = big;
+				}
+				W.qid[s] = q;
+				if (!sweep)
+					W.nodeq[s] = (unsigned)s << ITEM_SHIFT; // (slot, root)
+			}
+			__syncwarp();
+			n_node = sweep ? 0 : n_slots;
+			int sw_s = 0, sw_t = 0; // sweep position: slot, first tet of the next pass
+			const int sw_slots = sweep ? n_slots : 0;
+
+			// ---------------- shared-queue traversal ----------------
+#pragma unroll 1
+			while (n_node > 0 || n_leaf > 0 || sw_s < sw_slots) {
+				if (n_leaf >= 32 || (n_node == 0 && sw_s >= sw_slots)) {
+					// ---- drain up to 32 leaf items: leaf test, survivors are staged ----
+					const int k = min(32, n_leaf);
+					bool keep   = false;
+					int skip    = 0, s = 0;
+					unsigned tet = 0;
+					if (lane < k) {
+						const unsigned raw = W.leafq[n_leaf - k + lane];
+						s = (int)(raw >> ITEM_SHIFT), tet = raw & ITEM_MASK;
+						if constexpr (!QTET)
+							keep = leaf_test_rigid(P, W, s, (int)tet, skip);
+						else
+							keep = leaf_test_soft(P, W, s, (int)tet);
 					}
-					const float4 *nd = nodes4 + 4 * (size_t)it.y;
-#if HCS_BP_NODE256 // the 64-byte node as two 256-bit loads instead of 3 x 128 + 64 bits (round-2 candidate, unmeasured)
-					const F8 n0 = reinterpret_cast<const F8 *>(nd)[0], n1 = reinterpret_cast<const F8 *>(nd)[1];
-					float4 a = make_float4(n0.a[0], n0.a[1], n0.a[2], n0.a[3]), b = make_float4(n0.a[4], n0.a[5], n0.a[6], n0.a[7]);
-					float4 c = make_float4(n1.a[0], n1.a[1], n1.a[2], n1.a[3]), d = make_float4(n1.a[4], n1.a[5], n1.a[6], n1.a[7]);
-#else
-					float4 a = nd[0], b = nd[1], c = nd[2], d = nd[3];
-#endif
-					cl = __float_as_int(d.x), cr = __float_as_int(d.y);
-					if (paired) { // even lane: left child, odd lane: right child; reported through the "L" slots
-						const bool left = !(lane & 1);
-						if (!left)
-							cl = cr;
-						if (box_overlap<!QTET>(qb, pl, a, b, c, left)) {
+					n_leaf -= k;
+					evals += k;
+					const unsigned mk_ = __ballot_sync(FULL_MASK, keep);
+					if (keep)
+						W.stage[n_stage + __popc(mk_ & lt_mask)] = make_uint2((unsigned)W.qid[s], tet | ((unsigned)skip << CAND_MASK_SHIFT));
+					n_stage += __popc(mk_);
+					__syncwarp();
+					if (n_stage > STAGE - 32) // the next drain may not fit
+						flush_stage(P, io, W, lane, env, n_stage);
+				} else if (sw_s < sw_slots) {
+					// ---- sweep pass (small trees): slot sw_s against the boxes of tets sw_t .. sw_t + 31 ----
+					const int t = sw_t + lane;
+					bool hit    = false;
+					if (t < P.n_tree) {
+						float qb[6];
+#pragma unroll
+						for (int a = 0; a < 6; ++a)
+							qb[a] = W.qbox[a][sw_s];
+						float pl[4] = { 0.f, 0.f, 0.f, 0.f };
+						if (!QTET) {
+#pragma unroll
+							for (int a = 0; a < 4; ++a)
+								pl[a] = W.qpl[a][sw_s];
+						}
+						const F8 tb = *reinterpret_cast<const F8 *>(P.A.tet_box32 + t);
+						hit = child_overlap<!QTET>(qb, pl, tb.a[0], tb.a[1], tb.a[2], tb.a[3], tb.a[4], tb.a[5]);
+					}
+					const unsigned mh = __ballot_sync(FULL_MASK, hit);
+					if (hit)
+						W.leafq[n_leaf + __popc(mh & lt_mask)] = ((unsigned)sw_s << ITEM_SHIFT) | (unsigned)t;
+					n_leaf += __popc(mh);
+					sw_t += 32;
+					if (sw_t >= P.n_tree)
+						sw_t = 0, ++sw_s;
+					__syncwarp();
+				} else {
+					// ---- node iteration: pop k items, push <= 2k: the queue grows by <= k.  Near the capacity fewer items
+					// are popped, which turns the LIFO into a depth-first walk whose stack stays below the tree depth ----
+					const int k = max(1, min(min(32, n_node), NODE_Q - n_node));
+					bool pushL = false, pushR = false, leafL = false, leafR = false;
+					int cl = 0, cr = 0;
+					unsigned s = 0;
+					if (lane < k) {
+						const unsigned raw = W.nodeq[n_node - k + lane];
+						s                  = raw >> ITEM_SHIFT;
+						float qb[6];
+#pragma unroll
+						for (int a = 0; a < 6; ++a)
+							qb[a] = W.qbox[a][s];
+						float pl[4] = { 0.f, 0.f, 0.f, 0.f };
+						if (!QTET) {
+#pragma unroll
+							for (int a = 0; a < 4; ++a)
+								pl[a] = W.qpl[a][s];
+						}
+						const float4 *nd = nodes4 + 4 * (size_t)(raw & ITEM_MASK);
+						const float4 a = nd[0], b = nd[1], c = nd[2], d = nd[3];
+						cl = __float_as_int(d.x), cr = __float_as_int(d.y);
+						// node layout: llo[3] lhi[3] rlo[3] rhi[3]
+						if (child_overlap<!QTET>(qb, pl, a.x, a.y, a.z, a.w, b.x, b.y)) {
 							leafL = cl < 0;
 							pushL = !leafL;
 						}
-					} else {
-						if (box_overlap<!QTET>(qb, pl, a, b, c, true)) {
-							leafL = cl < 0;
-							pushL = !leafL;
-						}
-						if (box_overlap<!QTET>(qb, pl, a, b, c, false)) {
+						if (child_overlap<!QTET>(qb, pl, b.z, b.w, c.x, c.y, c.z, c.w)) {
 							leafR = cr < 0;
 							pushR = !leafR;
 						}
 					}
+					n_node -= k;
+					__syncwarp();
+					const unsigned mL = __ballot_sync(FULL_MASK, pushL), mR = __ballot_sync(FULL_MASK, pushR);
+					const unsigned lL = __ballot_sync(FULL_MASK, leafL), lR = __ballot_sync(FULL_MASK, leafR);
+					const int nL = __popc(mL), nR = __popc(mR), nlL = __popc(lL), nlR = __popc(lR);
+					if (n_node + nL + nR > NODE_Q) { // only with k forced to 1 on a full queue: a tree deeper than NODE_Q / 32
+						if (lane == 0)
+							atomicOr(io.flags + 1, 1);
+						n_node = 0;
+						n_leaf = 0;
+						break;
+					}
+					if (pushL)
+						W.nodeq[n_node + __popc(mL & lt_mask)] = (s << ITEM_SHIFT) | (unsigned)cl;
+					if (pushR)
+						W.nodeq[n_node + nL + __popc(mR & lt_mask)] = (s << ITEM_SHIFT) | (unsigned)cr;
+					// leaf items wait in the queue for an iteration or more
+					if (leafL)
+						W.leafq[n_leaf + __popc(lL & lt_mask)] = (s << ITEM_SHIFT) | (unsigned)~cl;
+					if (leafR)
+						W.leafq[n_leaf + nlL + __popc(lR & lt_mask)] = (s << ITEM_SHIFT) | (unsigned)~cr;
+					n_node += nL + nR;
+					n_leaf += nlL + nlR;
+					__syncwarp();
 				}
-				n_node -= k;
-				__syncwarp();
-				unsigned mL = __ballot_sync(FULL_MASK, pushL), mR = __ballot_sync(FULL_MASK, pushR);
-				unsigned lL = __ballot_sync(FULL_MASK, leafL), lR = __ballot_sync(FULL_MASK, leafR);
-				int nL = __popc(mL), nR = __popc(mR), nlL = __popc(lL), nlR = __popc(lR);
-				if (n_node + nL + nR > NODE_Q) { // cannot happen for trees shallower than NODE_Q/32 levels
-					if (lane == 0)
-						atomicOr(io.flags + 1, 1);
-					n_node = 0;
-					n_leaf = 0;
-					break;
-				}
-				if (pushL)
-					W.nodeq[n_node + __popc(mL & lt_mask)] = (s << ITEM_SHIFT) | (unsigned)cl;
-				if (pushR)
-					W.nodeq[n_node + nL + __popc(mR & lt_mask)] = (s << ITEM_SHIFT) | (unsigned)cr;
-				// leaf items wait in the queue for an iteration or more: their records travel meanwhile
-				if (leafL) {
-					W.leafq[n_leaf + __popc(lL & lt_mask)] = (s << ITEM_SHIFT) | (unsigned)~cl;
-					prefetch_leaf<QTET>(P, ~cl);
-				}
-				if (leafR) {
-					W.leafq[n_leaf + nlL + __popc(lR & lt_mask)] = (s << ITEM_SHIFT) | (unsigned)~cr;
-					prefetch_leaf<QTET>(P, ~cr);
-				}
-				n_node += nL + nR;
-				n_leaf += nlL + nlR;
-				__syncwarp();
 			}
 		}
-	}
-	if (n_stage > 0)
-		flush_stage(P, io, W, warp, lane, n_stage, n_stage, i0, last_range);
-	if (lane == 0) {
-		P.unit_count[warp] = i0;
-		P.unit_evals[warp] = evals;
-		if (last_range == -2)
-			P.unit_range[warp] = make_int4(0, 0, -1, 0);
+		if (n_stage > 0)
+			flush_stage(P, io, W, lane, env, n_stage);
+		// pair-evals started for this environment: LBVH leaf hits / tets classified
+		if (lane == 0 && evals > 0)
+			atomicAdd(reinterpret_cast<unsigned long long *>(P.accum + (size_t)env * ACC_WORDS + ACC_NEVALS), (unsigned long long)evals);
+		__syncwarp();
 	}
 }
 
-__device__ __forceinline__ int claim_unit(int32_t *counter, int lane)
+template <int KIND, bool SWEEP>
+static void launch_bp(const PairDesc &P, const StepIO &io, cudaStream_t s, int grid)
 {
-	int u = 0;
-	if (lane == 0)
-		u = atomicAdd(counter, 1);
-	return __shfl_sync(FULL_MASK, u, 0);
-}
-// Prefetches (next unit's poses, leaf records at push time) were measured and are off: the L1 data pipe is the busiest
-// unit of this kernel and the extra wavefronts cost more than the latency they hide (C1 broadphase 0.050 -> 0.075 ms).
-#ifndef HCS_BP_PREFETCH
-#define HCS_BP_PREFETCH 0
-#endif
-#ifndef HCS_EARLY_CLAIM
-#define HCS_EARLY_CLAIM 0
-#endif
-__device__ __forceinline__ void prefetch_l1(const void *p)
-{
-#if HCS_BP_PREFETCH
-	asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
-#endif
-}
-// Persistent warps: the resident CTAs of every SM pull (env, slice) units from a work counter, so the grid is
-// never a fractional number of waves and a slow unit does not hold three finished warps' resources.
-// KIND: 0 triangles of B against the tet tree of A, 1 tets of B against it, 2 the tets of A against a half space
-template <int KIND>
-__global__ void __launch_bounds__(BP_BLOCK, BP_CTAS_PER_SM) broadphase_kernel(PairDesc P, StepIO io)
-{
-	__shared__ WarpQueues sm[BP_WARPS];
-	WarpQueues &W     = sm[threadIdx.x >> 5];
-	const int lane    = threadIdx.x & 31;
-	const int n_units = io.n_env * P.n_slices;
-	pdl_release(); // the pair's narrowphase may become resident while this grid drains (it waits for our completion)
-#if HCS_BP_PERSISTENT
-	// HCS_EARLY_CLAIM=1 issues the work-counter atomic for the next unit before the current unit starts (its round
-	// trip is 4 % of the stall samples); measured slower (0.0503 -> 0.0550 ms on C1) and off by default.
-#if HCS_EARLY_CLAIM
-	int unit = claim_unit(P.counters + 2, lane);
-	while (unit < n_units) {
-		const int requested = lane == 0 ? atomicAdd(P.counters + 2, 1) : 0;
-		if (KIND == 2)
-			plane_unit(P, io, W, unit, lane);
-		else
-			broadphase_unit<KIND == 1>(P, io, W, unit, lane);
-		__syncwarp();
-		unit = __shfl_sync(FULL_MASK, requested, 0);
-	}
-#else
-	for (;;) {
-		int unit = claim_unit(P.counters + 2, lane);
-		if (unit >= n_units)
-			break;
-		if (KIND == 2)
-			plane_unit(P, io, W, unit, lane);
-		else
-			broadphase_unit<KIND == 1>(P, io, W, unit, lane);
-		__syncwarp();
-	}
-#endif
-#else
-	int unit = (blockIdx.x * BP_BLOCK + threadIdx.x) >> 5;
-	if (unit < n_units) {
-		if (KIND == 2)
-			plane_unit(P, io, W, unit, lane);
-		else
-			broadphase_unit<KIND == 1>(P, io, W, unit, lane);
-	}
-#endif
+	typedef typename std::conditional<KIND == 1, QueuesSoft, QueuesRigid>::type Queues;
+	const int smem = (int)sizeof(Queues) * BP_WARPS;
+	ensure_dynamic_smem(broadphase_kernel<KIND, SWEEP>, smem);
+	broadphase_kernel<KIND, SWEEP><<<grid, BP_BLOCK, smem, s>>>(P, io);
 }
 
 void launch_broadphase(const PairDesc &P, const StepIO &io, cudaStream_t s)
 {
-	long units = (long)io.n_env * P.n_slices;
+	const long units = (long)io.n_env * P.n_slices;
 	if (units == 0)
 		return;
-	int grid = (int)((units + BP_WARPS - 1) / BP_WARPS);
-#if HCS_BP_PERSISTENT
-	grid = (int)std::min<long>(grid, (long)io.n_sms * BP_CTAS_PER_SM);
-#endif
+	const int grid   = (int)std::max<long>(1, std::min<long>((units + BP_WARPS - 1) / BP_WARPS, (long)io.n_sms * BP_CTAS_PER_SM));
+	const bool sweep = P.n_tree <= SWEEP_MAX_TREE;
 	if (P.kind == PAIR_SOFT_RIGID)
-		broadphase_kernel<0><<<grid, BP_BLOCK, 0, s>>>(P, io);
+		sweep ? launch_bp<0, true>(P, io, s, grid) : launch_bp<0, false>(P, io, s, grid);
 	else if (P.kind == PAIR_SOFT_SOFT)
-		broadphase_kernel<1><<<grid, BP_BLOCK, 0, s>>>(P, io);
+		sweep ? launch_bp<1, true>(P, io, s, grid) : launch_bp<1, false>(P, io, s, grid);
 	else if (P.kind == PAIR_SOFT_PLANE)
-		broadphase_kernel<2><<<grid, BP_BLOCK, 0, s>>>(P, io);
+		launch_bp<2, false>(P, io, s, grid);
 }
 
 } // namespace hcs

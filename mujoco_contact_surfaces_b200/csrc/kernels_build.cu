@@ -84,6 +84,15 @@ __global__ void __launch_bounds__(128) build_tets_kernel(GeomDev g)
 			ts.v[k][a] = tl.v[k][a];
 	}
 	g.tet_leafss32[t] = ts;
+	TetBox32 tb;
+#pragma unroll
+	for (int a = 0; a < 3; ++a) {
+		const double lo = fmin(fmin(tg.v[0][a], tg.v[1][a]), fmin(tg.v[2][a], tg.v[3][a]));
+		const double hi = fmax(fmax(tg.v[0][a], tg.v[1][a]), fmax(tg.v[2][a], tg.v[3][a]));
+		tb.lo[a] = __double2float_rd(lo), tb.hi[a] = __double2float_ru(hi);
+	}
+	tb.pad[0] = tb.pad[1] = 0.f;
+	g.tet_box32[t] = tb;
 }
 
 __global__ void __launch_bounds__(128) build_tris_kernel(GeomDev g)

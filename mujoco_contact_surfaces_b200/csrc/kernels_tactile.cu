@@ -79,7 +79,7 @@ __global__ void __launch_bounds__(256) tactile_bin_kernel(const SensorDev *senso
 	const int n = min(*io.tri_count, io.max_tris);
 	for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
 		const TactileTri &t = io.tri_pool[i];
-		const PairDesc &P   = pairs[t.pair_slice >> TRI_SLICE_BITS];
+		const PairDesc &P   = pairs[t.key_hi >> TRI_PAIR_SHIFT];
 		for (int k = 0; k < n_sensors; ++k)
 			if (P.gM == sensors[k].geom || P.gN == sensors[k].geom)
 				bin_triangle<FILL>(sensors[k], io, t, i);
@@ -307,8 +307,8 @@ __global__ void __launch_bounds__(32 * RASTER_WARPS) tactile_raster_kernel(Senso
 				r = 0;
 				for (int k2 = 0; k2 < n; ++k2) {
 					const TactileTri &o = io.tri_pool[items[k2]];
-					r += (o.pair_slice < t.pair_slice) ||
-					     (o.pair_slice == t.pair_slice && (o.idx8 < t.idx8 || (o.idx8 == t.idx8 && items[k2] < items[k])));
+					r += (o.key_hi < t.key_hi) ||
+					     (o.key_hi == t.key_hi && (o.key_lo < t.key_lo || (o.key_lo == t.key_lo && items[k2] < items[k])));
 				}
 				rank_k[r] = k;
 			}
@@ -514,7 +514,7 @@ __global__ void __launch_bounds__(256) curved_bin_kernel(CurvedDev cd, StepIO io
 	const int n = min(*io.tri_count, io.max_tris);
 	for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
 		const TactileTri &t = io.tri_pool[i];
-		const PairDesc &P   = pairs[t.pair_slice >> TRI_SLICE_BITS];
+		const PairDesc &P   = pairs[t.key_hi >> TRI_PAIR_SHIFT];
 		if (P.gM != cd.geom && P.gN != cd.geom)
 			continue;
 		const int env    = t.env;
@@ -595,9 +595,9 @@ __global__ void __launch_bounds__(128) curved_cast_kernel(CurvedDev cd, StepIO i
 			float tt, u, v;
 			if (moller_trumbore(O, D, t, tt, u, v)) {
 				bool better = tt < best_t ||
-				              (tt == best_t && (t.pair_slice < best_ps || (t.pair_slice == best_ps && t.idx8 < best_idx)));
+				              (tt == best_t && (t.key_hi < best_ps || (t.key_hi == best_ps && t.key_lo < best_idx)));
 				if (better)
-					best_t = tt, best_u = u, best_v = v, best_ps = t.pair_slice, best_idx = t.idx8, best = item;
+					best_t = tt, best_u = u, best_v = v, best_ps = t.key_hi, best_idx = t.key_lo, best = item;
 			}
 		}
 		double raw = 0;
@@ -681,7 +681,7 @@ __global__ void __launch_bounds__(256) taxel_bin_kernel(TaxelDev td, StepIO io, 
 	const int n = min(*io.tri_count, io.max_tris);
 	for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
 		const TactileTri &t = io.tri_pool[i];
-		const PairDesc &P   = pairs[t.pair_slice >> TRI_SLICE_BITS];
+		const PairDesc &P   = pairs[t.key_hi >> TRI_PAIR_SHIFT];
 		if (P.gM != td.geom && P.gN != td.geom)
 			continue;
 		const int env = t.env;
@@ -744,7 +744,7 @@ __global__ void __launch_bounds__(128) taxel_gather_kernel(TaxelDev td, StepIO i
 			int r = 0;
 			for (int k2 = 0; k2 < n; ++k2) {
 				const TactileTri &o = io.tri_pool[items[k2]];
-				r += (o.pair_slice < t.pair_slice) || (o.pair_slice == t.pair_slice && o.idx8 < t.idx8);
+				r += (o.key_hi < t.key_hi) || (o.key_hi == t.key_hi && o.key_lo < t.key_lo);
 			}
 			order[r] = items[k];
 		}
@@ -825,7 +825,7 @@ __global__ void __launch_bounds__(256) taxel_ai_list_kernel(TaxelDev td, StepIO 
 	const int n = min(*io.tri_count, io.max_tris);
 	for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
 		const TactileTri &t = io.tri_pool[i];
-		const PairDesc &P   = pairs[t.pair_slice >> TRI_SLICE_BITS];
+		const PairDesc &P   = pairs[t.key_hi >> TRI_PAIR_SHIFT];
 		if (P.gM != td.geom && P.gN != td.geom)
 			continue;
 		if (!FILL)
@@ -873,8 +873,8 @@ __global__ void __launch_bounds__(256) taxel_ai_sample_kernel(TaxelDev td, StepI
 			const int it        = td.env_items[first + i];
 			const TactileTri &t = io.tri_pool[it];
 			const uint2 el      = io.tri_elem[it];
-			key[i]  = ((unsigned long long)(t.pair_slice >> TRI_SLICE_BITS) << 55) | ((unsigned long long)el.x << 29) |
-			         ((unsigned long long)el.y << 3) | (unsigned long long)(t.idx8 & 7u);
+			key[i]  = ((unsigned long long)(t.key_hi >> TRI_PAIR_SHIFT) << 55) | ((unsigned long long)el.x << 29) |
+			         ((unsigned long long)el.y << 3) | (unsigned long long)(t.key_lo & 7u);
 			item[i] = it;
 		} else {
 			key[i]  = ~0ull;
