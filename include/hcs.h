@@ -189,6 +189,25 @@ int hcs_step(hcs_ctx *ctx, const double *xpos, const double *xmat, const double 
 /* same with DEVICE pointers; asynchronous on the context stream, results stay on the GPU */
 int hcs_step_device(hcs_ctx *ctx, const double *d_xpos, const double *d_xmat, const double *d_vel,
                     int with_sensors);
+/* Pipelined end-to-end step (SURVEY.md section 8b "Threading": the reference's physics thread calls the path once per
+ * mj_step; a batched caller overlaps its own work, and the copies, with the GPU).  HOST pointers as hcs_step; the call
+ * returns as soon as the work is queued: the host-to-device copies of this step's inputs run on a copy stream and
+ * overlap the kernels of the previous step, the results go to the CALLER-OWNED host buffers of `out` (any member may be
+ * NULL; pinned memory keeps the copies asynchronous) on a second copy stream while the next step's kernels run.  Two
+ * steps may be in flight; a third call first finishes the oldest one.  Inputs may be reused as soon as the call
+ * returns only if they are pageable (the copy is staged); pinned inputs must stay untouched until hcs_wait(ticket) of
+ * that step or the next hcs_step_async call but one.  Geometry, pairs and sensors are those of hcs_step. */
+typedef struct hcs_outputs {
+	double *geom_wrench;           /* [n_envs * n_geoms * 6], as hcs_get_geom_wrenches */
+	float **sensor_images;         /* [n flat sensors] -> [n_envs * cx * cy], as hcs_get_sensor_image (with_sensors) */
+	float **curved_values;         /* [n curved sensors] -> [n_envs * n_taxels] */
+	float **taxel_values;          /* [n taxel sensors] -> [n_envs * n_taxels] */
+	hcs_pair_result *pair_results; /* [n_envs * n_pairs] diagnostics, as hcs_get_pair_results */
+} hcs_outputs;
+int hcs_step_async(hcs_ctx *ctx, const double *xpos, const double *xmat, const double *vel, int with_sensors,
+                   const hcs_outputs *out, int64_t *ticket);
+/* blocks until the step's results are in the caller's buffers; HCS_OK or the step's capacity / range error */
+int hcs_wait(hcs_ctx *ctx, int64_t ticket);
 /* wait for the stream, check the capacity flags (HCS_E_CAPACITY) */
 int hcs_sync(hcs_ctx *ctx);
 /* copy the device results of the last hcs_step_device into the context's pinned host mirrors */

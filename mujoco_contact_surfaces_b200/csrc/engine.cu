@@ -124,6 +124,19 @@ struct hcs_ctx {
 	cudaEvent_t ev[8]{};
 	float stage_ms[7]{};
 	bool results_on_host = false, pairs_on_host = false, sensors_on_host = false, last_with_sensors = false;
+	// asynchronous end-to-end pipeline (hcs_step_async / hcs_wait): two slots of input staging and outputs, a copy-in
+	// and a copy-out stream, so that the H2D of step i+1 and the D2H of step i-1 overlap the kernels of step i
+	static constexpr int DEPTH = 2;
+	struct Slot {
+		double *d_xpos = nullptr, *d_xmat = nullptr, *d_vel = nullptr, *d_wrench = nullptr;
+		int32_t *h_flags = nullptr, *dh_flags = nullptr; // pinned + mapped: the last kernel of a step writes them
+		cudaEvent_t ev_in = nullptr, ev_free = nullptr, ev_kdone = nullptr, ev_done = nullptr;
+		int64_t ticket = -1; // step that occupies the slot
+		bool waited = true;
+		int status = HCS_OK;
+	} slot[DEPTH];
+	cudaStream_t copy_in = nullptr, copy_out = nullptr;
+	int64_t next_ticket = 0;
 	int64_t step_counter = 0;                 // steps launched so far
 	std::vector<EmittedCache> emitted_cache;  // hcs_get_emitted: per pair, the last step's list indexed by environment
 };
@@ -677,6 +690,9 @@ static void release_step_buffers(hcs_ctx *c)
 		cudaFreeHost(c->h_wrench), c->h_wrench = nullptr;
 	if (c->h_flags)
 		cudaFreeHost(c->h_flags), c->h_flags = nullptr;
+	for (hcs_ctx::Slot &sl : c->slot)
+		if (sl.h_flags)
+			cudaFreeHost(sl.h_flags), sl.h_flags = nullptr, sl.dh_flags = nullptr;
 	c->d_pairs = nullptr;
 }
 
@@ -787,6 +803,19 @@ static void finalize(hcs_ctx *c)
 	CK(cudaMallocHost((void **)&c->h_wrench, std::max<size_t>((size_t)n_env * ng * 6, 1) * sizeof(double)));
 	CK(cudaMallocHost((void **)&c->h_flags, 4 * sizeof(int32_t)));
 	memset(c->h_flags, 0, 4 * sizeof(int32_t));
+	for (hcs_ctx::Slot &sl : c->slot) {
+		sl.d_xpos   = dalloc<double>(c->step_allocs, (size_t)n_env * ng * 3);
+		sl.d_xmat   = dalloc<double>(c->step_allocs, (size_t)n_env * ng * 9);
+		sl.d_vel    = dalloc<double>(c->step_allocs, (size_t)n_env * ng * 6);
+		sl.d_wrench = dalloc<double>(c->step_allocs, (size_t)n_env * ng * 6);
+		CK(cudaMallocHost((void **)&sl.h_flags, 4 * sizeof(int32_t)));
+		memset(sl.h_flags, 0, 4 * sizeof(int32_t));
+		if (cudaHostGetDevicePointer((void **)&sl.dh_flags, sl.h_flags, 0) != cudaSuccess) {
+			sl.dh_flags = nullptr;
+			cudaGetLastError();
+		}
+		sl.ticket = -1, sl.waited = true, sl.status = HCS_OK;
+	}
 	// device addresses of the pinned mirrors (pinned allocations are mapped under unified addressing)
 	c->dh_wrench = nullptr, c->dh_flags = nullptr;
 	if (cudaHostGetDevicePointer((void **)&c->dh_wrench, c->h_wrench, 0) != cudaSuccess ||
@@ -801,13 +830,17 @@ static void finalize(hcs_ctx *c)
 }
 
 static void step_device(hcs_ctx *c, const double *xpos, const double *xmat, const double *vel, int with_sensors,
-                        bool direct_out = false)
+                        bool direct_out = false, double *wrench_dev = nullptr, int32_t *flags_mapped = nullptr)
 {
 	StepIO io = c->io;
 	io.xpos = xpos, io.xmat = xmat, io.vel = vel;
 	// direct_out: the finalize kernel also writes wrenches and flags into the context's mapped pinned mirrors
 	io.geom_wrench_host = direct_out ? c->dh_wrench : nullptr;
 	io.flags_host       = direct_out ? c->dh_flags : nullptr;
+	if (wrench_dev) // pipelined steps: per-slot device buffer for the wrenches, per-slot mapped flags
+		io.geom_wrench = wrench_dev;
+	if (flags_mapped)
+		io.flags_host = flags_mapped;
 	cudaStream_t s = c->stream;
 	int64_t k      = 0;
 	bool prof      = c->profiling;
@@ -1014,6 +1047,11 @@ int hcs_create(const hcs_config *cfg, hcs_ctx **out)
 			CK(cudaEventCreateWithFlags(&c->ev_join[i], cudaEventDisableTiming));
 		}
 		CK(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+		CK(cudaStreamCreateWithFlags(&c->copy_in, cudaStreamNonBlocking));
+		CK(cudaStreamCreateWithFlags(&c->copy_out, cudaStreamNonBlocking));
+		for (hcs_ctx::Slot &sl : c->slot)
+			for (cudaEvent_t *e : { &sl.ev_in, &sl.ev_free, &sl.ev_kdone, &sl.ev_done })
+				CK(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
 	} catch (const std::exception &ex) {
 		g_create_error = ex.what();
 		delete c;
@@ -1043,6 +1081,14 @@ void hcs_destroy(hcs_ctx *c)
 	}
 	if (c->ev_fork)
 		cudaEventDestroy(c->ev_fork);
+	for (hcs_ctx::Slot &sl : c->slot)
+		for (cudaEvent_t e : { sl.ev_in, sl.ev_free, sl.ev_kdone, sl.ev_done })
+			if (e)
+				cudaEventDestroy(e);
+	if (c->copy_in)
+		cudaStreamDestroy(c->copy_in);
+	if (c->copy_out)
+		cudaStreamDestroy(c->copy_out);
 	if (c->own_stream)
 		cudaStreamDestroy(c->stream);
 	delete c;
@@ -1464,6 +1510,114 @@ int hcs_step(hcs_ctx *c, const double *xpos, const double *xmat, const double *v
 	step_device(c, in[0], in[1], in[2], with_sensors);
 	fetch(c, with_sensors, /*with_pairs=*/false);
 	return check_flags(c);
+	API_END(c)
+}
+
+// status of a finished pipelined step from its slot's flag mirror
+static int slot_status(hcs_ctx *c, hcs_ctx::Slot &sl)
+{
+	int32_t keep[4];
+	memcpy(keep, c->h_flags, sizeof keep);
+	memcpy(c->h_flags, sl.h_flags, sizeof keep);
+	int st = check_flags(c);
+	memcpy(c->h_flags, keep, sizeof keep);
+	return st;
+}
+
+int hcs_step_async(hcs_ctx *c, const double *xpos, const double *xmat, const double *vel, int with_sensors,
+                   const hcs_outputs *out, int64_t *ticket)
+{
+	API_BEGIN(c)
+	if (!c->finalized) {
+		c->err = "hcs_step_async: call hcs_finalize first";
+		return HCS_E_NOT_FINALIZED;
+	}
+	if (!xpos || !xmat || !vel || !ticket) {
+		c->err = "hcs_step_async: null pose/velocity/ticket pointer";
+		return HCS_E_INVALID;
+	}
+	const int64_t t     = c->next_ticket;
+	hcs_ctx::Slot &sl   = c->slot[t % hcs_ctx::DEPTH];
+	if (!sl.waited) { // the caller runs more than DEPTH steps ahead: finish the slot's previous step, keep its status
+		CK(cudaEventSynchronize(sl.ev_done));
+		sl.status = slot_status(c, sl);
+		sl.waited = true;
+	}
+	const size_t n = (size_t)c->cfg.n_envs * c->geoms.size();
+	const int n_env = c->cfg.n_envs;
+	// copy-in stream: the slot's staging buffers are free once the kernels of the step that used them last are done
+	if (sl.ticket >= 0)
+		CK(cudaStreamWaitEvent(c->copy_in, sl.ev_free, 0));
+	CK(cudaMemcpyAsync(sl.d_xpos, xpos, n * 3 * sizeof(double), cudaMemcpyHostToDevice, c->copy_in));
+	CK(cudaMemcpyAsync(sl.d_xmat, xmat, n * 9 * sizeof(double), cudaMemcpyHostToDevice, c->copy_in));
+	CK(cudaMemcpyAsync(sl.d_vel, vel, n * 6 * sizeof(double), cudaMemcpyHostToDevice, c->copy_in));
+	CK(cudaEventRecord(sl.ev_in, c->copy_in));
+	// compute stream
+	cudaStream_t s = c->stream;
+	CK(cudaStreamWaitEvent(s, sl.ev_in, 0));
+	if (sl.ticket >= 0) // the slot's wrench buffer must have left for the host before the finalize kernel rewrites it
+		CK(cudaStreamWaitEvent(s, sl.ev_done, 0));
+	memset(sl.h_flags, 0, 4 * sizeof(int32_t));
+	const bool sensors = with_sensors != 0;
+	step_device(c, sl.d_xpos, sl.d_xmat, sl.d_vel, with_sensors, false, sl.d_wrench, sensors ? nullptr : sl.dh_flags);
+	CK(cudaEventRecord(sl.ev_free, s));
+	if (sensors || !sl.dh_flags) {
+		// sensor kernels follow the finalize kernel and raise flags of their own, and their device buffers exist once:
+		// their results (and the flags) leave on the compute stream, in order
+		CK(cudaMemcpyAsync(sl.h_flags, c->io.flags, 4 * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+		if (out && sensors) {
+			for (size_t i = 0; i < c->sensors.size(); ++i)
+				if (out->sensor_images && out->sensor_images[i])
+					CK(cudaMemcpyAsync(out->sensor_images[i], c->sensors[i].dev.image,
+					                   (size_t)n_env * c->sensors[i].cx * c->sensors[i].cy * sizeof(float), cudaMemcpyDeviceToHost, s));
+			for (size_t i = 0; i < c->curved.size(); ++i)
+				if (out->curved_values && out->curved_values[i])
+					CK(cudaMemcpyAsync(out->curved_values[i], c->curved[i].dev.values,
+					                   (size_t)n_env * c->curved[i].n_taxels() * sizeof(float), cudaMemcpyDeviceToHost, s));
+			for (size_t i = 0; i < c->taxel.size(); ++i)
+				if (out->taxel_values && out->taxel_values[i])
+					CK(cudaMemcpyAsync(out->taxel_values[i], c->taxel[i].dev.values,
+					                   (size_t)n_env * c->taxel[i].n_taxels() * sizeof(float), cudaMemcpyDeviceToHost, s));
+		}
+	}
+	if (out && out->pair_results) // diagnostics: one device buffer, so in order on the compute stream
+		CK(cudaMemcpyAsync(out->pair_results, c->io.pair_out, (size_t)n_env * c->pairs.size() * sizeof(hcs_pair_result),
+		                   cudaMemcpyDeviceToHost, s));
+	CK(cudaEventRecord(sl.ev_kdone, s));
+	// copy-out stream: the wrenches of this step go to the caller while the next step's kernels run
+	CK(cudaStreamWaitEvent(c->copy_out, sl.ev_kdone, 0));
+	if (out && out->geom_wrench)
+		CK(cudaMemcpyAsync(out->geom_wrench, sl.d_wrench, n * 6 * sizeof(double), cudaMemcpyDeviceToHost, c->copy_out));
+	CK(cudaEventRecord(sl.ev_done, c->copy_out));
+	sl.ticket = t, sl.waited = false, sl.status = HCS_OK;
+	c->next_ticket = t + 1;
+	*ticket        = t;
+	// the synchronous getters read the context's own buffers: the pipelined step left its wrenches in the slot
+	c->results_on_host = c->pairs_on_host = c->sensors_on_host = false;
+	return HCS_OK;
+	API_END(c)
+}
+
+int hcs_wait(hcs_ctx *c, int64_t ticket)
+{
+	API_BEGIN(c)
+	if (ticket < 0 || ticket >= c->next_ticket) {
+		c->err = "hcs_wait: unknown ticket";
+		return HCS_E_INVALID;
+	}
+	hcs_ctx::Slot &sl = c->slot[ticket % hcs_ctx::DEPTH];
+	if (sl.ticket != ticket) {
+		c->err = "hcs_wait: the ticket's results have been overwritten (more than 2 steps were in flight)";
+		return HCS_E_INVALID;
+	}
+	if (!sl.waited) {
+		CK(cudaEventSynchronize(sl.ev_done));
+		sl.status = slot_status(c, sl);
+		sl.waited = true;
+	}
+	if (sl.status != HCS_OK)
+		(void)slot_status(c, sl); // sets the error text again
+	return sl.status;
 	API_END(c)
 }
 

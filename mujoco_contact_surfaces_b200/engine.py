@@ -25,6 +25,13 @@ class HcsConfig(C.Structure):
                 ("face_vertices", C.c_int)]
 
 
+class HcsOutputs(C.Structure):
+    """hcs_outputs: caller-owned host buffers of a pipelined step (include/hcs.h)."""
+    _fields_ = [("geom_wrench", C.c_void_p), ("sensor_images", C.POINTER(C.c_void_p)),
+                ("curved_values", C.POINTER(C.c_void_p)), ("taxel_values", C.POINTER(C.c_void_p)),
+                ("pair_results", C.c_void_p)]
+
+
 PAIR_RESULT_DTYPE = np.dtype([("F", "<f8", 3), ("tau", "<f8", 3), ("centroid", "<f8", 3), ("area", "<f8"),
                               ("gM", "<i4"), ("gN", "<i4"), ("n_polygons", "<i4"), ("n_faces", "<i4"),
                               ("n_points", "<i4"), ("n_candidates", "<i4"), ("n_clipped", "<i4"),
@@ -44,7 +51,7 @@ ABI_SYMBOLS = [
     "hcs_get_mesh", "hcs_get_lbvh", "hcs_get_counters", "hcs_set_profiling", "hcs_get_stage_ms", "hcs_version",
     "hcs_add_curved_sensor", "hcs_curved_sensor_info", "hcs_get_curved_values", "hcs_device_curved_values",
     "hcs_add_taxel_sensor", "hcs_get_taxel_values", "hcs_device_taxel_values", "hcs_get_face_vertices",
-    "hcs_update_flat_sensor",
+    "hcs_update_flat_sensor", "hcs_step_async", "hcs_wait",
 ]
 
 _LIB = None
@@ -82,6 +89,8 @@ def load_library():
         L.hcs_device_geom_wrenches.argtypes = [C.c_void_p]
         L.hcs_device_sensor_image.argtypes = [C.c_void_p, C.c_int]
         L.hcs_step_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+        L.hcs_step_async.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        L.hcs_wait.argtypes = [C.c_void_p, C.c_int64]
         L.hcs_step.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
         L.hcs_add_flat_sensor.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_int, C.c_int, C.c_float]
         L.hcs_update_flat_sensor.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float]
@@ -195,6 +204,24 @@ class HydroelasticEngine:
     def step_raw(self, xpos_ptr, xmat_ptr, vel_ptr, with_sensors=False):
         """hcs_step with raw host addresses (e.g. pinned torch tensors)."""
         self._check(self.L.hcs_step(self.h, xpos_ptr, xmat_ptr, vel_ptr, int(with_sensors)))
+
+    def step_async(self, xpos_ptr, xmat_ptr, vel_ptr, with_sensors=False, geom_wrench_ptr=None, sensor_image_ptrs=None,
+                   pair_results_ptr=None):
+        """hcs_step_async with raw HOST addresses (pinned memory keeps the copies asynchronous): queues the step and
+        returns its ticket; results land in the caller's buffers (wait(ticket) tells when)."""
+        out = HcsOutputs()
+        out.geom_wrench = geom_wrench_ptr
+        out.pair_results = pair_results_ptr
+        keep = None
+        if sensor_image_ptrs:
+            keep = (C.c_void_p * len(sensor_image_ptrs))(*sensor_image_ptrs)
+            out.sensor_images = C.cast(keep, C.POINTER(C.c_void_p))
+        t = C.c_int64(-1)
+        self._check(self.L.hcs_step_async(self.h, xpos_ptr, xmat_ptr, vel_ptr, int(with_sensors), C.byref(out), C.byref(t)))
+        return t.value
+
+    def wait(self, ticket):
+        self._check(self.L.hcs_wait(self.h, C.c_int64(ticket)))
 
     def step_device(self, xpos_ptr, xmat_ptr, vel_ptr, with_sensors=False):
         """Asynchronous step on device pointers (ints, e.g. torch.Tensor.data_ptr())."""
