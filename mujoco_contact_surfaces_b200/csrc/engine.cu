@@ -521,6 +521,12 @@ static void build_pairs(hcs_ctx *c)
 					P.acc_scale   = std::ldexp(1.0, -k);
 					P.acc_unscale = std::ldexp(1.0, k);
 				}
+				// flat broadphase: alive-query records, one per (env, query element) at most (4 GB cap; overflow is reported)
+				P.alive = nullptr, P.alive_cap = 0;
+				if (P.kind != PAIR_SOFT_PLANE) {
+					P.alive_cap = (int)std::min<long>((long)n_env * P.nq, 32L << 20);
+					P.alive     = dalloc<float>(c->step_allocs, (size_t)P.alive_cap * ALIVE_WORDS);
+				}
 				P.counters    = c->d_counters + 6 + PAIR_COUNTERS * pi;
 				P.pair_ctx    = dalloc<double>(c->step_allocs, (size_t)n_env * PAIR_CTX_DOUBLES);
 				CK(cudaMemsetAsync(P.accum, 0, (size_t)n_env * ACC_WORDS * sizeof(int64_t), c->stream)); // the finalize kernel keeps them zero

@@ -122,10 +122,14 @@ struct PairDesc {
 	                       // clears what it has read)
 	double acc_scale, acc_unscale; // 2^-k / 2^k: contributions are scaled into the accumulators' range (exact)
 	int32_t *counters;     // [0] candidates in the flat list, [1] next 32-candidate chunk of the narrowphase,
-	                       // [2] next (env, slice) unit of the broadphase, [3] -; zeroed per step
+	                       // [2] next (env, slice) unit / next batch of alive queries of the broadphase, [3] alive
+	                       // queries (flat broadphase); zeroed per step
+	float *alive;          // [alive_cap][ALIVE_WORDS] query elements that passed the root test (kernels_broadphase.cu)
+	int alive_cap;
 	double *pair_ctx;      // [n_env][PAIR_CTX_DOUBLES] poses, velocities, X_AB written by the broadphase
 };
 constexpr int PAIR_COUNTERS = 4;
+constexpr int ALIVE_WORDS   = 32; // floats per alive-query record (128 B)
 // candidate record .y = tree element | skip mask << 28: planes of the tet the clip may leave out (narrow.cuh cand_tet_tri)
 constexpr int CAND_MASK_SHIFT      = 28;
 constexpr unsigned CAND_ELEM_MASK  = (1u << CAND_MASK_SHIFT) - 1u;

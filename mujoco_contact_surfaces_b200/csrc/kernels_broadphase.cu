@@ -60,10 +60,12 @@ constexpr int SWEEP_MAX_TREE = HCS_SWEEP_MAX_TREE; // trees up to this many tets
 constexpr int ITEM_SHIFT = 26; // queue item = slot (6 bits) << 26 | node or tet index (26 bits)
 constexpr unsigned ITEM_MASK = (1u << ITEM_SHIFT) - 1u;
 
-// QF = floats kept per query (9: triangle vertices, 12: tet vertices), QX = extra rows (soft-soft)
-template <int QF, int QX>
+// QF = floats kept per query (9: triangle vertices, 12: tet vertices), QX = extra rows (soft-soft); NQ / NS: capacity of
+// the node queue / the candidate stage
+template <int QF, int QX, int NQ = NODE_Q, int NS = STAGE>
 struct __align__(16) WarpQueues {
-	unsigned nodeq[NODE_Q];
+	static constexpr int node_cap = NQ, stage_cap = NS;
+	unsigned nodeq[NQ];
 	unsigned leafq[LEAF_Q];
 	float qbox[6][BP_SLOTS];
 	float qpl[4][BP_SLOTS];  // soft-rigid: the query triangle's plane (unit normal, offset) in A's frame;
@@ -72,12 +74,18 @@ struct __align__(16) WarpQueues {
 	float qm[BP_SLOTS];      // soft-rigid: the filter's margin (4e-6 x the largest coordinate involved); soft-soft: that coordinate
 	float qx[QX > 0 ? QX : 1][BP_SLOTS]; // soft-soft: the query tet's unit gradient in A's frame (0..2), L1 norm of its gradient (3)
 	int qid[BP_SLOTS];
-	uint2 stage[STAGE];  // (query, tet | skip << 28) waiting to be appended to the pair's flat list
-	double xab[12];      // R_AB (row-major) + p_AB of the unit, for the exact fallbacks of the leaf tests
-	double pba[4];       // origin of A in B (p_NMo of field_intersection.cc)
+	int qenv[BP_SLOTS];  // flat traversal: the slot's environment (slots of one warp belong to several)
+	int qev[BP_SLOTS];   // flat traversal: leaf hits of the slot's query (pair-evals started, per environment)
+	uint2 stage[NS];     // (query or slot, tet | skip << 28) waiting to be appended to the pair's flat list
+	double xab[12];      // per-unit kernel: R_AB (row-major) + p_AB of the unit, for the exact fallbacks of the leaf tests
+	double pba[4];       //                  origin of A in B (p_NMo of field_intersection.cc)
 };
 typedef WarpQueues<9, 0> QueuesRigid;
 typedef WarpQueues<12, 4> QueuesSoft;
+// flat traversal (bp_traverse_kernel): smaller queues, so that more warps fit into an SM's shared memory
+constexpr int FT_NODE_Q = 512, FT_STAGE = 128;
+typedef WarpQueues<9, 0, FT_NODE_Q, FT_STAGE> FlatQueuesRigid;
+typedef WarpQueues<12, 4, FT_NODE_Q, FT_STAGE> FlatQueuesSoft;
 
 extern __shared__ __align__(16) unsigned char bp_smem[];
 
@@ -135,6 +143,18 @@ __device__ __forceinline__ Xform unit_xab(const Q &W)
 	return X;
 }
 
+// flat traversal: the slot's environment decides; the prepare kernel wrote the pair's context block
+template <class Q>
+__device__ __forceinline__ Xform slot_xab(const PairDesc &P, const Q &W, int s)
+{
+	const double *g = P.pair_ctx + (size_t)W.qenv[s] * PAIR_CTX_DOUBLES + CTX_RAB;
+	const D4 a = ld4(g), b = ld4(g + 4), c = ld4(g + 8);
+	Xform X;
+	X.R[0] = a.x, X.R[1] = a.y, X.R[2] = a.z, X.R[3] = a.w, X.R[4] = b.x, X.R[5] = b.y, X.R[6] = b.z, X.R[7] = b.w, X.R[8] = c.x;
+	X.p = mk(c.y, c.z, c.w);
+	return X;
+}
+
 // ---- leaf tests ------------------------------------------------------------------------------------
 // Soft-rigid.  Conservative float filter: the exact tests it stands for are early-outs, i.e. a pair
 // they reject clips to nothing, so rejecting a SUBSET of those pairs changes no result, and a pair that slips through is
@@ -142,7 +162,8 @@ __device__ __forceinline__ Xform unit_xab(const Q &W)
 // coordinate involved) is > 5x the worst rounding of the float dot products and of the inputs' conversion.  NaNs compare
 // false and fall through.  Only the gradient cull is a semantic filter: it is decided in float when clear by 1e-5,
 // otherwise by the reference's fp64 expression.  s: slot of the query; skip: tet planes the clip may leave out.
-__device__ __forceinline__ bool leaf_test_rigid(const PairDesc &P, const QueuesRigid &W, int s, int tet, int &skip)
+template <bool FLAT, class Q>
+__device__ __forceinline__ bool leaf_test_rigid(const PairDesc &P, const Q &W, int s, int tet, int &skip)
 {
 	skip = 0;
 	const TetLeaf32 *tl = P.A.tet_leaf32 + tet;
@@ -153,7 +174,7 @@ __device__ __forceinline__ bool leaf_test_rigid(const PairDesc &P, const QueuesR
 		return false;
 	if (cosg < (float)HCS_COS_ALPHA + 1e-5f) { // undecided in float: the reference's expression in double
 		const TriVerts tr = load_tri(P.B.tris + W.qid[s]);
-		const Xform X_AB  = unit_xab(W);
+		const Xform X_AB  = FLAT ? slot_xab(P, W, s) : unit_xab(W);
 		if (!(dot(load_ghat(P.A.tet_field + tet), rot(X_AB.R, tr.n)) > HCS_COS_ALPHA))
 			return false;
 	}
@@ -217,7 +238,8 @@ __device__ __forceinline__ bool leaf_test_rigid(const PairDesc &P, const QueuesR
 // otherwise the pair takes the exact path: CalcEquilibriumPlane + the two IsPlaneNormalAlongPressureGradient culls of
 // field_intersection.cc (same arithmetic as the clip kernel), then: the equal-pressure plane must cut BOTH tets.
 // Every comparison is written so that a NaN or an infinity leads to the exact path.
-__device__ __forceinline__ bool leaf_test_soft(const PairDesc &P, const QueuesSoft &W, int s, int tet)
+template <bool FLAT, class Q>
+__device__ __forceinline__ bool leaf_test_soft(const PairDesc &P, const Q &W, int s, int tet)
 {
 	bool keep = true, need_exact = true;
 	{
@@ -259,8 +281,8 @@ __device__ __forceinline__ bool leaf_test_soft(const PairDesc &P, const QueuesSo
 	}
 	if (!need_exact)
 		return keep;
-	const Xform X_AB   = unit_xab(W);
-	const D3 p_BAo     = mk(W.pba[0], W.pba[1], W.pba[2]);
+	const Xform X_AB   = FLAT ? slot_xab(P, W, s) : unit_xab(W);
+	const D3 p_BAo     = FLAT ? xyz(ld4(P.pair_ctx + (size_t)W.qenv[s] * PAIR_CTX_DOUBLES + CTX_PBA)) : mk(W.pba[0], W.pba[1], W.pba[2]);
 	const TetField *f0 = P.A.tet_field + tet, *f1 = P.B.tet_field + W.qid[s];
 	const D4 ge0 = load_grad_e0(f0), ge1 = load_grad_e0(f1);
 	D3 grad0 = xyz(ge0), grad1_N = xyz(ge1);
@@ -485,9 +507,9 @@ __global__ void __launch_bounds__(BP_BLOCK, BP_CTAS_PER_SM) broadphase_kernel(Pa
 						const unsigned raw = W.leafq[n_leaf - k + lane];
 						s = (int)(raw >> ITEM_SHIFT), tet = raw & ITEM_MASK;
 						if constexpr (!QTET)
-							keep = leaf_test_rigid(P, W, s, (int)tet, skip);
+							keep = leaf_test_rigid<false>(P, W, s, (int)tet, skip);
 						else
-							keep = leaf_test_soft(P, W, s, (int)tet);
+							keep = leaf_test_soft<false>(P, W, s, (int)tet);
 					}
 					n_leaf -= k;
 					evals += k;
@@ -593,6 +615,349 @@ __global__ void __launch_bounds__(BP_BLOCK, BP_CTAS_PER_SM) broadphase_kernel(Pa
 	}
 }
 
+// =====================================================================================================
+// Flat broadphase of the tree kinds (round 2): prepare + traverse.
+//
+// The per-unit kernel above gives every (env, query slice) its own warp: on the small scenes of configs 1 - 4 a unit has a
+// dozen alive queries at most, so 12 of 32 lanes worked per iteration, every lane repeated the unit's fp64 pose algebra,
+// and the kernel sat at 128 registers / 16 warps per SM.  Since the exact accumulators (hcs_internal.h) nothing
+// downstream depends on the order of candidates, so queries of different environments may share a warp:
+//   bp_prepare_kernel   one thread per (env, query element): relative pose, query into A's frame, root-box test; the
+//                       alive ones leave as 128-byte float records (box, plane, vertices, margin, ids) in the pair's alive
+//                       list (ballot + one atomicAdd per warp).  All the fp64 work of the broadphase is here.
+//   bp_traverse_kernel  persistent warps pull batches of 8 - 16 alive records, whatever their environments, and walk the
+//                       tree with the two shared queues as before: float only, all slots alive, more warps per SM.
+// =====================================================================================================
+constexpr int AR_BOX = 0, AR_PL = 6, AR_VF = 10, AR_M = 22, AR_QX = 23, AR_QID = 27, AR_ENV = 28;
+static_assert(ALIVE_WORDS == 32, "alive records are eight float4");
+#ifndef HCS_FT_CTAS_PER_SM
+#define HCS_FT_CTAS_PER_SM 6
+#endif
+constexpr int FT_CTAS_PER_SM = HCS_FT_CTAS_PER_SM;
+constexpr int PREP_BLOCK = 128;
+
+template <bool QTET>
+__global__ void __launch_bounds__(PREP_BLOCK) bp_prepare_kernel(PairDesc P, StepIO io)
+{
+	pdl_release();
+	const long f     = (long)blockIdx.x * PREP_BLOCK + threadIdx.x;
+	const long total = (long)io.n_env * P.nq;
+	const int lane   = threadIdx.x & 31;
+	bool alive       = f < total;
+	float rec[ALIVE_WORDS];
+#pragma unroll
+	for (int k = 0; k < ALIVE_WORDS; ++k)
+		rec[k] = 0.f;
+	if (alive) {
+		const int env = (int)(f / P.nq), q = (int)(f - (long)env * P.nq);
+		const Xform X_WA = load_pose(io.xpos, io.xmat, io.n_geoms, env, P.gA);
+		const Xform X_WB = load_pose(io.xpos, io.xmat, io.n_geoms, env, P.gB);
+		const Xform X_AB = invert_and_compose(X_WA, X_WB);
+		const D3 p_BAo   = -rotT(X_AB.R, X_AB.p); // origin of A expressed in B (p_NMo of field_intersection.cc)
+		if (q == 0)
+			write_pair_ctx(P, io, env, X_WA, X_WB, X_AB, p_BAo);
+		{ // pair-level reject on bounding spheres
+			D3 ca = apply(X_WA, mk(P.A.bound_c[0], P.A.bound_c[1], P.A.bound_c[2]));
+			D3 cb = apply(X_WB, mk(P.B.bound_c[0], P.B.bound_c[1], P.B.bound_c[2]));
+			D3 d  = ca - cb;
+			double rr = P.A.bound_r + P.B.bound_r + 1e-9;
+			alive     = !(dot(d, d) > rr * rr);
+		}
+		if (alive) {
+			const float leaf_scale =
+			    (float)(fmax(fmax(fabs(P.A.bound_c[0]), fabs(P.A.bound_c[1])), fabs(P.A.bound_c[2])) + P.A.bound_r);
+			double v[12];
+			double lo[3] = { 1e300, 1e300, 1e300 }, hi[3] = { -1e300, -1e300, -1e300 };
+			const double *vp = QTET ? reinterpret_cast<const double *>(P.B.tet_geom + q) : reinterpret_cast<const double *>(P.B.tris + q);
+			const D4 r0 = ld4(vp), r1 = ld4(vp + 4), r2 = ld4(vp + 8);
+			const D3 qv[4] = { mk(r0.x, r0.y, r0.z), mk(r0.w, r1.x, r1.y), mk(r1.z, r1.w, r2.x), mk(r2.y, r2.z, r2.w) };
+			constexpr int nvq = QTET ? 4 : 3;
+#pragma unroll
+			for (int i = 0; i < nvq; ++i) {
+				D3 p = apply(X_AB, qv[i]);
+				v[3 * i] = p.x, v[3 * i + 1] = p.y, v[3 * i + 2] = p.z;
+				lo[0] = fmin(lo[0], p.x), lo[1] = fmin(lo[1], p.y), lo[2] = fmin(lo[2], p.z);
+				hi[0] = fmax(hi[0], p.x), hi[1] = fmax(hi[1], p.y), hi[2] = fmax(hi[2], p.z);
+			}
+			if (!QTET) {
+				const D3 nS = rot(X_AB.R, qv[3]);
+				v[9] = nS.x, v[10] = nS.y, v[11] = nS.z;
+			}
+#pragma unroll
+			for (int a = 0; a < 3; ++a) {
+				rec[AR_BOX + a]     = __double2float_rd(lo[a] - 1e-9);
+				rec[AR_BOX + 3 + a] = __double2float_ru(hi[a] + 1e-9);
+			}
+			alive = rec[0] <= P.A.root_hi[0] && rec[3] >= P.A.root_lo[0] && rec[1] <= P.A.root_hi[1] && rec[4] >= P.A.root_lo[1] &&
+			        rec[2] <= P.A.root_hi[2] && rec[5] >= P.A.root_lo[2];
+			if (alive) {
+				float big = leaf_scale;
+				constexpr int nf = QTET ? 12 : 9;
+#pragma unroll
+				for (int k = 0; k < nf; ++k) {
+					rec[AR_VF + k] = (float)v[k];
+					big            = fmaxf(big, fabsf((float)v[k]));
+				}
+				if (!QTET) {
+					rec[AR_PL] = (float)v[9], rec[AR_PL + 1] = (float)v[10], rec[AR_PL + 2] = (float)v[11];
+					rec[AR_PL + 3] = (float)(v[9] * v[0] + v[10] * v[1] + v[11] * v[2]);
+					rec[AR_M]      = 4e-6f * big + 1e-30f;
+				} else {
+					// what the float filter of the soft-soft leaf test needs of the query tet, computed once per query in
+					// double: gradient and unit gradient rotated into A's frame, field value at A's origin
+					const TetField *f1 = P.B.tet_field + q;
+					const D4 ge1       = load_grad_e0(f1);
+					const D3 g1M = rot(X_AB.R, xyz(ge1)), gh1M = rot(X_AB.R, load_ghat(f1));
+					rec[AR_PL] = (float)g1M.x, rec[AR_PL + 1] = (float)g1M.y, rec[AR_PL + 2] = (float)g1M.z;
+					rec[AR_PL + 3] = (float)(dot(xyz(ge1), p_BAo) + ge1.w);
+					rec[AR_QX] = (float)gh1M.x, rec[AR_QX + 1] = (float)gh1M.y, rec[AR_QX + 2] = (float)gh1M.z;
+					rec[AR_QX + 3] = (float)(fabs(g1M.x) + fabs(g1M.y) + fabs(g1M.z));
+					rec[AR_M]      = big;
+				}
+				rec[AR_QID] = __int_as_float(q);
+				rec[AR_ENV] = __int_as_float(env);
+			}
+		}
+	}
+	const unsigned m_alive = __ballot_sync(FULL_MASK, alive);
+	if (m_alive == 0)
+		return;
+	int base = 0;
+	if (lane == 0)
+		base = atomicAdd(P.counters + 3, __popc(m_alive));
+	base = __shfl_sync(FULL_MASK, base, 0);
+	if (alive) {
+		const int slot = base + __popc(m_alive & ((1u << lane) - 1u));
+		if (slot < P.alive_cap) {
+			float4 *dst = reinterpret_cast<float4 *>(P.alive) + (size_t)slot * (ALIVE_WORDS / 4);
+#pragma unroll
+			for (int k = 0; k < ALIVE_WORDS / 4; ++k)
+				dst[k] = make_float4(rec[4 * k], rec[4 * k + 1], rec[4 * k + 2], rec[4 * k + 3]);
+		} else {
+			atomicOr(io.flags, 8);
+		}
+	}
+}
+
+// append the staged candidates (slot, tet | skip) of the current batch to the pair's flat list
+template <class Q>
+__device__ __forceinline__ void flush_flat(const PairDesc &P, const StepIO &io, Q &W, int lane, int &n_stage)
+{
+	int base = 0;
+	if (lane == 0)
+		base = atomicAdd(P.counters, n_stage);
+	base = __shfl_sync(FULL_MASK, base, 0);
+	for (int j = lane; j < n_stage; j += 32) {
+		if (base + j < P.contrib_cap) {
+			const uint2 cd   = W.stage[j];
+			P.flat[base + j] = make_uint4((unsigned)W.qid[cd.x], cd.y, (unsigned)W.qenv[cd.x], 0u);
+		} else {
+			atomicOr(io.flags, 8);
+		}
+	}
+	__syncwarp();
+	n_stage = 0;
+}
+
+template <bool QTET, bool SWEEP>
+__global__ void __launch_bounds__(BP_BLOCK, FT_CTAS_PER_SM) bp_traverse_kernel(PairDesc P, StepIO io, int fixed_slots)
+{
+	typedef typename std::conditional<QTET, FlatQueuesSoft, FlatQueuesRigid>::type Queues;
+	constexpr int NODE_CAP = Queues::node_cap, STAGE_CAP = Queues::stage_cap;
+	Queues &W              = reinterpret_cast<Queues *>(bp_smem)[threadIdx.x >> 5];
+	const int lane         = threadIdx.x & 31;
+	const unsigned lt_mask = (1u << lane) - 1u;
+	const float4 *nodes4   = reinterpret_cast<const float4 *>(P.A.nodes);
+	pdl_release(); // the pair's narrowphase may become resident while this grid drains (it waits for our completion)
+	pdl_wait();    // the prepare grid has completed: alive list, its count and the context blocks are visible
+	int n_alive = P.counters[3];
+	if (n_alive > P.alive_cap)
+		n_alive = P.alive_cap; // (the prepare kernel raised the flag)
+	// batch size: 16 alive queries per warp, 8 when that would leave resident warps of the grid without a batch.
+	// Measured (scripts/r02_run3.sh, broadphase stage): C1 x 4096 46.4 / 44.6 / 55.4 us, C3 x 4096 0.670 / 0.576 / 0.563 ms,
+	// C5 x 1024 - / 15.5 / 20.2 ms for 8 / 16 / 32: full batches fill the lanes of an iteration but leave fewer warps.
+	const int total_warps = (int)gridDim.x * BP_WARPS;
+	int slots             = n_alive < 8 * total_warps ? 8 : 16;
+	if (fixed_slots > 0) // tuning override (HCS_FT_SLOTS)
+		slots = fixed_slots;
+	const int n_batches = (n_alive + slots - 1) / slots;
+
+	for (;;) {
+		int batch = 0;
+		if (lane == 0)
+			batch = atomicAdd(P.counters + 2, 1);
+		batch = __shfl_sync(FULL_MASK, batch, 0);
+		if (batch >= n_batches)
+			break;
+		const int first = batch * slots, n_slots = min(slots, n_alive - first);
+		if (lane < n_slots) {
+			const float4 *src = reinterpret_cast<const float4 *>(P.alive) + (size_t)(first + lane) * (ALIVE_WORDS / 4);
+			float rec[ALIVE_WORDS];
+#pragma unroll
+			for (int k = 0; k < ALIVE_WORDS / 4; ++k) {
+				const float4 t = src[k];
+				rec[4 * k] = t.x, rec[4 * k + 1] = t.y, rec[4 * k + 2] = t.z, rec[4 * k + 3] = t.w;
+			}
+#pragma unroll
+			for (int k = 0; k < 6; ++k)
+				W.qbox[k][lane] = rec[AR_BOX + k];
+#pragma unroll
+			for (int k = 0; k < 4; ++k)
+				W.qpl[k][lane] = rec[AR_PL + k];
+			constexpr int nf = QTET ? 12 : 9;
+#pragma unroll
+			for (int k = 0; k < nf; ++k)
+				W.qvf[k][lane] = rec[AR_VF + k];
+			W.qm[lane] = rec[AR_M];
+			if (QTET) {
+#pragma unroll
+				for (int k = 0; k < 4; ++k)
+					W.qx[k][lane] = rec[AR_QX + k];
+			}
+			W.qid[lane]  = __float_as_int(rec[AR_QID]);
+			W.qenv[lane] = __float_as_int(rec[AR_ENV]);
+			W.qev[lane]  = 0;
+			if (!SWEEP)
+				W.nodeq[lane] = (unsigned)lane << ITEM_SHIFT; // (slot, root)
+		}
+		__syncwarp();
+		int n_stage = 0, n_leaf = 0;
+		int n_node  = SWEEP ? 0 : n_slots;
+		int sw_s = 0, sw_t = 0; // sweep position: slot, first tet of the next pass
+		const int sw_slots = SWEEP ? n_slots : 0;
+
+#pragma unroll 1
+		while (n_node > 0 || n_leaf > 0 || sw_s < sw_slots) {
+			if (n_leaf >= 32 || (n_node == 0 && sw_s >= sw_slots)) {
+				// ---- drain up to 32 leaf items: leaf test, survivors are staged ----
+				const int k = min(32, n_leaf);
+				bool keep   = false;
+				int skip    = 0, s = 0;
+				unsigned tet = 0;
+				if (lane < k) {
+					const unsigned raw = W.leafq[n_leaf - k + lane];
+					s = (int)(raw >> ITEM_SHIFT), tet = raw & ITEM_MASK;
+					atomicAdd(&W.qev[s], 1);
+					if constexpr (!QTET)
+						keep = leaf_test_rigid<true>(P, W, s, (int)tet, skip);
+					else
+						keep = leaf_test_soft<true>(P, W, s, (int)tet);
+				}
+				n_leaf -= k;
+				const unsigned mk_ = __ballot_sync(FULL_MASK, keep);
+				if (keep)
+					W.stage[n_stage + __popc(mk_ & lt_mask)] = make_uint2((unsigned)s, tet | ((unsigned)skip << CAND_MASK_SHIFT));
+				n_stage += __popc(mk_);
+				__syncwarp();
+				if (n_stage > STAGE_CAP - 32) // the next drain may not fit
+					flush_flat(P, io, W, lane, n_stage);
+			} else if (sw_s < sw_slots) {
+				// ---- sweep pass (small trees): slot sw_s against the boxes of tets sw_t .. sw_t + 31 ----
+				const int t = sw_t + lane;
+				bool hit    = false;
+				if (t < P.n_tree) {
+					float qb[6];
+#pragma unroll
+					for (int a = 0; a < 6; ++a)
+						qb[a] = W.qbox[a][sw_s];
+					float pl[4] = { 0.f, 0.f, 0.f, 0.f };
+					if (!QTET) {
+#pragma unroll
+						for (int a = 0; a < 4; ++a)
+							pl[a] = W.qpl[a][sw_s];
+					}
+					const F8 tb = *reinterpret_cast<const F8 *>(P.A.tet_box32 + t);
+					hit = child_overlap<!QTET>(qb, pl, tb.a[0], tb.a[1], tb.a[2], tb.a[3], tb.a[4], tb.a[5]);
+				}
+				const unsigned mh = __ballot_sync(FULL_MASK, hit);
+				if (hit)
+					W.leafq[n_leaf + __popc(mh & lt_mask)] = ((unsigned)sw_s << ITEM_SHIFT) | (unsigned)t;
+				n_leaf += __popc(mh);
+				sw_t += 32;
+				if (sw_t >= P.n_tree)
+					sw_t = 0, ++sw_s;
+				__syncwarp();
+			} else {
+				// ---- node iteration: pop k items, push <= 2k (near the capacity fewer are popped: depth-first walk) ----
+				const int k = max(1, min(min(32, n_node), NODE_CAP - n_node));
+				bool pushL = false, pushR = false, leafL = false, leafR = false;
+				int cl = 0, cr = 0;
+				unsigned s = 0;
+				if (lane < k) {
+					const unsigned raw = W.nodeq[n_node - k + lane];
+					s                  = raw >> ITEM_SHIFT;
+					float qb[6];
+#pragma unroll
+					for (int a = 0; a < 6; ++a)
+						qb[a] = W.qbox[a][s];
+					float pl[4] = { 0.f, 0.f, 0.f, 0.f };
+					if (!QTET) {
+#pragma unroll
+						for (int a = 0; a < 4; ++a)
+							pl[a] = W.qpl[a][s];
+					}
+					const float4 *nd = nodes4 + 4 * (size_t)(raw & ITEM_MASK);
+					const float4 a = nd[0], b = nd[1], c = nd[2], d = nd[3];
+					cl = __float_as_int(d.x), cr = __float_as_int(d.y);
+					if (child_overlap<!QTET>(qb, pl, a.x, a.y, a.z, a.w, b.x, b.y)) {
+						leafL = cl < 0;
+						pushL = !leafL;
+					}
+					if (child_overlap<!QTET>(qb, pl, b.z, b.w, c.x, c.y, c.z, c.w)) {
+						leafR = cr < 0;
+						pushR = !leafR;
+					}
+				}
+				n_node -= k;
+				__syncwarp();
+				const unsigned mL = __ballot_sync(FULL_MASK, pushL), mR = __ballot_sync(FULL_MASK, pushR);
+				const unsigned lL = __ballot_sync(FULL_MASK, leafL), lR = __ballot_sync(FULL_MASK, leafR);
+				const int nL = __popc(mL), nR = __popc(mR), nlL = __popc(lL), nlR = __popc(lR);
+				if (n_node + nL + nR > NODE_CAP) { // only with k forced to 1 on a full queue: a tree deeper than NODE_CAP / 32
+					if (lane == 0)
+						atomicOr(io.flags + 1, 1);
+					n_node = 0;
+					n_leaf = 0;
+					break;
+				}
+				if (pushL)
+					W.nodeq[n_node + __popc(mL & lt_mask)] = (s << ITEM_SHIFT) | (unsigned)cl;
+				if (pushR)
+					W.nodeq[n_node + nL + __popc(mR & lt_mask)] = (s << ITEM_SHIFT) | (unsigned)cr;
+				if (leafL)
+					W.leafq[n_leaf + __popc(lL & lt_mask)] = (s << ITEM_SHIFT) | (unsigned)~cl;
+				if (leafR)
+					W.leafq[n_leaf + nlL + __popc(lR & lt_mask)] = (s << ITEM_SHIFT) | (unsigned)~cr;
+				n_node += nL + nR;
+				n_leaf += nlL + nlR;
+				__syncwarp();
+			}
+		}
+		if (n_stage > 0)
+			flush_flat(P, io, W, lane, n_stage);
+		// pair-evals started (LBVH leaf hits), per environment
+		if (lane < n_slots && W.qev[lane] > 0)
+			atomicAdd(reinterpret_cast<unsigned long long *>(P.accum + (size_t)W.qenv[lane] * ACC_WORDS + ACC_NEVALS),
+			          (unsigned long long)W.qev[lane]);
+		__syncwarp();
+	}
+}
+
+template <bool QTET, bool SWEEP>
+static void launch_flat_bp(const PairDesc &P, const StepIO &io, cudaStream_t s)
+{
+	typedef typename std::conditional<QTET, FlatQueuesSoft, FlatQueuesRigid>::type Queues;
+	const long total = (long)io.n_env * P.nq;
+	bp_prepare_kernel<QTET><<<(unsigned)((total + PREP_BLOCK - 1) / PREP_BLOCK), PREP_BLOCK, 0, s>>>(P, io);
+	const int smem = (int)sizeof(Queues) * BP_WARPS;
+	auto kernel    = bp_traverse_kernel<QTET, SWEEP>;
+	ensure_dynamic_smem(kernel, smem);
+	// persistent warps; never more than one warp per 8 query elements
+	const int grid = (int)std::max<long>(1, std::min<long>((total + 8 * BP_WARPS - 1) / (8 * BP_WARPS), (long)io.n_sms * FT_CTAS_PER_SM));
+	static const int fixed_slots = getenv("HCS_FT_SLOTS") ? std::max(1, std::min(32, atoi(getenv("HCS_FT_SLOTS")))) : 0;
+	launch_chained(kernel, dim3(grid), dim3(BP_BLOCK), (size_t)smem, s, P, io, fixed_slots);
+}
+
 template <int KIND, bool SWEEP>
 static void launch_bp(const PairDesc &P, const StepIO &io, cudaStream_t s, int grid)
 {
@@ -609,6 +974,14 @@ void launch_broadphase(const PairDesc &P, const StepIO &io, cudaStream_t s)
 		return;
 	const int grid   = (int)std::max<long>(1, std::min<long>((units + BP_WARPS - 1) / BP_WARPS, (long)io.n_sms * BP_CTAS_PER_SM));
 	const bool sweep = P.n_tree <= SWEEP_MAX_TREE;
+	static const bool legacy = getenv("HCS_BP_LEGACY") != nullptr; // the per-unit kernel for the tree kinds (A/B measurements)
+	if (!legacy && P.alive && (P.kind == PAIR_SOFT_RIGID || P.kind == PAIR_SOFT_SOFT)) {
+		if (P.kind == PAIR_SOFT_RIGID)
+			sweep ? launch_flat_bp<false, true>(P, io, s) : launch_flat_bp<false, false>(P, io, s);
+		else
+			sweep ? launch_flat_bp<true, true>(P, io, s) : launch_flat_bp<true, false>(P, io, s);
+		return;
+	}
 	if (P.kind == PAIR_SOFT_RIGID)
 		sweep ? launch_bp<0, true>(P, io, s, grid) : launch_bp<0, false>(P, io, s, grid);
 	else if (P.kind == PAIR_SOFT_SOFT)
