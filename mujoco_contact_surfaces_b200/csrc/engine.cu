@@ -592,6 +592,7 @@ static void build_sensor(hcs_ctx *c, SensorHost &s)
 	d.bin_offset = dalloc<int32_t>(c->step_allocs, ncell + 1);
 	d.bin_cursor = dalloc<int32_t>(c->step_allocs, ncell);
 	d.scan_tmp   = dalloc<int32_t>(c->step_allocs, ncell / 1024 + 2);
+	d.raster_counter = dalloc<int32_t>(c->step_allocs, 1);
 	s.dev        = d; // items are sized in finalize() once the triangle pool capacity is known
 	CK(cudaMallocHost((void **)&s.h_image, std::max<size_t>(ncell, 1) * sizeof(float)));
 }

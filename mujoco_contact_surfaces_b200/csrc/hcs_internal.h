@@ -179,6 +179,7 @@ struct SensorDev {
 	int32_t *bin_cursor;  // [n_env * cx*cy] fill cursors
 	int32_t *bin_items;   // [items_cap] triangle ids, bins back to back
 	int32_t *scan_tmp;    // tile sums of the scan
+	int32_t *raster_counter; // next group of 32 taxels of the raster kernel's persistent warps (zeroed by the clear kernel)
 	int items_cap;
 };
 

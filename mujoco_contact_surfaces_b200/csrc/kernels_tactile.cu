@@ -168,11 +168,24 @@ __global__ void __launch_bounds__(256) scan_add_kernel(int32_t *out, const int32
 }
 
 constexpr int RASTER_WARPS = 4;
-constexpr int RANK_MAX     = 128; // chunk size; bins up to this size get an order-independent tie-break
-constexpr int RASTER_EXTRA = RANK_MAX * 16 + (RANK_MAX + 4) * 4 + RANK_MAX * 4 + RANK_MAX * 24; // fp_box + fp_cnt + rank_k + fp_xy
+// taxels a persistent warp takes at a time (HCS_RASTER_GROUP overrides).  Lit taxels come in clusters (the contact patch), so
+// coarse groups leave a tail of heavy ones: tactile stage of C2 box x 1024 envs 0.925 / 0.633 / 0.579 / 0.560 / 0.579 ms for
+// 32 / 8 / 4 / 2 / 1, C5 x 1024 17.6 / 14.3 / 13.9 / 13.4 / 13.3 ms (before the persistent warps: 0.994 and 16.0 ms)
+constexpr int RASTER_GROUP = 2;
+constexpr int RANK_MAX     = 128; // bins up to this size get an order-independent tie-break
+// Triangles of a bin whose sample footprints are staged in shared memory at a time: 64 where the sample arrays are large
+// (S = 20: 8 KB per warp, the stage decides how many CTAs fit), 128 where they are small and the bins deep (C5: S = 8,
+// hundreds of triangles per taxel: fewer passes of the per-chunk scan).
+__host__ __device__ inline int raster_chunk(int S) { return S <= 12 ? 128 : 64; }
+// per warp, behind the sample arrays: fp_box int4[chunk] | fp_xy float[6 chunk] | fp_cnt int[chunk + 4] | rank_k u8[RANK_MAX]
+__host__ __device__ inline size_t raster_extra_bytes(int S)
+{
+	const size_t c = (size_t)raster_chunk(S);
+	return c * 16 + c * 24 + (c + 4) * 4 + RANK_MAX; // 64: 2960 B (>= the 1536 B of the phase-0 products at S = 32), 128: 5776 B
+}
 __host__ __device__ inline size_t raster_warp_bytes(int S)
 {
-	return (((size_t)S * S * 20 + 15) & ~(size_t)15) + RASTER_EXTRA; // keys + origins, rounded to 16 B, + extras
+	return (((size_t)S * S * 20 + 15) & ~(size_t)15) + raster_extra_bytes(S); // keys + origins, rounded to 16 B, + extras
 }
 
 // Moeller-Trumbore, bvh.cpp:49-74, float32 and in the reference's operation order
@@ -197,7 +210,7 @@ __device__ __forceinline__ bool moller_trumbore(F3 O, F3 D, const TactileTri &t,
 	return tt > 0.0f;
 }
 
-// One warp per taxel.  Dynamic shared memory per warp: S*S 64-bit depth keys, S*S float3 ray origins,
+// One warp per lit taxel.  Dynamic shared memory per warp: S*S 64-bit depth keys, S*S float3 ray origins,
 // per-chunk triangle footprints/offsets and bin ranks.
 //   phase 0  lanes over samples: ray origins exactly as flat_tactile_sensor.cpp:324-337, keys = +inf
 //   phase 1  lanes over the taxel's binned triangles: each triangle is splatted onto the samples inside its
@@ -205,38 +218,32 @@ __device__ __forceinline__ bool moller_trumbore(F3 O, F3 D, const TactileTri &t,
 //            memory -> nearest hit per sample, ties resolved by a (pair, order) rank, never by arrival order
 //   phase 2  lanes over samples: winner's barycentric pressure * window weight (float/double mix of :346-391)
 //   phase 3  lane 0 sums the samples in the reference's (i, j) order -> bit-identical float accumulation
-__global__ void __launch_bounds__(32 * RASTER_WARPS) tactile_raster_kernel(SensorDev sd, StepIO io)
+// Round 2: persistent warps.  The grid is what fits the SMs; a warp pulls small groups of consecutive taxels from a counter,
+// its lanes look at one taxel each (empty ones get their 0 right there, one coalesced store), the lit ones are then
+// rasterised one after the other.  Before, every taxel had its own warp and every four their CTA, whose 57 KB of shared
+// memory stayed allocated until its slowest warp was done while the warps of empty taxels had long left (ncu, C2 box x
+// 1024 envs: 15 % of the warp slots active).  Footprints are staged 64 triangles at a time and the rank table is bytes:
+// 11 KB per warp at S = 20, 5 CTAs per SM instead of 3.
+__device__ __forceinline__ void raster_taxel(const SensorDev &sd, const StepIO &io, long unit, int env, int x, int y, float *out,
+                                             unsigned char *wsmem, int lane)
 {
-	extern __shared__ __align__(16) unsigned char raster_smem[];
-	int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
-	int ntax = sd.cx * sd.cy;
-	long unit = (long)blockIdx.x * RASTER_WARPS + wib;
-	if (unit >= (long)io.n_env * ntax)
-		return;
-	int env = (int)(unit / ntax), cell = (int)(unit - (long)env * ntax);
-	int x = cell % sd.cx, y = cell / sd.cx;
-	// the reference stores taxel (x,y) at x + cy*y (flat_tactile_sensor.cpp:396-397; quirk Q8: only a
-	// bijection when cx == cy); out-of-range indices of non-square arrays are dropped
-	int oidx = x + sd.cy * y;
-	if (oidx >= ntax)
-		return;
 	int first = sd.bin_offset[unit];
 	int n     = min(sd.bin_count[unit], max(sd.items_cap - first, 0));
-	float *out = sd.image + (size_t)env * ntax + oidx;
-	if (n == 0) {
+	if (n <= 0) {
 		if (lane == 0)
 			*out = 0.0f;
 		return;
 	}
 	const int S = sd.S, S2 = S * S;
 	size_t per_warp = raster_warp_bytes(S);
-	unsigned long long *key = reinterpret_cast<unsigned long long *>(raster_smem + wib * per_warp);
+	unsigned long long *key = reinterpret_cast<unsigned long long *>(wsmem);
 	float *org              = reinterpret_cast<float *>(key + S2); // [3][S2]
-	// per triangle of the chunk: i0, j0, cols, tie (16-byte aligned: starts at the rounded-up array size)
-	int4 *fp_box            = reinterpret_cast<int4 *>(raster_smem + wib * per_warp + (per_warp - RASTER_EXTRA));
-	int *fp_cnt             = reinterpret_cast<int *>(fp_box + RANK_MAX); // footprint sizes -> exclusive offsets
-	int *rank_k             = fp_cnt + RANK_MAX + 4;                      // rank -> bin slot
-	float *fp_xy            = reinterpret_cast<float *>(rank_k + RANK_MAX); // 2-D triangle vertices, taxel frame
+	// per triangle of the chunk: i0, j0, j1, tie (16-byte aligned: starts at the rounded-up array size)
+	const int FP_CHUNK      = raster_chunk(S);
+	int4 *fp_box            = reinterpret_cast<int4 *>(wsmem + (per_warp - raster_extra_bytes(S)));
+	float *fp_xy            = reinterpret_cast<float *>(fp_box + FP_CHUNK);  // 2-D triangle vertices, taxel frame
+	int *fp_cnt             = reinterpret_cast<int *>(fp_xy + 6 * FP_CHUNK); // footprint sizes -> exclusive offsets
+	unsigned char *rank_k   = reinterpret_cast<unsigned char *>(fp_cnt + FP_CHUNK + 4); // rank -> position in the bin
 	const int32_t *items = sd.bin_items + first;
 	const double *R  = io.xmat + ((size_t)env * io.n_geoms + sd.geom) * 9;
 	const double *xp = io.xpos + ((size_t)env * io.n_geoms + sd.geom) * 3;
@@ -268,13 +275,17 @@ __global__ void __launch_bounds__(32 * RASTER_WARPS) tactile_raster_kernel(Senso
 	__syncwarp();
 	double pz   = 1.5 * (double)zs;
 	double c[3] = { rot[2] * pz, rot[5] * pz, rot[8] * pz };
+	int i = lane / S, j = lane - i * S; // (i, j) of sample s = i * S + j, advanced by 32 samples per iteration without a division
+	const int di = 32 / S, dj = 32 - di * S;
 	for (int s = lane; s < S2; s += 32) {
-		int i = s / S, j = s - i * S;
 		double w[3] = { prod[i] + prod[3 * S + j] + c[0], prod[S + i] + prod[4 * S + j] + c[1], prod[2 * S + i] + prod[5 * S + j] + c[2] };
 		w[0] += xp[0], w[1] += xp[1], w[2] += xp[2];
 		F3 O = f3((float)w[0], (float)w[1], (float)w[2]) + off;
 		org[s] = O.x, org[S2 + s] = O.y, org[2 * S2 + s] = O.z;
 		key[s] = ~0ull;
+		i += di, j += dj;
+		if (j >= S)
+			j -= S, ++i;
 	}
 	__syncwarp();
 	// ---- phase 1: splat.  Triangles are taken in chunks of CHUNK; lanes first compute each triangle's sample
@@ -284,8 +295,8 @@ __global__ void __launch_bounds__(32 * RASTER_WARPS) tactile_raster_kernel(Senso
 	bool ranked = n <= RANK_MAX;
 	double base_x = topleft[0] + x * resolution, base_y = topleft[1] + y * resolution;
 	const double margin = 1e-5; // >> float32 rounding of the hit test at these magnitudes, << sample spacing
-	for (int c0 = 0; c0 < n; c0 += RANK_MAX) {
-		int m = min(RANK_MAX, n - c0);
+	for (int c0 = 0; c0 < n; c0 += FP_CHUNK) {
+		int m = min(FP_CHUNK, n - c0);
 		for (int k = lane; k < m; k += 32) {
 			const TactileTri &t = io.tri_pool[items[c0 + k]];
 			double lo[2] = { 1e300, 1e300 }, hi[2] = { -1e300, -1e300 }, lxy[3][2];
@@ -308,9 +319,9 @@ __global__ void __launch_bounds__(32 * RASTER_WARPS) tactile_raster_kernel(Senso
 				for (int k2 = 0; k2 < n; ++k2) {
 					const TactileTri &o = io.tri_pool[items[k2]];
 					r += (o.key_hi < t.key_hi) ||
-					     (o.key_hi == t.key_hi && (o.key_lo < t.key_lo || (o.key_lo == t.key_lo && items[k2] < items[k])));
+					     (o.key_hi == t.key_hi && (o.key_lo < t.key_lo || (o.key_lo == t.key_lo && items[k2] < items[c0 + k])));
 				}
-				rank_k[r] = k;
+				rank_k[r] = (unsigned char)(c0 + k);
 			}
 			fp_cnt[k] = cols > 0 ? rows : 0; // one item per sample row of the footprint
 			fp_box[k] = make_int4(i0, j0, j1, r);
@@ -321,7 +332,7 @@ __global__ void __launch_bounds__(32 * RASTER_WARPS) tactile_raster_kernel(Senso
 			}
 		}
 		__syncwarp();
-		// exclusive scan of up to RANK_MAX footprint sizes: 4 consecutive entries per lane
+		// exclusive scan of the (at most FP_CHUNK) footprint sizes, entry m = their total: 4 consecutive entries per lane
 		int v4[4], sum = 0;
 #pragma unroll
 		for (int q = 0; q < 4; ++q) {
@@ -346,8 +357,6 @@ __global__ void __launch_bounds__(32 * RASTER_WARPS) tactile_raster_kernel(Senso
 				fp_cnt[idx] = excl;
 			excl += v4[q];
 		}
-		if (lane == 31 && m == RANK_MAX)
-			fp_cnt[RANK_MAX] = total;
 		__syncwarp();
 		for (int w = lane; w < total; w += 32) {
 			int lo_k = 0, hi_k = m; // largest k with offset[k] <= w
@@ -409,8 +418,9 @@ __global__ void __launch_bounds__(32 * RASTER_WARPS) tactile_raster_kernel(Senso
 		}
 		__syncwarp();
 	}
-	// ---- phase 2: winners -> weighted sample pressures (written over the key slots)
-	float *val = reinterpret_cast<float *>(key);
+	// ---- phase 2: winners -> weighted sample pressures, written over the x plane of the origins (sample s is read and
+	// written by the same lane), so that phase 3 reads four values per 128-bit load
+	float *val = org;
 	for (int s = lane; s < S2; s += 32) {
 		unsigned long long kk = key[s];
 		float value = 0.0f;
@@ -429,16 +439,70 @@ __global__ void __launch_bounds__(32 * RASTER_WARPS) tactile_raster_kernel(Senso
 				value     = sd.weights[s] * raw;
 			}
 		}
-		val[2 * s] = value; // low word of this sample's own key slot (read above by the same lane)
+		val[s] = value;
 	}
 	__syncwarp();
 	// ---- phase 3
 	if (lane == 0) {
 		float avg = 0;
-#pragma unroll 8
-		for (int s = 0; s < S2; ++s) // loads are independent (batched by the unroll); the adds stay in order
-			avg += val[2 * s];
+		const float4 *v4 = reinterpret_cast<const float4 *>(val); // (org starts 16-byte aligned: S2 keys of 8 bytes behind a 16-byte base)
+		int s = 0;
+		if ((S2 & 1) == 0) { // key array = 8 * S2 bytes: org is 16-byte aligned when S2 is even
+#pragma unroll 4
+			for (; s + 4 <= S2; s += 4) { // loads are independent (batched by the unroll); the adds stay in order
+				const float4 q = v4[s >> 2];
+				avg += q.x;
+				avg += q.y;
+				avg += q.z;
+				avg += q.w;
+			}
+		}
+		for (; s < S2; ++s)
+			avg += val[s];
 		*out = avg;
+	}
+	__syncwarp(); // the warp's next taxel reuses the arrays
+}
+
+__global__ void __launch_bounds__(32 * RASTER_WARPS) tactile_raster_kernel(SensorDev sd, StepIO io, int group)
+{
+	extern __shared__ __align__(16) unsigned char raster_smem[];
+	const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	unsigned char *wsmem = raster_smem + wib * raster_warp_bytes(sd.S);
+	const int ntax   = sd.cx * sd.cy;
+	const long total = (long)io.n_env * ntax;
+	for (;;) {
+		int g = 0;
+		if (lane == 0)
+			g = atomicAdd(sd.raster_counter, 1);
+		g = __shfl_sync(0xffffffffu, g, 0);
+		const long u0 = (long)g * group;
+		if (u0 >= total)
+			break;
+		// lane l < RASTER_GROUP looks at taxel u0 + l: empty ones are done here
+		const long unit = u0 + lane;
+		bool lit = false;
+		if (lane < group && unit < total) {
+			const int env = (int)(unit / ntax), cell = (int)(unit - (long)env * ntax);
+			const int x = cell % sd.cx, y = cell / sd.cx;
+			// the reference stores taxel (x,y) at x + cy*y (flat_tactile_sensor.cpp:396-397; quirk Q8: only a
+			// bijection when cx == cy); out-of-range indices of non-square arrays are dropped
+			const int oidx = x + sd.cy * y;
+			if (oidx < ntax) {
+				lit = sd.bin_count[unit] > 0;
+				if (!lit)
+					sd.image[(size_t)env * ntax + oidx] = 0.0f;
+			}
+		}
+		unsigned m = __ballot_sync(0xffffffffu, lit);
+		while (m) {
+			const int src = __ffs(m) - 1;
+			m &= m - 1;
+			const long u  = u0 + src;
+			const int env = (int)(u / ntax), cell = (int)(u - (long)env * ntax);
+			const int x = cell % sd.cx, y = cell / sd.cx;
+			raster_taxel(sd, io, u, env, x, y, sd.image + (size_t)env * ntax + (x + sd.cy * y), wsmem, lane);
+		}
 	}
 }
 
@@ -449,6 +513,8 @@ __global__ void tactile_clear_kernel(SensorDev sd, int n)
 		sd.bin_count[i]  = 0;
 		sd.bin_cursor[i] = 0;
 	}
+	if (i == 0)
+		*sd.raster_counter = 0;
 }
 
 // per sensor: clear, 3-phase scan, raster; for all sensors together: one count pass and one fill pass over the pool
@@ -482,10 +548,15 @@ int launch_tactile(const SensorDev *sensors, const SensorDev *d_sensors, int n_s
 	}
 	for (int k = 0; k < n_sensors; ++k) {
 		const SensorDev &sd = sensors[k];
-		int ncell       = io.n_env * sd.cx * sd.cy;
+		long ncell      = (long)io.n_env * sd.cx * sd.cy;
 		int raster_smem = RASTER_WARPS * (int)raster_warp_bytes(sd.S);
-		cudaFuncSetAttribute(tactile_raster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, raster_smem);
-		tactile_raster_kernel<<<(ncell + RASTER_WARPS - 1) / RASTER_WARPS, 32 * RASTER_WARPS, raster_smem, s>>>(sd, io);
+		ensure_dynamic_smem(tactile_raster_kernel, raster_smem);
+		// persistent warps: as many CTAs as the SMs hold (shared memory; 80 registers allow 6), never more than groups
+		const int per_sm = std::max(1, std::min(6, (int)((227 * 1024) / (raster_smem + 1024))));
+		static const int group = getenv("HCS_RASTER_GROUP") ? std::max(1, std::min(32, atoi(getenv("HCS_RASTER_GROUP")))) : RASTER_GROUP;
+		const long groups = (ncell + group - 1) / group;
+		const int grid    = (int)std::max<long>(1, std::min<long>((long)io.n_sms * per_sm, (groups + RASTER_WARPS - 1) / RASTER_WARPS));
+		tactile_raster_kernel<<<grid, 32 * RASTER_WARPS, raster_smem, s>>>(sd, io, group);
 		++launches;
 	}
 	return launches;
