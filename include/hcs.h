@@ -244,6 +244,10 @@ int hcs_get_emitted(hcs_ctx *ctx, int env, int pair, int32_t *out, int cap);
 /* kTriangle contact-surface triangle soup of one env (world frame), 12 doubles per triangle:
  * 9 vertex coordinates + 3 vertex pressures; only pairs touching a sensor geom are kept. */
 int hcs_get_tactile_triangles(hcs_ctx *ctx, int env, double *out, int cap);
+/* the pair index of every triangle of hcs_get_tactile_triangles(env), same order (the soup is sorted by pair first):
+ * lets a host adapter hand each ContactSurface its own triangles (reference: one ContactSurface per geom pair,
+ * mujoco_contact_surfaces_plugin.cpp:301-315); returns count */
+int hcs_get_tactile_triangle_pairs(hcs_ctx *ctx, int env, int32_t *pair_out, int cap);
 
 /* --- introspection (tests, DESIGN.md evidence) ---------------------------------------------------------- */
 /* info = {kind (0 rigid mesh, 1 soft, 2 plane), n_vertices, n_elements} */

@@ -110,7 +110,12 @@ struct hcs_ctx {
 	int32_t *d_counters = nullptr; // zeroed by ONE memset per step: flags[4], face count, tactile triangle count,
 	size_t n_counters   = 0;       // then {flat-list length, next chunk} per pair
 	StepIO io{};
-	double *d_xpos = nullptr, *d_xmat = nullptr, *d_vel = nullptr; // staging for the host entry point
+	double *d_xpos = nullptr, *d_xmat = nullptr, *d_vel = nullptr; // staging for the host entry point (one block: xpos | xmat | vel)
+	double *h_in = nullptr;                                        // pinned copy of small inputs (CUDA-graph path of hcs_step)
+	// hcs_step of small batches replays a captured graph (one H2D copy, the kernels, the result copies): [with_sensors]
+	cudaGraphExec_t step_graph[2] = { nullptr, nullptr };
+	int64_t graph_kernels[2]      = { 0, 0 };
+	int steps_since_finalize      = 0;
 	hcs_pair_result *h_pair = nullptr;                             // pinned mirrors
 	double *h_wrench        = nullptr;
 	int32_t *h_flags        = nullptr;
@@ -673,6 +678,11 @@ static void build_curved(hcs_ctx *c, CurvedHost &s, int max_tris)
 	s.dev = d;
 }
 
+// hcs_step replays a CUDA graph when the step's inputs are at most this large (they are staged through a pinned buffer of
+// the context, so that the graph's copy node has fixed addresses): the reference's own case, one mjData per step, where
+// launch overheads are most of the call
+constexpr size_t GRAPH_INPUT_BYTES = 256u << 10;
+
 static void release_step_buffers(hcs_ctx *c)
 {
 	free_bag(c->step_allocs);
@@ -697,6 +707,12 @@ static void release_step_buffers(hcs_ctx *c)
 		cudaFreeHost(c->h_wrench), c->h_wrench = nullptr;
 	if (c->h_flags)
 		cudaFreeHost(c->h_flags), c->h_flags = nullptr;
+	if (c->h_in)
+		cudaFreeHost(c->h_in), c->h_in = nullptr;
+	for (cudaGraphExec_t &g : c->step_graph)
+		if (g)
+			cudaGraphExecDestroy(g), g = nullptr;
+	c->steps_since_finalize = 0;
 	for (hcs_ctx::Slot &sl : c->slot)
 		if (sl.h_flags)
 			cudaFreeHost(sl.h_flags), sl.h_flags = nullptr, sl.dh_flags = nullptr;
@@ -803,9 +819,11 @@ static void finalize(hcs_ctx *c)
 	io.geom_wrench = dalloc<double>(c->step_allocs, (size_t)n_env * ng * 6);
 	CK(cudaMemsetAsync(io.pair_out, 0, (size_t)n_env * np * sizeof(hcs_pair_result), c->stream));
 	CK(cudaMemsetAsync(io.geom_wrench, 0, (size_t)n_env * ng * 6 * sizeof(double), c->stream));
-	c->d_xpos = dalloc<double>(c->step_allocs, (size_t)n_env * ng * 3);
-	c->d_xmat = dalloc<double>(c->step_allocs, (size_t)n_env * ng * 9);
-	c->d_vel  = dalloc<double>(c->step_allocs, (size_t)n_env * ng * 6);
+	c->d_xpos = dalloc<double>(c->step_allocs, (size_t)n_env * ng * 18); // xpos | xmat | vel back to back: one copy suffices
+	c->d_xmat = c->d_xpos + (size_t)n_env * ng * 3;
+	c->d_vel  = c->d_xmat + (size_t)n_env * ng * 9;
+	if ((size_t)n_env * ng * 18 * sizeof(double) <= GRAPH_INPUT_BYTES)
+		CK(cudaMallocHost((void **)&c->h_in, std::max<size_t>((size_t)n_env * ng * 18, 1) * sizeof(double)));
 	CK(cudaMallocHost((void **)&c->h_pair, std::max<size_t>((size_t)n_env * np, 1) * sizeof(hcs_pair_result)));
 	CK(cudaMallocHost((void **)&c->h_wrench, std::max<size_t>((size_t)n_env * ng * 6, 1) * sizeof(double)));
 	CK(cudaMallocHost((void **)&c->h_flags, 4 * sizeof(int32_t)));
@@ -920,7 +938,7 @@ static void step_device(hcs_ctx *c, const double *xpos, const double *xmat, cons
 // D2H of what the caller applies: per-geom wrenches, flags and (when computed) the sensor outputs.  The per-pair
 // results are diagnostics (the reference has no such output): they are copied only when asked for
 // (hcs_get_pair_results, hcs_get_counters, hcs_fetch_results), so hcs_step does not pay for them every step.
-static void fetch(hcs_ctx *c, int with_sensors, bool with_pairs = true)
+static void fetch_enqueue(hcs_ctx *c, int with_sensors, bool with_pairs)
 {
 	const int n_env = c->cfg.n_envs, ng = (int)c->geoms.size(), np = (int)c->pairs.size();
 	cudaStream_t s = c->stream;
@@ -939,7 +957,12 @@ static void fetch(hcs_ctx *c, int with_sensors, bool with_pairs = true)
 		for (TaxelHost &th : c->taxel)
 			CK(cudaMemcpyAsync(th.h_values, th.dev.values, (size_t)n_env * th.n_taxels() * sizeof(float),
 			                   cudaMemcpyDeviceToHost, s));
-	CK(cudaStreamSynchronize(s));
+}
+
+static void fetch(hcs_ctx *c, int with_sensors, bool with_pairs = true)
+{
+	fetch_enqueue(c, with_sensors, with_pairs);
+	CK(cudaStreamSynchronize(c->stream));
 	c->results_on_host = true;
 	c->pairs_on_host   = c->pairs_on_host || with_pairs;
 	c->sensors_on_host = with_sensors != 0;
@@ -1474,6 +1497,60 @@ int hcs_step(hcs_ctx *c, const double *xpos, const double *xmat, const double *v
 		return HCS_E_INVALID;
 	}
 	size_t n = (size_t)c->cfg.n_envs * c->geoms.size();
+	// Small batches (the reference's own case is ONE mjData): the whole call - one H2D copy, every kernel, the result
+	// copies - is a CUDA graph captured on the second step after hcs_finalize and replayed from then on: one launch
+	// instead of three copies and 4 - 30 kernel launches.  The inputs go through the context's pinned staging buffer.
+	static const bool graphs_ok = getenv("HCS_NO_GRAPH") == nullptr;
+	if (graphs_ok && c->h_in && !c->profiling) {
+		const int key = with_sensors ? 1 : 0;
+		memcpy(c->h_in, xpos, n * 3 * sizeof(double));
+		memcpy(c->h_in + n * 3, xmat, n * 9 * sizeof(double));
+		memcpy(c->h_in + n * 12, vel, n * 6 * sizeof(double));
+		const bool direct = !with_sensors && c->dh_wrench && c->dh_flags;
+		auto enqueue = [&]() {
+			CK(cudaMemcpyAsync(c->d_xpos, c->h_in, n * 18 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+			step_device(c, c->d_xpos, c->d_xmat, c->d_vel, with_sensors, direct);
+			if (!direct)
+				fetch_enqueue(c, with_sensors, /*with_pairs=*/false);
+		};
+		if (c->step_graph[key]) {
+			CK(cudaGraphLaunch(c->step_graph[key], c->stream));
+			c->kernels_last_step = c->graph_kernels[key];
+			c->step_counter++;
+			c->last_with_sensors = with_sensors != 0;
+		} else if (c->steps_since_finalize >= 1) { // (the first step runs eagerly: one-time function attributes are set there)
+			cudaGraph_t g = nullptr;
+			CK(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeRelaxed));
+			try {
+				enqueue();
+			} catch (...) {
+				cudaStreamEndCapture(c->stream, &g);
+				if (g)
+					cudaGraphDestroy(g);
+				cudaGetLastError();
+				throw;
+			}
+			CK(cudaStreamEndCapture(c->stream, &g));
+			cudaError_t ie = cudaGraphInstantiate(&c->step_graph[key], g, 0);
+			cudaGraphDestroy(g);
+			if (ie != cudaSuccess) {
+				cudaGetLastError();
+				c->step_graph[key] = nullptr;
+				enqueue(); // no graph on this driver: plain launches
+			} else {
+				c->graph_kernels[key] = c->kernels_last_step;
+				CK(cudaGraphLaunch(c->step_graph[key], c->stream));
+			}
+		} else {
+			enqueue();
+		}
+		c->steps_since_finalize++;
+		CK(cudaStreamSynchronize(c->stream));
+		c->results_on_host = true;
+		c->pairs_on_host   = false;
+		c->sensors_on_host = with_sensors != 0;
+		return check_flags(c);
+	}
 	// Inputs are staged with three DMA copies.  Reading the poses straight from pinned host memory inside the kernels
 	// (zero-copy) was measured and dropped as the default: the reads are 8-byte uniform loads, which PCIe serves far
 	// below its copy bandwidth (C1 +3 % end to end, C4 with five geoms -9 %); HCS_ZERO_COPY_IN=1 keeps the experiment.
@@ -1801,13 +1878,12 @@ int hcs_get_emitted(hcs_ctx *c, int env, int pair, int32_t *out, int cap)
 	API_END(c)
 }
 
-int hcs_get_tactile_triangles(hcs_ctx *c, int env, double *out, int cap)
+// the environment's tactile triangles in canonical order (pair, query element, tree element, fan triangle)
+static std::vector<TactileTri> env_triangles(hcs_ctx *c, int env)
 {
-	API_BEGIN(c)
-	if (!c->finalized || env < 0 || env >= c->cfg.n_envs)
-		return HCS_E_INVALID;
+	std::vector<TactileTri> mine;
 	if (c->io.max_tris <= 0)
-		return 0;
+		return mine;
 	int32_t n = 0;
 	CK(cudaMemcpyAsync(&n, c->io.tri_count, sizeof n, cudaMemcpyDeviceToHost, c->stream));
 	CK(cudaStreamSynchronize(c->stream));
@@ -1817,21 +1893,45 @@ int hcs_get_tactile_triangles(hcs_ctx *c, int env, double *out, int cap)
 		CK(cudaMemcpyAsync(pool.data(), c->io.tri_pool, (size_t)n * sizeof(TactileTri), cudaMemcpyDeviceToHost, c->stream));
 		CK(cudaStreamSynchronize(c->stream));
 	}
-	std::vector<const TactileTri *> mine;
 	for (const TactileTri &t : pool)
 		if (t.env == env)
-			mine.push_back(&t);
-	std::sort(mine.begin(), mine.end(), [](const TactileTri *a, const TactileTri *b) {
-		return a->key_hi != b->key_hi ? a->key_hi < b->key_hi : a->key_lo < b->key_lo;
+			mine.push_back(t);
+	std::sort(mine.begin(), mine.end(), [](const TactileTri &a, const TactileTri &b) {
+		return a.key_hi != b.key_hi ? a.key_hi < b.key_hi : a.key_lo < b.key_lo;
 	});
+	return mine;
+}
+
+int hcs_get_tactile_triangles(hcs_ctx *c, int env, double *out, int cap)
+{
+	API_BEGIN(c)
+	if (!c->finalized || env < 0 || env >= c->cfg.n_envs)
+		return HCS_E_INVALID;
+	const std::vector<TactileTri> mine = env_triangles(c, env);
 	int m = 0;
-	for (const TactileTri *t : mine) {
+	for (const TactileTri &t : mine) {
 		if (m < cap && out) {
 			for (int k = 0; k < 9; ++k)
-				out[12 * m + k] = t->v[k];
+				out[12 * m + k] = t.v[k];
 			for (int k = 0; k < 3; ++k)
-				out[12 * m + 9 + k] = t->e[k];
+				out[12 * m + 9 + k] = t.e[k];
 		}
+		++m;
+	}
+	return m;
+	API_END(c)
+}
+
+int hcs_get_tactile_triangle_pairs(hcs_ctx *c, int env, int32_t *pair_out, int cap)
+{
+	API_BEGIN(c)
+	if (!c->finalized || env < 0 || env >= c->cfg.n_envs)
+		return HCS_E_INVALID;
+	const std::vector<TactileTri> mine = env_triangles(c, env);
+	int m = 0;
+	for (const TactileTri &t : mine) {
+		if (m < cap && pair_out)
+			pair_out[m] = (int32_t)(t.key_hi >> TRI_PAIR_SHIFT);
 		++m;
 	}
 	return m;

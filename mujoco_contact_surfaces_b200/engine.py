@@ -51,7 +51,7 @@ ABI_SYMBOLS = [
     "hcs_get_mesh", "hcs_get_lbvh", "hcs_get_counters", "hcs_set_profiling", "hcs_get_stage_ms", "hcs_version",
     "hcs_add_curved_sensor", "hcs_curved_sensor_info", "hcs_get_curved_values", "hcs_device_curved_values",
     "hcs_add_taxel_sensor", "hcs_get_taxel_values", "hcs_device_taxel_values", "hcs_get_face_vertices",
-    "hcs_update_flat_sensor", "hcs_step_async", "hcs_wait",
+    "hcs_update_flat_sensor", "hcs_step_async", "hcs_wait", "hcs_get_tactile_triangle_pairs",
 ]
 
 _LIB = None

@@ -261,7 +261,9 @@ void MujocoContactSurfacesPlugin::buildGeomCollisions()
 	pair_results_.resize(np);
 	if (hcs_get_pair_results(ctx_, pair_results_.data()) != HCS_OK)
 		return;
-	std::vector<hcs_face> faces(1 << 16);
+	if (faces_.empty())
+		faces_.resize(1 << 16); // allocated once (cfg.max_faces); the dump only overwrites what it returns
+	std::vector<hcs_face> &faces = faces_;
 	int nf = hcs_get_faces(ctx_, faces.data(), (int)faces.size());
 	if (nf < 0)
 		nf = 0;
@@ -283,12 +285,15 @@ void MujocoContactSurfacesPlugin::buildGeomCollisions()
 		return a.face < b.face;
 	});
 	std::vector<double> tris;
+	std::vector<int32_t> tri_pair; // the soup is sorted by pair: every surface gets its own run
 	int ntri = 0;
 	if (hydroelastic_contact_representation == HCS_REP_TRIANGLE) {
 		ntri = hcs_get_tactile_triangles(ctx_, 0, nullptr, 0);
 		if (ntri > 0) {
 			tris.resize(12 * (size_t)ntri);
+			tri_pair.resize(ntri);
 			hcs_get_tactile_triangles(ctx_, 0, tris.data(), ntri);
+			hcs_get_tactile_triangle_pairs(ctx_, 0, tri_pair.data(), ntri);
 		}
 	}
 	for (int p = 0; p < np; ++p) {
@@ -300,8 +305,9 @@ void MujocoContactSurfacesPlugin::buildGeomCollisions()
 		view->total_area  = r.area;
 		view->num_faces   = r.n_faces;
 		std::memcpy(view->centroid, r.centroid, sizeof view->centroid);
-		if (np == 1)
-			view->triangles = tris; // single-pair scenes: the whole soup belongs to this surface
+		for (int t = 0; t < ntri; ++t) // this surface's triangles (12 doubles each: vertices + pressures)
+			if (tri_pair[t] == p)
+				view->triangles.insert(view->triangles.end(), tris.begin() + 12 * (size_t)t, tris.begin() + 12 * (size_t)(t + 1));
 		GeomCollisionPtr gc(new GeomCollision(cfg_to_mj[r.gM], cfg_to_mj[r.gN], view));
 		int k = 0;
 		for (int j = 0; j < nf; ++j) {
@@ -368,7 +374,10 @@ void MujocoContactSurfacesPlugin::passiveCallback(const mjModel *m, mjData *d)
 		with_sensors |= plugin->wantsSensorUpdate(d);
 	if (finalized_ && !pair_list_.empty()) {
 		evaluateAndApply(m, d, with_sensors);
-		buildGeomCollisions();
+		// GeomCollision views exist for their consumers (CPU sub-plugins, the surface outlines): nobody to read them,
+		// nothing to fetch (the forces have been applied from the per-geom wrenches already)
+		if (visualizeContactSurfaces || !cb_ready_plugins.empty())
+			buildGeomCollisions();
 		if (visualizeContactSurfaces) { // plugin.cpp:509-516
 			for (const auto &gc : geomCollisions)
 				for (const auto &pc : gc->pointCollisions) {

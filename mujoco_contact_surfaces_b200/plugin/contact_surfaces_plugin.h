@@ -188,6 +188,7 @@ private:
 	std::vector<SurfacePluginPtr> plugins, cb_ready_plugins;
 	std::vector<double> xpos_, xmat_, vel_, wrench_;
 	std::vector<hcs_pair_result> pair_results_;
+	std::vector<hcs_face> faces_; // per-face dump of the last step (persistent: 1 << 16 records)
 };
 
 namespace sensors {

@@ -4,6 +4,7 @@
 //   mujoco_contact_surfaces/assets/sphere_on_box_world.xml          (config 1)
 //   mujoco_contact_surface_sensors/assets/myrmex_box_world.xml + config/myrmex_sensor.yaml  (config 2)
 // Prints one JSON object per scenario; tests/test_plugin_adapter.py checks it against the oracle.
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -444,6 +445,79 @@ static int scenario_curved_poisson()
 	return 0;
 }
 
+// passiveCallback latency of the reference's own execution model: ONE mjData, one call per mj_step, no consumers of the
+// per-face views (no sub-plugins, no visualisation).  Two worlds: config 1 (soft sphere on rigid box) and a config-4-like
+// world (four soft objects on a rigid plane).  The pose changes a little every step; reported per step: the collision
+// pass (dispatch only) and passiveCallback (poses in -> hcs_step -> wrenches applied).
+static double now_us()
+{
+	return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+static int scenario_timing()
+{
+	const double zero[3] = { 0, 0, 0 };
+	for (int world = 0; world < 2; ++world) {
+		ShimWorld w;
+		std::vector<int> movers;
+		std::vector<double> base_z;
+		int b0 = w.add_body(false, zero);
+		if (world == 0) {
+			double box_pos[3] = { 0, 0, 0.1 }, sph_pos[3] = { 0.012, -0.02, 0.2 + 0.08 - 0.012 };
+			int b1 = w.add_body(true, box_pos), b2 = w.add_body(true, sph_pos);
+			double s_box[3] = { 0.1, 0.1, 0.1 }, s_sph[3] = { 0.08, 0, 0 };
+			w.add_geom("box0", mjGEOM_BOX, b1, s_box, box_pos, I3);
+			movers.push_back(w.add_geom("sphere0", mjGEOM_SPHERE, b2, s_sph, sph_pos, I3));
+			base_z.push_back(sph_pos[2]);
+			w.add_numeric("cs::box0", { 0, 1.0, 0.1, 0.3, 0.3 });
+			w.add_numeric("cs::sphere0", { 5e4, 5.0, 0.05, 0.3, 0.3 });
+		} else {
+			double s_plane[3] = { 0, 0, 1 };
+			w.add_geom("ground", mjGEOM_PLANE, b0, s_plane, zero, I3);
+			w.add_numeric("cs::ground", { 0, 1.0, 0, 0.5, 0.5 });
+			const int types[4]    = { mjGEOM_SPHERE, mjGEOM_BOX, mjGEOM_ELLIPSOID, mjGEOM_CYLINDER };
+			const double sizes[4][3] = { { 0.05, 0, 0 }, { 0.04, 0.05, 0.03 }, { 0.05, 0.03, 0.04 }, { 0.04, 0.05, 0 } };
+			const double hz[4]       = { 0.05, 0.03, 0.04, 0.05 };
+			const char *names[4]     = { "obj_sphere", "obj_box", "obj_ellipsoid", "obj_cylinder" };
+			for (int k = 0; k < 4; ++k) {
+				double pos[3] = { 0.3 * k, 0, hz[k] - 0.004 };
+				int b         = w.add_body(true, pos);
+				movers.push_back(w.add_geom(names[k], types[k], b, sizes[k], pos, I3));
+				base_z.push_back(pos[2]);
+				w.add_numeric(std::string("cs::") + names[k], { 5e4, 3.0, 0.02, 0.3, 0.3 });
+			}
+		}
+		w.add_text("cs::HydroelasticContactRepresentation", "kPolygon");
+		w.finish();
+		MujocoContactSurfacesPlugin plugin;
+		if (!plugin.load(&w.m, &w.d)) {
+			std::printf("{\"scenario\": \"timing_%d\", \"error\": \"load failed\"}\n", world);
+			return 1;
+		}
+		const int warm = 50, steps = 2000;
+		double t_coll = 0, t_passive = 0, checksum = 0;
+		for (int step = 0; step < warm + steps; ++step) {
+			for (size_t k = 0; k < movers.size(); ++k)
+				w.xpos[3 * movers[k] + 2] = base_z[k] - 0.002 * std::sin(0.01 * step + (double)k);
+			std::fill(w.qfrc.begin(), w.qfrc.end(), 0.0);
+			double t0 = now_us();
+			w.collision_pass();
+			double t1 = now_us();
+			plugin.passiveCallback(&w.m, &w.d);
+			double t2 = now_us();
+			if (step >= warm)
+				t_coll += t1 - t0, t_passive += t2 - t1;
+			for (double q : w.qfrc)
+				checksum += std::fabs(q);
+			w.d.time += 0.001;
+		}
+		std::printf("{\"scenario\": \"timing_%s\", \"steps\": %d, \"collision_pass_us\": %.3f, \"passive_callback_us\": %.3f, "
+		            "\"qfrc_checksum\": %.9g}\n",
+		            world == 0 ? "sphere_on_box" : "objects_on_plane", steps, t_coll / steps, t_passive / steps, checksum);
+	}
+	return 0;
+}
+
 int main()
 {
 	int rc = scenario_sphere_on_box();
@@ -451,5 +525,6 @@ int main()
 	rc |= scenario_curved_tip();
 	rc |= scenario_taxel_tip();
 	rc |= scenario_curved_poisson();
+	rc |= scenario_timing();
 	return rc;
 }
