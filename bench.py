@@ -51,6 +51,8 @@ def parse():
                     help="diagnostic: leave the per-stage CUDA events out of the timed steps (no roofline then)")
     ap.add_argument("--sensors", type=int, default=-1, help="-1: on when the workload has sensors")
     ap.add_argument("--no-extra-workloads", action="store_true", help="only the headline workload (no `workloads` block)")
+    ap.add_argument("--multi-devices", default="", help="e.g. 0,1: ONE process drives these GPUs through the library's "
+                    "multi-device context (hcs_multi, C++ host threads); prints an end-to-end line, no torch.distributed")
     return ap.parse_args()
 
 
@@ -477,6 +479,57 @@ def cpu_leg(scene, with_sensors, budget_s):
             "single_thread_value": 1.0 / per_env}
 
 
+def run_multi(args, scene, with_sensors):
+    """One process, one hcs_multi context over the listed devices: end-to-end env-steps/s through hcs_multi_step_async /
+    hcs_multi_wait with pinned host buffers (weak scaling: args.envs environments per listed device)."""
+    import torch
+    from mujoco_contact_surfaces_b200 import REP_POLYGON, REP_TRIANGLE, MultiDeviceEngine
+    from mujoco_contact_surfaces_b200 import scenes as S
+    devices = [int(x) for x in args.multi_devices.split(",")]
+    n_envs = args.envs * len(devices)
+    eng = MultiDeviceEngine(n_envs, devices, representation=REP_TRIANGLE if scene.triangle else REP_POLYGON,
+                            apply_contact_forces=scene.apply_forces, **scene.engine_kwargs(n_envs))
+    S.configure(eng, scene)
+    eng.finalize()
+    ng = scene.n_geoms
+    sets = []
+    for i in range(min(args.pose_sets, 4)):
+        xp, xm, ve = scene.poses(n_envs, seed=1234 + i)
+        sets.append([torch.from_numpy(a.reshape(-1)).pin_memory() for a in (xp, xm, ve)])
+    wr = [torch.empty(n_envs * ng * 6, dtype=torch.float64).pin_memory() for _ in range(2)]
+    im = [[torch.empty(n_envs * cx * cy, dtype=torch.float32).pin_memory() for cx, cy in eng.sensors] if with_sensors else [] for _ in range(2)]
+
+    def pipe(n):
+        prev = None
+        for i in range(n):
+            h = sets[i % len(sets)]
+            t = eng.step_async(h[0].data_ptr(), h[1].data_ptr(), h[2].data_ptr(), with_sensors, wr[i & 1].data_ptr(),
+                               [b.data_ptr() for b in im[i & 1]] or None)
+            if prev is not None:
+                eng.wait(prev)
+            prev = t
+        if prev is not None:
+            eng.wait(prev)
+
+    pipe(args.warmup)
+    t0 = time.perf_counter()
+    pipe(args.steps)
+    dt = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        h = sets[i % len(sets)]
+        eng._check(eng.L.hcs_multi_step(eng.h, h[0].data_ptr(), h[1].data_ptr(), h[2].data_ptr(), int(with_sensors)))
+    dt_sync = time.perf_counter() - t0
+    print(json.dumps({"impl": "hcs_multi (one process, C++ host threads, no torch.distributed)", "devices": devices,
+                      "metric": "contact_surface_env_steps_per_sec", "unit": "env-steps/s", "workload": scene.name,
+                      "envs_total": n_envs, "steps": args.steps,
+                      "e2e": {"value": n_envs * args.steps / dt, "ms_per_step": 1e3 * dt / args.steps,
+                              "call": "hcs_multi_step_async + hcs_multi_wait, two steps in flight"},
+                      "e2e_synchronous": {"value": n_envs * args.steps / dt_sync, "ms_per_step": 1e3 * dt_sync / args.steps},
+                      "blocks": eng.blocks(), "wrench_checksum": float(wr[(args.steps - 1) & 1].abs().sum())}))
+    eng.close()
+
+
 def main():
     if len(sys.argv) > 1 and sys.argv[1] == "--cpu-flat":
         cpu_flat(sys.argv[2], float(sys.argv[3]), int(sys.argv[4]), float(sys.argv[5]))
@@ -488,6 +541,9 @@ def main():
     with_sensors = bool(scene.sensors) if args.sensors < 0 else bool(args.sensors)
     if args.impl == "reference":
         run_reference(args, scene, with_sensors)
+        return
+    if args.multi_devices:
+        run_multi(args, scene, with_sensors)
         return
 
     import torch

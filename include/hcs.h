@@ -266,6 +266,44 @@ int hcs_set_profiling(hcs_ctx *ctx, int enable);
 int hcs_get_stage_ms(hcs_ctx *ctx, float out[7]);
 const char *hcs_version(void);
 
+/* --- one context spanning several GPUs ---------------------------------------------------------------------------
+ * North star: "batched independent MuJoCo environments shard by environment index across the GPUs of one box, with no
+ * NCCL on the step path"; SURVEY.md section 8(b) "Threading".  A multi-device context owns one single-device context per
+ * entry of devices[] (a device may appear more than once), each with a contiguous block of the n_envs environments
+ * (sizes differ by at most one: block k starts at k * (n / D) + min(k, n % D)), and one host thread per block: every
+ * configuration call is replayed on all blocks (geometry is replicated at finalize), a step hands every block its slice
+ * of the env-major host arrays and runs the blocks concurrently, results land in the caller's env-major arrays.  The
+ * host code stays C++ (std::thread); nothing is exchanged between the GPUs.  cfg->device and cfg->stream are ignored
+ * (every block owns its stream), cfg->n_envs is the TOTAL.  Results are bit-identical to a single context with the same
+ * n_envs: environments never influence each other (exact integer accumulators, hcs_internal.h). */
+typedef struct hcs_multi hcs_multi;
+int hcs_multi_create(const hcs_config *cfg, const int *devices, int n_devices, hcs_multi **out);
+void hcs_multi_destroy(hcs_multi *m);
+const char *hcs_multi_last_error(const hcs_multi *m);
+int hcs_multi_n_blocks(const hcs_multi *m);
+/* first environment and environment count of block k; the block's own context (for everything not mirrored here) */
+int hcs_multi_block(const hcs_multi *m, int k, int *env_start, int *env_count, hcs_ctx **ctx);
+int hcs_multi_add_geom(hcs_multi *m, int mj_geom_type, const double size[3], const float *mesh_vert, int n_vert,
+                       const int32_t *mesh_face, int n_face, const double props[5]);
+int hcs_multi_add_soft_mesh(hcs_multi *m, const double *verts, int n_vert, const int32_t *tets, int n_tet,
+                            const double *vertex_pressure, const double props[5]);
+int hcs_multi_add_rigid_mesh(hcs_multi *m, const double *verts, int n_vert, const int32_t *tris, int n_tri,
+                             const double props[5]);
+int hcs_multi_update_geom(hcs_multi *m, int geom, const double size[3]);
+int hcs_multi_set_pairs(hcs_multi *m, const int32_t *g1, const int32_t *g2, int n_pairs);
+int hcs_multi_add_flat_sensor(hcs_multi *m, int geom, double resolution, int sampling_resolution, int window, float sigma);
+int hcs_multi_finalize(hcs_multi *m);
+/* HOST arrays of the whole batch, as hcs_step; returns when every block has finished (first error wins) */
+int hcs_multi_step(hcs_multi *m, const double *xpos, const double *xmat, const double *vel, int with_sensors);
+/* the same through every block's pipelined entry point (hcs_step_async): returns once all blocks have QUEUED their
+ * slice; out members are env-major arrays of the whole batch; hcs_multi_wait(ticket) as hcs_wait */
+int hcs_multi_step_async(hcs_multi *m, const double *xpos, const double *xmat, const double *vel, int with_sensors,
+                         const hcs_outputs *out, int64_t *ticket);
+int hcs_multi_wait(hcs_multi *m, int64_t ticket);
+int hcs_multi_get_geom_wrenches(hcs_multi *m, double *out);        /* [n_envs][n_geoms][6] */
+int hcs_multi_get_pair_results(hcs_multi *m, hcs_pair_result *out); /* [n_envs][n_pairs] */
+int hcs_multi_get_sensor_image(hcs_multi *m, int sensor, float *out); /* [n_envs][cx*cy] */
+
 #ifdef __cplusplus
 }
 #endif

@@ -6,4 +6,4 @@ sharding.py (env-index sharding across GPUs), plugin/ (C++ host adapter mirrorin
 """
 from .engine import (GEOM_BOX, GEOM_CYLINDER, GEOM_ELLIPSOID, GEOM_MESH, GEOM_PLANE, GEOM_SPHERE,  # noqa: F401
                      REP_POLYGON, REP_TRIANGLE, WINDOW_GAUSS, WINDOW_NONE, WINDOW_SQUARE, WINDOW_TUKEY,
-                     HcsError, HydroelasticEngine, load_library, version)
+                     HcsError, HydroelasticEngine, MultiDeviceEngine, load_library, version)

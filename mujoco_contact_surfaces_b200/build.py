@@ -18,12 +18,12 @@ OUT = os.path.join(HERE, "variants", "libhcs_b200.%s.so" % VARIANT) if VARIANT e
 OBJ = os.path.join(CSRC, "_build" + ("_" + VARIANT if VARIANT else ""))
 
 SOURCES = ["engine.cu", "kernels_build.cu", "kernels_step.cu", "kernels_broadphase.cu", "kernels_tactile.cu", "kernels_lbvh.cu",
-           "mesh_host.cpp"]
+           "mesh_host.cpp", "multi.cpp"]
 
 NVCC = os.environ.get("HCS_NVCC", "/usr/local/cuda/bin/nvcc")
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-fmad=false",
-    "-ccbin", "g++", "-Xcompiler", "-fPIC,-ffp-contract=off,-fno-fast-math,-O2", "-Xptxas", "-v",
+    "-ccbin", "g++", "-Xcompiler", "-fPIC,-ffp-contract=off,-fno-fast-math,-O2,-pthread", "-Xptxas", "-v",
 ] + os.environ.get("HCS_NVCC_DEFS", "").split()
 
 
@@ -67,7 +67,7 @@ def build(verbose=False, force=False):
         if verbose:
             print(log)
     if _stale(OUT, objs):
-        cmd = [NVCC, "-shared", "-o", OUT] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-ccbin", "g++"]
+        cmd = [NVCC, "-shared", "-o", OUT] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-ccbin", "g++", "-lpthread"]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError("link failed:\n%s\n%s" % (r.stdout, r.stderr))

@@ -52,6 +52,10 @@ ABI_SYMBOLS = [
     "hcs_add_curved_sensor", "hcs_curved_sensor_info", "hcs_get_curved_values", "hcs_device_curved_values",
     "hcs_add_taxel_sensor", "hcs_get_taxel_values", "hcs_device_taxel_values", "hcs_get_face_vertices",
     "hcs_update_flat_sensor", "hcs_step_async", "hcs_wait", "hcs_get_tactile_triangle_pairs",
+    "hcs_multi_create", "hcs_multi_destroy", "hcs_multi_last_error", "hcs_multi_n_blocks", "hcs_multi_block",
+    "hcs_multi_add_geom", "hcs_multi_add_soft_mesh", "hcs_multi_add_rigid_mesh", "hcs_multi_update_geom",
+    "hcs_multi_set_pairs", "hcs_multi_add_flat_sensor", "hcs_multi_finalize", "hcs_multi_step", "hcs_multi_step_async",
+    "hcs_multi_wait", "hcs_multi_get_geom_wrenches", "hcs_multi_get_pair_results", "hcs_multi_get_sensor_image",
 ]
 
 _LIB = None
@@ -92,6 +96,25 @@ def load_library():
         L.hcs_step_async.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         L.hcs_wait.argtypes = [C.c_void_p, C.c_int64]
         L.hcs_step.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+        L.hcs_multi_create.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.c_int, C.POINTER(C.c_void_p)]
+        L.hcs_multi_destroy.argtypes = [C.c_void_p]
+        L.hcs_multi_destroy.restype = None
+        L.hcs_multi_last_error.argtypes = [C.c_void_p]
+        L.hcs_multi_last_error.restype = C.c_char_p
+        L.hcs_multi_n_blocks.argtypes = [C.c_void_p]
+        L.hcs_multi_block.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_void_p)]
+        L.hcs_multi_add_geom.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_float), C.c_int,
+                                         C.POINTER(C.c_int32), C.c_int, C.POINTER(C.c_double)]
+        L.hcs_multi_set_pairs.argtypes = [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.c_int]
+        L.hcs_multi_add_flat_sensor.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_int, C.c_int, C.c_float]
+        L.hcs_multi_update_geom.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_double)]
+        L.hcs_multi_finalize.argtypes = [C.c_void_p]
+        L.hcs_multi_step.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+        L.hcs_multi_step_async.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        L.hcs_multi_wait.argtypes = [C.c_void_p, C.c_int64]
+        L.hcs_multi_get_geom_wrenches.argtypes = [C.c_void_p, C.c_void_p]
+        L.hcs_multi_get_pair_results.argtypes = [C.c_void_p, C.c_void_p]
+        L.hcs_multi_get_sensor_image.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         L.hcs_add_flat_sensor.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_int, C.c_int, C.c_float]
         L.hcs_update_flat_sensor.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_float]
         _LIB = L
@@ -362,6 +385,120 @@ class HydroelasticEngine:
 
     def device_sensor_image_ptr(self, sensor):
         return self.L.hcs_device_sensor_image(self.h, int(sensor))
+
+
+class MultiDeviceEngine:
+    """hcs_multi: ONE context spanning several GPUs (include/hcs.h), driven from one process and one Python thread; the
+    library shards the environments by index over the devices and runs the blocks on its own C++ threads.  Same
+    configuration / step surface as HydroelasticEngine (scenes.configure works on it)."""
+
+    def __init__(self, n_envs, devices, representation=REP_POLYGON, apply_contact_forces=True, **kw):
+        self.L = load_library()
+        cfg = HcsConfig(device=0, n_envs=int(n_envs), representation=int(representation),
+                        apply_contact_forces=int(apply_contact_forces),
+                        max_candidates_per_slice=int(kw.get("max_candidates_per_slice", 0)), max_faces=int(kw.get("max_faces", 0)),
+                        max_tactile_triangles=int(kw.get("max_tactile_triangles", 0)),
+                        max_triangles_per_taxel=int(kw.get("max_triangles_per_taxel", 0)), stream=None, face_vertices=0)
+        dev = (C.c_int * len(devices))(*[int(d) for d in devices])
+        h = C.c_void_p()
+        st = self.L.hcs_multi_create(C.byref(cfg), dev, len(devices), C.byref(h))
+        if st < 0:
+            raise HcsError(st, self.L.hcs_multi_last_error(None).decode())
+        self.h, self.n_envs, self.devices, self.sensors = h, int(n_envs), list(devices), []
+        self.n_geoms = self.n_pairs = 0
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.hcs_multi_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        self.close()
+
+    def _check(self, st):
+        if st < 0:
+            raise HcsError(st, self.L.hcs_multi_last_error(self.h).decode())
+        return st
+
+    def blocks(self):
+        out = []
+        for k in range(self.L.hcs_multi_n_blocks(self.h)):
+            a, b, c = C.c_int(), C.c_int(), C.c_void_p()
+            self._check(self.L.hcs_multi_block(self.h, k, C.byref(a), C.byref(b), C.byref(c)))
+            out.append((a.value, b.value))
+        return out
+
+    def add_geom(self, mj_type, size, props, mesh_vert=None, mesh_face=None):
+        size = _f64(np.resize(np.asarray(size, dtype=np.float64), 3))
+        props = _f64(props)
+        mv = np.ascontiguousarray(mesh_vert, dtype=np.float32) if mesh_vert is not None else None
+        mf = np.ascontiguousarray(mesh_face, dtype=np.int32) if mesh_face is not None else None
+        g = self._check(self.L.hcs_multi_add_geom(self.h, int(mj_type), _ptr(size, C.c_double), _ptr(mv, C.c_float),
+                                                  0 if mv is None else len(mv), _ptr(mf, C.c_int32),
+                                                  0 if mf is None else len(mf), _ptr(props, C.c_double)))
+        self.n_geoms = max(self.n_geoms, g + 1)
+        return g
+
+    def update_geom(self, geom, size):
+        size = _f64(np.resize(np.asarray(size, dtype=np.float64), 3))
+        self._check(self.L.hcs_multi_update_geom(self.h, int(geom), _ptr(size, C.c_double)))
+
+    def set_pairs(self, pairs):
+        pairs = np.asarray(pairs, dtype=np.int32).reshape(-1, 2)
+        g1, g2 = np.ascontiguousarray(pairs[:, 0]), np.ascontiguousarray(pairs[:, 1])
+        self._check(self.L.hcs_multi_set_pairs(self.h, _ptr(g1, C.c_int32), _ptr(g2, C.c_int32), len(pairs)))
+        self.n_pairs = len(pairs)
+
+    def add_flat_sensor(self, geom, resolution, sampling_resolution, window=WINDOW_NONE, sigma=-1.0):
+        s = self._check(self.L.hcs_multi_add_flat_sensor(self.h, int(geom), float(resolution), int(sampling_resolution),
+                                                         int(window), float(sigma)))
+        a, b, c = C.c_int(), C.c_int(), C.c_void_p()
+        self._check(self.L.hcs_multi_block(self.h, 0, C.byref(a), C.byref(b), C.byref(c)))
+        cx, cy = C.c_int(), C.c_int()
+        self.L.hcs_sensor_dims(c, s, C.byref(cx), C.byref(cy))
+        self.sensors.append((cx.value, cy.value))
+        return s
+
+    def finalize(self):
+        self._check(self.L.hcs_multi_finalize(self.h))
+
+    def step(self, xpos, xmat, vel, with_sensors=False):
+        xpos, xmat, vel = _f64(xpos), _f64(xmat), _f64(vel)
+        n = self.n_envs * self.n_geoms
+        assert xpos.size == n * 3 and xmat.size == n * 9 and vel.size == n * 6, "pose arrays have the wrong size"
+        self._check(self.L.hcs_multi_step(self.h, xpos.ctypes.data, xmat.ctypes.data, vel.ctypes.data, int(with_sensors)))
+
+    def step_async(self, xpos_ptr, xmat_ptr, vel_ptr, with_sensors=False, geom_wrench_ptr=None, sensor_image_ptrs=None,
+                   pair_results_ptr=None):
+        out = HcsOutputs()
+        out.geom_wrench = geom_wrench_ptr
+        out.pair_results = pair_results_ptr
+        keep = None
+        if sensor_image_ptrs:
+            keep = (C.c_void_p * len(sensor_image_ptrs))(*sensor_image_ptrs)
+            out.sensor_images = C.cast(keep, C.POINTER(C.c_void_p))
+        t = C.c_int64(-1)
+        self._check(self.L.hcs_multi_step_async(self.h, xpos_ptr, xmat_ptr, vel_ptr, int(with_sensors), C.byref(out), C.byref(t)))
+        return t.value
+
+    def wait(self, ticket):
+        self._check(self.L.hcs_multi_wait(self.h, C.c_int64(ticket)))
+
+    def geom_wrenches(self):
+        out = np.zeros((self.n_envs, self.n_geoms, 6))
+        self._check(self.L.hcs_multi_get_geom_wrenches(self.h, out.ctypes.data))
+        return out
+
+    def pair_results(self):
+        out = np.zeros((self.n_envs, self.n_pairs), dtype=PAIR_RESULT_DTYPE)
+        self._check(self.L.hcs_multi_get_pair_results(self.h, out.ctypes.data))
+        return out
+
+    def sensor_image(self, sensor):
+        cx, cy = self.sensors[sensor]
+        out = np.zeros((self.n_envs, cx * cy), dtype=np.float32)
+        self._check(self.L.hcs_multi_get_sensor_image(self.h, int(sensor), out.ctypes.data))
+        return out
 
 
 def version():

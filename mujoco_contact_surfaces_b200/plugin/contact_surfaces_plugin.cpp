@@ -415,6 +415,139 @@ void MujocoContactSurfacesPlugin::onGeomChanged(const mjModel *m, mjData *, cons
 		std::fprintf(stderr, "[mujoco_contact_surfaces] %s\n", hcs_last_error(ctx_));
 }
 
+// ---- batched host adapter -------------------------------------------------------------------------------------
+BatchedContactSurfaces::~BatchedContactSurfaces()
+{
+	if (ctx_)
+		hcs_multi_destroy(ctx_);
+}
+
+// the custom-field walk of parseMujocoCustomFields (plugin.cpp:571-813) for a multi-device context
+bool BatchedContactSurfaces::load(const mjModel *m, int n_envs, const std::vector<int> &devices)
+{
+	int representation = HCS_REP_TRIANGLE;
+	int hcp_id         = mj_name2id(m, mjOBJ_TEXT, (PREFIX + "HydroelasticContactRepresentation").c_str());
+	if (hcp_id >= 0 && m->text_adr[hcp_id] >= 0) {
+		std::string hcp(&m->text_data[m->text_adr[hcp_id]], m->text_size[hcp_id]);
+		if (hcp.find("kPolygon") != std::string::npos)
+			representation = HCS_REP_POLYGON;
+	}
+	int apsf_id = mj_name2id(m, mjOBJ_NUMERIC, (PREFIX + "ApplyContactSurfaceForces").c_str());
+	if (apsf_id >= 0 && m->numeric_size[apsf_id] == 1)
+		applyContactSurfaceForces = m->numeric_data[m->numeric_adr[apsf_id]] != 0;
+	hcs_config cfg;
+	std::memset(&cfg, 0, sizeof cfg);
+	cfg.n_envs               = n_envs;
+	cfg.representation       = representation;
+	cfg.apply_contact_forces = applyContactSurfaceForces;
+	if (hcs_multi_create(&cfg, devices.data(), (int)devices.size(), &ctx_) != HCS_OK) {
+		std::fprintf(stderr, "[mujoco_contact_surfaces] %s\n", hcs_multi_last_error(nullptr));
+		ctx_ = nullptr;
+		return false;
+	}
+	n_envs_ = n_envs;
+	for (int i = 0; i < m->nnumeric; ++i) {
+		const char *nm = mj_id2name(m, mjOBJ_NUMERIC, i);
+		if (!nm)
+			continue;
+		std::string full_name = nm;
+		if (full_name.rfind(PREFIX, 0) != 0)
+			continue;
+		std::string s = full_name.substr(PREFIX.length());
+		int id        = mj_name2id(m, mjOBJ_GEOM, s.c_str());
+		int adr = m->numeric_adr[i], size = m->numeric_size[i];
+		if (id < 0 || adr < 0 || size != 5)
+			continue;
+		const double *props = m->numeric_data + adr;
+		const float *mv     = nullptr;
+		const int32_t *mf   = nullptr;
+		int nv = 0, nf = 0;
+		if (m->geom_type[id] == mjGEOM_MESH && m->geom_dataid[id] >= 0) {
+			int did = m->geom_dataid[id];
+			nv = m->mesh_vertnum[did], nf = m->mesh_facenum[did];
+			mv = m->mesh_vert + 3 * m->mesh_vertadr[did];
+			mf = m->mesh_face + 3 * m->mesh_faceadr[did];
+		}
+		int cfg_idx = hcs_multi_add_geom(ctx_, m->geom_type[id], m->geom_size + 3 * id, mv, nv, mf, nf, props);
+		if (cfg_idx < 0)
+			continue; // unsupported geom: MuJoCo's default collision stays
+		auto cp              = std::make_shared<ContactProperties>();
+		cp->mujoco_geom_id   = id;
+		cp->drake_id         = cfg_idx;
+		cp->geom_name        = s;
+		cp->contact_type     = props[0] > 0 ? SOFT : RIGID;
+		cp->hydroelastic_modulus = props[0] > 0 ? props[0] : INFINITY;
+		cp->dissipation      = props[0] > 0 ? props[1] : 1.0;
+		cp->resolution_hint  = props[2];
+		cp->static_friction  = props[3];
+		cp->dynamic_friction = props[4];
+		contactProperties[id] = cp;
+		cfg_to_mj.push_back(id);
+	}
+	return true;
+}
+
+void BatchedContactSurfaces::recordPair(int g1, int g2)
+{
+	auto c1 = contactProperties.find(g1), c2 = contactProperties.find(g2);
+	if (c1 == contactProperties.end() || c2 == contactProperties.end() ||
+	    (c1->second->contact_type == RIGID && c2->second->contact_type == RIGID))
+		return;
+	std::pair<int, int> p(c1->second->drake_id, c2->second->drake_id);
+	if (known_pairs_.insert(p).second) {
+		pair_list_.push_back(p);
+		finalized_ = false;
+	}
+}
+
+bool BatchedContactSurfaces::finalize()
+{
+	if (!ctx_)
+		return false;
+	std::vector<int32_t> g1, g2;
+	for (const auto &p : pair_list_) {
+		g1.push_back(p.first);
+		g2.push_back(p.second);
+	}
+	if (hcs_multi_set_pairs(ctx_, g1.data(), g2.data(), (int)g1.size()) != HCS_OK || hcs_multi_finalize(ctx_) != HCS_OK) {
+		std::fprintf(stderr, "[mujoco_contact_surfaces] %s\n", hcs_multi_last_error(ctx_));
+		return false;
+	}
+	finalized_ = true;
+	return true;
+}
+
+void BatchedContactSurfaces::passiveCallback(const mjModel *m, mjData *const *d, int n)
+{
+	if (!ctx_ || n != n_envs_ || pair_list_.empty() || (!finalized_ && !finalize()))
+		return;
+	const int ng = (int)cfg_to_mj.size();
+	xpos_.resize((size_t)3 * ng * n), xmat_.resize((size_t)9 * ng * n), vel_.resize((size_t)6 * ng * n), wrench_.resize((size_t)6 * ng * n);
+	for (int e = 0; e < n; ++e)
+		for (int c = 0; c < ng; ++c) {
+			const int id = cfg_to_mj[c];
+			const size_t o = (size_t)e * ng + c;
+			std::memcpy(&xpos_[3 * o], d[e]->geom_xpos + 3 * id, 3 * sizeof(double));
+			std::memcpy(&xmat_[9 * o], d[e]->geom_xmat + 9 * id, 9 * sizeof(double));
+			mj_objectVelocity(m, d[e], mjOBJ_GEOM, id, &vel_[6 * o], 0);
+		}
+	if (hcs_multi_step(ctx_, xpos_.data(), xmat_.data(), vel_.data(), 0) != HCS_OK) {
+		std::fprintf(stderr, "[mujoco_contact_surfaces] %s\n", hcs_multi_last_error(ctx_));
+		return;
+	}
+	if (!applyContactSurfaceForces)
+		return;
+	hcs_multi_get_geom_wrenches(ctx_, wrench_.data());
+	const mjtNum origin[3] = { 0, 0, 0 };
+	for (int e = 0; e < n; ++e)
+		for (int c = 0; c < ng; ++c) {
+			const double *w = &wrench_[6 * ((size_t)e * ng + c)];
+			if (w[0] == 0 && w[1] == 0 && w[2] == 0 && w[3] == 0 && w[4] == 0 && w[5] == 0)
+				continue;
+			mj_applyFT(m, d[e], w, w + 3, origin, m->geom_bodyid[cfg_to_mj[c]], d[e]->qfrc_passive);
+		}
+}
+
 namespace sensors {
 
 static bool has(const PluginConfig &c, const char *k) { return c.find(k) != c.end(); }

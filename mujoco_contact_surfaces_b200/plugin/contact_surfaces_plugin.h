@@ -191,6 +191,35 @@ private:
 	std::vector<hcs_face> faces_; // per-face dump of the last step (persistent: 1 << 16 records)
 };
 
+// N independent mjData of ONE mjModel stepped together (the north star's "batched independent MuJoCo environments shard by
+// environment index across the GPUs"): one hcs_multi context with n_envs = N over the given devices; the host side stays
+// C++.  The reference serves one mjData per plugin instance (plugin.cpp:88, 225); this is the same load / collision /
+// passive sequence for a whole batch: geoms and contact properties come from the `cs::` custom fields of the model, the
+// candidate geom pairs are registered once (setPairs, or recorded from one world's collision pass with recordPair),
+// passiveCallback takes all N mjData, makes ONE library call and applies one wrench per geom to every world.
+class BatchedContactSurfaces
+{
+public:
+	~BatchedContactSurfaces();
+	bool load(const mjModel *m, int n_envs, const std::vector<int> &devices);
+	void recordPair(int mujoco_g1, int mujoco_g2); // as collision_cb would see it; ignored for rigid-rigid / unknown geoms
+	bool finalize();
+	void passiveCallback(const mjModel *m, mjData *const *d, int n);
+	hcs_multi *context() { return ctx_; }
+	int numPairs() const { return (int)pair_list_.size(); }
+
+private:
+	hcs_multi *ctx_ = nullptr;
+	int n_envs_     = 0;
+	bool applyContactSurfaceForces = true;
+	std::map<int, std::shared_ptr<ContactProperties>> contactProperties;
+	std::vector<int> cfg_to_mj;
+	std::set<std::pair<int, int>> known_pairs_;
+	std::vector<std::pair<int, int>> pair_list_;
+	std::vector<double> xpos_, xmat_, vel_, wrench_;
+	bool finalized_ = false;
+};
+
 namespace sensors {
 
 // tactile_sensor_base.h / tactile_sensor_base.cpp:61-120

@@ -518,6 +518,67 @@ static int scenario_timing()
 	return 0;
 }
 
+// BatchedContactSurfaces: six mjData of the sphere-on-box world (different poses and velocities) through ONE multi-device
+// context (two blocks), against six runs of the one-mjData plugin on the same poses: generalised forces bit for bit.
+static int scenario_batched()
+{
+	const double zero[3] = { 0, 0, 0 };
+	const int N = 6;
+	std::vector<ShimWorld> worlds(N);
+	std::vector<std::vector<double>> single(N);
+	int gs = -1, gb = -1;
+	for (int e = 0; e < N; ++e) {
+		ShimWorld &w = worlds[e];
+		double box_pos[3] = { 0, 0, 0.1 }, sph_pos[3] = { 0.01 * e - 0.02, 0.015 - 0.01 * e, 0.2 + 0.08 - 0.002 * (e + 1) };
+		double R[9];
+		rot_zyx(0.3 * e, -0.2 + 0.1 * e, 0.5 - 0.15 * e, R);
+		w.add_body(false, zero);
+		int b1 = w.add_body(true, box_pos), b2 = w.add_body(true, sph_pos);
+		double s_box[3] = { 0.1, 0.1, 0.1 }, s_sph[3] = { 0.08, 0, 0 };
+		gb = w.add_geom("box0", mjGEOM_BOX, b1, s_box, box_pos, I3);
+		gs = w.add_geom("sphere0", mjGEOM_SPHERE, b2, s_sph, sph_pos, R);
+		w.add_text("cs::HydroelasticContactRepresentation", "kPolygon");
+		w.add_numeric("cs::box0", { 0, 1.0, 0.1, 0.3, 0.3 });
+		w.add_numeric("cs::sphere0", { 5e4, 5.0, 0.05, 0.3, 0.3 });
+		w.finish();
+		double v[6] = { 0.3 - 0.1 * e, -0.2, 0.1 * e, 0.02, 0.01 * e, -0.05 };
+		std::memcpy(&w.vel6[6 * gs], v, sizeof v);
+	}
+	for (int e = 0; e < N; ++e) { // the reference's way: one plugin instance per mjData
+		ShimWorld &w = worlds[e];
+		MujocoContactSurfacesPlugin plugin;
+		if (!plugin.load(&w.m, &w.d)) {
+			std::printf("{\"scenario\": \"batched\", \"error\": \"load failed\"}\n");
+			return 1;
+		}
+		std::fill(w.qfrc.begin(), w.qfrc.end(), 0.0);
+		w.collision_pass();
+		plugin.passiveCallback(&w.m, &w.d);
+		single[e] = w.qfrc;
+	}
+	BatchedContactSurfaces batch;
+	if (!batch.load(&worlds[0].m, N, { 0, 0 })) {
+		std::printf("{\"scenario\": \"batched\", \"error\": \"batch load failed\"}\n");
+		return 1;
+	}
+	batch.recordPair(gs, gb); // mj_collideGeoms order: sphere (2) before box (6)
+	std::vector<mjData *> data;
+	for (ShimWorld &w : worlds) {
+		std::fill(w.qfrc.begin(), w.qfrc.end(), 0.0);
+		data.push_back(&w.d);
+	}
+	batch.passiveCallback(&worlds[0].m, data.data(), N);
+	double max_diff = 0, checksum = 0;
+	for (int e = 0; e < N; ++e)
+		for (size_t k = 0; k < single[e].size(); ++k) {
+			max_diff = std::max(max_diff, std::fabs(single[e][k] - worlds[e].qfrc[k]));
+			checksum += std::fabs(worlds[e].qfrc[k]);
+		}
+	std::printf("{\"scenario\": \"batched\", \"n\": %d, \"blocks\": %d, \"pairs\": %d, \"max_abs_diff\": %.17g, \"checksum\": %.9g}\n", N,
+	            hcs_multi_n_blocks(batch.context()), batch.numPairs(), max_diff, checksum);
+	return 0;
+}
+
 int main()
 {
 	int rc = scenario_sphere_on_box();
@@ -525,6 +586,7 @@ int main()
 	rc |= scenario_curved_tip();
 	rc |= scenario_taxel_tip();
 	rc |= scenario_curved_poisson();
+	rc |= scenario_batched();
 	rc |= scenario_timing();
 	return rc;
 }

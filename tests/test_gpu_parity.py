@@ -601,3 +601,62 @@ def test_pipelined_steps_equal_synchronous_steps(hcs_lib, name, n_envs):
     with pytest.raises(Exception):
         eng.wait(tickets[0])  # its slot has been reused
     eng.close()
+
+
+def _cuda_device_count():
+    import ctypes
+    for name in ("libcudart.so", "libcudart.so.12", "libcudart.so.13"):
+        try:
+            rt = ctypes.CDLL(name)
+        except OSError:
+            continue
+        n = ctypes.c_int(0)
+        if rt.cudaGetDeviceCount(ctypes.byref(n)) == 0:
+            return n.value
+    import torch
+    return torch.cuda.device_count()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,n_envs,n_blocks", [("sphere_on_box", 37, 2), ("objects_on_plane", 16, 3), ("myrmex_box", 5, 2)])
+def test_multi_device_context_equals_one_context(hcs_lib, name, n_envs, n_blocks):
+    """hcs_multi (one context spanning GPUs, env blocks by index, one C++ host thread per block): per-geom wrenches,
+    per-pair results and taxel images are bit for bit those of a single context with the same environments, through the
+    synchronous and the pipelined step.  On a box with several GPUs the blocks sit on different devices (SURVEY.md section
+    4 item 5: multi-GPU bit-identity on hardware), with one GPU they share it."""
+    from mujoco_contact_surfaces_b200 import MultiDeviceEngine, REP_POLYGON, REP_TRIANGLE
+    factory = {"sphere_on_box": scenes.sphere_on_box, "objects_on_plane": scenes.objects_on_plane,
+               "myrmex_box": lambda: scenes.myrmex("box", 4)}[name]
+    scene = factory()
+    with_sensors = bool(scene.sensors)
+    n_dev = _cuda_device_count()
+    devices = [k % max(1, n_dev) for k in range(n_blocks)]
+    xp, xm, ve = [np.ascontiguousarray(a) for a in scene.poses(n_envs, seed=91)]
+    one = make_engine(scene, n_envs)
+    one.step(xp, xm, ve, with_sensors=with_sensors)
+    ref_w, ref_p = one.geom_wrenches().copy(), one.pair_results().copy()
+    ref_img = one.sensor_image(0).copy() if with_sensors else None
+    one.close()
+    multi = MultiDeviceEngine(n_envs, devices, representation=REP_TRIANGLE if scene.triangle else REP_POLYGON,
+                              apply_contact_forces=scene.apply_forces, **scene.engine_kwargs(n_envs))
+    scenes.configure(multi, scene)
+    multi.finalize()
+    blocks = multi.blocks()
+    assert len(blocks) == n_blocks and sum(c for _, c in blocks) == n_envs and blocks[0][0] == 0
+    for _ in range(2):
+        multi.step(xp, xm, ve, with_sensors=with_sensors)
+        assert multi.geom_wrenches().tobytes() == ref_w.tobytes()
+        got = multi.pair_results()
+        for f in ("F", "tau", "centroid", "area", "n_polygons", "n_faces", "n_points", "n_clipped"):
+            assert got[f].tobytes() == ref_p[f].tobytes(), f
+        if with_sensors:
+            assert multi.sensor_image(0).tobytes() == ref_img.tobytes()
+    out = np.full((n_envs, scene.n_geoms, 6), np.nan)
+    img = np.full_like(ref_img, np.nan) if with_sensors else None
+    t = multi.step_async(xp.ctypes.data, xm.ctypes.data, ve.ctypes.data, with_sensors, out.ctypes.data,
+                         [img.ctypes.data] if with_sensors else None)
+    multi.wait(t)
+    assert out.tobytes() == ref_w.tobytes()
+    if with_sensors:
+        assert img.tobytes() == ref_img.tobytes()
+    multi.close()

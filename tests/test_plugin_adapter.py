@@ -163,3 +163,16 @@ def test_adapter_curved_sensor_poisson_disk_samples(plugin_built):
     radius = np.sqrt(r["area"] / (0.7 * np.pi * sample_num))
     assert sample_num > 1000 and r["min_distance"] >= radius
     assert 0.5 * sample_num < r["n_samples"] < 2.0 * sample_num
+
+
+@pytest.mark.gpu
+def test_batched_adapter_equals_one_plugin_per_mjdata(plugin_built):
+    """BatchedContactSurfaces (C++, one hcs_multi context over two blocks) applies to six mjData exactly the generalised
+    forces six one-mjData plugin instances apply; the timing scenarios report sane per-step latencies."""
+    res = _run(plugin_built)
+    b = res["batched"]
+    assert b["n"] == 6 and b["blocks"] == 2 and b["pairs"] == 1
+    assert b["checksum"] > 0 and b["max_abs_diff"] == 0.0
+    for name in ("timing_sphere_on_box", "timing_objects_on_plane"):
+        t = res[name]
+        assert 0 < t["passive_callback_us"] < 5000 and t["qfrc_checksum"] > 0
