@@ -51,6 +51,7 @@ def parse():
                     help="diagnostic: leave the per-stage CUDA events out of the timed steps (no roofline then)")
     ap.add_argument("--sensors", type=int, default=-1, help="-1: on when the workload has sensors")
     ap.add_argument("--no-extra-workloads", action="store_true", help="only the headline workload (no `workloads` block)")
+    ap.add_argument("--random-sizes", action="store_true", help="per-environment geom sizes (scenes that define them: C4)")
     ap.add_argument("--multi-devices", default="", help="e.g. 0,1: ONE process drives these GPUs through the library's "
                     "multi-device context (hcs_multi, C++ host threads); prints an end-to-end line, no torch.distributed")
     return ap.parse_args()
@@ -58,7 +59,9 @@ def parse():
 
 # short legs of the default invocation: (key, workload, envs per GPU (weak) , steps, warmup)
 EXTRA_WORKLOADS = [("c2_myrmex_box_s20", "c2_myrmex_box", 1024, 60, 5), ("c3_soft_soft", "c3_soft_soft", 4096, 40, 5),
-                   ("c4_objects_on_plane", "c4_objects_on_plane", 4096, 100, 10), ("c5_grasp_box", "c5_grasp_box", 1024, 6, 3)]
+                   ("c4_objects_on_plane", "c4_objects_on_plane", 4096, 100, 10),
+                   ("c4_objects_on_plane_random_sizes", "c4_objects_on_plane", 4096, 100, 10),  # per-environment sizes
+                   ("c5_grasp_box", "c5_grasp_box", 1024, 6, 3)]
 # strong-scaling legs under torchrun: total environments split over the ranks (BASELINE.json configs 4 and 5)
 STRONG_WORKLOADS = [("c4_objects_on_plane", 4096, 100, 10), ("c5_grasp_box", 1024, 6, 3)]
 # fp64 operations per pair-eval that reaches the clipper (SURVEY.md section 8d "Algorithmic flops"), polygon or not
@@ -247,7 +250,8 @@ class Rig:
         return [float(x) for x in t]
 
 
-def measure(rig, scene, n_envs, env_offset, steps, warmup, with_sensors, pose_sets, stage_events=True, sampler=None):
+def measure(rig, scene, n_envs, env_offset, steps, warmup, with_sensors, pose_sets, stage_events=True, sampler=None,
+            random_sizes=False):
     """One leg: `steps` timed steps of `scene` on this rank's `n_envs` environments (global indices from env_offset).
     Returns this rank's raw numbers; the caller reduces them over the ranks."""
     torch = rig.torch
@@ -258,7 +262,12 @@ def measure(rig, scene, n_envs, env_offset, steps, warmup, with_sensors, pose_se
                              apply_contact_forces=scene.apply_forces, device=rig.local_rank, stream=rig.stream.cuda_stream,
                              **scene.engine_kwargs(n_envs))
     S.configure(eng, scene)
+    if random_sizes:  # domain-randomised geometry: per-environment meshes, fields and LBVHs (hcs_set_env_sizes)
+        for g, sz in scene.env_sizes(n_envs, 1234, env_offset).items():
+            eng.set_env_sizes(g, sz)
+    t_fin = time.perf_counter()
     eng.finalize()
+    finalize_s = time.perf_counter() - t_fin
     # env shard of this rank: contiguous block [env_offset, env_offset + n_envs); distinct pose sets per step
     sets_h, sets_d = [], []
     for i in range(pose_sets):
@@ -315,6 +324,7 @@ def measure(rig, scene, n_envs, env_offset, steps, warmup, with_sensors, pose_se
     out["dev_ms"], out["wall_s"] = timed_pass(False)  # the timed region of `value`
     out["staged_ms"] = timed_pass(True)[0] if stage_events else out["dev_ms"]
     out["kernels"] = eng.counters()["kernels"]
+    out["finalize_s"] = finalize_s
     out["res"] = eng.pair_results()
     out["tactile_triangles"] = eng.counters()["tactile_triangles"]
 
@@ -563,7 +573,7 @@ def main():
     # ---------------- headline: weak scaling, args.envs environments per GPU ----------------
     sampler = ClockSampler(local_rank) if rank == 0 else None
     m = measure(rig, scene, n_envs, rank * n_envs, args.steps, args.warmup, with_sensors, args.pose_sets,
-                stage_events=not args.no_stage_events, sampler=sampler)
+                stage_events=not args.no_stage_events, sampler=sampler, random_sizes=args.random_sizes)
     head = leg_summary(rig, scene, m, args.steps, n_envs, n_envs * world, args.workload, "weak")
 
     # ---------------- the other configs (short legs) and the strong-scaling legs ----------------
@@ -572,9 +582,13 @@ def main():
         for key, wl, envs, steps, warm in EXTRA_WORKLOADS:
             sc = S.SCENES[wl]()
             ws = bool(sc.sensors)
-            mm = measure(rig, sc, envs, rank * envs, steps, warm, ws, min(args.pose_sets, 4))
+            rnd = key.endswith("_random_sizes")
+            mm = measure(rig, sc, envs, rank * envs, steps, warm, ws, min(args.pose_sets, 4), random_sizes=rnd)
             leg = leg_summary(rig, sc, mm, steps, envs, envs * world, wl, "weak")
-            if rank == 0 and not args.no_cpu_baseline:
+            if rnd:
+                leg["geometry"] = ("per-environment sizes (hcs_set_env_sizes): every environment its own meshes, pressure fields and "
+                                   "LBVHs, built on the GPU at finalize in %.2f s" % mm["finalize_s"])
+            if rank == 0 and not args.no_cpu_baseline and not rnd:
                 leg["cpu_baseline"] = cpu_leg(sc, ws, 2.5)
             extra[key] = leg
             del mm

@@ -123,6 +123,16 @@ int hcs_update_geom(hcs_ctx *ctx, int geom, const double size[3]);
 
 /* geom pairs MuJoCo's collision pass hands to collision_cb (plugin.cpp:255-318), same for every env.
  * (g1,g2) in the order MuJoCo would pass them; rigid-rigid pairs are accepted and ignored. */
+/* Per-environment sizes of one geom (domain randomisation; SURVEY.md section 8 f3 "GPU mesh/field/LBVH (re)build ... for
+ * domain-randomised sizes per env"; the reference rebuilds ONE geom of its one mjData in onGeomChanged, plugin.cpp:828-975).
+ * sizes = [n_envs][3] in the convention of hcs_add_geom.  Every environment gets the mesh, pressure field and LBVH the
+ * single-size path would build for its size; all environments must lead to the SAME topology (sphere / ellipsoid: same
+ * refinement level, box grid: same cell counts, ...), else HCS_E_UNSUPPORTED with the first offending environment in the
+ * error text.  Sphere and ellipsoid vertices and pressures are generated on the GPU from the unit mesh (bit-identical to
+ * the host generator); other shapes are generated per environment on the host; fields, element records and the LBVH
+ * are built on the GPU for every environment.  sizes == NULL returns the geom to one size for all environments.
+ * Before or after hcs_finalize (then the context is rebuilt, like hcs_update_geom). */
+int hcs_set_env_sizes(hcs_ctx *ctx, int geom, const double *sizes);
 int hcs_set_pairs(hcs_ctx *ctx, const int32_t *g1, const int32_t *g2, int n_pairs);
 
 /* replaces FlatTactileSensor::load (SENS/src/flat_tactile_sensor.cpp:127-214): taxel grid
@@ -290,6 +300,7 @@ int hcs_multi_add_soft_mesh(hcs_multi *m, const double *verts, int n_vert, const
 int hcs_multi_add_rigid_mesh(hcs_multi *m, const double *verts, int n_vert, const int32_t *tris, int n_tri,
                              const double props[5]);
 int hcs_multi_update_geom(hcs_multi *m, int geom, const double size[3]);
+int hcs_multi_set_env_sizes(hcs_multi *m, int geom, const double *sizes); /* [n_envs][3] of the whole batch */
 int hcs_multi_set_pairs(hcs_multi *m, const int32_t *g1, const int32_t *g2, int n_pairs);
 int hcs_multi_add_flat_sensor(hcs_multi *m, int geom, double resolution, int sampling_resolution, int window, float sigma);
 int hcs_multi_finalize(hcs_multi *m);

@@ -40,6 +40,8 @@ struct GeomHost {
 	HostMesh mesh;
 	GeomDev dev{};
 	bool custom = false; // added through hcs_add_soft_mesh / hcs_add_rigid_mesh
+	std::vector<double> env_sizes; // [n_envs][3] per-environment sizes (hcs_set_env_sizes), empty: one size for all
+	double base_size[3] = { 0, 0, 0 }; // the one size the geom had before per-environment sizes were set
 	std::vector<void *> allocs;
 	double E() const { return mesh.soft ? props[0] : std::numeric_limits<double>::infinity(); }
 	double dissipation() const { return mesh.soft ? props[1] : 1.0; } // ContactProperties ctor, plugin.h:197-198
@@ -306,9 +308,182 @@ static std::vector<BvhNode> build_lbvh(const HostMesh &m)
 	return nodes;
 }
 
+// bounding sphere about the box centre of the vertices
+static void bounding_sphere(const double *verts, int nv, double c[3], double &r)
+{
+	double lo[3] = { 1e300, 1e300, 1e300 }, hi[3] = { -1e300, -1e300, -1e300 };
+	for (int i = 0; i < nv; ++i)
+		for (int a = 0; a < 3; ++a) {
+			lo[a] = std::min(lo[a], verts[3 * (size_t)i + a]);
+			hi[a] = std::max(hi[a], verts[3 * (size_t)i + a]);
+		}
+	double r2 = 0;
+	for (int a = 0; a < 3; ++a)
+		c[a] = 0.5 * (lo[a] + hi[a]);
+	for (int i = 0; i < nv; ++i) {
+		double s = 0;
+		for (int a = 0; a < 3; ++a) {
+			double t = verts[3 * (size_t)i + a] - c[a];
+			s += t * t;
+		}
+		r2 = std::max(r2, s);
+	}
+	r = std::sqrt(r2) * (1 + 1e-12) + 1e-12;
+}
+
+// bounds of the tet centroids: they fix the Morton quantisation grid of the LBVH build
+static void centroid_bounds(const double *verts, const int32_t *elems, int ne, double glo[3], double ghi[3])
+{
+	for (int a = 0; a < 3; ++a)
+		glo[a] = 1e300, ghi[a] = -1e300;
+	for (int t = 0; t < ne; ++t) {
+		double cc[3] = { 0, 0, 0 };
+		for (int k = 0; k < 4; ++k)
+			for (int a = 0; a < 3; ++a)
+				cc[a] += 0.25 * verts[3 * (size_t)elems[4 * (size_t)t + k] + a];
+		for (int a = 0; a < 3; ++a) {
+			glo[a] = std::min(glo[a], cc[a]);
+			ghi[a] = std::max(ghi[a], cc[a]);
+		}
+	}
+}
+
+// Per-environment sizes (hcs_set_env_sizes): ONE topology (g.mesh, the mesh of environment 0), every
+// environment its own vertices, pressures, element records and LBVH, env-major.  Sphere / ellipsoid vertices and pressures
+// are generated on the GPU from the unit mesh; other shapes come from the host generator, environment by environment.
+// Fields, element records (K1) and the LBVH (K2) are built on the GPU for every environment.
+static void upload_geom_per_env(hcs_ctx *c, GeomHost &g)
+{
+	const int n_env   = c->cfg.n_envs;
+	const HostMesh &m = g.mesh;
+	if (m.plane || g.custom || (int)g.env_sizes.size() != 3 * n_env)
+		throw std::runtime_error("per-environment sizes: needs a generated (non-plane) geom and n_envs x 3 sizes");
+	GeomDev d{};
+	d.kind    = m.soft ? 1 : 0;
+	d.n_verts = m.n_verts();
+	d.n_elems = m.n_elems();
+	const int nv = d.n_verts, ne = d.n_elems, per = m.soft ? 4 : 3;
+	if (m.soft && ne < 2)
+		throw std::runtime_error("per-environment sizes: the soft geom needs at least two tets");
+	d.elems = dalloc<int32_t>(g.allocs, m.elems.size());
+	CK(cudaMemcpyAsync(d.elems, m.elems.data(), m.elems.size() * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+	d.verts = dalloc<double>(g.allocs, (size_t)n_env * nv * 3);
+	if (m.soft)
+		d.pressure = dalloc<double>(g.allocs, (size_t)n_env * nv);
+	std::vector<double> verts((size_t)n_env * nv * 3);
+	const bool sphere_like = g.mj_type == HCS_GEOM_SPHERE || g.mj_type == HCS_GEOM_ELLIPSOID;
+	if (sphere_like) {
+		const int level = sphere_like_level(g.mj_type, &g.env_sizes[0], g.props[2]);
+		for (int e = 1; e < n_env; ++e)
+			if (sphere_like_level(g.mj_type, &g.env_sizes[3 * (size_t)e], g.props[2]) != level)
+				throw std::runtime_error("per-environment sizes: environment " + std::to_string(e) +
+				                         " needs another refinement level than environment 0 (scale the resolution hint with the size)");
+		std::vector<double> unit;
+		unit_sphere_vertices(level, unit);
+		const int vol_offset = m.soft ? 0 : 1; // the rigid surface drops the centre vertex
+		if ((int)unit.size() / 3 != nv + vol_offset)
+			throw std::runtime_error("per-environment sizes: unit sphere and geom mesh disagree");
+		double *d_unit  = dalloc<double>(g.allocs, unit.size());
+		double *d_sizes = dalloc<double>(g.allocs, g.env_sizes.size());
+		CK(cudaMemcpyAsync(d_unit, unit.data(), unit.size() * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+		CK(cudaMemcpyAsync(d_sizes, g.env_sizes.data(), g.env_sizes.size() * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+		launch_sphere_env_verts(d_unit, nv, vol_offset, d_sizes, n_env, g.mj_type == HCS_GEOM_SPHERE, g.props[0], d.verts, d.pressure,
+		                        c->stream);
+		CK(cudaMemcpyAsync(verts.data(), d.verts, verts.size() * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+		CK(cudaStreamSynchronize(c->stream)); // (the host needs the vertices for the bounds below; `unit` is a local)
+	} else {
+		std::vector<double> pressure(m.soft ? (size_t)n_env * nv : 0);
+		for (int e = 0; e < n_env; ++e) {
+			HostMesh me;
+			std::string err;
+			if (!build_geom_mesh(g.mj_type, &g.env_sizes[3 * (size_t)e], nullptr, 0, nullptr, 0, g.props, me, err))
+				throw std::runtime_error("per-environment sizes: environment " + std::to_string(e) + ": " + err);
+			if (me.elems != m.elems || me.n_verts() != nv)
+				throw std::runtime_error("per-environment sizes: environment " + std::to_string(e) +
+				                         " leads to another mesh topology than environment 0");
+			std::copy(me.verts.begin(), me.verts.end(), verts.begin() + (size_t)e * nv * 3);
+			if (m.soft)
+				std::copy(me.pressure.begin(), me.pressure.end(), pressure.begin() + (size_t)e * nv);
+		}
+		CK(cudaMemcpyAsync(d.verts, verts.data(), verts.size() * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+		if (m.soft)
+			CK(cudaMemcpyAsync(d.pressure, pressure.data(), pressure.size() * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+		CK(cudaStreamSynchronize(c->stream)); // `pressure` is a local
+	}
+	d.env_stride       = ne;
+	d.env_stride_verts = nv;
+	d.env_stride_nodes = m.soft ? ne - 1 : 0;
+	std::vector<double> bounds((size_t)n_env * ENV_BOUNDS, 0.0);
+	if (m.soft) {
+		d.tet_geom     = dalloc<TetGeom>(g.allocs, (size_t)n_env * ne);
+		d.tet_field    = dalloc<TetField>(g.allocs, (size_t)n_env * ne);
+		d.tet_leaf32   = dalloc<TetLeaf32>(g.allocs, (size_t)n_env * ne);
+		d.tet_leafss32 = dalloc<TetLeafSS32>(g.allocs, (size_t)n_env * ne);
+		d.tet_box32    = dalloc<TetBox32>(g.allocs, (size_t)n_env * ne);
+		d.nodes        = dalloc<BvhNode>(g.allocs, (size_t)n_env * (ne - 1));
+	} else {
+		d.tris = dalloc<TriRec>(g.allocs, (size_t)n_env * ne);
+	}
+	void *scratch = nullptr;
+	if (m.soft)
+		CK(cudaMalloc(&scratch, lbvh_scratch_bytes(ne)));
+	for (int e = 0; e < n_env; ++e) {
+		GeomDev v = d; // environment e's slice of every array
+		v.verts   = d.verts + (size_t)e * nv * 3;
+		const double *hv = verts.data() + (size_t)e * nv * 3;
+		bounding_sphere(hv, nv, &bounds[(size_t)e * ENV_BOUNDS], bounds[(size_t)e * ENV_BOUNDS + 3]);
+		if (m.soft) {
+			v.pressure     = d.pressure + (size_t)e * nv;
+			v.tet_geom     = d.tet_geom + (size_t)e * ne;
+			v.tet_field    = d.tet_field + (size_t)e * ne;
+			v.tet_leaf32   = d.tet_leaf32 + (size_t)e * ne;
+			v.tet_leafss32 = d.tet_leafss32 + (size_t)e * ne;
+			v.tet_box32    = d.tet_box32 + (size_t)e * ne;
+			v.nodes        = d.nodes + (size_t)e * (ne - 1);
+			double glo[3], ghi[3];
+			centroid_bounds(hv, m.elems.data(), ne, glo, ghi);
+			launch_build_lbvh(v, glo, ghi, scratch, c->stream);
+			launch_build_tets(v, c->stream);
+		} else {
+			v.tris = d.tris + (size_t)e * ne;
+			launch_build_tris(v, c->stream);
+		}
+	}
+	if (m.soft) { // root boxes: node 0 of every environment
+		std::vector<BvhNode> roots(n_env);
+		CK(cudaMemcpy2DAsync(roots.data(), sizeof(BvhNode), d.nodes, (size_t)(ne - 1) * sizeof(BvhNode), sizeof(BvhNode), n_env,
+		                     cudaMemcpyDeviceToHost, c->stream));
+		CK(cudaStreamSynchronize(c->stream));
+		cudaFree(scratch);
+		for (int e = 0; e < n_env; ++e)
+			for (int a = 0; a < 3; ++a) {
+				bounds[(size_t)e * ENV_BOUNDS + 4 + a] = std::min(roots[e].llo[a], roots[e].rlo[a]);
+				bounds[(size_t)e * ENV_BOUNDS + 7 + a] = std::max(roots[e].lhi[a], roots[e].rhi[a]);
+			}
+	}
+	CK(cudaGetLastError());
+	double *d_bounds = dalloc<double>(g.allocs, bounds.size());
+	CK(cudaMemcpyAsync(d_bounds, bounds.data(), bounds.size() * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+	CK(cudaStreamSynchronize(c->stream)); // `bounds` is a local
+	d.env_bounds = d_bounds;
+	// the members that describe one geometry: environment 0; bound_r: the largest (pool sizing, accumulator scale)
+	for (int a = 0; a < 3; ++a) {
+		d.bound_c[a] = bounds[a];
+		d.root_lo[a] = (float)bounds[4 + a], d.root_hi[a] = (float)bounds[7 + a];
+	}
+	d.bound_r = 0;
+	for (int e = 0; e < n_env; ++e)
+		d.bound_r = std::max(d.bound_r, bounds[(size_t)e * ENV_BOUNDS + 3]);
+	g.dev = d;
+}
+
 static void upload_geom(hcs_ctx *c, GeomHost &g)
 {
 	free_bag(g.allocs);
+	if (!g.env_sizes.empty()) {
+		upload_geom_per_env(c, g);
+		return;
+	}
 	GeomDev d{};
 	const HostMesh &m = g.mesh;
 	d.kind            = m.plane ? 2 : (m.soft ? 1 : 0);
@@ -728,8 +903,11 @@ static void finalize(hcs_ctx *c)
 	const int n_env = c->cfg.n_envs, ng = (int)c->geoms.size(), np = (int)c->pairs.size();
 	for (GeomHost &g : c->geoms)
 		upload_geom(c, g);
-	for (SensorHost &s : c->sensors)
+	for (SensorHost &s : c->sensors) {
+		if (!c->geoms[s.geom].env_sizes.empty())
+			throw std::runtime_error("per-environment sizes: a flat-sensor geom keeps one size (its taxel grid is laid out from it)");
 		build_sensor(c, s);
+	}
 	c->n_counters = 6 + PAIR_COUNTERS * (size_t)np;
 	c->d_counters = dalloc<int32_t>(c->step_allocs, c->n_counters);
 	CK(cudaMemsetAsync(c->d_counters, 0, c->n_counters * sizeof(int32_t), c->stream));
@@ -1229,9 +1407,56 @@ int hcs_update_geom(hcs_ctx *c, int geom, const double size[3])
 	for (int i = 0; i < 3; ++i)
 		g.size[i] = size[i];
 	g.mesh = std::move(m);
+	g.env_sizes.clear(); // one size for every environment again
 	if (c->finalized) { // element counts may change: rebuild the per-pair buffers as well
 		CK(cudaStreamSynchronize(c->stream));
 		finalize(c);
+	}
+	return HCS_OK;
+	API_END(c)
+}
+
+int hcs_set_env_sizes(hcs_ctx *c, int geom, const double *sizes)
+{
+	API_BEGIN(c)
+	if (geom < 0 || geom >= (int)c->geoms.size() || c->geoms[geom].custom) {
+		c->err = "hcs_set_env_sizes: bad geom (needs a geom added with hcs_add_geom)";
+		return HCS_E_INVALID;
+	}
+	GeomHost &g = c->geoms[geom];
+	if (g.mj_type == HCS_GEOM_MESH || g.mj_type == HCS_GEOM_PLANE) {
+		c->err = "hcs_set_env_sizes: mesh and plane geoms do not depend on geom_size";
+		return HCS_E_UNSUPPORTED;
+	}
+	if (!sizes && g.env_sizes.empty())
+		return HCS_OK;
+	{
+		const double *one = sizes ? sizes : g.base_size; // the shared topology is the mesh of environment 0 / the geom's own size
+		HostMesh m;
+		std::string err;
+		if (!build_geom_mesh(g.mj_type, one, nullptr, 0, nullptr, 0, g.props, m, err)) {
+			c->err = err;
+			return HCS_E_UNSUPPORTED;
+		}
+		if (sizes && g.env_sizes.empty())
+			for (int i = 0; i < 3; ++i)
+				g.base_size[i] = g.size[i];
+		if (sizes)
+			g.env_sizes.assign(sizes, sizes + 3 * (size_t)c->cfg.n_envs);
+		else
+			g.env_sizes.clear();
+		for (int i = 0; i < 3; ++i)
+			g.size[i] = one[i];
+		g.mesh = std::move(m);
+	}
+	if (c->finalized) {
+		CK(cudaStreamSynchronize(c->stream));
+		try {
+			finalize(c);
+		} catch (const std::exception &ex) {
+			c->err = ex.what();
+			return std::string(ex.what()).find("per-environment sizes") != std::string::npos ? HCS_E_UNSUPPORTED : HCS_E_CUDA;
+		}
 	}
 	return HCS_OK;
 	API_END(c)

@@ -67,7 +67,19 @@ struct GeomDev {
 	double bound_c[3];  // bounding sphere in the geom frame
 	double bound_r;
 	float root_lo[3], root_hi[3]; // soft: box of the whole LBVH
+	// Per-environment sizes (hcs_set_env_sizes: domain-randomised geometry): every environment has
+	// its own vertices, pressures, element records and LBVH of ONE shared topology, laid out env-major.  env_stride = element
+	// records per environment (0: one geometry for all environments, the arrays above are it), env_stride_nodes likewise
+	// for the LBVH, env_stride_verts for verts / pressure; env_bounds = [n_env][ENV_BOUNDS] doubles: bound_c, bound_r,
+	// root_lo, root_hi of each environment (the members above then describe environment 0).
+	int env_stride, env_stride_nodes, env_stride_verts;
+	const double *env_bounds;
+#ifdef __CUDACC__
+	__host__ __device__ __forceinline__ size_t eoff(int env) const { return (size_t)env * (size_t)env_stride; }
+	__host__ __device__ __forceinline__ size_t noff(int env) const { return (size_t)env * (size_t)env_stride_nodes; }
+#endif
 };
+constexpr int ENV_BOUNDS = 10;
 
 enum PairKind { PAIR_NONE = 0, PAIR_SOFT_RIGID = 1, PAIR_SOFT_PLANE = 2, PAIR_SOFT_SOFT = 3 };
 
@@ -222,6 +234,31 @@ struct TaxelDev {
 	int max_samples;
 };
 
+#ifdef __CUDACC__
+struct GeomBounds {
+	double c[3], r;
+	float lo[3], hi[3];
+};
+// bounding sphere and root box of a geom in one environment
+__device__ __forceinline__ GeomBounds geom_bounds(const GeomDev &g, int env)
+{
+	GeomBounds b;
+	if (g.env_bounds) {
+		const double *p = g.env_bounds + (size_t)env * ENV_BOUNDS;
+#pragma unroll
+		for (int a = 0; a < 3; ++a)
+			b.c[a] = p[a], b.lo[a] = (float)p[4 + a], b.hi[a] = (float)p[7 + a];
+		b.r = p[3];
+	} else {
+#pragma unroll
+		for (int a = 0; a < 3; ++a)
+			b.c[a] = g.bound_c[a], b.lo[a] = g.root_lo[a], b.hi[a] = g.root_hi[a];
+		b.r = g.bound_r;
+	}
+	return b;
+}
+#endif
+
 // ---- programmatic dependent launch (sm_90+) -------------------------------------------------------
 // The step is a chain of short kernels (C1: 50 + 39 + 14 us).  A kernel launched with launch_chained may become
 // resident while its predecessor in the stream is still draining: the predecessor's CTAs call pdl_release() on entry,
@@ -268,6 +305,9 @@ static inline void launch_chained(void (*kernel)(KArgs...), dim3 grid, dim3 bloc
 // ---- launchers (definitions in the .cu files) ---------------------------------------------------
 void launch_build_tets(const GeomDev &g, cudaStream_t s);
 void launch_build_tris(const GeomDev &g, cudaStream_t s);
+// per-environment vertices (+ pressures) of a sphere / ellipsoid from the unit mesh and [n_env][3] sizes (device arrays)
+void launch_sphere_env_verts(const double *unit, int n_verts, int vol_offset, const double *sizes, int n_env, int is_sphere, double E,
+                             double *verts, double *pressure, cudaStream_t s);
 // K2: LBVH of a soft geom on the GPU (g.nodes receives n_elems-1 records); glo/ghi = centroid bounds
 size_t lbvh_scratch_bytes(int n);
 void launch_build_lbvh(const GeomDev &g, const double glo[3], const double ghi[3], void *scratch, cudaStream_t s);

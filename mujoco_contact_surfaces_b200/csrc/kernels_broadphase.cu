@@ -162,20 +162,21 @@ __device__ __forceinline__ Xform slot_xab(const PairDesc &P, const Q &W, int s)
 // coordinate involved) is > 5x the worst rounding of the float dot products and of the inputs' conversion.  NaNs compare
 // false and fall through.  Only the gradient cull is a semantic filter: it is decided in float when clear by 1e-5,
 // otherwise by the reference's fp64 expression.  s: slot of the query; skip: tet planes the clip may leave out.
-template <bool FLAT, class Q>
+template <bool FLAT, bool PRISM, class Q>
 __device__ __forceinline__ bool leaf_test_rigid(const PairDesc &P, const Q &W, int s, int tet, int &skip)
 {
 	skip = 0;
-	const TetLeaf32 *tl = P.A.tet_leaf32 + tet;
+	const int env_ = FLAT ? W.qenv[s] : 0; // (per-environment geometry goes through the flat kernels only)
+	const TetLeaf32 *tl = P.A.tet_leaf32 + P.A.eoff(env_) + tet;
 	const F8 l0 = ld8f(tl, 0), l1 = ld8f(tl, 1), l2 = ld8f(tl, 2), l3 = ld8f(tl, 3);
 	const float nx = W.qpl[0][s], ny = W.qpl[1][s], nz = W.qpl[2][s], dtf = W.qpl[3][s], m = W.qm[s];
 	const float cosg = fdot3(l2.a[0], l2.a[1], l2.a[2], nx, ny, nz);
 	if (cosg < (float)HCS_COS_ALPHA - 1e-5f)
 		return false;
 	if (cosg < (float)HCS_COS_ALPHA + 1e-5f) { // undecided in float: the reference's expression in double
-		const TriVerts tr = load_tri(P.B.tris + W.qid[s]);
+		const TriVerts tr = load_tri(P.B.tris + P.B.eoff(env_) + W.qid[s]);
 		const Xform X_AB  = FLAT ? slot_xab(P, W, s) : unit_xab(W);
-		if (!(dot(load_ghat(P.A.tet_field + tet), rot(X_AB.R, tr.n)) > HCS_COS_ALPHA))
+		if (!(dot(load_ghat(P.A.tet_field + P.A.eoff(env_) + tet), rot(X_AB.R, tr.n)) > HCS_COS_ALPHA))
 			return false;
 	}
 	const float ax = W.qvf[0][s], ay = W.qvf[1][s], az = W.qvf[2][s], bx = W.qvf[3][s], by = W.qvf[4][s], bz = W.qvf[5][s],
@@ -207,8 +208,8 @@ __device__ __forceinline__ bool leaf_test_rigid(const PairDesc &P, const Q &W, i
 	float h2 = fdot3(nx, ny, nz, tv[2][0], tv[2][1], tv[2][2]) - dtf, h3 = fdot3(nx, ny, nz, tv[3][0], tv[3][1], tv[3][2]) - dtf;
 	if ((h0 > m && h1 > m && h2 > m && h3 > m) || (h0 < -m && h1 < -m && h2 < -m && h3 < -m))
 		return false;
-#if HCS_BP_PRISM_TEST
-	// Prism test (off by default, see HCS_BP_PRISM_TEST): the plane through a triangle edge e = q - p along the triangle normal n has the (unnormalised) outward
+	if (PRISM || HCS_BP_PRISM_TEST)
+	// Prism test (large trees, see bp_traverse_kernel; HCS_BP_PRISM_TEST: everywhere): the plane through a triangle edge e = q - p along the triangle normal n has the (unnormalised) outward
 	// normal me = e x n, |me| = |e|.  All four tet vertices beyond it by more than m |e|_1 (>= m |e|: the float error of
 	// the expression is < m |e| / 4) => tet and triangle are separated by that plane => the clip is empty.
 	{
@@ -227,7 +228,6 @@ __device__ __forceinline__ bool leaf_test_rigid(const PairDesc &P, const Q &W, i
 				return false;
 		}
 	}
-#endif
 	return true;
 }
 
@@ -242,8 +242,9 @@ template <bool FLAT, class Q>
 __device__ __forceinline__ bool leaf_test_soft(const PairDesc &P, const Q &W, int s, int tet)
 {
 	bool keep = true, need_exact = true;
+	const int env_ = FLAT ? W.qenv[s] : 0;
 	{
-		const TetLeafSS32 *tl = P.A.tet_leafss32 + tet;
+		const TetLeafSS32 *tl = P.A.tet_leafss32 + P.A.eoff(env_) + tet;
 		const F8 l0 = ld8f(tl, 0), l1 = ld8f(tl, 1), l2 = ld8f(tl, 2);
 		const float nx = l0.a[0] - W.qpl[0][s], ny = l0.a[1] - W.qpl[1][s], nz = l0.a[2] - W.qpl[2][s];
 		const float mag2 = fdot3(nx, ny, nz, nx, ny, nz);
@@ -283,7 +284,7 @@ __device__ __forceinline__ bool leaf_test_soft(const PairDesc &P, const Q &W, in
 		return keep;
 	const Xform X_AB   = FLAT ? slot_xab(P, W, s) : unit_xab(W);
 	const D3 p_BAo     = FLAT ? xyz(ld4(P.pair_ctx + (size_t)W.qenv[s] * PAIR_CTX_DOUBLES + CTX_PBA)) : mk(W.pba[0], W.pba[1], W.pba[2]);
-	const TetField *f0 = P.A.tet_field + tet, *f1 = P.B.tet_field + W.qid[s];
+	const TetField *f0 = P.A.tet_field + P.A.eoff(env_) + tet, *f1 = P.B.tet_field + P.B.eoff(env_) + W.qid[s];
 	const D4 ge0 = load_grad_e0(f0), ge1 = load_grad_e0(f1);
 	D3 grad0 = xyz(ge0), grad1_N = xyz(ge1);
 	D3 grad1_M   = rot(X_AB.R, grad1_N);
@@ -299,11 +300,11 @@ __device__ __forceinline__ bool leaf_test_soft(const PairDesc &P, const Q &W, in
 		return false;
 	if (!(dot(rotT(X_AB.R, -nhat), load_ghat(f1)) > HCS_COS_ALPHA))
 		return false;
-	const TetVerts tg = load_tet_verts(P.A.tet_geom + tet);
+	const TetVerts tg = load_tet_verts(P.A.tet_geom + P.A.eoff(env_) + tet);
 	double h0 = dot(nhat, tg.v0) - pd, h1 = dot(nhat, tg.v1) - pd, h2 = dot(nhat, tg.v2) - pd, h3 = dot(nhat, tg.v3) - pd;
 	if ((h0 > 1e-12 && h1 > 1e-12 && h2 > 1e-12 && h3 > 1e-12) || (h0 < -1e-12 && h1 < -1e-12 && h2 < -1e-12 && h3 < -1e-12))
 		return false;
-	const TetVerts tq = load_tet_verts(P.B.tet_geom + W.qid[s]);
+	const TetVerts tq = load_tet_verts(P.B.tet_geom + P.B.eoff(env_) + W.qid[s]);
 	double g0 = dot(nhat, apply(X_AB, tq.v0)) - pd, g1 = dot(nhat, apply(X_AB, tq.v1)) - pd,
 	       g2 = dot(nhat, apply(X_AB, tq.v2)) - pd, g3 = dot(nhat, apply(X_AB, tq.v3)) - pd;
 	if ((g0 > 1e-12 && g1 > 1e-12 && g2 > 1e-12 && g3 > 1e-12) || (g0 < -1e-12 && g1 < -1e-12 && g2 < -1e-12 && g3 < -1e-12))
@@ -380,7 +381,8 @@ __global__ void __launch_bounds__(BP_BLOCK, BP_CTAS_PER_SM) broadphase_kernel(Pa
 			n_S = mk(X_AB.R[2], X_AB.R[5], X_AB.R[8]);
 			pd  = dot(n_S, X_AB.p);
 			// the whole geom above the plane: nothing can be cut
-			active = !(dot(n_S, mk(P.A.bound_c[0], P.A.bound_c[1], P.A.bound_c[2])) - pd > P.A.bound_r + 1e-9);
+			const GeomBounds bA = geom_bounds(P.A, env);
+			active = !(dot(n_S, mk(bA.c[0], bA.c[1], bA.c[2])) - pd > bA.r + 1e-9);
 		}
 		if (lane == 0) { // what the exact fallbacks of the leaf tests read back (rare paths)
 #pragma unroll
@@ -405,7 +407,7 @@ __global__ void __launch_bounds__(BP_BLOCK, BP_CTAS_PER_SM) broadphase_kernel(Pa
 				// ---- half space: classify tet q of A; the tets the plane cuts are the unit's candidates ----
 				bool keep = false;
 				if (alive) {
-					const TetVerts tg = load_tet_verts(P.A.tet_geom + q);
+					const TetVerts tg = load_tet_verts(P.A.tet_geom + P.A.eoff(env) + q);
 					int code = 0;
 #pragma unroll
 					for (int k = 0; k < 4; ++k)
@@ -507,7 +509,7 @@ __global__ void __launch_bounds__(BP_BLOCK, BP_CTAS_PER_SM) broadphase_kernel(Pa
 						const unsigned raw = W.leafq[n_leaf - k + lane];
 						s = (int)(raw >> ITEM_SHIFT), tet = raw & ITEM_MASK;
 						if constexpr (!QTET)
-							keep = leaf_test_rigid<false>(P, W, s, (int)tet, skip);
+							keep = leaf_test_rigid<false, false>(P, W, s, (int)tet, skip);
 						else
 							keep = leaf_test_soft<false>(P, W, s, (int)tet);
 					}
@@ -656,19 +658,20 @@ __global__ void __launch_bounds__(PREP_BLOCK) bp_prepare_kernel(PairDesc P, Step
 		const D3 p_BAo   = -rotT(X_AB.R, X_AB.p); // origin of A expressed in B (p_NMo of field_intersection.cc)
 		if (q == 0)
 			write_pair_ctx(P, io, env, X_WA, X_WB, X_AB, p_BAo);
+		const GeomBounds bA = geom_bounds(P.A, env), bB = geom_bounds(P.B, env);
 		{ // pair-level reject on bounding spheres
-			D3 ca = apply(X_WA, mk(P.A.bound_c[0], P.A.bound_c[1], P.A.bound_c[2]));
-			D3 cb = apply(X_WB, mk(P.B.bound_c[0], P.B.bound_c[1], P.B.bound_c[2]));
+			D3 ca = apply(X_WA, mk(bA.c[0], bA.c[1], bA.c[2]));
+			D3 cb = apply(X_WB, mk(bB.c[0], bB.c[1], bB.c[2]));
 			D3 d  = ca - cb;
-			double rr = P.A.bound_r + P.B.bound_r + 1e-9;
+			double rr = bA.r + bB.r + 1e-9;
 			alive     = !(dot(d, d) > rr * rr);
 		}
 		if (alive) {
-			const float leaf_scale =
-			    (float)(fmax(fmax(fabs(P.A.bound_c[0]), fabs(P.A.bound_c[1])), fabs(P.A.bound_c[2])) + P.A.bound_r);
+			const float leaf_scale = (float)(fmax(fmax(fabs(bA.c[0]), fabs(bA.c[1])), fabs(bA.c[2])) + bA.r);
 			double v[12];
 			double lo[3] = { 1e300, 1e300, 1e300 }, hi[3] = { -1e300, -1e300, -1e300 };
-			const double *vp = QTET ? reinterpret_cast<const double *>(P.B.tet_geom + q) : reinterpret_cast<const double *>(P.B.tris + q);
+			const double *vp = QTET ? reinterpret_cast<const double *>(P.B.tet_geom + P.B.eoff(env) + q) :
+			                          reinterpret_cast<const double *>(P.B.tris + P.B.eoff(env) + q);
 			const D4 r0 = ld4(vp), r1 = ld4(vp + 4), r2 = ld4(vp + 8);
 			const D3 qv[4] = { mk(r0.x, r0.y, r0.z), mk(r0.w, r1.x, r1.y), mk(r1.z, r1.w, r2.x), mk(r2.y, r2.z, r2.w) };
 			constexpr int nvq = QTET ? 4 : 3;
@@ -688,8 +691,8 @@ __global__ void __launch_bounds__(PREP_BLOCK) bp_prepare_kernel(PairDesc P, Step
 				rec[AR_BOX + a]     = __double2float_rd(lo[a] - 1e-9);
 				rec[AR_BOX + 3 + a] = __double2float_ru(hi[a] + 1e-9);
 			}
-			alive = rec[0] <= P.A.root_hi[0] && rec[3] >= P.A.root_lo[0] && rec[1] <= P.A.root_hi[1] && rec[4] >= P.A.root_lo[1] &&
-			        rec[2] <= P.A.root_hi[2] && rec[5] >= P.A.root_lo[2];
+			alive = rec[0] <= bA.hi[0] && rec[3] >= bA.lo[0] && rec[1] <= bA.hi[1] && rec[4] >= bA.lo[1] && rec[2] <= bA.hi[2] &&
+			        rec[5] >= bA.lo[2];
 			if (alive) {
 				float big = leaf_scale;
 				constexpr int nf = QTET ? 12 : 9;
@@ -705,7 +708,7 @@ __global__ void __launch_bounds__(PREP_BLOCK) bp_prepare_kernel(PairDesc P, Step
 				} else {
 					// what the float filter of the soft-soft leaf test needs of the query tet, computed once per query in
 					// double: gradient and unit gradient rotated into A's frame, field value at A's origin
-					const TetField *f1 = P.B.tet_field + q;
+					const TetField *f1 = P.B.tet_field + P.B.eoff(env) + q;
 					const D4 ge1       = load_grad_e0(f1);
 					const D3 g1M = rot(X_AB.R, xyz(ge1)), gh1M = rot(X_AB.R, load_ghat(f1));
 					rec[AR_PL] = (float)g1M.x, rec[AR_PL + 1] = (float)g1M.y, rec[AR_PL + 2] = (float)g1M.z;
@@ -759,7 +762,12 @@ __device__ __forceinline__ void flush_flat(const PairDesc &P, const StepIO &io, 
 	n_stage = 0;
 }
 
-template <bool QTET, bool SWEEP>
+// PRISM (soft-rigid, trees of PRISM_MIN_TREE tets and more): the leaf filter also tests the three planes through the
+// triangle's edges along its normal.  Measured (scripts/r02_run8.sh): C5 x 1024 (131 072-tet pads) broadphase 15.4 -> 17.8 ms,
+// narrowphase 19.9 -> 15.0 ms (93.3 k -> 66.5 k candidates per env reach the clipper): step 42.5 -> 38.1 ms; C1 x 4096
+// (128 tets) +3.3 / -4.1 us: a wash, left off there.
+constexpr int PRISM_MIN_TREE = 4096;
+template <bool QTET, bool SWEEP, bool PRISM>
 __global__ void __launch_bounds__(BP_BLOCK, FT_CTAS_PER_SM) bp_traverse_kernel(PairDesc P, StepIO io, int fixed_slots)
 {
 	typedef typename std::conditional<QTET, FlatQueuesSoft, FlatQueuesRigid>::type Queues;
@@ -839,7 +847,7 @@ __global__ void __launch_bounds__(BP_BLOCK, FT_CTAS_PER_SM) bp_traverse_kernel(P
 					s = (int)(raw >> ITEM_SHIFT), tet = raw & ITEM_MASK;
 					atomicAdd(&W.qev[s], 1);
 					if constexpr (!QTET)
-						keep = leaf_test_rigid<true>(P, W, s, (int)tet, skip);
+						keep = leaf_test_rigid<true, PRISM>(P, W, s, (int)tet, skip);
 					else
 						keep = leaf_test_soft<true>(P, W, s, (int)tet);
 				}
@@ -866,7 +874,7 @@ __global__ void __launch_bounds__(BP_BLOCK, FT_CTAS_PER_SM) bp_traverse_kernel(P
 						for (int a = 0; a < 4; ++a)
 							pl[a] = W.qpl[a][sw_s];
 					}
-					const F8 tb = *reinterpret_cast<const F8 *>(P.A.tet_box32 + t);
+					const F8 tb = *reinterpret_cast<const F8 *>(P.A.tet_box32 + P.A.eoff(W.qenv[sw_s]) + t);
 					hit = child_overlap<!QTET>(qb, pl, tb.a[0], tb.a[1], tb.a[2], tb.a[3], tb.a[4], tb.a[5]);
 				}
 				const unsigned mh = __ballot_sync(FULL_MASK, hit);
@@ -896,7 +904,7 @@ __global__ void __launch_bounds__(BP_BLOCK, FT_CTAS_PER_SM) bp_traverse_kernel(P
 						for (int a = 0; a < 4; ++a)
 							pl[a] = W.qpl[a][s];
 					}
-					const float4 *nd = nodes4 + 4 * (size_t)(raw & ITEM_MASK);
+					const float4 *nd = nodes4 + 4 * (P.A.noff(W.qenv[s]) + (size_t)(raw & ITEM_MASK));
 					const float4 a = nd[0], b = nd[1], c = nd[2], d = nd[3];
 					cl = __float_as_int(d.x), cr = __float_as_int(d.y);
 					if (child_overlap<!QTET>(qb, pl, a.x, a.y, a.z, a.w, b.x, b.y)) {
@@ -943,14 +951,14 @@ __global__ void __launch_bounds__(BP_BLOCK, FT_CTAS_PER_SM) bp_traverse_kernel(P
 	}
 }
 
-template <bool QTET, bool SWEEP>
+template <bool QTET, bool SWEEP, bool PRISM = false>
 static void launch_flat_bp(const PairDesc &P, const StepIO &io, cudaStream_t s)
 {
 	typedef typename std::conditional<QTET, FlatQueuesSoft, FlatQueuesRigid>::type Queues;
 	const long total = (long)io.n_env * P.nq;
 	bp_prepare_kernel<QTET><<<(unsigned)((total + PREP_BLOCK - 1) / PREP_BLOCK), PREP_BLOCK, 0, s>>>(P, io);
 	const int smem = (int)sizeof(Queues) * BP_WARPS;
-	auto kernel    = bp_traverse_kernel<QTET, SWEEP>;
+	auto kernel    = bp_traverse_kernel<QTET, SWEEP, PRISM>;
 	ensure_dynamic_smem(kernel, smem);
 	// persistent warps; never more than one warp per 8 query elements
 	const int grid = (int)std::max<long>(1, std::min<long>((total + 8 * BP_WARPS - 1) / (8 * BP_WARPS), (long)io.n_sms * FT_CTAS_PER_SM));
@@ -975,9 +983,11 @@ void launch_broadphase(const PairDesc &P, const StepIO &io, cudaStream_t s)
 	const int grid   = (int)std::max<long>(1, std::min<long>((units + BP_WARPS - 1) / BP_WARPS, (long)io.n_sms * BP_CTAS_PER_SM));
 	const bool sweep = P.n_tree <= SWEEP_MAX_TREE;
 	static const bool legacy = getenv("HCS_BP_LEGACY") != nullptr; // the per-unit kernel for the tree kinds (A/B measurements)
-	if (!legacy && P.alive && (P.kind == PAIR_SOFT_RIGID || P.kind == PAIR_SOFT_SOFT)) {
+	const bool per_env = P.A.env_stride > 0 || P.B.env_stride > 0; // per-environment geometry: the flat kernels only
+	if ((!legacy || per_env) && P.alive && (P.kind == PAIR_SOFT_RIGID || P.kind == PAIR_SOFT_SOFT)) {
 		if (P.kind == PAIR_SOFT_RIGID)
-			sweep ? launch_flat_bp<false, true>(P, io, s) : launch_flat_bp<false, false>(P, io, s);
+			sweep ? launch_flat_bp<false, true>(P, io, s) :
+			        (P.n_tree >= PRISM_MIN_TREE ? launch_flat_bp<false, false, true>(P, io, s) : launch_flat_bp<false, false>(P, io, s));
 		else
 			sweep ? launch_flat_bp<true, true>(P, io, s) : launch_flat_bp<true, false>(P, io, s);
 		return;

@@ -114,6 +114,40 @@ __global__ void __launch_bounds__(128) build_tris_kernel(GeomDev g)
 	g.tris[t] = r;
 }
 
+// Per-environment sizes of sphere / ellipsoid geoms (hcs_set_env_sizes): vertices = unit-sphere vertex x semi-axes and the
+// pressure extent field of mesh_host.cpp build_geom_mesh, same expressions in the same order (IEEE sqrt / division, no
+// FMA contraction: bit-identical to the host generator).  One thread per (environment, vertex).
+// vol_offset: 1 for rigid geoms, whose surface mesh is the volume mesh without its centre vertex (vertex 0).
+__global__ void __launch_bounds__(128) sphere_env_verts_kernel(const double *unit, int n_verts, int vol_offset, const double *sizes,
+                                                               int n_env, int is_sphere, double E, double *verts, double *pressure)
+{
+	const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= (long)n_env * n_verts)
+		return;
+	const int env = (int)(i / n_verts), v = (int)(i - (long)env * n_verts);
+	const double a = sizes[3 * env], b = is_sphere ? a : sizes[3 * env + 1], c = is_sphere ? a : sizes[3 * env + 2];
+	const double *u = unit + 3 * (size_t)(v + vol_offset);
+	const D3 p      = mk(u[0] * a, u[1] * b, u[2] * c);
+	verts[3 * (size_t)i] = p.x, verts[3 * (size_t)i + 1] = p.y, verts[3 * (size_t)i + 2] = p.z;
+	if (pressure) {
+		const D3 q       = is_sphere ? p : mk(p.x / a, p.y / b, p.z / c);
+		const double rad = sqrt(dot(q, q));
+		double ext       = is_sphere ? 1.0 - rad / a : 1.0 - rad;
+		if (fabs(ext) < 1e-14)
+			ext = 0.0;
+		pressure[i] = E * ext;
+	}
+}
+
+void launch_sphere_env_verts(const double *unit, int n_verts, int vol_offset, const double *sizes, int n_env, int is_sphere, double E,
+                             double *verts, double *pressure, cudaStream_t s)
+{
+	const long n = (long)n_env * n_verts;
+	if (n > 0)
+		sphere_env_verts_kernel<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(unit, n_verts, vol_offset, sizes, n_env, is_sphere, E, verts,
+		                                                                  pressure);
+}
+
 void launch_build_tets(const GeomDev &g, cudaStream_t s)
 {
 	if (g.n_elems > 0)

@@ -67,6 +67,8 @@ __device__ __forceinline__ int flat_total(const PairDesc &P, const StepIO &io)
 // a function of v alone, so sums of limbs are exact integer sums of deterministic values.
 __device__ __forceinline__ void to_limbs(double v, long long &hi, long long &lo)
 {
+	// (splitting the limbs off with two additions of 1.5 * 2^k constants instead of the 64-bit conversions was measured on
+	// one box, three alternations: narrowphase 0.0438 vs 0.0440 ms on C1 x 4096: no difference, not kept)
 	hi             = __double2ll_rn(v * ACC_HI_SCALE);
 	const double r = fma(-__ll2double_rn(hi), 1.0 / ACC_HI_SCALE, v);
 	lo             = __double2ll_rn(r * ACC_LO_SCALE);

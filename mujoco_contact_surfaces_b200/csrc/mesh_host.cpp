@@ -392,4 +392,21 @@ bool build_geom_mesh(int mj_type, const double size[3], const float *mesh_vert, 
 	return true;
 }
 
+int sphere_like_level(int mj_type, const double size[3], double hint)
+{
+	if (mj_type == GEOM_SPHERE)
+		return sphere_level(size[0], hint);
+	return sphere_level(1.0, hint / std::max(size[0], std::max(size[1], size[2])));
+}
+
+void unit_sphere_vertices(int level, std::vector<double> &verts)
+{
+	Builder b;
+	std::vector<int32_t> boundary;
+	unit_sphere(level, b, boundary);
+	verts.clear();
+	for (const P3 &p : b.v)
+		verts.push_back(p.x), verts.push_back(p.y), verts.push_back(p.z);
+}
+
 } // namespace hcs

@@ -24,4 +24,11 @@ struct HostMesh {
 bool build_geom_mesh(int mj_type, const double size[3], const float *mesh_vert, int n_vert, const int32_t *mesh_face,
                      int n_face, const double props[5], HostMesh &out, std::string &err);
 
+// Sphere / ellipsoid geoms are a unit sphere (single interior vertex, boundary refined `level` times) scaled by the
+// semi-axes; the level follows from the sizes and the resolution hint.  Exposed for per-environment sizes
+// (hcs_set_env_sizes): one unit mesh, every environment's vertices and pressures are generated from it on the GPU.
+int sphere_like_level(int mj_type, const double size[3], double hint);
+// vertices of the unit sphere mesh of that level in generation order (vertex 0 = centre)
+void unit_sphere_vertices(int level, std::vector<double> &verts);
+
 } // namespace hcs

@@ -230,6 +230,13 @@ int hcs_multi_update_geom(hcs_multi *m, int geom, const double size[3])
 	return fan_out(m, [=](Block &b) { return hcs_update_geom(b.ctx, geom, size); });
 }
 
+int hcs_multi_set_env_sizes(hcs_multi *m, int geom, const double *sizes)
+{
+	if (!m)
+		return HCS_E_INVALID;
+	return fan_out(m, [=](Block &b) { return hcs_set_env_sizes(b.ctx, geom, sizes ? sizes + 3 * (size_t)b.start : nullptr); });
+}
+
 int hcs_multi_set_pairs(hcs_multi *m, const int32_t *g1, const int32_t *g2, int n_pairs)
 {
 	if (!m)

@@ -554,8 +554,8 @@ __device__ __forceinline__ int cand_tet_tri(const PairDesc &P, const StepIO &io,
                                             unsigned buf0, unsigned buf_stride, Acc &acc, int &cur, D3 &cen, double &ec, int &nv)
 {
 	const double kInf  = __longlong_as_double(0x7ff0000000000000LL);
-	const TetField *tf = P.A.tet_field + tet;
-	const TriVerts tr  = load_tri(P.B.tris + tri);
+	const TetField *tf = P.A.tet_field + P.A.eoff(ctx.env) + tet;
+	const TriVerts tr  = load_tri(P.B.tris + P.B.eoff(ctx.env) + tri);
 	// the normal/gradient cull and the trivial rejects already ran in the broadphase
 	const Xform X_SR = ctx.X_AB();
 	D3 nS = rot(X_SR.R, tr.n);
@@ -602,8 +602,8 @@ __device__ __forceinline__ int cand_tet_plane(const PairDesc &P, const StepIO &i
 	D3 n_S     = mk(X_SR.R[2], X_SR.R[5], X_SR.R[8]);
 	double pd  = dot(n_S, X_SR.p);
 	D3 nhat_W  = rot(X_WS.R, n_S);
-	const TetVerts tg = load_tet_verts(P.A.tet_geom + t);
-	const D4 te       = load_tet_pressures(P.A.tet_geom + t);
+	const TetVerts tg = load_tet_verts(P.A.tet_geom + P.A.eoff(ctx.env) + t);
+	const D4 te       = load_tet_pressures(P.A.tet_geom + P.A.eoff(ctx.env) + t);
 	double dist[4];
 	int code = 0;
 #pragma unroll
@@ -637,7 +637,7 @@ __device__ __forceinline__ int cand_tet_plane(const PairDesc &P, const StepIO &i
 	}
 	if (nv < 3)
 		return 0;
-	D3 grad_W = rot(X_WS.R, xyz(load_grad_e0(P.A.tet_field + t)));
+	D3 grad_W = rot(X_WS.R, xyz(load_grad_e0(P.A.tet_field + P.A.eoff(ctx.env) + t)));
 	integrate_polygon<TRI, true>(poly, nv, nhat_W, grad_W, e, kInf, ctx, io, t, 0, acc, cen, ec);
 	return nv;
 }
@@ -651,9 +651,10 @@ __device__ __forceinline__ int cand_tet_tet(const PairDesc &P, const StepIO &io,
 	cur        = 0;
 	const Xform X_MN = ctx.X_AB();
 	D3 p_NMo         = ctx.p_BAo();
-	const TetField *f0 = P.A.tet_field + t0, *f1 = P.B.tet_field + t1;
-	prefetch_l1(P.A.tet_geom + t0); // sliced / clipped against further down, behind dependent branches
-	prefetch_l1(P.B.tet_geom + t1);
+	const size_t offA = P.A.eoff(ctx.env), offB = P.B.eoff(ctx.env);
+	const TetField *f0 = P.A.tet_field + offA + t0, *f1 = P.B.tet_field + offB + t1;
+	prefetch_l1(P.A.tet_geom + offA + t0); // sliced / clipped against further down, behind dependent branches
+	prefetch_l1(P.B.tet_geom + offB + t1);
 	prefetch_l1(ctx.g + 32);        // velocities of the force law
 	// CalcEquilibriumPlane
 	const D4 ge0 = load_grad_e0(f0), ge1 = load_grad_e0(f1);
@@ -678,7 +679,7 @@ __device__ __forceinline__ int cand_tet_tet(const PairDesc &P, const StepIO &io,
 	}
 	int n = 0;
 	if (ok) { // SliceTetrahedronWithPlane(tet0)
-		const TetVerts g0 = load_tet_verts(P.A.tet_geom + t0);
+		const TetVerts g0 = load_tet_verts(P.A.tet_geom + offA + t0);
 		double dist[4];
 		int code = 0;
 #pragma unroll
@@ -702,7 +703,7 @@ __device__ __forceinline__ int cand_tet_tet(const PairDesc &P, const StepIO &io,
 		ok = n >= 3;
 	}
 	if (ok) { // clip by the four half spaces of tet1 expressed in M
-		const TetVerts g1 = load_tet_verts(P.B.tet_geom + t1);
+		const TetVerts g1 = load_tet_verts(P.B.tet_geom + offB + t1);
 		D3 pv[4];
 #pragma unroll
 		for (int k = 0; k < 4; ++k)

@@ -51,7 +51,7 @@ ABI_SYMBOLS = [
     "hcs_get_mesh", "hcs_get_lbvh", "hcs_get_counters", "hcs_set_profiling", "hcs_get_stage_ms", "hcs_version",
     "hcs_add_curved_sensor", "hcs_curved_sensor_info", "hcs_get_curved_values", "hcs_device_curved_values",
     "hcs_add_taxel_sensor", "hcs_get_taxel_values", "hcs_device_taxel_values", "hcs_get_face_vertices",
-    "hcs_update_flat_sensor", "hcs_step_async", "hcs_wait", "hcs_get_tactile_triangle_pairs",
+    "hcs_update_flat_sensor", "hcs_step_async", "hcs_wait", "hcs_get_tactile_triangle_pairs", "hcs_set_env_sizes", "hcs_multi_set_env_sizes",
     "hcs_multi_create", "hcs_multi_destroy", "hcs_multi_last_error", "hcs_multi_n_blocks", "hcs_multi_block",
     "hcs_multi_add_geom", "hcs_multi_add_soft_mesh", "hcs_multi_add_rigid_mesh", "hcs_multi_update_geom",
     "hcs_multi_set_pairs", "hcs_multi_add_flat_sensor", "hcs_multi_finalize", "hcs_multi_step", "hcs_multi_step_async",
@@ -96,6 +96,8 @@ def load_library():
         L.hcs_step_async.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         L.hcs_wait.argtypes = [C.c_void_p, C.c_int64]
         L.hcs_step.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+        L.hcs_set_env_sizes.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        L.hcs_multi_set_env_sizes.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         L.hcs_multi_create.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.c_int, C.POINTER(C.c_void_p)]
         L.hcs_multi_destroy.argtypes = [C.c_void_p]
         L.hcs_multi_destroy.restype = None
@@ -191,6 +193,14 @@ class HydroelasticEngine:
     def update_geom(self, geom, size):
         size = _f64(np.resize(np.asarray(size, dtype=np.float64), 3))
         self._check(self.L.hcs_update_geom(self.h, int(geom), _ptr(size, C.c_double)))
+
+    def set_env_sizes(self, geom, sizes):
+        """Per-environment sizes [n_envs][3] of one geom (hcs_set_env_sizes); None: one size for all again."""
+        if sizes is None:
+            self._check(self.L.hcs_set_env_sizes(self.h, int(geom), None))
+            return
+        sizes = _f64(np.asarray(sizes, dtype=np.float64).reshape(self.n_envs, 3))
+        self._check(self.L.hcs_set_env_sizes(self.h, int(geom), sizes.ctypes.data))
 
     def set_pairs(self, pairs):
         pairs = np.asarray(pairs, dtype=np.int32).reshape(-1, 2)

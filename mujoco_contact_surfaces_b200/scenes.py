@@ -28,6 +28,7 @@ class Scene:
         self.name, self.geoms, self.pairs = name, geoms, [tuple(p) for p in pairs]
         self.triangle, self.sensors, self.apply_forces = triangle, list(sensors), apply_forces
         self.pose_fn = None
+        self.env_sizes_fn = None  # optional: (n_envs, seed, env_offset) -> {geom index: sizes[n_envs][3]} (domain randomisation)
         # sizing hints for engine pools that cannot be derived from the geometry alone, per environment
         # (e.g. {"tactile_triangles_per_env": n}); engine_kwargs() scales them to a batch
         self.hints = {}
@@ -41,6 +42,10 @@ class Scene:
     @property
     def n_geoms(self):
         return len(self.geoms)
+
+    def env_sizes(self, n_envs, seed, env_offset=0):
+        """Per-environment geom sizes for hcs_set_env_sizes, or {} when the scene has none."""
+        return self.env_sizes_fn(n_envs, seed, env_offset) if self.env_sizes_fn else {}
 
     def poses(self, n_envs, seed, env_offset=0):
         """xpos[n,ng,3], xmat[n,ng,9], vel[n,ng,6] for envs env_offset .. env_offset+n-1 (per-env RNG streams,
@@ -243,6 +248,21 @@ def objects_on_plane(triangle=False):
     extents = [None, np.full(3, 0.05), np.array([0.06, 0.04, 0.03]), None, None]
     box_corners = np.array([[sx * 0.05, sy * 0.04, sz * 0.03] for sx in (-1, 1) for sy in (-1, 1) for sz in (-1, 1)])
     tip = tip_v.astype(np.float64)
+
+    def env_sizes(n_envs, seed, env_offset=0):
+        """Domain-randomised sizes (sizes drawn per environment): every object scaled by its own
+        factor in [0.92, 1.08] (inside one refinement level of the sphere and the ellipsoid; the box keeps its proportions,
+        hence its medial-axis topology)."""
+        out = {1: np.zeros((n_envs, 3)), 2: np.zeros((n_envs, 3)), 3: np.zeros((n_envs, 3))}
+        for e in range(n_envs):
+            rng = np.random.Generator(np.random.PCG64([seed, 7777, env_offset + e]))
+            f = rng.uniform(0.92, 1.08, size=3)
+            out[1][e] = [0.05 * f[0], 0, 0]
+            out[2][e] = np.array([0.06, 0.04, 0.03]) * f[1]
+            out[3][e] = np.array([0.05, 0.04, 0.03]) * f[2]
+        return out
+
+    sc.env_sizes_fn = env_sizes
 
     def pose(rng, env, xpos, xmat, vel):
         xmat[0] = np.eye(3).reshape(-1)

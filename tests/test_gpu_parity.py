@@ -660,3 +660,106 @@ def test_multi_device_context_equals_one_context(hcs_lib, name, n_envs, n_blocks
     if with_sensors:
         assert img.tobytes() == ref_img.tobytes()
     multi.close()
+
+
+def _resized(scene_fn, sizes_by_geom):
+    sc = scene_fn()
+    for g, s in sizes_by_geom.items():
+        sc.geoms[g].size = np.resize(np.asarray(s, dtype=np.float64), 3)
+    return sc
+
+
+@pytest.mark.gpu
+def test_per_env_sizes_equal_one_engine_per_size(hcs_lib):
+    """hcs_set_env_sizes (domain-randomised sizes per environment; the reference rebuilds one geom of
+    its one mjData in onGeomChanged, plugin.cpp:828-975).  Every environment of a batch has its own sphere radius (vertices
+    and pressures generated on the GPU from the unit mesh) and its own rigid box (host generator per environment); fields,
+    element records and LBVHs are built on the GPU per environment.  Environment e gives, bit for bit, what a one-environment
+    engine configured with e's sizes gives on e's poses, and matches the oracle configured with e's sizes."""
+    n_envs = 10
+    rng = np.random.default_rng(5)
+    radii = rng.uniform(0.07, 0.12, n_envs)     # refinement level 2 for hint 0.05 needs 0.0653 < r <= 0.128
+    halves = rng.uniform(0.08, 0.1, (n_envs, 3))  # 2 x 2 x 2 cells for hint 0.1 needs 0.05 < half size <= 0.1
+    scene = scenes.sphere_on_box()
+    eng = make_engine(scene, n_envs)
+    s_sph = np.zeros((n_envs, 3))
+    s_sph[:, 0] = radii
+    eng.set_env_sizes(1, s_sph)   # after hcs_finalize: the context is rebuilt
+    eng.set_env_sizes(0, halves)
+    xp, xm, ve = scene.poses(n_envs, seed=17)
+    for e in range(n_envs):       # box top at 0.1 + half height, sphere pressed 6 .. 15 mm into it (the level-2 sphere is faceted)
+        xp[e, 1, 2] = xp[e, 0, 2] + halves[e, 2] + radii[e] - 0.001 * (6 + e)
+    eng.step(xp, xm, ve)
+    W, P = eng.geom_wrenches().copy(), eng.pair_results().copy()
+    assert (P["n_polygons"][:, 0] > 0).all()
+    worst = 0.0
+    for e in range(n_envs):
+        one_scene = _resized(scenes.sphere_on_box, {0: halves[e], 1: [radii[e]] * 3})
+        one = make_engine(one_scene, 1)
+        one.step(xp[e:e + 1], xm[e:e + 1], ve[e:e + 1])
+        assert one.geom_wrenches().tobytes() == W[e:e + 1].tobytes(), "env %d" % e
+        got = one.pair_results()
+        for f in ("n_polygons", "n_faces", "n_points", "n_clipped"):
+            assert got[f][0, 0] == P[f][e, 0]
+        one.close()
+        if e < 4:
+            orc = make_oracle(one_scene)
+            ref_pairs, _ = oracle_env(orc, one_scene, xp[e], xm[e], ve[e], sensors=False)
+            worst = max(worst, compare_env(P[e], [eng.emitted(e, 0)], ref_pairs))
+    assert worst < 1e-8
+    # back to one size: the plain configuration again
+    eng.set_env_sizes(1, None)
+    eng.set_env_sizes(0, None)
+    eng.step(*scene.poses(n_envs, seed=17))
+    ref = make_engine(scenes.sphere_on_box(), n_envs)
+    ref.step(*scene.poses(n_envs, seed=17))
+    assert eng.geom_wrenches().tobytes() == ref.geom_wrenches().tobytes()
+    ref.close()
+    # a radius that needs another refinement level is refused, with the environment named
+    s_bad = s_sph.copy()
+    s_bad[3, 0] = 0.03
+    with pytest.raises(Exception, match="environment 3"):
+        eng.set_env_sizes(1, s_bad)
+    eng.close()
+
+
+@pytest.mark.gpu
+def test_per_env_sizes_soft_soft_and_half_space(hcs_lib):
+    """Per-environment ellipsoid semi-axes on both sides of a soft-soft pair (equal-pressure plane, per-environment LBVH on the
+    tree side and per-environment query tets) and per-environment soft geoms on a rigid half space."""
+    n_envs = 6
+    rng = np.random.default_rng(9)
+    f = rng.uniform(0.9, 1.0, (n_envs, 1))  # (ell0 changes its refinement level at 1.02 x, ell1 at 0.85 x)
+    a, b = np.array([0.05, 0.04, 0.03]) * f, np.array([0.04, 0.04, 0.06]) * f[::-1]
+    scene = scenes.soft_soft()
+    eng = make_engine(scene, n_envs)
+    eng.set_env_sizes(0, a)
+    eng.set_env_sizes(1, b)
+    xp, xm, ve = scene.poses(n_envs, seed=23)
+    eng.step(xp, xm, ve)
+    W = eng.geom_wrenches().copy()
+    hit = 0
+    for e in range(n_envs):
+        one = make_engine(_resized(scenes.soft_soft, {0: a[e], 1: b[e]}), 1)
+        one.step(xp[e:e + 1], xm[e:e + 1], ve[e:e + 1])
+        assert one.geom_wrenches().tobytes() == W[e:e + 1].tobytes(), "env %d" % e
+        hit += int(one.pair_results()["n_polygons"][0, 0] > 0)
+        one.close()
+    assert hit > 0
+    eng.close()
+    # half space: spheres of per-environment radius on the plane
+    scene = scenes.objects_on_plane()
+    eng = make_engine(scene, n_envs)
+    radii = rng.uniform(0.045, 0.055, n_envs)
+    s = np.zeros((n_envs, 3))
+    s[:, 0] = radii
+    eng.set_env_sizes(1, s)
+    xp, xm, ve = scene.poses(n_envs, seed=29)
+    eng.step(xp, xm, ve)
+    W = eng.geom_wrenches().copy()
+    for e in range(n_envs):
+        one = make_engine(_resized(scenes.objects_on_plane, {1: [radii[e]] * 3}), 1)
+        one.step(xp[e:e + 1], xm[e:e + 1], ve[e:e + 1])
+        assert one.geom_wrenches().tobytes() == W[e:e + 1].tobytes(), "env %d" % e
+        one.close()
+    eng.close()
