@@ -17,7 +17,7 @@ VARIANT = os.environ.get("HCS_VARIANT", "")
 OUT = os.path.join(HERE, "variants", "libhcs_b200.%s.so" % VARIANT) if VARIANT else os.path.join(HERE, "libhcs_b200.so")
 OBJ = os.path.join(CSRC, "_build" + ("_" + VARIANT if VARIANT else ""))
 
-SOURCES = ["engine.cu", "kernels_build.cu", "kernels_step.cu", "kernels_broadphase.cu", "kernels_tactile.cu", "kernels_lbvh.cu",
+SOURCES = ["engine.cu", "kernels_build.cu", "kernels_step.cu", "kernels_broadphase.cu", "kernels_tactile.cu", "kernels_lbvh.cu", "kernels_meshgen.cu",
            "mesh_host.cpp", "multi.cpp"]
 
 NVCC = os.environ.get("HCS_NVCC", "/usr/local/cuda/bin/nvcc")

@@ -348,6 +348,78 @@ static void centroid_bounds(const double *verts, const int32_t *elems, int ne, d
 	}
 }
 
+// The unit sphere of a refinement level, generated on the GPU (kernels_meshgen.cu); the arrays go into `bag`
+static void device_unit_sphere(hcs_ctx *c, int level, std::vector<void *> &bag, double **d_unit, int32_t **d_tri, int *nv, int *nt)
+{
+	unit_sphere_counts(level, nv, nt);
+	*d_unit = dalloc<double>(bag, (size_t)*nv * 3);
+	*d_tri  = dalloc<int32_t>(bag, (size_t)*nt * 3);
+	void *scratch = nullptr;
+	CK(cudaMalloc(&scratch, unit_sphere_scratch_bytes(level) + sizeof(int32_t)));
+	int32_t *d_bad = reinterpret_cast<int32_t *>(static_cast<char *>(scratch) + unit_sphere_scratch_bytes(level));
+	launch_unit_sphere(level, *d_unit, *d_tri, scratch, d_bad, c->stream);
+	int32_t bad = 0;
+	CK(cudaMemcpyAsync(&bad, d_bad, sizeof bad, cudaMemcpyDeviceToHost, c->stream));
+	CK(cudaStreamSynchronize(c->stream));
+	CK(cudaGetLastError());
+	cudaFree(scratch);
+	if (bad)
+		throw std::runtime_error("GPU sphere refinement: the boundary is not a closed surface");
+}
+
+static bool gpu_meshgen_wanted(const GeomHost &g, int level)
+{
+	return !g.custom && (g.mj_type == HCS_GEOM_SPHERE || g.mj_type == HCS_GEOM_ELLIPSOID) && level <= unit_sphere_max_gpu_level() &&
+	       getenv("HCS_MESHGEN_HOST") == nullptr;
+}
+
+// Sphere and ellipsoid geoms: topology, vertices and pressures generated on the GPU (K0), mirrored into g.mesh for the
+// host-side bookkeeping (bounds, pool sizes, getters).  hcs_add_geom has validated the geom with the host generator and
+// left its mesh in g.mesh: with HCS_MESHGEN_CHECK set the two are compared bit for bit.
+static void gpu_generate_sphere_like(hcs_ctx *c, GeomHost &g)
+{
+	const int level = sphere_like_level(g.mj_type, g.size, g.props[2]);
+	if (!gpu_meshgen_wanted(g, level) || g.mesh.plane)
+		return;
+	std::vector<void *> tmp;
+	try {
+		double *d_unit = nullptr;
+		int32_t *d_tri = nullptr;
+		int nv_vol = 0, nt = 0;
+		device_unit_sphere(c, level, tmp, &d_unit, &d_tri, &nv_vol, &nt);
+		const bool soft      = g.mesh.soft;
+		const int vol_offset = soft ? 0 : 1, nv = nv_vol - vol_offset, per = soft ? 4 : 3;
+		double *d_verts  = dalloc<double>(tmp, (size_t)nv * 3);
+		double *d_press  = soft ? dalloc<double>(tmp, (size_t)nv) : nullptr;
+		int32_t *d_elems = dalloc<int32_t>(tmp, (size_t)nt * per);
+		double *d_size   = dalloc<double>(tmp, 3);
+		CK(cudaMemcpyAsync(d_size, g.size, 3 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+		launch_sphere_env_verts(d_unit, nv, vol_offset, d_size, 1, g.mj_type == HCS_GEOM_SPHERE, g.props[0], d_verts, d_press, c->stream);
+		launch_sphere_elems(d_tri, nt, soft ? 1 : 0, d_elems, c->stream);
+		HostMesh gm;
+		gm.soft = soft;
+		gm.verts.resize((size_t)nv * 3), gm.elems.resize((size_t)nt * per), gm.pressure.resize(soft ? nv : 0);
+		CK(cudaMemcpyAsync(gm.verts.data(), d_verts, gm.verts.size() * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+		CK(cudaMemcpyAsync(gm.elems.data(), d_elems, gm.elems.size() * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+		if (soft)
+			CK(cudaMemcpyAsync(gm.pressure.data(), d_press, gm.pressure.size() * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+		CK(cudaStreamSynchronize(c->stream));
+		CK(cudaGetLastError());
+		if (getenv("HCS_MESHGEN_CHECK")) {
+			auto same = [](const std::vector<double> &a, const std::vector<double> &b) {
+				return a.size() == b.size() && (a.empty() || memcmp(a.data(), b.data(), a.size() * sizeof(double)) == 0);
+			};
+			if (!same(gm.verts, g.mesh.verts) || gm.elems != g.mesh.elems || !same(gm.pressure, g.mesh.pressure))
+				throw std::runtime_error("HCS_MESHGEN_CHECK: the GPU-generated sphere mesh differs from the host generator's");
+		}
+		g.mesh = std::move(gm);
+	} catch (...) {
+		free_bag(tmp);
+		throw;
+	}
+	free_bag(tmp);
+}
+
 // Per-environment sizes (hcs_set_env_sizes): ONE topology (g.mesh, the mesh of environment 0), every
 // environment its own vertices, pressures, element records and LBVH, env-major.  Sphere / ellipsoid vertices and pressures
 // are generated on the GPU from the unit mesh; other shapes come from the host generator, environment by environment.
@@ -378,14 +450,24 @@ static void upload_geom_per_env(hcs_ctx *c, GeomHost &g)
 			if (sphere_like_level(g.mj_type, &g.env_sizes[3 * (size_t)e], g.props[2]) != level)
 				throw std::runtime_error("per-environment sizes: environment " + std::to_string(e) +
 				                         " needs another refinement level than environment 0 (scale the resolution hint with the size)");
-		std::vector<double> unit;
-		unit_sphere_vertices(level, unit);
 		const int vol_offset = m.soft ? 0 : 1; // the rigid surface drops the centre vertex
-		if ((int)unit.size() / 3 != nv + vol_offset)
-			throw std::runtime_error("per-environment sizes: unit sphere and geom mesh disagree");
-		double *d_unit  = dalloc<double>(g.allocs, unit.size());
+		double *d_unit = nullptr;
+		std::vector<double> unit;
+		if (gpu_meshgen_wanted(g, level)) { // unit mesh and element list from the GPU generator (K0)
+			int32_t *d_tri = nullptr;
+			int nv_vol = 0, nt = 0;
+			device_unit_sphere(c, level, g.allocs, &d_unit, &d_tri, &nv_vol, &nt);
+			if (nv_vol != nv + vol_offset || nt != ne)
+				throw std::runtime_error("per-environment sizes: unit sphere and geom mesh disagree");
+			launch_sphere_elems(d_tri, nt, m.soft ? 1 : 0, d.elems, c->stream);
+		} else {
+			unit_sphere_vertices(level, unit);
+			if ((int)unit.size() / 3 != nv + vol_offset)
+				throw std::runtime_error("per-environment sizes: unit sphere and geom mesh disagree");
+			d_unit = dalloc<double>(g.allocs, unit.size());
+			CK(cudaMemcpyAsync(d_unit, unit.data(), unit.size() * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+		}
 		double *d_sizes = dalloc<double>(g.allocs, g.env_sizes.size());
-		CK(cudaMemcpyAsync(d_unit, unit.data(), unit.size() * sizeof(double), cudaMemcpyHostToDevice, c->stream));
 		CK(cudaMemcpyAsync(d_sizes, g.env_sizes.data(), g.env_sizes.size() * sizeof(double), cudaMemcpyHostToDevice, c->stream));
 		launch_sphere_env_verts(d_unit, nv, vol_offset, d_sizes, n_env, g.mj_type == HCS_GEOM_SPHERE, g.props[0], d.verts, d.pressure,
 		                        c->stream);
@@ -484,6 +566,8 @@ static void upload_geom(hcs_ctx *c, GeomHost &g)
 		upload_geom_per_env(c, g);
 		return;
 	}
+	if (!g.custom && (g.mj_type == HCS_GEOM_SPHERE || g.mj_type == HCS_GEOM_ELLIPSOID))
+		gpu_generate_sphere_like(c, g);
 	GeomDev d{};
 	const HostMesh &m = g.mesh;
 	d.kind            = m.plane ? 2 : (m.soft ? 1 : 0);

@@ -312,6 +312,17 @@ void launch_sphere_env_verts(const double *unit, int n_verts, int vol_offset, co
 size_t lbvh_scratch_bytes(int n);
 void launch_build_lbvh(const GeomDev &g, const double glo[3], const double ghi[3], void *scratch, cudaStream_t s);
 
+// K0: the refined-octahedron unit sphere on the GPU (kernels_meshgen.cu), bit-identical to mesh_host.cpp
+int unit_sphere_max_gpu_level();
+void unit_sphere_counts(int level, int *n_verts, int *n_tri);
+size_t unit_sphere_scratch_bytes(int level);
+void launch_unit_sphere(int level, double *verts, int32_t *tri, void *scratch, int32_t *bad_flag, cudaStream_t s);
+void launch_sphere_elems(const int32_t *tri, int n_tri, int soft, int32_t *elems, cudaStream_t s);
+// load-time helpers shared by the builders: in-place bitonic sort of n_pad (power of two) 64-bit keys; exclusive scan of n
+// int32 values (tile_tmp: n / 1024 + 2 ints, total: one int)
+void launch_bitonic_sort_u64(unsigned long long *keys, int n_pad, cudaStream_t s);
+void launch_exclusive_scan_i32(const int32_t *in, int32_t *out, int32_t *tile_tmp, int n, int32_t *total, cudaStream_t s);
+
 void launch_broadphase(const PairDesc &P, const StepIO &io, cudaStream_t s);
 // chained: the kernel directly behind it in the stream is the one whose output it consumes (launch_chained above)
 void launch_narrowphase(const PairDesc &P, const StepIO &io, cudaStream_t s, bool chained);

@@ -177,6 +177,13 @@ size_t lbvh_scratch_bytes(int n)
 	return b + 256;
 }
 
+void launch_bitonic_sort_u64(unsigned long long *keys, int n_pad, cudaStream_t s)
+{
+	for (int k = 2; k <= n_pad; k <<= 1)
+		for (int j = k >> 1; j > 0; j >>= 1)
+			bitonic_step_kernel<<<(n_pad + 255) / 256, 256, 0, s>>>(keys, j, k, n_pad);
+}
+
 void launch_build_lbvh(const GeomDev &g, const double glo[3], const double ghi[3], void *scratch, cudaStream_t s)
 {
 	int n = g.n_elems;
@@ -196,9 +203,7 @@ void launch_build_lbvh(const GeomDev &g, const double glo[3], const double ghi[3
 	cudaMemsetAsync(arrived, 0, sizeof(int) * (size_t)n, s);
 	lbvh_leaf_kernel<<<(n_pad + 127) / 128, 128, 0, s>>>(g, make_double3(glo[0], glo[1], glo[2]),
 	                                                      make_double3(ghi[0], ghi[1], ghi[2]), leaf_box, keys, n_pad);
-	for (int k = 2; k <= n_pad; k <<= 1)
-		for (int j = k >> 1; j > 0; j >>= 1)
-			bitonic_step_kernel<<<(n_pad + 255) / 256, 256, 0, s>>>(keys, j, k, n_pad);
+	launch_bitonic_sort_u64(keys, n_pad, s);
 	lbvh_karras_kernel<<<(n - 1 + 127) / 128, 128, 0, s>>>(keys, n, left, right, parent);
 	lbvh_refit_kernel<<<(n + 127) / 128, 128, 0, s>>>(keys, n, left, right, parent, leaf_box, node_box, arrived, g.nodes);
 }

@@ -167,6 +167,16 @@ __global__ void __launch_bounds__(256) scan_add_kernel(int32_t *out, const int32
 			out[base + k] += off;
 }
 
+void launch_exclusive_scan_i32(const int32_t *in, int32_t *out, int32_t *tile_tmp, int n, int32_t *total, cudaStream_t s)
+{
+	if (n <= 0)
+		return;
+	const int n_tiles = (n + SCAN_TILE - 1) / SCAN_TILE;
+	scan_tiles_kernel<<<n_tiles, 256, 0, s>>>(in, out, tile_tmp, n);
+	scan_sums_kernel<<<1, 1024, 0, s>>>(tile_tmp, n_tiles, total);
+	scan_add_kernel<<<n_tiles, 256, 0, s>>>(out, tile_tmp, n);
+}
+
 constexpr int RASTER_WARPS = 4;
 // taxels a persistent warp takes at a time (HCS_RASTER_GROUP overrides).  Lit taxels come in clusters (the contact patch), so
 // coarse groups leave a tail of heavy ones: tactile stage of C2 box x 1024 envs 0.925 / 0.633 / 0.579 / 0.560 / 0.579 ms for

@@ -1,0 +1,3 @@
+#!/bin/bash
+. scripts/r02_common.sh
+python -m pytest tests -m gpu -x -q 2>&1 | tail -25

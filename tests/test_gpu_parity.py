@@ -763,3 +763,37 @@ def test_per_env_sizes_soft_soft_and_half_space(hcs_lib):
         assert one.geom_wrenches().tobytes() == W[e:e + 1].tobytes(), "env %d" % e
         one.close()
     eng.close()
+
+
+@pytest.mark.gpu
+def test_gpu_sphere_generation_equals_host_generator(hcs_lib, monkeypatch):
+    """K0 (kernels_meshgen.cu): sphere and ellipsoid meshes are generated on the GPU - topology by sorting the edge slots of
+    every refinement level into first-use order, vertices, pressures - and must equal the host generator's mesh bit for
+    bit (HCS_MESHGEN_CHECK makes hcs_finalize compare them).  Levels 0 .. 7 (131 072 tets, the pads of config 5), soft and
+    rigid, sphere and ellipsoid; the device mesh is also the one the oracle builds (vertex order included)."""
+    from mujoco_contact_surfaces_b200 import HydroelasticEngine, GEOM_ELLIPSOID, GEOM_SPHERE
+    from oracle.oracle import OracleScene
+    monkeypatch.setenv("HCS_MESHGEN_CHECK", "1")
+    eng = HydroelasticEngine(1)
+    orc = OracleScene(False, True)
+    cases = []
+    for level, hint in ((0, 0.2), (1, 0.08), (2, 0.05), (3, 0.02), (5, 0.005)):
+        cases.append((GEOM_SPHERE, [0.08, 0, 0], [5e4, 5.0, hint, 0.3, 0.3]))   # soft spheres
+    cases.append((GEOM_SPHERE, [0.05, 0, 0], [0, 1.0, 0.02, 0.5, 0.5]))         # rigid sphere
+    cases.append((GEOM_ELLIPSOID, [0.05, 0.04, 0.03], [5e4, 5.0, 0.01, 0.3, 0.3]))
+    cases.append((GEOM_ELLIPSOID, [0.05, 0.03, 0.04], [0, 1.0, 0.02, 0.5, 0.5]))  # rigid ellipsoid
+    cases.append((GEOM_ELLIPSOID, [0.010, 0.010, 0.012], [1e5, 2.0, 0.00025, 0.6, 0.6]))  # a fingertip pad of config 5: level 7
+    for t, size, props in cases:
+        eng.add_geom(t, size, props)
+        orc.add_geom(t, size, props)
+    eng.set_pairs([(0, 5)])
+    eng.finalize()  # raises if any GPU-generated mesh differs from the host generator's
+    counts = []
+    for g in range(len(cases)):
+        m, o = eng.geom_mesh(g), orc.geom_mesh(g)
+        for key in o:
+            if key != "kind":
+                assert np.array_equal(m[key], o[key]), "geom %d: %s differs" % (g, key)
+        counts.append(len(m["elems"]))
+    assert counts[0] == 8 and counts[2] == 128 and counts[-1] == 131072
+    eng.close()
