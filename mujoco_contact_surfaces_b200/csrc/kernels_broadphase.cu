@@ -336,6 +336,10 @@ __device__ __forceinline__ void flush_stage(const PairDesc &P, const StepIO &io,
 // KIND: 0 triangles of B against the tet tree of A, 1 tets of B against it, 2 the tets of A against a half space.
 // Persistent warps: the resident CTAs of every SM pull (env, slice) units from a work counter, so the grid is never a
 // fractional number of waves and a slow unit does not hold three finished warps' resources.
+// KIND 2 (half space) stays on this kernel.  A flat one-thread-per-(env, tet) classification was measured in round 2 and
+// dropped: every thread repeats the pose algebra a unit does once per 32 .. 512 tets (ncu, config 4 x 4096 envs: 17.1 M
+// instead of 6.3 M warp instructions for the 512-tet ellipsoid, 68 vs 43 us; all four pairs 137 vs 104 us), with one
+// append per warp or per CTA alike (profiles/r02_c4_launches*.csv).
 template <int KIND, bool SWEEP>
 __global__ void __launch_bounds__(BP_BLOCK, BP_CTAS_PER_SM) broadphase_kernel(PairDesc P, StepIO io)
 {

@@ -206,17 +206,20 @@ __device__ __forceinline__ double from_limbs(long long hi, long long lo)
 	return __ll2double_rn(hi) * (1.0 / ACC_HI_SCALE) + __ll2double_rn(lo) * (1.0 / ACC_LO_SCALE);
 }
 
-constexpr int FIN_BLOCK = 128;
-__global__ void __launch_bounds__(FIN_BLOCK) finalize_kernel(const PairDesc *pairs, StepIO io, int use_smem)
+// One thread per environment walks its pairs: the better variant for scenes with one or two pairs (config 1: 10.4 us of
+// stage time against 12.0 for the (env, pair)-parallel kernel below, which wins from three pairs on: config 4 24.6 -> 16.5 us,
+// config 5 27 -> 13 us).
+constexpr int FIN1_BLOCK = 128;
+__global__ void __launch_bounds__(FIN1_BLOCK) finalize_env_kernel(const PairDesc *pairs, StepIO io, int use_smem)
 {
-	extern __shared__ double fin_smem[]; // [n_geoms * 6][FIN_BLOCK] wrench accumulators (scenes with many geoms: below)
+	extern __shared__ double fin_smem[]; // [n_geoms * 6][FIN1_BLOCK] wrench accumulators (scenes with many geoms: below)
 	pdl_wait(); // chained behind the last narrowphase kernel (no-op otherwise)
-	const int env = blockIdx.x * FIN_BLOCK + threadIdx.x;
+	const int env = blockIdx.x * FIN1_BLOCK + threadIdx.x;
 	if (env < io.n_env) {
 		double *w = fin_smem + threadIdx.x;
 		if (use_smem)
 			for (int k = 0; k < io.n_geoms * 6; ++k)
-				w[k * FIN_BLOCK] = 0.0;
+				w[k * FIN1_BLOCK] = 0.0;
 		for (int p = 0; p < io.n_pairs; ++p) {
 			const PairDesc &P = pairs[p];
 			hcs_pair_result r;
@@ -255,8 +258,8 @@ __global__ void __launch_bounds__(FIN_BLOCK) finalize_kernel(const PairDesc *pai
 				r.n_candidates = (int)wds[ACC_NEVALS];
 				if (use_smem)
 					for (int k = 0; k < 3; ++k) {
-						w[(6 * r.gM + k) * FIN_BLOCK] += r.F[k], w[(6 * r.gM + 3 + k) * FIN_BLOCK] += r.tau[k];
-						w[(6 * r.gN + k) * FIN_BLOCK] -= r.F[k], w[(6 * r.gN + 3 + k) * FIN_BLOCK] -= r.tau[k];
+						w[(6 * r.gM + k) * FIN1_BLOCK] += r.F[k], w[(6 * r.gM + 3 + k) * FIN1_BLOCK] += r.tau[k];
+						w[(6 * r.gN + k) * FIN1_BLOCK] -= r.F[k], w[(6 * r.gN + 3 + k) * FIN1_BLOCK] -= r.tau[k];
 					}
 			}
 			io.pair_out[(size_t)env * io.n_pairs + p] = r;
@@ -288,14 +291,102 @@ __global__ void __launch_bounds__(FIN_BLOCK) finalize_kernel(const PairDesc *pai
 		// the block's wrenches are contiguous in the output: written by consecutive threads (the end-to-end path writes the
 		// caller's copy straight into mapped pinned memory: coalesced posted writes instead of 8-byte ones)
 		__syncthreads();
-		const int env0 = blockIdx.x * FIN_BLOCK, n_here = min(FIN_BLOCK, io.n_env - env0), per = io.n_geoms * 6;
-		for (int i = threadIdx.x; i < n_here * per; i += FIN_BLOCK) {
+		const int env0 = blockIdx.x * FIN1_BLOCK, n_here = min(FIN1_BLOCK, io.n_env - env0), per = io.n_geoms * 6;
+		for (int i = threadIdx.x; i < n_here * per; i += FIN1_BLOCK) {
 			const int e = i / per, k = i - e * per;
-			const double v = fin_smem[k * FIN_BLOCK + e];
+			const double v = fin_smem[k * FIN1_BLOCK + e];
 			io.geom_wrench[(size_t)env0 * per + i] = v;
 			if (io.geom_wrench_host)
 				io.geom_wrench_host[(size_t)env0 * per + i] = v;
 		}
+	}
+	// The finalize kernel is the last kernel of a step without sensors: one thread mirrors the error flags into the
+	// caller's mapped pinned memory, so that the end-to-end path needs no copy after the kernels (every kernel that can
+	// raise a flag has finished: stream order).
+	if (io.flags_host && blockIdx.x == 0 && threadIdx.x == 0)
+		for (int k = 0; k < 4; ++k)
+			io.flags_host[k] = io.flags[k];
+}
+
+// One work item per (environment, pair): read (and clear) the pair's exact accumulators, write hcs_pair_result; then one
+// item per (environment, geom): the geom's wrench = its pairs' results in pair order.  A block covers whole environments
+// (FIN_BLOCK / n_pairs of them, at least one), so the second phase finds the first phase's results in shared memory.
+// Round 1/early round 2 ran ONE thread per environment through all its pairs (ncu: 9.5 us for the 4096 environments of
+// config 1 on 32 CTAs, 24.8 us for config 4 with four pairs: a chain of dependent loads per pair).
+constexpr int FIN_BLOCK = 64;
+__global__ void __launch_bounds__(FIN_BLOCK) finalize_kernel(const PairDesc *pairs, StepIO io, int envs_per_block)
+{
+	extern __shared__ double fin_smem[]; // [envs_per_block][n_pairs][6]: F, tau of every (env, pair) of the block
+	pdl_wait(); // chained behind the last narrowphase kernel (no-op otherwise)
+	const int env0 = blockIdx.x * envs_per_block, n_here = min(envs_per_block, io.n_env - env0);
+	const int np = io.n_pairs, ng = io.n_geoms;
+	for (int it = threadIdx.x; it < n_here * np; it += FIN_BLOCK) {
+		const int el = it / np, p = it - el * np, env = env0 + el;
+		const PairDesc &P = pairs[p];
+		hcs_pair_result r;
+		for (int k = 0; k < 3; ++k)
+			r.F[k] = r.tau[k] = r.centroid[k] = 0;
+		r.area = 0;
+		r.gM = P.gM, r.gN = P.gN;
+		r.n_polygons = r.n_faces = r.n_points = r.n_candidates = r.n_clipped = r.reserved = 0;
+		if (P.kind != PAIR_NONE) {
+			long long *a = reinterpret_cast<long long *>(P.accum) + (size_t)env * ACC_WORDS;
+			long long wds[ACC_WORDS];
+			const longlong2 *a2 = reinterpret_cast<const longlong2 *>(a); // 192-byte records: 16-byte aligned
+#pragma unroll
+			for (int k = 0; k < ACC_WORDS / 2; ++k) {
+				const longlong2 q = a2[k];
+				wds[2 * k] = q.x, wds[2 * k + 1] = q.y;
+			}
+#pragma unroll
+			for (int k = 0; k < ACC_WORDS / 2; ++k)
+				reinterpret_cast<longlong2 *>(a)[k] = make_longlong2(0, 0); // zero between steps
+			double d[10];
+#pragma unroll
+			for (int k = 0; k < 10; ++k)
+				d[k] = from_limbs(wds[2 * k], wds[2 * k + 1]) * P.acc_unscale;
+			for (int k = 0; k < 3; ++k) {
+				r.F[k]        = P.sign * d[k];
+				r.tau[k]      = P.sign * d[3 + k];
+				r.centroid[k] = d[6] > 0 ? d[7 + k] / d[6] : 0.0;
+			}
+			r.area = d[6];
+			const unsigned long long cnt = (unsigned long long)wds[ACC_COUNTS];
+			r.n_faces      = (int)(cnt & ((1ull << ACC_POLY_SHIFT) - 1));
+			r.n_polygons   = (int)((cnt >> ACC_POLY_SHIFT) & ((1ull << (ACC_POINT_SHIFT - ACC_POLY_SHIFT)) - 1));
+			r.n_points     = (int)(cnt >> ACC_POINT_SHIFT);
+			r.n_clipped    = (int)wds[ACC_NCLIPPED];
+			r.n_candidates = (int)wds[ACC_NEVALS];
+		}
+		double *w = fin_smem + (size_t)it * 6;
+		for (int k = 0; k < 3; ++k)
+			w[k] = r.F[k], w[3 + k] = r.tau[k];
+		io.pair_out[(size_t)env * np + p] = r;
+	}
+	__syncthreads();
+	// per-geom wrenches: the geom's pairs in pair order (+ as M, - as N); the block's wrenches are contiguous in the output
+	// (the end-to-end path writes the caller's copy straight into mapped pinned memory)
+	for (int it = threadIdx.x; it < n_here * ng; it += FIN_BLOCK) {
+		const int el = it / ng, g = it - el * ng;
+		double wg[6] = { 0, 0, 0, 0, 0, 0 };
+		for (int p = 0; p < np; ++p) {
+			const PairDesc &P = pairs[p];
+			if (P.kind == PAIR_NONE)
+				continue;
+			const double *w = fin_smem + ((size_t)el * np + p) * 6;
+			if (P.gM == g)
+				for (int k = 0; k < 6; ++k)
+					wg[k] += w[k];
+			if (P.gN == g)
+				for (int k = 0; k < 6; ++k)
+					wg[k] -= w[k];
+		}
+		const size_t o = ((size_t)(env0 + el) * ng + g) * 6;
+		for (int k = 0; k < 6; ++k)
+			io.geom_wrench[o + k] = wg[k];
+		if (io.geom_wrench_host)
+			for (int k = 0; k < 6; ++k)
+				io.geom_wrench_host[o + k] = wg[k];
 	}
 	// The finalize kernel is the last kernel of a step without sensors: one thread mirrors the error flags into the
 	// caller's mapped pinned memory, so that the end-to-end path needs no copy after the kernels (every kernel that can
@@ -360,16 +451,29 @@ int launch_finalize(const PairDesc *d_pairs, const StepIO &io, cudaStream_t s, b
 {
 	if (io.n_env <= 0)
 		return 0;
-	const int grid = (io.n_env + FIN_BLOCK - 1) / FIN_BLOCK;
-	size_t smem    = (size_t)FIN_BLOCK * io.n_geoms * 6 * sizeof(double);
-	const int use_smem = smem <= 96 * 1024;
-	if (!use_smem)
-		smem = 0;
+	const int np = std::max(io.n_pairs, 1);
+	if (np <= 2) { // one thread per environment
+		const int grid1 = (io.n_env + FIN1_BLOCK - 1) / FIN1_BLOCK;
+		size_t smem1    = (size_t)FIN1_BLOCK * io.n_geoms * 6 * sizeof(double);
+		const int use_smem = smem1 <= 96 * 1024;
+		if (!use_smem)
+			smem1 = 0;
+		ensure_dynamic_smem(finalize_env_kernel, (int)std::max<size_t>(smem1, 1024));
+		if (chained)
+			launch_chained(finalize_env_kernel, dim3(grid1), dim3(FIN1_BLOCK), smem1, s, d_pairs, io, use_smem);
+		else
+			finalize_env_kernel<<<grid1, FIN1_BLOCK, smem1, s>>>(d_pairs, io, use_smem);
+		return 1;
+	}
+	// whole environments per block; the block's (env, pair) wrenches live in shared memory (<= 48 KB: up to 1024 pairs)
+	const int envs_per_block = std::max(1, FIN_BLOCK / np);
+	const int grid           = (io.n_env + envs_per_block - 1) / envs_per_block;
+	const size_t smem        = (size_t)envs_per_block * np * 6 * sizeof(double);
 	ensure_dynamic_smem(finalize_kernel, (int)std::max<size_t>(smem, 1024));
 	if (chained)
-		launch_chained(finalize_kernel, dim3(grid), dim3(FIN_BLOCK), smem, s, d_pairs, io, use_smem);
+		launch_chained(finalize_kernel, dim3(grid), dim3(FIN_BLOCK), smem, s, d_pairs, io, envs_per_block);
 	else
-		finalize_kernel<<<grid, FIN_BLOCK, smem, s>>>(d_pairs, io, use_smem);
+		finalize_kernel<<<grid, FIN_BLOCK, smem, s>>>(d_pairs, io, envs_per_block);
 	return 1;
 }
 
