@@ -631,6 +631,10 @@ __global__ void __launch_bounds__(BP_BLOCK, BP_CTAS_PER_SM) broadphase_kernel(Pa
 //   bp_prepare_kernel   one thread per (env, query element): relative pose, query into A's frame, root-box test; the
 //                       alive ones leave as 128-byte float records (box, plane, vertices, margin, ids) in the pair's alive
 //                       list (ballot + one atomicAdd per warp).  All the fp64 work of the broadphase is here.
+//   (Also measured in round 2 and dropped, profiles/r02_per_lane_walk_ab.log: one alive query per LANE, each lane walking the
+//   tree with a stack of its own in local memory, the warp alternating between a node phase and a leaf phase by majority:
+//   no queue bookkeeping, but a query's frontier is no longer spread over the lanes.  C1 x 4096 broadphase 0.127 ms against
+//   0.046, C3 0.74 against 0.60 ms, C5 x 1024 140 against 18 ms: there a few large triangles meet 131 072-tet trees.)
 //   bp_traverse_kernel  persistent warps pull batches of 8 - 16 alive records, whatever their environments, and walk the
 //                       tree with the two shared queues as before: float only, all slots alive, more warps per SM.
 // =====================================================================================================
