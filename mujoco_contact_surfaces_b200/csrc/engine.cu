@@ -637,6 +637,30 @@ static void upload_geom(hcs_ctx *c, GeomHost &g)
 				d.root_lo[a] = std::min(root.llo[a], root.rlo[a]);
 				d.root_hi[a] = std::max(root.lhi[a], root.rhi[a]);
 			}
+			if (d.n_elems >= SPLIT_MIN_TREE) { // subtree roots at depth SPLIT_DEPTH for the flat traversal
+				std::vector<BvhNode> nodes((size_t)d.n_elems - 1);
+				CK(cudaMemcpyAsync(nodes.data(), d.nodes, nodes.size() * sizeof(BvhNode), cudaMemcpyDeviceToHost, c->stream));
+				CK(cudaStreamSynchronize(c->stream));
+				std::vector<int32_t> level{ 0 }, split;
+				for (int depth = 0; depth < SPLIT_DEPTH; ++depth) {
+					std::vector<int32_t> next;
+					for (int32_t n : level) {
+						for (int32_t ch : { nodes[n].left, nodes[n].right }) {
+							if (ch < 0)
+								split.push_back(ch); // a leaf above the split depth is a subtree of its own
+							else
+								next.push_back(ch);
+						}
+					}
+					level.swap(next);
+				}
+				split.insert(split.end(), level.begin(), level.end());
+				int32_t *d_split = dalloc<int32_t>(g.allocs, split.size());
+				CK(cudaMemcpyAsync(d_split, split.data(), split.size() * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+				CK(cudaStreamSynchronize(c->stream)); // `split` is a local
+				d.split_nodes = d_split;
+				d.n_split     = (int)split.size();
+			}
 			launch_build_tets(d, c->stream);
 		} else {
 			d.tris = dalloc<TriRec>(g.allocs, d.n_elems);

@@ -74,12 +74,17 @@ struct GeomDev {
 	// root_lo, root_hi of each environment (the members above then describe environment 0).
 	int env_stride, env_stride_nodes, env_stride_verts;
 	const double *env_bounds;
+	// Large trees: the nodes at depth SPLIT_DEPTH (and the leaves above it), so that the flat traversal can hand the K
+	// subtrees of one query to different warps (kernels_broadphase.cu); NULL for small trees and per-environment geometry
+	const int32_t *split_nodes; // >= 0 internal node, < 0 leaf ~tet
+	int n_split;
 #ifdef __CUDACC__
 	__host__ __device__ __forceinline__ size_t eoff(int env) const { return (size_t)env * (size_t)env_stride; }
 	__host__ __device__ __forceinline__ size_t noff(int env) const { return (size_t)env * (size_t)env_stride_nodes; }
 #endif
 };
 constexpr int ENV_BOUNDS = 10;
+constexpr int SPLIT_DEPTH = 6, SPLIT_MIN_TREE = 4096; // subtree split of the flat traversal: 64 subtrees for trees of >= 4096 tets
 
 enum PairKind { PAIR_NONE = 0, PAIR_SOFT_RIGID = 1, PAIR_SOFT_PLANE = 2, PAIR_SOFT_SOFT = 3 };
 

@@ -641,9 +641,10 @@ __global__ void __launch_bounds__(BP_BLOCK, BP_CTAS_PER_SM) broadphase_kernel(Pa
 constexpr int AR_BOX = 0, AR_PL = 6, AR_VF = 10, AR_M = 22, AR_QX = 23, AR_QID = 27, AR_ENV = 28;
 static_assert(ALIVE_WORDS == 32, "alive records are eight float4");
 #ifndef HCS_FT_CTAS_PER_SM
-#define HCS_FT_CTAS_PER_SM 6
+#define HCS_FT_CTAS_PER_SM 5
 #endif
-constexpr int FT_CTAS_PER_SM = HCS_FT_CTAS_PER_SM;
+constexpr int FT_CTAS_PER_SM = HCS_FT_CTAS_PER_SM; // 5 (96-register cap): C1 bp 0.0441 vs 0.0460 ms at 6, C5 equal, C3 +2 %
+constexpr int PRISM_MIN_TREE = 4096;               // trees from this size on: prism test in the leaf filter, one query per batch
 constexpr int PREP_BLOCK = 128;
 
 template <bool QTET>
@@ -774,7 +775,6 @@ __device__ __forceinline__ void flush_flat(const PairDesc &P, const StepIO &io, 
 // triangle's edges along its normal.  Measured (scripts/r02_run8.sh): C5 x 1024 (131 072-tet pads) broadphase 15.4 -> 17.8 ms,
 // narrowphase 19.9 -> 15.0 ms (93.3 k -> 66.5 k candidates per env reach the clipper): step 42.5 -> 38.1 ms; C1 x 4096
 // (128 tets) +3.3 / -4.1 us: a wash, left off there.
-constexpr int PRISM_MIN_TREE = 4096;
 template <bool QTET, bool SWEEP, bool PRISM>
 __global__ void __launch_bounds__(BP_BLOCK, FT_CTAS_PER_SM) bp_traverse_kernel(PairDesc P, StepIO io, int fixed_slots)
 {
@@ -790,24 +790,44 @@ __global__ void __launch_bounds__(BP_BLOCK, FT_CTAS_PER_SM) bp_traverse_kernel(P
 	if (n_alive > P.alive_cap)
 		n_alive = P.alive_cap; // (the prepare kernel raised the flag)
 	// batch size: 16 alive queries per warp, 8 when that would leave resident warps of the grid without a batch.
-	// Measured (scripts/r02_run3.sh, broadphase stage): C1 x 4096 46.4 / 44.6 / 55.4 us, C3 x 4096 0.670 / 0.576 / 0.563 ms,
-	// C5 x 1024 - / 15.5 / 20.2 ms for 8 / 16 / 32: full batches fill the lanes of an iteration but leave fewer warps.
+	// Measured (scripts/r02_run3.sh, broadphase stage): C1 x 4096 46.4 / 44.6 / 55.4 us, C3 x 4096 0.670 / 0.576 / 0.563 ms
+	// for 8 / 16 / 32: full batches fill the lanes of an iteration but leave fewer warps.  Large trees (the 131 072-tet pads
+	// of config 5) are the other regime: one query alone keeps thousands of items in flight, so its frontier fills the lanes,
+	// and a batch of several such queries is a long serial tail for the warp that draws it: C5 x 1024 broadphase stage
+	// 10.1 / 11.3 / 14.0 / 15.5 / 18.1 ms for 1 / 2 / 4 / 8 / 16 queries per batch (scripts/r02_run17.sh).
+	// Subtree split (large trees that have a split table, GeomDev::split_nodes): a work item is (alive query, one of K
+	// subtrees at depth SPLIT_DEPTH), the walk starts at that subtree's root.  One query of config 5 meets thousands of
+	// tets: K items of 1 / K the size balance the warps (and give a SINGLE environment K times the parallelism).
 	const int total_warps = (int)gridDim.x * BP_WARPS;
-	int slots             = n_alive < 8 * total_warps ? 8 : 16;
+	const int K           = (!SWEEP && P.A.split_nodes && P.A.env_stride == 0) ? P.A.n_split : 1;
+	const long n_items    = (long)n_alive * K;
+	int slots             = P.n_tree >= PRISM_MIN_TREE ? 1 : (n_alive < 8 * total_warps ? 8 : 16);
+	if (K > 1) { // C5 x 1024 broadphase stage 10.8 / 9.5 / 8.7 / 9.1 ms for 4 / 8 / 16 / 32 items per batch (10.1 unsplit);
+		         // small batches (one environment: 3840 items) get smaller batches so that every resident warp has one
+		slots = 16;
+		while (slots > 1 && n_items / slots < 2L * total_warps)
+			slots >>= 1;
+	}
 	if (fixed_slots > 0) // tuning override (HCS_FT_SLOTS)
 		slots = fixed_slots;
-	const int n_batches = (n_alive + slots - 1) / slots;
+	const long n_batches = (n_items + slots - 1) / slots;
 
 	for (;;) {
 		int batch = 0;
 		if (lane == 0)
 			batch = atomicAdd(P.counters + 2, 1);
 		batch = __shfl_sync(FULL_MASK, batch, 0);
-		if (batch >= n_batches)
+		if ((long)batch >= n_batches)
 			break;
-		const int first = batch * slots, n_slots = min(slots, n_alive - first);
+		const long first  = (long)batch * slots;
+		const int n_slots = (int)min((long)slots, n_items - first);
+		int start         = 0; // where the slot's walk starts: the root, or the root of its subtree (< 0: a single leaf ~start)
 		if (lane < n_slots) {
-			const float4 *src = reinterpret_cast<const float4 *>(P.alive) + (size_t)(first + lane) * (ALIVE_WORDS / 4);
+			const long item = first + lane;
+			const long qi   = item / K;
+			if (K > 1)
+				start = P.A.split_nodes[(int)(item - qi * K)];
+			const float4 *src = reinterpret_cast<const float4 *>(P.alive) + (size_t)qi * (ALIVE_WORDS / 4);
 			float rec[ALIVE_WORDS];
 #pragma unroll
 			for (int k = 0; k < ALIVE_WORDS / 4; ++k) {
@@ -833,12 +853,19 @@ __global__ void __launch_bounds__(BP_BLOCK, FT_CTAS_PER_SM) bp_traverse_kernel(P
 			W.qid[lane]  = __float_as_int(rec[AR_QID]);
 			W.qenv[lane] = __float_as_int(rec[AR_ENV]);
 			W.qev[lane]  = 0;
-			if (!SWEEP)
-				W.nodeq[lane] = (unsigned)lane << ITEM_SHIFT; // (slot, root)
+		}
+		// start items: internal nodes go to the node queue, subtrees that are a single leaf to the leaf queue
+		int n_stage = 0, n_leaf = 0, n_node = 0;
+		if (!SWEEP) {
+			const bool s_node = lane < n_slots && start >= 0, s_leaf = lane < n_slots && start < 0;
+			const unsigned m_n = __ballot_sync(FULL_MASK, s_node), m_l = __ballot_sync(FULL_MASK, s_leaf);
+			if (s_node)
+				W.nodeq[__popc(m_n & lt_mask)] = ((unsigned)lane << ITEM_SHIFT) | (unsigned)start;
+			if (s_leaf)
+				W.leafq[__popc(m_l & lt_mask)] = ((unsigned)lane << ITEM_SHIFT) | (unsigned)~start;
+			n_node = __popc(m_n), n_leaf = __popc(m_l);
 		}
 		__syncwarp();
-		int n_stage = 0, n_leaf = 0;
-		int n_node  = SWEEP ? 0 : n_slots;
 		int sw_s = 0, sw_t = 0; // sweep position: slot, first tet of the next pass
 		const int sw_slots = SWEEP ? n_slots : 0;
 

@@ -1,5 +1,5 @@
-// Device code shared by the narrowphase kernels (kernels_step.cu: flat over the batch's candidate lists) and the fused
-// per-unit pipeline (kernels_fused.cu): polygon tiles in shared memory, Sutherland-Hodgman clip, duplicate removal,
+// Device code of the narrowphase kernels (kernels_step.cu: flat over the batch's candidate lists): polygon tiles in
+// shared memory, Sutherland-Hodgman clip, duplicate removal,
 // polygon quadrature + force law (mujoco_contact_surfaces_plugin.cpp:320-483), tactile triangle emission.
 // Restates Drake mesh_intersection.cc / mesh_plane_intersection.cc / field_intersection.cc.
 #pragma once
