@@ -306,8 +306,10 @@ int hcs_multi_add_flat_sensor(hcs_multi *m, int geom, double resolution, int sam
 int hcs_multi_finalize(hcs_multi *m);
 /* HOST arrays of the whole batch, as hcs_step; returns when every block has finished (first error wins) */
 int hcs_multi_step(hcs_multi *m, const double *xpos, const double *xmat, const double *vel, int with_sensors);
-/* the same through every block's pipelined entry point (hcs_step_async): returns once all blocks have QUEUED their
- * slice; out members are env-major arrays of the whole batch; hcs_multi_wait(ticket) as hcs_wait */
+/* the same through every block's pipelined entry point (hcs_step_async): only hands the step to the blocks' host threads
+ * and returns (they queue their slices on their own time; errors surface in hcs_multi_wait); out members are env-major
+ * arrays of the whole batch; the input arrays must stay untouched until hcs_multi_wait(ticket); at most two steps may be
+ * un-waited */
 int hcs_multi_step_async(hcs_multi *m, const double *xpos, const double *xmat, const double *vel, int with_sensors,
                          const hcs_outputs *out, int64_t *ticket);
 int hcs_multi_wait(hcs_multi *m, int64_t ticket);

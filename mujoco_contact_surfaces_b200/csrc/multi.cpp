@@ -7,6 +7,7 @@
 // on every block; a step gives every block its slice of the caller's env-major arrays.  No collective: environments
 // exchange nothing.  Host code only (the blocks are driven through the C ABI), so it carries no device code of its own.
 #include <condition_variable>
+#include <deque>
 #include <functional>
 #include <mutex>
 #include <string>
@@ -17,7 +18,8 @@
 
 namespace {
 
-// one worker per block: runs the jobs it is handed, in order
+// one worker per block: runs the jobs it is handed, in order.  post() never blocks; wait() returns when everything posted so
+// far has run, with the first negative return code since the last wait() (0 if none).
 class Worker {
 public:
 	Worker() : th_([this] { loop(); }) {}
@@ -34,17 +36,19 @@ public:
 	{
 		{
 			std::lock_guard<std::mutex> l(mu_);
-			job_    = std::move(job);
-			has_    = true;
-			done_   = false;
+			jobs_.push_back(std::move(job));
+			++posted_;
 		}
 		cv_.notify_all();
 	}
 	int wait()
 	{
 		std::unique_lock<std::mutex> l(mu_);
-		cv_.wait(l, [this] { return done_; });
-		return rc_;
+		const long target = posted_;
+		cv_.wait(l, [this, target] { return done_ >= target; });
+		const int rc = first_error_ < 0 ? first_error_ : last_rc_;
+		first_error_ = 0;
+		return rc;
 	}
 
 private:
@@ -54,26 +58,29 @@ private:
 			std::function<int()> job;
 			{
 				std::unique_lock<std::mutex> l(mu_);
-				cv_.wait(l, [this] { return has_ || quit_; });
-				if (quit_ && !has_)
+				cv_.wait(l, [this] { return !jobs_.empty() || quit_; });
+				if (jobs_.empty())
 					return;
-				job  = std::move(job_);
-				has_ = false;
+				job = std::move(jobs_.front());
+				jobs_.pop_front();
 			}
-			int rc = job();
+			const int rc = job();
 			{
 				std::lock_guard<std::mutex> l(mu_);
-				rc_   = rc;
-				done_ = true;
+				last_rc_ = rc;
+				if (rc < 0 && first_error_ == 0)
+					first_error_ = rc;
+				++done_;
 			}
 			cv_.notify_all();
 		}
 	}
 	std::mutex mu_;
 	std::condition_variable cv_;
-	std::function<int()> job_;
-	bool has_ = false, done_ = true, quit_ = false;
-	int rc_ = 0;
+	std::deque<std::function<int()>> jobs_;
+	long posted_ = 0, done_ = 0;
+	bool quit_   = false;
+	int last_rc_ = 0, first_error_ = 0;
 	std::thread th_; // last member: the thread starts when everything above exists
 };
 
@@ -285,26 +292,39 @@ int hcs_multi_step_async(hcs_multi *m, const double *xpos, const double *xmat, c
 {
 	if (!m || !xpos || !xmat || !vel || !ticket)
 		return HCS_E_INVALID;
+	// The call only hands the step to the blocks' workers and returns: every worker queues its slice through the block's
+	// pipelined entry point on its own time, so the caller's thread costs a few microseconds per step however many GPUs
+	// there are (waiting for all enqueues cost 0.116 ms per step on 8 GPUs against 0.091 ms of GPU time).  Errors of the
+	// enqueue are reported by hcs_multi_wait.  The caller's arrays must stay untouched until hcs_multi_wait(ticket).
 	const size_t n_img = m->sensor_dims.size();
-	int rc = fan_out(m, [=](Block &b) {
-		const size_t ng = (size_t)hcs_n_geoms(b.ctx), np = (size_t)hcs_n_pairs(b.ctx), o = (size_t)b.start * ng;
-		hcs_outputs mine{};
-		if (out) {
-			mine.geom_wrench  = out->geom_wrench ? out->geom_wrench + o * 6 : nullptr;
-			mine.pair_results = out->pair_results ? out->pair_results + (size_t)b.start * np : nullptr;
-			if (out->sensor_images && with_sensors) {
-				b.img.assign(n_img, nullptr);
+	hcs_outputs o{};
+	std::vector<float *> images;
+	if (out) {
+		o = *out;
+		if (out->sensor_images && with_sensors)
+			images.assign(out->sensor_images, out->sensor_images + n_img);
+	}
+	for (Block &b : m->blocks) {
+		if (b.count == 0)
+			continue;
+		Block *bp = &b;
+		b.worker->post([=]() {
+			Block &blk      = *bp;
+			const size_t ng = (size_t)hcs_n_geoms(blk.ctx), np = (size_t)hcs_n_pairs(blk.ctx), off = (size_t)blk.start * ng;
+			hcs_outputs mine{};
+			mine.geom_wrench  = o.geom_wrench ? o.geom_wrench + off * 6 : nullptr;
+			mine.pair_results = o.pair_results ? o.pair_results + (size_t)blk.start * np : nullptr;
+			if (!images.empty()) {
+				blk.img.assign(n_img, nullptr);
 				for (size_t s = 0; s < n_img; ++s)
-					if (out->sensor_images[s])
-						b.img[s] = out->sensor_images[s] + (size_t)b.start * m->sensor_dims[s].first * m->sensor_dims[s].second;
-				mine.sensor_images = b.img.data();
+					if (images[s])
+						blk.img[s] = images[s] + (size_t)blk.start * m->sensor_dims[s].first * m->sensor_dims[s].second;
+				mine.sensor_images = blk.img.data();
 			}
 			// curved / taxel sensors are configured per block (hcs_multi_block): their outputs are not mirrored here
-		}
-		return hcs_step_async(b.ctx, xpos + o * 3, xmat + o * 9, vel + o * 6, with_sensors, &mine, &b.ticket);
-	});
-	if (rc < 0)
-		return rc;
+			return hcs_step_async(blk.ctx, xpos + off * 3, xmat + off * 9, vel + off * 6, with_sensors, &mine, &blk.ticket);
+		});
+	}
 	*ticket = m->next_ticket++;
 	return HCS_OK;
 }
