@@ -647,6 +647,10 @@ constexpr int FT_CTAS_PER_SM = HCS_FT_CTAS_PER_SM; // 5 (96-register cap): C1 bp
 constexpr int PRISM_MIN_TREE = 4096;               // trees from this size on: prism test in the leaf filter, one query per batch
 constexpr int PREP_BLOCK = 128;
 
+// (Every thread repeats its environment's pose algebra: 111 of its ~250 fp64 operations.  Doing it once per environment
+// and block - one thread per environment, results through shared memory behind a barrier - was measured and is slower:
+// C1 x 4096 broadphase 0.0456 vs 0.0444 ms, C3 0.656 vs 0.620 ms, scripts/r02_run21.sh: the kernel waits on loads, not on
+// the fp64 pipe, and the barrier adds a dependent stage.)
 template <bool QTET>
 __global__ void __launch_bounds__(PREP_BLOCK) bp_prepare_kernel(PairDesc P, StepIO io)
 {
