@@ -42,6 +42,8 @@ struct GeomHost {
 	bool custom = false; // added through hcs_add_soft_mesh / hcs_add_rigid_mesh
 	std::vector<double> env_sizes; // [n_envs][3] per-environment sizes (hcs_set_env_sizes), empty: one size for all
 	double base_size[3] = { 0, 0, 0 }; // the one size the geom had before per-environment sizes were set
+	bool uploaded = false; // the device records (g.dev, g.allocs) are those of the current mesh / sizes: hcs_finalize after a
+	                       // new geom pair or a sensor change keeps them (no mesh generation, no LBVH build)
 	std::vector<void *> allocs;
 	double E() const { return mesh.soft ? props[0] : std::numeric_limits<double>::infinity(); }
 	double dissipation() const { return mesh.soft ? props[1] : 1.0; } // ContactProperties ctor, plugin.h:197-198
@@ -1010,7 +1012,10 @@ static void finalize(hcs_ctx *c)
 	release_step_buffers(c);
 	const int n_env = c->cfg.n_envs, ng = (int)c->geoms.size(), np = (int)c->pairs.size();
 	for (GeomHost &g : c->geoms)
-		upload_geom(c, g);
+		if (!g.uploaded) {
+			upload_geom(c, g);
+			g.uploaded = true;
+		}
 	for (SensorHost &s : c->sensors) {
 		if (!c->geoms[s.geom].env_sizes.empty())
 			throw std::runtime_error("per-environment sizes: a flat-sensor geom keeps one size (its taxel grid is laid out from it)");
@@ -1515,6 +1520,7 @@ int hcs_update_geom(hcs_ctx *c, int geom, const double size[3])
 	for (int i = 0; i < 3; ++i)
 		g.size[i] = size[i];
 	g.mesh = std::move(m);
+	g.uploaded = false;
 	g.env_sizes.clear(); // one size for every environment again
 	if (c->finalized) { // element counts may change: rebuild the per-pair buffers as well
 		CK(cudaStreamSynchronize(c->stream));
@@ -1555,7 +1561,8 @@ int hcs_set_env_sizes(hcs_ctx *c, int geom, const double *sizes)
 			g.env_sizes.clear();
 		for (int i = 0; i < 3; ++i)
 			g.size[i] = one[i];
-		g.mesh = std::move(m);
+		g.mesh     = std::move(m);
+		g.uploaded = false;
 	}
 	if (c->finalized) {
 		CK(cudaStreamSynchronize(c->stream));

@@ -797,3 +797,44 @@ def test_gpu_sphere_generation_equals_host_generator(hcs_lib, monkeypatch):
         counts.append(len(m["elems"]))
     assert counts[0] == 8 and counts[2] == 128 and counts[-1] == 131072
     eng.close()
+
+
+@pytest.mark.gpu
+def test_refinalize_with_more_pairs_and_empty_configurations(hcs_lib):
+    """hcs_set_pairs + hcs_finalize on a running context (what the adapter does when MuJoCo reports a geom pair for the
+    first time, plugin.cpp:255-318) keeps the geoms' device records and gives the old pairs the same results; a context
+    without pairs, and a multi-device context with more blocks than environments, step to exact zeros / the same bytes."""
+    from mujoco_contact_surfaces_b200 import MultiDeviceEngine, REP_POLYGON
+    scene = scenes.objects_on_plane()
+    n_envs = 5
+    xp, xm, ve = scene.poses(n_envs, seed=41)
+    full = make_engine(scene, n_envs)
+    full.step(xp, xm, ve)
+    ref = full.pair_results().copy()
+    eng = make_engine(scenes.objects_on_plane(), n_envs)
+    eng.set_pairs([])                      # no pairs at all: a legal configuration
+    eng.finalize()
+    eng.step(xp, xm, ve)
+    assert not eng.geom_wrenches().any() and eng.pair_results().shape == (n_envs, 0)
+    eng.set_pairs(scene.pairs[:2])         # pairs appear one after the other
+    eng.finalize()
+    eng.step(xp, xm, ve)
+    first = eng.pair_results().copy()
+    eng.set_pairs(scene.pairs)
+    eng.finalize()
+    eng.step(xp, xm, ve)
+    got = eng.pair_results()
+    for f in ("F", "tau", "centroid", "area", "n_polygons", "n_faces", "n_points"):
+        assert got[f].tobytes() == ref[f].tobytes(), f
+        assert first[f].tobytes() == ref[f][:, :2].tobytes(), f
+    assert eng.geom_wrenches().tobytes() == full.geom_wrenches().tobytes()
+    eng.close()
+    # three blocks for two environments: one block stays empty
+    multi = MultiDeviceEngine(2, [0, 0, 0], representation=REP_POLYGON, apply_contact_forces=scene.apply_forces)
+    scenes.configure(multi, scene)
+    multi.finalize()
+    assert [c for _, c in multi.blocks()] == [1, 1, 0]
+    multi.step(xp[:2], xm[:2], ve[:2])
+    assert multi.geom_wrenches().tobytes() == full.geom_wrenches()[:2].tobytes()
+    multi.close()
+    full.close()
