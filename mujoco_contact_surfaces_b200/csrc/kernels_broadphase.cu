@@ -805,7 +805,12 @@ __global__ void __launch_bounds__(BP_BLOCK, FT_CTAS_PER_SM) bp_traverse_kernel(P
 	const int total_warps = (int)gridDim.x * BP_WARPS;
 	const int K           = (!SWEEP && P.A.split_nodes && P.A.env_stride == 0) ? P.A.n_split : 1;
 	const long n_items    = (long)n_alive * K;
-	int slots             = P.n_tree >= PRISM_MIN_TREE ? 1 : (n_alive < 8 * total_warps ? 8 : 16);
+	// (small batches, down to the reference's single mjData: fewer queries per batch, one per warp when the grid has a warp
+	// for every alive query: the walk of one query is ~9 dependent iterations instead of ~27 for a batch of 14;
+	// traversal of config 1 with ONE environment 12.7 -> see profiles/r02_notes.md)
+	int slots = P.n_tree >= PRISM_MIN_TREE ? 1 : 16;
+	while (slots > 1 && n_alive < (slots / 2) * total_warps) // 16 from 8 alive queries per warp of the grid on, ... 1 below one
+		slots >>= 1;
 	if (K > 1) { // C5 x 1024 broadphase stage 10.8 / 9.5 / 8.7 / 9.1 ms for 4 / 8 / 16 / 32 items per batch (10.1 unsplit);
 		         // small batches (one environment: 3840 items) get smaller batches so that every resident warp has one
 		slots = 16;
@@ -999,8 +1004,8 @@ static void launch_flat_bp(const PairDesc &P, const StepIO &io, cudaStream_t s)
 	const int smem = (int)sizeof(Queues) * BP_WARPS;
 	auto kernel    = bp_traverse_kernel<QTET, SWEEP, PRISM>;
 	ensure_dynamic_smem(kernel, smem);
-	// persistent warps; never more than one warp per 8 query elements
-	const int grid = (int)std::max<long>(1, std::min<long>((total + 8 * BP_WARPS - 1) / (8 * BP_WARPS), (long)io.n_sms * FT_CTAS_PER_SM));
+	// persistent warps; never more than one warp per query element
+	const int grid = (int)std::max<long>(1, std::min<long>((total + BP_WARPS - 1) / BP_WARPS, (long)io.n_sms * FT_CTAS_PER_SM));
 	static const int fixed_slots = getenv("HCS_FT_SLOTS") ? std::max(1, std::min(32, atoi(getenv("HCS_FT_SLOTS")))) : 0;
 	launch_chained(kernel, dim3(grid), dim3(BP_BLOCK), (size_t)smem, s, P, io, fixed_slots);
 }
