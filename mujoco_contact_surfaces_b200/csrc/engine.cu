@@ -111,8 +111,10 @@ struct hcs_ctx {
 	PairDesc *d_pairs = nullptr;
 	std::vector<SensorDev> sensor_dev; // device records of all sensors, host copy + device copy
 	SensorDev *d_sensors = nullptr;
-	int32_t *d_counters = nullptr; // zeroed by ONE memset per step: flags[4], face count, tactile triangle count,
-	size_t n_counters   = 0;       // then {flat-list length, next chunk} per pair
+	int32_t *d_counters = nullptr; // flags[4], face count, tactile triangle count, then PAIR_COUNTERS ints per pair; TWO
+	size_t n_counters   = 0;       // sets of n_counters ints: a step uses one, its finalize kernel zeroes the other
+	bool set_clean[2]   = { false, false }; // the set is all zero
+	int cur_set         = 0;                // the set of the last step (what the getters read)
 	StepIO io{};
 	double *d_xpos = nullptr, *d_xmat = nullptr, *d_vel = nullptr; // staging for the host entry point (one block: xpos | xmat | vel)
 	double *h_in = nullptr;                                        // pinned copy of small inputs (CUDA-graph path of hcs_step)
@@ -1022,8 +1024,10 @@ static void finalize(hcs_ctx *c)
 		build_sensor(c, s);
 	}
 	c->n_counters = 6 + PAIR_COUNTERS * (size_t)np;
-	c->d_counters = dalloc<int32_t>(c->step_allocs, c->n_counters);
-	CK(cudaMemsetAsync(c->d_counters, 0, c->n_counters * sizeof(int32_t), c->stream));
+	c->d_counters = dalloc<int32_t>(c->step_allocs, 2 * c->n_counters);
+	CK(cudaMemsetAsync(c->d_counters, 0, 2 * c->n_counters * sizeof(int32_t), c->stream));
+	c->set_clean[0] = c->set_clean[1] = true;
+	c->cur_set                        = 0;
 	build_pairs(c);
 	StepIO io{};
 	io.n_env = n_env, io.n_geoms = ng, io.n_pairs = np;
@@ -1145,10 +1149,36 @@ static void finalize(hcs_ctx *c)
 	c->finalized = true;
 }
 
-static void step_device(hcs_ctx *c, const double *xpos, const double *xmat, const double *vel, int with_sensors,
-                        bool direct_out = false, double *wrench_dev = nullptr, int32_t *flags_mapped = nullptr)
+// Point the context's records (c->io, c->pair_desc: what the launches and the getters use) at one set of step counters
+static void select_counter_set(hcs_ctx *c, int set)
 {
+	int32_t *base   = c->d_counters + (size_t)set * c->n_counters;
+	c->io.flags      = base;
+	c->io.face_count = base + 4;
+	c->io.tri_count  = base + 5;
+	for (size_t pi = 0; pi < c->pair_desc.size(); ++pi)
+		if (c->pair_desc[pi].kind != PAIR_NONE)
+			c->pair_desc[pi].counters = base + 6 + PAIR_COUNTERS * pi;
+	c->cur_set = set;
+}
+
+// fixed_set: the step must always use the same counters (a captured CUDA graph bakes the addresses in): set 0, cleared by
+// a memset in front of the kernels, and no zeroing of the other set behind them
+static void step_device(hcs_ctx *c, const double *xpos, const double *xmat, const double *vel, int with_sensors,
+                        bool direct_out = false, double *wrench_dev = nullptr, int32_t *flags_mapped = nullptr,
+                        bool fixed_set = false)
+{
+	static const bool no_memset_ok = getenv("HCS_STEP_MEMSET") == nullptr; // HCS_STEP_MEMSET=1: a memset per step (A/B)
+	int set = -1;
+	if (!fixed_set && no_memset_ok && !c->profiling)
+		set = c->set_clean[0] ? 0 : (c->set_clean[1] ? 1 : -1);
+	const bool memset_first = set < 0;
+	if (memset_first)
+		set = 0;
+	select_counter_set(c, set);
 	StepIO io = c->io;
+	io.zero_next = memset_first ? nullptr : c->d_counters + (size_t)(1 - set) * c->n_counters;
+	io.n_zero    = (int)c->n_counters;
 	io.xpos = xpos, io.xmat = xmat, io.vel = vel;
 	// direct_out: the finalize kernel also writes wrenches and flags into the context's mapped pinned mirrors
 	io.geom_wrench_host = direct_out ? c->dh_wrench : nullptr;
@@ -1162,7 +1192,11 @@ static void step_device(hcs_ctx *c, const double *xpos, const double *xmat, cons
 	bool prof      = c->profiling;
 	if (prof)
 		CK(cudaEventRecord(c->ev[0], s));
-	CK(cudaMemsetAsync(c->d_counters, 0, c->n_counters * sizeof(int32_t), s)); // flags, pool counts, flat-list counters
+	if (memset_first) // flags, pool counts, flat-list counters
+		CK(cudaMemsetAsync(c->d_counters, 0, c->n_counters * sizeof(int32_t), s));
+	c->set_clean[set] = false;
+	if (!memset_first)
+		c->set_clean[1 - set] = true; // (by this step's finalize kernel)
 	if (prof)
 		CK(cudaEventRecord(c->ev[1], s));
 	int n_active = 0;
@@ -1849,11 +1883,13 @@ int hcs_step(hcs_ctx *c, const double *xpos, const double *xmat, const double *v
 		const bool direct = !with_sensors && c->dh_wrench && c->dh_flags;
 		auto enqueue = [&]() {
 			CK(cudaMemcpyAsync(c->d_xpos, c->h_in, n * 18 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
-			step_device(c, c->d_xpos, c->d_xmat, c->d_vel, with_sensors, direct);
+			step_device(c, c->d_xpos, c->d_xmat, c->d_vel, with_sensors, direct, nullptr, nullptr, /*fixed_set=*/true);
 			if (!direct)
 				fetch_enqueue(c, with_sensors, /*with_pairs=*/false);
 		};
 		if (c->step_graph[key]) {
+			select_counter_set(c, 0); // the graph's set
+			c->set_clean[0] = false;
 			CK(cudaGraphLaunch(c->step_graph[key], c->stream));
 			c->kernels_last_step = c->graph_kernels[key];
 			c->step_counter++;

@@ -306,6 +306,9 @@ __global__ void __launch_bounds__(FIN1_BLOCK) finalize_env_kernel(const PairDesc
 	if (io.flags_host && blockIdx.x == 0 && threadIdx.x == 0)
 		for (int k = 0; k < 4; ++k)
 			io.flags_host[k] = io.flags[k];
+	if (io.zero_next) // the other set of step counters, for the next step (hcs_internal.h StepIO::zero_next)
+		for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < io.n_zero; i += gridDim.x * blockDim.x)
+			io.zero_next[i] = 0;
 }
 
 // One work item per (environment, pair): read (and clear) the pair's exact accumulators, write hcs_pair_result; then one
@@ -394,6 +397,9 @@ __global__ void __launch_bounds__(FIN_BLOCK) finalize_kernel(const PairDesc *pai
 	if (io.flags_host && blockIdx.x == 0 && threadIdx.x == 0)
 		for (int k = 0; k < 4; ++k)
 			io.flags_host[k] = io.flags[k];
+	if (io.zero_next) // the other set of step counters, for the next step (hcs_internal.h StepIO::zero_next)
+		for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < io.n_zero; i += gridDim.x * blockDim.x)
+			io.zero_next[i] = 0;
 }
 
 // =================================================================================================
