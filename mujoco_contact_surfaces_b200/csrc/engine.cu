@@ -119,8 +119,8 @@ struct hcs_ctx {
 	double *d_xpos = nullptr, *d_xmat = nullptr, *d_vel = nullptr; // staging for the host entry point (one block: xpos | xmat | vel)
 	double *h_in = nullptr;                                        // pinned copy of small inputs (CUDA-graph path of hcs_step)
 	// hcs_step of small batches replays a captured graph (one H2D copy, the kernels, the result copies): [with_sensors]
-	cudaGraphExec_t step_graph[2] = { nullptr, nullptr };
-	int64_t graph_kernels[2]      = { 0, 0 };
+	cudaGraphExec_t step_graph[2][2] = { { nullptr, nullptr }, { nullptr, nullptr } }; // [with_sensors][counter set]
+	int64_t graph_kernels[2][2]      = { { 0, 0 }, { 0, 0 } };
 	int steps_since_finalize      = 0;
 	hcs_pair_result *h_pair = nullptr;                             // pinned mirrors
 	double *h_wrench        = nullptr;
@@ -996,9 +996,10 @@ static void release_step_buffers(hcs_ctx *c)
 		cudaFreeHost(c->h_flags), c->h_flags = nullptr;
 	if (c->h_in)
 		cudaFreeHost(c->h_in), c->h_in = nullptr;
-	for (cudaGraphExec_t &g : c->step_graph)
-		if (g)
-			cudaGraphExecDestroy(g), g = nullptr;
+	for (auto &row : c->step_graph)
+		for (cudaGraphExec_t &g : row)
+			if (g)
+				cudaGraphExecDestroy(g), g = nullptr;
 	c->steps_since_finalize = 0;
 	for (hcs_ctx::Slot &sl : c->slot)
 		if (sl.h_flags)
@@ -1162,22 +1163,27 @@ static void select_counter_set(hcs_ctx *c, int set)
 	c->cur_set = set;
 }
 
-// fixed_set: the step must always use the same counters (a captured CUDA graph bakes the addresses in): set 0, cleared by
-// a memset in front of the kernels, and no zeroing of the other set behind them
-static void step_device(hcs_ctx *c, const double *xpos, const double *xmat, const double *vel, int with_sensors,
-                        bool direct_out = false, double *wrench_dev = nullptr, int32_t *flags_mapped = nullptr,
-                        bool fixed_set = false)
+// the counter set the next step will use: a clean one, else -1 (set 0 behind a memset)
+static int next_counter_set(const hcs_ctx *c)
 {
 	static const bool no_memset_ok = getenv("HCS_STEP_MEMSET") == nullptr; // HCS_STEP_MEMSET=1: a memset per step (A/B)
-	int set = -1;
-	if (!fixed_set && no_memset_ok && !c->profiling)
-		set = c->set_clean[0] ? 0 : (c->set_clean[1] ? 1 : -1);
+	if (!no_memset_ok)
+		return -1;
+	return c->set_clean[0] ? 0 : (c->set_clean[1] ? 1 : -1);
+}
+
+// Every step zeroes the other set behind itself, so consecutive steps alternate between the sets and none needs a memset
+// (a captured CUDA graph bakes its set in: hcs_step keeps one graph per set).
+static void step_device(hcs_ctx *c, const double *xpos, const double *xmat, const double *vel, int with_sensors,
+                        bool direct_out = false, double *wrench_dev = nullptr, int32_t *flags_mapped = nullptr)
+{
+	int set = next_counter_set(c);
 	const bool memset_first = set < 0;
 	if (memset_first)
 		set = 0;
 	select_counter_set(c, set);
 	StepIO io = c->io;
-	io.zero_next = memset_first ? nullptr : c->d_counters + (size_t)(1 - set) * c->n_counters;
+	io.zero_next = c->d_counters + (size_t)(1 - set) * c->n_counters;
 	io.n_zero    = (int)c->n_counters;
 	io.xpos = xpos, io.xmat = xmat, io.vel = vel;
 	// direct_out: the finalize kernel also writes wrenches and flags into the context's mapped pinned mirrors
@@ -1194,9 +1200,8 @@ static void step_device(hcs_ctx *c, const double *xpos, const double *xmat, cons
 		CK(cudaEventRecord(c->ev[0], s));
 	if (memset_first) // flags, pool counts, flat-list counters
 		CK(cudaMemsetAsync(c->d_counters, 0, c->n_counters * sizeof(int32_t), s));
-	c->set_clean[set] = false;
-	if (!memset_first)
-		c->set_clean[1 - set] = true; // (by this step's finalize kernel)
+	c->set_clean[set]     = false;
+	c->set_clean[1 - set] = true; // (by this step's finalize kernel)
 	if (prof)
 		CK(cudaEventRecord(c->ev[1], s));
 	int n_active = 0;
@@ -1883,18 +1888,19 @@ int hcs_step(hcs_ctx *c, const double *xpos, const double *xmat, const double *v
 		const bool direct = !with_sensors && c->dh_wrench && c->dh_flags;
 		auto enqueue = [&]() {
 			CK(cudaMemcpyAsync(c->d_xpos, c->h_in, n * 18 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
-			step_device(c, c->d_xpos, c->d_xmat, c->d_vel, with_sensors, direct, nullptr, nullptr, /*fixed_set=*/true);
+			step_device(c, c->d_xpos, c->d_xmat, c->d_vel, with_sensors, direct);
 			if (!direct)
 				fetch_enqueue(c, with_sensors, /*with_pairs=*/false);
 		};
-		if (c->step_graph[key]) {
-			select_counter_set(c, 0); // the graph's set
-			c->set_clean[0] = false;
-			CK(cudaGraphLaunch(c->step_graph[key], c->stream));
-			c->kernels_last_step = c->graph_kernels[key];
+		const int set = next_counter_set(c); // the graph of this set: it bakes the counters' addresses in
+		if (set >= 0 && c->step_graph[key][set]) {
+			select_counter_set(c, set);
+			c->set_clean[set] = false, c->set_clean[1 - set] = true;
+			CK(cudaGraphLaunch(c->step_graph[key][set], c->stream));
+			c->kernels_last_step = c->graph_kernels[key][set];
 			c->step_counter++;
 			c->last_with_sensors = with_sensors != 0;
-		} else if (c->steps_since_finalize >= 1) { // (the first step runs eagerly: one-time function attributes are set there)
+		} else if (set >= 0 && c->steps_since_finalize >= 1) { // (the first step runs eagerly: one-time function attributes are set there)
 			cudaGraph_t g = nullptr;
 			CK(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeRelaxed));
 			try {
@@ -1907,15 +1913,17 @@ int hcs_step(hcs_ctx *c, const double *xpos, const double *xmat, const double *v
 				throw;
 			}
 			CK(cudaStreamEndCapture(c->stream, &g));
-			cudaError_t ie = cudaGraphInstantiate(&c->step_graph[key], g, 0);
+			cudaError_t ie = cudaGraphInstantiate(&c->step_graph[key][set], g, 0);
 			cudaGraphDestroy(g);
 			if (ie != cudaSuccess) {
 				cudaGetLastError();
-				c->step_graph[key] = nullptr;
+				c->step_graph[key][set] = nullptr;
+				c->set_clean[set]       = true; // (nothing ran: the capture only recorded the step)
+				c->set_clean[1 - set]   = false;
 				enqueue(); // no graph on this driver: plain launches
 			} else {
-				c->graph_kernels[key] = c->kernels_last_step;
-				CK(cudaGraphLaunch(c->step_graph[key], c->stream));
+				c->graph_kernels[key][set] = c->kernels_last_step;
+				CK(cudaGraphLaunch(c->step_graph[key][set], c->stream));
 			}
 		} else {
 			enqueue();
