@@ -167,10 +167,50 @@ __global__ void __launch_bounds__(256) scan_add_kernel(int32_t *out, const int32
 			out[base + k] += off;
 }
 
+// n <= SCAN_TILE (one environment with a 16 x 16 or 32 x 32 array: the reference's own case): the whole scan in one launch
+__global__ void __launch_bounds__(256) scan_single_kernel(const int32_t *in, int32_t *out, int n, int32_t *total_out)
+{
+	__shared__ int warp_sums[8];
+	const int base = threadIdx.x * 4;
+	int v[4], sum = 0;
+#pragma unroll
+	for (int k = 0; k < 4; ++k) {
+		v[k] = base + k < n ? in[base + k] : 0;
+		sum += v[k];
+	}
+	const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+	int incl = sum;
+#pragma unroll
+	for (int o = 1; o < 32; o <<= 1) {
+		int t = __shfl_up_sync(0xffffffffu, incl, o);
+		if (lane >= o)
+			incl += t;
+	}
+	if (lane == 31)
+		warp_sums[w] = incl;
+	__syncthreads();
+	int woff = 0;
+	for (int k = 0; k < w; ++k)
+		woff += warp_sums[k];
+	int excl = woff + incl - sum;
+#pragma unroll
+	for (int k = 0; k < 4; ++k) {
+		if (base + k < n)
+			out[base + k] = excl;
+		excl += v[k];
+	}
+	if (threadIdx.x == 255)
+		*total_out = woff + incl;
+}
+
 void launch_exclusive_scan_i32(const int32_t *in, int32_t *out, int32_t *tile_tmp, int n, int32_t *total, cudaStream_t s)
 {
 	if (n <= 0)
 		return;
+	if (n <= SCAN_TILE) {
+		scan_single_kernel<<<1, 256, 0, s>>>(in, out, n, total);
+		return;
+	}
 	const int n_tiles = (n + SCAN_TILE - 1) / SCAN_TILE;
 	scan_tiles_kernel<<<n_tiles, 256, 0, s>>>(in, out, tile_tmp, n);
 	scan_sums_kernel<<<1, 1024, 0, s>>>(tile_tmp, n_tiles, total);
@@ -547,10 +587,8 @@ int launch_tactile(const SensorDev *sensors, const SensorDev *d_sensors, int n_s
 	for (int k = 0; k < n_sensors; ++k) {
 		const SensorDev &sd = sensors[k];
 		int ncell = io.n_env * sd.cx * sd.cy, n_tiles = (ncell + SCAN_TILE - 1) / SCAN_TILE;
-		scan_tiles_kernel<<<n_tiles, 256, 0, s>>>(sd.bin_count, sd.bin_offset, sd.scan_tmp, ncell);
-		scan_sums_kernel<<<1, 1024, 0, s>>>(sd.scan_tmp, n_tiles, sd.bin_offset + ncell);
-		scan_add_kernel<<<n_tiles, 256, 0, s>>>(sd.bin_offset, sd.scan_tmp, ncell);
-		launches += 3;
+		launch_exclusive_scan_i32(sd.bin_count, sd.bin_offset, sd.scan_tmp, ncell, sd.bin_offset + ncell, s);
+		launches += ncell <= SCAN_TILE ? 1 : 3;
 	}
 	if (io.max_tris > 0) {
 		tactile_bin_kernel<true><<<tgrid, 256, 0, s>>>(d_sensors, n_sensors, io, d_pairs);
