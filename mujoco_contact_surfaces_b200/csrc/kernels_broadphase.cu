@@ -76,6 +76,7 @@ struct __align__(16) WarpQueues {
 	int qid[BP_SLOTS];
 	int qenv[BP_SLOTS];  // flat traversal: the slot's environment (slots of one warp belong to several)
 	int qev[BP_SLOTS];   // flat traversal: leaf hits of the slot's query (pair-evals started, per environment)
+	int hist[BP_SLOTS];  // flat traversal: candidates per slot in the stage (flush_flat's counting sort)
 	uint2 stage[NS];     // (query or slot, tet | skip << 28) waiting to be appended to the pair's flat list
 	double xab[12];      // per-unit kernel: R_AB (row-major) + p_AB of the unit, for the exact fallbacks of the leaf tests
 	double pba[4];       //                  origin of A in B (p_NMo of field_intersection.cc)
@@ -755,14 +756,72 @@ __global__ void __launch_bounds__(PREP_BLOCK) bp_prepare_kernel(PairDesc P, Step
 	}
 }
 
-// append the staged candidates (slot, tet | skip) of the current batch to the pair's flat list
+// Append the staged candidates (slot, tet | skip) of the current batch to the pair's flat list, grouped by slot.  The leaf
+// drains take leaf items of all slots as they come, so the stage alternates between the batch's environments; written out
+// in that order a 32-candidate chunk of the narrowphase holds a dozen short runs of equal environments, and every run
+// costs it 22 integer atomics (accumulate_chunk).  A counting sort by slot inside the warp (histogram with shared-memory
+// atomics, one warp scan, scatter) makes the runs as long as the slots' candidate lists.  FT_STAGE <= 4 x 32 entries.
+#ifndef HCS_FLUSH_SORTED
+#define HCS_FLUSH_SORTED 1
+#endif
+// Measured on one box (scripts/r02_run26.sh): C1 x 4096 narrowphase 0.0430 -> 0.0405 ms, broadphase 0.0443 -> 0.0458 ms
+// (value 44.4 -> 44.9 M); soft-soft batches (hundreds of candidates per slot: the runs are long anyway) and single-slot
+// batches of large trees only pay for it (C3 broadphase 0.631 -> 0.656 ms), so they keep the staged order (`sorted`).
 template <class Q>
-__device__ __forceinline__ void flush_flat(const PairDesc &P, const StepIO &io, Q &W, int lane, int &n_stage)
+__device__ __forceinline__ void flush_flat(const PairDesc &P, const StepIO &io, Q &W, int lane, int &n_stage, bool sorted)
 {
 	int base = 0;
 	if (lane == 0)
 		base = atomicAdd(P.counters, n_stage);
 	base = __shfl_sync(FULL_MASK, base, 0);
+#if HCS_FLUSH_SORTED
+	static_assert(Q::stage_cap <= 4 * 32, "flush_flat keeps four staged entries per lane");
+	if (!sorted) {
+		for (int j = lane; j < n_stage; j += 32) {
+			if (base + j < P.contrib_cap) {
+				const uint2 cd   = W.stage[j];
+				P.flat[base + j] = make_uint4((unsigned)W.qid[cd.x], cd.y, (unsigned)W.qenv[cd.x], 0u);
+			} else {
+				atomicOr(io.flags, 8);
+			}
+		}
+		__syncwarp();
+		n_stage = 0;
+		return;
+	}
+	W.hist[lane] = 0;
+	__syncwarp();
+	int rank[4];
+#pragma unroll
+	for (int k = 0; k < 4; ++k) {
+		const int j = lane + 32 * k;
+		rank[k]     = j < n_stage ? atomicAdd(&W.hist[W.stage[j].x], 1) : 0; // position inside the slot's group
+	}
+	__syncwarp();
+	const int cnt = W.hist[lane];
+	int incl      = cnt;
+#pragma unroll
+	for (int o = 1; o < 32; o <<= 1) {
+		const int t = __shfl_up_sync(FULL_MASK, incl, o);
+		if (lane >= o)
+			incl += t;
+	}
+	__syncwarp();
+	W.hist[lane] = incl - cnt; // first position of the slot's group
+	__syncwarp();
+#pragma unroll
+	for (int k = 0; k < 4; ++k) {
+		const int j = lane + 32 * k;
+		if (j < n_stage) {
+			const uint2 cd = W.stage[j];
+			const int dst  = base + W.hist[cd.x] + rank[k];
+			if (dst < P.contrib_cap)
+				P.flat[dst] = make_uint4((unsigned)W.qid[cd.x], cd.y, (unsigned)W.qenv[cd.x], 0u);
+			else
+				atomicOr(io.flags, 8);
+		}
+	}
+#else
 	for (int j = lane; j < n_stage; j += 32) {
 		if (base + j < P.contrib_cap) {
 			const uint2 cd   = W.stage[j];
@@ -771,6 +830,7 @@ __device__ __forceinline__ void flush_flat(const PairDesc &P, const StepIO &io, 
 			atomicOr(io.flags, 8);
 		}
 	}
+#endif
 	__syncwarp();
 	n_stage = 0;
 }
@@ -902,7 +962,7 @@ __global__ void __launch_bounds__(BP_BLOCK, FT_CTAS_PER_SM) bp_traverse_kernel(P
 				n_stage += __popc(mk_);
 				__syncwarp();
 				if (n_stage > STAGE_CAP - 32) // the next drain may not fit
-					flush_flat(P, io, W, lane, n_stage);
+					flush_flat(P, io, W, lane, n_stage, !QTET && slots > 1 && K == 1);
 			} else if (sw_s < sw_slots) {
 				// ---- sweep pass (small trees): slot sw_s against the boxes of tets sw_t .. sw_t + 31 ----
 				const int t = sw_t + lane;
@@ -986,7 +1046,7 @@ __global__ void __launch_bounds__(BP_BLOCK, FT_CTAS_PER_SM) bp_traverse_kernel(P
 			}
 		}
 		if (n_stage > 0)
-			flush_flat(P, io, W, lane, n_stage);
+			flush_flat(P, io, W, lane, n_stage, !QTET && slots > 1 && K == 1);
 		// pair-evals started (LBVH leaf hits), per environment
 		if (lane < n_slots && W.qev[lane] > 0)
 			atomicAdd(reinterpret_cast<unsigned long long *>(P.accum + (size_t)W.qenv[lane] * ACC_WORDS + ACC_NEVALS),
