@@ -360,11 +360,19 @@ __global__ void __launch_bounds__(BP_BLOCK, BP_CTAS_PER_SM) broadphase_kernel(Pa
 	constexpr bool sweep = SWEEP;
 	pdl_release(); // the pair's narrowphase may become resident while this grid drains (it waits for our completion)
 
+	// (a warp's first unit is its own index in the grid, later ones come from the work counter: narrow_kernel)
+	const int total_warps = (int)gridDim.x * BP_WARPS;
+	bool first            = true;
 	for (;;) {
-		int unit = 0;
-		if (lane == 0)
-			unit = atomicAdd(P.counters + 2, 1);
-		unit = __shfl_sync(FULL_MASK, unit, 0);
+		int unit = (int)blockIdx.x * BP_WARPS + (int)(threadIdx.x >> 5);
+		if (!first) {
+			if (n_units <= total_warps)
+				break;
+			if (lane == 0)
+				unit = atomicAdd(P.counters + 2, 1);
+			unit = total_warps + __shfl_sync(FULL_MASK, unit, 0);
+		}
+		first = false;
 		if (unit >= n_units)
 			break;
 		const int env = unit / P.n_slices, slice = unit - env * P.n_slices;
@@ -881,11 +889,18 @@ __global__ void __launch_bounds__(BP_BLOCK, FT_CTAS_PER_SM) bp_traverse_kernel(P
 		slots = fixed_slots;
 	const long n_batches = (n_items + slots - 1) / slots;
 
+	// (a warp's first batch is its own index in the grid, later ones come from the work counter: narrow_kernel)
+	bool first = true;
 	for (;;) {
-		int batch = 0;
-		if (lane == 0)
-			batch = atomicAdd(P.counters + 2, 1);
-		batch = __shfl_sync(FULL_MASK, batch, 0);
+		int batch = (int)blockIdx.x * BP_WARPS + (int)(threadIdx.x >> 5);
+		if (!first) {
+			if (n_batches <= (long)total_warps)
+				break;
+			if (lane == 0)
+				batch = atomicAdd(P.counters + 2, 1);
+			batch = total_warps + __shfl_sync(FULL_MASK, batch, 0);
+		}
+		first = false;
 		if ((long)batch >= n_batches)
 			break;
 		const long first  = (long)batch * slots;

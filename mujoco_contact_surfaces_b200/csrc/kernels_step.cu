@@ -155,7 +155,11 @@ __global__ void __launch_bounds__(32 * WARPS, CTAS) narrow_kernel(PairDesc P, St
 	const unsigned buf0 = smem_addr(&T.xyz[0][0][lane]), buf_stride = (unsigned)sizeof(T.xyz) / (8u / SM_UNIT);
 	const int total    = flat_total(P, io);
 	const int n_chunks = (total + 31) >> 5;
-	int chunk = next_chunk(P.counters + 1, lane);
+	// Every warp's FIRST chunk is its own index in the grid, later ones come from the work counter: at kernel start all
+	// warps of the grid (2368 on config 1) would otherwise queue up on ONE address, and a step of one environment pays
+	// two L2 round trips per warp for a counter that only ever hands out chunk 0 and "done".
+	const int total_warps = (int)gridDim.x * WARPS;
+	int chunk             = (int)blockIdx.x * WARPS + (int)(threadIdx.x >> 5);
 #pragma unroll 1
 	while (chunk < n_chunks) {
 		const int g = chunk * 32 + lane;
@@ -190,7 +194,9 @@ __global__ void __launch_bounds__(32 * WARPS, CTAS) narrow_kernel(PairDesc P, St
 #ifndef HCS_NP_NO_ACCUM // timing experiments only: results are wrong without it
 		accumulate_chunk(P, io, R, lane, have ? env : -1, acc);
 #endif
-		chunk = next_chunk(P.counters + 1, lane);
+		if (n_chunks <= total_warps)
+			break; // (every chunk was some warp's first)
+		chunk = total_warps + next_chunk(P.counters + 1, lane);
 	}
 }
 
