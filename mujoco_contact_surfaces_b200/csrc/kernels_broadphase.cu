@@ -109,28 +109,36 @@ __device__ __forceinline__ bool child_overlap(const float *q, const float *pl, f
 }
 
 // per (env, pair) context block read by the narrowphase (layout: hcs_internal.h)
+// part 0: the poses (from the caller's registers), part 1: the velocities (loaded here), part -1: both.  The flat prepare
+// kernel gives the two parts to two threads of the environment: the one thread that wrote all 48 doubles behind its 12
+// dependent velocity loads held its warp for 13 % of the kernel's stall samples (profiles/r02_ncu_c1_final.txt).
 __device__ __forceinline__ void write_pair_ctx(const PairDesc &P, const StepIO &io, int env, const Xform &X_WA, const Xform &X_WB,
-                                               const Xform &X_AB, D3 p_BAo)
+                                               const Xform &X_AB, D3 p_BAo, int part = -1)
 {
 	double *cb = P.pair_ctx + (size_t)env * PAIR_CTX_DOUBLES;
-	const double *velA = io.vel + ((size_t)env * io.n_geoms + P.gA) * 6;
-	const double *velB = io.vel + ((size_t)env * io.n_geoms + P.gB) * 6;
+	if (part != 1) {
 #pragma unroll
-	for (int i = 0; i < 9; ++i) {
-		cb[i]           = X_WA.R[i];
-		cb[CTX_RAB + i] = X_AB.R[i];
+		for (int i = 0; i < 9; ++i) {
+			cb[i]           = X_WA.R[i];
+			cb[CTX_RAB + i] = X_AB.R[i];
+		}
+		cb[CTX_XA] = X_WA.p.x, cb[CTX_XA + 1] = X_WA.p.y, cb[CTX_XA + 2] = X_WA.p.z;
+		cb[CTX_XB] = X_WB.p.x, cb[CTX_XB + 1] = X_WB.p.y, cb[CTX_XB + 2] = X_WB.p.z;
+		cb[CTX_PAB] = X_AB.p.x, cb[CTX_PAB + 1] = X_AB.p.y, cb[CTX_PAB + 2] = X_AB.p.z;
+		cb[CTX_PBA] = p_BAo.x, cb[CTX_PBA + 1] = p_BAo.y, cb[CTX_PBA + 2] = p_BAo.z;
+		// the pad of every 32-byte group too: a sector that is only partly written is completed from DRAM when it is read
+		cb[CTX_XB + 3] = cb[CTX_PBA + 3] = 0.0;
 	}
+	if (part != 0) {
+		const double *velA = io.vel + ((size_t)env * io.n_geoms + P.gA) * 6;
+		const double *velB = io.vel + ((size_t)env * io.n_geoms + P.gB) * 6;
 #pragma unroll
-	for (int i = 0; i < 3; ++i) {
-		cb[CTX_WA + i] = velA[i], cb[CTX_VA + i] = velA[3 + i];
-		cb[CTX_WB + i] = velB[i], cb[CTX_VB + i] = velB[3 + i];
+		for (int i = 0; i < 3; ++i) {
+			cb[CTX_WA + i] = velA[i], cb[CTX_VA + i] = velA[3 + i];
+			cb[CTX_WB + i] = velB[i], cb[CTX_VB + i] = velB[3 + i];
+		}
+		cb[CTX_WA + 3] = cb[CTX_VA + 3] = cb[CTX_WB + 3] = cb[CTX_VB + 3] = 0.0;
 	}
-	cb[CTX_XA] = X_WA.p.x, cb[CTX_XA + 1] = X_WA.p.y, cb[CTX_XA + 2] = X_WA.p.z;
-	cb[CTX_XB] = X_WB.p.x, cb[CTX_XB + 1] = X_WB.p.y, cb[CTX_XB + 2] = X_WB.p.z;
-	cb[CTX_PAB] = X_AB.p.x, cb[CTX_PAB + 1] = X_AB.p.y, cb[CTX_PAB + 2] = X_AB.p.z;
-	cb[CTX_PBA] = p_BAo.x, cb[CTX_PBA + 1] = p_BAo.y, cb[CTX_PBA + 2] = p_BAo.z;
-	// the pad of every 32-byte group too: a sector that is only partly written is completed from DRAM when it is read
-	cb[CTX_WA + 3] = cb[CTX_VA + 3] = cb[CTX_XB + 3] = cb[CTX_WB + 3] = cb[CTX_VB + 3] = cb[CTX_PBA + 3] = 0.0;
 }
 
 template <class Q>
@@ -581,8 +589,12 @@ __global__ void __launch_bounds__(BP_BLOCK, BP_CTAS_PER_SM) broadphase_kernel(Pa
 							for (int a = 0; a < 4; ++a)
 								pl[a] = W.qpl[a][s];
 						}
-						const float4 *nd = nodes4 + 4 * (size_t)(raw & ITEM_MASK);
-						const float4 a = nd[0], b = nd[1], c = nd[2], d = nd[3];
+						// the 64-byte node as two 256-bit loads: every lane reads another node, an LDG costs one L1 wavefront per line it
+						// touches whatever its width (records.cuh), and the node loads are most of the traversal's L1 traffic
+						const F8 *nd = reinterpret_cast<const F8 *>(nodes4 + 4 * (size_t)(raw & ITEM_MASK));
+						const F8 n0 = nd[0], n1 = nd[1];
+						const float4 a = make_float4(n0.a[0], n0.a[1], n0.a[2], n0.a[3]), b = make_float4(n0.a[4], n0.a[5], n0.a[6], n0.a[7]);
+						const float4 c = make_float4(n1.a[0], n1.a[1], n1.a[2], n1.a[3]), d = make_float4(n1.a[4], n1.a[5], n1.a[6], n1.a[7]);
 						cl = __float_as_int(d.x), cr = __float_as_int(d.y);
 						// node layout: llo[3] lhi[3] rlo[3] rhi[3]
 						if (child_overlap<!QTET>(qb, pl, a.x, a.y, a.z, a.w, b.x, b.y)) {
@@ -655,13 +667,16 @@ static_assert(ALIVE_WORDS == 32, "alive records are eight float4");
 constexpr int FT_CTAS_PER_SM = HCS_FT_CTAS_PER_SM; // 5 (96-register cap): C1 bp 0.0441 vs 0.0460 ms at 6, C5 equal, C3 +2 %
 constexpr int PRISM_MIN_TREE = 4096;               // trees from this size on: prism test in the leaf filter, one query per batch
 constexpr int PREP_BLOCK = 128;
+#ifndef HCS_PREP_CTAS // resident CTAs per SM the prepare kernel is compiled for (register cap)
+#define HCS_PREP_CTAS 5
+#endif
 
 // (Every thread repeats its environment's pose algebra: 111 of its ~250 fp64 operations.  Doing it once per environment
 // and block - one thread per environment, results through shared memory behind a barrier - was measured and is slower:
 // C1 x 4096 broadphase 0.0456 vs 0.0444 ms, C3 0.656 vs 0.620 ms, scripts/r02_run21.sh: the kernel waits on loads, not on
 // the fp64 pipe, and the barrier adds a dependent stage.)
 template <bool QTET>
-__global__ void __launch_bounds__(PREP_BLOCK) bp_prepare_kernel(PairDesc P, StepIO io)
+__global__ void __launch_bounds__(PREP_BLOCK, HCS_PREP_CTAS) bp_prepare_kernel(PairDesc P, StepIO io)
 {
 	pdl_release();
 	const long f     = (long)blockIdx.x * PREP_BLOCK + threadIdx.x;
@@ -679,7 +694,9 @@ __global__ void __launch_bounds__(PREP_BLOCK) bp_prepare_kernel(PairDesc P, Step
 		const Xform X_AB = invert_and_compose(X_WA, X_WB);
 		const D3 p_BAo   = -rotT(X_AB.R, X_AB.p); // origin of A expressed in B (p_NMo of field_intersection.cc)
 		if (q == 0)
-			write_pair_ctx(P, io, env, X_WA, X_WB, X_AB, p_BAo);
+			write_pair_ctx(P, io, env, X_WA, X_WB, X_AB, p_BAo, P.nq > 1 ? 0 : -1);
+		else if (q == 1)
+			write_pair_ctx(P, io, env, X_WA, X_WB, X_AB, p_BAo, 1);
 		const GeomBounds bA = geom_bounds(P.A, env), bB = geom_bounds(P.B, env);
 		{ // pair-level reject on bounding spheres
 			D3 ca = apply(X_WA, mk(bA.c[0], bA.c[1], bA.c[2]));
@@ -911,12 +928,14 @@ __global__ void __launch_bounds__(BP_BLOCK, FT_CTAS_PER_SM) bp_traverse_kernel(P
 			const long qi   = item / K;
 			if (K > 1)
 				start = P.A.split_nodes[(int)(item - qi * K)];
-			const float4 *src = reinterpret_cast<const float4 *>(P.alive) + (size_t)qi * (ALIVE_WORDS / 4);
+			const F8 *src = reinterpret_cast<const F8 *>(P.alive) + (size_t)qi * (ALIVE_WORDS / 8);
 			float rec[ALIVE_WORDS];
 #pragma unroll
-			for (int k = 0; k < ALIVE_WORDS / 4; ++k) {
-				const float4 t = src[k];
-				rec[4 * k] = t.x, rec[4 * k + 1] = t.y, rec[4 * k + 2] = t.z, rec[4 * k + 3] = t.w;
+			for (int k = 0; k < ALIVE_WORDS / 8; ++k) {
+				const F8 t = src[k];
+#pragma unroll
+				for (int j = 0; j < 8; ++j)
+					rec[8 * k + j] = t.a[j];
 			}
 #pragma unroll
 			for (int k = 0; k < 6; ++k)
@@ -1023,8 +1042,12 @@ __global__ void __launch_bounds__(BP_BLOCK, FT_CTAS_PER_SM) bp_traverse_kernel(P
 						for (int a = 0; a < 4; ++a)
 							pl[a] = W.qpl[a][s];
 					}
-					const float4 *nd = nodes4 + 4 * (P.A.noff(W.qenv[s]) + (size_t)(raw & ITEM_MASK));
-					const float4 a = nd[0], b = nd[1], c = nd[2], d = nd[3];
+					// the 64-byte node as two 256-bit loads: every lane reads another node, an LDG costs one L1 wavefront per line it
+					// touches whatever its width (records.cuh), and the node loads are most of the traversal's L1 traffic
+					const F8 *nd = reinterpret_cast<const F8 *>(nodes4 + 4 * (P.A.noff(W.qenv[s]) + (size_t)(raw & ITEM_MASK)));
+					const F8 n0 = nd[0], n1 = nd[1];
+					const float4 a = make_float4(n0.a[0], n0.a[1], n0.a[2], n0.a[3]), b = make_float4(n0.a[4], n0.a[5], n0.a[6], n0.a[7]);
+					const float4 c = make_float4(n1.a[0], n1.a[1], n1.a[2], n1.a[3]), d = make_float4(n1.a[4], n1.a[5], n1.a[6], n1.a[7]);
 					cl = __float_as_int(d.x), cr = __float_as_int(d.y);
 					if (child_overlap<!QTET>(qb, pl, a.x, a.y, a.z, a.w, b.x, b.y)) {
 						leafL = cl < 0;
