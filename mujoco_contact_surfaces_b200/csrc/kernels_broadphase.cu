@@ -893,7 +893,10 @@ __global__ void __launch_bounds__(BP_BLOCK, FT_CTAS_PER_SM) bp_traverse_kernel(P
 	// (small batches, down to the reference's single mjData: fewer queries per batch, one per warp when the grid has a warp
 	// for every alive query: the walk of one query is ~9 dependent iterations instead of ~27 for a batch of 14;
 	// traversal of config 1 with ONE environment 12.7 -> see profiles/r02_notes.md)
-	int slots = P.n_tree >= PRISM_MIN_TREE ? 1 : 16;
+	// (tet queries: 32 per batch, C3 x 4096 broadphase 0.586 / 0.576 / 0.566 ms for 16 / 20 / 24, scripts/r02_run37.sh; triangle
+	// queries of config 1: 0.0475 - 0.0481 ms for 8 ... 14 against 0.0440 for 16: the walk is bound by the instructions of
+	// its iterations, fewer and fuller ones win even when a third of the grid's warps get no batch)
+	int slots = P.n_tree >= PRISM_MIN_TREE ? 1 : (QTET ? 32 : 16);
 	while (slots > 1 && n_alive < (slots / 2) * total_warps) // 16 from 8 alive queries per warp of the grid on, ... 1 below one
 		slots >>= 1;
 	if (K > 1) { // C5 x 1024 broadphase stage 10.8 / 9.5 / 8.7 / 9.1 ms for 4 / 8 / 16 / 32 items per batch (10.1 unsplit);

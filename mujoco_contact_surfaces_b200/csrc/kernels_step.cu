@@ -215,7 +215,10 @@ __device__ __forceinline__ double from_limbs(long long hi, long long lo)
 // One thread per environment walks its pairs: the better variant for scenes with one or two pairs (config 1: 10.4 us of
 // stage time against 12.0 for the (env, pair)-parallel kernel below, which wins from three pairs on: config 4 24.6 -> 16.5 us,
 // config 5 27 -> 13 us).
-constexpr int FIN1_BLOCK = 128;
+#ifndef HCS_FIN1_BLOCK
+#define HCS_FIN1_BLOCK 32 // 128 CTAs for 4096 environments instead of 32: C1 x 4096 value 45.35 -> 45.77 M env-steps/s (scripts/r02_run36.sh)
+#endif
+constexpr int FIN1_BLOCK = HCS_FIN1_BLOCK;
 __global__ void __launch_bounds__(FIN1_BLOCK) finalize_env_kernel(const PairDesc *pairs, StepIO io, int use_smem)
 {
 	extern __shared__ double fin_smem[]; // [n_geoms * 6][FIN1_BLOCK] wrench accumulators (scenes with many geoms: below)
