@@ -74,6 +74,16 @@ __device__ __forceinline__ void to_limbs(double v, long long &hi, long long &lo)
 	lo             = __double2ll_rn(r * ACC_LO_SCALE);
 }
 
+// Copies of the column loop's body (with its two atomics) in accumulate_chunk: 16 (fully unrolled) for the small kernels,
+// 4 for the large ones (tet-tet, and everything that also emits tactile triangles), which are 50 - 60 KB of SASS against a
+// 32 KB instruction cache.  Measured (scripts/r02_run38.sh, narrowphase stage): C3 0.915 -> 0.895 ms, C5 x 512 7.64 -> 7.53 ms
+// with 4; C1 0.0405 -> 0.0411, C4 0.0904 -> 0.0931 ms with 4: those keep 16.
+#ifndef HCS_ACC_UNROLL_LARGE
+#define HCS_ACC_UNROLL_LARGE 4
+#endif
+#ifndef HCS_ACC_UNROLL_SMALL
+#define HCS_ACC_UNROLL_SMALL 16
+#endif
 constexpr int RED_PAIRS  = 11; // 10 components (hi, lo) + (packed counts, n_clipped)
 constexpr int RED_STRIDE = 23; // words per candidate (22 used): odd, so that candidate rows start in distinct bank pairs
 struct WarpReduce {            // [candidate][word], aliased with the (dead) polygon tile of the warp
@@ -85,6 +95,7 @@ struct WarpReduce {            // [candidate][word], aliased with the (dead) pol
 // pair c and adds every run of equal environments of its half to that environment's accumulator (two 64-bit integer
 // atomics per run).  The broadphase appends a unit's candidates together, so a chunk holds a few runs; runs that straddle
 // the halves (or chunks) simply arrive as several exact additions.
+template <int ACC_UNROLL>
 __device__ __forceinline__ void accumulate_chunk(const PairDesc &P, const StepIO &io, WarpReduce &R, int lane, int env, const Acc &acc)
 {
 	__syncwarp(); // every lane is done with its polygon buffers
@@ -112,7 +123,7 @@ __device__ __forceinline__ void accumulate_chunk(const PairDesc &P, const StepIO
 	const long long *col = R.w + (half * 16) * RED_STRIDE + 2 * (own ? c : 0);
 	long long s0 = 0, s1 = 0;
 	int cur = __shfl_sync(FULL_MASK, env, half * 16);
-#pragma unroll
+#pragma unroll ACC_UNROLL
 	for (int j = 0; j < 16; ++j) {
 		const int e = __shfl_sync(FULL_MASK, env, half * 16 + j);
 		if (e != cur) { // (uniform within a half warp)
@@ -192,7 +203,7 @@ __global__ void __launch_bounds__(32 * WARPS, CTAS) narrow_kernel(PairDesc P, St
 				                    io, lane, elemA, elemB);
 		}
 #ifndef HCS_NP_NO_ACCUM // timing experiments only: results are wrong without it
-		accumulate_chunk(P, io, R, lane, have ? env : -1, acc);
+		accumulate_chunk<(KIND == 1 || TRI) ? HCS_ACC_UNROLL_LARGE : HCS_ACC_UNROLL_SMALL>(P, io, R, lane, have ? env : -1, acc);
 #endif
 		if (n_chunks <= total_warps)
 			break; // (every chunk was some warp's first)

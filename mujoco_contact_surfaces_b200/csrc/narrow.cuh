@@ -642,6 +642,9 @@ __device__ __forceinline__ int cand_tet_plane(const PairDesc &P, const StepIO &i
 	return nv;
 }
 
+#ifndef HCS_TT_UNROLL
+#define HCS_TT_UNROLL 0
+#endif
 // ---- one (tet of A, tet of B) candidate: field_intersection.cc CalcEquilibriumPlane + IntersectTetrahedra -----------------
 template <bool TRI>
 __device__ __forceinline__ int cand_tet_tet(const PairDesc &P, const StepIO &io, const CandCtx &ctx, int t1, int t0, unsigned buf0,
@@ -708,18 +711,19 @@ __device__ __forceinline__ int cand_tet_tet(const PairDesc &P, const StepIO &io,
 #pragma unroll
 		for (int k = 0; k < 4; ++k)
 			pv[k] = apply(X_MN, g1.at(k));
+		// ONE copy of the pass, the face's vertices selected by k (HCS_TT_UNROLL=1: four copies): the kernel is 63 KB of SASS
+		// against a 32 KB instruction cache (ncu: `no_instruction` stalls 1.1 per issue on config 3)
+#if HCS_TT_UNROLL
 #pragma unroll
+#else
+#pragma unroll 1
+#endif
 		for (int k = 0; k < 4; ++k) {
 			if (ok) {
-				D3 A, B, C; // outward faces {1,2,3},{0,3,2},{0,1,3},{0,2,1}
-				if (k == 0)
-					A = pv[1], B = pv[2], C = pv[3];
-				else if (k == 1)
-					A = pv[0], B = pv[3], C = pv[2];
-				else if (k == 2)
-					A = pv[0], B = pv[1], C = pv[3];
-				else
-					A = pv[0], B = pv[2], C = pv[1];
+				// outward faces {1,2,3},{0,3,2},{0,1,3},{0,2,1}
+				const D3 A = k == 0 ? pv[1] : pv[0];
+				const D3 B = k == 0 ? pv[2] : (k == 1 ? pv[3] : (k == 2 ? pv[1] : pv[2]));
+				const D3 C = k == 0 ? pv[3] : (k == 1 ? pv[2] : (k == 2 ? pv[3] : pv[1]));
 				D3 nh = normalized(cross(B - A, C - A));
 				n     = clip_halfspace(Poly{ buf0 + cur * buf_stride }, n, nh, dot(nh, A), Poly{ buf0 + (cur ^ 1) * buf_stride });
 				cur ^= 1;
