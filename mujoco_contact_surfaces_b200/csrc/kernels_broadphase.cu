@@ -8,8 +8,10 @@
 //     filter: decided in float only when clear, otherwise by the reference's fp64 expression);
 //   * trivial rejects of pairs that clip to nothing (conservative float filter): all triangle
 //     vertices outside one tet half space; all tet vertices on one side of the triangle's / the equal-pressure plane;
-//     new in round 2, all tet vertices outside the plane through a triangle EDGE along the triangle normal;
-//   * new in round 2: a 4-bit mask of tet planes that cannot cut the triangle, which the clip then skips.
+//     round 2, trees of >= 4096 tets only (PRISM_MIN_TREE): all tet vertices outside the plane through a triangle EDGE
+//     along the triangle normal;
+//   * behind HCS_BP_SKIP_MASK (measured, off): a 4-bit mask of tet planes that cannot cut the triangle, which the clip
+//     then skips.
 //
 // One warp owns one (env, pair, query slice) unit.  Lane-per-query traversal left 3 of 32 lanes busy on the sphere-on-box
 // scene (most query triangles die at the root), so the warp shares two LIFO queues in shared memory: node items (query
@@ -935,7 +937,7 @@ __global__ void __launch_bounds__(BP_BLOCK, FT_CTAS_PER_SM) bp_traverse_kernel(P
 			float rec[ALIVE_WORDS];
 #pragma unroll
 			for (int k = 0; k < ALIVE_WORDS / 8; ++k) {
-				const F8 t = src[k];
+				const F8 t = ld8f_stream(src + k);
 #pragma unroll
 				for (int j = 0; j < 8; ++j)
 					rec[8 * k + j] = t.a[j];

@@ -180,7 +180,11 @@ __global__ void __launch_bounds__(32 * WARPS, CTAS) narrow_kernel(PairDesc P, St
 		uint4 rec  = make_uint4(0, 0, 0, 0); // (query element of B, tree element of A | skip mask, env, -)
 		const bool have = g < total;
 		if (have)
+#if HCS_STREAM_LOADS
+			rec = __ldcs(P.flat + g); // (read once: streaming)
+#else
 			rec = P.flat[g];
+#endif
 		const int env = (int)rec.z;
 		CandCtx ctx   = cand_ctx(P, io, env);
 		Acc acc       = zero_acc();

@@ -102,13 +102,14 @@ __device__ __forceinline__ unsigned smem_addr(const void *p)
 // in hcs_internal.h), written by the broadphase.  They are read on demand with 256-bit loads instead of being held
 // in registers: holding them across the clip loop cost ~80 registers per thread and capped the kernel at 3 warps
 // per scheduler (profiles/r01_notes.md).  The lanes of a warp may belong to different environments; lanes of one
-// environment read the same lines.
+// environment read the same lines.  (Plain loads: with L1::no_allocate config 5, where one environment's block serves
+// 67 000 candidates, loses 2 % of its narrowphase; configs 1 and 3 do not care: scripts/r02_run39.sh.)
 struct CandCtx {
 	const double *g;
 	double dissipation, mu, sign;
 	int apply, env, pair;
 	__device__ __forceinline__ D3 v(int i) const { return xyz(ld4(g + i)); } // groups that start a 32-byte group
-	__device__ __forceinline__ Xform xf(int r) const                        // R[9] + p[3] = three groups
+	__device__ __forceinline__ Xform xf(int r) const                               // R[9] + p[3] = three groups
 	{
 		D4 a = ld4(g + r), b = ld4(g + r + 4), c = ld4(g + r + 8);
 		Xform X;

@@ -42,6 +42,19 @@ struct __align__(32) F8 {
 	float a[8];
 };
 __device__ __forceinline__ F8 ld8f(const TetLeaf32 *t, int group) { return reinterpret_cast<const F8 *>(t)[group]; }
+// eight floats that are read once per step (alive records): no L1 allocation (dmath.cuh ld4_stream)
+__device__ __forceinline__ F8 ld8f_stream(const F8 *p)
+{
+#if HCS_STREAM_LOADS
+	F8 q;
+	asm("ld.global.L1::no_allocate.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+	    : "=f"(q.a[0]), "=f"(q.a[1]), "=f"(q.a[2]), "=f"(q.a[3]), "=f"(q.a[4]), "=f"(q.a[5]), "=f"(q.a[6]), "=f"(q.a[7])
+	    : "l"(p));
+	return q;
+#else
+	return *p;
+#endif
+}
 // TetLeafSS32: grad, e0, ghat, - | v0, v1, v2.xy | v2.z, v3, -
 __device__ __forceinline__ F8 ld8f(const TetLeafSS32 *t, int group) { return reinterpret_cast<const F8 *>(t)[group]; }
 __device__ __forceinline__ float fdot3(float ax, float ay, float az, float bx, float by, float bz)
