@@ -35,22 +35,12 @@ struct __align__(32) D4 {
 	double x, y, z, w;
 };
 __device__ __forceinline__ D4 ld4(const double *p) { return *reinterpret_cast<const D4 *>(p); }
-// The same for data that is read once per step (alive records; candidate records go through __ldcs): no L1 allocation, so that
-// the records every lane gathers again and again (tet fields, triangles, tree nodes: a few tens of KB per geom) stay in
-// the L1 that the kernels' shared memory leaves (HCS_STREAM_LOADS=0: plain loads).
+// Records that are read once per step (alive queries: records.cuh ld8f_stream; candidates: __ldcs) are loaded without L1
+// allocation, so that the records every lane gathers again and again (tet fields, triangles, tree nodes: a few tens of KB
+// per geom) stay in the L1 that the kernels' shared memory leaves (HCS_STREAM_LOADS=0: plain loads).
 #ifndef HCS_STREAM_LOADS
 #define HCS_STREAM_LOADS 1
 #endif
-__device__ __forceinline__ D4 ld4_stream(const double *p)
-{
-#if HCS_STREAM_LOADS
-	D4 q;
-	asm("ld.global.L1::no_allocate.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(q.x), "=d"(q.y), "=d"(q.z), "=d"(q.w) : "l"(p));
-	return q;
-#else
-	return ld4(p);
-#endif
-}
 __host__ __device__ __forceinline__ D3 xyz(const D4 &q) { return mk(q.x, q.y, q.z); }
 
 struct Xform { // p_A = R * p_B + p, R row-major

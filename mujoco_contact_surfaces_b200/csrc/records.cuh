@@ -42,7 +42,7 @@ struct __align__(32) F8 {
 	float a[8];
 };
 __device__ __forceinline__ F8 ld8f(const TetLeaf32 *t, int group) { return reinterpret_cast<const F8 *>(t)[group]; }
-// eight floats that are read once per step (alive records): no L1 allocation (dmath.cuh ld4_stream)
+// eight floats that are read once per step (alive records): no L1 allocation (dmath.cuh HCS_STREAM_LOADS)
 __device__ __forceinline__ F8 ld8f_stream(const F8 *p)
 {
 #if HCS_STREAM_LOADS
