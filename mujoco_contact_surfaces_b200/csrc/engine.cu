@@ -1174,6 +1174,18 @@ static int next_counter_set(const hcs_ctx *c)
 
 // Every step zeroes the other set behind itself, so consecutive steps alternate between the sets and none needs a memset
 // (a captured CUDA graph bakes its set in: hcs_step keeps one graph per set).
+static void dbg_launch(const char *what, int pair)
+{
+	static const bool on = getenv("HCS_DEBUG_LAUNCH") != nullptr;
+	if (!on)
+		return;
+	const cudaError_t e = cudaPeekAtLastError();
+	int dev = -1;
+	cudaGetDevice(&dev);
+	if (e != cudaSuccess)
+		fprintf(stderr, "hcs: %s (pair %d, current device %d): %s\n", what, pair, dev, cudaGetErrorString(e));
+}
+
 static void step_device(hcs_ctx *c, const double *xpos, const double *xmat, const double *vel, int with_sensors,
                         bool direct_out = false, double *wrench_dev = nullptr, int32_t *flags_mapped = nullptr)
 {
@@ -1196,6 +1208,11 @@ static void step_device(hcs_ctx *c, const double *xpos, const double *xmat, cons
 	cudaStream_t s = c->stream;
 	int64_t k      = 0;
 	bool prof      = c->profiling;
+	{ // an error some earlier, unchecked runtime call of this host thread left behind must not be blamed on this step's launches
+		const cudaError_t stale = cudaGetLastError();
+		if (stale != cudaSuccess && getenv("HCS_DEBUG_LAUNCH"))
+			fprintf(stderr, "hcs: stale CUDA error before the step: %s\n", cudaGetErrorString(stale));
+	}
 	if (prof)
 		CK(cudaEventRecord(c->ev[0], s));
 	if (memset_first) // flags, pool counts, flat-list counters
@@ -1222,7 +1239,9 @@ static void step_device(hcs_ctx *c, const double *xpos, const double *xmat, cons
 				if (j < hcs_ctx::N_AUX)
 					CK(cudaStreamWaitEvent(st, c->ev_fork, 0));
 				launch_broadphase(P, io, st);
+				dbg_launch("forked broadphase", P.index);
 				launch_narrowphase(P, io, st, /*chained=*/true);
+				dbg_launch("forked narrowphase", P.index);
 				k += 2;
 				++j;
 			}
@@ -1246,7 +1265,9 @@ static void step_device(hcs_ctx *c, const double *xpos, const double *xmat, cons
 		if (prof)
 			CK(cudaEventRecord(c->ev[3], s));
 	}
+	dbg_launch("before finalize", -1);
 	k += launch_finalize(c->d_pairs, io, s, /*chained=*/!prof && !forked);
+	dbg_launch("finalize", -1);
 	if (prof)
 		CK(cudaEventRecord(c->ev[4], s));
 	if (with_sensors) {

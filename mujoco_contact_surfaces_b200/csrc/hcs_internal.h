@@ -5,6 +5,11 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#ifdef __CUDACC__
+#include <map>
+#include <mutex>
+#include <utility>
+#endif
 
 #include "../../include/hcs.h"
 
@@ -280,19 +285,26 @@ __device__ __forceinline__ GeomBounds geom_bounds(const GeomDev &g, int env)
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_release() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
-// Opt a kernel in to its dynamic shared memory size once per device (contexts may live on several devices; the call
-// costs a microsecond or two of host time, which the end-to-end path of small steps notices).
+// Opt a kernel in to more than the default 48 KB of dynamic shared memory, once per (kernel, device) and size (contexts may
+// live on several devices and are stepped from several host threads; the call costs a microsecond or two of host time,
+// which the end-to-end path of small steps notices).  Sizes up to 48 KB need no opt-in and MUST NOT get one: the attribute
+// is a limit, so setting it to a small launch's size makes a later, larger launch of the same kernel fail with "invalid
+// argument".  (Until the third session of round 2 the bookkeeping was one array per function-pointer TYPE: kernels of equal
+// signature shared it, e.g. the two finalize kernels, and a scene with three pairs followed by one with four could hit
+// exactly that: found by the multi-device test on a 2-GPU box.)
 template <class K>
 static inline void ensure_dynamic_smem(K kernel, int bytes)
 {
-	static int done[64] = { 0 };
+	if (bytes <= 48 * 1024)
+		return;
+	static std::mutex mu;
+	static std::map<std::pair<const void *, int>, int> done;
 	int dev = 0;
 	cudaGetDevice(&dev);
-	if (dev < 0 || dev >= 64 || done[dev] < bytes) {
-		cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-		if (dev >= 0 && dev < 64)
-			done[dev] = bytes;
-	}
+	std::lock_guard<std::mutex> lock(mu);
+	int &have = done[std::make_pair(reinterpret_cast<const void *>(kernel), dev)];
+	if (have < bytes && cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) == cudaSuccess)
+		have = bytes;
 }
 
 template <class... KArgs, class... Args>

@@ -1,6 +1,8 @@
 """GPU parity tests proper: the CUDA path (through the C ABI) against the CPU oracle on identical
 seeded inputs.  Bars (BASELINE.json north star): emitted candidate set + polygon vertex counts bit-exact,
 per-pair force/torque within 1e-8 relative (fp64 geometry mode), taxel images within 1e-6 relative."""
+import os
+
 import numpy as np
 import pytest
 
@@ -838,3 +840,35 @@ def test_refinalize_with_more_pairs_and_empty_configurations(hcs_lib):
     assert multi.geom_wrenches().tobytes() == full.geom_wrenches()[:2].tobytes()
     multi.close()
     full.close()
+
+
+@pytest.mark.gpu
+def test_kernel_shared_memory_opt_in_survives_a_change_of_scene(hcs_lib):
+    """Regression (found by the multi-device test on a 2-GPU box): the dynamic shared memory attribute of a kernel is a LIMIT.
+    The launcher used to set it to every launch's size, with one bookkeeping array per function-pointer type, which the two
+    finalize kernels share: a scene with three pairs (limit of finalize_kernel := 3024 B), one with two geoms (the shared
+    entry := 3072 B, set for finalize_env_kernel) and then one with four pairs (3072 B: "already set") made that last launch
+    fail with "invalid argument".  Runs in a fresh interpreter, because the order of the first launches is the point."""
+    import subprocess
+    import sys
+    code = r'''
+import sys
+sys.path.insert(0, "tests")
+import os
+
+import numpy as np
+from mujoco_contact_surfaces_b200 import scenes
+from parity_utils import make_engine
+for factory, n in ((scenes.myrmex_multi, 3), (scenes.sphere_on_box, 5), (scenes.objects_on_plane, 16)):
+    sc = factory()
+    xp, xm, ve = [np.ascontiguousarray(a) for a in sc.poses(n, seed=3)]
+    e = make_engine(sc, n)
+    for _ in range(3):
+        e.step(xp, xm, ve, with_sensors=bool(sc.sensors))
+    assert np.isfinite(e.geom_wrenches()).all()
+    e.close()
+print("ok")
+'''
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600,
+                       cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    assert r.returncode == 0 and r.stdout.strip().endswith("ok"), r.stdout[-2000:] + r.stderr[-2000:]
