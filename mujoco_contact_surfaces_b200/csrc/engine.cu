@@ -1172,8 +1172,7 @@ static int next_counter_set(const hcs_ctx *c)
 	return c->set_clean[0] ? 0 : (c->set_clean[1] ? 1 : -1);
 }
 
-// Every step zeroes the other set behind itself, so consecutive steps alternate between the sets and none needs a memset
-// (a captured CUDA graph bakes its set in: hcs_step keeps one graph per set).
+// HCS_DEBUG_LAUNCH=1: name the launch of a step that the runtime refused (launches are not checked one by one otherwise)
 static void dbg_launch(const char *what, int pair)
 {
 	static const bool on = getenv("HCS_DEBUG_LAUNCH") != nullptr;
@@ -1186,6 +1185,8 @@ static void dbg_launch(const char *what, int pair)
 		fprintf(stderr, "hcs: %s (pair %d, current device %d): %s\n", what, pair, dev, cudaGetErrorString(e));
 }
 
+// Every step zeroes the other set behind itself, so consecutive steps alternate between the sets and none needs a memset
+// (a captured CUDA graph bakes its set in: hcs_step keeps one graph per set).
 static void step_device(hcs_ctx *c, const double *xpos, const double *xmat, const double *vel, int with_sensors,
                         bool direct_out = false, double *wrench_dev = nullptr, int32_t *flags_mapped = nullptr)
 {
@@ -1253,6 +1254,7 @@ static void step_device(hcs_ctx *c, const double *xpos, const double *xmat, cons
 		for (const PairDesc &P : c->pair_desc)
 			if (P.kind != PAIR_NONE) {
 				launch_broadphase(P, io, s);
+				dbg_launch("broadphase", P.index);
 				++k;
 			}
 		if (prof)
@@ -1260,6 +1262,7 @@ static void step_device(hcs_ctx *c, const double *xpos, const double *xmat, cons
 		for (const PairDesc &P : c->pair_desc)
 			if (P.kind != PAIR_NONE) {
 				launch_narrowphase(P, io, s, /*chained=*/!prof);
+				dbg_launch("narrowphase", P.index);
 				++k;
 			}
 		if (prof)
