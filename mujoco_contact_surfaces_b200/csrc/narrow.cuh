@@ -257,7 +257,9 @@ __device__ __forceinline__ int remove_duplicates(Poly p, int n)
 		D3 q = p.get(i);
 		D3 d = last - q;
 		if (!(dot(d, d) < eps2)) {
-			p.set(m++, q);
+			if (m != i) // (nothing dropped so far: the vertex already sits in its slot; the usual case)
+				p.set(m, q);
+			++m;
 			last = q;
 		}
 	}
@@ -581,8 +583,11 @@ __device__ __forceinline__ int cand_tet_tri(const PairDesc &P, const StepIO &io,
 	D4 ge     = load_grad_e0(tf);
 	D3 grad   = xyz(ge);
 	double e0 = ge.w;
+	// vertex pressures: the kPolygon quadrature only reads vertex 0's (the centroid's follows from the gradient), the
+	// centroid fan of kTriangle and the tactile emission read them all
+	const int n_press = TRI ? n : 1;
 #pragma unroll 1
-	for (int k = 0; k < n; ++k)
+	for (int k = 0; k < n_press; ++k)
 		PressTile{ buf0 + (cur ^ 1) * buf_stride }.set(k, dot(grad, Poly{ buf0 + cur * buf_stride }.get(k)) + e0);
 	integrate_polygon<TRI, false>(Poly{ buf0 + cur * buf_stride }, n, nS, grad, PressTile{ buf0 + (cur ^ 1) * buf_stride }, kInf,
 	                              ctx, io, tet, tri, acc, cen, ec);
@@ -632,7 +637,8 @@ __device__ __forceinline__ int cand_tet_plane(const PairDesc &P, const StepIO &i
 		D3 a = tg.at(l0), b = tg.at(l1);
 		double tt = d0 / (d0 - d1);
 		D3 pc     = a + tt * (b - a);
-		e.set(nv, pick(te, l0) + tt * (pick(te, l1) - pick(te, l0)));
+		if (TRI || nv == 0) // (kPolygon reads vertex 0's pressure only: cand_tet_tri)
+			e.set(nv, pick(te, l0) + tt * (pick(te, l1) - pick(te, l0)));
 		poly.set(nv, apply(X_WS, pc));
 		++nv;
 	}
@@ -736,8 +742,9 @@ __device__ __forceinline__ int cand_tet_tet(const PairDesc &P, const StepIO &io,
 	nv = 0;
 	if (ok) {
 		nv = n;
+		const int n_press = TRI ? n : 1; // (see cand_tet_tri)
 #pragma unroll 1
-		for (int k = 0; k < n; ++k)
+		for (int k = 0; k < n_press; ++k)
 			PressTile{ buf0 + (cur ^ 1) * buf_stride }.set(k, dot(grad0, Poly{ buf0 + cur * buf_stride }.get(k)) + f0_Mo);
 		double gN = -dot(grad1_M, nhat);
 		integrate_polygon<TRI, false>(Poly{ buf0 + cur * buf_stride }, n, nhat, grad0, PressTile{ buf0 + (cur ^ 1) * buf_stride },
