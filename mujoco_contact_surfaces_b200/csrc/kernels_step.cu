@@ -1,13 +1,13 @@
 // Narrowphase + finalize kernels of the hydroelastic contact engine (sm_100a, fp64, -fmad=false).
 //
-//   K4 narrow_tet_tri_kernel   one thread per (tet, triangle) candidate that survived the broadphase
+//   K4 narrow_kernel<0>        one thread per (tet, triangle) candidate that survived the broadphase
 //                              early-outs: Sutherland-Hodgman clip against the tet's four precomputed half
 //                              spaces, duplicate removal, polygon quadrature (mujoco_contact_surfaces_plugin.
 //                              cpp:320-409) and the force law (plugin.cpp:411-483).  Restates Drake
 //                              mesh_intersection.cc.
-//   K5 narrow_tet_plane_kernel one thread per tet the half space cuts (classified by the broadphase): marching-tets
+//   K5 narrow_kernel<2>        one thread per tet the half space cuts (classified by the broadphase): marching-tets
 //                              slice (App. A.5).
-//   K6 narrow_tet_tet_kernel   one thread per (tet, tet) candidate: equal-pressure plane, slice + clip (A.6).
+//   K6 narrow_kernel<1>        one thread per (tet, tet) candidate: equal-pressure plane, slice + clip (A.6).
 //   K7 finalize_kernel         exact accumulators -> per-pair results and per-geom wrenches (replaces two mj_applyFT
 //                              per face, plugin.cpp:477-482).
 // The candidate bodies live in narrow.cuh.  All three narrowphase kernels are flat over the batch: persistent warps pull
