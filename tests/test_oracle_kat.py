@@ -595,3 +595,45 @@ def test_face_vertices_export_is_consistent_with_the_point_collisions(triangle):
         assert np.allclose(nrm / (2 * area), pcs[k, 3:6], atol=1e-9)
         total += area
     assert abs(total - s.pair_result(0)["area"]) < 1e-12
+
+
+def soft_box_stack_closed_form(E, a, b, c, d):
+    """Two soft medial-axis boxes of equal thickness 2c stacked with overlap d, the upper one wider than the lower one's
+    footprint 2a x 2b by more than d/2.  Fields: p0 = E/c min(a-|x|, b-|y|, dist to the top face), p1 = E/c (dist to the
+    upper box's bottom face) over the footprint.  The equal-pressure surface is the mid-plane in the interior and a 45-degree
+    roof within t = d/2 of the lower box's sides; its pressure over the footprint is E/c min(t, a-|x|, b-|y|), so by the
+    layer-cake formula  F_z = E/c int_0^t (2a-2s)(2b-2s) ds = E/c (4ab t - 2(a+b) t^2 + 4/3 t^3)  (n_z dA = dx dy),
+    and the surface area is the inner rectangle plus sqrt(2) times the frame."""
+    t = d / 2
+    force = E / c * (4 * a * b * t - 2 * (a + b) * t * t + 4 / 3 * t ** 3)
+    inner = (2 * a - 2 * t) * (2 * b - 2 * t)
+    return force, inner + np.sqrt(2.0) * (4 * a * b - inner)
+
+
+@pytest.mark.parametrize("d", [0.004, 0.01, 0.016])
+def test_soft_box_stack_force_and_area_closed_form(d):
+    """Soft-soft path end to end (medial-axis box meshes, BVH, equal-pressure planes incl. the oblique pieces where one field
+    is governed by a side face, both gradient culls, clip, quadrature, force law at rest): the linear fields are exact on the
+    meshes, so the closed form must be met to rounding, in any rigid placement of the pair."""
+    E, a, b, c, A, B = 5e4, 0.06, 0.04, 0.02, 0.12, 0.10
+    force, area = soft_box_stack_closed_form(E, a, b, c, d)
+    for R, p in ((np.eye(3), np.zeros(3)), (rot([1, 2, 3], 0.7), np.array([0.3, -0.2, 0.5]))):
+        s = OracleScene()
+        g0 = s.add_geom(GEOM_BOX, [a, b, c], [E, 0, 0, 0.3, 0.3])
+        g1 = s.add_geom(GEOM_BOX, [A, B, c], [E, 0, 0, 0.3, 0.3])
+        s.set_pairs([[g0, g1]])
+        offs = np.array([0.003, -0.002, 2 * c - d])
+        s.step(np.array([p, p + R @ offs]), np.stack([R.reshape(-1), R.reshape(-1)]))
+        r = s.pair_result(0)
+        assert r["has_surface"]
+        F_local = R.T @ np.asarray(r["F"])
+        assert np.isclose(abs(F_local[2]), force, rtol=1e-12)
+        assert abs(F_local[0]) < 1e-12 * force and abs(F_local[1]) < 1e-12 * force
+        assert np.isclose(r["area"], area, rtol=1e-12)
+        # the surface is symmetric about the lower box's axis: so is its area centroid.  (The torque about that axis is NOT
+        # zero to rounding: one quadrature point per polygon integrates the linear pressure exactly, its moment only to
+        # second order, and the medial-axis tetrahedralisation is not symmetric: a lever arm below 1 % of the half size here.)
+        cen_local = R.T @ (np.asarray(r["centroid"]) - p)
+        assert abs(cen_local[0]) < 1e-12 and abs(cen_local[1]) < 1e-12 and c - d < cen_local[2] < c
+        tau_about_box0 = np.asarray(r["tau"]) - np.cross(p, np.asarray(r["F"]))
+        assert np.linalg.norm(tau_about_box0) < 1e-2 * force * a
