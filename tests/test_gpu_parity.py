@@ -881,29 +881,34 @@ def test_soft_box_stack_meets_the_closed_form_on_the_gpu(hcs_lib):
     (tests/test_oracle_kat.py::soft_box_stack_closed_form).  A batch of rigid placements and overlaps, one per environment."""
     from mujoco_contact_surfaces_b200 import HydroelasticEngine, GEOM_BOX
     from test_oracle_kat import rot, soft_box_stack_closed_form
-    E, a, b, c, A, B = 5e4, 0.06, 0.04, 0.02, 0.12, 0.10
+    E, c = 5e4, 0.02
     overlaps = [0.004, 0.01, 0.016, 0.007, 0.012, 0.002]
     n = len(overlaps)
     rng = np.random.default_rng(11)
-    eng = HydroelasticEngine(n)
-    eng.add_geom(GEOM_BOX, [a, b, c], [E, 0, 0, 0.3, 0.3])
-    eng.add_geom(GEOM_BOX, [A, B, c], [E, 0, 0, 0.3, 0.3])
-    eng.set_pairs([(0, 1)])
-    eng.finalize()
-    xp, xm, ve = np.zeros((n, 2, 3)), np.zeros((n, 2, 9)), np.zeros((n, 2, 6))
-    Rs = []
-    for e, d in enumerate(overlaps):
-        R = np.eye(3) if e == 0 else rot(rng.normal(size=3), rng.uniform(0, np.pi))
-        p = rng.uniform(-0.5, 0.5, size=3)
-        xp[e, 0], xp[e, 1] = p, p + R @ np.array([0.003, -0.002, 2 * c - d])
-        xm[e, 0] = xm[e, 1] = R.reshape(-1)
-        Rs.append(R)
-    eng.step(xp, xm, ve)
-    res = eng.pair_results()
-    for e, d in enumerate(overlaps):
-        force, area = soft_box_stack_closed_form(E, a, b, c, d)
-        F_local = Rs[e].T @ res["F"][e, 0]
-        assert np.isclose(abs(F_local[2]), force, rtol=1e-11), (e, F_local, force)
-        assert abs(F_local[0]) < 1e-11 * force and abs(F_local[1]) < 1e-11 * force
-        assert np.isclose(res["area"][e, 0], area, rtol=1e-11)
-    eng.close()
+    # (lower box, upper box, footprint a x b, area known): upper wider both ways; upper narrower in x and wider in y (crossed:
+    # roof pieces of both fields and vertical pieces in the corners, test_crossed_soft_boxes_force_closed_form)
+    for lo, up, fa, fb, with_area in (((0.06, 0.04, c), (0.12, 0.10, c), 0.06, 0.04, True),
+                                      ((0.08, 0.04, c), (0.03, 0.10, c), 0.03, 0.04, False)):
+        eng = HydroelasticEngine(n)
+        eng.add_geom(GEOM_BOX, list(lo), [E, 0, 0, 0.3, 0.3])
+        eng.add_geom(GEOM_BOX, list(up), [E, 0, 0, 0.3, 0.3])
+        eng.set_pairs([(0, 1)])
+        eng.finalize()
+        xp, xm, ve = np.zeros((n, 2, 3)), np.zeros((n, 2, 9)), np.zeros((n, 2, 6))
+        Rs = []
+        for e, d in enumerate(overlaps):
+            R = np.eye(3) if e == 0 else rot(rng.normal(size=3), rng.uniform(0, np.pi))
+            p = rng.uniform(-0.5, 0.5, size=3)
+            xp[e, 0], xp[e, 1] = p, p + R @ np.array([0.003, -0.002, 2 * c - d])
+            xm[e, 0] = xm[e, 1] = R.reshape(-1)
+            Rs.append(R)
+        eng.step(xp, xm, ve)
+        res = eng.pair_results()
+        for e, d in enumerate(overlaps):
+            force, area = soft_box_stack_closed_form(E, fa, fb, c, d)
+            F_local = Rs[e].T @ res["F"][e, 0]
+            assert np.isclose(abs(F_local[2]), force, rtol=1e-11), (e, F_local, force)
+            assert abs(F_local[0]) < 1e-11 * force and abs(F_local[1]) < 1e-11 * force
+            if with_area:
+                assert np.isclose(res["area"][e, 0], area, rtol=1e-11)
+        eng.close()

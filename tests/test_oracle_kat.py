@@ -637,3 +637,23 @@ def test_soft_box_stack_force_and_area_closed_form(d):
         assert abs(cen_local[0]) < 1e-12 and abs(cen_local[1]) < 1e-12 and c - d < cen_local[2] < c
         tau_about_box0 = np.asarray(r["tau"]) - np.cross(p, np.asarray(r["F"]))
         assert np.linalg.norm(tau_about_box0) < 1e-2 * force * a
+
+
+@pytest.mark.parametrize("d", [0.004, 0.01, 0.016])
+def test_crossed_soft_boxes_force_closed_form(d):
+    """As above with the upper box NARROWER than the lower one in x and wider in y: within t = d/2 of the upper box's sides
+    ITS field is governed by a side face (roof pieces whose normal leans the other way), in the corners both are (a vertical
+    piece of the equal-pressure surface, which carries no F_z).  Over the common footprint 2a' x 2b the surface pressure is
+    E/c min(t, a'-|x|, b-|y|) again, so F_z = E/c (4a'b t - 2(a'+b) t^2 + 4/3 t^3)."""
+    E, c = 5e4, 0.02
+    lo, up = (0.08, 0.04, c), (0.03, 0.10, c)
+    force, _ = soft_box_stack_closed_form(E, up[0], lo[1], c, d)
+    for R, p in ((np.eye(3), np.zeros(3)), (rot([1, 2, 3], 0.7), np.array([0.3, -0.2, 0.5]))):
+        s = OracleScene()
+        g0 = s.add_geom(GEOM_BOX, list(lo), [E, 0, 0, 0.3, 0.3])
+        g1 = s.add_geom(GEOM_BOX, list(up), [E, 0, 0, 0.3, 0.3])
+        s.set_pairs([[g0, g1]])
+        s.step(np.array([p, p + R @ np.array([0.004, -0.003, 2 * c - d])]), np.stack([R.reshape(-1), R.reshape(-1)]))
+        F_local = R.T @ np.asarray(s.pair_result(0)["F"])
+        assert np.isclose(abs(F_local[2]), force, rtol=1e-12)
+        assert abs(F_local[0]) < 1e-12 * force and abs(F_local[1]) < 1e-12 * force
