@@ -879,7 +879,7 @@ def test_soft_box_stack_meets_the_closed_form_on_the_gpu(hcs_lib):
     """The soft-soft path of the CUDA engine against an ANALYTIC answer (not only against the oracle): two medial-axis boxes
     stacked with overlap d, the upper one wider; F_z = E/c (4ab t - 2(a+b) t^2 + 4/3 t^3), t = d/2, and the surface area
     (tests/test_oracle_kat.py::soft_box_stack_closed_form).  A batch of rigid placements and overlaps, one per environment."""
-    from mujoco_contact_surfaces_b200 import HydroelasticEngine, GEOM_BOX
+    from mujoco_contact_surfaces_b200 import HydroelasticEngine, GEOM_BOX, REP_POLYGON, REP_TRIANGLE
     from test_oracle_kat import rot, soft_box_stack_closed_form
     E, c = 5e4, 0.02
     overlaps = [0.004, 0.01, 0.016, 0.007, 0.012, 0.002]
@@ -887,9 +887,10 @@ def test_soft_box_stack_meets_the_closed_form_on_the_gpu(hcs_lib):
     rng = np.random.default_rng(11)
     # (lower box, upper box, footprint a x b, area known): upper wider both ways; upper narrower in x and wider in y (crossed:
     # roof pieces of both fields and vertical pieces in the corners, test_crossed_soft_boxes_force_closed_form)
-    for lo, up, fa, fb, with_area in (((0.06, 0.04, c), (0.12, 0.10, c), 0.06, 0.04, True),
-                                      ((0.08, 0.04, c), (0.03, 0.10, c), 0.03, 0.04, False)):
-        eng = HydroelasticEngine(n)
+    for lo, up, fa, fb, with_area, rep in (((0.06, 0.04, c), (0.12, 0.10, c), 0.06, 0.04, True, REP_POLYGON),
+                                           ((0.08, 0.04, c), (0.03, 0.10, c), 0.03, 0.04, False, REP_POLYGON),
+                                           ((0.06, 0.04, c), (0.12, 0.10, c), 0.06, 0.04, True, REP_TRIANGLE)):
+        eng = HydroelasticEngine(n, representation=rep)
         eng.add_geom(GEOM_BOX, list(lo), [E, 0, 0, 0.3, 0.3])
         eng.add_geom(GEOM_BOX, list(up), [E, 0, 0, 0.3, 0.3])
         eng.set_pairs([(0, 1)])

@@ -610,15 +610,16 @@ def soft_box_stack_closed_form(E, a, b, c, d):
     return force, inner + np.sqrt(2.0) * (4 * a * b - inner)
 
 
+@pytest.mark.parametrize("triangle", [False, True])
 @pytest.mark.parametrize("d", [0.004, 0.01, 0.016])
-def test_soft_box_stack_force_and_area_closed_form(d):
+def test_soft_box_stack_force_and_area_closed_form(d, triangle):
     """Soft-soft path end to end (medial-axis box meshes, BVH, equal-pressure planes incl. the oblique pieces where one field
     is governed by a side face, both gradient culls, clip, quadrature, force law at rest): the linear fields are exact on the
     meshes, so the closed form must be met to rounding, in any rigid placement of the pair."""
     E, a, b, c, A, B = 5e4, 0.06, 0.04, 0.02, 0.12, 0.10
     force, area = soft_box_stack_closed_form(E, a, b, c, d)
     for R, p in ((np.eye(3), np.zeros(3)), (rot([1, 2, 3], 0.7), np.array([0.3, -0.2, 0.5]))):
-        s = OracleScene()
+        s = OracleScene(triangle_representation=triangle)  # kTriangle: centroid fans, pressure (ea + eb + ec) / 3: exact too
         g0 = s.add_geom(GEOM_BOX, [a, b, c], [E, 0, 0, 0.3, 0.3])
         g1 = s.add_geom(GEOM_BOX, [A, B, c], [E, 0, 0, 0.3, 0.3])
         s.set_pairs([[g0, g1]])
