@@ -913,3 +913,30 @@ def test_soft_box_stack_meets_the_closed_form_on_the_gpu(hcs_lib):
             if with_area:
                 assert np.isclose(res["area"][e, 0], area, rtol=1e-11)
         eng.close()
+
+
+@pytest.mark.gpu
+def test_faces_without_pressure_gradient_along_their_normal_carry_no_force_on_the_gpu(hcs_lib):
+    """plugin.cpp:366-373 on the half-space path of the CUDA engine, against the analytic answer
+    (tests/test_oracle_kat.py::test_faces_without_pressure_gradient_along_their_normal_carry_no_force): axis-aligned soft box
+    pressed into a rigid plane, F = E d / h (2a - 2d)(2b - 2d), surface area 4ab."""
+    from mujoco_contact_surfaces_b200 import HydroelasticEngine, GEOM_BOX, GEOM_PLANE
+    E, a, b, c = 5e4, 0.06, 0.04, 0.03
+    depths = [0.003, 0.008, 0.015]
+    n = len(depths)
+    eng = HydroelasticEngine(n)
+    eng.add_geom(GEOM_PLANE, [0, 0, 1], [0, 1, 0, 0.3, 0.3])
+    eng.add_geom(GEOM_BOX, [a, b, c], [E, 0, 0, 0.3, 0.3])
+    eng.set_pairs([(0, 1)])
+    eng.finalize()
+    xp, xm, ve = np.zeros((n, 2, 3)), np.zeros((n, 2, 9)), np.zeros((n, 2, 6))
+    xm[:, :] = np.eye(3).reshape(-1)
+    for e, d in enumerate(depths):
+        xp[e, 1] = [0.01, 0.02, c - d]
+    eng.step(xp, xm, ve)
+    res = eng.pair_results()
+    for e, d in enumerate(depths):
+        assert np.isclose(res["area"][e, 0], 4 * a * b, rtol=1e-12)
+        assert np.isclose(abs(res["F"][e, 0][2]), E * d / min(a, b, c) * (2 * a - 2 * d) * (2 * b - 2 * d), rtol=1e-11)
+        assert 0 < res["n_points"][e, 0] < res["n_faces"][e, 0]
+    eng.close()

@@ -658,3 +658,22 @@ def test_crossed_soft_boxes_force_closed_form(d):
         F_local = R.T @ np.asarray(s.pair_result(0)["F"])
         assert np.isclose(abs(F_local[2]), force, rtol=1e-12)
         assert abs(F_local[0]) < 1e-12 * force and abs(F_local[1]) < 1e-12 * force
+
+
+@pytest.mark.parametrize("d", [0.003, 0.008, 0.015])
+def test_faces_without_pressure_gradient_along_their_normal_carry_no_force(d):
+    """plugin.cpp:366-373 (reference-owned): a face with gM < 1e-14 is skipped.  A soft medial-axis box pressed d into a
+    rigid plane, axis-aligned: the cut is the rectangle 2a x 2b (the surface's area), but within d of the sides the field
+    is governed by a side face, its gradient is horizontal, gM = 0 exactly, and those faces carry no force: what is left is the
+    inner rectangle under the uniform pressure E d / h:  F = E d / h (2a - 2d)(2b - 2d)."""
+    E, a, b, c = 5e4, 0.06, 0.04, 0.03
+    s = OracleScene()
+    plane = s.add_geom(GEOM_PLANE, [0, 0, 1], [0, 1, 0, 0.3, 0.3])
+    box = s.add_geom(GEOM_BOX, [a, b, c], [E, 0, 0, 0.3, 0.3])
+    s.set_pairs([[plane, box]])
+    s.step(np.array([[0, 0, 0], [0.01, 0.02, c - d]]), np.stack([I3, I3]))
+    r = s.pair_result(0)
+    assert np.isclose(r["area"], 4 * a * b, rtol=1e-13)
+    assert np.isclose(abs(r["F"][2]), E * d / min(a, b, c) * (2 * a - 2 * d) * (2 * b - 2 * d), rtol=1e-12)
+    assert abs(r["F"][0]) < 1e-12 and abs(r["F"][1]) < 1e-12
+    assert 0 < r["n_points"] < r["n_faces"]
