@@ -662,10 +662,13 @@ def test_crossed_soft_boxes_force_closed_form(d):
 
 @pytest.mark.parametrize("d", [0.003, 0.008, 0.015])
 def test_faces_without_pressure_gradient_along_their_normal_carry_no_force(d):
-    """plugin.cpp:366-373 (reference-owned): a face with gM < 1e-14 is skipped.  A soft medial-axis box pressed d into a
-    rigid plane, axis-aligned: the cut is the rectangle 2a x 2b (the surface's area), but within d of the sides the field
-    is governed by a side face, its gradient is horizontal, gM = 0 exactly, and those faces carry no force: what is left is the
-    inner rectangle under the uniform pressure E d / h:  F = E d / h (2a - 2d)(2b - 2d)."""
+    """plugin.cpp:366-373 (reference-owned): a face with gM < 1e-14 or gN < 1e-14 is skipped.  A soft medial-axis box pressed d
+    into a rigid plane, axis-aligned: the cut is the rectangle 2a x 2b (the surface's area), but within d of the sides the field
+    is governed by a side face, its gradient is horizontal with an exactly zero z component (the box's vertex coordinates and
+    pressures make it so), the plane's normal is exactly (0, 0, 1), so the box's gradient along the normal (gN: the box is N) is
+    exactly 0 and those faces carry no force: what is left is the inner rectangle under the uniform pressure E d / h:
+    F = E d / h (2a - 2d)(2b - 2d).  (Pressed by a rigid BOX instead, the face normals carry 1e-16 of rounding, one frame
+    face gets gN ~ 1e-10 > 1e-14 and its whole pressure counts: the rule is a knife edge there, in the reference as here.)"""
     E, a, b, c = 5e4, 0.06, 0.04, 0.03
     s = OracleScene()
     plane = s.add_geom(GEOM_PLANE, [0, 0, 1], [0, 1, 0, 0.3, 0.3])
